@@ -1,0 +1,92 @@
+"""ctypes binding of the C ABI in include/grafx_b200.h (the only way the Python host code
+reaches the CUDA kernels).  There is NO CPU fallback: if the shared library is missing and
+cannot be built, or a call returns an error code, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgrafx_b200.so")
+
+_lib = None
+_lock = threading.Lock()
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_size_t = ctypes.c_size_t
+c_float = ctypes.c_float
+
+# name -> (restype, argtypes); must list every symbol declared in include/grafx_b200.h
+SIGNATURES = {
+    "gfx_version": (c_int, []),
+    "gfx_last_cuda_error": (c_int, []),
+    "gfx_error_string": (ctypes.c_char_p, [c_int]),
+    "gfx_device_sm_count": (c_int, []),
+    "gfx_biquad_cascade_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "gfx_biquad_cascade_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_int, c_ll, c_void_p, c_size_t, c_void_p]),
+    "gfx_biquad_cascade_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_int, c_ll, c_void_p, c_size_t, c_void_p]),
+}
+
+
+class GrafxB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads (building first if the sources are newer / the .so is absent) the CUDA library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build
+
+            _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise GrafxB200Error(
+                f"{LIB_PATH} is missing and could not be built; grafx_b200 has no CPU fallback")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+        return _lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        L = lib()
+        msg = L.gfx_error_string(code).decode()
+        extra = f" (cudaError {L.gfx_last_cuda_error()})" if code == -3 else ""
+        raise GrafxB200Error(f"{what}: {msg}{extra}")
+
+
+def require_cuda(*tensors: torch.Tensor):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise GrafxB200Error(
+                "grafx_b200 processes CUDA tensors only (no CPU fallback); got a tensor on "
+                f"{t.device}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)

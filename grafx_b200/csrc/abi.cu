@@ -1,0 +1,52 @@
+// Library-level entry points of the C ABI (version, errors, device info).
+#include "common.cuh"
+#include "../../include/grafx_b200.h"
+
+int g_gfx_last_cuda_error = 0;
+
+namespace gfx {
+const DeviceInfo& device_info() {
+    static DeviceInfo info[64];
+    static bool have[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!have[dev]) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+            info[dev].sm_count = prop.multiProcessorCount;
+            info[dev].max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+        } else {
+            info[dev].sm_count = 148;
+            info[dev].max_smem_optin = 227 * 1024;
+        }
+        have[dev] = true;
+    }
+    return info[dev];
+}
+}  // namespace gfx
+
+extern "C" {
+
+int gfx_version(void) { return 0 * 10000 + 1 * 100 + 0; }
+
+int gfx_last_cuda_error(void) { return g_gfx_last_cuda_error; }
+
+const char* gfx_error_string(int code) {
+    switch (code) {
+        case GFX_OK: return "ok";
+        case GFX_ERR_INVALID: return "invalid argument";
+        case GFX_ERR_WORKSPACE: return "workspace missing or too small";
+        case GFX_ERR_CUDA: return "CUDA runtime error (see gfx_last_cuda_error)";
+        case GFX_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown error";
+    }
+}
+
+int gfx_device_sm_count(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    return gfx::device_info().sm_count;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// grafx_b200 -- shared device/host helpers for the sm_100a kernels.
+// Everything here is header-only and private to csrc/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/grafx_b200.h"  // error codes + the exported prototypes
+
+extern int g_gfx_last_cuda_error;
+
+#define GFX_CUDA_CHECK(expr)                                   \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) {                               \
+            g_gfx_last_cuda_error = (int)_e;                   \
+            return GFX_ERR_CUDA;                               \
+        }                                                      \
+    } while (0)
+
+namespace gfx {
+
+// ---------------------------------------------------------------- device info (cached)
+struct DeviceInfo {
+    int sm_count;
+    int max_smem_optin;
+};
+const DeviceInfo& device_info();
+
+// ---------------------------------------------------------------- cp.async (LDGSTS) helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+// 16-byte async copy global->shared with zero fill of the bytes past src_bytes (0..16).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// streaming (evict-first) 128-bit global access for data touched exactly once
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w));
+}
+
+// ---------------------------------------------------------------- ordered-chain primitives
+// Tiles of one row form a dependency chain (tile t needs the filter state left by tile t-1).
+// Work items are handed out by an atomic ticket in tile-major order, so the item a CTA waits
+// on always has a smaller ticket and is owned by a CTA that is already running: no deadlock,
+// no co-residency requirement, perfect load balance for any rows x tiles.
+__device__ __forceinline__ unsigned int take_ticket(unsigned int* ctr, unsigned int wrap_at) {
+    // wraps back to 0 after exactly (n_items + gridDim.x) increments => self-resetting
+    return atomicInc(ctr, wrap_at);
+}
+__device__ __forceinline__ void chain_wait(const int* flag, int needed) {
+    volatile const int* vf = flag;
+    while (*vf < needed) { __nanosleep(32); }
+    __threadfence();
+}
+__device__ __forceinline__ void chain_publish(int* flag, int value) {
+    __threadfence();
+    atomicExch(flag, value);
+}
+
+// ---------------------------------------------------------------- 128-byte-row XOR swizzle
+// A tile is stored in shared memory as rows of 128 bytes (one row per thread = that thread's
+// contiguous chunk of samples).  16-byte unit c of row r lives at unit (c ^ (r & 7)): the
+// coalesced tile load/store (consecutive threads -> consecutive units) and the per-thread
+// chunk access (thread r reads units 0..7 of row r) are both bank-conflict free.
+__device__ __forceinline__ int swz_unit(int row, int unit) { return (row << 3) | (unit ^ (row & 7)); }
+
+}  // namespace gfx

@@ -1,0 +1,66 @@
+/* grafx_b200 -- C ABI of the B200 (sm_100a) batched audio-DSP hot path.
+ *
+ * The reference (sh-lee97/grafx @ 474e5dc) has no FFI of its own: its operator interface is the
+ * Python processor protocol `nn.Module.forward(input_signals[N,C,L], **parameter_tensors)`
+ * (sphinx-doc/source/introduction/processors.rst:170-192, call site render/graph.py:143-145).
+ * Each entry point below replaces the O(samples) inner loop of one reference function; the
+ * comment on each cites the reference file:line it stands in for.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous memory unless the name ends in `_host`;
+ *   - all functions are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream), never allocate, never synchronise, never throw;
+ *   - scratch memory is supplied by the caller: ask `*_workspace_bytes` first;
+ *   - return value: GFX_OK (0) or a negative error code; after GFX_ERR_CUDA the failing
+ *     cudaError_t is available from gfx_last_cuda_error();
+ *   - input and output buffers must not overlap.
+ */
+#ifndef GRAFX_B200_H
+#define GRAFX_B200_H
+
+#include <stddef.h>
+
+#if defined(__GNUC__)
+#define GFX_API __attribute__((visibility("default")))
+#else
+#define GFX_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFX_OK 0
+#define GFX_ERR_INVALID (-1)
+#define GFX_ERR_WORKSPACE (-2)
+#define GFX_ERR_CUDA (-3)
+#define GFX_ERR_UNSUPPORTED (-4)
+
+/* ---- library ---------------------------------------------------------------------------- */
+GFX_API int gfx_version(void);              /* major*10000 + minor*100 + patch */
+GFX_API int gfx_last_cuda_error(void);      /* cudaError_t of the last failed runtime call, 0 if none */
+GFX_API const char* gfx_error_string(int code);
+GFX_API int gfx_device_sm_count(void);      /* SMs of the current device (148 on B200), <0 on error */
+
+/* ---- exact biquad cascade ------------------------------------------------------------------
+ * Replaces IIRFilter._process_lfilter (processors/core/iir.py:154-184: K sequential
+ * torchaudio.functional.lfilter calls) and IIRFilter._process_ssm (iir.py:186-261).
+ *   x  [batch, c_sig, L]          Bs, As [batch, c_filt, K, 3] (b0,b1,b2 / a0,a1,a2, not normalised)
+ *   y  [batch, max(c_sig,c_filt), L]
+ * Channel broadcasting follows iir.py:158-167: c_sig==c_filt, or either one is 1.
+ * Each section is normalised by its own a0; zero initial state; no clamping. */
+GFX_API size_t gfx_biquad_cascade_workspace_bytes(int batch, int c_sig, int c_filt, int K, int elem_size);
+GFX_API int gfx_biquad_cascade_f32(const float* x, float* y, const float* Bs, const float* As, int batch,
+                           int c_sig, int c_filt, int K, long long L, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* float64 variant: the reference's only known-answer test runs in double
+ * (tests/processors/test_filter.py:215-233). */
+GFX_API int gfx_biquad_cascade_f64(const double* x, double* y, const double* Bs, const double* As, int batch,
+                           int c_sig, int c_filt, int K, long long L, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAFX_B200_H */

@@ -1,0 +1,107 @@
+"""Helpers shared by the oracle (CPU) and parity (GPU) tests: fixture loading and the mapping
+from a fixture name to (a) the oracle call and (b) the grafx_b200 processor."""
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CLASS_OF_PREFIX = {
+    "peq": "ParametricEqualizer",
+    "cfg1_biquad": "BiquadFilter",
+    "biquadfilter": "BiquadFilter",
+    "statevariablefilter": "StateVariableFilter",
+    "lowpassfilter": "LowPassFilter",
+    "highpassfilter": "HighPassFilter",
+    "bandpassfilter": "BandPassFilter",
+    "bandrejectfilter": "BandRejectFilter",
+    "allpassfilter": "AllPassFilter",
+    "peakingfilter": "PeakingFilter",
+    "lowshelf": "LowShelf",
+    "highshelf": "HighShelf",
+    "firfilter": "FIRFilter",
+    "compressor": "Compressor",
+    "noisegate": "NoiseGate",
+    "reverb": "STFTMaskedNoiseReverb",
+}
+
+
+def fixture_names(prefixes=None):
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    names = [n for n in names if not n.startswith(("kat_", "render_", "convolve_"))]
+    if prefixes:
+        names = [n for n in names if n.startswith(tuple(prefixes))]
+    return names
+
+
+def class_of(name):
+    for pre in sorted(CLASS_OF_PREFIX, key=len, reverse=True):
+        if name.startswith(pre):
+            return CLASS_OF_PREFIX[pre]
+    raise KeyError(name)
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode()) if "meta" in z.files else {}
+    x = torch.from_numpy(z["x"])
+    y = torch.from_numpy(z["y"])
+    params = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p_")}
+    extra = {k[2:]: z[k] for k in z.files if k.startswith("e_")}
+    return x, params, meta, y, extra
+
+
+def oracle_call(name, x, params, kwargs, dtype=None):
+    """Runs the oracle restatement for the fixture `name`."""
+    from oracle import grafx_oracle as O
+
+    if dtype is not None:
+        x = x.to(dtype)
+        params = {k: v.to(dtype) for k, v in params.items()}
+    cls = class_of(name)
+    kw = dict(kwargs)
+    backend = kw.get("backend", "lfilter")
+    fir_len = kw.get("fsm_fir_len", 4000)
+    ta = dtype is None
+
+    def run_iir(Bs, As):
+        return O._iir(x, Bs, As, backend, fir_len, use_torchaudio=ta)
+
+    if cls == "ParametricEqualizer":
+        return O.parametric_equalizer(x, **params, processor_channel=kw["processor_channel"], backend=backend,
+                                      fsm_fir_len=fir_len, use_torchaudio=ta)
+    if cls == "BiquadFilter":
+        return O.biquad_filter(x, **params, backend=backend, fsm_fir_len=fir_len, use_torchaudio=ta)
+    if cls == "StateVariableFilter":
+        Bs, As = O.svf_coeffs(**params)
+        return run_iir(Bs.unsqueeze(1), As.unsqueeze(1))
+    if cls in ("LowPassFilter", "HighPassFilter", "BandPassFilter", "BandRejectFilter", "AllPassFilter"):
+        c, alpha, _ = O.peq_activations(params["w0"], params["q_inv"])
+        Bs, As = O.simple_filter_coeffs(cls[:-6].lower(), c, alpha)
+        return run_iir(Bs.unsqueeze(1), As.unsqueeze(1))
+    if cls in ("PeakingFilter", "LowShelf", "HighShelf"):
+        c, alpha, A = O.peq_activations(params["w0"], params["q_inv"], params["log_gain"])
+        fn = {"PeakingFilter": O.peaking_coeffs, "LowShelf": O.lowshelf_coeffs, "HighShelf": O.highshelf_coeffs}[cls]
+        Bs, As = fn(c, alpha, A)
+        return run_iir(Bs.unsqueeze(1), As.unsqueeze(1))
+    if cls == "FIRFilter":
+        return O.fir_filter(x, params["fir"], kw["processor_channel"])
+    if cls in ("Compressor", "NoiseGate"):
+        kw.pop("flashfftconv", None)
+        return O.dynamics(cls.lower(), x, **params, **kw)
+    if cls == "STFTMaskedNoiseReverb":
+        return O.stft_masked_noise_reverb(x, **params, ir_len=kw["ir_len"], processor_channel=kw["processor_channel"])
+    raise KeyError(cls)
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def max_rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
