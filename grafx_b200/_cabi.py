@@ -33,6 +33,7 @@ SIGNATURES = {
                                        c_int, c_ll, c_void_p, c_size_t, c_void_p]),
     "gfx_biquad_cascade_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_ll, c_void_p, c_size_t, c_void_p]),
+    "gfx_midside_f32": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_float, c_void_p]),
 }
 
 

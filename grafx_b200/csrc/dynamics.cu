@@ -1,0 +1,503 @@
+// Fused dynamic-range processors: Compressor / NoiseGate (and serial chains of them) in ONE pass
+// over HBM: energy -> envelope smoother -> log -> knee -> gain smoother -> gain * x.
+//
+// Replaces (reference, /root/reference/src/grafx/processors):
+//   dynamics.py:361-419,443-489  Compressor.forward + knees
+//   dynamics.py:598-651,675-721  NoiseGate.forward + knees
+//   core/envelope.py:34-60       TruncatedOnePoleIIRFilter  (16384-tap FFT convolution + relu upstream)
+//   core/envelope.py:84-101      Ballistics -> torchcomp.compressor_core (sequential attack/release)
+//   container.py:116-140         SerialChain of dynamics processors (stages fused here)
+//
+// Layout: like csrc/biquad.cu -- a row (= one batch item, all C channels) is cut into tiles of
+// NT*32 samples, staged in shared memory with the XOR swizzle; thread t owns 32 consecutive
+// samples.  Tiles of a row are chained through a few words of smoother state (common.cuh).
+//
+// One-pole smoother ("iir"): upstream convolves with h[n] = (1-a) a^n, n < N, then relu.  That
+// truncated response obeys the exact recursion
+//      T[n] = a T[n-1] + (1-a) (u[n] - a^N u[n-N]),
+// which is evaluated with a chunked scan (zero-state pass, shuffle scan with a^(32*2^j), re-run
+// from the true state).  The lagged term only matters when a^N is representable (a within
+// ~100/N of 1): then u[n-N] is re-derived from x (first stage energy) or read back from a
+// caller-provided history buffer (other smoothers).  Constants a^k are formed in double.
+// Ballistics (y = (1-c) y + c u, c = at if u < y else rt, y[-1] = 1) is not associative: one
+// thread walks the tile; parallelism comes from rows (small tiles, many resident CTAs).
+#include "common.cuh"
+
+namespace gfx {
+
+constexpr int DYN_MAX_STAGES = 4;
+
+struct SmootherDesc {
+    int kind;        // 0 none, 1 truncated one-pole, 2 ballistics
+    const float* z;  // [rows, 1] (iir) or [rows, 2] (ballistics)
+    float* hist;     // [rows, L] input history for the truncation tail (may be null)
+};
+struct StageDesc {
+    int kind;        // 0 compressor, 1 noise gate
+    int knee;        // 0 hard, 1 quadratic, 2 exponential
+    int log_domain;  // gain smoother runs on the log-gain
+    const float* log_threshold;
+    const float* log_ratio;
+    const float* log_knee;
+    SmootherDesc pre, post;
+};
+struct DynParams {
+    const float* x;
+    float* y;
+    int batch, C;
+    long long L;
+    int tiles;
+    unsigned int n_items;
+    unsigned int* ticket;
+    int* flags;
+    float* state;  // [batch][2*n_stages]
+    int n_stages;
+    int iir_len;
+    int aligned;
+    StageDesc st[DYN_MAX_STAGES];
+};
+
+__device__ __forceinline__ float softplus_torch(float v) {
+    // torch.nn.functional.softplus (beta=1, threshold=20)
+    return v > 20.f ? v : log1pf(expf(v));
+}
+
+template <int NT>
+struct DynCtx {
+    static constexpr int S = 32;
+    static constexpr int NW = NT / 32;
+    float4* xs4;     // [C][NT*8] swizzled input tile
+    float4* work4;   // [NT*8] scratch tile (ballistics)
+    float* wt;       // [2][NW]
+    float* s_state;  // [2*DYN_MAX_STAGES]
+    int tid, lane, warp;
+    int t_idx, row;
+    long long t0, remain;
+    int sync_parity;
+    bool have_state;
+};
+
+template <int NT>
+__device__ __forceinline__ void ensure_state(DynCtx<NT>& cx, const DynParams& p) {
+    if (cx.have_state) return;
+    cx.have_state = true;
+    const int ns2 = 2 * p.n_stages;
+    if (cx.warp == 0) {
+        if (cx.t_idx > 0) {
+            if (cx.lane == 0) chain_wait(p.flags + cx.row, cx.t_idx);
+            __syncwarp();
+            if (cx.lane < ns2) cx.s_state[cx.lane] = __ldcg(p.state + (size_t)cx.row * ns2 + cx.lane);
+        } else if (cx.lane < ns2) {
+            const StageDesc& sd = p.st[cx.lane >> 1];
+            const int kind = (cx.lane & 1) ? sd.post.kind : sd.pre.kind;
+            cx.s_state[cx.lane] = kind == 2 ? 1.f : 0.f;  // ballistics starts from zi = 1
+        }
+    }
+    __syncthreads();
+}
+
+// ---- truncated one-pole smoother on the register chunk u[32]; `slot` = index into the row state
+template <int NT, typename LagFn>
+__device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, float (&u)[32],
+                                           const SmootherDesc& sm, int slot, LagFn lag_input) {
+    constexpr int S = 32, NW = NT / 32;
+    const float zraw = sm.z[cx.row];
+    float alpha = 1.f / (1.f + expf(-zraw));
+    alpha = fminf(alpha, 1.f - 1e-5f);
+    const double ad = (double)alpha;
+    // truncation tail a^N (0 when it underflows fp32 or when the signal is shorter than N)
+    float aN = 0.f;
+    if ((long long)p.iir_len < p.L) {
+        const double v = exp((double)p.iir_len * log(ad));
+        aN = v < 1e-37 ? 0.f : (float)v;
+    }
+    const float oma = 1.f - alpha;
+    if (aN != 0.f) {
+        const long long chunk0 = cx.t0 + (long long)cx.tid * S;
+        if (sm.hist != nullptr) {
+            float* hr = sm.hist + (size_t)cx.row * (size_t)p.L;
+#pragma unroll
+            for (int i = 0; i < S; ++i)
+                if (chunk0 + i < p.L) hr[chunk0 + i] = u[i];
+            __threadfence();
+            // earlier tiles of the row must have finished writing their history; lagged
+            // samples of this very tile come from other threads of this CTA
+            ensure_state(cx, p);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            const long long pos = chunk0 + i - p.iir_len;
+            const float lagv = (pos >= 0 && chunk0 + i < p.L) ? lag_input(pos) : 0.f;
+            u[i] = fmaf(-aN, lagv, u[i]);
+        }
+    }
+    // zero-state pass
+    float w = 0.f;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        u[i] *= oma;
+        w = fmaf(alpha, w, u[i]);
+    }
+    // powers of alpha (double): a^32, a^(32*2^j), a^(32*lane), a^(32*32)
+    double a32 = ad;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) a32 *= a32;
+    double sq = a32, pl = 1.0;
+    float z = w;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float pv = __shfl_up_sync(0xffffffffu, z, 1 << j);
+        if (cx.lane >= (1 << j)) z = fmaf((float)sq, pv, z);
+        if ((cx.lane >> j) & 1) pl *= sq;
+        sq *= sq;
+    }
+    const float aW = (float)sq;  // a^(32*32)
+    float* wt = cx.wt + (cx.sync_parity & 1) * NW;
+    cx.sync_parity++;
+    if (cx.lane == 31) wt[cx.warp] = z;
+    ensure_state(cx, p);  // (first stateful op of the tile also syncs here)
+    __syncthreads();
+    float s = cx.s_state[slot];
+    for (int q = 0; q < cx.warp; ++q) s = fmaf(aW, s, wt[q]);
+    float ex = __shfl_up_sync(0xffffffffu, z, 1);
+    if (cx.lane == 0) ex = 0.f;
+    float y = fmaf((float)pl, s, ex);  // T[-1] of this chunk
+    // true pass + relu
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        y = fmaf(alpha, y, u[i]);
+        u[i] = fmaxf(y, 0.f);
+    }
+    if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles) p.state[(size_t)cx.row * 2 * p.n_stages + slot] = y;
+}
+
+// ---- attack/release ballistics on the register chunk (sequential over the tile)
+template <int NT>
+__device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParams& p, float (&u)[32],
+                                                  const SmootherDesc& sm, int slot) {
+    const float at = 1.f / (1.f + expf(-sm.z[(size_t)cx.row * 2 + 0]));
+    const float rt = 1.f / (1.f + expf(-sm.z[(size_t)cx.row * 2 + 1]));
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        cx.work4[swz_unit(cx.tid, c)] = make_float4(u[4 * c], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
+    ensure_state(cx, p);
+    __syncthreads();
+    if (cx.tid == 0) {
+        float y = cx.s_state[slot];
+        const float omat = 1.f - at, omrt = 1.f - rt;
+#pragma unroll 1
+        for (int r = 0; r < NT; ++r) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int idx = swz_unit(r, c);
+                float4 v = cx.work4[idx];
+                float* e = reinterpret_cast<float*>(&v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float ya = fmaf(omat, y, at * e[k]);
+                    const float yr = fmaf(omrt, y, rt * e[k]);
+                    y = e[k] < y ? ya : yr;
+                    e[k] = y;
+                }
+                cx.work4[idx] = v;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 v = cx.work4[swz_unit(cx.tid, c)];
+        u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
+    }
+    if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles) {
+        // the state after the last sample of a FULL tile (partial tiles are always the last)
+        p.state[(size_t)cx.row * 2 * p.n_stages + slot] = u[31];
+    }
+}
+
+__device__ __forceinline__ float knee_log_gain(int kind, int knee, float G, float T, float lr, float lk) {
+    // returns log-gain  G_out - G   (dynamics.py:443-489 compressor, :675-721 gate)
+    if (kind == 0) {
+        const float ratio = 1.f + expf(lr);
+        if (knee == 0) return fminf(G, T + (G - T) / ratio) - G;
+        if (knee == 1) {
+            const float W = expf(lk) * 0.5f;
+            float out;
+            if (G < T - W) out = G;
+            else if (G > T + W) out = T + (G - T) / ratio;
+            else { const float d = G - T + W; out = G + (1.f / ratio - 1.f) * (d * d) / (4.f * W); }
+            return out - G;
+        }
+        const float W = expf(lk);
+        return (1.f / ratio - 1.f) * softplus_torch(W * (G - T)) / W;
+    } else {
+        if (knee == 0) { const float ratio = 1.f + expf(lr); return fminf(G, ratio * (G - T) + T) - G; }
+        if (knee == 1) {
+            const float ratio = 1.f + expf(lr);
+            const float W = expf(lk) * 0.5f;
+            float out;
+            if (G < T - W) out = ratio * (G - T) + T;
+            else if (G > T + W) out = G;
+            else { const float d = G - T - W; out = G + (1.f - ratio) * (d * d) / (4.f * W); }
+            return out - G;
+        }
+        const float W = expf(lk);
+        return -expf(lr) * softplus_torch(W * (T - G)) / W;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) dynamics_kernel(const DynParams p) {
+    constexpr int S = 32, TILE = NT * S, NW = NT / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DynCtx<NT> cx;
+    cx.xs4 = reinterpret_cast<float4*>(smem_raw);
+    cx.work4 = cx.xs4 + (size_t)p.C * NT * 8;
+    cx.wt = reinterpret_cast<float*>(cx.work4 + (NT == 64 ? (size_t)NT * 8 : 0));
+    cx.s_state = cx.wt + 2 * NW;
+    float* xs = reinterpret_cast<float*>(cx.xs4);
+    __shared__ unsigned int sh_item;
+    cx.tid = threadIdx.x; cx.lane = cx.tid & 31; cx.warp = cx.tid >> 5;
+    const int C = p.C;
+    const float inv_c = 1.f / (float)C;
+
+    for (;;) {
+        __syncthreads();
+        if (cx.tid == 0) sh_item = take_ticket(p.ticket, p.n_items + gridDim.x - 1);
+        __syncthreads();
+        const unsigned int item = sh_item;
+        if (item >= p.n_items) break;
+        cx.t_idx = (int)(item / (unsigned)p.batch);
+        cx.row = (int)(item - (unsigned)cx.t_idx * (unsigned)p.batch);
+        cx.t0 = (long long)cx.t_idx * TILE;
+        cx.remain = p.L - cx.t0;
+        cx.sync_parity = 0;
+        cx.have_state = false;
+        const float* xrow = p.x + (size_t)cx.row * C * (size_t)p.L;
+        float* yrow = p.y + (size_t)cx.row * C * (size_t)p.L;
+
+        // ---- stage all channels of the tile
+        if (p.aligned) {
+            for (int c = 0; c < C; ++c) {
+                const float* xr = xrow + (size_t)c * p.L;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int g = cx.tid + j * NT;
+                    const long long pos = (long long)g * 4;
+                    const long long nb = (cx.remain - pos) * 4;
+                    const int src_bytes = nb >= 16 ? 16 : (nb > 0 ? (int)nb : 0);
+                    const float* src = src_bytes > 0 ? xr + cx.t0 + pos : xr;
+                    cp_async16(&cx.xs4[(size_t)c * NT * 8 + swz_unit(g >> 3, g & 7)], src, src_bytes);
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        } else {
+            for (int c = 0; c < C; ++c) {
+                const float* xr = xrow + (size_t)c * p.L;
+                for (int i = cx.tid; i < TILE; i += NT) {
+                    const float val = (i < cx.remain) ? xr[cx.t0 + i] : 0.f;
+                    xs[(size_t)c * TILE + (size_t)swz_unit(i >> 5, (i & 31) >> 2) * 4 + (i & 3)] = val;
+                }
+            }
+        }
+        __syncthreads();
+
+        float G[S];   // cumulative linear gain of the stages done so far
+        float u[S];   // working chunk
+#pragma unroll
+        for (int i = 0; i < S; ++i) G[i] = 1.f;
+
+        for (int d = 0; d < p.n_stages; ++d) {
+            const StageDesc& sd = p.st[d];
+            // energy of the signal entering this stage: mean_c (G x_c)^2
+#pragma unroll
+            for (int i = 0; i < S; ++i) u[i] = 0.f;
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 v = cx.xs4[(size_t)c * NT * 8 + swz_unit(cx.tid, q)];
+                    u[4 * q] = fmaf(v.x, v.x, u[4 * q]);
+                    u[4 * q + 1] = fmaf(v.y, v.y, u[4 * q + 1]);
+                    u[4 * q + 2] = fmaf(v.z, v.z, u[4 * q + 2]);
+                    u[4 * q + 3] = fmaf(v.w, v.w, u[4 * q + 3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < S; ++i) u[i] = u[i] * inv_c * (G[i] * G[i]);
+
+            if (sd.pre.kind == 1) {
+                if (d == 0) {
+                    // lagged energy re-derived from x itself (read-only input): no history buffer
+                    auto lag = [&](long long pos) {
+                        float e = 0.f;
+                        for (int c = 0; c < C; ++c) { const float v = xrow[(size_t)c * p.L + pos]; e = fmaf(v, v, e); }
+                        return e * inv_c;
+                    };
+                    SmootherDesc sm = sd.pre;
+                    sm.hist = nullptr;
+                    smooth_iir<NT>(cx, p, u, sm, 2 * d, lag);
+                } else {
+                    const float* hr = sd.pre.hist + (size_t)cx.row * (size_t)p.L;
+                    auto lag = [&](long long pos) { return __ldcg(hr + pos); };
+                    smooth_iir<NT>(cx, p, u, sd.pre, 2 * d, lag);
+                }
+            } else if (sd.pre.kind == 2) {
+                smooth_ballistics<NT>(cx, p, u, sd.pre, 2 * d);
+            }
+
+            const float T = sd.log_threshold[cx.row] - 6.f;
+            const float lr = sd.log_ratio[cx.row];
+            const float lk = sd.log_knee ? sd.log_knee[cx.row] : 0.f;
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                const float Gl = logf(u[i] + 1e-5f);
+                u[i] = knee_log_gain(sd.kind, sd.knee, Gl, T, lr, lk);
+            }
+            if (sd.post.kind == 0) {
+#pragma unroll
+                for (int i = 0; i < S; ++i) u[i] = expf(u[i]);
+            } else {
+                if (!sd.log_domain) {
+#pragma unroll
+                    for (int i = 0; i < S; ++i) u[i] = expf(u[i]);
+                }
+                if (sd.post.kind == 1) {
+                    const float* hr = sd.post.hist ? sd.post.hist + (size_t)cx.row * (size_t)p.L : nullptr;
+                    auto lag = [&](long long pos) { return __ldcg(hr + pos); };
+                    smooth_iir<NT>(cx, p, u, sd.post, 2 * d + 1, lag);
+                } else {
+                    smooth_ballistics<NT>(cx, p, u, sd.post, 2 * d + 1);
+                }
+                if (sd.log_domain) {
+#pragma unroll
+                    for (int i = 0; i < S; ++i) u[i] = expf(u[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < S; ++i) G[i] *= u[i];
+        }
+        if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles && cx.have_state) chain_publish(p.flags + cx.row, cx.t_idx + 1);
+
+        // ---- apply the gain in place in shared memory, then store coalesced
+        for (int c = 0; c < C; ++c) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4* pv = &cx.xs4[(size_t)c * NT * 8 + swz_unit(cx.tid, q)];
+                float4 v = *pv;
+                v.x *= G[4 * q]; v.y *= G[4 * q + 1]; v.z *= G[4 * q + 2]; v.w *= G[4 * q + 3];
+                *pv = v;
+            }
+        }
+        __syncthreads();
+        for (int c = 0; c < C; ++c) {
+            float* yr = yrow + (size_t)c * p.L;
+            if (p.aligned) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int g = cx.tid + j * NT;
+                    const long long pos = (long long)g * 4;
+                    if (pos + 4 <= cx.remain) {
+                        stg_stream(reinterpret_cast<float4*>(yr + cx.t0 + pos),
+                                   cx.xs4[(size_t)c * NT * 8 + swz_unit(g >> 3, g & 7)]);
+                    } else if (pos < cx.remain) {
+                        const float* sv = xs + (size_t)c * TILE + (size_t)swz_unit(g >> 3, g & 7) * 4;
+                        for (int e = 0; e < 4 && pos + e < cx.remain; ++e) yr[cx.t0 + pos + e] = sv[e];
+                    }
+                }
+            } else {
+                for (int i = cx.tid; i < TILE && i < cx.remain; i += NT)
+                    yr[cx.t0 + i] = xs[(size_t)c * TILE + (size_t)swz_unit(i >> 5, (i & 31) >> 2) * 4 + (i & 3)];
+            }
+        }
+    }
+}
+
+static size_t dyn_smem_bytes(int NT, int C) {
+    // the scratch tile is only used by the ballistics variant (NT == 64)
+    return (size_t)(C + (NT == 64 ? 1 : 0)) * NT * 128 + (size_t)(2 * (NT / 32) + 2 * DYN_MAX_STAGES) * sizeof(float) + 64;
+}
+
+static size_t dyn_workspace_bytes(int batch, int n_stages) {
+    size_t flags = ((size_t)batch * sizeof(int) + 255) / 256 * 256;
+    return 256 + flags + (size_t)batch * 2 * n_stages * sizeof(float);
+}
+
+template <int NT>
+static int launch_dynamics(DynParams& p, cudaStream_t stream) {
+    const size_t smem = dyn_smem_bytes(NT, p.C);
+    if (smem > (size_t)device_info().max_smem_optin) return GFX_ERR_UNSUPPORTED;
+    auto kern = dynamics_kernel<NT>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        GFX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int occ = 0;
+    GFX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) return GFX_ERR_UNSUPPORTED;
+    long long grid = (long long)device_info().sm_count * occ;
+    if (grid > (long long)p.n_items) grid = p.n_items;
+    kern<<<(unsigned)grid, NT, smem, stream>>>(p);
+    GFX_CUDA_CHECK(cudaGetLastError());
+    return GFX_OK;
+}
+
+}  // namespace gfx
+
+extern "C" {
+
+size_t gfx_dynamics_workspace_bytes(int batch, int n_stages) { return gfx::dyn_workspace_bytes(batch, n_stages); }
+
+int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long long L,
+                     const gfx_dynamics_stage* stages, int n_stages, int iir_len, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    using namespace gfx;
+    if (!x || !y || !stages) return GFX_ERR_INVALID;
+    if (batch <= 0 || channels <= 0 || L <= 0 || n_stages <= 0 || iir_len <= 0) return GFX_ERR_INVALID;
+    if (n_stages > DYN_MAX_STAGES) return GFX_ERR_UNSUPPORTED;
+    DynParams p;
+    bool any_ballistics = false;
+    for (int d = 0; d < n_stages; ++d) {
+        const gfx_dynamics_stage& s = stages[d];
+        if (s.kind < 0 || s.kind > 1 || s.knee < 0 || s.knee > 2) return GFX_ERR_INVALID;
+        if (s.energy_smoother < 0 || s.energy_smoother > 2 || s.gain_smoother < 0 || s.gain_smoother > 2) return GFX_ERR_INVALID;
+        if (!s.log_threshold || !s.log_ratio) return GFX_ERR_INVALID;
+        if (s.knee != 0 && !s.log_knee) return GFX_ERR_INVALID;
+        if (s.energy_smoother && !s.z_alpha_pre) return GFX_ERR_INVALID;
+        if (s.gain_smoother && !s.z_alpha_post) return GFX_ERR_INVALID;
+        // history buffers are needed whenever the truncation tail could matter
+        if ((long long)iir_len < L) {
+            if (s.energy_smoother == 1 && d > 0 && !s.hist_pre) return GFX_ERR_WORKSPACE;
+            if (s.gain_smoother == 1 && !s.hist_post) return GFX_ERR_WORKSPACE;
+        }
+        StageDesc& o = p.st[d];
+        o.kind = s.kind; o.knee = s.knee; o.log_domain = s.gain_smooth_in_log;
+        o.log_threshold = s.log_threshold; o.log_ratio = s.log_ratio; o.log_knee = s.log_knee;
+        o.pre = SmootherDesc{s.energy_smoother, s.z_alpha_pre, s.hist_pre};
+        o.post = SmootherDesc{s.gain_smoother, s.z_alpha_post, s.hist_post};
+        any_ballistics |= (s.energy_smoother == 2 || s.gain_smoother == 2);
+    }
+    const int NT = any_ballistics ? 64 : 256;
+    const long long tile = (long long)NT * 32;
+    const long long tiles_ll = (L + tile - 1) / tile;
+    if ((long long)batch * tiles_ll > 0x7fff0000LL) return GFX_ERR_UNSUPPORTED;
+    const size_t need = dyn_workspace_bytes(batch, n_stages);
+    if (!workspace || workspace_bytes < need) return GFX_ERR_WORKSPACE;
+    p.x = x; p.y = y; p.batch = batch; p.C = channels; p.L = L;
+    p.tiles = (int)tiles_ll;
+    p.n_items = (unsigned)((long long)batch * tiles_ll);
+    unsigned char* w = (unsigned char*)workspace;
+    const size_t flags_bytes = ((size_t)batch * sizeof(int) + 255) / 256 * 256;
+    p.ticket = (unsigned int*)w;
+    p.flags = (int*)(w + 256);
+    p.state = (float*)(w + 256 + flags_bytes);
+    p.n_stages = n_stages;
+    p.iir_len = iir_len;
+    p.aligned = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (L % 4 == 0);
+    GFX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256 + flags_bytes, (cudaStream_t)stream));
+    return any_ballistics ? launch_dynamics<64>(p, (cudaStream_t)stream) : launch_dynamics<256>(p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,16 @@
+"""Drop-in mirror of grafx.processors (processors/__init__.py:1-36) for the hot path."""
+from . import core  # noqa: F401
+from .eq import ParametricEqualizer  # noqa: F401
+from .filter import (  # noqa: F401
+    AllPassFilter,
+    BandPassFilter,
+    BandRejectFilter,
+    BiquadFilter,
+    HighPassFilter,
+    HighShelf,
+    LowPassFilter,
+    LowShelf,
+    PeakingFilter,
+    PoleZeroFilter,
+    StateVariableFilter,
+)

@@ -1,0 +1,2 @@
+from .iir import IIRFilter  # noqa: F401
+from .midside import lr_to_ms, ms_to_lr  # noqa: F401

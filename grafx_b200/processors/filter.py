@@ -1,0 +1,141 @@
+"""Filter processors -- drop-ins for grafx.processors.filter (filter.py:20-754).
+
+Same class names, constructor kwargs, `forward(input_signals, **params)` signatures and
+`parameter_size()` as the reference.  Coefficient design is O(parameters) PyTorch
+(processors/design.py); the O(samples) filtering runs in the CUDA kernels behind IIRFilter.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import functional as F_
+from . import design
+from .core.iir import IIRFilter
+
+
+class _BiquadStack(nn.Module):
+    """Shared plumbing: design -> add the broadcast channel axis -> IIRFilter."""
+
+    def __init__(self, **backend_kwargs):
+        super().__init__()
+        self.biquad = IIRFilter(order=2, **backend_kwargs)
+
+    def _run(self, input_signals, num, den):
+        return self.biquad(input_signals, num.unsqueeze(1), den.unsqueeze(1))
+
+
+class BiquadFilter(_BiquadStack):
+    """filter.py:87-168."""
+
+    def __init__(self, num_filters=1, normalized=False, **backend_kwargs):
+        super().__init__(**backend_kwargs)
+        self.num_filters = num_filters
+        self.normalized = normalized
+
+    def forward(self, input_signals, Bs, A1_pre, A2_pre, A0=None):
+        num, den = design.stable_biquad(Bs, A1_pre, A2_pre, A0, scale_by_a0=self.normalized)
+        return self._run(input_signals, num, den)
+
+    def parameter_size(self):
+        size = {"Bs": (self.num_filters, 3), "A1_pre": self.num_filters, "A2_pre": self.num_filters}
+        if self.normalized:
+            size["A0"] = self.num_filters
+        return size
+
+
+class PoleZeroFilter(_BiquadStack):
+    """filter.py:171-255.  Upstream forgets the channel axis on (Bs, As) and cannot run; the
+    documented behaviour (one filter shared by all channels, overall gain exp(log_gain)) is
+    implemented here."""
+
+    def __init__(self, num_filters=1, **backend_kwargs):
+        super().__init__(**backend_kwargs)
+        self.num_filters = num_filters
+
+    def forward(self, input_signals, log_gain, poles, zeros):
+        num, den = design.pole_zero(poles, zeros)
+        # fold the gain into the first section's numerator: no extra pass over the audio
+        gain = torch.exp(log_gain).reshape(-1, 1, 1)
+        num = torch.cat([num[:, :1] * gain, num[:, 1:]], 1)
+        return self._run(input_signals, num, den)
+
+    def parameter_size(self):
+        return {"log_gain": 1, "poles": (self.num_filters, 2), "zeros": (self.num_filters, 2)}
+
+
+class StateVariableFilter(_BiquadStack):
+    """filter.py:258-338."""
+
+    def __init__(self, num_filters=1, **backend_kwargs):
+        super().__init__(**backend_kwargs)
+        self.num_filters = num_filters
+
+    def forward(self, input_signals, twoR, G, c_hp, c_bp, c_lp):
+        return self._run(input_signals, *design.state_variable(twoR, G, c_hp, c_bp, c_lp))
+
+    def parameter_size(self):
+        return {k: self.num_filters for k in ("twoR", "G", "c_hp", "c_bp", "c_lp")}
+
+
+class BaseParametricFilter(_BiquadStack):
+    """filter.py:341-390: two parameters (cutoff, inverse Q), one biquad."""
+
+    kind = None
+
+    def __init__(self, **backend_kwargs):
+        super().__init__(**backend_kwargs)
+
+    def forward(self, input_signals, w0, q_inv):
+        return self._run(input_signals, *design.simple_filter(self.kind, w0, q_inv))
+
+    def parameter_size(self):
+        return {"w0": 1, "q_inv": 1}
+
+
+class LowPassFilter(BaseParametricFilter):
+    kind = "lowpass"
+
+
+class HighPassFilter(BaseParametricFilter):
+    kind = "highpass"
+
+
+class BandPassFilter(BaseParametricFilter):
+    kind = "bandpass"
+
+
+class BandRejectFilter(BaseParametricFilter):
+    kind = "bandreject"
+
+
+class AllPassFilter(BaseParametricFilter):
+    kind = "allpass"
+
+
+class BaseParametricEqualizerFilter(_BiquadStack):
+    """filter.py:559-616: three parameters per band (cutoff, inverse Q, log gain), K bands."""
+
+    kind = None
+
+    def __init__(self, num_filters=1, **backend_kwargs):
+        super().__init__(**backend_kwargs)
+        self.num_filters = num_filters
+
+    def forward(self, input_signals, w0, q_inv, log_gain):
+        return self._run(input_signals, *design.eq_band(self.kind, w0, q_inv, log_gain))
+
+    def parameter_size(self):
+        return {k: self.num_filters for k in ("w0", "q_inv", "log_gain")}
+
+
+class PeakingFilter(BaseParametricEqualizerFilter):
+    kind = "peaking"
+
+
+class LowShelf(BaseParametricEqualizerFilter):
+    kind = "lowshelf"
+
+
+class HighShelf(BaseParametricEqualizerFilter):
+    kind = "highshelf"

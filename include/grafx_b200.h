@@ -60,6 +60,39 @@ GFX_API int gfx_biquad_cascade_f64(const double* x, double* y, const double* Bs,
                            int c_sig, int c_filt, int K, long long L, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ---- stereo <-> mid/side -------------------------------------------------------------------
+ * Replaces lr_to_ms / ms_to_lr (processors/core/midside.py:4-17).  x, y [batch, 2, L]:
+ *   y[:,0] = (x[:,0] + x[:,1]) * mult,  y[:,1] = (x[:,0] - x[:,1]) * mult
+ * mult = 0.5 is lr_to_ms, mult = 1 is ms_to_lr. */
+GFX_API int gfx_midside_f32(const float* x, float* y, int batch, long long L, float mult, void* stream);
+
+/* ---- dynamics: Compressor / NoiseGate, and fused serial chains of them -------------------------
+ * Replaces Compressor.forward / NoiseGate.forward (processors/dynamics.py:361-419,598-651), the
+ * knees (:443-489, :675-721), TruncatedOnePoleIIRFilter and Ballistics
+ * (processors/core/envelope.py:34-60, 84-101) and, with n_stages > 1, a SerialChain of such
+ * processors (processors/container.py:116-140) without materialising the intermediate signal.
+ *   x, y [batch, channels, L];  every parameter pointer is a device array with leading dim batch.
+ * `stages` is a HOST array of n_stages (<= 4) descriptors, consumed before the call returns. */
+typedef struct gfx_dynamics_stage {
+    int kind;               /* 0 compressor, 1 noise gate */
+    int knee;               /* 0 hard, 1 quadratic, 2 exponential */
+    int energy_smoother;    /* 0 none, 1 truncated one-pole ("iir"), 2 ballistics */
+    int gain_smoother;      /* same coding */
+    int gain_smooth_in_log; /* gain smoother runs on the log-gain */
+    int reserved;
+    const float* log_threshold; /* [batch] */
+    const float* log_ratio;     /* [batch] */
+    const float* log_knee;      /* [batch], may be NULL for the hard knee */
+    const float* z_alpha_pre;   /* [batch,1] iir / [batch,2] ballistics / NULL */
+    const float* z_alpha_post;  /* same for the gain smoother */
+    float* hist_pre;            /* [batch, L] scratch; required for stages > 0 with an iir energy smoother when iir_len < L */
+    float* hist_post;           /* [batch, L] scratch; required for an iir gain smoother when iir_len < L */
+} gfx_dynamics_stage;
+GFX_API size_t gfx_dynamics_workspace_bytes(int batch, int n_stages);
+GFX_API int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long long L,
+                             const gfx_dynamics_stage* stages, int n_stages, int iir_len,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

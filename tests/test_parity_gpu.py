@@ -1,0 +1,126 @@
+"""GPU parity tests proper: the CUDA path (through the nn.Module boundary and the C ABI) against
+(a) golden vectors produced by the reference's own code and (b) the oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star: within 1e-4 relative of the reference):
+    rel-L2 <= 1e-4  and  max|err| <= 1e-4 * max|ref|   per fixture.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _golden import GOLDEN, class_of, fixture_names, load, max_rel, oracle_call, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+IIR_PREFIXES = ["peq_lfilter", "cfg1_biquad_lfilter", "biquadfilter", "statevariablefilter", "lowpassfilter",
+                "highpassfilter", "bandpassfilter", "bandrejectfilter", "allpassfilter", "peakingfilter",
+                "lowshelf", "highshelf"]
+
+
+def build_processor(name, kwargs):
+    import grafx_b200.processors as P
+
+    return getattr(P, class_of(name))(**kwargs).cuda()
+
+
+def run_product(name, x, params, kwargs):
+    proc = build_processor(name, kwargs)
+    out = proc(x.cuda(), **{k: v.cuda() for k, v in params.items()})
+    if isinstance(out, tuple):
+        out = out[0]
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def assert_close(y, y_ref, name, tol=TOL):
+    assert y.shape == y_ref.shape, (name, y.shape, y_ref.shape)
+    assert torch.isfinite(y).all(), name
+    r, m = rel_l2(y, y_ref), max_rel(y, y_ref)
+    assert r <= tol and m <= tol, (name, r, m)
+
+
+@pytest.mark.parametrize("name", fixture_names(IIR_PREFIXES))
+def test_iir_family_vs_reference_golden(name):
+    x, params, meta, y_ref, _ = load(name)
+    assert_close(run_product(name, x, params, meta["kwargs"]), y_ref, name)
+
+
+def test_kat_ssm_equals_lfilter_float64():
+    """The reference's known-answer test (tests/processors/test_filter.py:215-233) in double."""
+    from grafx_b200.processors.core import IIRFilter
+
+    z = np.load(os.path.join(GOLDEN, "kat_iir_f64.npz"))
+    x, Bs, As, y = (torch.from_numpy(z[k]) for k in ("x", "Bs", "As", "y"))
+    for backend in ("ssm", "lfilter"):
+        out = IIRFilter(backend=backend)(x.cuda(), Bs.cuda(), As.cuda()).cpu()
+        assert out.dtype == torch.float64
+        assert torch.allclose(out, y, rtol=1e-9, atol=1e-9), (out - y).abs().max()
+
+
+@pytest.mark.parametrize("shape", [(3, 2, 1), (2, 1, 7), (2, 2, 8191), (1, 2, 8193), (5, 1, 16385), (2, 2, 40001)])
+@pytest.mark.parametrize("K", [1, 4])
+def test_cascade_ragged_lengths_vs_oracle(shape, K):
+    """Tile boundaries, unaligned lengths (scalar path), tiny inputs."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.functional as F_
+
+    torch.manual_seed(1)
+    b, c, L = shape
+    x = torch.randn(b, c, L)
+    w0, q, g = (torch.randn(b, c, K) for _ in range(3))
+    Bs, As = O.peq_coeffs(w0, q, g, use_shelving_filters=False)
+    y_ref = O.iir_lfilter(x, Bs, As)
+    y = F_.biquad_cascade(x.cuda(), Bs.cuda(), As.cuda()).cpu()
+    assert_close(y, y_ref, f"ragged{shape}K{K}")
+
+
+@pytest.mark.parametrize("c_sig,c_filt", [(1, 2), (2, 1), (2, 2), (1, 1)])
+def test_cascade_channel_broadcast(c_sig, c_filt):
+    from oracle import grafx_oracle as O
+    import grafx_b200.functional as F_
+
+    torch.manual_seed(2)
+    x = torch.randn(3, c_sig, 9000)
+    w0, q, g = (torch.randn(3, c_filt, 3) for _ in range(3))
+    Bs, As = O.peq_coeffs(w0, q, g)
+    y_ref = O.iir_lfilter(x, Bs, As)
+    y = F_.biquad_cascade(x.cuda(), Bs.cuda(), As.cuda()).cpu()
+    assert_close(y, y_ref, f"bcast{c_sig}{c_filt}")
+
+
+def test_cfg2_full_size_vs_oracle_and_linearity():
+    """BASELINE config 2 at full size (256 x 2 x 131072, K=5): against the oracle (torchaudio
+    lfilter on the host, a few seconds) and through linearity f(a x1 + x2) = a f(x1) + f(x2)."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    torch.manual_seed(0)
+    B, C, L, K = 256, 2, 131072, 5
+    x = torch.randn(B, C, L)
+    prm = {k: torch.randn(B, C, K) for k in ("w0", "q_inv", "log_gain")}
+    proc = P.ParametricEqualizer(num_filters=K, processor_channel="stereo", backend="lfilter").cuda()
+    prm_d = {k: v.cuda() for k, v in prm.items()}
+    y = proc(x.cuda(), **prm_d)
+    y_ref = O.parametric_equalizer(x, **prm, processor_channel="stereo", backend="lfilter")
+    yc = y.cpu()
+    assert torch.isfinite(yc).all()
+    assert rel_l2(yc, y_ref) <= TOL
+    # per-row check (worst row), not only the aggregate
+    num = (yc - y_ref).double().flatten(0, 1).norm(dim=-1)
+    den = y_ref.double().flatten(0, 1).norm(dim=-1)
+    assert float((num / den).max()) <= TOL, float((num / den).max())
+    x2 = torch.randn(B, C, L, device="cuda")
+    lhs = proc(0.5 * x.cuda() + x2, **prm_d)
+    rhs = 0.5 * y + proc(x2, **prm_d)
+    assert rel_l2(lhs.cpu(), rhs.cpu()) <= 1e-5
+
+
+def test_cpu_tensor_fails_loudly():
+    import grafx_b200.processors as P
+    from grafx_b200._cabi import GrafxB200Error
+
+    with pytest.raises(GrafxB200Error):
+        P.LowPassFilter(backend="lfilter")(torch.randn(1, 1, 64), torch.zeros(1, 1), torch.zeros(1, 1))
