@@ -22,6 +22,19 @@ c_ll = ctypes.c_longlong
 c_size_t = ctypes.c_size_t
 c_float = ctypes.c_float
 
+
+class DynamicsStage(ctypes.Structure):
+    """gfx_dynamics_stage (include/grafx_b200.h)."""
+
+    _fields_ = [
+        ("kind", c_int), ("knee", c_int), ("energy_smoother", c_int), ("gain_smoother", c_int),
+        ("gain_smooth_in_log", c_int), ("reserved", c_int),
+        ("log_threshold", c_void_p), ("log_ratio", c_void_p), ("log_knee", c_void_p),
+        ("z_alpha_pre", c_void_p), ("z_alpha_post", c_void_p),
+        ("hist_pre", c_void_p), ("hist_post", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/grafx_b200.h
 SIGNATURES = {
     "gfx_version": (c_int, []),
@@ -33,6 +46,18 @@ SIGNATURES = {
                                        c_int, c_ll, c_void_p, c_size_t, c_void_p]),
     "gfx_biquad_cascade_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_ll, c_void_p, c_size_t, c_void_p]),
+    "gfx_dynamics_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gfx_dynamics_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, ctypes.POINTER(DynamicsStage), c_int,
+                                 c_int, c_void_p, c_size_t, c_void_p]),
+    "gfx_fir_fft_size": (c_int, [c_int]),
+    "gfx_fft_plan_bytes": (c_size_t, [c_int]),
+    "gfx_fft_plan_init": (c_int, [c_void_p, c_int, c_void_p]),
+    "gfx_fir_conv_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_ll, c_int, c_int]),
+    "gfx_fir_conv_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_int, c_int, c_void_p,
+                                 c_void_p, c_size_t, c_void_p]),
+    "gfx_drywet_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
+    "gfx_node_sum_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll,
+                                 c_void_p]),
     "gfx_midside_f32": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_float, c_void_p]),
 }
 

@@ -46,3 +46,93 @@ extern "C" int gfx_midside_f32(const float* x, float* y, int batch, long long L,
     GFX_CUDA_CHECK(cudaGetLastError());
     return GFX_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Dry/wet mix (reference: processors/container.py:62-67):  y = w * wet + (1 - w) * dry, w per item.
+namespace gfx {
+__global__ void __launch_bounds__(256) drywet_kernel(const float* __restrict__ dry, const float* __restrict__ wet,
+                                                     const float* __restrict__ w, float* __restrict__ y,
+                                                     long long inner, long long total, int vec) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        if (vec) {
+            const long long b = (i * 4) / inner;
+            const float a = w[b], c = 1.f - a;
+            const float4 d = ldg_stream(reinterpret_cast<const float4*>(dry) + i);
+            const float4 e = ldg_stream(reinterpret_cast<const float4*>(wet) + i);
+            float4 o;
+            o.x = a * e.x + c * d.x; o.y = a * e.y + c * d.y; o.z = a * e.z + c * d.z; o.w = a * e.w + c * d.w;
+            stg_stream(reinterpret_cast<float4*>(y) + i, o);
+        } else {
+            const float a = w[i / inner];
+            y[i] = a * wet[i] + (1.f - a) * dry[i];
+        }
+    }
+}
+
+// Node-axis aggregation of the render loop (reference: render/core.py:101-112 aggregate_tensor,
+// "sum" and "scatter").  src is a [batch, n_src, inner] view (strided), dst a [batch, n_dst, inner]
+// view; dst[b, j] = sum over sources i with index[i] == j  (index == NULL: every source -> j = 0).
+__global__ void __launch_bounds__(256) node_sum_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                       const int* __restrict__ index, int batch, int n_src, int n_dst,
+                                                       long long inner, long long src_bs, long long src_ns,
+                                                       long long dst_bs, long long dst_ns, int vec) {
+    const long long per = vec ? inner / 4 : inner;
+    const long long total = (long long)batch * n_dst * per;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long q = i % per;
+        const long long bj = i / per;
+        const int j = (int)(bj % n_dst);
+        const long long b = bj / n_dst;
+        const float* sb = src + b * src_bs;
+        float* out = dst + b * dst_bs + (long long)j * dst_ns;
+        if (vec) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < n_src; ++s) {
+                if (index && index[s] != j) continue;
+                const float4 v = ldg_stream(reinterpret_cast<const float4*>(sb + (long long)s * src_ns) + q);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            stg_stream(reinterpret_cast<float4*>(out) + q, acc);
+        } else {
+            float acc = 0.f;
+            for (int s = 0; s < n_src; ++s) {
+                if (index && index[s] != j) continue;
+                acc += sb[(long long)s * src_ns + q];
+            }
+            out[q] = acc;
+        }
+    }
+}
+}  // namespace gfx
+
+extern "C" int gfx_drywet_f32(const float* dry, const float* wet, const float* weight, float* y, int batch,
+                              long long inner, void* stream) {
+    if (!dry || !wet || !weight || !y || batch <= 0 || inner <= 0) return GFX_ERR_INVALID;
+    const int vec = (((uintptr_t)dry | (uintptr_t)wet | (uintptr_t)y) % 16 == 0) && (inner % 4 == 0);
+    const long long total = vec ? (long long)batch * inner / 4 : (long long)batch * inner;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)gfx::device_info().sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    gfx::drywet_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dry, wet, weight, y, inner, total, vec);
+    GFX_CUDA_CHECK(cudaGetLastError());
+    return GFX_OK;
+}
+
+extern "C" int gfx_node_sum_f32(const float* src, float* dst, const int* index, int batch, int n_src, int n_dst,
+                                long long inner, long long src_batch_stride, long long src_node_stride,
+                                long long dst_batch_stride, long long dst_node_stride, void* stream) {
+    if (!src || !dst || batch <= 0 || n_src <= 0 || n_dst <= 0 || inner <= 0) return GFX_ERR_INVALID;
+    const int vec = (((uintptr_t)src | (uintptr_t)dst) % 16 == 0) && (inner % 4 == 0) && (src_batch_stride % 4 == 0) &&
+                    (src_node_stride % 4 == 0) && (dst_batch_stride % 4 == 0) && (dst_node_stride % 4 == 0);
+    const long long total = (long long)batch * n_dst * (vec ? inner / 4 : inner);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)gfx::device_info().sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    gfx::node_sum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        src, dst, index, batch, n_src, n_dst, inner, src_batch_stride, src_node_stride, dst_batch_stride,
+        dst_node_stride, vec);
+    GFX_CUDA_CHECK(cudaGetLastError());
+    return GFX_OK;
+}

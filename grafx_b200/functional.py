@@ -70,6 +70,196 @@ def ms_to_lr(x: torch.Tensor) -> torch.Tensor:
     return _midside(x, 1.0)
 
 
+_PLANS: dict = {}
+
+
+def _fft_plan(device: torch.device, n: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), n)
+    plan = _PLANS.get(key)
+    if plan is None:
+        L_ = _cabi.lib()
+        plan = torch.empty(L_.gfx_fft_plan_bytes(n), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            _cabi.check(L_.gfx_fft_plan_init(plan.data_ptr(), n, _cabi.stream_ptr()), "gfx_fft_plan_init")
+        _PLANS[key] = plan
+    return plan
+
+
+def fir_conv(x: torch.Tensor, h: torch.Tensor, mode: str = "causal") -> torch.Tensor:
+    """Linear convolution sliced to len(x) (reference: convolve(), core/convolution.py:119-134).
+
+    x [B, Cx, L] (or [B, L]), h [B, Ch, N] (or [B, N]); channels broadcast; mode "causal" or
+    "zerophase" (output shifted by N // 2)."""
+    _cabi.require_cuda(x, h)
+    if mode not in ("causal", "zerophase"):
+        raise ValueError(f"unsupported convolution mode: {mode}")
+    squeeze = x.ndim == 2 and h.ndim == 2
+    x3 = x.unsqueeze(1) if x.ndim == 2 else x
+    h3 = h.unsqueeze(1) if h.ndim == 2 else h
+    assert x3.ndim == 3 and h3.ndim == 3 and x3.shape[0] == h3.shape[0]
+    B, cx, L = x3.shape
+    _, ch, N = h3.shape
+    assert cx == ch or cx == 1 or ch == 1, "channel mismatch between signal and filter"
+    x3, h3 = _prep(x3, torch.float32), _prep(h3, torch.float32)
+    y = torch.empty(B, max(cx, ch), L, dtype=torch.float32, device=x.device)
+    if y.numel():
+        L_ = _cabi.lib()
+        n = L_.gfx_fir_fft_size(N)
+        plan = _fft_plan(x.device, n)
+        zp = int(mode == "zerophase")
+        ws = _cabi.workspace(L_.gfx_fir_conv_workspace_bytes(B, cx, ch, L, N, zp), x.device)
+        with torch.cuda.device(x.device):
+            code = L_.gfx_fir_conv_f32(x3.data_ptr(), h3.data_ptr(), y.data_ptr(), B, cx, ch, L, N, zp,
+                                       plan.data_ptr(), ws.data_ptr(), ws.numel(), _cabi.stream_ptr())
+        _cabi.check(code, "gfx_fir_conv_f32")
+    return y.squeeze(1) if squeeze else y
+
+
+def normalize_impulse(ir: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """core/utils.py:14-18 -- O(filter taps) parameter-side math, stays in PyTorch."""
+    assert ir.ndim == 3
+    e = ir.square().sum(2, keepdim=True).mean(1, keepdim=True)
+    return ir / torch.sqrt(e + eps)
+
+
+def iir_fsm_fir(Bs: torch.Tensor, As: torch.Tensor, fir_len: int) -> torch.Tensor:
+    """Frequency-sampled FIR of a biquad cascade (core/iir.py:147-150, 263-276):
+    irfft_N( prod_k B_k(w_m) / A_k(w_m) ), w_m = 2 pi m / N.  O(parameters x N) filter DESIGN
+    (512 rows x 4000 taps at config 2), evaluated with torch on the device."""
+    m = torch.arange(fir_len // 2 + 1, device=Bs.device, dtype=torch.float32)
+    ang = (-2.0 * torch.pi / fir_len) * m
+    z1 = torch.polar(torch.ones_like(ang), ang)
+    z2 = torch.polar(torch.ones_like(ang), 2 * ang)
+    Bs, As = Bs.to(torch.float32), As.to(torch.float32)
+    num = Bs[..., 0:1] + Bs[..., 1:2] * z1 + Bs[..., 2:3] * z2
+    den = As[..., 0:1] + As[..., 1:2] * z1 + As[..., 2:3] * z2
+    return torch.fft.irfft((num / den).prod(-2), n=fir_len, dim=-1)
+
+
 def iir_fsm(x: torch.Tensor, Bs: torch.Tensor, As: torch.Tensor, fir_len: int) -> torch.Tensor:
     """Frequency-sampled FIR of the cascade + causal convolution (core/iir.py:147-152,263-276)."""
-    raise NotImplementedError("fsm backend: FIR convolution kernel not built yet")
+    _cabi.require_cuda(x, Bs, As)
+    return fir_conv(x, iir_fsm_fir(Bs.detach(), As.detach(), fir_len), "causal")
+
+
+_KNEE = {"hard": 0, "quadratic": 1, "exponential": 2}
+_SMOOTHER = {None: 0, "iir": 1, "ballistics": 2}
+_DYN_KIND = {"compressor": 0, "noisegate": 1}
+
+
+def dynamics_chain(x: torch.Tensor, stages: list[dict], iir_len: int = 16384) -> torch.Tensor:
+    """Compressor / NoiseGate, or several of them back to back, in one pass over the audio.
+
+    Reference: Compressor.forward / NoiseGate.forward (processors/dynamics.py:361-419, 598-651).
+    x [B, C, L].  Each stage is a dict: kind ("compressor"|"noisegate"), knee, energy_smoother,
+    gain_smoother, gain_smooth_in_log, log_threshold, log_ratio, log_knee, z_alpha_pre,
+    z_alpha_post (tensors with leading dim B)."""
+    _cabi.require_cuda(x)
+    assert x.ndim == 3
+    B, C, L = x.shape
+    x = _prep(x, torch.float32)
+    y = torch.empty_like(x)
+    if y.numel() == 0:
+        return y
+    L_ = _cabi.lib()
+    keep = []  # keep parameter tensors alive until the launch is enqueued
+
+    def dev(t, cols):
+        if t is None:
+            return None
+        _cabi.require_cuda(t)
+        t = _prep(t, torch.float32).reshape(B, -1)
+        assert t.shape[1] == cols, f"parameter has {t.shape[1]} columns, expected {cols}"
+        keep.append(t)
+        return t.data_ptr()
+
+    arr = (_cabi.DynamicsStage * len(stages))()
+    for d, st in enumerate(stages):
+        s = arr[d]
+        s.kind = _DYN_KIND[st["kind"]]
+        s.knee = _KNEE[st.get("knee", "quadratic")]
+        s.energy_smoother = _SMOOTHER[st.get("energy_smoother", "iir")]
+        s.gain_smoother = _SMOOTHER[st.get("gain_smoother", None)]
+        s.gain_smooth_in_log = int(bool(st.get("gain_smooth_in_log", False)))
+        s.log_threshold = dev(st["log_threshold"], 1)
+        s.log_ratio = dev(st["log_ratio"], 1)
+        s.log_knee = dev(st.get("log_knee"), 1) if s.knee != 0 else None
+        if s.knee != 0 and s.log_knee is None:
+            raise AssertionError("log_knee is required for the quadratic / exponential knee")
+        s.z_alpha_pre = dev(st.get("z_alpha_pre"), s.energy_smoother) if s.energy_smoother else None
+        s.z_alpha_post = dev(st.get("z_alpha_post"), s.gain_smoother) if s.gain_smoother else None
+        if s.energy_smoother and s.z_alpha_pre is None:
+            raise AssertionError("z_alpha_pre is required by the energy smoother")
+        if s.gain_smoother and s.z_alpha_post is None:
+            raise AssertionError("z_alpha_post is required by the gain smoother")
+        if iir_len < L:
+            # scratch for the truncation tail; only touched for rows whose pole is within ~100/N of 1
+            if s.energy_smoother == 1 and d > 0:
+                h = torch.empty(B, L, dtype=torch.float32, device=x.device)
+                keep.append(h)
+                s.hist_pre = h.data_ptr()
+            if s.gain_smoother == 1:
+                h = torch.empty(B, L, dtype=torch.float32, device=x.device)
+                keep.append(h)
+                s.hist_post = h.data_ptr()
+    ws = _cabi.workspace(L_.gfx_dynamics_workspace_bytes(B, len(stages)), x.device)
+    with torch.cuda.device(x.device):
+        code = L_.gfx_dynamics_f32(x.data_ptr(), y.data_ptr(), B, C, L, arr, len(stages), int(iir_len),
+                                   ws.data_ptr(), ws.numel(), _cabi.stream_ptr())
+    _cabi.check(code, "gfx_dynamics_f32")
+    # the caching allocator keeps stream order: freeing `keep`/`ws` here is safe on this stream
+    return y
+
+
+def drywet_mix(dry: torch.Tensor, wet: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """y = w * wet + (1 - w) * dry, w per batch item used as given (container.py:62-67)."""
+    _cabi.require_cuda(dry, wet, weight)
+    assert dry.shape == wet.shape
+    dry, wet = _prep(dry, torch.float32), _prep(wet, torch.float32)
+    w = _prep(weight, torch.float32).reshape(-1)
+    assert w.numel() == dry.shape[0]
+    y = torch.empty_like(dry)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(dry.device):
+        code = _cabi.lib().gfx_drywet_f32(dry.data_ptr(), wet.data_ptr(), w.data_ptr(), y.data_ptr(), dry.shape[0],
+                                          dry[0].numel(), _cabi.stream_ptr())
+    _cabi.check(code, "gfx_drywet_f32")
+    return y
+
+
+def node_sum(src: torch.Tensor, node_dim: int, index: torch.Tensor | None = None, n_dst: int = 1,
+             out: torch.Tensor | None = None) -> torch.Tensor:
+    """Sum (index None) or scatter-sum over the node axis of a signal-buffer view
+    (render/core.py:101-112).  `src` is [Q, C, L] (node_dim 0) or [B, Q, C, L] (node_dim 1) and may
+    be a slice of the buffer (only the node/batch axes may be strided).  `out`, if given, is a
+    view with n_dst nodes that is written in place."""
+    _cabi.require_cuda(src)
+    assert src.dtype == torch.float32
+    if node_dim == 0:
+        src4 = src.unsqueeze(0)
+    else:
+        src4 = src
+    B, Q, C, L = src4.shape
+    if src4.stride(3) != 1 or src4.stride(2) != L:
+        src4 = src4.contiguous()
+    shape = (B, n_dst, C, L)
+    if out is None:
+        out4 = torch.empty(shape, dtype=torch.float32, device=src.device)
+    else:
+        out4 = out.unsqueeze(0) if node_dim == 0 else out
+        assert tuple(out4.shape) == shape and out4.stride(3) == 1 and out4.stride(2) == L
+    idx_ptr = None
+    if index is not None:
+        index = index.to(device=src.device, dtype=torch.int32).contiguous()
+        assert index.numel() == Q
+        idx_ptr = index.data_ptr()
+    if out4.numel():
+        with torch.cuda.device(src.device):
+            code = _cabi.lib().gfx_node_sum_f32(src4.data_ptr(), out4.data_ptr(), idx_ptr, B, Q, n_dst, C * L,
+                                                src4.stride(0), src4.stride(1), out4.stride(0), out4.stride(1),
+                                                _cabi.stream_ptr())
+        _cabi.check(code, "gfx_node_sum_f32")
+    if out is not None:
+        return out
+    return out4.squeeze(0) if node_dim == 0 else out4

@@ -1,0 +1,65 @@
+"""Container processors -- drop-ins for grafx.processors.container (container.py:10-148).
+
+SerialChain keeps the reference contract (returns `(output, intermediates)`, takes one kwargs
+dict per wrapped processor).  When every wrapped processor is a Compressor / NoiseGate with the
+same `iir_len`, the chain is executed by ONE fused kernel launch (the intermediate signal never
+goes to HBM); otherwise the processors run one after another.
+"""
+from __future__ import annotations
+
+import torch.nn as nn
+
+from .. import functional as F_
+from .dynamics import _DynamicsBase
+
+_MAX_FUSED = 4
+
+
+class DryWet(nn.Module):
+    """y = w * f(u) + (1 - w) * u with w used as given (container.py:45-71)."""
+
+    def __init__(self, processor, external_param=True):
+        super().__init__()
+        self.processor = processor
+        self.external_param = external_param
+
+    def forward(self, input_signals, drywet_weight, **processor_kwargs):
+        out = self.processor(input_signals, **processor_kwargs)
+        wet, inter = out if isinstance(out, tuple) else (out, None)
+        mixed = F_.drywet_mix(input_signals, wet, drywet_weight)
+        return (mixed, inter) if isinstance(out, tuple) else mixed
+
+    def parameter_size(self):
+        size = self.processor.parameter_size()
+        if not self.external_param:
+            size["drywet_weight"] = (1,)
+        return size
+
+
+class SerialChain(nn.Module):
+    def __init__(self, processors):
+        super().__init__()
+        self.processors = nn.ModuleDict(processors)
+
+    def _fusable(self):
+        procs = list(self.processors.values())
+        return (1 < len(procs) <= _MAX_FUSED and all(isinstance(p, _DynamicsBase) for p in procs)
+                and len({p.iir_len for p in procs}) == 1)
+
+    def forward(self, input_signals, **processors_kwargs):
+        intermediates = {}
+        if self._fusable():
+            stages = [p.stage(**processors_kwargs[k]) for k, p in self.processors.items()]
+            iir_len = next(iter(self.processors.values())).iir_len
+            return F_.dynamics_chain(input_signals, stages, iir_len), intermediates
+        output_signals = input_signals
+        for k, processor in self.processors.items():
+            out = processor(output_signals, **processors_kwargs[k])
+            if isinstance(out, tuple):
+                output_signals, intermediates[k] = out
+            else:
+                output_signals = out
+        return output_signals, intermediates
+
+    def parameter_size(self):
+        return {k: v.parameter_size() for k, v in self.processors.items()}

@@ -1,0 +1,66 @@
+"""Compressor / NoiseGate -- drop-ins for grafx.processors.dynamics (dynamics.py:213-721).
+
+Same constructor kwargs, forward signature and parameter_size() as the reference; the whole
+forward pass (energy, envelope smoother, log, knee, optional gain smoother, gain multiply) is one
+fused CUDA kernel (csrc/dynamics.cu).  `flashfftconv` / `max_input_len` are accepted and ignored.
+Quirks reproduced as shipped: the relu inside the one-pole smoother also
+applies when it smooths a log-gain; ballistics always starts from 1; parameter_size() omits
+log_knee for the hard knee.
+"""
+from __future__ import annotations
+
+import torch.nn as nn
+
+from .. import functional as F_
+
+_SMOOTHERS = ("iir", "ballistics", None)
+_KNEES = ("hard", "quadratic", "exponential")
+
+
+class _DynamicsBase(nn.Module):
+    kind = None
+
+    def __init__(self, energy_smoother="iir", gain_smoother=None, gain_smooth_in_log=False, knee="quadratic",
+                 iir_len=16384, flashfftconv=True, max_input_len=2**17):
+        super().__init__()
+        if energy_smoother not in _SMOOTHERS:
+            raise ValueError(f"Unknown energy_smoother: {energy_smoother}")
+        if gain_smoother not in _SMOOTHERS:
+            raise ValueError(f"Unknown gain_smoother: {gain_smoother}")
+        if knee not in _KNEES:
+            raise ValueError(f"Unknown knee: {knee}")
+        self.energy_smoother = energy_smoother
+        self.gain_smoother = gain_smoother
+        self.gain_smooth_in_log = gain_smooth_in_log
+        self.knee = knee
+        self.iir_len = iir_len
+
+    def stage(self, log_threshold, log_ratio, log_knee=None, z_alpha_pre=None, z_alpha_post=None):
+        """Descriptor of this processor for functional.dynamics_chain (also used by SerialChain)."""
+        return dict(kind=self.kind, knee=self.knee, energy_smoother=self.energy_smoother,
+                    gain_smoother=self.gain_smoother, gain_smooth_in_log=self.gain_smooth_in_log,
+                    log_threshold=log_threshold, log_ratio=log_ratio, log_knee=log_knee,
+                    z_alpha_pre=z_alpha_pre, z_alpha_post=z_alpha_post)
+
+    def forward(self, input_signals, log_threshold, log_ratio, log_knee=None, z_alpha_pre=None, z_alpha_post=None):
+        st = self.stage(log_threshold, log_ratio, log_knee, z_alpha_pre, z_alpha_post)
+        return F_.dynamics_chain(input_signals, [st], self.iir_len)
+
+    def parameter_size(self):
+        size = {"log_threshold": 1, "log_ratio": 1}
+        if self.knee != "hard":
+            size["log_knee"] = 1
+        for name, kind in (("z_alpha_pre", self.energy_smoother), ("z_alpha_post", self.gain_smoother)):
+            if kind == "iir":
+                size[name] = 1
+            elif kind == "ballistics":
+                size[name] = 2
+        return size
+
+
+class Compressor(_DynamicsBase):
+    kind = "compressor"
+
+
+class NoiseGate(_DynamicsBase):
+    kind = "noisegate"

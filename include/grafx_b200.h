@@ -66,6 +66,39 @@ GFX_API int gfx_biquad_cascade_f64(const double* x, double* y, const double* Bs,
  * mult = 0.5 is lr_to_ms, mult = 1 is ms_to_lr. */
 GFX_API int gfx_midside_f32(const float* x, float* y, int batch, long long L, float mult, void* stream);
 
+/* ---- FIR convolution (overlap-save, in-kernel FFT) --------------------------------------------
+ * Replaces convolve() / FIRConvolution._native_forward (processors/core/convolution.py:82-83,
+ * 119-134: pad, rfft, multiply, irfft, slice through torch.fft / cuFFT) with its intended
+ * semantics (true linear convolution; the shipped code is only correct for even Lx+Lh-1):
+ *   y[b,c,n] = sum_k h[b,c',k] x[b,c'',n + shift - k],  n < L,  shift = 0 (causal) | filter_len/2 (zerophase)
+ *   x [batch, cx, L], h [batch, ch, filter_len], y [batch, max(cx,ch), L]; cx == ch or one of them is 1.
+ * `plan` is the twiddle table for n = gfx_fir_fft_size(filter_len): allocate gfx_fft_plan_bytes(n)
+ * bytes once per device and fill them with gfx_fft_plan_init.  The workspace holds filter (and,
+ * for filter_len > 16384, input) spectra; any size >= the one for batch = 1 works, the size
+ * returned for the full batch is the fastest. */
+GFX_API int gfx_fir_fft_size(int filter_len);
+GFX_API size_t gfx_fft_plan_bytes(int n);
+GFX_API int gfx_fft_plan_init(void* plan, int n, void* stream);
+GFX_API size_t gfx_fir_conv_workspace_bytes(int batch, int cx, int ch, long long L, int filter_len, int zerophase);
+GFX_API int gfx_fir_conv_f32(const float* x, const float* h, float* y, int batch, int cx, int ch, long long L,
+                             int filter_len, int zerophase, const void* plan, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* ---- dry/wet mix -----------------------------------------------------------------------------
+ * Replaces the mix in DryWet.forward (processors/container.py:62-67):
+ *   y[b] = weight[b] * wet[b] + (1 - weight[b]) * dry[b],   dry/wet/y [batch, inner], weight [batch]. */
+GFX_API int gfx_drywet_f32(const float* dry, const float* wet, const float* weight, float* y, int batch,
+                           long long inner, void* stream);
+
+/* ---- node-axis aggregation of the render loop --------------------------------------------------
+ * Replaces aggregate_tensor "sum" / "scatter" (render/core.py:101-112, torch.sum / torch_geometric
+ * scatter).  src is a strided view [batch, n_src, inner], dst a strided view [batch, n_dst, inner]
+ * (strides in elements, so slices of the signal buffer are read and written in place):
+ *   dst[b, j] = sum_{i : index[i] == j} src[b, i]      (index == NULL: all sources go to j = 0). */
+GFX_API int gfx_node_sum_f32(const float* src, float* dst, const int* index, int batch, int n_src, int n_dst,
+                             long long inner, long long src_batch_stride, long long src_node_stride,
+                             long long dst_batch_stride, long long dst_node_stride, void* stream);
+
 /* ---- dynamics: Compressor / NoiseGate, and fused serial chains of them -------------------------
  * Replaces Compressor.forward / NoiseGate.forward (processors/dynamics.py:361-419,598-651), the
  * knees (:443-489, :675-721), TruncatedOnePoleIIRFilter and Ballistics
