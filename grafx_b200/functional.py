@@ -263,3 +263,35 @@ def node_sum(src: torch.Tensor, node_dim: int, index: torch.Tensor | None = None
     if out is not None:
         return out
     return out4.squeeze(0) if node_dim == 0 else out4
+
+
+def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_log_magnitude: torch.Tensor,
+              gain_env_log_magnitude: torch.Tensor | None, window: torch.Tensor, ir_len: int, n_fft: int,
+              hop_length: int, to_lr: bool) -> torch.Tensor:
+    """Masked-noise STFT -> impulse response [B, 2, ir_len], (ms->lr) and unit-energy normalised
+    (reference: STFTMaskedNoiseReverb.compute_ir + _process_* prologue, reverb.py:161-228)."""
+    _cabi.require_cuda(noise_stft, init_log_magnitude, delta_log_magnitude, window)
+    B = init_log_magnitude.shape[0]
+    bins, frames = n_fft // 2 + 1, 1 + ir_len // hop_length
+    assert tuple(init_log_magnitude.shape) == (B, 2, bins) and tuple(delta_log_magnitude.shape) == (B, 2, bins)
+    assert noise_stft.is_complex() and tuple(noise_stft.shape[-3:]) == (2, bins, frames)
+    nz = torch.view_as_real(noise_stft.detach().to(torch.complex64).contiguous())
+    nb = noise_stft.shape[0] if noise_stft.ndim == 4 else 1
+    assert nb in (1, B)
+    bstride = 0 if nb == 1 else 2 * bins * frames
+    h0, hd = _prep(init_log_magnitude, torch.float32), _prep(delta_log_magnitude, torch.float32)
+    ge = None
+    if gain_env_log_magnitude is not None:
+        ge = _prep(gain_env_log_magnitude, torch.float32)
+        assert tuple(ge.shape) == (B, 2, frames)
+    win = _prep(window, torch.float32)
+    ir = torch.empty(B, 2, ir_len, dtype=torch.float32, device=h0.device)
+    energy = torch.empty(B, 2, dtype=torch.float32, device=h0.device)
+    with torch.cuda.device(h0.device):
+        code = _cabi.lib().gfx_reverb_ir_f32(nz.data_ptr(), bstride, h0.data_ptr(), hd.data_ptr(), _cabi.ptr(ge),
+                                             win.data_ptr(), ir.data_ptr(), energy.data_ptr(), B, n_fft, hop_length,
+                                             ir_len, int(to_lr), _cabi.stream_ptr())
+    if code == -4:
+        raise NotImplementedError("reverb IR synthesis supports n_fft=384, hop_length=192 only")
+    _cabi.check(code, "gfx_reverb_ir_f32")
+    return ir

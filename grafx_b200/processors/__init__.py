@@ -8,6 +8,7 @@ from .filter import (  # noqa: F401
     BandPassFilter,
     BandRejectFilter,
     BiquadFilter,
+    FIRFilter,
     HighPassFilter,
     HighShelf,
     LowPassFilter,
@@ -16,3 +17,4 @@ from .filter import (  # noqa: F401
     PoleZeroFilter,
     StateVariableFilter,
 )
+from .reverb import STFTMaskedNoiseReverb  # noqa: F401

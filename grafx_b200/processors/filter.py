@@ -11,7 +11,33 @@ import torch.nn as nn
 
 from .. import functional as F_
 from . import design
+from .core.convolution import FIRConvolution
 from .core.iir import IIRFilter
+
+
+class FIRFilter(nn.Module):
+    """Learnable FIR filter (filter.py:20-84): tanh -> unit-energy normalisation -> causal
+    convolution, in mono / stereo / mid-side modes.  The upstream constructor raises (it forwards
+    `fir_len` to FIRConvolution and reads `processor_channel` before storing it, SURVEY.md R3);
+    this class implements the documented signature."""
+
+    def __init__(self, fir_len=1023, processor_channel="mono", **backend_kwargs):
+        super().__init__()
+        if processor_channel not in ("mono", "stereo", "midside"):
+            raise ValueError(f"Unknown channel type: {processor_channel}")
+        self.fir_len = fir_len
+        self.processor_channel = processor_channel
+        self.num_channels = 1 if processor_channel == "mono" else 2
+        self.conv = FIRConvolution(mode="causal", **backend_kwargs)
+
+    def forward(self, input_signals, fir):
+        fir = F_.normalize_impulse(torch.tanh(fir))
+        if self.processor_channel == "midside":
+            return F_.ms_to_lr(self.conv(F_.lr_to_ms(input_signals), fir))
+        return self.conv(input_signals, fir)
+
+    def parameter_size(self):
+        return {"fir": (self.num_channels, self.fir_len)}
 
 
 class _BiquadStack(nn.Module):

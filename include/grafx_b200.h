@@ -84,6 +84,20 @@ GFX_API int gfx_fir_conv_f32(const float* x, const float* h, float* y, int batch
                              int filter_len, int zerophase, const void* plan, void* workspace,
                              size_t workspace_bytes, void* stream);
 
+/* ---- reverb impulse-response synthesis ---------------------------------------------------------
+ * Replaces STFTMaskedNoiseReverb.compute_stft_mask / compute_ir (processors/reverb.py:161-200:
+ * mask, torch.istft) and the ms_to_lr + normalize_impulse of _process_* (reverb.py:215-228).
+ *   noise_stft [*, 2, bins, frames] complex64 (re,im interleaved); noise_batch_stride = complex
+ *     elements between batch items, 0 when one fixed noise is shared (the default upstream);
+ *   init/delta_log_magnitude [batch, 2, bins]; gain_env_log_magnitude [batch, 2, frames] or NULL;
+ *   window [n_fft] (the registered hann buffer); ir [batch, 2, ir_len] (output);
+ *   energy_ws [batch, 2] floats of scratch; ms_to_lr != 0 for the pseudo_midside channel mode.
+ * bins = n_fft/2+1, frames = 1 + ir_len/hop.  Supported geometry: n_fft = 384, hop = 192. */
+GFX_API int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, const float* init_log_magnitude,
+                              const float* delta_log_magnitude, const float* gain_env_log_magnitude,
+                              const float* window, float* ir, float* energy_ws, int batch, int n_fft, int hop,
+                              int ir_len, int ms_to_lr, void* stream);
+
 /* ---- dry/wet mix -----------------------------------------------------------------------------
  * Replaces the mix in DryWet.forward (processors/container.py:62-67):
  *   y[b] = weight[b] * wet[b] + (1 - weight[b]) * dry[b],   dry/wet/y [batch, inner], weight [batch]. */

@@ -214,3 +214,105 @@ def test_drywet_and_midside():
     y = wrapped(x.cuda(), drywet_weight=w.cuda(), **prm).cpu()
     wet = P.LowPassFilter(backend="lfilter").cuda()(x.cuda(), **prm).cpu()
     assert torch.allclose(y, w.view(-1, 1, 1) * wet + (1 - w.view(-1, 1, 1)) * x, atol=1e-5)
+
+
+# ------------------------------------------------------------------ FIR convolution / fsm / FIRFilter
+@pytest.mark.parametrize("name", fixture_names(["peq_fsm", "cfg1_biquad_fsm", "firfilter"]))
+def test_fir_family_vs_reference_golden(name):
+    x, params, meta, y_ref, _ = load(name)
+    assert_close(run_product(name, x, params, meta["kwargs"]), y_ref, name)
+
+
+def test_convolve_fixture_causal_and_zerophase():
+    import grafx_b200.functional as F_
+
+    x, params, meta, y_ref, extra = load("convolve_causal_zerophase")
+    h = params["h"]
+    assert_close(F_.fir_conv(x.cuda(), h.cuda(), "causal").cpu(), y_ref, "conv-causal")
+    assert_close(F_.fir_conv(x.cuda(), h.cuda(), "zerophase").cpu(), torch.from_numpy(extra["y_zerophase"]), "conv-zp")
+
+
+@pytest.mark.parametrize("L,N", [(1, 1), (5, 3), (100, 512), (4097, 513), (10000, 2048), (9001, 2049), (70000, 4000),
+                                 (40000, 16384), (50000, 16385), (70001, 40000)])
+@pytest.mark.parametrize("mode", ["causal", "zerophase"])
+def test_fir_conv_sizes_vs_oracle(L, N, mode):
+    """All three FFT sizes, the partitioned path (N > 16384), unaligned lengths, filter longer
+    than the signal."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.functional as F_
+
+    torch.manual_seed(L + N)
+    x = torch.randn(2, 2, L)
+    h = torch.randn(2, 1, N) / (N ** 0.5)
+    y_ref = O.convolve(x.double(), h.double(), mode).float()
+    y = F_.fir_conv(x.cuda(), h.cuda(), mode).cpu()
+    assert_close(y, y_ref, f"conv L{L} N{N} {mode}", tol=2e-5)
+
+
+def test_fir_conv_2d_and_broadcast():
+    from oracle import grafx_oracle as O
+    import grafx_b200.functional as F_
+
+    torch.manual_seed(7)
+    x = torch.randn(3, 5000)
+    h = torch.randn(3, 700)
+    assert_close(F_.fir_conv(x.cuda(), h.cuda()).cpu(), O.convolve(x, h, "causal"), "conv2d")
+    x = torch.randn(3, 1, 5000)
+    h = torch.randn(3, 2, 300)
+    assert_close(F_.fir_conv(x.cuda(), h.cuda()).cpu(), O.convolve(x, h, "causal"), "conv-bcast")
+
+
+def test_cfg3b_firfilter_full_size_impulse_and_linearity():
+    """FIRFilter(1023, stereo) at 512 x 2 x 131072: impulse response reproduces the normalised
+    taps; linearity; a sampled set of rows against the oracle."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    torch.manual_seed(0)
+    B, L, N = 512, 131072, 1023
+    proc = P.FIRFilter(fir_len=N, processor_channel="stereo").cuda()
+    fir = torch.randn(B, 2, N)
+    x = torch.randn(B, 2, L)
+    y = proc(x.cuda(), fir.cuda())
+    rows = [0, 17, 255, 511]
+    y_ref = O.fir_filter(x[rows], fir[rows], "stereo")
+    assert_close(y[rows].cpu(), y_ref, "cfg3b rows")
+    imp = torch.zeros(4, 2, L); imp[:, :, 0] = 1
+    yi = proc(imp.cuda(), fir[:4].cuda()).cpu()
+    taps = O.normalize_impulse(torch.tanh(fir[:4]))
+    assert float((yi[:, :, :N] - taps).abs().max()) < 1e-6 and float(yi[:, :, N:].abs().max()) < 1e-6
+    x2 = torch.randn(B, 2, L, device="cuda")
+    lhs = proc(2.0 * x.cuda() - x2, fir.cuda())
+    assert rel_l2(lhs.cpu(), (2.0 * y - proc(x2, fir.cuda())).cpu()) < 1e-5
+
+
+# ------------------------------------------------------------------ reverb
+@pytest.mark.parametrize("name", fixture_names(["reverb"]))
+def test_reverb_vs_reference_golden(name):
+    x, params, meta, y_ref, extra = load(name)
+    kw = meta["kwargs"]
+    assert_close(run_product(name, x, params, kw), y_ref, name)
+    # the impulse response itself (reference compute_ir output is un-normalised mid/side)
+    from oracle import grafx_oracle as O
+
+    proc = build_processor(name, kw)
+    ir = proc.compute_ir(**{k: v.cuda() for k, v in params.items()}).cpu()
+    ir_ref = O.normalize_impulse(torch.from_numpy(extra["ir"]))
+    assert_close(ir, ir_ref, name + ":ir", tol=2e-5)
+
+
+@pytest.mark.parametrize("ir_len", [60000, 96000])
+def test_reverb_long_ir_vs_oracle(ir_len):
+    """Default (60000, not a multiple of the hop) and the BASELINE 2 s @ 48 kHz IR (96000 taps ->
+    partitioned convolution), batch reduced so the host oracle runs in seconds."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    gen = torch.Generator().manual_seed(ir_len)
+    B, L = 3, 131072
+    proc = P.STFTMaskedNoiseReverb(ir_len=ir_len).cuda()
+    x = torch.randn(B, 2, L, generator=gen)
+    prm = {k: 0.5 * torch.randn(B, *v, generator=gen) for k, v in proc.parameter_size().items()}
+    y = proc(x.cuda(), **{k: v.cuda() for k, v in prm.items()}).cpu()
+    y_ref = O.stft_masked_noise_reverb(x, **prm, ir_len=ir_len)
+    assert_close(y, y_ref, f"reverb{ir_len}")
