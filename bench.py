@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the grafx hot path on B200 (contract: see README / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg3b|cfg4|cfg4b|cfg5]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+A step = one pass of the hot path over one batch of synthetic 48 kHz audio.  Default workload =
+BASELINE.json configs[1]: ParametricEqualizer, 5 biquads, stereo, batch 256, 131072 samples
+(backend "lfilter": the exact cascade).  Under torchrun (N > 1) every rank processes its own
+batch of the same size (weak scaling; the path shards over the batch axis with no collective).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L2_BYTES = 126 * 2**20
+
+
+# --------------------------------------------------------------------------- workloads
+class Workload:
+    """name, per-GPU shapes, parameter factory and the module(s) under test."""
+
+    def __init__(self, name, batch_div=1):
+        self.name = name
+        g = torch.Generator().manual_seed(0)
+        self.gen = g
+        if name == "cfg2":
+            self.B, self.C, self.L = 256 // batch_div, 2, 131072
+            self.desc = "ParametricEqualizer(num_filters=5, stereo, backend=lfilter) batch=256 x 2ch x 131072"
+            self.kw = dict(num_filters=5, processor_channel="stereo", backend="lfilter", flashfftconv=False)
+            self.cls = "ParametricEqualizer"
+            self.param_shapes = {k: (2, 5) for k in ("w0", "q_inv", "log_gain")}
+            self.launches = 1          # biquad_cascade_kernel (the cudaMemsetAsync of 2 KB is not a kernel)
+            self.bytes_per_sample = 8
+            self.dominant = "biquad_cascade_kernel<float,256>"
+        elif name == "cfg3":
+            self.B, self.C, self.L = 512 // batch_div, 2, 131072
+            self.desc = "STFTMaskedNoiseReverb(ir_len=96000) batch=512 x 2ch x 131072"
+            self.kw = dict(ir_len=96000, flashfftconv=False)
+            self.cls = "STFTMaskedNoiseReverb"
+            self.param_shapes = {"init_log_magnitude": (2, 193), "delta_log_magnitude": (2, 193)}
+            self.launches = None
+            self.bytes_per_sample = 8
+            self.dominant = "fir_upols_kernel<16384,1024>"
+        elif name == "cfg3b":
+            self.B, self.C, self.L = 512 // batch_div, 2, 131072
+            self.desc = "FIRFilter(fir_len=1023, stereo) batch=512 x 2ch x 131072"
+            self.kw = dict(fir_len=1023, processor_channel="stereo")
+            self.cls = "FIRFilter"
+            self.param_shapes = {"fir": (2, 1023)}
+            self.launches = 2
+            self.bytes_per_sample = 8
+            self.dominant = "fir_ols_kernel<4096,256>"
+        elif name in ("cfg4", "cfg4b"):
+            self.B, self.C, self.L = 1024 // batch_div, 1, 65536
+            sm = "iir" if name == "cfg4" else "ballistics"
+            self.desc = f"SerialChain(Compressor({sm}) -> NoiseGate({sm})) fused, batch=1024 x 1ch x 65536"
+            self.kw = dict(energy_smoother=sm, flashfftconv=False)
+            self.cls = "chain"
+            n = 1 if sm == "iir" else 2
+            self.param_shapes = {"log_threshold": (1,), "log_ratio": (1,), "log_knee": (1,), "z_alpha_pre": (n,)}
+            self.launches = 1
+            self.bytes_per_sample = 8
+            self.dominant = "dynamics_kernel"
+        elif name == "cfg5":
+            self.B, self.C, self.L = 16 // batch_div if batch_div <= 16 else 1, 2, 131072
+            self.tracks = 32
+            self.desc = "mixing graph 32 x (in->eq->compressor->reverb) -> out, batch=16 per GPU (128 over 8), 2ch x 131072"
+            self.cls = "graph"
+            self.launches = None
+            self.bytes_per_sample = None
+            self.dominant = "graph"
+        else:
+            raise SystemExit(f"unknown workload {name}")
+
+    # ---- product modules (CUDA)
+    def build(self, device):
+        import grafx_b200.processors as P
+
+        if self.cls == "chain":
+            self.mod = P.SerialChain({"comp": P.Compressor(**self.kw), "gate": P.NoiseGate(**self.kw)}).to(device)
+        elif self.cls == "graph":
+            from grafx_b200.render import mixing_console_plan
+
+            self.procs = {"eq": P.ParametricEqualizer(num_filters=5, processor_channel="stereo", backend="lfilter").to(device),
+                          "compressor": P.Compressor().to(device),
+                          "reverb": P.STFTMaskedNoiseReverb(ir_len=96000).to(device)}
+            self.plan = mixing_console_plan(self.tracks, ["eq", "compressor", "reverb"])
+        else:
+            self.mod = getattr(P, self.cls)(**self.kw).to(device)
+
+    def host_inputs(self, pin=False):
+        if self.cls == "graph":
+            x = torch.randn(self.B, self.tracks, self.C, self.L, generator=self.gen)
+            prm = {t: {k: 0.3 * torch.randn(self.tracks, *((v,) if isinstance(v, int) else v), generator=self.gen)
+                       for k, v in p.parameter_size().items()} for t, p in self.procs.items()}
+        else:
+            x = torch.randn(self.B, self.C, self.L, generator=self.gen)
+            if self.cls == "chain":
+                prm = {n: {k: torch.randn(self.B, *s, generator=self.gen) for k, s in self.param_shapes.items()} for n in ("comp", "gate")}
+            else:
+                prm = {k: torch.randn(self.B, *s, generator=self.gen) for k, s in self.param_shapes.items()}
+        if pin:
+            x = x.pin_memory()
+        return x, prm
+
+    def forward(self, x, prm):
+        if self.cls == "graph":
+            from grafx_b200.render import render_grafx
+
+            return render_grafx(self.procs, x, prm, self.plan, parameters_grad=False)[0]
+        if self.cls == "chain":
+            return self.mod(x, **prm)[0]
+        return self.mod(x, **prm)
+
+    def samples(self):
+        if self.cls == "graph":
+            return self.B * self.C * self.L       # rendered output samples per graph render
+        return self.B * self.C * self.L
+
+    # ---- reference arm: the oracle port on the host CPU (torch CPU ops + torchaudio lfilter,
+    # the same library calls the reference makes)
+    def cpu_forward(self, x, prm):
+        from oracle import grafx_oracle as O
+
+        if self.name == "cfg2":
+            return O.parametric_equalizer(x, **prm, processor_channel="stereo", backend="lfilter")
+        if self.name == "cfg3":
+            return O.stft_masked_noise_reverb(x, **prm, ir_len=96000)
+        if self.name == "cfg3b":
+            return O.fir_filter(x, prm["fir"], "stereo")
+        if self.name in ("cfg4", "cfg4b"):
+            sm = "iir" if self.name == "cfg4" else "ballistics"
+            return O.noisegate(O.compressor(x, **prm["comp"], energy_smoother=sm), **prm["gate"], energy_smoother=sm)
+        if self.name == "cfg5":
+            procs = {"eq": lambda s, **p: O.parametric_equalizer(s, **p, processor_channel="stereo", backend="lfilter"),
+                     "compressor": lambda s, **p: O.compressor(s, **p),
+                     "reverb": lambda s, **p: O.stft_masked_noise_reverb(s, **p, ir_len=96000)}
+            T = self.tracks
+            plan = {"num_nodes": 4 * T + 1, "iters": [None] + [
+                {"type": t, "reads": [("slice", (i * T, (i + 1) * T))], "aggs": [("none", None)], "param": ("slice", (0, T)),
+                 "write": ("slice", ((i + 1) * T, (i + 2) * T))} for i, t in enumerate(["eq", "compressor", "reverb"])] + [
+                {"type": "out", "reads": [("slice", (3 * T, 4 * T))], "aggs": [("sum", None)], "param": ("slice", (0, 1)),
+                 "write": ("slice", (4 * T, 4 * T + 1))}]}
+            return O.render_plan(procs, x, prm, plan)[0]
+        raise SystemExit(self.name)
+
+
+def tree_to(obj, device, non_blocking=False):
+    if isinstance(obj, torch.Tensor):
+        return obj.to(device, non_blocking=non_blocking)
+    return {k: tree_to(v, device, non_blocking) for k, v in obj.items()}
+
+
+def tree_bytes(obj):
+    if isinstance(obj, torch.Tensor):
+        return obj.numel() * obj.element_size()
+    return sum(tree_bytes(v) for v in obj.values())
+
+
+def tree_slice(obj, lo, hi):
+    if isinstance(obj, torch.Tensor):
+        return obj[lo:hi]
+    return {k: tree_slice(v, lo, hi) for k, v in obj.items()}
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    wl = Workload(args.workload)
+    if wl.cls == "graph":
+        wl.B = 1
+        import grafx_b200.processors as P  # parameter_size() only (no CUDA)
+
+        wl.procs = {"eq": P.ParametricEqualizer(num_filters=5, processor_channel="stereo", backend="lfilter"),
+                    "compressor": P.Compressor(), "reverb": P.STFTMaskedNoiseReverb(ir_len=96000)}
+    else:
+        # bounded sample of the workload: 1/8 of the batch per step
+        wl.B = max(1, wl.B // 8)
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    x, prm = wl.host_inputs()
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            wl.cpu_forward(x, prm)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            wl.cpu_forward(x, prm)
+        dt = (time.perf_counter() - t0) / args.steps
+    val = wl.samples() / dt
+    line = {"impl": "reference", "metric": "audio samples/sec (batch x chan x len)", "value": val, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.desc, "sample": f"batch {wl.B} per step (bounded sample of the workload)"},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{wl.name}: batch {wl.B} x {wl.C}ch x {wl.L}, oracle port (torch CPU ops + torchaudio lfilter as the reference calls them), {args.steps} steps"},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the host arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from grafx_b200.render.parallel import max_over_ranks
+
+    batch_div = 1
+    if args.workload == "cfg5":
+        batch_div = 1  # 16 renders per GPU (= 128 over 8 GPUs)
+    wl = Workload(args.workload, batch_div)
+    wl.build(device)
+    x_h, prm_h = wl.host_inputs(pin=False)
+    x = x_h.to(device)
+    prm = tree_to(prm_h, device)
+    samples = wl.samples()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            y = wl.forward(x, prm)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            y = wl.forward(x, prm)
+        ev1.record()
+        barrier()
+        ms_total = max_over_ranks(ev0.elapsed_time(ev1), device)
+        clocks = sampler.stop() if rank == 0 else None
+        ms_step = ms_total / args.steps
+        value = samples * world / (ms_step * 1e-3)
+
+        # ---- dominant kernel alone (device time, events on the launching stream)
+        roofline = None
+        if wl.name == "cfg2":
+            import grafx_b200.functional as F_
+            from grafx_b200.processors import design
+
+            Bs, As = design.parametric_eq(prm["w0"], prm["q_inv"], prm["log_gain"])
+            for _ in range(3):
+                F_.biquad_cascade(x, Bs, As)
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for _ in range(args.steps):
+                F_.biquad_cascade(x, Bs, As)
+            k1.record()
+            torch.cuda.synchronize()
+            k_ms = k0.elapsed_time(k1) / args.steps
+            peak, how = 6650.0, "of fallback"
+            try:
+                peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+                how = "of measured"
+            except Exception:
+                pass
+            alg = wl.bytes_per_sample * samples
+            ach = alg / (k_ms * 1e-3) / 1e9
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl.name)
+            except Exception:
+                pass
+            roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": traffic, "kernel": wl.dominant, "kernel_ms": k_ms, "algorithmic_bytes": alg,
+                        "peak_source": how}
+
+        # ---- end to end through the public nn.Module API with HOST buffers (pinned), copies inside
+        e2e = None
+        if not args.no_e2e:
+            xp, prm_p = x_h.pin_memory(), prm_h
+            out_p = torch.empty((wl.B, 1 if wl.cls == "graph" else wl.C, wl.L) if wl.cls != "graph" else (wl.B, 1, wl.C, wl.L),
+                                dtype=torch.float32).pin_memory()
+            nchunk = 8 if wl.B >= 8 else 1
+            streams = [torch.cuda.Stream(device) for _ in range(min(3, nchunk))]
+            bounds = [(wl.B * i // nchunk, wl.B * (i + 1) // nchunk) for i in range(nchunk)]
+            per_item_params = wl.cls != "graph"
+
+            def e2e_step():
+                for i, (lo, hi) in enumerate(bounds):
+                    s = streams[i % len(streams)]
+                    with torch.cuda.stream(s):
+                        xd = xp[lo:hi].to(device, non_blocking=True)
+                        pd = tree_to(tree_slice(prm_p, lo, hi) if per_item_params else prm_p, device, True)
+                        yd = wl.forward(xd, pd)
+                        out_p[lo:hi].copy_(yd, non_blocking=True)
+                for s in streams:
+                    s.synchronize()
+
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            n_e2e = max(3, min(args.steps, 10))
+            for _ in range(n_e2e):
+                e2e_step()
+            barrier()
+            e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_e2e, device)
+            e2e = {"value": samples * world / (e_ms * 1e-3), "unit": "samples/s",
+                   "h2d_bytes_per_step": tree_bytes(xp) + (tree_bytes(prm_p)),
+                   "d2h_bytes_per_step": tree_bytes(out_p), "ms_per_step": e_ms,
+                   "how": f"pinned host tensors -> {nchunk} chunks over {len(streams)} streams: H2D, nn.Module forward, D2H of the output audio"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cwl = Workload(args.workload)
+        if cwl.cls == "graph":
+            cwl.B = 1
+            cwl.procs = wl.procs
+        else:
+            cwl.B = max(1, cwl.B // 4)
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        cx, cprm = cwl.host_inputs()
+        with torch.no_grad():
+            cwl.cpu_forward(cx, cprm)
+            best = 1e30
+            t_start = time.perf_counter()
+            reps = 0
+            while reps < 3 or (time.perf_counter() - t_start < 10 and reps < 10):
+                t0 = time.perf_counter()
+                cwl.cpu_forward(cx, cprm)
+                best = min(best, time.perf_counter() - t0)
+                reps += 1
+        cpu_baseline = {"value": cwl.samples() / best, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{cwl.name}: batch {cwl.B} x {cwl.C}ch x {cwl.L} (1/4 of the workload), best of {reps}, oracle port = torch CPU ops + torchaudio lfilter as the reference calls them"}
+
+    if rank == 0:
+        launches = wl.launches
+        line = {"metric": "audio samples/sec (batch x chan x len)", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl.desc, "per_gpu_batch": wl.B, "channels": wl.C, "length": wl.L,
+                           "l2": f"inputs larger than L2 ({tree_bytes(x) / 2**20:.0f} MiB read + as much written per step vs 126 MiB L2)",
+                           "parallelism": f"batch shard x{world}, no collective on the data path"},
+                "clocks": clocks, "e2e": e2e,
+                "gpu_launches": (launches * args.steps * world) if launches else None,
+                "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

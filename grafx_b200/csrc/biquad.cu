@@ -8,8 +8,9 @@
 //   v[n] = b0 u[n] + b1 u[n-1] + b2 u[n-2];   y[n] = v[n] - a1 y[n-1] - a2 y[n-2];   zero initial state.
 //
 // Algorithm.  A row is cut into tiles of NT*S samples; a tile is staged in shared memory
-// (cp.async, XOR-swizzled 128-byte rows) so that thread t owns the S contiguous samples
-// [t*S, (t+1)*S) in registers.  Per section:
+// (cp.async, XOR-swizzled 128-byte rows, double buffered: the next tile streams in while this one
+// is computed) so that thread t owns the S contiguous samples [t*S, (t+1)*S) in registers.
+// Per section:
 //   1. feed-forward part in place (needs the two samples before the chunk: the neighbour's state);
 //   2. zero-state recursion over the chunk -> end state z_t (two values);
 //   3. the true state at each chunk start is s_{t+1} = M s_t + z_t with M = A^S, A = [[-a1,-a2],[1,0]]:
@@ -17,19 +18,21 @@
 //      incoming state taken from the previous tile of the row (ordered chain, see common.cuh);
 //   4. the recursion is re-run from the true state -- this pass is arithmetically the sequential
 //      DF-I loop, so rounding differs from the reference only through the carried state.
-// Powers M^l (l = 0..32) are computed per tile in double precision by one warp per section.
+// The normalised coefficients and the powers M^l (l = 0..32) of every (coefficient row, section)
+// are produced once per call in double precision by a small prologue kernel (36 x 4 words each)
+// and travel to shared memory with the tile.
 // HBM traffic: x read once, y written once (8 B/sample fp32) + 2K words of state per tile.
 #include "common.cuh"
-#include "../../include/grafx_b200.h"
 
 namespace gfx {
+
+constexpr int TAB_ENTRIES = 36;  // per (coef row, section): 33 matrices, [33] = (b0,b1,b2,-a1), [34] = (-a2,..)
 
 template <typename T>
 struct CascadeParams {
     const T* x;
     T* y;
-    const T* Bs;
-    const T* As;
+    const T* tables;  // [coef rows][K][36][4]
     int batch, c_sig, c_filt, c_out, K;
     long long L;
     int rows, tiles;
@@ -40,11 +43,6 @@ struct CascadeParams {
     int aligned;  // 1: x/y rows are 16-byte aligned (vector path)
 };
 
-template <typename T>
-struct Mat2 {
-    T m00, m01, m10, m11;
-};
-
 __device__ __forceinline__ void mat2_mul(const double a[4], const double b[4], double c[4]) {
     c[0] = a[0] * b[0] + a[1] * b[2];
     c[1] = a[0] * b[1] + a[1] * b[3];
@@ -52,41 +50,81 @@ __device__ __forceinline__ void mat2_mul(const double a[4], const double b[4], d
     c[3] = a[2] * b[1] + a[3] * b[3];
 }
 
-template <typename T, int NT>
-__global__ void __launch_bounds__(NT) biquad_cascade_kernel(const CascadeParams<T> p) {
+// ---- prologue: one warp per (coefficient row, section)
+template <typename T>
+__global__ void __launch_bounds__(128) cascade_tables_kernel(const T* __restrict__ Bs, const T* __restrict__ As,
+                                                             T* __restrict__ tables, int n_sections) {
+    constexpr int S = 128 / (int)sizeof(T);
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_sections) return;
+    const T* bp = Bs + (size_t)w * 3;
+    const T* ap = As + (size_t)w * 3;
+    const T a0 = ap[0];
+    const T nb0 = bp[0] / a0, nb1 = bp[1] / a0, nb2 = bp[2] / a0;
+    const T na1 = ap[1] / a0, na2 = ap[2] / a0;
+    double base[4] = {-(double)na1, -(double)na2, 1.0, 0.0}, tmp[4];
+#pragma unroll 1
+    for (int sq = 1; sq < S; sq <<= 1) {  // M = A^S
+        mat2_mul(base, base, tmp);
+        base[0] = tmp[0]; base[1] = tmp[1]; base[2] = tmp[2]; base[3] = tmp[3];
+    }
+    double res[4] = {1.0, 0.0, 0.0, 1.0};  // lane l -> M^l
+#pragma unroll 1
+    for (int bit = 0; bit < 5; ++bit) {
+        if ((lane >> bit) & 1) {
+            mat2_mul(res, base, tmp);
+            res[0] = tmp[0]; res[1] = tmp[1]; res[2] = tmp[2]; res[3] = tmp[3];
+        }
+        mat2_mul(base, base, tmp);
+        base[0] = tmp[0]; base[1] = tmp[1]; base[2] = tmp[2]; base[3] = tmp[3];
+    }
+    T* out = tables + (size_t)w * TAB_ENTRIES * 4;
+    out[lane * 4 + 0] = (T)res[0]; out[lane * 4 + 1] = (T)res[1];
+    out[lane * 4 + 2] = (T)res[2]; out[lane * 4 + 3] = (T)res[3];
+    if (lane == 0) {
+        out[32 * 4 + 0] = (T)base[0]; out[32 * 4 + 1] = (T)base[1];
+        out[32 * 4 + 2] = (T)base[2]; out[32 * 4 + 3] = (T)base[3];
+        out[33 * 4 + 0] = nb0; out[33 * 4 + 1] = nb1; out[33 * 4 + 2] = nb2; out[33 * 4 + 3] = -na1;
+        out[34 * 4 + 0] = -na2; out[34 * 4 + 1] = T(0); out[34 * 4 + 2] = T(0); out[34 * 4 + 3] = T(0);
+        out[35 * 4 + 0] = T(0); out[35 * 4 + 1] = T(0); out[35 * 4 + 2] = T(0); out[35 * 4 + 3] = T(0);
+    }
+}
+
+template <typename T>
+struct Mat2 {
+    T m00, m01, m10, m11;
+};
+
+template <typename T, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) biquad_cascade_kernel(const CascadeParams<T> p) {
     constexpr int S = 128 / (int)sizeof(T);   // samples per thread (32 fp32 / 16 fp64)
     constexpr int PER = 16 / (int)sizeof(T);  // samples per 16-byte unit
     constexpr int TILE = NT * S;
     constexpr int NW = NT / 32;
+    constexpr int TAB_UNITS = TAB_ENTRIES * 4 * (int)sizeof(T) / 16;  // 16-byte units per (row, section)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint4* tile4 = reinterpret_cast<uint4*>(smem_raw);            // NT*8 units
-    T* tile = reinterpret_cast<T*>(smem_raw);
-    T* coef = reinterpret_cast<T*>(smem_raw + (size_t)NT * 128);  // [K][8] (5 used)
-    Mat2<T>* ptab = reinterpret_cast<Mat2<T>*>(coef + (size_t)p.K * 8);  // [K][33]
-    T* s_in = reinterpret_cast<T*>(ptab + (size_t)p.K * 33);      // [K][2]
-    T* wtot = s_in + (size_t)p.K * 2;                             // [2][NW][2]
-    __shared__ unsigned int sh_item;
+    const int K = p.K;
+    const size_t tab_bytes = (size_t)K * TAB_UNITS * 16;
+    const size_t stage_bytes = (size_t)NT * 128 + tab_bytes + 16;  // tile | tables | 2 history samples
+    T* s_in = reinterpret_cast<T*>(smem_raw + 2 * stage_bytes);   // [K][2]
+    T* wtot = s_in + (size_t)K * 2;                                 // [2][NW][2]
+    __shared__ unsigned int sh_item[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = p.K;
 
-    for (;;) {
-        __syncthreads();  // previous tile fully stored / sh_item consumed
-        if (tid == 0) sh_item = take_ticket(p.ticket, p.n_items + gridDim.x - 1);
-        __syncthreads();
-        const unsigned int item = sh_item;
-        if (item >= p.n_items) break;
+    // issues the asynchronous loads of one work item into stage `st`
+    auto prefetch = [&](unsigned int item, int st) {
+        unsigned char* base = smem_raw + (size_t)st * stage_bytes;
+        uint4* tile4 = reinterpret_cast<uint4*>(base);
         const int t_idx = (int)(item / (unsigned)p.rows);
         const int row = (int)(item - (unsigned)t_idx * (unsigned)p.rows);
         const int b = row / p.c_out, c = row - b * p.c_out;
         const T* xr = p.x + ((size_t)b * p.c_sig + (p.c_sig == 1 ? 0 : c)) * (size_t)p.L;
-        T* yr = p.y + (size_t)row * (size_t)p.L;
         const size_t crow = (size_t)b * p.c_filt + (p.c_filt == 1 ? 0 : c);
         const long long t0 = (long long)t_idx * TILE;
-        const long long remain = p.L - t0;  // > 0
-
-        // ---- stage the input tile (zero padded past L)
+        const long long remain = p.L - t0;
         if (p.aligned) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -97,51 +135,53 @@ __global__ void __launch_bounds__(NT) biquad_cascade_kernel(const CascadeParams<
                 const T* src = src_bytes > 0 ? xr + t0 + pos : xr;
                 cp_async16(&tile4[swz_unit(g >> 3, g & 7)], src, src_bytes);
             }
-            cp_async_commit();
         } else {
+            T* tile = reinterpret_cast<T*>(base);
             for (int i = tid; i < TILE; i += NT) {
                 const T val = (i < remain) ? xr[t0 + i] : T(0);
                 const int r = i / S, n = i - r * S;
                 tile[(size_t)swz_unit(r, n / PER) * PER + (n % PER)] = val;
             }
         }
-
-        // ---- per-section constants: normalised coefficients and the powers of M = A^S
-        for (int k = warp; k < K; k += NW) {
-            const T* bp = p.Bs + (crow * K + k) * 3;
-            const T* ap = p.As + (crow * K + k) * 3;
-            const T a0 = ap[0];
-            const T nb0 = bp[0] / a0, nb1 = bp[1] / a0, nb2 = bp[2] / a0;
-            const T na1 = ap[1] / a0, na2 = ap[2] / a0;
-            if (lane == 0) {
-                T* ck = coef + (size_t)k * 8;
-                ck[0] = nb0; ck[1] = nb1; ck[2] = nb2; ck[3] = na1; ck[4] = na2;
-            }
-            double base[4] = {-(double)na1, -(double)na2, 1.0, 0.0}, tmp[4];
-            // M = A^S  (S = 2^5 or 2^4)
-#pragma unroll 1
-            for (int sq = 1; sq < S; sq <<= 1) {
-                mat2_mul(base, base, tmp);
-                base[0] = tmp[0]; base[1] = tmp[1]; base[2] = tmp[2]; base[3] = tmp[3];
-            }
-            // lane l -> M^l by binary exponentiation; after 5 squarings base = M^32
-            double res[4] = {1.0, 0.0, 0.0, 1.0};
-#pragma unroll 1
-            for (int bit = 0; bit < 5; ++bit) {
-                if ((lane >> bit) & 1) {
-                    mat2_mul(res, base, tmp);
-                    res[0] = tmp[0]; res[1] = tmp[1]; res[2] = tmp[2]; res[3] = tmp[3];
-                }
-                mat2_mul(base, base, tmp);
-                base[0] = tmp[0]; base[1] = tmp[1]; base[2] = tmp[2]; base[3] = tmp[3];
-            }
-            Mat2<T>* pk = ptab + (size_t)k * 33;
-            pk[lane] = Mat2<T>{(T)res[0], (T)res[1], (T)res[2], (T)res[3]};
-            if (lane == 0) pk[32] = Mat2<T>{(T)base[0], (T)base[1], (T)base[2], (T)base[3]};
+        const unsigned char* tsrc = reinterpret_cast<const unsigned char*>(p.tables + crow * K * TAB_ENTRIES * 4);
+        unsigned char* tdst = base + (size_t)NT * 128;
+        for (int u = tid; u < K * TAB_UNITS; u += NT) cp_async16(tdst + (size_t)u * 16, tsrc + (size_t)u * 16, 16);
+        if (tid < 2) {
+            // the two input samples before the tile (needed by thread 0 only)
+            T* hist = reinterpret_cast<T*>(base + (size_t)NT * 128 + tab_bytes);
+            if (t_idx > 0) cp_async_small<(int)sizeof(T)>(hist + tid, xr + t0 - 1 - tid);
+            else hist[tid] = T(0);
         }
+    };
 
-        if (p.aligned) cp_async_wait<0>();
+    if (tid == 0) sh_item[0] = take_ticket(p.ticket, 0xffffffffu);
+    __syncthreads();
+    unsigned int item = sh_item[0];
+    if (item < p.n_items) prefetch(item, 0);
+    cp_async_commit();
+    int st = 0;
+
+    while (item < p.n_items) {
+        // next ticket + its loads go out before this tile is touched
+        if (tid == 0) sh_item[(st ^ 1) & 1] = take_ticket(p.ticket, 0xffffffffu);
+        __syncthreads();  // (also: every thread is done with stage st^1 of the previous iteration)
+        const unsigned int next_item = sh_item[(st ^ 1) & 1];
+        if (next_item < p.n_items) prefetch(next_item, st ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
+
+        unsigned char* base = smem_raw + (size_t)st * stage_bytes;
+        uint4* tile4 = reinterpret_cast<uint4*>(base);
+        T* tile = reinterpret_cast<T*>(base);
+        const Mat2<T>* tab = reinterpret_cast<const Mat2<T>*>(base + (size_t)NT * 128);
+        const T* hist = reinterpret_cast<const T*>(base + (size_t)NT * 128 + tab_bytes);
+
+        const int t_idx = (int)(item / (unsigned)p.rows);
+        const int row = (int)(item - (unsigned)t_idx * (unsigned)p.rows);
+        T* yr = p.y + (size_t)row * (size_t)p.L;
+        const long long t0 = (long long)t_idx * TILE;
+        const long long remain = p.L - t0;  // > 0
 
         // ---- own chunk -> registers
         T v[S];
@@ -159,14 +199,14 @@ __global__ void __launch_bounds__(NT) biquad_cascade_kernel(const CascadeParams<
             um1 = tile[base_idx + PER - 1];
             um2 = tile[base_idx + PER - 2];
         } else {
-            um1 = (t_idx > 0) ? xr[t0 - 1] : T(0);
-            um2 = (t_idx > 0) ? xr[t0 - 2] : T(0);
+            um1 = hist[0];
+            um2 = hist[1];
         }
 
         for (int k = 0; k < K; ++k) {
-            const T* ck = coef + (size_t)k * 8;
-            const T b0 = ck[0], b1 = ck[1], b2 = ck[2], na1 = -ck[3], na2 = -ck[4];
-            const Mat2<T>* pk = ptab + (size_t)k * 33;
+            const Mat2<T>* pk = tab + (size_t)k * TAB_ENTRIES;
+            const Mat2<T> c0 = pk[33];
+            const T b0 = c0.m00, b1 = c0.m01, b2 = c0.m10, na1 = c0.m11, na2 = pk[34].m00;
 
             // 1. feed-forward part, in place (descending so the taps are still inputs)
 #pragma unroll
@@ -280,19 +320,24 @@ __global__ void __launch_bounds__(NT) biquad_cascade_kernel(const CascadeParams<
                 yr[t0 + i] = tile[(size_t)swz_unit(r, n / PER) * PER + (n % PER)];
             }
         }
+        item = next_item;
+        st ^= 1;
     }
+    cp_async_wait<0>();
 }
 
 template <typename T>
 static size_t cascade_smem_bytes(int NT, int K) {
-    return (size_t)NT * 128 + (size_t)K * 8 * sizeof(T) + (size_t)K * 33 * 4 * sizeof(T) +
-           (size_t)K * 2 * sizeof(T) + (size_t)2 * (NT / 32) * 2 * sizeof(T) + 64;
+    const size_t stage = (size_t)NT * 128 + (size_t)K * TAB_ENTRIES * 4 * sizeof(T) + 16;
+    return 2 * stage + (size_t)K * 2 * sizeof(T) + (size_t)2 * (NT / 32) * 2 * sizeof(T) + 64;
 }
 
-static size_t cascade_workspace_bytes(int rows, int K, size_t elem) {
-    // [ticket | pad to 256] [flags: rows ints, padded to 256] [state: rows*2K elems]
-    size_t flags = ((size_t)rows * sizeof(int) + 255) / 256 * 256;
-    return 256 + flags + (size_t)rows * 2 * K * elem;
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+static size_t cascade_workspace_bytes(int rows, int coef_rows, int K, size_t elem) {
+    // [ticket | pad to 256] [flags: rows ints] [state: rows*2K elems] [tables: coef_rows*K*36*4 elems]
+    return 256 + align256((size_t)rows * sizeof(int)) + align256((size_t)rows * 2 * K * elem) +
+           (size_t)coef_rows * K * TAB_ENTRIES * 4 * elem;
 }
 
 template <typename T>
@@ -301,6 +346,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
                           cudaStream_t stream) {
     constexpr int NT = 256;
     constexpr int S = 128 / (int)sizeof(T);
+    constexpr int MINB = sizeof(T) == 4 ? 3 : 1;
     if (!x || !y || !Bs || !As) return GFX_ERR_INVALID;
     if (batch <= 0 || c_sig <= 0 || c_filt <= 0 || K <= 0 || L <= 0) return GFX_ERR_INVALID;
     if (c_sig != c_filt && c_sig != 1 && c_filt != 1) return GFX_ERR_INVALID;
@@ -310,25 +356,32 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     const long long tiles_ll = (L + (long long)NT * S - 1) / ((long long)NT * S);
     if (rows_ll * tiles_ll > 0x7fff0000LL) return GFX_ERR_UNSUPPORTED;
     const int rows = (int)rows_ll, tiles = (int)tiles_ll;
-    const size_t need = cascade_workspace_bytes(rows, K, sizeof(T));
+    const int coef_rows = batch * c_filt;
+    const size_t need = cascade_workspace_bytes(rows, coef_rows, K, sizeof(T));
     if (!ws || ws_bytes < need) return GFX_ERR_WORKSPACE;
 
     CascadeParams<T> p;
-    p.x = x; p.y = y; p.Bs = Bs; p.As = As;
+    p.x = x; p.y = y;
     p.batch = batch; p.c_sig = c_sig; p.c_filt = c_filt; p.c_out = c_out; p.K = K;
     p.L = L; p.rows = rows; p.tiles = tiles;
     p.n_items = (unsigned)(rows * (long long)tiles);
     unsigned char* w = (unsigned char*)ws;
     p.ticket = (unsigned int*)w;
     p.flags = (int*)(w + 256);
-    const size_t flags_bytes = ((size_t)rows * sizeof(int) + 255) / 256 * 256;
+    const size_t flags_bytes = align256((size_t)rows * sizeof(int));
     p.state = (T*)(w + 256 + flags_bytes);
+    T* tables = (T*)(w + 256 + flags_bytes + align256((size_t)rows * 2 * K * sizeof(T)));
+    p.tables = tables;
     p.aligned = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && ((L * (long long)sizeof(T)) % 16 == 0);
 
     GFX_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256 + flags_bytes, stream));
+    const int n_sections = coef_rows * K;
+    cascade_tables_kernel<T><<<(n_sections * 32 + 127) / 128, 128, 0, stream>>>(Bs, As, tables, n_sections);
+    GFX_CUDA_CHECK(cudaGetLastError());
 
     const size_t smem = cascade_smem_bytes<T>(NT, K);
-    auto kern = biquad_cascade_kernel<T, NT>;
+    if (smem > (size_t)device_info().max_smem_optin) return GFX_ERR_UNSUPPORTED;
+    auto kern = biquad_cascade_kernel<T, NT, MINB>;
     static size_t configured_smem[2] = {0, 0};
     const int slot = sizeof(T) == 4 ? 0 : 1;
     if (smem > configured_smem[slot]) {
@@ -351,7 +404,7 @@ extern "C" {
 
 size_t gfx_biquad_cascade_workspace_bytes(int batch, int c_sig, int c_filt, int K, int elem_size) {
     const int c_out = c_sig > c_filt ? c_sig : c_filt;
-    return gfx::cascade_workspace_bytes(batch * c_out, K, (size_t)elem_size);
+    return gfx::cascade_workspace_bytes(batch * c_out, batch * c_filt, K, (size_t)elem_size);
 }
 
 int gfx_biquad_cascade_f32(const float* x, float* y, const float* Bs, const float* As, int batch,

@@ -35,6 +35,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(src_bytes));
 }
+// 4- or 8-byte async copy (for the odd scalar that must travel with a tile)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gmem_src) {
+    static_assert(BYTES == 4 || BYTES == 8, "cp.async.ca supports 4, 8, 16 bytes");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -120,10 +120,13 @@ __global__ void __launch_bounds__(RV_NT) reverb_ir_kernel(const ReverbParams p) 
             }
         }
         __syncwarp();
-        // 3. three inverse FFT-64 (decimation in time, radix 4), 16 threads = 16 butterflies per pass
-        if (m0 + g < p.frames) {
+        // 3. three inverse FFT-64 (decimation in time, radix 4), 16 threads = 16 butterflies per pass.
+        // NB every lane of the warp reaches each __syncwarp (the two frame groups of a warp may differ
+        // in validity at the end of the frame axis).
+        const bool fvalid = (m0 + g < p.frames);
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
+        for (int pass = 0; pass < 3; ++pass) {
+            if (fvalid) {
                 const int ST = 1 << (2 * pass);              // 1, 4, 16
                 const int TWS = RV_NFFT / (4 * ST);          // 384/M : 96, 24, 6
                 const int j = tau & (ST - 1);
@@ -149,8 +152,10 @@ __global__ void __launch_bounds__(RV_NT) reverb_ir_kernel(const ReverbParams p) 
                     re[i0 + 2 * ST] = s02r - s13r; im[i0 + 2 * ST] = s02i - s13i;
                     re[i0 + 3 * ST] = d02r + d13i; im[i0 + 3 * ST] = d02i - d13r;
                 }
-                __syncwarp();
             }
+            __syncwarp();
+        }
+        if (fvalid) {
             // 4. interleave residues, scale, window
             for (int n = tau; n < RV_NFFT; n += 16) {
                 const int q = n / 6, r = n - 6 * q;

@@ -1,0 +1,144 @@
+"""render_grafx -- drop-in for grafx.render.graph.render_grafx (render/graph.py:16-177) with the
+tensor primitives of render/core.py (:6-140) folded in.
+
+Same signature and return value: `(output_signals, intermediates_list, signal_buffer)`; accepts
+3-D `[|V0|, C, L]` or 4-D `[B, |V0|, C, L]` sources and any RenderData-like plan (the reference's
+own objects work: only attributes are read).  Forward only: `parameters_grad` /
+`input_signal_grad` are accepted for compatibility; nothing is recorded for autograd.
+
+What runs where: processors are the CUDA kernels of this package; node-axis aggregation
+(`sum` / `scatter`) is csrc/elementwise.cu:node_sum_kernel reading and writing slices of the
+signal buffer in place; slice reads are views; the remaining copies are torch device copies.
+"""
+from __future__ import annotations
+
+from typing import Mapping
+
+import torch
+import torch.nn as nn
+
+from .. import functional as F_
+
+UTILITY_TYPES = ("in", "out", "mix")  # grafx/data/configs.py
+
+
+def _read(x, access, dim):
+    """read_tensor_or_tensor_dict (render/core.py:36-73)."""
+    if isinstance(x, torch.Tensor):
+        if access.method == "slice":
+            return x.narrow(dim, access.idx[0], access.idx[1] - access.idx[0])
+        if access.method == "index":
+            return x.index_select(dim, access.idx.to(x.device))
+        raise Exception(f"The provided read method is not available: {access.method}.")
+    if isinstance(x, (dict, nn.ParameterDict, nn.ModuleDict)):
+        return {k: _read(v, access, dim) for k, v in x.items()}
+    if isinstance(x, list):
+        return x[access.idx[0]]
+    raise TypeError(type(x))
+
+
+def _map_tensors(x, fn):
+    if isinstance(x, torch.Tensor):
+        return fn(x)
+    return {k: _map_tensors(v, fn) for k, v in x.items()}
+
+
+def _flatten2(x):
+    return x.reshape(-1, *x.shape[2:])
+
+
+def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_parameters: Mapping, render_data,
+                 common_parameters=None, parameters_grad=True, input_signal_grad=False):
+    method = render_data.method
+    ndim = input_signals.ndim
+    if ndim == 3:
+        node_dim, batch_size = 0, None
+        num_sources, channels, audio_len = input_signals.shape
+    elif ndim == 4:
+        node_dim = 1
+        batch_size, num_sources, channels, audio_len = input_signals.shape
+        expand = lambda t: t.detach().unsqueeze(0).expand(batch_size, *t.shape)  # noqa: E731
+        per_type_parameters = _map_tensors(per_type_parameters, expand)
+        if common_parameters is not None:
+            common_parameters = _map_tensors(common_parameters, expand)
+    else:
+        raise Exception(f"input_signal has shape of {input_signals.shape} ({ndim} ndims), which is not 3 or 4 dims.")
+    post = _flatten2 if ndim == 4 else (lambda t: t)
+    input_signals = input_signals.detach()
+
+    # create_signal_buffer (render/core.py:6-33)
+    one_by_one = method == "one-by-one"
+    if one_by_one:
+        assert ndim == 3, "the one-by-one list buffer has no batch axis upstream either"
+        signal_buffer = [x[None] for x in input_signals] + [None] * (render_data.num_nodes - num_sources)
+    else:
+        shape = (render_data.num_nodes, channels, audio_len) if ndim == 3 else (batch_size, render_data.num_nodes, channels, audio_len)
+        signal_buffer = torch.empty(shape, device=input_signals.device, dtype=torch.float32)
+        signal_buffer.narrow(node_dim, 0, num_sources).copy_(input_signals)
+
+    intermediates_list = []
+    output_signals = None
+    for i in range(1, int(render_data.max_order) + 1):
+        it = render_data.iter_list[i]
+        node_type = it.node_type
+        is_proc = node_type in processors
+        if not is_proc and node_type not in UTILITY_TYPES:
+            raise Exception(f"Wrong node type given: {node_type}")
+        dest = it.dest_write
+        direct_dest = None
+        if (not one_by_one) and (not is_proc) and len(it.source_reads) == 1 and dest.method == "slice":
+            # utility node: aggregate straight into the destination slice of the buffer
+            direct_dest = signal_buffer.narrow(node_dim, dest.idx[0], dest.idx[1] - dest.idx[0])
+
+        inputs = []
+        wrote_direct = False
+        for read, agg in zip(it.source_reads, it.aggregations):
+            src = _read(signal_buffer, read, node_dim)
+            if agg.method == "sum":
+                out_view = direct_dest if (direct_dest is not None and direct_dest.shape[node_dim] == 1) else None
+                src = F_.node_sum(src, node_dim, None, 1, out=out_view)
+                wrote_direct = out_view is not None
+            elif agg.method == "scatter":
+                n_dst = int(agg.idx.max()) + 1
+                out_view = direct_dest if (direct_dest is not None and direct_dest.shape[node_dim] == n_dst) else None
+                src = F_.node_sum(src, node_dim, agg.idx, n_dst, out=out_view)
+                wrote_direct = out_view is not None
+            elif agg.method != "none":
+                raise Exception(f"The provided aggregation method is not available: {agg.method}.")
+            inputs.append(post(src))
+
+        if is_proc:
+            parameters = _map_tensors(_read(per_type_parameters[node_type], it.parameter_read, node_dim), post)
+            common_i = {}
+            if common_parameters is not None:
+                common_i = _map_tensors(_read(common_parameters, dest, node_dim), post)
+                if isinstance(common_i, torch.Tensor):
+                    common_i = {"parameter": common_i}
+            if isinstance(parameters, torch.Tensor):
+                parameters = {"parameter": parameters}
+            output = processors[node_type](*inputs, **parameters, **common_i)
+            if isinstance(output, tuple):
+                output_signals, intermediates = output
+                intermediates_list.append(intermediates)
+            else:
+                output_signals = output
+        else:
+            output_signals = inputs
+
+        if isinstance(output_signals, list):
+            output_signals = output_signals[0] if len(output_signals) == 1 else torch.stack(output_signals, -3).view(-1, channels, audio_len)
+        if ndim == 4:
+            output_signals = output_signals.view(batch_size, -1, channels, audio_len)
+
+        # inplace_write_tensor (render/core.py:80-98)
+        if one_by_one:
+            signal_buffer[dest.idx[0]] = output_signals
+        elif wrote_direct:
+            pass  # the aggregation kernel already wrote the slice; output_signals is that view
+        elif dest.method == "slice":
+            signal_buffer.narrow(node_dim, dest.idx[0], dest.idx[1] - dest.idx[0]).copy_(output_signals)
+        elif dest.method == "index":
+            signal_buffer.index_copy_(node_dim, dest.idx.to(signal_buffer.device), output_signals)
+        else:
+            raise Exception(f"The provided inplace write method is not available: {dest.method}.")
+    return output_signals, intermediates_list, signal_buffer

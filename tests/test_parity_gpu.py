@@ -316,3 +316,53 @@ def test_reverb_long_ir_vs_oracle(ir_len):
     y = proc(x.cuda(), **{k: v.cuda() for k, v in prm.items()}).cpu()
     y_ref = O.stft_masked_noise_reverb(x, **prm, ir_len=ir_len)
     assert_close(y, y_ref, f"reverb{ir_len}")
+
+
+# ------------------------------------------------------------------ graph render
+@pytest.mark.parametrize("tag", ["3d", "4d"])
+def test_render_vs_reference_golden(tag):
+    """3-track in->eq->compressor->reverb->out graph rendered by the reference's render_grafx
+    (tests/graph/test_render.py:13-37 with real processors): output AND the whole signal buffer."""
+    import json
+    import grafx_b200.processors as P
+    from grafx_b200.render import mixing_console_plan, plan_from_dict, render_grafx
+
+    z = np.load(os.path.join(GOLDEN, f"render_mix3_{tag}.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    kws = meta["kwargs"]
+    procs = {"eq": P.ParametricEqualizer(**kws["eq"]).cuda(), "compressor": P.Compressor(**kws["compressor"]).cuda(),
+             "reverb": P.STFTMaskedNoiseReverb(**kws["reverb"]).cuda()}
+    params = {}
+    for k in z.files:
+        if k.startswith("p_"):
+            t, name = k[2:].split("__")
+            params.setdefault(t, {})[name] = torch.from_numpy(z[k]).cuda()
+    x = torch.from_numpy(z["x"]).cuda()
+    for rd in (plan_from_dict(meta["plan"]), mixing_console_plan(3, ["eq", "compressor", "reverb"])):
+        out, inter, buf = render_grafx(procs, x, params, rd, parameters_grad=False)
+        assert inter == []
+        assert_close(out.cpu(), torch.from_numpy(z["y"]), f"render-{tag}")
+        assert_close(buf.cpu(), torch.from_numpy(z["buffer"]), f"render-buffer-{tag}")
+
+
+def test_render_scatter_and_index_paths():
+    """Irregular plan: index reads, scatter aggregation into two buses, index write."""
+    from grafx_b200.render import render_grafx
+    from grafx_b200.render.plan import RenderData, _AggregationData, _SingleRenderData, _TensorAccessData
+    import grafx_b200.processors as P
+
+    torch.manual_seed(11)
+    x = torch.randn(2, 4, 2, 3000, device="cuda")  # B=2, 4 sources
+    gate = P.NoiseGate().cuda()
+    prm = {"gate": {k: torch.randn(4, v, device="cuda") for k, v in gate.parameter_size().items()}}
+    idx = torch.tensor([2, 0, 3, 1])
+    rd = RenderData("beam", 10, 2, True, [
+        _SingleRenderData("in", [_TensorAccessData("none", ())], [_AggregationData("none")], _TensorAccessData("slice", (0, 4)), _TensorAccessData("slice", (0, 4))),
+        _SingleRenderData("gate", [_TensorAccessData("index", idx)], [_AggregationData("none")], _TensorAccessData("index", idx), _TensorAccessData("slice", (4, 8))),
+        _SingleRenderData("mix", [_TensorAccessData("slice", (4, 8))], [_AggregationData("scatter", torch.tensor([0, 1, 1, 0]))], _TensorAccessData("slice", (0, 2)), _TensorAccessData("slice", (8, 10))),
+    ])
+    out, _, buf = render_grafx({"gate": gate}, x, prm, rd)
+    g = gate(x[:, idx].reshape(8, 2, 3000), **{k: v[idx].unsqueeze(0).expand(2, 4, -1).reshape(8, -1) for k, v in prm["gate"].items()}).view(2, 4, 2, 3000)
+    ref = torch.stack([g[:, 0] + g[:, 3], g[:, 1] + g[:, 2]], 1)
+    assert torch.allclose(out, ref, atol=1e-5)
+    assert torch.equal(buf[:, 8:10], out)
