@@ -18,10 +18,13 @@ LIB = os.path.join(LIBDIR, "libgrafx_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-fmad=true",
     "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden",
     "-cudart", "static",
 ]
+
+
+# coefficient design must round like the separate torch ops it replaces: no FMA contraction there
+PER_FILE_FLAGS = {"design.cu": ["-fmad=false"]}
 
 
 def _nvcc() -> str:
@@ -56,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *PER_FILE_FLAGS.get(os.path.basename(src), ["-fmad=true"]), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

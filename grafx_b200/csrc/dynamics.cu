@@ -247,8 +247,8 @@ __device__ __forceinline__ float knee_log_gain(int kind, int knee, float G, floa
     }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) dynamics_kernel(const DynParams p) {
+template <int NT, bool MULTI>
+__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 8)) dynamics_kernel(const DynParams p) {
     constexpr int S = 32, TILE = NT * S, NW = NT / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DynCtx<NT> cx;
@@ -304,10 +304,12 @@ __global__ void __launch_bounds__(NT) dynamics_kernel(const DynParams p) {
         }
         __syncthreads();
 
-        float G[S];   // cumulative linear gain of the stages done so far
-        float u[S];   // working chunk
+        float G[MULTI ? S : 1];   // cumulative linear gain of the stages done so far (chains only)
+        float u[S];               // working chunk
+        if constexpr (MULTI) {
 #pragma unroll
-        for (int i = 0; i < S; ++i) G[i] = 1.f;
+            for (int i = 0; i < S; ++i) G[i] = 1.f;
+        }
 
         for (int d = 0; d < p.n_stages; ++d) {
             const StageDesc& sd = p.st[d];
@@ -324,8 +326,13 @@ __global__ void __launch_bounds__(NT) dynamics_kernel(const DynParams p) {
                     u[4 * q + 3] = fmaf(v.w, v.w, u[4 * q + 3]);
                 }
             }
+            if constexpr (MULTI) {
 #pragma unroll
-            for (int i = 0; i < S; ++i) u[i] = u[i] * inv_c * (G[i] * G[i]);
+                for (int i = 0; i < S; ++i) u[i] = u[i] * inv_c * (G[i] * G[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < S; ++i) u[i] = u[i] * inv_c;
+            }
 
             if (sd.pre.kind == 1) {
                 if (d == 0) {
@@ -375,8 +382,10 @@ __global__ void __launch_bounds__(NT) dynamics_kernel(const DynParams p) {
                     for (int i = 0; i < S; ++i) u[i] = expf(u[i]);
                 }
             }
+            if constexpr (MULTI) {
 #pragma unroll
-            for (int i = 0; i < S; ++i) G[i] *= u[i];
+                for (int i = 0; i < S; ++i) G[i] *= u[i];
+            }
         }
         if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles && cx.have_state) chain_publish(p.flags + cx.row, cx.t_idx + 1);
 
@@ -386,7 +395,11 @@ __global__ void __launch_bounds__(NT) dynamics_kernel(const DynParams p) {
             for (int q = 0; q < 8; ++q) {
                 float4* pv = &cx.xs4[(size_t)c * NT * 8 + swz_unit(cx.tid, q)];
                 float4 v = *pv;
-                v.x *= G[4 * q]; v.y *= G[4 * q + 1]; v.z *= G[4 * q + 2]; v.w *= G[4 * q + 3];
+                if constexpr (MULTI) {
+                    v.x *= G[4 * q]; v.y *= G[4 * q + 1]; v.z *= G[4 * q + 2]; v.w *= G[4 * q + 3];
+                } else {
+                    v.x *= u[4 * q]; v.y *= u[4 * q + 1]; v.z *= u[4 * q + 2]; v.w *= u[4 * q + 3];
+                }
                 *pv = v;
             }
         }
@@ -424,11 +437,11 @@ static size_t dyn_workspace_bytes(int batch, int n_stages) {
     return 256 + flags + (size_t)batch * 2 * n_stages * sizeof(float);
 }
 
-template <int NT>
+template <int NT, bool MULTI>
 static int launch_dynamics(DynParams& p, cudaStream_t stream) {
     const size_t smem = dyn_smem_bytes(NT, p.C);
     if (smem > (size_t)device_info().max_smem_optin) return GFX_ERR_UNSUPPORTED;
-    auto kern = dynamics_kernel<NT>;
+    auto kern = dynamics_kernel<NT, MULTI>;
     static size_t configured = 0;
     if (smem > configured) {
         GFX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -497,7 +510,9 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
     p.iir_len = iir_len;
     p.aligned = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (L % 4 == 0);
     GFX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256 + flags_bytes, (cudaStream_t)stream));
-    return any_ballistics ? launch_dynamics<64>(p, (cudaStream_t)stream) : launch_dynamics<256>(p, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_stages > 1) return any_ballistics ? launch_dynamics<64, true>(p, st) : launch_dynamics<256, true>(p, st);
+    return any_ballistics ? launch_dynamics<64, false>(p, st) : launch_dynamics<256, false>(p, st);
 }
 
 }  // extern "C"

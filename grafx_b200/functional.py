@@ -295,3 +295,29 @@ def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_
         raise NotImplementedError("reverb IR synthesis supports n_fft=384, hop_length=192 only")
     _cabi.check(code, "gfx_reverb_ir_f32")
     return ir
+
+
+DESIGN_FAMILY = {"peq": 0, "peaking": 1, "lowshelf": 2, "highshelf": 3, "lowpass": 4, "highpass": 5, "bandpass": 6,
+                 "bandreject": 7, "allpass": 8, "stable": 9, "svf": 10}
+
+
+def biquad_design(family: str, *params: torch.Tensor, flags: int = 0):
+    """Parameter activations -> (Bs, As) in one launch (reference: the coefficient designers of
+    processors/filter.py and eq.py:300-314; same formulas as processors/design.py, which stays as
+    the PyTorch statement of them).  All parameter tensors share the shape [..., K] (for "stable"
+    the first one is [..., K, 3]); returns Bs, As of shape [..., K, 3]."""
+    fam = DESIGN_FAMILY[family]
+    ref = params[1]
+    _cabi.require_cuda(*[t for t in params if t is not None])
+    K = ref.shape[-1]
+    n_rows = ref.numel() // K
+    ps = [None if t is None else _prep(t, torch.float32) for t in params]
+    ps += [None] * (5 - len(ps))
+    Bs = torch.empty(*ref.shape, 3, dtype=torch.float32, device=ref.device)
+    As = torch.empty_like(Bs)
+    if Bs.numel():
+        with torch.cuda.device(ref.device):
+            code = _cabi.lib().gfx_biquad_design_f32(fam, *[_cabi.ptr(t) for t in ps], Bs.data_ptr(), As.data_ptr(),
+                                                     n_rows, K, int(flags), _cabi.stream_ptr())
+        _cabi.check(code, "gfx_biquad_design_f32")
+    return Bs, As

@@ -105,9 +105,9 @@ def stable_biquad(Bs, A1_pre, A2_pre, A0=None, scale_by_a0=False):
 
 def state_variable(twoR, G, c_hp, c_bp, c_lp):
     g = torch.tan(0.5 * math.pi * torch.sigmoid(G))
-    r2 = F.softplus(twoR) / _LN2 + 1e-2
+    r2 = (1.0 / _LN2) * F.softplus(twoR) + 1e-2
     g2 = g * g
-    num = _taps(c_hp + c_bp * g + c_lp * g2, 2 * c_lp * g2 - 2 * c_hp, c_hp - c_bp * g + c_lp * g2)
+    num = _taps(c_hp + c_bp * g + c_lp * g2, -c_hp * 2 + c_lp * 2 * g2, c_hp - c_bp * g + c_lp * g2)
     den = _taps(1 + g2 + r2 * g, 2 * g2 - 2, 1 + g2 - r2 * g)
     return num, den
 

@@ -4,7 +4,6 @@ from __future__ import annotations
 import torch.nn as nn
 
 from .. import functional as F_
-from . import design
 from .core.iir import IIRFilter
 
 
@@ -22,7 +21,7 @@ class ParametricEqualizer(nn.Module):
         self.biquad = IIRFilter(order=2, **backend_kwargs)
 
     def forward(self, input_signals, w0, q_inv, log_gain):
-        Bs, As = design.parametric_eq(w0, q_inv, log_gain, self.use_shelving_filters)
+        Bs, As = F_.biquad_design("peq", w0, q_inv, log_gain, flags=int(self.use_shelving_filters))
         if self.processor_channel == "midside":
             return F_.ms_to_lr(self.biquad(F_.lr_to_ms(input_signals), Bs, As))
         return self.biquad(input_signals, Bs, As)

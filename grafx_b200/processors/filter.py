@@ -60,7 +60,8 @@ class BiquadFilter(_BiquadStack):
         self.normalized = normalized
 
     def forward(self, input_signals, Bs, A1_pre, A2_pre, A0=None):
-        num, den = design.stable_biquad(Bs, A1_pre, A2_pre, A0, scale_by_a0=self.normalized)
+        num, den = F_.biquad_design("stable", Bs, A1_pre, A2_pre, A0 if self.normalized else None,
+                                    flags=2 if self.normalized else 0)
         return self._run(input_signals, num, den)
 
     def parameter_size(self):
@@ -98,7 +99,7 @@ class StateVariableFilter(_BiquadStack):
         self.num_filters = num_filters
 
     def forward(self, input_signals, twoR, G, c_hp, c_bp, c_lp):
-        return self._run(input_signals, *design.state_variable(twoR, G, c_hp, c_bp, c_lp))
+        return self._run(input_signals, *F_.biquad_design("svf", twoR, G, c_hp, c_bp, c_lp))
 
     def parameter_size(self):
         return {k: self.num_filters for k in ("twoR", "G", "c_hp", "c_bp", "c_lp")}
@@ -113,7 +114,7 @@ class BaseParametricFilter(_BiquadStack):
         super().__init__(**backend_kwargs)
 
     def forward(self, input_signals, w0, q_inv):
-        return self._run(input_signals, *design.simple_filter(self.kind, w0, q_inv))
+        return self._run(input_signals, *F_.biquad_design(self.kind, w0, q_inv))
 
     def parameter_size(self):
         return {"w0": 1, "q_inv": 1}
@@ -149,7 +150,7 @@ class BaseParametricEqualizerFilter(_BiquadStack):
         self.num_filters = num_filters
 
     def forward(self, input_signals, w0, q_inv, log_gain):
-        return self._run(input_signals, *design.eq_band(self.kind, w0, q_inv, log_gain))
+        return self._run(input_signals, *F_.biquad_design(self.kind, w0, q_inv, log_gain))
 
     def parameter_size(self):
         return {k: self.num_filters for k in ("w0", "q_inv", "log_gain")}

@@ -60,6 +60,20 @@ GFX_API int gfx_biquad_cascade_f64(const double* x, double* y, const double* Bs,
                            int c_sig, int c_filt, int K, long long L, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ---- parameter activations -> biquad coefficients ----------------------------------------------
+ * Replaces the elementwise coefficient designers of processors/filter.py (:144-154 BiquadFilter,
+ * :303-338 StateVariableFilter, :373-383/:592-604 activations, :416-556 LP/HP/BP/BR/AP,
+ * :645-754 Peaking/LowShelf/HighShelf) and the band layout of ParametricEqualizer (eq.py:300-314)
+ * with one launch.  n_rows = product of the leading dims of the parameter tensors, each [n_rows, K].
+ * family: 0 parametric EQ (flags&1: low shelf / peaks / high shelf layout), 1 peaking, 2 low shelf,
+ * 3 high shelf (p0=w0, p1=q_inv, p2=log_gain); 4 low-pass, 5 high-pass, 6 band-pass, 7 band-reject,
+ * 8 all-pass (p0=w0, p1=q_inv); 9 stability-constrained direct form (p0=Bs[n_rows,K,3], p1=A1_pre,
+ * p2=A2_pre, p3=A0 used when flags&2); 10 state-variable (p0=twoR, p1=G, p2=c_hp, p3=c_bp, p4=c_lp).
+ * Output Bs, As [n_rows, K, 3]. */
+GFX_API int gfx_biquad_design_f32(int family, const float* p0, const float* p1, const float* p2, const float* p3,
+                                  const float* p4, float* Bs, float* As, int n_rows, int K, int flags,
+                                  void* stream);
+
 /* ---- stereo <-> mid/side -------------------------------------------------------------------
  * Replaces lr_to_ms / ms_to_lr (processors/core/midside.py:4-17).  x, y [batch, 2, L]:
  *   y[:,0] = (x[:,0] + x[:,1]) * mult,  y[:,1] = (x[:,0] - x[:,1]) * mult

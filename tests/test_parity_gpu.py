@@ -366,3 +366,27 @@ def test_render_scatter_and_index_paths():
     ref = torch.stack([g[:, 0] + g[:, 3], g[:, 1] + g[:, 2]], 1)
     assert torch.allclose(out, ref, atol=1e-5)
     assert torch.equal(buf[:, 8:10], out)
+
+
+def test_design_kernel_matches_torch_statement():
+    """The one-launch coefficient design against its PyTorch statement (processors/design.py)."""
+    import grafx_b200.functional as F_
+    from grafx_b200.processors import design as D
+
+    torch.manual_seed(9)
+    w0, q, g = (torch.randn(7, 2, 6, device="cuda") for _ in range(3))
+    for shelf in (True, False):
+        for a, b in zip(F_.biquad_design("peq", w0, q, g, flags=int(shelf)), D.parametric_eq(w0, q, g, shelf)):
+            assert torch.allclose(a, b, rtol=2e-6, atol=1e-6), (a - b).abs().max()
+    for kind in ("peaking", "lowshelf", "highshelf"):
+        for a, b in zip(F_.biquad_design(kind, w0, q, g), D.eq_band(kind, w0, q, g)):
+            assert torch.allclose(a, b, rtol=2e-6, atol=1e-6)
+    for kind in ("lowpass", "highpass", "bandpass", "bandreject", "allpass"):
+        for a, b in zip(F_.biquad_design(kind, w0, q), D.simple_filter(kind, w0, q)):
+            assert torch.allclose(a, b, rtol=2e-6, atol=1e-6)
+    Bs = torch.randn(7, 6, 3, device="cuda"); a1, a2, a0 = (torch.randn(7, 6, device="cuda") for _ in range(3))
+    for a, b in zip(F_.biquad_design("stable", Bs, a1, a2, a0, flags=2), D.stable_biquad(Bs, a1, a2, a0, True)):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-6)
+    p = [torch.randn(7, 6, device="cuda") for _ in range(5)]
+    for a, b in zip(F_.biquad_design("svf", *p), D.state_variable(*p)):
+        assert torch.allclose(a, b, rtol=5e-6, atol=1e-5)
