@@ -22,6 +22,8 @@
 // are produced once per call in double precision by a small prologue kernel (36 x 4 words each)
 // and travel to shared memory with the tile.
 // HBM traffic: x read once, y written once (8 B/sample fp32) + 2K words of state per tile.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gfx {
@@ -326,6 +328,272 @@ __global__ void __launch_bounds__(NT, MINB) biquad_cascade_kernel(const CascadeP
     cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 fast path: TWO chunks per thread, packed into the lanes of Blackwell's FFMA2 / FMUL2
+// (fma.rn.f32x2, __ffma2_rn): one issue slot does two FMAs, which frees the other issue slots of
+// the SMSP for the scan / staging instructions (measured on B200: FFMA and FFMA2 both peak at
+// ~122 FMA/clk/SM, FFMA2 with half the instructions -- tools/fma_peak.cu).
+// 128 threads; the tile is 256 rows of 32 samples; thread t owns rows t ("A", lane .x) and t+128
+// ("B", lane .y), i.e. samples [32t, 32t+32) and [4096+32t, ...).  The scan runs packed over both
+// halves; the B half starts from the state the A half ends with.
+// Packed values live in 64-bit registers end to end (inline PTX on .b64 operands): going through
+// float2 made ptxas re-pack the halves around every FFMA2 (28 IMAD.MOV per sample, profiles/).
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk_make(float lo, float hi) {
+    pk2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ pk2 pk_dup(float a) { return pk_make(a, a); }
+__device__ __forceinline__ void pk_split(pk2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) {
+    pk2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) {
+    pk2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ pk2 pk_shfl_up(pk2 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) biquad_cascade_x2_kernel(const CascadeParams<float> p) {
+    constexpr int NT = 128, S = 32, ROWS = 256, TILE = ROWS * S, NVW = 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = p.K;
+    const size_t tab_bytes = (size_t)K * TAB_ENTRIES * 16;
+    const size_t stage_bytes = (size_t)ROWS * 128 + tab_bytes + 16;
+    float* s_in = reinterpret_cast<float*>(smem_raw + 2 * stage_bytes);  // [K][2]
+    float2* wtot = reinterpret_cast<float2*>(s_in + (size_t)K * 2 + (K & 1) * 2);  // [2][NVW] (8-byte aligned)
+    __shared__ unsigned int sh_item[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    auto prefetch = [&](unsigned int item, int st) {
+        unsigned char* base = smem_raw + (size_t)st * stage_bytes;
+        uint4* tile4 = reinterpret_cast<uint4*>(base);
+        const int t_idx = (int)(item / (unsigned)p.rows);
+        const int row = (int)(item - (unsigned)t_idx * (unsigned)p.rows);
+        const int b = row / p.c_out, c = row - b * p.c_out;
+        const float* xr = p.x + ((size_t)b * p.c_sig + (p.c_sig == 1 ? 0 : c)) * (size_t)p.L;
+        const size_t crow = (size_t)b * p.c_filt + (p.c_filt == 1 ? 0 : c);
+        const long long t0 = (long long)t_idx * TILE;
+        const long long remain = p.L - t0;
+        if (p.aligned) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int g = tid + j * NT;
+                const long long pos = (long long)g * 4;
+                const long long nb = (remain - pos) * 4;
+                const int src_bytes = nb >= 16 ? 16 : (nb > 0 ? (int)nb : 0);
+                const float* src = src_bytes > 0 ? xr + t0 + pos : xr;
+                cp_async16(&tile4[swz_unit(g >> 3, g & 7)], src, src_bytes);
+            }
+        } else {
+            float* tile = reinterpret_cast<float*>(base);
+            for (int i = tid; i < TILE; i += NT) {
+                const float val = (i < remain) ? xr[t0 + i] : 0.f;
+                tile[(size_t)swz_unit(i >> 5, (i & 31) >> 2) * 4 + (i & 3)] = val;
+            }
+        }
+        const unsigned char* tsrc = reinterpret_cast<const unsigned char*>(p.tables + crow * K * TAB_ENTRIES * 4);
+        unsigned char* tdst = base + (size_t)ROWS * 128;
+        for (int u = tid; u < K * TAB_ENTRIES; u += NT) cp_async16(tdst + (size_t)u * 16, tsrc + (size_t)u * 16, 16);
+        if (tid < 2) {
+            float* hist = reinterpret_cast<float*>(base + (size_t)ROWS * 128 + tab_bytes);
+            if (t_idx > 0) cp_async_small<4>(hist + tid, xr + t0 - 1 - tid);
+            else hist[tid] = 0.f;
+        }
+    };
+
+    if (tid == 0) sh_item[0] = take_ticket(p.ticket, 0xffffffffu);
+    __syncthreads();
+    unsigned int item = sh_item[0];
+    if (item < p.n_items) prefetch(item, 0);
+    cp_async_commit();
+    int st = 0;
+
+    while (item < p.n_items) {
+        if (tid == 0) sh_item[st ^ 1] = take_ticket(p.ticket, 0xffffffffu);
+        __syncthreads();
+        const unsigned int next_item = sh_item[st ^ 1];
+        if (next_item < p.n_items) prefetch(next_item, st ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        unsigned char* base = smem_raw + (size_t)st * stage_bytes;
+        float4* tile4 = reinterpret_cast<float4*>(base);
+        const float* tile = reinterpret_cast<const float*>(base);
+        const float4* tab = reinterpret_cast<const float4*>(base + (size_t)ROWS * 128);
+        const float* hist = reinterpret_cast<const float*>(base + (size_t)ROWS * 128 + tab_bytes);
+
+        const int t_idx = (int)(item / (unsigned)p.rows);
+        const int row = (int)(item - (unsigned)t_idx * (unsigned)p.rows);
+        float* yr = p.y + (size_t)row * (size_t)p.L;
+        const long long t0 = (long long)t_idx * TILE;
+        const long long remain = p.L - t0;
+
+        pk2 v[S];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 qa = tile4[swz_unit(tid, u)];
+            const float4 qb = tile4[swz_unit(tid + NT, u)];
+            v[4 * u + 0] = pk_make(qa.x, qb.x);
+            v[4 * u + 1] = pk_make(qa.y, qb.y);
+            v[4 * u + 2] = pk_make(qa.z, qb.z);
+            v[4 * u + 3] = pk_make(qa.w, qb.w);
+        }
+        pk2 um1, um2;  // the two input samples before each chunk
+        {
+            const int rb = swz_unit(tid + NT - 1, 7) * 4;
+            float a1v, a2v;
+            if (tid > 0) {
+                const int ra = swz_unit(tid - 1, 7) * 4;
+                a1v = tile[ra + 3]; a2v = tile[ra + 2];
+            } else {
+                a1v = hist[0]; a2v = hist[1];
+            }
+            um1 = pk_make(a1v, tile[rb + 3]);
+            um2 = pk_make(a2v, tile[rb + 2]);
+        }
+
+        for (int k = 0; k < K; ++k) {
+            const float4* pk = tab + k * TAB_ENTRIES;
+            const float4 c0 = pk[33];
+            const pk2 B0 = pk_dup(c0.x), B1 = pk_dup(c0.y), B2 = pk_dup(c0.z), NA1 = pk_dup(c0.w), NA2 = pk_dup(pk[34].x);
+
+            // 1. feed-forward part in place
+#pragma unroll
+            for (int n = S - 1; n >= 2; --n)
+                v[n] = pk_fma(B2, v[n - 2], pk_fma(B1, v[n - 1], pk_mul(B0, v[n])));
+            v[1] = pk_fma(B2, um1, pk_fma(B1, v[0], pk_mul(B0, v[1])));
+            v[0] = pk_fma(B2, um2, pk_fma(B1, um1, pk_mul(B0, v[0])));
+
+            // 2. zero-state recursion -> end states (both halves at once)
+            pk2 z1 = 0ull, z2 = 0ull;
+#pragma unroll
+            for (int n = 0; n < S; ++n) {
+                const pk2 w = pk_fma(NA1, z1, pk_fma(NA2, z2, v[n]));
+                z2 = z1;
+                z1 = w;
+            }
+
+            // 3. packed scan of s' = M s + z inside each warp
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int d = 1 << j;
+                pk2 p1 = pk_shfl_up(z1, d), p2 = pk_shfl_up(z2, d);
+                if (lane < d) { p1 = 0ull; p2 = 0ull; }
+                const float4 m = pk[d];
+                z1 = pk_fma(pk_dup(m.x), p1, pk_fma(pk_dup(m.y), p2, z1));
+                z2 = pk_fma(pk_dup(m.z), p1, pk_fma(pk_dup(m.w), p2, z2));
+            }
+            float2* wt = wtot + (k & 1) * NVW;
+            if (lane == 31) {
+                float z1a, z1b, z2a, z2b;
+                pk_split(z1, z1a, z1b);
+                pk_split(z2, z2a, z2b);
+                wt[warp] = make_float2(z1a, z2a);       // half A
+                wt[4 + warp] = make_float2(z1b, z2b);   // half B
+            }
+            if (k == 0) {
+                if (warp == 0) {
+                    if (t_idx > 0) {
+                        if (lane == 0) chain_wait(p.flags + row, t_idx);
+                        __syncwarp();
+                        for (int i = lane; i < 2 * K; i += 32) s_in[i] = __ldcg(p.state + (size_t)row * 2 * K + i);
+                    } else {
+                        for (int i = lane; i < 2 * K; i += 32) s_in[i] = 0.f;
+                    }
+                }
+            }
+            __syncthreads();
+            // state at the start of this thread's warp in half A and in half B (virtual warps 0..7)
+            float sx = s_in[2 * k], sy = s_in[2 * k + 1];
+            float sAx = 0.f, sAy = 0.f, sBx = 0.f, sBy = 0.f;
+            {
+                const float4 mw = pk[32];
+#pragma unroll
+                for (int q = 0; q < NVW; ++q) {
+                    if (q == warp) { sAx = sx; sAy = sy; }
+                    if (q == 4 + warp) { sBx = sx; sBy = sy; }
+                    const float2 wq = wt[q];
+                    const float tx = fmaf(mw.x, sx, fmaf(mw.y, sy, wq.x));
+                    const float ty = fmaf(mw.z, sx, fmaf(mw.w, sy, wq.y));
+                    sx = tx;
+                    sy = ty;
+                }
+            }
+            pk2 e1 = pk_shfl_up(z1, 1), e2 = pk_shfl_up(z2, 1);
+            if (lane == 0) { e1 = 0ull; e2 = 0ull; }
+            const float4 ml = pk[lane];
+            const pk2 S1 = pk_make(sAx, sBx), S2 = pk_make(sAy, sBy);
+            pk2 y1 = pk_fma(pk_dup(ml.x), S1, pk_fma(pk_dup(ml.y), S2, e1));  // y[-1] of the chunks
+            pk2 y2 = pk_fma(pk_dup(ml.z), S1, pk_fma(pk_dup(ml.w), S2, e2));  // y[-2]
+            um1 = y1;
+            um2 = y2;
+
+            // 4. the recursion again, from the true states
+#pragma unroll
+            for (int n = 0; n < S; ++n) {
+                const pk2 w = pk_fma(NA1, y1, pk_fma(NA2, y2, v[n]));
+                y2 = y1;
+                y1 = w;
+                v[n] = w;
+            }
+            if (tid == NT - 1 && t_idx + 1 < p.tiles) {
+                float lo, hi1, hi2;
+                pk_split(y1, lo, hi1);
+                pk_split(y2, lo, hi2);
+                p.state[(size_t)row * 2 * K + 2 * k] = hi1;
+                p.state[(size_t)row * 2 * K + 2 * k + 1] = hi2;
+            }
+        }
+        if (tid == NT - 1 && t_idx + 1 < p.tiles) chain_publish(p.flags + row, t_idx + 1);
+
+        // ---- registers -> tile -> global
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float4 qa, qb;
+            pk_split(v[4 * u + 0], qa.x, qb.x);
+            pk_split(v[4 * u + 1], qa.y, qb.y);
+            pk_split(v[4 * u + 2], qa.z, qb.z);
+            pk_split(v[4 * u + 3], qa.w, qb.w);
+            tile4[swz_unit(tid, u)] = qa;
+            tile4[swz_unit(tid + NT, u)] = qb;
+        }
+        __syncthreads();
+        if (p.aligned) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int g = tid + j * NT;
+                const long long pos = (long long)g * 4;
+                if (pos + 4 <= remain) {
+                    stg_stream(reinterpret_cast<float4*>(yr + t0 + pos), tile4[swz_unit(g >> 3, g & 7)]);
+                } else if (pos < remain) {
+                    const int sb = swz_unit(g >> 3, g & 7) * 4;
+                    for (int e = 0; e < 4 && pos + e < remain; ++e) yr[t0 + pos + e] = tile[sb + e];
+                }
+            }
+        } else {
+            for (int i = tid; i < TILE && i < remain; i += NT)
+                yr[t0 + i] = tile[(size_t)swz_unit(i >> 5, (i & 31) >> 2) * 4 + (i & 3)];
+        }
+        item = next_item;
+        st ^= 1;
+    }
+    cp_async_wait<0>();
+}
+
+static size_t cascade_x2_smem_bytes(int K) {
+    const size_t stage = (size_t)256 * 128 + (size_t)K * TAB_ENTRIES * 16 + 16;
+    return 2 * stage + (size_t)(K * 2 + 2) * sizeof(float) + (size_t)2 * 8 * sizeof(float2) + 64;
+}
+
 template <typename T>
 static size_t cascade_smem_bytes(int NT, int K) {
     const size_t stage = (size_t)NT * 128 + (size_t)K * TAB_ENTRIES * 4 * sizeof(T) + 16;
@@ -353,6 +621,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     if (K > 64) return GFX_ERR_UNSUPPORTED;
     const int c_out = c_sig > c_filt ? c_sig : c_filt;
     const long long rows_ll = (long long)batch * c_out;
+    constexpr bool X2 = sizeof(T) == 4;  // fp32: packed two-chunk kernel (same 8192-sample tiles)
     const long long tiles_ll = (L + (long long)NT * S - 1) / ((long long)NT * S);
     if (rows_ll * tiles_ll > 0x7fff0000LL) return GFX_ERR_UNSUPPORTED;
     const int rows = (int)rows_ll, tiles = (int)tiles_ll;
@@ -379,6 +648,27 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     cascade_tables_kernel<T><<<(n_sections * 32 + 127) / 128, 128, 0, stream>>>(Bs, As, tables, n_sections);
     GFX_CUDA_CHECK(cudaGetLastError());
 
+    static const bool force_scalar = (getenv("GFX_CASCADE_SCALAR") != nullptr);  // A/B testing only
+    if constexpr (X2) {
+        const size_t smem2 = cascade_x2_smem_bytes(K);
+        if (!force_scalar && smem2 <= (size_t)device_info().max_smem_optin) {
+            auto kern2 = biquad_cascade_x2_kernel<3>;
+            static size_t configured2 = 0;
+            if (smem2 > configured2) {
+                GFX_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                configured2 = smem2;
+            }
+            int occ2 = 0;
+            GFX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, 128, smem2));
+            if (occ2 >= 1) {
+                long long grid2 = (long long)device_info().sm_count * occ2;
+                if (grid2 > (long long)p.n_items) grid2 = p.n_items;
+                kern2<<<(unsigned)grid2, 128, smem2, stream>>>(p);
+                GFX_CUDA_CHECK(cudaGetLastError());
+                return GFX_OK;
+            }
+        }
+    }
     const size_t smem = cascade_smem_bytes<T>(NT, K);
     if (smem > (size_t)device_info().max_smem_optin) return GFX_ERR_UNSUPPORTED;
     auto kern = biquad_cascade_kernel<T, NT, MINB>;
