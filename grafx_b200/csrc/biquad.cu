@@ -42,6 +42,7 @@ struct CascadeParams {
     unsigned int* ticket;
     int* flags;  // [rows]   number of finished tiles of the row
     T* state;    // [rows][2K] (y_k[-1], y_k[-2]) left by the last finished tile
+    unsigned long long* xstate;  // packed-kernel variant: [rows][K][2] {value, tag} words
     int aligned;  // 1: x/y rows are 16-byte aligned (vector path)
 };
 
@@ -89,7 +90,8 @@ __global__ void __launch_bounds__(128) cascade_tables_kernel(const T* __restrict
         out[32 * 4 + 2] = (T)base[2]; out[32 * 4 + 3] = (T)base[3];
         out[33 * 4 + 0] = nb0; out[33 * 4 + 1] = nb1; out[33 * 4 + 2] = nb2; out[33 * 4 + 3] = -na1;
         out[34 * 4 + 0] = -na2; out[34 * 4 + 1] = T(0); out[34 * 4 + 2] = T(0); out[34 * 4 + 3] = T(0);
-        out[35 * 4 + 0] = T(0); out[35 * 4 + 1] = T(0); out[35 * 4 + 2] = T(0); out[35 * 4 + 3] = T(0);
+        mat2_mul(base, base, tmp);  // M^64
+        out[35 * 4 + 0] = (T)tmp[0]; out[35 * 4 + 1] = (T)tmp[1]; out[35 * 4 + 2] = (T)tmp[2]; out[35 * 4 + 3] = (T)tmp[3];
     }
 }
 
@@ -360,32 +362,70 @@ __device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) {
 }
 __device__ __forceinline__ pk2 pk_shfl_up(pk2 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 
+// Each WARP is an independent worker: it owns a tile of 64 rows x 32 samples (lane l: rows l and
+// l+32), takes its own tickets, and never meets a block barrier -- the only synchronisation is
+// __syncwarp and the row chain in global memory.  With 4 such warps per SMSP the dependent
+// FFMA2 chains, the shuffle scan and the tile loads of different warps overlap freely.
+constexpr int X2_WARPS = 4;           // warps per CTA (pure packaging: they share nothing)
+constexpr int X2_ROWS = 64;           // 128-byte rows per warp tile
+constexpr int X2_TILE = X2_ROWS * 32; // 2048 samples
+
+static __host__ __device__ __forceinline__ size_t x2_warp_smem_bytes(int K) {
+    // tile | tables | 2 history samples + pad
+    return (size_t)X2_ROWS * 128 + (size_t)K * TAB_ENTRIES * 16 + 16;
+}
+
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) biquad_cascade_x2_kernel(const CascadeParams<float> p) {
-    constexpr int NT = 128, S = 32, ROWS = 256, TILE = ROWS * S, NVW = 8;
+__global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(const CascadeParams<float> p) {
+    constexpr int S = 32, TILE = X2_TILE, ITEM = X2_WARPS * X2_TILE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = p.K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t tab_bytes = (size_t)K * TAB_ENTRIES * 16;
-    const size_t stage_bytes = (size_t)ROWS * 128 + tab_bytes + 16;
-    float* s_in = reinterpret_cast<float*>(smem_raw + 2 * stage_bytes);  // [K][2]
-    float2* wtot = reinterpret_cast<float2*>(s_in + (size_t)K * 2 + (K & 1) * 2);  // [2][NVW] (8-byte aligned)
-    __shared__ unsigned int sh_item[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * x2_warp_smem_bytes(K);
+    float4* tile4 = reinterpret_cast<float4*>(base);
+    float* tile = reinterpret_cast<float*>(base);
+    const float4* tab = reinterpret_cast<const float4*>(base + (size_t)X2_ROWS * 128);
+    float* hist = reinterpret_cast<float*>(base + (size_t)X2_ROWS * 128 + tab_bytes);
+    // coalesced phases: unit g = lane + 32 j lives in row (lane>>3) + 4 j, column (lane&7) ^ (row&7)
+    const int cu0 = (lane & 7) ^ (lane >> 3);
+    // the 4 warps of a CTA take 4 CONSECUTIVE sub-tiles of one row (one ticket = 8192 samples) and
+    // hand the state from warp to warp through shared memory (cheap hop); only the hop from the last
+    // warp to the next item of the row goes through global memory.
+    float2* totals = reinterpret_cast<float2*>(smem_raw + (size_t)X2_WARPS * x2_warp_smem_bytes(K));  // [K][X2_WARPS]
+    float2* sin_relay = totals + (size_t)K * X2_WARPS;                                                // [K]
+    volatile int* ready = reinterpret_cast<volatile int*>(sin_relay + K);                             // [X2_WARPS]
+    volatile int* sin_ready = ready + X2_WARPS;
+    __shared__ unsigned int sh_item;
+    if (threadIdx.x <= X2_WARPS) ready[threadIdx.x] = 0;
+    int seq_base = 0;
 
-    auto prefetch = [&](unsigned int item, int st) {
-        unsigned char* base = smem_raw + (size_t)st * stage_bytes;
-        uint4* tile4 = reinterpret_cast<uint4*>(base);
+    for (;;) {
+        __syncthreads();  // every warp is done with the previous item
+        if (threadIdx.x == 0) sh_item = take_ticket(p.ticket, 0xffffffffu);
+        __syncthreads();
+        const unsigned int item = sh_item;
+        if (item >= p.n_items) break;
         const int t_idx = (int)(item / (unsigned)p.rows);
         const int row = (int)(item - (unsigned)t_idx * (unsigned)p.rows);
         const int b = row / p.c_out, c = row - b * p.c_out;
         const float* xr = p.x + ((size_t)b * p.c_sig + (p.c_sig == 1 ? 0 : c)) * (size_t)p.L;
+        float* yr = p.y + (size_t)row * (size_t)p.L;
         const size_t crow = (size_t)b * p.c_filt + (p.c_filt == 1 ? 0 : c);
-        const long long t0 = (long long)t_idx * TILE;
-        const long long remain = p.L - t0;
-        if (p.aligned) {
+        const long long t0 = (long long)t_idx * ITEM + (long long)warp * TILE;  // this warp's sub-tile
+        const long long remain = p.L - t0;                                        // may be <= 0 (all padding)
+        const bool full = p.aligned && remain >= TILE;
+
+        // ---- stage the tile, the section tables and the two samples before the tile
+        if (full) {
+            const float* src = xr + t0 + lane * 4;
+            float4* dst = tile4 + (lane >> 3) * 8;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cp_async16(dst + j * 32 + (cu0 ^ ((j & 1) << 2)), src + j * 128, 16);
+        } else if (p.aligned) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int g = tid + j * NT;
+                const int g = lane + j * 32;
                 const long long pos = (long long)g * 4;
                 const long long nb = (remain - pos) * 4;
                 const int src_bytes = nb >= 16 ? 16 : (nb > 0 ? (int)nb : 0);
@@ -393,55 +433,29 @@ __global__ void __launch_bounds__(128, MINB) biquad_cascade_x2_kernel(const Casc
                 cp_async16(&tile4[swz_unit(g >> 3, g & 7)], src, src_bytes);
             }
         } else {
-            float* tile = reinterpret_cast<float*>(base);
-            for (int i = tid; i < TILE; i += NT) {
+            for (int i = lane; i < TILE; i += 32) {
                 const float val = (i < remain) ? xr[t0 + i] : 0.f;
                 tile[(size_t)swz_unit(i >> 5, (i & 31) >> 2) * 4 + (i & 3)] = val;
             }
         }
-        const unsigned char* tsrc = reinterpret_cast<const unsigned char*>(p.tables + crow * K * TAB_ENTRIES * 4);
-        unsigned char* tdst = base + (size_t)ROWS * 128;
-        for (int u = tid; u < K * TAB_ENTRIES; u += NT) cp_async16(tdst + (size_t)u * 16, tsrc + (size_t)u * 16, 16);
-        if (tid < 2) {
-            float* hist = reinterpret_cast<float*>(base + (size_t)ROWS * 128 + tab_bytes);
-            if (t_idx > 0) cp_async_small<4>(hist + tid, xr + t0 - 1 - tid);
-            else hist[tid] = 0.f;
+        {
+            const unsigned char* tsrc = reinterpret_cast<const unsigned char*>(p.tables + crow * K * TAB_ENTRIES * 4);
+            unsigned char* tdst = base + (size_t)X2_ROWS * 128;
+            for (int u = lane; u < K * TAB_ENTRIES; u += 32) cp_async16(tdst + (size_t)u * 16, tsrc + (size_t)u * 16, 16);
+            if (lane < 2) {
+                if (t0 > 0 && t0 - 1 - lane < p.L) cp_async_small<4>(hist + lane, xr + t0 - 1 - lane);
+                else hist[lane] = 0.f;
+            }
         }
-    };
-
-    if (tid == 0) sh_item[0] = take_ticket(p.ticket, 0xffffffffu);
-    __syncthreads();
-    unsigned int item = sh_item[0];
-    if (item < p.n_items) prefetch(item, 0);
-    cp_async_commit();
-    int st = 0;
-
-    while (item < p.n_items) {
-        if (tid == 0) sh_item[st ^ 1] = take_ticket(p.ticket, 0xffffffffu);
-        __syncthreads();
-        const unsigned int next_item = sh_item[st ^ 1];
-        if (next_item < p.n_items) prefetch(next_item, st ^ 1);
         cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-
-        unsigned char* base = smem_raw + (size_t)st * stage_bytes;
-        float4* tile4 = reinterpret_cast<float4*>(base);
-        const float* tile = reinterpret_cast<const float*>(base);
-        const float4* tab = reinterpret_cast<const float4*>(base + (size_t)ROWS * 128);
-        const float* hist = reinterpret_cast<const float*>(base + (size_t)ROWS * 128 + tab_bytes);
-
-        const int t_idx = (int)(item / (unsigned)p.rows);
-        const int row = (int)(item - (unsigned)t_idx * (unsigned)p.rows);
-        float* yr = p.y + (size_t)row * (size_t)p.L;
-        const long long t0 = (long long)t_idx * TILE;
-        const long long remain = p.L - t0;
+        cp_async_wait<0>();
+        __syncwarp();
 
         pk2 v[S];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const float4 qa = tile4[swz_unit(tid, u)];
-            const float4 qb = tile4[swz_unit(tid + NT, u)];
+            const float4 qa = tile4[swz_unit(lane, u)];
+            const float4 qb = tile4[swz_unit(lane + 32, u)];
             v[4 * u + 0] = pk_make(qa.x, qb.x);
             v[4 * u + 1] = pk_make(qa.y, qb.y);
             v[4 * u + 2] = pk_make(qa.z, qb.z);
@@ -449,10 +463,10 @@ __global__ void __launch_bounds__(128, MINB) biquad_cascade_x2_kernel(const Casc
         }
         pk2 um1, um2;  // the two input samples before each chunk
         {
-            const int rb = swz_unit(tid + NT - 1, 7) * 4;
+            const int rb = swz_unit(lane + 31, 7) * 4;
             float a1v, a2v;
-            if (tid > 0) {
-                const int ra = swz_unit(tid - 1, 7) * 4;
+            if (lane > 0) {
+                const int ra = swz_unit(lane - 1, 7) * 4;
                 a1v = tile[ra + 3]; a2v = tile[ra + 2];
             } else {
                 a1v = hist[0]; a2v = hist[1];
@@ -482,7 +496,7 @@ __global__ void __launch_bounds__(128, MINB) biquad_cascade_x2_kernel(const Casc
                 z1 = w;
             }
 
-            // 3. packed scan of s' = M s + z inside each warp
+            // 3. packed scan of s' = M s + z over the 32 lanes (each half separately)
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
                 const int d = 1 << j;
@@ -492,68 +506,90 @@ __global__ void __launch_bounds__(128, MINB) biquad_cascade_x2_kernel(const Casc
                 z1 = pk_fma(pk_dup(m.x), p1, pk_fma(pk_dup(m.y), p2, z1));
                 z2 = pk_fma(pk_dup(m.z), p1, pk_fma(pk_dup(m.w), p2, z2));
             }
-            float2* wt = wtot + (k & 1) * NVW;
+            // ---- stitch the warps: totals of this warp's 64 chunks -> shared memory, then fold the
+            //      totals of the warps before it onto the state the previous item of the row left
+            float zAx, zBx, zAy, zBy;
+            pk_split(z1, zAx, zBx);
+            pk_split(z2, zAy, zBy);
+            const float totAx = __shfl_sync(0xffffffffu, zAx, 31), totAy = __shfl_sync(0xffffffffu, zAy, 31);
+            const float4 mw = pk[32];   // M^32
+            const int seq = seq_base + k + 1;
             if (lane == 31) {
-                float z1a, z1b, z2a, z2b;
-                pk_split(z1, z1a, z1b);
-                pk_split(z2, z2a, z2b);
-                wt[warp] = make_float2(z1a, z2a);       // half A
-                wt[4 + warp] = make_float2(z1b, z2b);   // half B
+                totals[k * X2_WARPS + warp] = make_float2(fmaf(mw.x, zAx, fmaf(mw.y, zAy, zBx)),
+                                                          fmaf(mw.z, zAx, fmaf(mw.w, zAy, zBy)));
+                __threadfence_block();
+                ready[warp] = seq;
             }
-            if (k == 0) {
+            // incoming state of the item for THIS section: one 64-bit {value, tag} word per component
+            // (an aligned 8-byte access is single-copy atomic: no fence, no separate flag), published
+            // section by section so that consecutive items of a row run as a pipeline
+            // Only warp 0 reads the global word (the last warp of this very item overwrites it with the
+            // next tag as soon as IT is done with the section); it relays the state through shared memory.
+            float sAx = 0.f, sAy = 0.f;
+            if (t_idx > 0) {
                 if (warp == 0) {
-                    if (t_idx > 0) {
-                        if (lane == 0) chain_wait(p.flags + row, t_idx);
-                        __syncwarp();
-                        for (int i = lane; i < 2 * K; i += 32) s_in[i] = __ldcg(p.state + (size_t)row * 2 * K + i);
-                    } else {
-                        for (int i = lane; i < 2 * K; i += 32) s_in[i] = 0.f;
+                    float sv = 0.f;
+                    if (lane < 2) {
+                        const volatile unsigned long long* w = p.xstate + ((size_t)row * K + k) * 2 + lane;
+                        unsigned long long word;
+                        do { word = *w; } while ((unsigned)(word >> 32) != (unsigned)t_idx);
+                        sv = __uint_as_float((unsigned)word);
                     }
+                    sAx = __shfl_sync(0xffffffffu, sv, 0);
+                    sAy = __shfl_sync(0xffffffffu, sv, 1);
+                    if (lane == 0) {
+                        sin_relay[k] = make_float2(sAx, sAy);
+                        __threadfence_block();
+                        *sin_ready = seq;
+                    }
+                } else {
+                    if (lane == 0) { while (*sin_ready < seq) { } }
+                    __syncwarp();
+                    __threadfence_block();
+                    const float2 si = sin_relay[k];
+                    sAx = si.x;
+                    sAy = si.y;
                 }
             }
-            __syncthreads();
-            // state at the start of this thread's warp in half A and in half B (virtual warps 0..7)
-            float sx = s_in[2 * k], sy = s_in[2 * k + 1];
-            float sAx = 0.f, sAy = 0.f, sBx = 0.f, sBy = 0.f;
-            {
-                const float4 mw = pk[32];
-#pragma unroll
-                for (int q = 0; q < NVW; ++q) {
-                    if (q == warp) { sAx = sx; sAy = sy; }
-                    if (q == 4 + warp) { sBx = sx; sBy = sy; }
-                    const float2 wq = wt[q];
-                    const float tx = fmaf(mw.x, sx, fmaf(mw.y, sy, wq.x));
-                    const float ty = fmaf(mw.z, sx, fmaf(mw.w, sy, wq.y));
-                    sx = tx;
-                    sy = ty;
+            if (warp > 0) {
+                if (lane < warp) { while (ready[lane] < seq) { } }
+                __syncwarp();
+                __threadfence_block();
+                const float4 m64 = pk[35];  // M^64
+                for (int q = 0; q < warp; ++q) {
+                    const float2 tq = totals[k * X2_WARPS + q];
+                    const float tx = fmaf(m64.x, sAx, fmaf(m64.y, sAy, tq.x));
+                    const float ty = fmaf(m64.z, sAx, fmaf(m64.w, sAy, tq.y));
+                    sAx = tx;
+                    sAy = ty;
                 }
             }
+            const float sBx = fmaf(mw.x, sAx, fmaf(mw.y, sAy, totAx));
+            const float sBy = fmaf(mw.z, sAx, fmaf(mw.w, sAy, totAy));
             pk2 e1 = pk_shfl_up(z1, 1), e2 = pk_shfl_up(z2, 1);
             if (lane == 0) { e1 = 0ull; e2 = 0ull; }
             const float4 ml = pk[lane];
             const pk2 S1 = pk_make(sAx, sBx), S2 = pk_make(sAy, sBy);
-            pk2 y1 = pk_fma(pk_dup(ml.x), S1, pk_fma(pk_dup(ml.y), S2, e1));  // y[-1] of the chunks
-            pk2 y2 = pk_fma(pk_dup(ml.z), S1, pk_fma(pk_dup(ml.w), S2, e2));  // y[-2]
+            const pk2 y1 = pk_fma(pk_dup(ml.x), S1, pk_fma(pk_dup(ml.y), S2, e1));  // y[-1] of the chunks
+            const pk2 y2 = pk_fma(pk_dup(ml.z), S1, pk_fma(pk_dup(ml.w), S2, e2));  // y[-2]
             um1 = y1;
             um2 = y2;
 
-            // 4. the recursion again, from the true states
+            // 4. the recursion again, from the true states (on the array itself: no register rotation)
+            v[0] = pk_fma(NA1, y1, pk_fma(NA2, y2, v[0]));
+            v[1] = pk_fma(NA1, v[0], pk_fma(NA2, y1, v[1]));
 #pragma unroll
-            for (int n = 0; n < S; ++n) {
-                const pk2 w = pk_fma(NA1, y1, pk_fma(NA2, y2, v[n]));
-                y2 = y1;
-                y1 = w;
-                v[n] = w;
-            }
-            if (tid == NT - 1 && t_idx + 1 < p.tiles) {
+            for (int n = 2; n < S; ++n) v[n] = pk_fma(NA1, v[n - 1], pk_fma(NA2, v[n - 2], v[n]));
+            if (warp == X2_WARPS - 1 && lane == 31 && t_idx + 1 < p.tiles) {
                 float lo, hi1, hi2;
-                pk_split(y1, lo, hi1);
-                pk_split(y2, lo, hi2);
-                p.state[(size_t)row * 2 * K + 2 * k] = hi1;
-                p.state[(size_t)row * 2 * K + 2 * k + 1] = hi2;
+                pk_split(v[S - 1], lo, hi1);
+                pk_split(v[S - 2], lo, hi2);
+                volatile unsigned long long* w = p.xstate + ((size_t)row * K + k) * 2;
+                const unsigned long long tag = (unsigned long long)(unsigned)(t_idx + 1) << 32;
+                w[0] = tag | __float_as_uint(hi1);
+                w[1] = tag | __float_as_uint(hi2);
             }
         }
-        if (tid == NT - 1 && t_idx + 1 < p.tiles) chain_publish(p.flags + row, t_idx + 1);
 
         // ---- registers -> tile -> global
 #pragma unroll
@@ -563,14 +599,19 @@ __global__ void __launch_bounds__(128, MINB) biquad_cascade_x2_kernel(const Casc
             pk_split(v[4 * u + 1], qa.y, qb.y);
             pk_split(v[4 * u + 2], qa.z, qb.z);
             pk_split(v[4 * u + 3], qa.w, qb.w);
-            tile4[swz_unit(tid, u)] = qa;
-            tile4[swz_unit(tid + NT, u)] = qb;
+            tile4[swz_unit(lane, u)] = qa;
+            tile4[swz_unit(lane + 32, u)] = qb;
         }
-        __syncthreads();
-        if (p.aligned) {
+        __syncwarp();
+        if (full) {
+            float4* dst = reinterpret_cast<float4*>(yr + t0) + lane;
+            const float4* src = tile4 + (lane >> 3) * 8;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) stg_stream(dst + j * 32, src[j * 32 + (cu0 ^ ((j & 1) << 2))]);
+        } else if (p.aligned) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int g = tid + j * NT;
+                const int g = lane + j * 32;
                 const long long pos = (long long)g * 4;
                 if (pos + 4 <= remain) {
                     stg_stream(reinterpret_cast<float4*>(yr + t0 + pos), tile4[swz_unit(g >> 3, g & 7)]);
@@ -580,18 +621,16 @@ __global__ void __launch_bounds__(128, MINB) biquad_cascade_x2_kernel(const Casc
                 }
             }
         } else {
-            for (int i = tid; i < TILE && i < remain; i += NT)
+            for (int i = lane; i < TILE && i < remain; i += 32)
                 yr[t0 + i] = tile[(size_t)swz_unit(i >> 5, (i & 31) >> 2) * 4 + (i & 3)];
         }
-        item = next_item;
-        st ^= 1;
+        seq_base += K;
     }
-    cp_async_wait<0>();
 }
 
 static size_t cascade_x2_smem_bytes(int K) {
-    const size_t stage = (size_t)256 * 128 + (size_t)K * TAB_ENTRIES * 16 + 16;
-    return 2 * stage + (size_t)(K * 2 + 2) * sizeof(float) + (size_t)2 * 8 * sizeof(float2) + 64;
+    return (size_t)X2_WARPS * x2_warp_smem_bytes(K) + (size_t)K * (X2_WARPS + 1) * sizeof(float2) +
+           (X2_WARPS + 1) * sizeof(int) + 16;
 }
 
 template <typename T>
@@ -603,8 +642,8 @@ static size_t cascade_smem_bytes(int NT, int K) {
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 static size_t cascade_workspace_bytes(int rows, int coef_rows, int K, size_t elem) {
-    // [ticket | pad to 256] [flags: rows ints] [state: rows*2K elems] [tables: coef_rows*K*36*4 elems]
-    return 256 + align256((size_t)rows * sizeof(int)) + align256((size_t)rows * 2 * K * elem) +
+    // [ticket | pad to 256] [flags: rows*K ints] [state: rows*2K elems] [tables: coef_rows*K*36*4 elems]
+    return 256 + align256((size_t)rows * K * sizeof(int)) + align256((size_t)rows * 2 * K * 8) +
            (size_t)coef_rows * K * TAB_ENTRIES * 4 * elem;
 }
 
@@ -621,8 +660,11 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     if (K > 64) return GFX_ERR_UNSUPPORTED;
     const int c_out = c_sig > c_filt ? c_sig : c_filt;
     const long long rows_ll = (long long)batch * c_out;
-    constexpr bool X2 = sizeof(T) == 4;  // fp32: packed two-chunk kernel (same 8192-sample tiles)
-    const long long tiles_ll = (L + (long long)NT * S - 1) / ((long long)NT * S);
+    static const bool force_scalar = (getenv("GFX_CASCADE_SCALAR") != nullptr);  // A/B testing only
+    const bool X2 = sizeof(T) == 4 && !force_scalar &&
+                    cascade_x2_smem_bytes(K) <= (size_t)device_info().max_smem_optin;  // fp32: packed warp-tile kernel
+    const long long tile_len = X2 ? (long long)X2_WARPS * X2_TILE : (long long)NT * S;
+    const long long tiles_ll = (L + tile_len - 1) / tile_len;
     if (rows_ll * tiles_ll > 0x7fff0000LL) return GFX_ERR_UNSUPPORTED;
     const int rows = (int)rows_ll, tiles = (int)tiles_ll;
     const int coef_rows = batch * c_filt;
@@ -637,36 +679,36 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     unsigned char* w = (unsigned char*)ws;
     p.ticket = (unsigned int*)w;
     p.flags = (int*)(w + 256);
-    const size_t flags_bytes = align256((size_t)rows * sizeof(int));
+    const size_t flags_bytes = align256((size_t)rows * K * sizeof(int));
     p.state = (T*)(w + 256 + flags_bytes);
-    T* tables = (T*)(w + 256 + flags_bytes + align256((size_t)rows * 2 * K * sizeof(T)));
+    p.xstate = (unsigned long long*)(w + 256 + flags_bytes);
+    const size_t state_bytes = align256((size_t)rows * 2 * K * 8);
+    T* tables = (T*)(w + 256 + flags_bytes + state_bytes);
     p.tables = tables;
     p.aligned = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && ((L * (long long)sizeof(T)) % 16 == 0);
 
-    GFX_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256 + flags_bytes, stream));
+    GFX_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256 + flags_bytes + state_bytes, stream));
     const int n_sections = coef_rows * K;
     cascade_tables_kernel<T><<<(n_sections * 32 + 127) / 128, 128, 0, stream>>>(Bs, As, tables, n_sections);
     GFX_CUDA_CHECK(cudaGetLastError());
 
-    static const bool force_scalar = (getenv("GFX_CASCADE_SCALAR") != nullptr);  // A/B testing only
-    if constexpr (X2) {
+    if constexpr (sizeof(T) == 4) {
         const size_t smem2 = cascade_x2_smem_bytes(K);
-        if (!force_scalar && smem2 <= (size_t)device_info().max_smem_optin) {
-            auto kern2 = biquad_cascade_x2_kernel<3>;
+        if (X2) {
+            auto kern2 = biquad_cascade_x2_kernel<4>;
             static size_t configured2 = 0;
             if (smem2 > configured2) {
                 GFX_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
                 configured2 = smem2;
             }
             int occ2 = 0;
-            GFX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, 128, smem2));
-            if (occ2 >= 1) {
-                long long grid2 = (long long)device_info().sm_count * occ2;
-                if (grid2 > (long long)p.n_items) grid2 = p.n_items;
-                kern2<<<(unsigned)grid2, 128, smem2, stream>>>(p);
-                GFX_CUDA_CHECK(cudaGetLastError());
-                return GFX_OK;
-            }
+            GFX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, 32 * X2_WARPS, smem2));
+            if (occ2 < 1) return GFX_ERR_UNSUPPORTED;
+            long long grid2 = (long long)device_info().sm_count * occ2;
+            if (grid2 > (long long)p.n_items) grid2 = p.n_items;
+            kern2<<<(unsigned)grid2, 32 * X2_WARPS, smem2, stream>>>(p);
+            GFX_CUDA_CHECK(cudaGetLastError());
+            return GFX_OK;
         }
     }
     const size_t smem = cascade_smem_bytes<T>(NT, K);

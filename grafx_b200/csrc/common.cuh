@@ -75,8 +75,9 @@ __device__ __forceinline__ void chain_wait(const int* flag, int needed) {
     __threadfence();
 }
 __device__ __forceinline__ void chain_publish(int* flag, int value) {
+    // release: the state words written by this thread before the call are visible to whoever sees the flag
     __threadfence();
-    atomicExch(flag, value);
+    *reinterpret_cast<volatile int*>(flag) = value;
 }
 
 // ---------------------------------------------------------------- 128-byte-row XOR swizzle
