@@ -360,6 +360,12 @@ __device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// in-place forms (destination tied to the addend / multiplicand): keep the sample array in fixed
+// registers across the section loop -- otherwise ptxas computes into fresh pairs and copies back
+__device__ __forceinline__ void pk_fma_acc(pk2& c, pk2 a, pk2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void pk_mul_acc(pk2& c, pk2 a) { asm("mul.rn.f32x2 %0, %1, %0;" : "+l"(c) : "l"(a)); }
 __device__ __forceinline__ pk2 pk_shfl_up(pk2 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 
 // Each WARP is an independent worker: it owns a tile of 64 rows x 32 samples (lane l: rows l and
@@ -375,11 +381,13 @@ static __host__ __device__ __forceinline__ size_t x2_warp_smem_bytes(int K) {
     return (size_t)X2_ROWS * 128 + (size_t)K * TAB_ENTRIES * 16 + 16;
 }
 
-template <int MINB>
+// KT > 0: the section loop is fully unrolled for K == KT (no loop-carried register shuffling of the
+// 64 sample registers); KT == 0: generic K.
+template <int MINB, int KT>
 __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(const CascadeParams<float> p) {
     constexpr int S = 32, TILE = X2_TILE, ITEM = X2_WARPS * X2_TILE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int K = p.K;
+    const int K = KT > 0 ? KT : p.K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t tab_bytes = (size_t)K * TAB_ENTRIES * 16;
     unsigned char* base = smem_raw + (size_t)warp * x2_warp_smem_bytes(K);
@@ -475,17 +483,21 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
             um2 = pk_make(a2v, tile[rb + 2]);
         }
 
-        for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int k = 0; k < (KT > 0 ? KT : K); ++k) {
             const float4* pk = tab + k * TAB_ENTRIES;
             const float4 c0 = pk[33];
             const pk2 B0 = pk_dup(c0.x), B1 = pk_dup(c0.y), B2 = pk_dup(c0.z), NA1 = pk_dup(c0.w), NA2 = pk_dup(pk[34].x);
 
-            // 1. feed-forward part in place
+            // 1. feed-forward part in place (descending, so the taps are still inputs)
 #pragma unroll
-            for (int n = S - 1; n >= 2; --n)
-                v[n] = pk_fma(B2, v[n - 2], pk_fma(B1, v[n - 1], pk_mul(B0, v[n])));
-            v[1] = pk_fma(B2, um1, pk_fma(B1, v[0], pk_mul(B0, v[1])));
-            v[0] = pk_fma(B2, um2, pk_fma(B1, um1, pk_mul(B0, v[0])));
+            for (int n = S - 1; n >= 2; --n) {
+                pk_mul_acc(v[n], B0);
+                pk_fma_acc(v[n], B1, v[n - 1]);
+                pk_fma_acc(v[n], B2, v[n - 2]);
+            }
+            pk_mul_acc(v[1], B0); pk_fma_acc(v[1], B1, v[0]); pk_fma_acc(v[1], B2, um1);
+            pk_mul_acc(v[0], B0); pk_fma_acc(v[0], B1, um1);  pk_fma_acc(v[0], B2, um2);
 
             // 2. zero-state recursion -> end states (both halves at once)
             pk2 z1 = 0ull, z2 = 0ull;
@@ -576,10 +588,13 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
             um2 = y2;
 
             // 4. the recursion again, from the true states (on the array itself: no register rotation)
-            v[0] = pk_fma(NA1, y1, pk_fma(NA2, y2, v[0]));
-            v[1] = pk_fma(NA1, v[0], pk_fma(NA2, y1, v[1]));
+            pk_fma_acc(v[0], NA2, y2); pk_fma_acc(v[0], NA1, y1);
+            pk_fma_acc(v[1], NA2, y1); pk_fma_acc(v[1], NA1, v[0]);
 #pragma unroll
-            for (int n = 2; n < S; ++n) v[n] = pk_fma(NA1, v[n - 1], pk_fma(NA2, v[n - 2], v[n]));
+            for (int n = 2; n < S; ++n) {
+                pk_fma_acc(v[n], NA2, v[n - 2]);
+                pk_fma_acc(v[n], NA1, v[n - 1]);
+            }
             if (warp == X2_WARPS - 1 && lane == 31 && t_idx + 1 < p.tiles) {
                 float lo, hi1, hi2;
                 pk_split(v[S - 1], lo, hi1);
@@ -695,7 +710,9 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     if constexpr (sizeof(T) == 4) {
         const size_t smem2 = cascade_x2_smem_bytes(K);
         if (X2) {
-            auto kern2 = biquad_cascade_x2_kernel<4>;
+            // (fully unrolling the section loop per K was measured: no gain -- ptxas keeps its
+            //  register-pair copies -- and a bigger instruction footprint; generic K only)
+            auto kern2 = biquad_cascade_x2_kernel<4, 0>;
             static size_t configured2 = 0;
             if (smem2 > configured2) {
                 GFX_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
