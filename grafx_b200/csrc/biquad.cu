@@ -338,36 +338,6 @@ __global__ void __launch_bounds__(NT, MINB) biquad_cascade_kernel(const CascadeP
 // 128 threads; the tile is 256 rows of 32 samples; thread t owns rows t ("A", lane .x) and t+128
 // ("B", lane .y), i.e. samples [32t, 32t+32) and [4096+32t, ...).  The scan runs packed over both
 // halves; the B half starts from the state the A half ends with.
-// Packed values live in 64-bit registers end to end (inline PTX on .b64 operands): going through
-// float2 made ptxas re-pack the halves around every FFMA2 (28 IMAD.MOV per sample, profiles/).
-typedef unsigned long long pk2;
-__device__ __forceinline__ pk2 pk_make(float lo, float hi) {
-    pk2 d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-    return d;
-}
-__device__ __forceinline__ pk2 pk_dup(float a) { return pk_make(a, a); }
-__device__ __forceinline__ void pk_split(pk2 v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) {
-    pk2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) {
-    pk2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-// in-place forms (destination tied to the addend / multiplicand): keep the sample array in fixed
-// registers across the section loop -- otherwise ptxas computes into fresh pairs and copies back
-__device__ __forceinline__ void pk_fma_acc(pk2& c, pk2 a, pk2 b) {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
-}
-__device__ __forceinline__ void pk_mul_acc(pk2& c, pk2 a) { asm("mul.rn.f32x2 %0, %1, %0;" : "+l"(c) : "l"(a)); }
-__device__ __forceinline__ pk2 pk_shfl_up(pk2 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
-
 // Each WARP is an independent worker: it owns a tile of 64 rows x 32 samples (lane l: rows l and
 // l+32), takes its own tickets, and never meets a block barrier -- the only synchronisation is
 // __syncwarp and the row chain in global memory.  With 4 such warps per SMSP the dependent

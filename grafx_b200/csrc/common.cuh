@@ -60,6 +60,53 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
                  "f"(v.y), "f"(v.z), "f"(v.w));
 }
 
+// ---------------------------------------------------------------- packed fp32x2 (Blackwell FFMA2 / FADD2 / FMUL2)
+// Packed values live in 64-bit registers end to end (inline PTX on .b64 operands): going through
+// float2 made ptxas re-pack the halves around every FFMA2 (28 IMAD.MOV per sample, profiles/).
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk_make(float lo, float hi) {
+    pk2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ pk2 pk_dup(float a) { return pk_make(a, a); }
+__device__ __forceinline__ void pk_split(pk2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) {
+    pk2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) {
+    pk2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// in-place forms (destination tied to the addend / multiplicand): keep the sample array in fixed
+// registers across the section loop -- otherwise ptxas computes into fresh pairs and copies back
+__device__ __forceinline__ void pk_fma_acc(pk2& c, pk2 a, pk2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void pk_mul_acc(pk2& c, pk2 a) { asm("mul.rn.f32x2 %0, %1, %0;" : "+l"(c) : "l"(a)); }
+__device__ __forceinline__ pk2 pk_shfl_up(pk2 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+
+__device__ __forceinline__ pk2 pk_add(pk2 a, pk2 b) {
+    pk2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ pk2 pk_sub(pk2 a, pk2 b) {
+    pk2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ pk2 pk_swap(pk2 v) {
+    float lo, hi;
+    pk_split(v, lo, hi);
+    return pk_make(hi, lo);
+}
+
 // ---------------------------------------------------------------- ordered-chain primitives
 // Tiles of one row form a dependency chain (tile t needs the filter state left by tile t-1).
 // Work items are handed out by an atomic ticket in tile-major order, so the item a CTA waits

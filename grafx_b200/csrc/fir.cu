@@ -23,199 +23,272 @@
 
 namespace gfx {
 
+// ------------------------------------------------------------------ complex arithmetic on packed pairs
+// A complex number is one 64-bit register pair (re, im); add/sub are one FADD2, a twiddle multiply is
+// FMUL2 + FFMA2 with the twiddle supplied as two pairs:  forward (wr, wi) & (-wi, wr);  conjugate
+// (wr, -wi) & (wi, wr).  The table entry of angle t is { fwd.xy, fwd.zw, inv.xy, inv.zw } (32 bytes).
+struct Tw { pk2 a, b; };
+__device__ __forceinline__ pk2 cmul_tw(pk2 v, const Tw& w) {
+    float re, im;
+    pk_split(v, re, im);
+    return pk_fma(pk_dup(re), w.a, pk_mul(pk_dup(im), w.b));
+}
+__device__ __forceinline__ float4 ld_tw4(const float4* p) {
+    // volatile: keeps the twiddle requests where they are written (first), so that their latency
+    // overlaps the shared-memory loads and the butterfly that follow
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ Tw as_tw(const float4& e) {
+    Tw w;
+    w.a = pk_make(e.x, e.y);
+    w.b = pk_make(e.z, e.w);
+    return w;
+}
+__device__ __forceinline__ Tw const_tw(float c, float s, bool inv) {
+    // omega = exp(-i theta) = (c, -s) forward; conj for the inverse
+    Tw w;
+    const float wi = inv ? s : -s;
+    w.a = pk_make(c, wi);
+    w.b = pk_make(-wi, c);
+    return w;
+}
+
+template <bool INV>
+__device__ __forceinline__ void r4(pk2& a0, pk2& a1, pk2& a2, pk2& a3) {
+    // 4-point DFT (INV: inverse, unnormalised); omega_4 = -i
+    const pk2 s02 = pk_add(a0, a2), d02 = pk_sub(a0, a2), s13 = pk_add(a1, a3), d13 = pk_sub(a1, a3);
+    const pk2 r = pk_swap(d13);                     // (d13.im, d13.re)
+    const pk2 pm = pk_make(1.f, -1.f), mp = pk_make(-1.f, 1.f);
+    a0 = pk_add(s02, s13);
+    a2 = pk_sub(s02, s13);
+    a1 = pk_fma(r, INV ? mp : pm, d02);             // d02 -/+ i d13
+    a3 = pk_fma(r, INV ? pm : mp, d02);
+}
+
+// 16-point DFT in registers.  In: a[q] natural order.  Out: register a[4*i + j] holds X[4*j + i].
+template <bool INV>
+__device__ __forceinline__ void r16(pk2 (&a)[16]) {
+#pragma unroll
+    for (int q0 = 0; q0 < 4; ++q0) r4<INV>(a[q0], a[q0 + 4], a[q0 + 8], a[q0 + 12]);
+    // a[q0 + 4 r0] *= omega_16^(q0 r0)
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+    const Tw w1 = const_tw(C1, S1, INV), w2 = const_tw(H, H, INV), w3 = const_tw(S1, C1, INV);
+    const Tw w4 = const_tw(0.f, 1.f, INV), w6 = const_tw(-H, H, INV), w9 = const_tw(-C1, -S1, INV);
+    a[1 + 4] = cmul_tw(a[1 + 4], w1); a[2 + 4] = cmul_tw(a[2 + 4], w2); a[3 + 4] = cmul_tw(a[3 + 4], w3);
+    a[1 + 8] = cmul_tw(a[1 + 8], w2); a[2 + 8] = cmul_tw(a[2 + 8], w4); a[3 + 8] = cmul_tw(a[3 + 8], w6);
+    a[1 + 12] = cmul_tw(a[1 + 12], w3); a[2 + 12] = cmul_tw(a[2 + 12], w6); a[3 + 12] = cmul_tw(a[3 + 12], w9);
+#pragma unroll
+    for (int r0 = 0; r0 < 4; ++r0) r4<INV>(a[4 * r0], a[4 * r0 + 1], a[4 * r0 + 2], a[4 * r0 + 3]);
+}
+
+// shared-memory layout: complex point i lives at 64-bit slot i + (i >> 4) (one pad slot per 16 points):
+// every pass below is then bank-conflict free for 64-bit accesses.
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr int fft_smem_slots(int n) { return n + n / 16 + 16; }
+
+// ---- radix plans (forward order).  N = 1024: 4,16,16   N = 4096: 16,16,16   N = 16384: 4,16,16,16
+__host__ __device__ constexpr int plan_radix(int n, int s) {
+    return n == 4096 ? (s < 3 ? 16 : 1) : (s == 0 ? 4 : (s < (n == 1024 ? 3 : 4) ? 16 : 1));
+}
+__host__ __device__ constexpr int plan_m(int n, int s) {  // sub-transform length entering pass s
+    int m = n;
+    for (int i = 0; i < s; ++i) m /= plan_radix(n, i);
+    return m;
+}
+__host__ __device__ constexpr int plan_entries(int n, int s) {  // twiddles of pass s: (R-1) * ST, none when ST == 1
+    const int r = plan_radix(n, s);
+    const int st = r > 1 ? plan_m(n, s) / r : 1;
+    return (r > 1 && st > 1) ? (r - 1) * st : 0;
+}
+__host__ __device__ constexpr int plan_offset(int n, int s) {
+    int o = 0;
+    for (int i = 0; i < s; ++i) o += plan_entries(n, i);
+    return o;
+}
+__host__ __device__ constexpr int plan_total(int n) { return plan_offset(n, 4); }
+// plan memory (float4 units): [ half-angle table: n float2 = n/2 float4 | forward pass tables | inverse pass tables ]
+//   pass table entry (r-1) * ST + j = twiddle omega_M^(j r) as { wr, wi, -wi, wr } (forward) / { wr, -wi, wi, wr }
+//   (conjugate): consecutive threads (j) read consecutive 16-byte entries.
+
+template <int N, int NT, int S, bool INV>
+__device__ __forceinline__ void fft_pass(pk2* z, const float4* __restrict__ plan) {
+    constexpr int R = plan_radix(N, S);
+    constexpr int M = plan_m(N, S);
+    constexpr int ST = M / R;
+    const float4* tp = plan + N / 2 + plan_offset(N, S) + (INV ? plan_total(N) : 0);
+    for (int b = threadIdx.x; b < N / R; b += NT) {
+        const int j = b & (ST - 1);
+        const int i0 = (b - j) * R + j;
+        if constexpr (R == 4) {
+            float4 t1, t2, t3;
+            if constexpr (ST > 1) { t1 = ld_tw4(tp + j); t2 = ld_tw4(tp + ST + j); t3 = ld_tw4(tp + 2 * ST + j); }
+            pk2 a0 = z[pidx(i0)], a1 = z[pidx(i0 + ST)], a2 = z[pidx(i0 + 2 * ST)], a3 = z[pidx(i0 + 3 * ST)];
+            if constexpr (INV && ST > 1) {
+                a1 = cmul_tw(a1, as_tw(t1)); a2 = cmul_tw(a2, as_tw(t2)); a3 = cmul_tw(a3, as_tw(t3));
+            }
+            r4<INV>(a0, a1, a2, a3);
+            if constexpr (!INV && ST > 1) {
+                a1 = cmul_tw(a1, as_tw(t1)); a2 = cmul_tw(a2, as_tw(t2)); a3 = cmul_tw(a3, as_tw(t3));
+            }
+            z[pidx(i0)] = a0; z[pidx(i0 + ST)] = a1; z[pidx(i0 + 2 * ST)] = a2; z[pidx(i0 + 3 * ST)] = a3;
+        } else {
+            float4 tw[15];
+            if constexpr (ST > 1) {
+#pragma unroll
+                for (int r = 1; r < 16; ++r) tw[r - 1] = ld_tw4(tp + (r - 1) * ST + j);
+            }
+            pk2 a[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) a[q] = z[pidx(i0 + q * ST)];
+            if constexpr (INV && ST > 1) {
+#pragma unroll
+                for (int q = 1; q < 16; ++q) a[q] = cmul_tw(a[q], as_tw(tw[q - 1]));
+            }
+            r16<INV>(a);
+            // register a[4*i + jj] holds output index 4*jj + i
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int r = 4 * jj + i;
+                    pk2 v = a[4 * i + jj];
+                    if constexpr (!INV && ST > 1) {
+                        if (r > 0) v = cmul_tw(v, as_tw(tw[r - 1]));
+                    }
+                    z[pidx(i0 + r * ST)] = v;
+                }
+            }
+        }
+    }
+}
+
+template <int N, int NT>
+__device__ __forceinline__ void fft_forward(pk2* z, const float4* __restrict__ plan) {
+    fft_pass<N, NT, 0, false>(z, plan);
+    __syncthreads();
+    fft_pass<N, NT, 1, false>(z, plan);
+    __syncthreads();
+    fft_pass<N, NT, 2, false>(z, plan);
+    __syncthreads();
+    if constexpr (plan_radix(N, 3) > 1) {
+        fft_pass<N, NT, 3, false>(z, plan);
+        __syncthreads();
+    }
+}
+template <int N, int NT>
+__device__ __forceinline__ void fft_inverse(pk2* z, const float4* __restrict__ plan) {
+    if constexpr (plan_radix(N, 3) > 1) {
+        fft_pass<N, NT, 3, true>(z, plan);
+        __syncthreads();
+    }
+    fft_pass<N, NT, 2, true>(z, plan);
+    __syncthreads();
+    fft_pass<N, NT, 1, true>(z, plan);
+    __syncthreads();
+    fft_pass<N, NT, 0, true>(z, plan);
+    __syncthreads();
+}
+
+// digit reversal of the plans above: position (mixed-radix digits, first radix most significant) <-> bin
+template <int N> __device__ __forceinline__ int bin_of_pos(int p);
+template <int N> __device__ __forceinline__ int pos_of_bin(int k);
+template <> __device__ __forceinline__ int bin_of_pos<1024>(int p) { return (p >> 8) | (((p >> 4) & 15) << 2) | ((p & 15) << 6); }
+template <> __device__ __forceinline__ int pos_of_bin<1024>(int k) { return ((k & 3) << 8) | (((k >> 2) & 15) << 4) | (k >> 6); }
+template <> __device__ __forceinline__ int bin_of_pos<4096>(int p) { return (p >> 8) | (((p >> 4) & 15) << 4) | ((p & 15) << 8); }
+template <> __device__ __forceinline__ int pos_of_bin<4096>(int k) { return ((k & 15) << 8) | (((k >> 4) & 15) << 4) | (k >> 8); }
+template <> __device__ __forceinline__ int bin_of_pos<16384>(int p) {
+    return (p >> 12) | (((p >> 8) & 15) << 2) | (((p >> 4) & 15) << 6) | ((p & 15) << 10);
+}
+template <> __device__ __forceinline__ int pos_of_bin<16384>(int k) {
+    return ((k & 3) << 12) | (((k >> 2) & 15) << 8) | (((k >> 6) & 15) << 4) | (k >> 10);
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
     return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
-
-template <int LOG4>
-__device__ __forceinline__ int drev4(int p) {
-    unsigned r = __brev((unsigned)p) >> (32 - 2 * LOG4);
-    return (int)(((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u));
+__device__ __forceinline__ float2 ld_c(const pk2* z, int i) {
+    float re, im;
+    pk_split(z[pidx(i)], re, im);
+    return make_float2(re, im);
+}
+__device__ __forceinline__ void st_c(pk2* z, int i, float re, float im) { z[pidx(i)] = pk_make(re, im); }
+__device__ __forceinline__ float2 half_tw(const float4* __restrict__ plan, int k) {  // exp(-i pi k / N), k < N
+    return __ldg(reinterpret_cast<const float2*>(plan) + k);
 }
 
-// ------------------------------------------------------------------ FFT passes (in place, smem)
-template <int N, int NT, int M>
-__device__ __forceinline__ void dif_pass(float* re, float* im, const float2* __restrict__ tw) {
-    constexpr int ST = M / 4;
-    constexpr int TWS = 2 * (N / M);  // omega_M^j = tw[j * TWS],  tw[k] = exp(-i pi k / N)
-    for (int b = threadIdx.x; b < N / 4; b += NT) {
-        const int j = b & (ST - 1);
-        const int i0 = ((b - j) << 2) + j;
-        float ar[4], ai[4];
-        if (ST == 1) {
-            const float4 vr = *reinterpret_cast<const float4*>(re + i0);
-            const float4 vi = *reinterpret_cast<const float4*>(im + i0);
-            ar[0] = vr.x; ar[1] = vr.y; ar[2] = vr.z; ar[3] = vr.w;
-            ai[0] = vi.x; ai[1] = vi.y; ai[2] = vi.z; ai[3] = vi.w;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { ar[q] = re[i0 + q * ST]; ai[q] = im[i0 + q * ST]; }
-        }
-        // 4-point DFT, omega_4 = -i
-        const float s02r = ar[0] + ar[2], s02i = ai[0] + ai[2], d02r = ar[0] - ar[2], d02i = ai[0] - ai[2];
-        const float s13r = ar[1] + ar[3], s13i = ai[1] + ai[3], d13r = ar[1] - ar[3], d13i = ai[1] - ai[3];
-        float2 u0 = make_float2(s02r + s13r, s02i + s13i);
-        float2 u2 = make_float2(s02r - s13r, s02i - s13i);
-        float2 u1 = make_float2(d02r + d13i, d02i - d13r);  // d02 - i d13
-        float2 u3 = make_float2(d02r - d13i, d02i + d13r);  // d02 + i d13
-        if (ST == 1) {
-            *reinterpret_cast<float4*>(re + i0) = make_float4(u0.x, u1.x, u2.x, u3.x);
-            *reinterpret_cast<float4*>(im + i0) = make_float4(u0.y, u1.y, u2.y, u3.y);
-        } else {
-            const float2 w1 = __ldg(tw + j * TWS);
-            const float2 w2 = cmul(w1, w1);
-            const float2 w3 = cmul(w2, w1);
-            u1 = cmul(u1, w1); u2 = cmul(u2, w2); u3 = cmul(u3, w3);
-            re[i0] = u0.x; im[i0] = u0.y;
-            re[i0 + ST] = u1.x; im[i0 + ST] = u1.y;
-            re[i0 + 2 * ST] = u2.x; im[i0 + 2 * ST] = u2.y;
-            re[i0 + 3 * ST] = u3.x; im[i0 + 3 * ST] = u3.y;
-        }
-    }
-}
-
-template <int N, int NT, int M>
-__device__ __forceinline__ void dit_pass(float* re, float* im, const float2* __restrict__ tw) {
-    constexpr int ST = M / 4;
-    constexpr int TWS = 2 * (N / M);
-    for (int b = threadIdx.x; b < N / 4; b += NT) {
-        const int j = b & (ST - 1);
-        const int i0 = ((b - j) << 2) + j;
-        float2 u0, u1, u2, u3;
-        if (ST == 1) {
-            const float4 vr = *reinterpret_cast<const float4*>(re + i0);
-            const float4 vi = *reinterpret_cast<const float4*>(im + i0);
-            u0 = make_float2(vr.x, vi.x); u1 = make_float2(vr.y, vi.y);
-            u2 = make_float2(vr.z, vi.z); u3 = make_float2(vr.w, vi.w);
-        } else {
-            u0 = make_float2(re[i0], im[i0]);
-            u1 = make_float2(re[i0 + ST], im[i0 + ST]);
-            u2 = make_float2(re[i0 + 2 * ST], im[i0 + 2 * ST]);
-            u3 = make_float2(re[i0 + 3 * ST], im[i0 + 3 * ST]);
-            const float2 w1 = __ldg(tw + j * TWS);
-            const float2 w2 = cmul(w1, w1);
-            const float2 w3 = cmul(w2, w1);
-            u1 = cmulc(u1, w1); u2 = cmulc(u2, w2); u3 = cmulc(u3, w3);
-        }
-        // inverse 4-point DFT (omega_4^-1 = +i), unnormalised
-        const float s02r = u0.x + u2.x, s02i = u0.y + u2.y, d02r = u0.x - u2.x, d02i = u0.y - u2.y;
-        const float s13r = u1.x + u3.x, s13i = u1.y + u3.y, d13r = u1.x - u3.x, d13i = u1.y - u3.y;
-        const float a0r = s02r + s13r, a0i = s02i + s13i;
-        const float a2r = s02r - s13r, a2i = s02i - s13i;
-        const float a1r = d02r - d13i, a1i = d02i + d13r;  // d02 + i d13
-        const float a3r = d02r + d13i, a3i = d02i - d13r;  // d02 - i d13
-        if (ST == 1) {
-            *reinterpret_cast<float4*>(re + i0) = make_float4(a0r, a1r, a2r, a3r);
-            *reinterpret_cast<float4*>(im + i0) = make_float4(a0i, a1i, a2i, a3i);
-        } else {
-            re[i0] = a0r; im[i0] = a0i;
-            re[i0 + ST] = a1r; im[i0 + ST] = a1i;
-            re[i0 + 2 * ST] = a2r; im[i0 + 2 * ST] = a2i;
-            re[i0 + 3 * ST] = a3r; im[i0 + 3 * ST] = a3i;
-        }
-    }
-}
-
-template <int N, int NT, int M>
-struct FwdPasses {
-    static __device__ __forceinline__ void run(float* re, float* im, const float2* tw) {
-        dif_pass<N, NT, M>(re, im, tw);
-        __syncthreads();
-        if constexpr (M > 4) FwdPasses<N, NT, M / 4>::run(re, im, tw);
-    }
-};
-template <int N, int NT, int M>
-struct InvPasses {
-    static __device__ __forceinline__ void run(float* re, float* im, const float2* tw) {
-        dit_pass<N, NT, M>(re, im, tw);
-        __syncthreads();
-        if constexpr (M < N) InvPasses<N, NT, M * 4>::run(re, im, tw);
-    }
-};
-
-template <int N> struct Log4;
-template <> struct Log4<1024> { static constexpr int v = 5; };
-template <> struct Log4<4096> { static constexpr int v = 6; };
-template <> struct Log4<16384> { static constexpr int v = 7; };
+// The last radix is 16 in every plan: bins k < N/2 are the positions whose last digit is < 8; bin N/2 is
+// position 8, bin 0 position 0.
+#define GFX_FOR_PAIRS(N, NT)                                                     \
+    for (int q = threadIdx.x; q < (N) / 2; q += (NT))                            \
+        if (const int p = ((q >> 3) << 4) | (q & 7); true)                       \
+            if (const int k = bin_of_pos<N>(p); true)
 
 // packed complex FFT Z (digit-reversed order, in smem) -> true half spectrum A (same order):
 //   slot 0 holds (A[0], A[N]) (both real); slot pos(k) holds A[k], 0 < k < N.  `scale` multiplies.
 template <int N, int NT>
-__device__ __forceinline__ void untangle_inplace(float* re, float* im, const float2* __restrict__ tw, float scale) {
-    constexpr int L4 = Log4<N>::v;
-    for (int q = threadIdx.x; q < N / 2; q += NT) {
-        const int p = ((q >> 1) << 2) | (q & 1);
-        const int k = drev4<L4>(p);
+__device__ __forceinline__ void untangle_inplace(pk2* z, const float4* __restrict__ tw4, float scale) {
+    GFX_FOR_PAIRS(N, NT) {
         if (k == 0) {
-            const float a = re[0], b = im[0];
-            re[0] = (a + b) * scale; im[0] = (a - b) * scale;
-            im[2] = -im[2] * scale; re[2] = re[2] * scale;  // k = N/2 lives at position 2: conj
+            const float2 z0 = ld_c(z, 0), zh = ld_c(z, 8);
+            st_c(z, 0, (z0.x + z0.y) * scale, (z0.x - z0.y) * scale);
+            st_c(z, 8, zh.x * scale, -zh.y * scale);  // k = N/2: conj
             continue;
         }
-        const int pm = drev4<L4>(N - k);
-        const float2 zk = make_float2(re[p], im[p]), zm = make_float2(re[pm], im[pm]);
-        const float2 w = __ldg(tw + k);
+        const int pm = pos_of_bin<N>(N - k);
+        const float2 zk = ld_c(z, p), zm = ld_c(z, pm);
+        const float2 w = half_tw(tw4, k);
         const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
         const float dr = zk.x - zm.x, di = zk.y + zm.y;
-        // O = -(i/2) w D
-        const float2 wd = cmul(w, make_float2(dr, di));
+        const float2 wd = cmul(w, make_float2(dr, di));  // O = -(i/2) w D
         const float orr = 0.5f * wd.y, oi = -0.5f * wd.x;
-        re[p] = (er + orr) * scale; im[p] = (ei + oi) * scale;
-        re[pm] = (er - orr) * scale; im[pm] = -(ei - oi) * scale;
+        st_c(z, p, (er + orr) * scale, (ei + oi) * scale);
+        st_c(z, pm, (er - orr) * scale, -(ei - oi) * scale);
     }
 }
 
 // true spectrum Y (digit-reversed order, slot 0 = (Y[0], Y[N])) -> packed complex Z' for the inverse
 template <int N, int NT>
-__device__ __forceinline__ void retangle_inplace(float* re, float* im, const float2* __restrict__ tw) {
-    constexpr int L4 = Log4<N>::v;
-    for (int q = threadIdx.x; q < N / 2; q += NT) {
-        const int p = ((q >> 1) << 2) | (q & 1);
-        const int k = drev4<L4>(p);
+__device__ __forceinline__ void retangle_inplace(pk2* z, const float4* __restrict__ tw4) {
+    GFX_FOR_PAIRS(N, NT) {
         if (k == 0) {
-            const float y0 = re[0], yn = im[0];
-            re[0] = 0.5f * (y0 + yn); im[0] = 0.5f * (y0 - yn);
-            im[2] = -im[2];
+            const float2 y0 = ld_c(z, 0), yh = ld_c(z, 8);
+            st_c(z, 0, 0.5f * (y0.x + y0.y), 0.5f * (y0.x - y0.y));
+            st_c(z, 8, yh.x, -yh.y);
             continue;
         }
-        const int pm = drev4<L4>(N - k);
-        const float2 yk = make_float2(re[p], im[p]), ym = make_float2(re[pm], im[pm]);
-        const float2 w = __ldg(tw + k);
+        const int pm = pos_of_bin<N>(N - k);
+        const float2 yk = ld_c(z, p), ym = ld_c(z, pm);
+        const float2 w = half_tw(tw4, k);
         const float er = 0.5f * (yk.x + ym.x), ei = 0.5f * (yk.y - ym.y);
         const float dr = yk.x - ym.x, di = yk.y + ym.y;
-        // O' = (i/2) conj(w) D'
-        const float2 wd = cmulc(make_float2(dr, di), w);
+        const float2 wd = cmulc(make_float2(dr, di), w);  // O' = (i/2) conj(w) D'
         const float orr = -0.5f * wd.y, oi = 0.5f * wd.x;
-        re[p] = er + orr; im[p] = ei + oi;
-        re[pm] = er - orr; im[pm] = -(ei - oi);
+        st_c(z, p, er + orr, ei + oi);
+        st_c(z, pm, er - orr, -(ei - oi));
     }
 }
 
 // fused: untangle X, multiply by the (already 1/N-scaled) filter spectrum H, retangle
 template <int N, int NT>
-__device__ __forceinline__ void pointwise_filter(float* re, float* im, const float2* __restrict__ tw,
-                                                 const float2* __restrict__ H) {
-    constexpr int L4 = Log4<N>::v;
-    for (int q = threadIdx.x; q < N / 2; q += NT) {
-        const int p = ((q >> 1) << 2) | (q & 1);
-        const int k = drev4<L4>(p);
+__device__ __forceinline__ void pointwise_filter(pk2* z, const float4* __restrict__ tw4, const float2* __restrict__ H) {
+    GFX_FOR_PAIRS(N, NT) {
         if (k == 0) {
-            const float a = re[0], b = im[0];
+            const float2 z0 = ld_c(z, 0), zh = ld_c(z, 8);
             const float2 h0 = H[0];
-            const float y0 = (a + b) * h0.x, yn = (a - b) * h0.y;
-            re[0] = 0.5f * (y0 + yn); im[0] = 0.5f * (y0 - yn);
-            // k = N/2 at position 2: X = conj(Z), Y = X H, Z' = conj(Y) = Z conj(H)
-            const float2 z2 = make_float2(re[2], im[2]);
-            const float2 r2 = cmulc(z2, H[2]);
-            re[2] = r2.x; im[2] = r2.y;
+            const float y0 = (z0.x + z0.y) * h0.x, yn = (z0.x - z0.y) * h0.y;
+            st_c(z, 0, 0.5f * (y0 + yn), 0.5f * (y0 - yn));
+            const float2 r2 = cmulc(zh, H[8]);  // X = conj(Z), Y = X H, Z' = conj(Y) = Z conj(H)
+            st_c(z, 8, r2.x, r2.y);
             continue;
         }
-        const int pm = drev4<L4>(N - k);
-        const float2 zk = make_float2(re[p], im[p]), zm = make_float2(re[pm], im[pm]);
-        const float2 w = __ldg(tw + k);
+        const int pm = pos_of_bin<N>(N - k);
+        const float2 zk = ld_c(z, p), zm = ld_c(z, pm);
+        const float2 w = half_tw(tw4, k);
         float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
         float dr = zk.x - zm.x, di = zk.y + zm.y;
         float2 wd = cmul(w, make_float2(dr, di));
@@ -228,16 +301,16 @@ __device__ __forceinline__ void pointwise_filter(float* re, float* im, const flo
         dr = yk.x - ym.x; di = yk.y + ym.y;
         wd = cmulc(make_float2(dr, di), w);
         orr = -0.5f * wd.y; oi = 0.5f * wd.x;
-        re[p] = er + orr; im[p] = ei + oi;
-        re[pm] = er - orr; im[pm] = -(ei - oi);
+        st_c(z, p, er + orr, ei + oi);
+        st_c(z, pm, er - orr, -(ei - oi));
     }
 }
 
 // ------------------------------------------------------------------ segment load / store
 // loads F = 2N real samples src[s0 .. s0+F) (zero outside [0, len)) as z[j] = x[2j] + i x[2j+1]
 template <int N, int NT>
-__device__ __forceinline__ void load_packed(float* re, float* im, const float* __restrict__ src, long long s0,
-                                            long long len, bool vec_ok) {
+__device__ __forceinline__ void load_packed(pk2* z, const float* __restrict__ src, long long s0, long long len,
+                                            bool vec_ok) {
     if (vec_ok && (s0 & 3) == 0) {
         for (int t = threadIdx.x; t < N / 2; t += NT) {
             const long long pos = s0 + 4LL * t;
@@ -250,42 +323,44 @@ __device__ __forceinline__ void load_packed(float* re, float* im, const float* _
                 for (int c = 0; c < 4; ++c) e[c] = (pos + c >= 0 && pos + c < len) ? src[pos + c] : 0.f;
                 v = make_float4(e[0], e[1], e[2], e[3]);
             }
-            *reinterpret_cast<float2*>(re + 2 * t) = make_float2(v.x, v.z);
-            *reinterpret_cast<float2*>(im + 2 * t) = make_float2(v.y, v.w);
+            z[pidx(2 * t)] = pk_make(v.x, v.y);
+            z[pidx(2 * t + 1)] = pk_make(v.z, v.w);
         }
     } else {
-        for (int i = threadIdx.x; i < 2 * N; i += NT) {
-            const long long pos = s0 + i;
-            const float v = (pos >= 0 && pos < len) ? src[pos] : 0.f;
-            if (i & 1) im[i >> 1] = v; else re[i >> 1] = v;
+        for (int j = threadIdx.x; j < N; j += NT) {
+            const long long pos = s0 + 2LL * j;
+            const float a = (pos >= 0 && pos < len) ? src[pos] : 0.f;
+            const float b = (pos + 1 >= 0 && pos + 1 < len) ? src[pos + 1] : 0.f;
+            z[pidx(j)] = pk_make(a, b);
         }
     }
 }
 
 // writes segment samples [i_lo, i_lo + count) to dst[d0 .. d0+count), clipped to [0, len)
 template <int N, int NT>
-__device__ __forceinline__ void store_packed(const float* re, const float* im, float* __restrict__ dst, int i_lo,
-                                             int count, long long d0, long long len, bool vec_ok) {
+__device__ __forceinline__ void store_packed(const pk2* z, float* __restrict__ dst, int i_lo, int count, long long d0,
+                                             long long len, bool vec_ok) {
     if (vec_ok && (i_lo & 3) == 0 && (d0 & 3) == 0 && (count & 3) == 0) {
         for (int t = threadIdx.x; t < count / 4; t += NT) {
             const int i = i_lo + 4 * t;
             const long long pos = d0 + 4LL * t;
+            const float2 a = ld_c(z, i >> 1), b = ld_c(z, (i >> 1) + 1);
             if (pos >= 0 && pos + 4 <= len) {
-                const float2 r = *reinterpret_cast<const float2*>(re + (i >> 1));
-                const float2 m = *reinterpret_cast<const float2*>(im + (i >> 1));
-                stg_stream(reinterpret_cast<float4*>(dst + pos), make_float4(r.x, m.x, r.y, m.y));
+                stg_stream(reinterpret_cast<float4*>(dst + pos), make_float4(a.x, a.y, b.x, b.y));
             } else {
-                for (int c = 0; c < 4; ++c) {
-                    const long long pc = pos + c;
-                    if (pc >= 0 && pc < len) dst[pc] = ((i + c) & 1) ? im[(i + c) >> 1] : re[(i + c) >> 1];
-                }
+                const float e[4] = {a.x, a.y, b.x, b.y};
+                for (int c = 0; c < 4; ++c)
+                    if (pos + c >= 0 && pos + c < len) dst[pos + c] = e[c];
             }
         }
     } else {
         for (int t = threadIdx.x; t < count; t += NT) {
             const int i = i_lo + t;
             const long long pos = d0 + t;
-            if (pos >= 0 && pos < len) dst[pos] = (i & 1) ? im[i >> 1] : re[i >> 1];
+            if (pos >= 0 && pos < len) {
+                const float2 a = ld_c(z, i >> 1);
+                dst[pos] = (i & 1) ? a.y : a.x;
+            }
         }
     }
 }
@@ -304,62 +379,56 @@ struct RowMap {  // output row -> (x row, h row) with channel broadcasting
 template <int N, int NT>
 __global__ void __launch_bounds__(NT) fir_spectrum_kernel(const float* __restrict__ h, float2* __restrict__ Hs,
                                                           int Nh, int part_len, int P,
-                                                          const float2* __restrict__ tw, int vec_ok) {
-    extern __shared__ __align__(16) float smem_f[];
-    float* re = smem_f;
-    float* im = smem_f + N;
+                                                          const float4* __restrict__ tw, int vec_ok) {
+    extern __shared__ __align__(16) pk2 zbuf[];
     const int hrow = blockIdx.x / P, part = blockIdx.x - hrow * P;
     const float* src = h + (size_t)hrow * Nh + (size_t)part * part_len;
     long long len = (long long)Nh - (long long)part * part_len;
     if (len > part_len) len = part_len;
     const bool v = vec_ok && ((((size_t)hrow * Nh + (size_t)part * part_len) & 3) == 0);
-    load_packed<N, NT>(re, im, src, 0, len, v);
+    load_packed<N, NT>(zbuf, src, 0, len, v);
     __syncthreads();
-    FwdPasses<N, NT, N>::run(re, im, tw);
-    untangle_inplace<N, NT>(re, im, tw, 1.f / (float)N);
+    fft_forward<N, NT>(zbuf, tw);
+    untangle_inplace<N, NT>(zbuf, tw, 1.f / (float)N);
     __syncthreads();
     float2* out = Hs + (size_t)blockIdx.x * N;
-    for (int i = threadIdx.x; i < N; i += NT) out[i] = make_float2(re[i], im[i]);
+    for (int i = threadIdx.x; i < N; i += NT) out[i] = ld_c(zbuf, i);
 }
 
 // single-partition overlap-save: block j produces full-convolution samples [j*hop, (j+1)*hop)
 template <int N, int NT>
 __global__ void __launch_bounds__(NT) fir_ols_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                      const float2* __restrict__ Hs, RowMap rm, long long L, int pre,
-                                                     int hop, int shift, int nblk, const float2* __restrict__ tw,
+                                                     int hop, int shift, int nblk, const float4* __restrict__ tw,
                                                      int vec_ok) {
-    extern __shared__ __align__(16) float smem_f[];
-    float* re = smem_f;
-    float* im = smem_f + N;
+    extern __shared__ __align__(16) pk2 zbuf[];
     const int row = blockIdx.x / nblk, j = blockIdx.x - row * nblk;
     int xr, hr;
     rm.map(row, xr, hr);
     const long long m0 = (long long)j * hop;
-    load_packed<N, NT>(re, im, x + (size_t)xr * L, m0 - pre, L, vec_ok);
+    load_packed<N, NT>(zbuf, x + (size_t)xr * L, m0 - pre, L, vec_ok);
     __syncthreads();
-    FwdPasses<N, NT, N>::run(re, im, tw);
-    pointwise_filter<N, NT>(re, im, tw, Hs + (size_t)hr * N);
+    fft_forward<N, NT>(zbuf, tw);
+    pointwise_filter<N, NT>(zbuf, tw, Hs + (size_t)hr * N);
     __syncthreads();
-    InvPasses<N, NT, 4>::run(re, im, tw);
-    store_packed<N, NT>(re, im, y + (size_t)row * L, pre, hop, m0 - shift, L, vec_ok);
+    fft_inverse<N, NT>(zbuf, tw);
+    store_packed<N, NT>(zbuf, y + (size_t)row * L, pre, hop, m0 - shift, L, vec_ok);
 }
 
 // UPOLS step 1: spectra of input blocks.  Xs[(rloc * nblk + j) * N + pos] = rfft of x[(j-1)B, (j+1)B), B = N
 template <int N, int NT>
 __global__ void __launch_bounds__(NT) fir_xspec_kernel(const float* __restrict__ x, float2* __restrict__ Xs,
                                                        int xrow0, long long L, int nblk,
-                                                       const float2* __restrict__ tw, int vec_ok) {
-    extern __shared__ __align__(16) float smem_f[];
-    float* re = smem_f;
-    float* im = smem_f + N;
+                                                       const float4* __restrict__ tw, int vec_ok) {
+    extern __shared__ __align__(16) pk2 zbuf[];
     const int rloc = blockIdx.x / nblk, j = blockIdx.x - rloc * nblk;
-    load_packed<N, NT>(re, im, x + (size_t)(xrow0 + rloc) * L, ((long long)j - 1) * N, L, vec_ok);
+    load_packed<N, NT>(zbuf, x + (size_t)(xrow0 + rloc) * L, ((long long)j - 1) * N, L, vec_ok);
     __syncthreads();
-    FwdPasses<N, NT, N>::run(re, im, tw);
-    untangle_inplace<N, NT>(re, im, tw, 1.f);
+    fft_forward<N, NT>(zbuf, tw);
+    untangle_inplace<N, NT>(zbuf, tw, 1.f);
     __syncthreads();
     float2* out = Xs + (size_t)blockIdx.x * N;
-    for (int i = threadIdx.x; i < N; i += NT) out[i] = make_float2(re[i], im[i]);
+    for (int i = threadIdx.x; i < N; i += NT) out[i] = ld_c(zbuf, i);
 }
 
 // UPOLS step 2: Y_j = sum_p X_{j-p} H_p, inverse FFT, keep the second half of the block
@@ -367,10 +436,8 @@ template <int N, int NT>
 __global__ void __launch_bounds__(NT) fir_upols_kernel(const float2* __restrict__ Xs, const float2* __restrict__ Hs,
                                                        float* __restrict__ y, RowMap rm, int row0, int xrow0,
                                                        int hrow0, long long L, int P, int nblk, int shift,
-                                                       const float2* __restrict__ tw, int vec_ok) {
-    extern __shared__ __align__(16) float smem_f[];
-    float* re = smem_f;
-    float* im = smem_f + N;
+                                                       const float4* __restrict__ tw, int vec_ok) {
+    extern __shared__ __align__(16) pk2 zbuf[];
     const int rloc = blockIdx.x / nblk, j = blockIdx.x - rloc * nblk;
     const int row = row0 + rloc;
     int xr, hr;
@@ -393,20 +460,31 @@ __global__ void __launch_bounds__(NT) fir_upols_kernel(const float2* __restrict_
                 ai = fmaf(xv.x, hv.y, ai); ai = fmaf(xv.y, hv.x, ai);
             }
         }
-        re[i] = ar; im[i] = ai;
+        st_c(zbuf, i, ar, ai);
     }
     __syncthreads();
-    retangle_inplace<N, NT>(re, im, tw);
+    retangle_inplace<N, NT>(zbuf, tw);
     __syncthreads();
-    InvPasses<N, NT, 4>::run(re, im, tw);
-    store_packed<N, NT>(re, im, y + (size_t)row * L, N, N, (long long)j * N - shift, L, vec_ok);
+    fft_inverse<N, NT>(zbuf, tw);
+    store_packed<N, NT>(zbuf, y + (size_t)row * L, N, N, (long long)j * N - shift, L, vec_ok);
 }
 
-__global__ void fft_plan_kernel(float2* tw, int n) {
+__global__ void fft_plan_half_kernel(float2* ht, int n) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < 2 * n) {
+    if (k < n) {
         const double a = (double)k / (double)n;
-        tw[k] = make_float2((float)cospi(a), (float)(-sinpi(a)));
+        ht[k] = make_float2((float)cospi(a), (float)(-sinpi(a)));
+    }
+}
+__global__ void fft_plan_pass_kernel(float4* fwd, float4* inv, int M, int R) {
+    const int ST = M / R;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < (R - 1) * ST) {
+        const int r = e / ST + 1, j = e - (r - 1) * ST;
+        const double a = 2.0 * (double)((long long)j * r) / (double)M;  // angle = 2 pi j r / M
+        const float wr = (float)cospi(a), wi = (float)(-sinpi(a));
+        fwd[e] = make_float4(wr, wi, -wi, wr);
+        inv[e] = make_float4(wr, -wi, wi, wr);
     }
 }
 
@@ -425,7 +503,7 @@ static int set_smem(K kern, size_t smem) {
 struct FirArgs {
     const float* x; const float* h; float* y;
     int batch, cx, ch; long long L; int Nh; int shift;
-    const float2* tw; unsigned char* ws; size_t ws_bytes; cudaStream_t stream;
+    const float4* tw; unsigned char* ws; size_t ws_bytes; cudaStream_t stream;
 };
 
 template <int N, int NT>
@@ -435,7 +513,7 @@ static int run_ols(const FirArgs& a) {
     const size_t need = (size_t)hrows * N * sizeof(float2);
     if (!a.ws || a.ws_bytes < need) return GFX_ERR_WORKSPACE;
     float2* Hs = (float2*)a.ws;
-    const size_t smem = (size_t)2 * N * sizeof(float);
+    const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
     static bool configured = false;
     if (!configured) {
         if (set_smem(fir_spectrum_kernel<N, NT>, smem) || set_smem(fir_ols_kernel<N, NT>, smem)) return GFX_ERR_CUDA;
@@ -472,7 +550,7 @@ static int run_upols(const FirArgs& a) {
     if (!a.ws || a.ws_bytes < per_item) return GFX_ERR_WORKSPACE;
     long long chunk = (long long)(a.ws_bytes / per_item);
     if (chunk > a.batch) chunk = a.batch;
-    const size_t smem = (size_t)2 * N * sizeof(float);
+    const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
     static bool configured = false;
     if (!configured) {
         if (set_smem(fir_spectrum_kernel<N, NT>, smem) || set_smem(fir_xspec_kernel<N, NT>, smem) ||
@@ -507,12 +585,24 @@ extern "C" {
 
 int gfx_fir_fft_size(int filter_len) { return filter_len <= 0 ? GFX_ERR_INVALID : gfx::pick_fft_size(filter_len); }
 
-size_t gfx_fft_plan_bytes(int n) { return (size_t)2 * n * sizeof(float2); }
+size_t gfx_fft_plan_bytes(int n) {
+    if (n != 1024 && n != 4096 && n != 16384) return 0;
+    return ((size_t)n / 2 + 2 * (size_t)gfx::plan_total(n)) * sizeof(float4);
+}
 
 int gfx_fft_plan_init(void* plan, int n, void* stream) {
     if (!plan || (n != 1024 && n != 4096 && n != 16384)) return GFX_ERR_INVALID;
-    gfx::fft_plan_kernel<<<(2 * n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float2*)plan, n);
+    float4* base = (float4*)plan;
+    gfx::fft_plan_half_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float2*)plan, n);
     GFX_CUDA_CHECK(cudaGetLastError());
+    for (int s = 0; s < 4; ++s) {
+        const int entries = gfx::plan_entries(n, s);
+        if (entries == 0) continue;
+        float4* fwd = base + n / 2 + gfx::plan_offset(n, s);
+        gfx::fft_plan_pass_kernel<<<(entries + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+            fwd, fwd + gfx::plan_total(n), gfx::plan_m(n, s), gfx::plan_radix(n, s));
+        GFX_CUDA_CHECK(cudaGetLastError());
+    }
     return GFX_OK;
 }
 
@@ -536,15 +626,15 @@ int gfx_fir_conv_f32(const float* x, const float* h, float* y, int batch, int cx
     if (!x || !h || !y || !plan) return GFX_ERR_INVALID;
     if (batch <= 0 || cx <= 0 || ch <= 0 || L <= 0 || filter_len <= 0) return GFX_ERR_INVALID;
     if (cx != ch && cx != 1 && ch != 1) return GFX_ERR_INVALID;
-    FirArgs a{x, h, y, batch, cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, (const float2*)plan,
+    FirArgs a{x, h, y, batch, cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, (const float4*)plan,
               (unsigned char*)workspace, workspace_bytes, (cudaStream_t)stream};
     const int n = pick_fft_size(filter_len);
     if (filter_len <= 16384) {
-        if (n == 1024) return run_ols<1024, 256>(a);
+        if (n == 1024) return run_ols<1024, 128>(a);
         if (n == 4096) return run_ols<4096, 256>(a);
-        return run_ols<16384, 1024>(a);
+        return run_ols<16384, 512>(a);
     }
-    return run_upols<16384, 1024>(a);
+    return run_upols<16384, 512>(a);
 }
 
 }  // extern "C"
