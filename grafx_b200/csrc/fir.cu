@@ -118,13 +118,17 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float4* __restrict__ plan
     constexpr int M = plan_m(N, S);
     constexpr int ST = M / R;
     const float4* tp = plan + N / 2 + plan_offset(N, S) + (INV ? plan_total(N) : 0);
+    // slot of element q of a butterfly: pidx(i0 + q ST) = pidx(i0) + q * PST  (ST is a multiple of 16, or 1)
+    constexpr int PST = ST >= 16 ? ST + ST / 16 : 1;
+    static_assert(ST == 1 || ST % 16 == 0, "stride must keep the padding pattern linear");
     for (int b = threadIdx.x; b < N / R; b += NT) {
         const int j = b & (ST - 1);
         const int i0 = (b - j) * R + j;
+        pk2* zb = z + pidx(i0);
         if constexpr (R == 4) {
             float4 t1, t2, t3;
             if constexpr (ST > 1) { t1 = ld_tw4(tp + j); t2 = ld_tw4(tp + ST + j); t3 = ld_tw4(tp + 2 * ST + j); }
-            pk2 a0 = z[pidx(i0)], a1 = z[pidx(i0 + ST)], a2 = z[pidx(i0 + 2 * ST)], a3 = z[pidx(i0 + 3 * ST)];
+            pk2 a0 = zb[0], a1 = zb[PST], a2 = zb[2 * PST], a3 = zb[3 * PST];
             if constexpr (INV && ST > 1) {
                 a1 = cmul_tw(a1, as_tw(t1)); a2 = cmul_tw(a2, as_tw(t2)); a3 = cmul_tw(a3, as_tw(t3));
             }
@@ -132,7 +136,7 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float4* __restrict__ plan
             if constexpr (!INV && ST > 1) {
                 a1 = cmul_tw(a1, as_tw(t1)); a2 = cmul_tw(a2, as_tw(t2)); a3 = cmul_tw(a3, as_tw(t3));
             }
-            z[pidx(i0)] = a0; z[pidx(i0 + ST)] = a1; z[pidx(i0 + 2 * ST)] = a2; z[pidx(i0 + 3 * ST)] = a3;
+            zb[0] = a0; zb[PST] = a1; zb[2 * PST] = a2; zb[3 * PST] = a3;
         } else {
             float4 tw[15];
             if constexpr (ST > 1) {
@@ -141,7 +145,7 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float4* __restrict__ plan
             }
             pk2 a[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) a[q] = z[pidx(i0 + q * ST)];
+            for (int q = 0; q < 16; ++q) a[q] = zb[q * PST];
             if constexpr (INV && ST > 1) {
 #pragma unroll
                 for (int q = 1; q < 16; ++q) a[q] = cmul_tw(a[q], as_tw(tw[q - 1]));
@@ -157,7 +161,7 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float4* __restrict__ plan
                     if constexpr (!INV && ST > 1) {
                         if (r > 0) v = cmul_tw(v, as_tw(tw[r - 1]));
                     }
-                    z[pidx(i0 + r * ST)] = v;
+                    zb[r * PST] = v;
                 }
             }
         }
@@ -632,9 +636,9 @@ int gfx_fir_conv_f32(const float* x, const float* h, float* y, int batch, int cx
     if (filter_len <= 16384) {
         if (n == 1024) return run_ols<1024, 128>(a);
         if (n == 4096) return run_ols<4096, 256>(a);
-        return run_ols<16384, 512>(a);
+        return run_ols<16384, 1024>(a);
     }
-    return run_upols<16384, 512>(a);
+    return run_upols<16384, 1024>(a);
 }
 
 }  // extern "C"
