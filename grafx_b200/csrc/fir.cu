@@ -9,51 +9,115 @@
 // Semantics: y[n] = sum_k h[k] x[n + shift - k], n < L; shift = 0 (causal) or N//2 (zerophase);
 // rows of x and h broadcast over the channel axis like tensor broadcasting does upstream.
 //
-// On chip: a real block of F = 2n samples is packed into n complex points (even/odd), transformed
-// by an in-place radix-4 decimation-in-frequency FFT in shared memory (split re/im arrays, output
-// left in base-4 digit-reversed order), untangled / multiplied by the filter spectrum / re-tangled
-// pairwise in that order, and brought back by the matching decimation-in-time inverse -- no
-// bit-reversal pass, no complex intermediate in HBM.  n is 1024, 4096 or 16384.
-//   short filters (N <= 16384): one spectrum per filter row, blocks of F-N+1 new outputs;
-//   long filters (reverb IRs):  uniformly partitioned overlap-save, partition = n taps, X and H
-//       partition spectra kept in a workspace sized to stay L2-resident, frequency-domain
-//       accumulation, one inverse FFT per block.
-// Twiddles e^{-i pi k / n} come from a table built once per n (gfx_fft_plan_init) in double.
+// On chip: a real block of F = 2n samples is packed into n complex points (even/odd) and transformed
+// by an in-place mixed-radix decimation-in-frequency FFT in shared memory (packed (re,im) 64-bit
+// slots, radix 16 / 16 / {-,2,4} / 16, output left digit-reversed); the matching decimation-in-time
+// inverse brings it back -- no bit-reversal pass, no complex intermediate of the FFT itself in HBM.
+// Half spectra live in HBM/L2 as "pair slots": float4 q = { A[k], A[n-k] } (the two bins the real-FFT
+// untangling couples), so that untangle / multiply / retangle are one fused, coalesced step.
+//   short filters (N <= 16384): one spectrum per filter row, blocks of F-N+1 new outputs, one kernel;
+//   long filters (reverb IRs):  uniformly partitioned overlap-save, partition = n taps:
+//       X-block and H-partition spectra (FFT kernels) -> per-bin multiply-accumulate over the
+//       partitions (streaming kernel, filter and input history in registers: each spectrum is read
+//       once) -> inverse FFT kernel.
+// Twiddles: per pass only w^j, w^2j, w^3j (and w^4j, w^8j, w^12j for radix 16) come from a small
+// L1-resident table built in double (gfx_fft_plan_init); the other radix-16 twiddles are products.
 #include "common.cuh"
 
 namespace gfx {
 
-// ------------------------------------------------------------------ complex arithmetic on packed pairs
-// A complex number is one 64-bit register pair (re, im); add/sub are one FADD2, a twiddle multiply is
-// FMUL2 + FFMA2 with the twiddle supplied as two pairs:  forward (wr, wi) & (-wi, wr);  conjugate
-// (wr, -wi) & (wi, wr).  The table entry of angle t is { fwd.xy, fwd.zw, inv.xy, inv.zw } (32 bytes).
-struct Tw { pk2 a, b; };
-__device__ __forceinline__ pk2 cmul_tw(pk2 v, const Tw& w) {
+// ------------------------------------------------------------------ radix plans
+// n = 1024: 16,4,16   n = 4096: 16,16,16   n = 8192: 16,16,2,16   n = 16384: 16,16,4,16
+// (every pass has stride 1 or a multiple of 16, the last radix is always 16)
+__host__ __device__ constexpr bool plan_ok(int n) { return n == 1024 || n == 4096 || n == 8192 || n == 16384; }
+__host__ __device__ constexpr int plan_stages(int n) { return (n == 1024 || n == 4096) ? 3 : 4; }
+__host__ __device__ constexpr int plan_radix(int n, int s) {
+    if (s < 0 || s >= plan_stages(n)) return 1;
+    if (n == 1024) return s == 1 ? 4 : 16;
+    if (n == 4096) return 16;
+    if (n == 8192) return s == 2 ? 2 : 16;
+    return s == 2 ? 4 : 16;
+}
+__host__ __device__ constexpr int plan_m(int n, int s) {  // sub-transform length entering pass s
+    int m = n;
+    for (int i = 0; i < s; ++i) m /= plan_radix(n, i);
+    return m;
+}
+__host__ __device__ constexpr int tw_per_butterfly(int r) { return r == 16 ? 6 : (r == 4 ? 3 : (r == 2 ? 1 : 0)); }
+__host__ __device__ constexpr int tw_exponent(int r, int e) {  // exponent of table entry e
+    return r == 16 ? (e < 3 ? e + 1 : 4 * (e - 2)) : e + 1;
+}
+__host__ __device__ constexpr int plan_entries(int n, int s) {
+    const int r = plan_radix(n, s);
+    const int st = r > 1 ? plan_m(n, s) / r : 1;
+    return (r > 1 && st > 1) ? tw_per_butterfly(r) * st : 0;
+}
+__host__ __device__ constexpr int plan_offset(int n, int s) {
+    int o = 0;
+    for (int i = 0; i < s; ++i) o += plan_entries(n, i);
+    return o;
+}
+__host__ __device__ constexpr int plan_total(int n) { return plan_offset(n, plan_stages(n)); }
+__host__ __device__ constexpr int ilog2c(int v) {
+    int l = 0;
+    while (v > 1) { v >>= 1; ++l; }
+    return l;
+}
+// plan memory (float2 units): [ pair half-twiddles: n/2 | pass tables: plan_total(n) ]
+//   pair table entry q = exp(-i pi k(q) / n), k(q) = the bin (< n/2) of pair slot q
+//   pass table entry e * ST + j = omega_M^(j * tw_exponent(R, e)) = (cos, -sin): consecutive threads (j) read
+//   consecutive 8-byte entries; the inverse uses the conjugate of the same table.
+
+// digit reversal: position (mixed-radix digits, first radix most significant) <-> bin
+template <int N>
+__host__ __device__ __forceinline__ int pos_of_bin(int k) {
+    int p = 0, kshift = 0, pshift = ilog2c(N);
+#pragma unroll
+    for (int s = 0; s < plan_stages(N); ++s) {
+        const int lr = ilog2c(plan_radix(N, s));
+        pshift -= lr;
+        p |= ((k >> kshift) & ((1 << lr) - 1)) << pshift;
+        kshift += lr;
+    }
+    return p;
+}
+template <int N>
+__host__ __device__ __forceinline__ int bin_of_pos(int p) {
+    int k = 0, kshift = 0, pshift = ilog2c(N);
+#pragma unroll
+    for (int s = 0; s < plan_stages(N); ++s) {
+        const int lr = ilog2c(plan_radix(N, s));
+        pshift -= lr;
+        k |= ((p >> pshift) & ((1 << lr) - 1)) << kshift;
+        kshift += lr;
+    }
+    return k;
+}
+// pair slot q < N/2 -> position of its bin k < N/2 (last digit < 8 because the last radix is 16)
+__host__ __device__ __forceinline__ int pair_pos(int q) { return ((q >> 3) << 4) | (q & 7); }
+
+// ------------------------------------------------------------------ complex helpers
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+// v * w (forward) or v * conj(w) (inverse), v packed
+template <bool INV>
+__device__ __forceinline__ pk2 tw_apply(pk2 v, float2 w) {
     float re, im;
     pk_split(v, re, im);
-    return pk_fma(pk_dup(re), w.a, pk_mul(pk_dup(im), w.b));
+    if constexpr (!INV) return pk_make(fmaf(re, w.x, -(im * w.y)), fmaf(re, w.y, im * w.x));
+    else return pk_make(fmaf(re, w.x, im * w.y), fmaf(im, w.x, -(re * w.y)));
 }
-__device__ __forceinline__ float4 ld_tw4(const float4* p) {
-    // volatile: keeps the twiddle requests where they are written (first), so that their latency
-    // overlaps the shared-memory loads and the butterfly that follow
-    float4 r;
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
+template <bool INV>
+__device__ __forceinline__ pk2 mul_minus_i(pk2 v) {  // forward: v * (-i); inverse: v * (+i)
+    float re, im;
+    pk_split(v, re, im);
+    return INV ? pk_make(-im, re) : pk_make(im, -re);
 }
-__device__ __forceinline__ Tw as_tw(const float4& e) {
-    Tw w;
-    w.a = pk_make(e.x, e.y);
-    w.b = pk_make(e.z, e.w);
-    return w;
-}
-__device__ __forceinline__ Tw const_tw(float c, float s, bool inv) {
-    // omega = exp(-i theta) = (c, -s) forward; conj for the inverse
-    Tw w;
-    const float wi = inv ? s : -s;
-    w.a = pk_make(c, wi);
-    w.b = pk_make(-wi, c);
-    return w;
-}
+__device__ __forceinline__ float2 ld_tw(const float2* p) { return __ldg(p); }
 
 template <bool INV>
 __device__ __forceinline__ void r4(pk2& a0, pk2& a1, pk2& a2, pk2& a3) {
@@ -72,13 +136,13 @@ template <bool INV>
 __device__ __forceinline__ void r16(pk2 (&a)[16]) {
 #pragma unroll
     for (int q0 = 0; q0 < 4; ++q0) r4<INV>(a[q0], a[q0 + 4], a[q0 + 8], a[q0 + 12]);
-    // a[q0 + 4 r0] *= omega_16^(q0 r0)
+    // a[q0 + 4 r0] *= omega_16^(q0 r0)   (forward constants; tw_apply<INV> conjugates)
     const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
-    const Tw w1 = const_tw(C1, S1, INV), w2 = const_tw(H, H, INV), w3 = const_tw(S1, C1, INV);
-    const Tw w4 = const_tw(0.f, 1.f, INV), w6 = const_tw(-H, H, INV), w9 = const_tw(-C1, -S1, INV);
-    a[1 + 4] = cmul_tw(a[1 + 4], w1); a[2 + 4] = cmul_tw(a[2 + 4], w2); a[3 + 4] = cmul_tw(a[3 + 4], w3);
-    a[1 + 8] = cmul_tw(a[1 + 8], w2); a[2 + 8] = cmul_tw(a[2 + 8], w4); a[3 + 8] = cmul_tw(a[3 + 8], w6);
-    a[1 + 12] = cmul_tw(a[1 + 12], w3); a[2 + 12] = cmul_tw(a[2 + 12], w6); a[3 + 12] = cmul_tw(a[3 + 12], w9);
+    const float2 w1 = make_float2(C1, -S1), w2 = make_float2(H, -H), w3 = make_float2(S1, -C1);
+    const float2 w6 = make_float2(-H, -H), w9 = make_float2(-C1, S1);
+    a[1 + 4] = tw_apply<INV>(a[1 + 4], w1); a[2 + 4] = tw_apply<INV>(a[2 + 4], w2); a[3 + 4] = tw_apply<INV>(a[3 + 4], w3);
+    a[1 + 8] = tw_apply<INV>(a[1 + 8], w2); a[2 + 8] = mul_minus_i<INV>(a[2 + 8]);  a[3 + 8] = tw_apply<INV>(a[3 + 8], w6);
+    a[1 + 12] = tw_apply<INV>(a[1 + 12], w3); a[2 + 12] = tw_apply<INV>(a[2 + 12], w6); a[3 + 12] = tw_apply<INV>(a[3 + 12], w9);
 #pragma unroll
     for (int r0 = 0; r0 < 4; ++r0) r4<INV>(a[4 * r0], a[4 * r0 + 1], a[4 * r0 + 2], a[4 * r0 + 3]);
 }
@@ -88,70 +152,61 @@ __device__ __forceinline__ void r16(pk2 (&a)[16]) {
 __device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
 __host__ __device__ constexpr int fft_smem_slots(int n) { return n + n / 16 + 16; }
 
-// ---- radix plans (forward order).  N = 1024: 4,16,16   N = 4096: 16,16,16   N = 16384: 4,16,16,16
-__host__ __device__ constexpr int plan_radix(int n, int s) {
-    return n == 4096 ? (s < 3 ? 16 : 1) : (s == 0 ? 4 : (s < (n == 1024 ? 3 : 4) ? 16 : 1));
-}
-__host__ __device__ constexpr int plan_m(int n, int s) {  // sub-transform length entering pass s
-    int m = n;
-    for (int i = 0; i < s; ++i) m /= plan_radix(n, i);
-    return m;
-}
-__host__ __device__ constexpr int plan_entries(int n, int s) {  // twiddles of pass s: (R-1) * ST, none when ST == 1
-    const int r = plan_radix(n, s);
-    const int st = r > 1 ? plan_m(n, s) / r : 1;
-    return (r > 1 && st > 1) ? (r - 1) * st : 0;
-}
-__host__ __device__ constexpr int plan_offset(int n, int s) {
-    int o = 0;
-    for (int i = 0; i < s; ++i) o += plan_entries(n, i);
-    return o;
-}
-__host__ __device__ constexpr int plan_total(int n) { return plan_offset(n, 4); }
-// plan memory (float4 units): [ half-angle table: n float2 = n/2 float4 | forward pass tables | inverse pass tables ]
-//   pass table entry (r-1) * ST + j = twiddle omega_M^(j r) as { wr, wi, -wi, wr } (forward) / { wr, -wi, wi, wr }
-//   (conjugate): consecutive threads (j) read consecutive 16-byte entries.
-
 template <int N, int NT, int S, bool INV>
-__device__ __forceinline__ void fft_pass(pk2* z, const float4* __restrict__ plan) {
+__device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan) {
     constexpr int R = plan_radix(N, S);
     constexpr int M = plan_m(N, S);
     constexpr int ST = M / R;
-    const float4* tp = plan + N / 2 + plan_offset(N, S) + (INV ? plan_total(N) : 0);
+    const float2* tp = plan + N / 2 + plan_offset(N, S);
     // slot of element q of a butterfly: pidx(i0 + q ST) = pidx(i0) + q * PST  (ST is a multiple of 16, or 1)
     constexpr int PST = ST >= 16 ? ST + ST / 16 : 1;
     static_assert(ST == 1 || ST % 16 == 0, "stride must keep the padding pattern linear");
+#pragma unroll 1
     for (int b = threadIdx.x; b < N / R; b += NT) {
         const int j = b & (ST - 1);
         const int i0 = (b - j) * R + j;
         pk2* zb = z + pidx(i0);
-        if constexpr (R == 4) {
-            float4 t1, t2, t3;
-            if constexpr (ST > 1) { t1 = ld_tw4(tp + j); t2 = ld_tw4(tp + ST + j); t3 = ld_tw4(tp + 2 * ST + j); }
+        if constexpr (R == 2) {
+            float2 t1 = make_float2(1.f, 0.f);
+            if constexpr (ST > 1) t1 = ld_tw(tp + j);
+            pk2 a0 = zb[0], a1 = zb[PST];
+            if constexpr (INV && ST > 1) a1 = tw_apply<true>(a1, t1);
+            const pk2 s = pk_add(a0, a1);
+            pk2 d = pk_sub(a0, a1);
+            if constexpr (!INV && ST > 1) d = tw_apply<false>(d, t1);
+            zb[0] = s; zb[PST] = d;
+        } else if constexpr (R == 4) {
+            float2 t1, t2, t3;
+            if constexpr (ST > 1) { t1 = ld_tw(tp + j); t2 = ld_tw(tp + ST + j); t3 = ld_tw(tp + 2 * ST + j); }
             pk2 a0 = zb[0], a1 = zb[PST], a2 = zb[2 * PST], a3 = zb[3 * PST];
             if constexpr (INV && ST > 1) {
-                a1 = cmul_tw(a1, as_tw(t1)); a2 = cmul_tw(a2, as_tw(t2)); a3 = cmul_tw(a3, as_tw(t3));
+                a1 = tw_apply<true>(a1, t1); a2 = tw_apply<true>(a2, t2); a3 = tw_apply<true>(a3, t3);
             }
             r4<INV>(a0, a1, a2, a3);
             if constexpr (!INV && ST > 1) {
-                a1 = cmul_tw(a1, as_tw(t1)); a2 = cmul_tw(a2, as_tw(t2)); a3 = cmul_tw(a3, as_tw(t3));
+                a1 = tw_apply<false>(a1, t1); a2 = tw_apply<false>(a2, t2); a3 = tw_apply<false>(a3, t3);
             }
             zb[0] = a0; zb[PST] = a1; zb[2 * PST] = a2; zb[3 * PST] = a3;
         } else {
-            float4 tw[15];
+            // twiddle of index r = r0 + 4 r1:  omega^(j r0) * omega^(4 j r1);  lo[r0], hi[r1] from the table
+            float2 lo[4], hi[4];
             if constexpr (ST > 1) {
 #pragma unroll
-                for (int r = 1; r < 16; ++r) tw[r - 1] = ld_tw4(tp + (r - 1) * ST + j);
+                for (int e = 0; e < 3; ++e) { lo[e + 1] = ld_tw(tp + e * ST + j); hi[e + 1] = ld_tw(tp + (e + 3) * ST + j); }
             }
             pk2 a[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) a[q] = zb[q * PST];
             if constexpr (INV && ST > 1) {
 #pragma unroll
-                for (int q = 1; q < 16; ++q) a[q] = cmul_tw(a[q], as_tw(tw[q - 1]));
+                for (int q = 1; q < 16; ++q) {
+                    const int r0 = q & 3, r1 = q >> 2;
+                    const float2 w = r1 == 0 ? lo[r0] : (r0 == 0 ? hi[r1] : cmul(lo[r0], hi[r1]));
+                    a[q] = tw_apply<true>(a[q], w);
+                }
             }
             r16<INV>(a);
-            // register a[4*i + jj] holds output index 4*jj + i
+            // register a[4*i + jj] holds output index r = 4*jj + i
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
 #pragma unroll
@@ -159,7 +214,10 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float4* __restrict__ plan
                     const int r = 4 * jj + i;
                     pk2 v = a[4 * i + jj];
                     if constexpr (!INV && ST > 1) {
-                        if (r > 0) v = cmul_tw(v, as_tw(tw[r - 1]));
+                        if (r > 0) {
+                            const float2 w = jj == 0 ? lo[i] : (i == 0 ? hi[jj] : cmul(lo[i], hi[jj]));
+                            v = tw_apply<false>(v, w);
+                        }
                     }
                     zb[r * PST] = v;
                 }
@@ -169,21 +227,21 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float4* __restrict__ plan
 }
 
 template <int N, int NT>
-__device__ __forceinline__ void fft_forward(pk2* z, const float4* __restrict__ plan) {
+__device__ __forceinline__ void fft_forward(pk2* z, const float2* __restrict__ plan) {
     fft_pass<N, NT, 0, false>(z, plan);
     __syncthreads();
     fft_pass<N, NT, 1, false>(z, plan);
     __syncthreads();
     fft_pass<N, NT, 2, false>(z, plan);
     __syncthreads();
-    if constexpr (plan_radix(N, 3) > 1) {
+    if constexpr (plan_stages(N) > 3) {
         fft_pass<N, NT, 3, false>(z, plan);
         __syncthreads();
     }
 }
 template <int N, int NT>
-__device__ __forceinline__ void fft_inverse(pk2* z, const float4* __restrict__ plan) {
-    if constexpr (plan_radix(N, 3) > 1) {
+__device__ __forceinline__ void fft_inverse(pk2* z, const float2* __restrict__ plan) {
+    if constexpr (plan_stages(N) > 3) {
         fft_pass<N, NT, 3, true>(z, plan);
         __syncthreads();
     }
@@ -195,136 +253,126 @@ __device__ __forceinline__ void fft_inverse(pk2* z, const float4* __restrict__ p
     __syncthreads();
 }
 
-// digit reversal of the plans above: position (mixed-radix digits, first radix most significant) <-> bin
-template <int N> __device__ __forceinline__ int bin_of_pos(int p);
-template <int N> __device__ __forceinline__ int pos_of_bin(int k);
-template <> __device__ __forceinline__ int bin_of_pos<1024>(int p) { return (p >> 8) | (((p >> 4) & 15) << 2) | ((p & 15) << 6); }
-template <> __device__ __forceinline__ int pos_of_bin<1024>(int k) { return ((k & 3) << 8) | (((k >> 2) & 15) << 4) | (k >> 6); }
-template <> __device__ __forceinline__ int bin_of_pos<4096>(int p) { return (p >> 8) | (((p >> 4) & 15) << 4) | ((p & 15) << 8); }
-template <> __device__ __forceinline__ int pos_of_bin<4096>(int k) { return ((k & 15) << 8) | (((k >> 4) & 15) << 4) | (k >> 8); }
-template <> __device__ __forceinline__ int bin_of_pos<16384>(int p) {
-    return (p >> 12) | (((p >> 8) & 15) << 2) | (((p >> 4) & 15) << 6) | ((p & 15) << 10);
-}
-template <> __device__ __forceinline__ int pos_of_bin<16384>(int k) {
-    return ((k & 3) << 12) | (((k >> 2) & 15) << 8) | (((k >> 6) & 15) << 4) | (k >> 10);
-}
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
-    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
-}
 __device__ __forceinline__ float2 ld_c(const pk2* z, int i) {
     float re, im;
     pk_split(z[pidx(i)], re, im);
     return make_float2(re, im);
 }
 __device__ __forceinline__ void st_c(pk2* z, int i, float re, float im) { z[pidx(i)] = pk_make(re, im); }
-__device__ __forceinline__ float2 half_tw(const float4* __restrict__ plan, int k) {  // exp(-i pi k / N), k < N
-    return __ldg(reinterpret_cast<const float2*>(plan) + k);
+
+// ------------------------------------------------------------------ real-FFT untangling on pair slots
+// Z = FFT of z[j] = x[2j] + i x[2j+1] (digit-reversed in smem).  For the pair (k, N-k), w = exp(-i pi k / N):
+//   E = (Z_k + conj Z_{N-k}) / 2,  O = -(i/2) w (Z_k - conj Z_{N-k}),  A_k = E + O,  A_{N-k} = conj(E - O).
+// Slot 0 is special: { (A_0, A_N) both real, A_{N/2} }.
+struct PairA { float2 k, m; };
+__device__ __forceinline__ PairA untangle_pair(float2 zk, float2 zm, float2 w) {
+    const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
+    const float dr = zk.x - zm.x, di = zk.y + zm.y;
+    const float2 wd = cmul(w, make_float2(dr, di));
+    const float orr = 0.5f * wd.y, oi = -0.5f * wd.x;
+    PairA r;
+    r.k = make_float2(er + orr, ei + oi);
+    r.m = make_float2(er - orr, -(ei - oi));
+    return r;
+}
+// inverse of the above: from Y_k, Y_{N-k} to the packed Z'_k, Z'_{N-k}
+__device__ __forceinline__ PairA retangle_pair(float2 yk, float2 ym, float2 w) {
+    const float er = 0.5f * (yk.x + ym.x), ei = 0.5f * (yk.y - ym.y);
+    const float dr = yk.x - ym.x, di = yk.y + ym.y;
+    const float2 wd = cmulc(make_float2(dr, di), w);  // O' = (i/2) conj(w) D'
+    const float orr = -0.5f * wd.y, oi = 0.5f * wd.x;
+    PairA r;
+    r.k = make_float2(er + orr, ei + oi);
+    r.m = make_float2(er - orr, -(ei - oi));
+    return r;
 }
 
-// The last radix is 16 in every plan: bins k < N/2 are the positions whose last digit is < 8; bin N/2 is
-// position 8, bin 0 position 0.
-#define GFX_FOR_PAIRS(N, NT)                                                     \
-    for (int q = threadIdx.x; q < (N) / 2; q += (NT))                            \
-        if (const int p = ((q >> 3) << 4) | (q & 7); true)                       \
-            if (const int k = bin_of_pos<N>(p); true)
-
-// packed complex FFT Z (digit-reversed order, in smem) -> true half spectrum A (same order):
-//   slot 0 holds (A[0], A[N]) (both real); slot pos(k) holds A[k], 0 < k < N.  `scale` multiplies.
+// smem FFT output -> pair slots in global memory (scaled)
 template <int N, int NT>
-__device__ __forceinline__ void untangle_inplace(pk2* z, const float4* __restrict__ tw4, float scale) {
-    GFX_FOR_PAIRS(N, NT) {
-        if (k == 0) {
+__device__ __forceinline__ void untangle_store(const pk2* z, const float2* __restrict__ plan, float4* __restrict__ out,
+                                               float scale) {
+    for (int q = threadIdx.x; q < N / 2; q += NT) {
+        float4 o;
+        if (q == 0) {
             const float2 z0 = ld_c(z, 0), zh = ld_c(z, 8);
-            st_c(z, 0, (z0.x + z0.y) * scale, (z0.x - z0.y) * scale);
-            st_c(z, 8, zh.x * scale, -zh.y * scale);  // k = N/2: conj
-            continue;
+            o = make_float4((z0.x + z0.y) * scale, (z0.x - z0.y) * scale, zh.x * scale, -zh.y * scale);
+        } else {
+            const int p = pair_pos(q);
+            const int pm = pos_of_bin<N>(N - bin_of_pos<N>(p));
+            const PairA a = untangle_pair(ld_c(z, p), ld_c(z, pm), __ldg(plan + q));
+            o = make_float4(a.k.x * scale, a.k.y * scale, a.m.x * scale, a.m.y * scale);
         }
-        const int pm = pos_of_bin<N>(N - k);
-        const float2 zk = ld_c(z, p), zm = ld_c(z, pm);
-        const float2 w = half_tw(tw4, k);
-        const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
-        const float dr = zk.x - zm.x, di = zk.y + zm.y;
-        const float2 wd = cmul(w, make_float2(dr, di));  // O = -(i/2) w D
-        const float orr = 0.5f * wd.y, oi = -0.5f * wd.x;
-        st_c(z, p, (er + orr) * scale, (ei + oi) * scale);
-        st_c(z, pm, (er - orr) * scale, -(ei - oi) * scale);
+        out[q] = o;
     }
 }
 
-// true spectrum Y (digit-reversed order, slot 0 = (Y[0], Y[N])) -> packed complex Z' for the inverse
+// pair slots in global memory -> packed spectrum in smem, ready for the inverse FFT
 template <int N, int NT>
-__device__ __forceinline__ void retangle_inplace(pk2* z, const float4* __restrict__ tw4) {
-    GFX_FOR_PAIRS(N, NT) {
-        if (k == 0) {
-            const float2 y0 = ld_c(z, 0), yh = ld_c(z, 8);
-            st_c(z, 0, 0.5f * (y0.x + y0.y), 0.5f * (y0.x - y0.y));
-            st_c(z, 8, yh.x, -yh.y);
-            continue;
+__device__ __forceinline__ void retangle_load(pk2* z, const float2* __restrict__ plan, const float4* __restrict__ Y) {
+    for (int q = threadIdx.x; q < N / 2; q += NT) {
+        const float4 y = ldg_stream(Y + q);
+        if (q == 0) {
+            st_c(z, 0, 0.5f * (y.x + y.y), 0.5f * (y.x - y.y));
+            st_c(z, 8, y.z, -y.w);
+        } else {
+            const int p = pair_pos(q);
+            const int pm = pos_of_bin<N>(N - bin_of_pos<N>(p));
+            const PairA a = retangle_pair(make_float2(y.x, y.y), make_float2(y.z, y.w), __ldg(plan + q));
+            st_c(z, p, a.k.x, a.k.y);
+            st_c(z, pm, a.m.x, a.m.y);
         }
-        const int pm = pos_of_bin<N>(N - k);
-        const float2 yk = ld_c(z, p), ym = ld_c(z, pm);
-        const float2 w = half_tw(tw4, k);
-        const float er = 0.5f * (yk.x + ym.x), ei = 0.5f * (yk.y - ym.y);
-        const float dr = yk.x - ym.x, di = yk.y + ym.y;
-        const float2 wd = cmulc(make_float2(dr, di), w);  // O' = (i/2) conj(w) D'
-        const float orr = -0.5f * wd.y, oi = 0.5f * wd.x;
-        st_c(z, p, er + orr, ei + oi);
-        st_c(z, pm, er - orr, -(ei - oi));
     }
 }
 
-// fused: untangle X, multiply by the (already 1/N-scaled) filter spectrum H, retangle
+// fused in place: untangle X, multiply by the (already 1/N-scaled) filter spectrum H (pair slots), retangle
 template <int N, int NT>
-__device__ __forceinline__ void pointwise_filter(pk2* z, const float4* __restrict__ tw4, const float2* __restrict__ H) {
-    GFX_FOR_PAIRS(N, NT) {
-        if (k == 0) {
+__device__ __forceinline__ void pointwise_filter(pk2* z, const float2* __restrict__ plan, const float4* __restrict__ H) {
+    for (int q = threadIdx.x; q < N / 2; q += NT) {
+        const float4 h = __ldg(H + q);
+        if (q == 0) {
             const float2 z0 = ld_c(z, 0), zh = ld_c(z, 8);
-            const float2 h0 = H[0];
-            const float y0 = (z0.x + z0.y) * h0.x, yn = (z0.x - z0.y) * h0.y;
+            const float y0 = (z0.x + z0.y) * h.x, yn = (z0.x - z0.y) * h.y;
             st_c(z, 0, 0.5f * (y0 + yn), 0.5f * (y0 - yn));
-            const float2 r2 = cmulc(zh, H[8]);  // X = conj(Z), Y = X H, Z' = conj(Y) = Z conj(H)
+            // X_{N/2} = conj(Z), Y = X H, Z' = conj(Y) = Z conj(H)
+            const float2 r2 = cmulc(zh, make_float2(h.z, h.w));
             st_c(z, 8, r2.x, r2.y);
-            continue;
+        } else {
+            const int p = pair_pos(q);
+            const int pm = pos_of_bin<N>(N - bin_of_pos<N>(p));
+            const float2 w = __ldg(plan + q);
+            const PairA x = untangle_pair(ld_c(z, p), ld_c(z, pm), w);
+            const PairA y = retangle_pair(cmul(x.k, make_float2(h.x, h.y)), cmul(x.m, make_float2(h.z, h.w)), w);
+            st_c(z, p, y.k.x, y.k.y);
+            st_c(z, pm, y.m.x, y.m.y);
         }
-        const int pm = pos_of_bin<N>(N - k);
-        const float2 zk = ld_c(z, p), zm = ld_c(z, pm);
-        const float2 w = half_tw(tw4, k);
-        float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
-        float dr = zk.x - zm.x, di = zk.y + zm.y;
-        float2 wd = cmul(w, make_float2(dr, di));
-        float orr = 0.5f * wd.y, oi = -0.5f * wd.x;
-        const float2 xk = make_float2(er + orr, ei + oi);
-        const float2 xm = make_float2(er - orr, -(ei - oi));
-        const float2 yk = cmul(xk, H[p]);
-        const float2 ym = cmul(xm, H[pm]);
-        er = 0.5f * (yk.x + ym.x); ei = 0.5f * (yk.y - ym.y);
-        dr = yk.x - ym.x; di = yk.y + ym.y;
-        wd = cmulc(make_float2(dr, di), w);
-        orr = -0.5f * wd.y; oi = 0.5f * wd.x;
-        st_c(z, p, er + orr, ei + oi);
-        st_c(z, pm, er - orr, -(ei - oi));
     }
 }
 
 // ------------------------------------------------------------------ segment load / store
-// loads F = 2N real samples src[s0 .. s0+F) (zero outside [0, len)) as z[j] = x[2j] + i x[2j+1]
+// loads F = 2N real samples src[s0 .. s0+F) (zero outside [0, len)) as z[j] = x[2j] + i x[2j+1];
+// with src2 != nullptr the sample is src + sgn2 * src2 (mid/side -> left/right of a reverb IR).
 template <int N, int NT>
-__device__ __forceinline__ void load_packed(pk2* z, const float* __restrict__ src, long long s0, long long len,
-                                            bool vec_ok) {
+__device__ __forceinline__ void load_packed(pk2* z, const float* __restrict__ src, const float* __restrict__ src2,
+                                            float sgn2, long long s0, long long len, bool vec_ok) {
     if (vec_ok && (s0 & 3) == 0) {
+#pragma unroll 4
         for (int t = threadIdx.x; t < N / 2; t += NT) {
             const long long pos = s0 + 4LL * t;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (pos >= 0 && pos + 4 <= len) {
-                v = __ldg(reinterpret_cast<const float4*>(src + pos));
+                v = ldg_stream(reinterpret_cast<const float4*>(src + pos));
+                if (src2) {
+                    const float4 u = ldg_stream(reinterpret_cast<const float4*>(src2 + pos));
+                    v.x = fmaf(sgn2, u.x, v.x); v.y = fmaf(sgn2, u.y, v.y); v.z = fmaf(sgn2, u.z, v.z); v.w = fmaf(sgn2, u.w, v.w);
+                }
             } else if (pos + 4 > 0 && pos < len) {
                 float e[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) e[c] = (pos + c >= 0 && pos + c < len) ? src[pos + c] : 0.f;
+                for (int c = 0; c < 4; ++c) {
+                    const bool in = (pos + c >= 0 && pos + c < len);
+                    e[c] = in ? src[pos + c] : 0.f;
+                    if (in && src2) e[c] = fmaf(sgn2, src2[pos + c], e[c]);
+                }
                 v = make_float4(e[0], e[1], e[2], e[3]);
             }
             z[pidx(2 * t)] = pk_make(v.x, v.y);
@@ -333,8 +381,9 @@ __device__ __forceinline__ void load_packed(pk2* z, const float* __restrict__ sr
     } else {
         for (int j = threadIdx.x; j < N; j += NT) {
             const long long pos = s0 + 2LL * j;
-            const float a = (pos >= 0 && pos < len) ? src[pos] : 0.f;
-            const float b = (pos + 1 >= 0 && pos + 1 < len) ? src[pos + 1] : 0.f;
+            float a = 0.f, b = 0.f;
+            if (pos >= 0 && pos < len) { a = src[pos]; if (src2) a = fmaf(sgn2, src2[pos], a); }
+            if (pos + 1 >= 0 && pos + 1 < len) { b = src[pos + 1]; if (src2) b = fmaf(sgn2, src2[pos + 1], b); }
             z[pidx(j)] = pk_make(a, b);
         }
     }
@@ -345,6 +394,7 @@ template <int N, int NT>
 __device__ __forceinline__ void store_packed(const pk2* z, float* __restrict__ dst, int i_lo, int count, long long d0,
                                              long long len, bool vec_ok) {
     if (vec_ok && (i_lo & 3) == 0 && (d0 & 3) == 0 && (count & 3) == 0) {
+#pragma unroll 4
         for (int t = threadIdx.x; t < count / 4; t += NT) {
             const int i = i_lo + 4 * t;
             const long long pos = d0 + 4LL * t;
@@ -378,124 +428,215 @@ struct RowMap {  // output row -> (x row, h row) with channel broadcasting
     }
 };
 
+// how filter rows are read: plain, or a raw mid/side reverb IR turned into unit-energy left/right on the fly
+// (reference: ms_to_lr + normalize_impulse, reverb.py:215-228, core/utils.py:14-18)
+struct FilterSrc {
+    const float* h;       // [hrows, Nh]
+    const float* energy;  // [batch, 2] sum_t h^2 of the raw rows, or null (plain)
+    int to_lr;            // with energy: rows are (mid, side) -> (mid + side, mid - side)
+};
+
+constexpr int fir_min_blocks(int n) { return n <= 4096 ? 3 : (n <= 8192 ? 3 : 1); }
+
 // ------------------------------------------------------------------ kernels
-// spectra of filter partitions: Hs[(hrow * P + part) * N + pos], scaled by 1/N
+// spectra of filter partitions: Hs[(hrow * P + part) * N/2 + q] pair slots, scaled by 1/N (and the energy norm)
 template <int N, int NT>
-__global__ void __launch_bounds__(NT) fir_spectrum_kernel(const float* __restrict__ h, float2* __restrict__ Hs,
-                                                          int Nh, int part_len, int P,
-                                                          const float4* __restrict__ tw, int vec_ok) {
+__global__ void __launch_bounds__(NT, fir_min_blocks(N)) fir_spectrum_kernel(FilterSrc fs, float4* __restrict__ Hs,
+                                                                             int hrow0, int Nh, int part_len, int P,
+                                                                             const float2* __restrict__ plan, int vec_ok) {
     extern __shared__ __align__(16) pk2 zbuf[];
-    const int hrow = blockIdx.x / P, part = blockIdx.x - hrow * P;
-    const float* src = h + (size_t)hrow * Nh + (size_t)part * part_len;
+    const int hloc = blockIdx.x / P, part = blockIdx.x - hloc * P;
+    const int hrow = hrow0 + hloc;
+    const size_t off = (size_t)hrow * Nh + (size_t)part * part_len;
     long long len = (long long)Nh - (long long)part * part_len;
     if (len > part_len) len = part_len;
-    const bool v = vec_ok && ((((size_t)hrow * Nh + (size_t)part * part_len) & 3) == 0);
-    load_packed<N, NT>(zbuf, src, 0, len, v);
+    float scale = 1.f / (float)N;
+    const float* src2 = nullptr;
+    size_t off2 = 0;
+    if (fs.energy) {
+        const float e0 = fs.energy[hrow & ~1], e1 = fs.energy[hrow | 1];
+        if (fs.to_lr) {
+            scale *= rsqrtf(e0 + e1 + 1e-12f);  // mean_c sum_t (m +- s)^2 = sum m^2 + sum s^2
+            off2 = (size_t)(hrow ^ 1) * Nh + (size_t)part * part_len;
+            src2 = fs.h + off2;
+        } else {
+            scale *= rsqrtf(0.5f * (e0 + e1) + 1e-12f);
+        }
+    }
+    const bool v = vec_ok && ((off & 3) == 0) && ((off2 & 3) == 0);
+    if (src2 && (hrow & 1)) {
+        // this row is the side channel: right = mid - side
+        load_packed<N, NT>(zbuf, src2, fs.h + off, -1.f, 0, len, v);
+    } else {
+        load_packed<N, NT>(zbuf, fs.h + off, src2, 1.f, 0, len, v);
+    }
     __syncthreads();
-    fft_forward<N, NT>(zbuf, tw);
-    untangle_inplace<N, NT>(zbuf, tw, 1.f / (float)N);
-    __syncthreads();
-    float2* out = Hs + (size_t)blockIdx.x * N;
-    for (int i = threadIdx.x; i < N; i += NT) out[i] = ld_c(zbuf, i);
+    fft_forward<N, NT>(zbuf, plan);
+    untangle_store<N, NT>(zbuf, plan, Hs + (size_t)blockIdx.x * (N / 2), scale);
 }
 
 // single-partition overlap-save: block j produces full-convolution samples [j*hop, (j+1)*hop)
 template <int N, int NT>
-__global__ void __launch_bounds__(NT) fir_ols_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                     const float2* __restrict__ Hs, RowMap rm, long long L, int pre,
-                                                     int hop, int shift, int nblk, const float4* __restrict__ tw,
-                                                     int vec_ok) {
+__global__ void __launch_bounds__(NT, fir_min_blocks(N)) fir_ols_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                        const float4* __restrict__ Hs, RowMap rm,
+                                                                        long long L, int pre, int hop, int shift, int nblk,
+                                                                        const float2* __restrict__ plan, int vec_ok) {
     extern __shared__ __align__(16) pk2 zbuf[];
     const int row = blockIdx.x / nblk, j = blockIdx.x - row * nblk;
     int xr, hr;
     rm.map(row, xr, hr);
     const long long m0 = (long long)j * hop;
-    load_packed<N, NT>(zbuf, x + (size_t)xr * L, m0 - pre, L, vec_ok);
+    load_packed<N, NT>(zbuf, x + (size_t)xr * L, nullptr, 0.f, m0 - pre, L, vec_ok);
     __syncthreads();
-    fft_forward<N, NT>(zbuf, tw);
-    pointwise_filter<N, NT>(zbuf, tw, Hs + (size_t)hr * N);
+    fft_forward<N, NT>(zbuf, plan);
+    pointwise_filter<N, NT>(zbuf, plan, Hs + (size_t)hr * (N / 2));
     __syncthreads();
-    fft_inverse<N, NT>(zbuf, tw);
+    fft_inverse<N, NT>(zbuf, plan);
     store_packed<N, NT>(zbuf, y + (size_t)row * L, pre, hop, m0 - shift, L, vec_ok);
 }
 
-// UPOLS step 1: spectra of input blocks.  Xs[(rloc * nblk + j) * N + pos] = rfft of x[(j-1)B, (j+1)B), B = N
+// UPOLS step 1: spectra of input blocks.  Xs[(rloc * nblk + j) * N/2 + q] = rfft of x[(j-1)B, (j+1)B), B = N
 template <int N, int NT>
-__global__ void __launch_bounds__(NT) fir_xspec_kernel(const float* __restrict__ x, float2* __restrict__ Xs,
-                                                       int xrow0, long long L, int nblk,
-                                                       const float4* __restrict__ tw, int vec_ok) {
+__global__ void __launch_bounds__(NT, fir_min_blocks(N)) fir_xspec_kernel(const float* __restrict__ x, float4* __restrict__ Xs,
+                                                                          int xrow0, long long L, int nblk,
+                                                                          const float2* __restrict__ plan, int vec_ok) {
     extern __shared__ __align__(16) pk2 zbuf[];
     const int rloc = blockIdx.x / nblk, j = blockIdx.x - rloc * nblk;
-    load_packed<N, NT>(zbuf, x + (size_t)(xrow0 + rloc) * L, ((long long)j - 1) * N, L, vec_ok);
+    load_packed<N, NT>(zbuf, x + (size_t)(xrow0 + rloc) * L, nullptr, 0.f, ((long long)j - 1) * N, L, vec_ok);
     __syncthreads();
-    fft_forward<N, NT>(zbuf, tw);
-    untangle_inplace<N, NT>(zbuf, tw, 1.f);
-    __syncthreads();
-    float2* out = Xs + (size_t)blockIdx.x * N;
-    for (int i = threadIdx.x; i < N; i += NT) out[i] = ld_c(zbuf, i);
+    fft_forward<N, NT>(zbuf, plan);
+    untangle_store<N, NT>(zbuf, plan, Xs + (size_t)blockIdx.x * (N / 2), 1.f);
 }
 
-// UPOLS step 2: Y_j = sum_p X_{j-p} H_p, inverse FFT, keep the second half of the block
-template <int N, int NT>
-__global__ void __launch_bounds__(NT) fir_upols_kernel(const float2* __restrict__ Xs, const float2* __restrict__ Hs,
-                                                       float* __restrict__ y, RowMap rm, int row0, int xrow0,
-                                                       int hrow0, long long L, int P, int nblk, int shift,
-                                                       const float4* __restrict__ tw, int vec_ok) {
-    extern __shared__ __align__(16) pk2 zbuf[];
-    const int rloc = blockIdx.x / nblk, j = blockIdx.x - rloc * nblk;
-    const int row = row0 + rloc;
+// UPOLS step 2: Y_j = sum_p X_{j-p} H_p on pair slots, partitions [p0, p0 + PC).  One thread owns one pair slot of
+// one output row and walks the blocks in order: the PC filter values and the last PC input values stay in
+// registers, so every spectrum is read exactly once.  accumulate != 0 adds to Ys (filters with more than
+// MAC_MAX_PC partitions are processed in groups).
+constexpr int MAC_MAX_PC = 12;
+constexpr int MAC_NT = 256;
+
+__device__ __forceinline__ void cmac4(float4& acc, const float4& x, const float4& h) {
+    acc.x = fmaf(x.x, h.x, acc.x); acc.x = fmaf(-x.y, h.y, acc.x);
+    acc.y = fmaf(x.x, h.y, acc.y); acc.y = fmaf(x.y, h.x, acc.y);
+    acc.z = fmaf(x.z, h.z, acc.z); acc.z = fmaf(-x.w, h.w, acc.z);
+    acc.w = fmaf(x.z, h.w, acc.w); acc.w = fmaf(x.w, h.z, acc.w);
+}
+
+template <int PC>
+__global__ void __launch_bounds__(MAC_NT, 2) fir_mac_kernel(const float4* __restrict__ Xs, const float4* __restrict__ Hs,
+                                                            float4* __restrict__ Ys, RowMap rm, int xrow0, int hrow0,
+                                                            int row0, int P, int p0, int nblk, int half, int accumulate) {
+    const int q = blockIdx.x * MAC_NT + threadIdx.x;
+    const int rloc = blockIdx.y;
     int xr, hr;
-    rm.map(row, xr, hr);
-    const float2* Xrow = Xs + (size_t)(xr - xrow0) * nblk * N;
-    const float2* Hrow = Hs + (size_t)(hr - hrow0) * P * N;
-    const int pmax = j < P - 1 ? j : P - 1;
-    for (int i = threadIdx.x; i < N; i += NT) {
-        float ar = 0.f, ai = 0.f;
-        if (i == 0) {
-            for (int p = 0; p <= pmax; ++p) {
-                const float2 xv = __ldg(Xrow + (size_t)(j - p) * N), hv = __ldg(Hrow + (size_t)p * N);
-                ar = fmaf(xv.x, hv.x, ar);
-                ai = fmaf(xv.y, hv.y, ai);
+    rm.map(row0 + rloc, xr, hr);
+    const float4* X = Xs + (size_t)(xr - xrow0) * nblk * half + q;
+    const float4* H = Hs + ((size_t)(hr - hrow0) * P + p0) * half + q;
+    float4* Y = Ys + (size_t)rloc * nblk * half + q;
+    float4 h[PC], ring[PC];
+#pragma unroll
+    for (int p = 0; p < PC; ++p) {
+        h[p] = __ldg(H + (size_t)p * half);
+        ring[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (q == 0) {
+        // slot 0 carries (A_0, A_N), two REAL bins, in .xy: not a complex product -- warp 0 adds them below
+#pragma unroll
+        for (int p = 0; p < PC; ++p) { h[p].x = 0.f; h[p].y = 0.f; }
+    }
+    constexpr int G = PC < 4 ? PC : 4;  // loads issued together
+    const int last = nblk - 1 - p0;     // last valid input block index for this partition group
+#pragma unroll 1
+    for (int j0 = p0; j0 < nblk; j0 += PC) {
+#pragma unroll
+        for (int g0 = 0; g0 < PC; g0 += G) {
+            float4 xn[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                int jb = j0 - p0 + g0 + g;  // input block feeding output block j0 + g0 + g
+                jb = jb < last ? jb : last;
+                xn[g] = ldg_stream(X + (size_t)jb * half);
             }
-        } else {
-            for (int p = 0; p <= pmax; ++p) {
-                const float2 xv = __ldg(Xrow + (size_t)(j - p) * N + i), hv = __ldg(Hrow + (size_t)p * N + i);
-                ar = fmaf(xv.x, hv.x, ar); ar = fmaf(-xv.y, hv.y, ar);
-                ai = fmaf(xv.x, hv.y, ai); ai = fmaf(xv.y, hv.x, ai);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (g0 + g < PC) {
+                    const int jj = g0 + g;
+                    const int j = j0 + jj;
+                    ring[jj] = xn[g];
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < nblk) {
+                        if (accumulate) acc = Y[(size_t)j * half];
+#pragma unroll
+                        for (int p = 0; p < PC; ++p) cmac4(acc, ring[(jj - p + PC) % PC], h[p]);
+                        Y[(size_t)j * half] = acc;
+                    }
+                }
             }
         }
-        st_c(zbuf, i, ar, ai);
     }
-    __syncthreads();
-    retangle_inplace<N, NT>(zbuf, tw);
-    __syncthreads();
-    fft_inverse<N, NT>(zbuf, tw);
-    store_packed<N, NT>(zbuf, y + (size_t)row * L, N, N, (long long)j * N - shift, L, vec_ok);
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // DC / Nyquist of every block (the .xy lanes of slot 0): lanes over output blocks
+        __syncwarp();
+        const float4* X0 = X - q;
+        const float4* H0 = H - q;
+        float4* Y0 = Y - q;
+        for (int j = p0 + (int)threadIdx.x; j < nblk; j += 32) {
+            float a0 = 0.f, an = 0.f;
+            for (int p = 0; p < PC && p0 + p <= j; ++p) {
+                const float4 xv = __ldg(X0 + (size_t)(j - p0 - p) * half);
+                const float4 hv = __ldg(H0 + (size_t)p * half);
+                a0 = fmaf(xv.x, hv.x, a0);
+                an = fmaf(xv.y, hv.y, an);
+            }
+            // lane 0 (q == 0) wrote slot 0 of block j in the main loop; the __syncwarp above orders that store
+            Y0[(size_t)j * half].x += a0;
+            Y0[(size_t)j * half].y += an;
+        }
+    }
 }
 
-__global__ void fft_plan_half_kernel(float2* ht, int n) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) {
-        const double a = (double)k / (double)n;
-        ht[k] = make_float2((float)cospi(a), (float)(-sinpi(a)));
+// UPOLS step 3: inverse FFT of Y_j, keep the second half of the block
+template <int N, int NT>
+__global__ void __launch_bounds__(NT, fir_min_blocks(N)) fir_inv_kernel(const float4* __restrict__ Ys, float* __restrict__ y,
+                                                                        int row0, long long L, int nblk, int shift,
+                                                                        const float2* __restrict__ plan, int vec_ok) {
+    extern __shared__ __align__(16) pk2 zbuf[];
+    const int rloc = blockIdx.x / nblk, j = blockIdx.x - rloc * nblk;
+    retangle_load<N, NT>(zbuf, plan, Ys + (size_t)blockIdx.x * (N / 2));
+    __syncthreads();
+    fft_inverse<N, NT>(zbuf, plan);
+    store_packed<N, NT>(zbuf, y + (size_t)(row0 + rloc) * L, N, N, (long long)j * N - shift, L, vec_ok);
+}
+
+// ------------------------------------------------------------------ plan construction
+template <int N>
+__global__ void fft_plan_pairs_kernel(float2* ht) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < N / 2) {
+        const int k = bin_of_pos<N>(pair_pos(q));
+        const double a = (double)k / (double)N;
+        ht[q] = make_float2((float)cospi(a), (float)(-sinpi(a)));
     }
 }
-__global__ void fft_plan_pass_kernel(float4* fwd, float4* inv, int M, int R) {
+__global__ void fft_plan_pass_kernel(float2* tab, int M, int R) {
     const int ST = M / R;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < (R - 1) * ST) {
-        const int r = e / ST + 1, j = e - (r - 1) * ST;
-        const double a = 2.0 * (double)((long long)j * r) / (double)M;  // angle = 2 pi j r / M
-        const float wr = (float)cospi(a), wi = (float)(-sinpi(a));
-        fwd[e] = make_float4(wr, wi, -wi, wr);
-        inv[e] = make_float4(wr, -wi, wi, wr);
+    if (e < tw_per_butterfly(R) * ST) {
+        const int ei = e / ST, j = e - ei * ST;
+        const double a = 2.0 * (double)((long long)j * tw_exponent(R, ei)) / (double)M;  // angle = 2 pi j r / M
+        tab[e] = make_float2((float)cospi(a), (float)(-sinpi(a)));
     }
 }
+
+// ------------------------------------------------------------------ host side
+static int g_long_n = 8192;  // partition size of the long-filter path (tunable: gfx_fir_set_tuning)
+static int g_mid_n = 8192;   // FFT size for 2048 < taps <= g_mid_n / 2 (longer single-partition filters: 16384)
 
 static int pick_fft_size(int Nh) {
     if (Nh <= 512) return 1024;
     if (Nh <= 2048) return 4096;
-    return 16384;
+    if (Nh <= 16384) return Nh <= g_mid_n / 2 ? g_mid_n : 16384;
+    return g_long_n;
 }
 
 template <typename K>
@@ -505,26 +646,26 @@ static int set_smem(K kern, size_t smem) {
 }
 
 struct FirArgs {
-    const float* x; const float* h; float* y;
+    const float* x; FilterSrc fs; float* y;
     int batch, cx, ch; long long L; int Nh; int shift;
-    const float4* tw; unsigned char* ws; size_t ws_bytes; cudaStream_t stream;
+    const float2* plan; unsigned char* ws; size_t ws_bytes; cudaStream_t stream;
 };
 
 template <int N, int NT>
 static int run_ols(const FirArgs& a) {
     const int c_out = a.cx > a.ch ? a.cx : a.ch;
     const int rows = a.batch * c_out, hrows = a.batch * a.ch;
-    const size_t need = (size_t)hrows * N * sizeof(float2);
+    const size_t need = (size_t)hrows * (N / 2) * sizeof(float4);
     if (!a.ws || a.ws_bytes < need) return GFX_ERR_WORKSPACE;
-    float2* Hs = (float2*)a.ws;
+    float4* Hs = (float4*)a.ws;
     const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
     static bool configured = false;
     if (!configured) {
         if (set_smem(fir_spectrum_kernel<N, NT>, smem) || set_smem(fir_ols_kernel<N, NT>, smem)) return GFX_ERR_CUDA;
         configured = true;
     }
-    const int hvec = ((uintptr_t)a.h % 16 == 0);
-    fir_spectrum_kernel<N, NT><<<hrows, NT, smem, a.stream>>>(a.h, Hs, a.Nh, a.Nh, 1, a.tw, hvec);
+    const int hvec = ((uintptr_t)a.fs.h % 16 == 0);
+    fir_spectrum_kernel<N, NT><<<hrows, NT, smem, a.stream>>>(a.fs, Hs, 0, a.Nh, a.Nh, 1, a.plan, hvec);
     GFX_CUDA_CHECK(cudaGetLastError());
     const int pre = (a.Nh - 1 + 3) & ~3;
     const int hop = (2 * N - pre) & ~3;
@@ -534,23 +675,30 @@ static int run_ols(const FirArgs& a) {
     const int vec = (((uintptr_t)a.x | (uintptr_t)a.y) % 16 == 0) && (a.L % 4 == 0);
     RowMap rm{c_out, a.cx, a.ch};
     fir_ols_kernel<N, NT><<<(unsigned)(nblk * rows), NT, smem, a.stream>>>(a.x, a.y, Hs, rm, a.L, pre, hop, a.shift,
-                                                                           (int)nblk, a.tw, vec);
+                                                                           (int)nblk, a.plan, vec);
     GFX_CUDA_CHECK(cudaGetLastError());
     return GFX_OK;
 }
 
-static void upols_geometry(int batch, int cx, int ch, long long L, int Nh, int shift, int N, int& P, long long& nblk,
+static void upols_geometry(int cx, int ch, long long L, int Nh, int shift, int N, int& P, long long& nblk,
                            size_t& per_item_bytes) {
+    const int c_out = cx > ch ? cx : ch;
     P = (Nh + N - 1) / N;
     nblk = (L + shift + N - 1) / N;
-    per_item_bytes = ((size_t)ch * P + (size_t)cx * nblk) * N * sizeof(float2);
+    per_item_bytes = ((size_t)ch * P + (size_t)(cx + c_out) * nblk) * (N / 2) * sizeof(float4);
+}
+
+template <int PC>
+static void launch_mac(dim3 grid, cudaStream_t st, const float4* Xs, const float4* Hs, float4* Ys, RowMap rm, int xrow0,
+                       int hrow0, int row0, int P, int p0, int nblk, int half, int acc) {
+    fir_mac_kernel<PC><<<grid, MAC_NT, 0, st>>>(Xs, Hs, Ys, rm, xrow0, hrow0, row0, P, p0, nblk, half, acc);
 }
 
 template <int N, int NT>
 static int run_upols(const FirArgs& a) {
     const int c_out = a.cx > a.ch ? a.cx : a.ch;
     int P; long long nblk; size_t per_item;
-    upols_geometry(a.batch, a.cx, a.ch, a.L, a.Nh, a.shift, N, P, nblk, per_item);
+    upols_geometry(a.cx, a.ch, a.L, a.Nh, a.shift, N, P, nblk, per_item);
     if (!a.ws || a.ws_bytes < per_item) return GFX_ERR_WORKSPACE;
     long long chunk = (long long)(a.ws_bytes / per_item);
     if (chunk > a.batch) chunk = a.batch;
@@ -558,53 +706,97 @@ static int run_upols(const FirArgs& a) {
     static bool configured = false;
     if (!configured) {
         if (set_smem(fir_spectrum_kernel<N, NT>, smem) || set_smem(fir_xspec_kernel<N, NT>, smem) ||
-            set_smem(fir_upols_kernel<N, NT>, smem)) return GFX_ERR_CUDA;
+            set_smem(fir_inv_kernel<N, NT>, smem)) return GFX_ERR_CUDA;
         configured = true;
     }
-    const int hvec = ((uintptr_t)a.h % 16 == 0) && (a.Nh % 4 == 0);
+    constexpr int half = N / 2;
+    const int hvec = ((uintptr_t)a.fs.h % 16 == 0);
     const int vec = (((uintptr_t)a.x | (uintptr_t)a.y) % 16 == 0) && (a.L % 4 == 0);
     RowMap rm{c_out, a.cx, a.ch};
     for (long long b0 = 0; b0 < a.batch; b0 += chunk) {
         const int nb = (int)((a.batch - b0 < chunk) ? a.batch - b0 : chunk);
-        float2* Hs = (float2*)a.ws;
-        float2* Xs = Hs + (size_t)nb * a.ch * P * N;
+        float4* Hs = (float4*)a.ws;
+        float4* Xs = Hs + (size_t)nb * a.ch * P * half;
+        float4* Ys = Xs + (size_t)nb * a.cx * nblk * half;
         const int hrow0 = (int)b0 * a.ch, xrow0 = (int)b0 * a.cx, row0 = (int)b0 * c_out;
-        if ((long long)nb * a.cx * nblk > 0x7fffffffLL || (long long)nb * c_out * nblk > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
-        fir_spectrum_kernel<N, NT><<<nb * a.ch * P, NT, smem, a.stream>>>(a.h + (size_t)hrow0 * a.Nh, Hs, a.Nh, N, P,
-                                                                          a.tw, hvec);
+        if ((long long)nb * a.cx * nblk > 0x7fffffffLL || (long long)nb * c_out * nblk > 0x7fffffffLL ||
+            (long long)nb * c_out > 65535) return GFX_ERR_UNSUPPORTED;
+        fir_spectrum_kernel<N, NT><<<nb * a.ch * P, NT, smem, a.stream>>>(a.fs, Hs, hrow0, a.Nh, N, P, a.plan, hvec);
         GFX_CUDA_CHECK(cudaGetLastError());
         fir_xspec_kernel<N, NT><<<(unsigned)(nb * a.cx * nblk), NT, smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk,
-                                                                                      a.tw, vec);
+                                                                                      a.plan, vec);
         GFX_CUDA_CHECK(cudaGetLastError());
-        fir_upols_kernel<N, NT><<<(unsigned)(nb * c_out * nblk), NT, smem, a.stream>>>(
-            Xs, Hs, a.y, rm, row0, xrow0, hrow0, a.L, P, (int)nblk, a.shift, a.tw, vec);
+        const dim3 grid(half / MAC_NT, nb * c_out);
+        for (int p0 = 0; p0 < P; p0 += MAC_MAX_PC) {
+            const int pc = P - p0 < MAC_MAX_PC ? P - p0 : MAC_MAX_PC;
+            const int acc = p0 > 0;
+#define GFX_MAC_CASE(PCV) case PCV: launch_mac<PCV>(grid, a.stream, Xs, Hs, Ys, rm, xrow0, hrow0, row0, P, p0, (int)nblk, half, acc); break;
+            switch (pc) {
+                GFX_MAC_CASE(1) GFX_MAC_CASE(2) GFX_MAC_CASE(3) GFX_MAC_CASE(4) GFX_MAC_CASE(5) GFX_MAC_CASE(6)
+                GFX_MAC_CASE(7) GFX_MAC_CASE(8) GFX_MAC_CASE(9) GFX_MAC_CASE(10) GFX_MAC_CASE(11) GFX_MAC_CASE(12)
+            }
+#undef GFX_MAC_CASE
+            GFX_CUDA_CHECK(cudaGetLastError());
+        }
+        fir_inv_kernel<N, NT><<<(unsigned)(nb * c_out * nblk), NT, smem, a.stream>>>(Ys, a.y, row0, a.L, (int)nblk,
+                                                                                     a.shift, a.plan, vec);
         GFX_CUDA_CHECK(cudaGetLastError());
     }
     return GFX_OK;
+}
+
+static int fir_dispatch(const FirArgs& a) {
+    const int n = pick_fft_size(a.Nh);
+    if (a.Nh <= 16384) {
+        if (n == 1024) return run_ols<1024, 128>(a);
+        if (n == 4096) return run_ols<4096, 256>(a);
+        if (n == 8192) return run_ols<8192, 256>(a);
+        return run_ols<16384, 512>(a);
+    }
+    if (n == 4096) return run_upols<4096, 256>(a);
+    if (n == 8192) return run_upols<8192, 256>(a);
+    return run_upols<16384, 512>(a);
 }
 
 }  // namespace gfx
 
 extern "C" {
 
+int gfx_fir_set_tuning(int long_n, int mid_n) {
+    if (long_n) {
+        if (long_n != 4096 && long_n != 8192 && long_n != 16384) return GFX_ERR_INVALID;
+        gfx::g_long_n = long_n;
+    }
+    if (mid_n) {
+        if (mid_n != 8192 && mid_n != 16384) return GFX_ERR_INVALID;
+        gfx::g_mid_n = mid_n;
+    }
+    return GFX_OK;
+}
+
 int gfx_fir_fft_size(int filter_len) { return filter_len <= 0 ? GFX_ERR_INVALID : gfx::pick_fft_size(filter_len); }
 
 size_t gfx_fft_plan_bytes(int n) {
-    if (n != 1024 && n != 4096 && n != 16384) return 0;
-    return ((size_t)n / 2 + 2 * (size_t)gfx::plan_total(n)) * sizeof(float4);
+    if (!gfx::plan_ok(n)) return 0;
+    return ((size_t)n / 2 + (size_t)gfx::plan_total(n)) * sizeof(float2);
 }
 
 int gfx_fft_plan_init(void* plan, int n, void* stream) {
-    if (!plan || (n != 1024 && n != 4096 && n != 16384)) return GFX_ERR_INVALID;
-    float4* base = (float4*)plan;
-    gfx::fft_plan_half_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float2*)plan, n);
+    using namespace gfx;
+    if (!plan || !plan_ok(n)) return GFX_ERR_INVALID;
+    float2* base = (float2*)plan;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gb = (n / 2 + 255) / 256;
+    if (n == 1024) fft_plan_pairs_kernel<1024><<<gb, 256, 0, st>>>(base);
+    else if (n == 4096) fft_plan_pairs_kernel<4096><<<gb, 256, 0, st>>>(base);
+    else if (n == 8192) fft_plan_pairs_kernel<8192><<<gb, 256, 0, st>>>(base);
+    else fft_plan_pairs_kernel<16384><<<gb, 256, 0, st>>>(base);
     GFX_CUDA_CHECK(cudaGetLastError());
-    for (int s = 0; s < 4; ++s) {
-        const int entries = gfx::plan_entries(n, s);
+    for (int s = 0; s < plan_stages(n); ++s) {
+        const int entries = plan_entries(n, s);
         if (entries == 0) continue;
-        float4* fwd = base + n / 2 + gfx::plan_offset(n, s);
-        gfx::fft_plan_pass_kernel<<<(entries + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-            fwd, fwd + gfx::plan_total(n), gfx::plan_m(n, s), gfx::plan_radix(n, s));
+        fft_plan_pass_kernel<<<(entries + 255) / 256, 256, 0, st>>>(base + n / 2 + plan_offset(n, s), plan_m(n, s),
+                                                                   plan_radix(n, s));
         GFX_CUDA_CHECK(cudaGetLastError());
     }
     return GFX_OK;
@@ -613,32 +805,41 @@ int gfx_fft_plan_init(void* plan, int n, void* stream) {
 size_t gfx_fir_conv_workspace_bytes(int batch, int cx, int ch, long long L, int filter_len, int zerophase) {
     if (batch <= 0 || cx <= 0 || ch <= 0 || L <= 0 || filter_len <= 0) return 0;
     const int n = gfx::pick_fft_size(filter_len);
-    if (filter_len <= 16384) return (size_t)batch * ch * n * sizeof(float2);
+    if (filter_len <= 16384) return (size_t)batch * ch * (n / 2) * sizeof(float4);
     int P; long long nblk; size_t per_item;
-    gfx::upols_geometry(batch, cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, n, P, nblk, per_item);
-    // spectra of ~48 MB worth of batch items per sweep stay L2-resident on B200 (126 MB L2)
-    size_t items = (size_t)(48u << 20) / per_item;
+    gfx::upols_geometry(cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, n, P, nblk, per_item);
+    // spectra of up to ~1.5 GB worth of batch items per sweep (every kernel of a sweep then has several full waves)
+    size_t items = ((size_t)1536 << 20) / per_item;
     if (items < 1) items = 1;
     if (items > (size_t)batch) items = batch;
     return items * per_item;
 }
 
+static int fir_conv_common(const float* x, gfx::FilterSrc fs, float* y, int batch, int cx, int ch, long long L,
+                           int filter_len, int zerophase, const void* plan, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    using namespace gfx;
+    if (!x || !fs.h || !y || !plan) return GFX_ERR_INVALID;
+    if (batch <= 0 || cx <= 0 || ch <= 0 || L <= 0 || filter_len <= 0) return GFX_ERR_INVALID;
+    if (cx != ch && cx != 1 && ch != 1) return GFX_ERR_INVALID;
+    FirArgs a{x, fs, y, batch, cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, (const float2*)plan,
+              (unsigned char*)workspace, workspace_bytes, (cudaStream_t)stream};
+    return fir_dispatch(a);
+}
+
 int gfx_fir_conv_f32(const float* x, const float* h, float* y, int batch, int cx, int ch, long long L,
                      int filter_len, int zerophase, const void* plan, void* workspace, size_t workspace_bytes,
                      void* stream) {
-    using namespace gfx;
-    if (!x || !h || !y || !plan) return GFX_ERR_INVALID;
-    if (batch <= 0 || cx <= 0 || ch <= 0 || L <= 0 || filter_len <= 0) return GFX_ERR_INVALID;
-    if (cx != ch && cx != 1 && ch != 1) return GFX_ERR_INVALID;
-    FirArgs a{x, h, y, batch, cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, (const float4*)plan,
-              (unsigned char*)workspace, workspace_bytes, (cudaStream_t)stream};
-    const int n = pick_fft_size(filter_len);
-    if (filter_len <= 16384) {
-        if (n == 1024) return run_ols<1024, 128>(a);
-        if (n == 4096) return run_ols<4096, 256>(a);
-        return run_ols<16384, 1024>(a);
-    }
-    return run_upols<16384, 1024>(a);
+    return fir_conv_common(x, gfx::FilterSrc{h, nullptr, 0}, y, batch, cx, ch, L, filter_len, zerophase, plan,
+                           workspace, workspace_bytes, stream);
+}
+
+int gfx_fir_conv_midside_ir_f32(const float* x, const float* ir_raw, const float* energy, float* y, int batch, int cx,
+                                long long L, int ir_len, int ms_to_lr, const void* plan, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    if (!energy) return GFX_ERR_INVALID;
+    return fir_conv_common(x, gfx::FilterSrc{ir_raw, energy, ms_to_lr ? 1 : 0}, y, batch, cx, 2, L, ir_len, 0, plan,
+                           workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"
