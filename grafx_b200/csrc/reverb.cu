@@ -8,19 +8,25 @@
 // torch.istft(center=True) is: per frame irfft * window, overlap-add at m*hop, divide by the
 // overlap-added squared window, drop n_fft/2 leading samples, keep ir_len.
 //
-// One CTA owns one (batch item, mid|side) row and walks its frames in tiles of 16.  A frame is
-// inverted by 16 threads: the 384-point real inverse DFT is split as n = 6q + r into six 64-point
-// inverse DFTs of  G_r[k0] = sum_j X[k0 + 64 j] e^{2 pi i (k0 + 64 j) r / 384};  residues are paired
-// (G_2s + i G_2s+1) so that three complex radix-4 FFT-64 (shared memory, digit-reversed input)
-// yield the 384 real samples.  Supported geometry: n_fft = 384, hop = 192 (the reference default).
+// One CTA owns 16 consecutive frames of one (batch item, mid|side) row and emits the 15 hops they
+// fully determine (one frame of overlap between neighbouring CTAs is recomputed: +6.7 % work, no
+// carried state, 34 x rows independent CTAs).  A frame is inverted by 16 threads: the 384-point
+// inverse real DFT is a 192-point complex inverse FFT of the re-tangled half spectrum
+// (fftcore.cuh: retangle_pair), done as 192 = 16 x 12:
+//   thread t: inverse DFT-12 (3 x radix-4, 4 x radix-3) of Z[t + 16 m], twiddle e^{2 pi i r t / 192},
+//   exchange through shared memory, thread r < 12: inverse DFT-16 -> z[r + 12 s] = x[2n] + i x[2n+1].
+// Row energies are reduced per CTA into `partial` and summed in a fixed order (deterministic).
+// Supported geometry: n_fft = 384, hop = 192 (the reference default).
 #include "common.cuh"
+#include "fftcore.cuh"
 
 namespace gfx {
 
-constexpr int RV_NFFT = 384, RV_HOP = 192, RV_BINS = 193, RV_FT = 16;  // frames per tile
+constexpr int RV_NFFT = 384, RV_HOP = 192, RV_BINS = 193, RV_N = 192;
+constexpr int RV_FT = 16;         // frames per CTA
+constexpr int RV_HT = RV_FT - 1;  // hops emitted per CTA
 constexpr int RV_NT = 256;
-
-__device__ __forceinline__ int drev4_3(int p) { return ((p & 3) << 4) | (p & 12) | ((p >> 4) & 3); }
+constexpr int RV_ZS = 209;        // 64-bit slots per frame work buffer (odd: conflict-free across frames)
 
 struct ReverbParams {
     const float2* noise;      // [noise_batch?][2][bins][frames]
@@ -30,163 +36,174 @@ struct ReverbParams {
     const float* genv;        // [B][2][frames] or null
     const float* window;      // [384]
     float* ir;                // [B][2][ir_len]  (mid/side, un-normalised)
-    float* energy;            // [B][2]  sum_t ir^2
-    int frames, ir_len;
+    float* partial;           // [B*2][tiles]  sum of ir^2 per CTA
+    int frames, ir_len, tiles;
 };
 
-__global__ void __launch_bounds__(RV_NT) reverb_ir_kernel(const ReverbParams p) {
+// inverse DFT-3 (unnormalised): y_r = sum_m a_m e^{+2 pi i m r / 3}
+__device__ __forceinline__ void idft3(pk2& a0, pk2& a1, pk2& a2) {
+    const pk2 s = pk_add(a1, a2), d = pk_sub(a1, a2);
+    const pk2 t = pk_fma(s, pk_dup(-0.5f), a0);
+    const pk2 r = pk_mul(pk_swap(d), pk_make(-0.86602540378443865f, 0.86602540378443865f));  // i (sqrt3/2) d
+    a0 = pk_add(a0, s);
+    a1 = pk_add(t, r);
+    a2 = pk_sub(t, r);
+}
+
+// inverse DFT-12 in registers.  In: a[m] natural order.  Out: register a[r1 + 3 r2] holds A[r2 + 4 r1].
+__device__ __forceinline__ void idft12(pk2 (&a)[12]) {
+#pragma unroll
+    for (int m1 = 0; m1 < 3; ++m1) r4<true>(a[m1], a[m1 + 3], a[m1 + 6], a[m1 + 9]);
+    // a[m1 + 3 r2] *= e^{+2 pi i m1 r2 / 12}   (tw_apply<true> multiplies by the conjugate of its argument)
+    const float C = 0.86602540378443865f;
+    a[1 + 3] = tw_apply<true>(a[1 + 3], make_float2(C, -0.5f));      // e^{i pi/6}
+    a[1 + 6] = tw_apply<true>(a[1 + 6], make_float2(0.5f, -C));      // e^{i pi/3}
+    a[1 + 9] = mul_minus_i<true>(a[1 + 9]);                          // i
+    a[2 + 3] = tw_apply<true>(a[2 + 3], make_float2(0.5f, -C));      // e^{i pi/3}
+    a[2 + 6] = tw_apply<true>(a[2 + 6], make_float2(-0.5f, -C));     // e^{2 i pi/3}
+    a[2 + 9] = pk_mul(a[2 + 9], pk_dup(-1.f));                       // -1
+#pragma unroll
+    for (int r2 = 0; r2 < 4; ++r2) idft3(a[3 * r2], a[3 * r2 + 1], a[3 * r2 + 2]);
+}
+
+__global__ void __launch_bounds__(RV_NT, 3) reverb_ir_kernel(const ReverbParams p) {
     extern __shared__ __align__(16) unsigned char rv_smem[];
-    float2* tw = reinterpret_cast<float2*>(rv_smem);                        // [384] e^{+2 pi i t / 384}
-    float2 (*X)[RV_BINS + 1] = reinterpret_cast<float2 (*)[RV_BINS + 1]>(tw + RV_NFFT);   // [16][194] masked spectra
-    float (*fr)[3][64] = reinterpret_cast<float (*)[3][64]>(X + RV_FT);     // [16][3][64]
-    float (*fi)[3][64] = fr + RV_FT;
-    float (*frame)[RV_NFFT] = reinterpret_cast<float (*)[RV_NFFT]>(fi + RV_FT);  // [16][384] windowed frames
-    float* a0 = reinterpret_cast<float*>(frame + RV_FT);                    // [193] H0/8 ... actually H0
-    float* a1 = a0 + RV_BINS + 3;                                           // [193] softplus(Hd)
-    float* win = a1 + RV_BINS + 3;                                          // [384]
-    float* carry = win + RV_NFFT;                                           // [192]
-    float* red = carry + RV_HOP;                                            // [8]
+    pk2* zb = reinterpret_cast<pk2*>(rv_smem);                        // [16][RV_ZS]
+    float* fr = reinterpret_cast<float*>(zb + RV_FT * RV_ZS);         // [16][384] windowed frames
+    float2* w192 = reinterpret_cast<float2*>(fr + RV_FT * RV_NFFT);   // [192] e^{+2 pi i j / 192}
+    float2* hw = w192 + RV_N;                                         // [96]  e^{-i pi k / 192}
+    float* win = reinterpret_cast<float*>(hw + RV_N / 2);             // [384]
+    float* a0 = win + RV_NFFT;                                        // [196] H0
+    float* a1 = a0 + RV_BINS + 3;                                     // [196] softplus(Hd)
+    float* xn = a1 + RV_BINS + 3;                                     // [16]  Nyquist bin (real) per frame
+    float* red = xn + RV_FT;                                          // [8]
 
     const int tid = threadIdx.x;
-    const int row = blockIdx.x;  // b * 2 + ch
+    const int tile = blockIdx.x % p.tiles, row = blockIdx.x / p.tiles;  // row = b * 2 + ch
     const int b = row >> 1, ch = row & 1;
     const float2* noise = p.noise + (size_t)b * p.noise_bstride + (size_t)ch * RV_BINS * p.frames;
     const float* genv = p.genv ? p.genv + (size_t)row * p.frames : nullptr;
+    const int m0 = tile * RV_HT;  // first frame of the CTA; hops m0+1 .. m0+15
 
     for (int t = tid; t < RV_NFFT; t += RV_NT) {
-        float s, c;
-        sincospif(2.f * (float)t / (float)RV_NFFT, &s, &c);
-        tw[t] = make_float2(c, s);
         win[t] = p.window[t];
+        if (t < RV_N) {
+            float s, c;
+            sincospif((float)t * (2.f / (float)RV_N), &s, &c);
+            w192[t] = make_float2(c, s);
+        } else if (t < RV_N + RV_N / 2) {
+            float s, c;
+            sincospif((float)(t - RV_N) * (1.f / (float)RV_N), &s, &c);
+            hw[t - RV_N] = make_float2(c, -s);
+        }
     }
     for (int k = tid; k < RV_BINS; k += RV_NT) {
         a0[k] = p.h0[(size_t)row * RV_BINS + k];
         const float d = p.hd[(size_t)row * RV_BINS + k];
         a1[k] = d > 20.f ? d : log1pf(expf(d));  // torch softplus
     }
-    for (int n = tid; n < RV_HOP; n += RV_NT) carry[n] = 0.f;
     __syncthreads();
 
-    const int g = tid >> 4, tau = tid & 15;  // frame slot within the tile, thread within the frame group
-    float esum = 0.f;
-    const int last_tp = RV_HOP + p.ir_len - 1;           // last needed overlap-add position
-    const int ntiles = last_tp / (RV_FT * RV_HOP) + 1;
-
-    for (int tile = 0; tile < ntiles; ++tile) {
-        const int m0 = tile * RV_FT;
-        // 1. masked spectra of the tile's frames (coalesced over the frame axis)
-        for (int i = tid; i < RV_BINS * RV_FT; i += RV_NT) {
-            const int k = i / RV_FT, f = i - k * RV_FT;
-            const int m = m0 + f;
-            float2 v = make_float2(0.f, 0.f);
-            if (m < p.frames) {
-                const float2 nz = __ldg(noise + (size_t)k * p.frames + m);
-                float lg = a0[k] - a1[k] * (float)m;
-                if (genv) lg += genv[m];
-                const float mk = expf(lg * 0.125f);
-                v = make_float2(nz.x * mk, (k == 0 || k == RV_BINS - 1) ? 0.f : nz.y * mk);
-            }
-            X[f][k] = v;
+    // 1. masked spectra of the CTA's frames (coalesced over the frame axis); bins 0 and 192 are real
+    for (int i = tid; i < RV_BINS * RV_FT; i += RV_NT) {
+        const int k = i >> 4, f = i & (RV_FT - 1);
+        const int m = m0 + f;
+        float2 v = make_float2(0.f, 0.f);
+        if (m < p.frames) {
+            const float2 nz = __ldg(noise + (size_t)k * p.frames + m);
+            float lg = a0[k] - a1[k] * (float)m;
+            if (genv) lg += genv[m];
+            const float mk = __expf(lg * 0.125f);
+            v = make_float2(nz.x * mk, nz.y * mk);
         }
-        __syncthreads();
-        // 2. residue spectra G_r[k0], paired and scattered in digit-reversed order
-        if (m0 + g < p.frames) {
-            for (int k0 = tau; k0 < 64; k0 += 16) {
-                float2 xf[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    const int k = k0 + 64 * j;
-                    if (k <= 192) xf[j] = X[g][k];
-                    else { const float2 c = X[g][384 - k]; xf[j] = make_float2(c.x, -c.y); }
-                }
-                float2 G[6];
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    float gr = 0.f, gi = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const float2 w = tw[((k0 + 64 * j) * r) % RV_NFFT];
-                        gr = fmaf(xf[j].x, w.x, gr); gr = fmaf(-xf[j].y, w.y, gr);
-                        gi = fmaf(xf[j].x, w.y, gi); gi = fmaf(xf[j].y, w.x, gi);
-                    }
-                    G[r] = make_float2(gr, gi);
-                }
-                const int pos = drev4_3(k0);
-#pragma unroll
-                for (int s = 0; s < 3; ++s) {
-                    fr[g][s][pos] = G[2 * s].x - G[2 * s + 1].y;
-                    fi[g][s][pos] = G[2 * s].y + G[2 * s + 1].x;
-                }
-            }
-        }
-        __syncwarp();
-        // 3. three inverse FFT-64 (decimation in time, radix 4), 16 threads = 16 butterflies per pass.
-        // NB every lane of the warp reaches each __syncwarp (the two frame groups of a warp may differ
-        // in validity at the end of the frame axis).
-        const bool fvalid = (m0 + g < p.frames);
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-            if (fvalid) {
-                const int ST = 1 << (2 * pass);              // 1, 4, 16
-                const int TWS = RV_NFFT / (4 * ST);          // 384/M : 96, 24, 6
-                const int j = tau & (ST - 1);
-                const int i0 = ((tau - j) << 2) + j;
-#pragma unroll
-                for (int s = 0; s < 3; ++s) {
-                    float* re = fr[g][s];
-                    float* im = fi[g][s];
-                    float2 u0 = make_float2(re[i0], im[i0]);
-                    float2 u1 = make_float2(re[i0 + ST], im[i0 + ST]);
-                    float2 u2 = make_float2(re[i0 + 2 * ST], im[i0 + 2 * ST]);
-                    float2 u3 = make_float2(re[i0 + 3 * ST], im[i0 + 3 * ST]);
-                    if (pass > 0) {
-                        const float2 w1 = tw[j * TWS], w2 = tw[2 * j * TWS], w3 = tw[3 * j * TWS];
-                        u1 = make_float2(u1.x * w1.x - u1.y * w1.y, u1.x * w1.y + u1.y * w1.x);
-                        u2 = make_float2(u2.x * w2.x - u2.y * w2.y, u2.x * w2.y + u2.y * w2.x);
-                        u3 = make_float2(u3.x * w3.x - u3.y * w3.y, u3.x * w3.y + u3.y * w3.x);
-                    }
-                    const float s02r = u0.x + u2.x, s02i = u0.y + u2.y, d02r = u0.x - u2.x, d02i = u0.y - u2.y;
-                    const float s13r = u1.x + u3.x, s13i = u1.y + u3.y, d13r = u1.x - u3.x, d13i = u1.y - u3.y;
-                    re[i0] = s02r + s13r; im[i0] = s02i + s13i;
-                    re[i0 + ST] = d02r - d13i; im[i0 + ST] = d02i + d13r;
-                    re[i0 + 2 * ST] = s02r - s13r; im[i0 + 2 * ST] = s02i - s13i;
-                    re[i0 + 3 * ST] = d02r + d13i; im[i0 + 3 * ST] = d02i - d13r;
-                }
-            }
-            __syncwarp();
-        }
-        if (fvalid) {
-            // 4. interleave residues, scale, window
-            for (int n = tau; n < RV_NFFT; n += 16) {
-                const int q = n / 6, r = n - 6 * q;
-                const float v = (r & 1) ? fi[g][r >> 1][q] : fr[g][r >> 1][q];
-                frame[g][n] = v * (1.f / (float)RV_NFFT) * win[n];
-            }
-        }
-        __syncthreads();
-        // 5. overlap-add, envelope division, trim
-        for (int i = tid; i < RV_FT * RV_HOP; i += RV_NT) {
-            const int f = i / RV_HOP, n = i - f * RV_HOP;
-            const int m = m0 + f;
-            const int tp = m * RV_HOP + n;
-            const int t = tp - RV_HOP;
-            if (t < 0 || t >= p.ir_len) continue;
-            float val = 0.f, env = 0.f;
-            if (m < p.frames) { val = frame[f][n]; env = win[n] * win[n]; }
-            if (m >= 1 && m - 1 < p.frames) {
-                val += (f > 0) ? frame[f - 1][n + RV_HOP] : carry[n];
-                env += win[n + RV_HOP] * win[n + RV_HOP];
-            }
-            val = val / env;
-            p.ir[(size_t)row * p.ir_len + t] = val;
-            esum = fmaf(val, val, esum);
-        }
-        __syncthreads();
-        for (int n = tid; n < RV_HOP; n += RV_NT)
-            carry[n] = (m0 + RV_FT - 1 < p.frames) ? frame[RV_FT - 1][n + RV_HOP] : 0.f;
-        __syncthreads();
+        if (k == RV_BINS - 1) xn[f] = v.x;
+        else zb[f * RV_ZS + k] = pk_make(v.x, v.y);
     }
-    // energy of the row
+    __syncthreads();
+
+    const int g = tid >> 4, tau = tid & 15;  // frame slot, thread within the frame group
+    pk2* z = zb + g * RV_ZS;
+    // 2. re-tangle the half spectrum into the 192-point complex spectrum (in place, pair-local)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int k = tau + 16 * i;
+        if (k == 0) {
+            float x0, x0i, xh, xhi;
+            pk_split(z[0], x0, x0i);
+            pk_split(z[RV_N / 2], xh, xhi);
+            const float xN = xn[g];
+            z[0] = pk_make(0.5f * (x0 + xN), 0.5f * (x0 - xN));
+            z[RV_N / 2] = pk_make(xh, -xhi);
+        } else {
+            float yr, yi, mr, mi;
+            pk_split(z[k], yr, yi);
+            pk_split(z[RV_N - k], mr, mi);
+            const PairA a = retangle_pair(make_float2(yr, yi), make_float2(mr, mi), hw[k]);
+            z[k] = pk_make(a.k.x, a.k.y);
+            z[RV_N - k] = pk_make(a.m.x, a.m.y);
+        }
+    }
+    __syncwarp();
+    // 3. thread tau: inverse DFT-12 over Z[tau + 16 m], twiddle, to B[r][tau] at slot r * 17 + tau
+    {
+        pk2 a[12];
+#pragma unroll
+        for (int m = 0; m < 12; ++m) a[m] = z[tau + 16 * m];
+        __syncwarp();  // every Z has been read before B overwrites the buffer
+        idft12(a);
+#pragma unroll
+        for (int r1 = 0; r1 < 3; ++r1) {
+#pragma unroll
+            for (int r2 = 0; r2 < 4; ++r2) {
+                const int r = r2 + 4 * r1;
+                pk2 v = a[r1 + 3 * r2];
+                if (r > 0) v = tw_apply<false>(v, w192[r * tau]);
+                z[r * 17 + tau] = v;
+            }
+        }
+    }
+    __syncwarp();
+    // 4. thread r < 12: inverse DFT-16 over B[r][.] -> z[r + 12 s], scaled and windowed into the frame
+    if (tau < 12) {
+        pk2 bq[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) bq[t] = z[tau * 17 + t];
+        r16<true>(bq);
+        float* frame = fr + g * RV_NFFT;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int s = 4 * j + i;
+                const int n = tau + 12 * s;
+                float re, im;
+                pk_split(bq[4 * i + j], re, im);
+                const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * n);
+                *reinterpret_cast<float2*>(frame + 2 * n) =
+                    make_float2(re * (1.f / (float)RV_N) * w2.x, im * (1.f / (float)RV_N) * w2.y);
+            }
+        }
+    }
+    __syncthreads();
+
+    // 5. overlap-add, envelope division, trim
+    float esum = 0.f;
+    float* irow = p.ir + (size_t)row * p.ir_len;
+    for (int i = tid; i < RV_HT * RV_HOP; i += RV_NT) {
+        const int hh = i / RV_HOP, n = i - hh * RV_HOP;
+        const int h = m0 + 1 + hh;                 // hop index = frame index of its first half
+        const int t = (h - 1) * RV_HOP + n;        // output sample (tp - hop)
+        if (t >= p.ir_len) continue;
+        float val = 0.f, env = 0.f;
+        if (h < p.frames) { val = fr[(hh + 1) * RV_NFFT + n]; env = win[n] * win[n]; }
+        if (h - 1 < p.frames) {
+            val += fr[hh * RV_NFFT + n + RV_HOP];
+            env += win[n + RV_HOP] * win[n + RV_HOP];
+        }
+        val = val / env;
+        irow[t] = val;
+        esum = fmaf(val, val, esum);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
     if ((tid & 31) == 0) red[tid >> 5] = esum;
@@ -194,7 +211,16 @@ __global__ void __launch_bounds__(RV_NT) reverb_ir_kernel(const ReverbParams p) 
     if (tid == 0) {
         float s = 0.f;
         for (int w = 0; w < RV_NT / 32; ++w) s += red[w];
-        p.energy[row] = s;
+        p.partial[(size_t)row * p.tiles + tile] = s;
+    }
+}
+
+__global__ void reverb_energy_kernel(const float* __restrict__ partial, float* __restrict__ energy, int rows, int tiles) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) {
+        float s = 0.f;
+        for (int t = 0; t < tiles; ++t) s += partial[(size_t)r * tiles + t];
+        energy[r] = s;
     }
 }
 
@@ -222,37 +248,62 @@ __global__ void __launch_bounds__(256) reverb_finalize_kernel(float* ir, const f
     }
 }
 
+static int reverb_tiles(int ir_len) {
+    const int last_hop = (RV_HOP - 1 + ir_len) / RV_HOP;  // hops 1 .. last_hop carry output samples
+    return (last_hop + RV_HT - 1) / RV_HT;
+}
+
 }  // namespace gfx
 
-extern "C" int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, const float* init_log_magnitude,
-                                 const float* delta_log_magnitude, const float* gain_env_log_magnitude,
-                                 const float* window, float* ir, float* energy_ws, int batch, int n_fft, int hop,
-                                 int ir_len, int ms_to_lr, void* stream) {
+extern "C" {
+
+size_t gfx_reverb_ir_workspace_bytes(int batch, int ir_len) {
+    if (batch <= 0 || ir_len <= 0) return 0;
+    return ((size_t)batch * 2 * (gfx::reverb_tiles(ir_len) + 1)) * sizeof(float);
+}
+
+// mode: 0 = raw mid/side IR + energies only, 1 = normalise in place, 2 = ms_to_lr + normalise in place
+int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, const float* init_log_magnitude,
+                      const float* delta_log_magnitude, const float* gain_env_log_magnitude,
+                      const float* window, float* ir, float* energy, void* workspace, size_t workspace_bytes,
+                      int batch, int n_fft, int hop, int ir_len, int mode, void* stream) {
     using namespace gfx;
-    if (!noise_stft || !init_log_magnitude || !delta_log_magnitude || !window || !ir || !energy_ws) return GFX_ERR_INVALID;
-    if (batch <= 0 || ir_len <= 0) return GFX_ERR_INVALID;
+    if (!noise_stft || !init_log_magnitude || !delta_log_magnitude || !window || !ir || !energy) return GFX_ERR_INVALID;
+    if (batch <= 0 || ir_len <= 0 || mode < 0 || mode > 2) return GFX_ERR_INVALID;
     if (n_fft != RV_NFFT || hop != RV_HOP) return GFX_ERR_UNSUPPORTED;
+    const int tiles = reverb_tiles(ir_len);
+    if (!workspace || workspace_bytes < (size_t)batch * 2 * tiles * sizeof(float)) return GFX_ERR_WORKSPACE;
+    if ((long long)batch * 2 * tiles > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
     ReverbParams p;
     p.noise = (const float2*)noise_stft;
     p.noise_bstride = noise_batch_stride;
     p.h0 = init_log_magnitude; p.hd = delta_log_magnitude; p.genv = gain_env_log_magnitude;
-    p.window = window; p.ir = ir; p.energy = energy_ws;
+    p.window = window; p.ir = ir; p.partial = (float*)workspace;
     p.frames = 1 + ir_len / hop;
     p.ir_len = ir_len;
-    const size_t smem = sizeof(float2) * (RV_NFFT + RV_FT * (RV_BINS + 1)) +
-                        sizeof(float) * (2 * RV_FT * 3 * 64 + RV_FT * RV_NFFT + 2 * (RV_BINS + 3) + RV_NFFT + RV_HOP + 8);
+    p.tiles = tiles;
+    const size_t smem = sizeof(pk2) * (RV_FT * RV_ZS) + sizeof(float) * (RV_FT * RV_NFFT) +
+                        sizeof(float2) * (RV_N + RV_N / 2) +
+                        sizeof(float) * (RV_NFFT + 2 * (RV_BINS + 3) + RV_FT + 8);
     static bool configured = false;
     if (!configured) {
         GFX_CUDA_CHECK(cudaFuncSetAttribute(reverb_ir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    reverb_ir_kernel<<<batch * 2, RV_NT, smem, (cudaStream_t)stream>>>(p);
+    cudaStream_t st = (cudaStream_t)stream;
+    reverb_ir_kernel<<<(unsigned)(batch * 2 * tiles), RV_NT, smem, st>>>(p);
     GFX_CUDA_CHECK(cudaGetLastError());
-    const long long total = (long long)batch * ir_len;
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)device_info().sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    reverb_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ir, energy_ws, batch, ir_len, ms_to_lr);
+    reverb_energy_kernel<<<(batch * 2 + 127) / 128, 128, 0, st>>>(p.partial, energy, batch * 2, tiles);
     GFX_CUDA_CHECK(cudaGetLastError());
+    if (mode != 0) {
+        const long long total = (long long)batch * ir_len;
+        long long blocks = (total + 255) / 256;
+        const long long cap = (long long)device_info().sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        reverb_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(ir, energy, batch, ir_len, mode == 2);
+        GFX_CUDA_CHECK(cudaGetLastError());
+    }
     return GFX_OK;
 }
+
+}  // extern "C"

@@ -267,9 +267,14 @@ def node_sum(src: torch.Tensor, node_dim: int, index: torch.Tensor | None = None
 
 def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_log_magnitude: torch.Tensor,
               gain_env_log_magnitude: torch.Tensor | None, window: torch.Tensor, ir_len: int, n_fft: int,
-              hop_length: int, to_lr: bool) -> torch.Tensor:
-    """Masked-noise STFT -> impulse response [B, 2, ir_len], (ms->lr) and unit-energy normalised
-    (reference: STFTMaskedNoiseReverb.compute_ir + _process_* prologue, reverb.py:161-228)."""
+              hop_length: int, finish: str = "unit"):
+    """Masked-noise STFT -> impulse response [B, 2, ir_len]
+    (reference: STFTMaskedNoiseReverb.compute_ir + _process_* prologue, reverb.py:161-228).
+
+    finish = "unit": mid/side rows normalised to unit energy (normalize_impulse);
+             "lr":   ms_to_lr, then normalised (pseudo_midside);
+             "raw":  returns (ir_raw, energy[B, 2]) for fir_conv_midside_ir, which applies the channel
+                     epilogue while it forms the filter spectra (the finished IR is never stored)."""
     _cabi.require_cuda(noise_stft, init_log_magnitude, delta_log_magnitude, window)
     B = init_log_magnitude.shape[0]
     bins, frames = n_fft // 2 + 1, 1 + ir_len // hop_length
@@ -285,16 +290,44 @@ def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_
         ge = _prep(gain_env_log_magnitude, torch.float32)
         assert tuple(ge.shape) == (B, 2, frames)
     win = _prep(window, torch.float32)
+    mode = {"raw": 0, "unit": 1, "lr": 2}[finish]
     ir = torch.empty(B, 2, ir_len, dtype=torch.float32, device=h0.device)
     energy = torch.empty(B, 2, dtype=torch.float32, device=h0.device)
+    if B == 0:
+        return (ir, energy) if mode == 0 else ir
+    L_ = _cabi.lib()
+    ws = _cabi.workspace(L_.gfx_reverb_ir_workspace_bytes(B, ir_len), h0.device)
     with torch.cuda.device(h0.device):
-        code = _cabi.lib().gfx_reverb_ir_f32(nz.data_ptr(), bstride, h0.data_ptr(), hd.data_ptr(), _cabi.ptr(ge),
-                                             win.data_ptr(), ir.data_ptr(), energy.data_ptr(), B, n_fft, hop_length,
-                                             ir_len, int(to_lr), _cabi.stream_ptr())
+        code = L_.gfx_reverb_ir_f32(nz.data_ptr(), bstride, h0.data_ptr(), hd.data_ptr(), _cabi.ptr(ge),
+                                    win.data_ptr(), ir.data_ptr(), energy.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    B, n_fft, hop_length, ir_len, mode, _cabi.stream_ptr())
     if code == -4:
         raise NotImplementedError("reverb IR synthesis supports n_fft=384, hop_length=192 only")
     _cabi.check(code, "gfx_reverb_ir_f32")
-    return ir
+    return (ir, energy) if mode == 0 else ir
+
+
+def fir_conv_midside_ir(x: torch.Tensor, ir_raw: torch.Tensor, energy: torch.Tensor, to_lr: bool) -> torch.Tensor:
+    """Causal convolution of x [B, 1|2, L] with the reverb response given as the raw mid/side IR
+    [B, 2, N] + its row energies [B, 2]: ms_to_lr (optional) and normalize_impulse
+    (reverb.py:215-228) are folded into the filter spectra."""
+    _cabi.require_cuda(x, ir_raw, energy)
+    assert x.ndim == 3 and ir_raw.ndim == 3 and ir_raw.shape[1] == 2 and x.shape[0] == ir_raw.shape[0]
+    B, cx, L = x.shape
+    N = ir_raw.shape[2]
+    assert cx in (1, 2), "channel mismatch between signal and filter"
+    x, ir_raw, energy = _prep(x, torch.float32), _prep(ir_raw, torch.float32), _prep(energy, torch.float32)
+    y = torch.empty(B, 2, L, dtype=torch.float32, device=x.device)
+    if y.numel():
+        L_ = _cabi.lib()
+        plan = _fft_plan(x.device, L_.gfx_fir_fft_size(N))
+        ws = _cabi.workspace(L_.gfx_fir_conv_workspace_bytes(B, cx, 2, L, N, 0), x.device)
+        with torch.cuda.device(x.device):
+            code = L_.gfx_fir_conv_midside_ir_f32(x.data_ptr(), ir_raw.data_ptr(), energy.data_ptr(), y.data_ptr(), B,
+                                                  cx, L, N, int(bool(to_lr)), plan.data_ptr(), ws.data_ptr(),
+                                                  ws.numel(), _cabi.stream_ptr())
+        _cabi.check(code, "gfx_fir_conv_midside_ir_f32")
+    return y
 
 
 DESIGN_FAMILY = {"peq": 0, "peaking": 1, "lowshelf": 2, "highshelf": 3, "lowpass": 4, "highpass": 5, "bandpass": 6,

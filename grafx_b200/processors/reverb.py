@@ -45,22 +45,22 @@ class STFTMaskedNoiseReverb(nn.Module):
         st = self._stft(noise)
         return st.reshape(batch, 2, st.shape[-2], st.shape[-1])
 
-    def compute_ir(self, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude=None, _finish="raw"):
+    def compute_ir(self, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude=None, _finish="unit"):
         """Mid/side impulse response.  NB upstream returns it un-normalised; here the kernel also
-        applies the channel-mode epilogue, selected by `_finish` ("raw" keeps upstream's meaning
-        up to the unit-energy scale)."""
+        applies the channel-mode epilogue, selected by `_finish`: "unit" keeps upstream's meaning up
+        to the unit-energy scale, "lr" adds ms_to_lr, "raw" returns (raw response, row energies)."""
         genv = gain_env_log_magnitude if self.gain_envelope else None
         noise = self._noise(init_log_magnitude.shape[0], init_log_magnitude.device)
         return F_.reverb_ir(noise, init_log_magnitude, delta_log_magnitude, genv, self.window, self.ir_len,
-                            self.n_fft, self.hop_length, to_lr=(_finish == "lr"))
+                            self.n_fft, self.hop_length, finish=_finish)
 
     def forward(self, input_signals, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude=None):
-        to_lr = self.processor_channel == "pseudo_midside"
-        fir = self.compute_ir(init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude,
-                              _finish="lr" if to_lr else "raw")
+        # raw mid/side response + energies; ms_to_lr / normalize_impulse (reverb.py:215-228) happen
+        # inside the convolution while the filter spectra are formed
+        ir_raw, energy = self.compute_ir(init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude, _finish="raw")
         if self.processor_channel == "midside":
-            return F_.ms_to_lr(F_.fir_conv(F_.lr_to_ms(input_signals), fir, "causal"))
-        return F_.fir_conv(input_signals, fir, "causal")
+            return F_.ms_to_lr(F_.fir_conv_midside_ir(F_.lr_to_ms(input_signals), ir_raw, energy, to_lr=False))
+        return F_.fir_conv_midside_ir(input_signals, ir_raw, energy, to_lr=self.processor_channel == "pseudo_midside")
 
     def parameter_size(self):
         size = {"init_log_magnitude": (2, self.num_bins), "delta_log_magnitude": (2, self.num_bins)}

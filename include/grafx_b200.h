@@ -117,12 +117,17 @@ GFX_API int gfx_fir_conv_midside_ir_f32(const float* x, const float* ir_raw, con
  *     elements between batch items, 0 when one fixed noise is shared (the default upstream);
  *   init/delta_log_magnitude [batch, 2, bins]; gain_env_log_magnitude [batch, 2, frames] or NULL;
  *   window [n_fft] (the registered hann buffer); ir [batch, 2, ir_len] (output);
- *   energy_ws [batch, 2] floats of scratch; ms_to_lr != 0 for the pseudo_midside channel mode.
+ *   energy [batch, 2] (output): sum_t of the squared RAW mid/side rows;
+ *   workspace: gfx_reverb_ir_workspace_bytes(batch, ir_len) bytes of scratch;
+ *   mode 0: ir = raw mid/side response (feed it with `energy` to gfx_fir_conv_midside_ir_f32);
+ *   mode 1: ir normalised to unit energy in place; mode 2: ms_to_lr, then normalised (pseudo_midside).
  * bins = n_fft/2+1, frames = 1 + ir_len/hop.  Supported geometry: n_fft = 384, hop = 192. */
+GFX_API size_t gfx_reverb_ir_workspace_bytes(int batch, int ir_len);
 GFX_API int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, const float* init_log_magnitude,
                               const float* delta_log_magnitude, const float* gain_env_log_magnitude,
-                              const float* window, float* ir, float* energy_ws, int batch, int n_fft, int hop,
-                              int ir_len, int ms_to_lr, void* stream);
+                              const float* window, float* ir, float* energy, void* workspace,
+                              size_t workspace_bytes, int batch, int n_fft, int hop, int ir_len, int mode,
+                              void* stream);
 
 /* ---- dry/wet mix -----------------------------------------------------------------------------
  * Replaces the mix in DryWet.forward (processors/container.py:62-67):
