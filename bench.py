@@ -42,27 +42,18 @@ class Workload:
             self.kw = dict(num_filters=5, processor_channel="stereo", backend="lfilter", flashfftconv=False)
             self.cls = "ParametricEqualizer"
             self.param_shapes = {k: (2, 5) for k in ("w0", "q_inv", "log_gain")}
-            self.launches = 1          # biquad_cascade_kernel (the cudaMemsetAsync of 2 KB is not a kernel)
-            self.bytes_per_sample = 8
-            self.dominant = "biquad_cascade_kernel<float,256>"
         elif name == "cfg3":
             self.B, self.C, self.L = 512 // batch_div, 2, 131072
             self.desc = "STFTMaskedNoiseReverb(ir_len=96000) batch=512 x 2ch x 131072"
             self.kw = dict(ir_len=96000, flashfftconv=False)
             self.cls = "STFTMaskedNoiseReverb"
             self.param_shapes = {"init_log_magnitude": (2, 193), "delta_log_magnitude": (2, 193)}
-            self.launches = None
-            self.bytes_per_sample = 8
-            self.dominant = "fir_upols_kernel<16384,1024>"
         elif name == "cfg3b":
             self.B, self.C, self.L = 512 // batch_div, 2, 131072
             self.desc = "FIRFilter(fir_len=1023, stereo) batch=512 x 2ch x 131072"
             self.kw = dict(fir_len=1023, processor_channel="stereo")
             self.cls = "FIRFilter"
             self.param_shapes = {"fir": (2, 1023)}
-            self.launches = 2
-            self.bytes_per_sample = 8
-            self.dominant = "fir_ols_kernel<4096,256>"
         elif name in ("cfg4", "cfg4b"):
             self.B, self.C, self.L = 1024 // batch_div, 1, 65536
             sm = "iir" if name == "cfg4" else "ballistics"
@@ -71,17 +62,11 @@ class Workload:
             self.cls = "chain"
             n = 1 if sm == "iir" else 2
             self.param_shapes = {"log_threshold": (1,), "log_ratio": (1,), "log_knee": (1,), "z_alpha_pre": (n,)}
-            self.launches = 1
-            self.bytes_per_sample = 8
-            self.dominant = "dynamics_kernel"
         elif name == "cfg5":
             self.B, self.C, self.L = 16 // batch_div if batch_div <= 16 else 1, 2, 131072
             self.tracks = 32
             self.desc = "mixing graph 32 x (in->eq->compressor->reverb) -> out, batch=16 per GPU (128 over 8), 2ch x 131072"
             self.cls = "graph"
-            self.launches = None
-            self.bytes_per_sample = None
-            self.dominant = "graph"
         else:
             raise SystemExit(f"unknown workload {name}")
 
@@ -124,6 +109,30 @@ class Workload:
         if self.cls == "chain":
             return self.mod(x, **prm)[0]
         return self.mod(x, **prm)
+
+    def dominant_call(self, x, prm):
+        """(callable, kernel name(s), algorithmic bytes per call) of the O(samples) kernel(s) of the workload,
+        without the parameter-side statement around them.  Algorithmic bytes: SURVEY.md section 8(d)."""
+        import grafx_b200.functional as F_
+        from grafx_b200.processors import design
+
+        n = self.B * self.C * self.L
+        if self.name == "cfg2":
+            Bs, As = design.parametric_eq(prm["w0"], prm["q_inv"], prm["log_gain"])
+            return (lambda: F_.biquad_cascade(x, Bs, As)), "biquad_cascade_x2_kernel<4,0> (+ cascade_tables_kernel)", 8 * n
+        if self.name == "cfg3":
+            return (lambda: self.mod(x, **prm)), \
+                "reverb pipeline: reverb_ir + fir_spectrum<8192> + fir_xspec<8192> + fir_mac<12> + fir_inv<8192>", 8 * n
+        if self.name == "cfg3b":
+            h = F_.normalize_impulse(torch.tanh(prm["fir"]))
+            return (lambda: F_.fir_conv(x, h)), "fir_ols_kernel<4096,256> (+ fir_spectrum_kernel)", 8 * n + 4 * h.numel()
+        if self.name in ("cfg4", "cfg4b"):
+            return (lambda: self.mod(x, **prm)), "dynamics_kernel (Compressor -> NoiseGate fused, one launch)", 8 * n
+        if self.name == "cfg5":
+            # contract-preserving render (signal buffer returned): 129 node signals written, 160 read
+            return (lambda: self.forward(x, prm)), "render_grafx: 5 orders (copy, cascade, dynamics, reverb pipeline, node_sum)", \
+                289 * self.B * self.C * self.L * 4
+        raise SystemExit(self.name)
 
     def samples(self):
         if self.cls == "graph":
@@ -332,49 +341,49 @@ def main():
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        from grafx_b200 import _cabi
+        launches0 = _cabi.lib().gfx_kernel_launch_count()
         ev0.record()
         for _ in range(args.steps):
             y = wl.forward(x, prm)
         ev1.record()
         barrier()
+        launches_timed = int(_cabi.lib().gfx_kernel_launch_count() - launches0)
         ms_total = max_over_ranks(ev0.elapsed_time(ev1), device)
         clocks = sampler.stop() if rank == 0 else None
         ms_step = ms_total / args.steps
         value = samples * world / (ms_step * 1e-3)
 
-        # ---- dominant kernel alone (device time, events on the launching stream)
-        roofline = None
-        if wl.name == "cfg2":
-            import grafx_b200.functional as F_
-            from grafx_b200.processors import design
-
-            Bs, As = design.parametric_eq(prm["w0"], prm["q_inv"], prm["log_gain"])
-            for _ in range(3):
-                F_.biquad_cascade(x, Bs, As)
-            torch.cuda.synchronize()
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            k0.record()
-            for _ in range(args.steps):
-                F_.biquad_cascade(x, Bs, As)
-            k1.record()
-            torch.cuda.synchronize()
-            k_ms = k0.elapsed_time(k1) / args.steps
-            peak, how = 6650.0, "of fallback"
-            try:
-                peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-                how = "of measured"
-            except Exception:
-                pass
-            alg = wl.bytes_per_sample * samples
-            ach = alg / (k_ms * 1e-3) / 1e9
-            traffic = None
-            try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl.name)
-            except Exception:
-                pass
-            roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": traffic, "kernel": wl.dominant, "kernel_ms": k_ms, "algorithmic_bytes": alg,
-                        "peak_source": how}
+        # ---- dominant kernel(s) alone (device time, events on the launching stream = torch's current stream)
+        dom_fn, dom_name, alg = wl.dominant_call(x, prm)
+        L_ = _cabi.lib()
+        for _ in range(3):
+            dom_fn()
+        torch.cuda.synchronize()
+        n0 = L_.gfx_kernel_launch_count()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(args.steps):
+            dom_fn()
+        k1.record()
+        torch.cuda.synchronize()
+        k_ms = k0.elapsed_time(k1) / args.steps
+        dom_launches = (L_.gfx_kernel_launch_count() - n0) / args.steps
+        peak, how = 6650.0, "of fallback"
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            how = "of measured"
+        except Exception:
+            pass
+        ach = alg / (k_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl.name)
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "kernel": dom_name, "kernel_ms": k_ms, "launches_per_step": dom_launches,
+                    "algorithmic_bytes": alg, "peak_source": how}
 
         # ---- end to end through the public nn.Module API with HOST buffers (pinned), copies inside
         e2e = None
@@ -436,7 +445,6 @@ def main():
                         "sample": f"{cwl.name}: batch {cwl.B} x {cwl.C}ch x {cwl.L} (1/4 of the workload), best of {reps} at the best thread count ({threads} of {cores} host cores), oracle port = torch CPU ops + torchaudio lfilter as the reference calls them"}
 
     if rank == 0:
-        launches = wl.launches
         line = {"metric": "audio samples/sec (batch x chan x len)", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -444,7 +452,7 @@ def main():
                            "l2": f"inputs larger than L2 ({tree_bytes(x) / 2**20:.0f} MiB read + as much written per step vs 126 MiB L2)",
                            "parallelism": f"batch shard x{world}, no collective on the data path"},
                 "clocks": clocks, "e2e": e2e,
-                "gpu_launches": (launches * args.steps * world) if launches else None,
+                "gpu_launches": launches_timed * world,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:

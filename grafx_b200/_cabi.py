@@ -40,6 +40,7 @@ SIGNATURES = {
     "gfx_version": (c_int, []),
     "gfx_last_cuda_error": (c_int, []),
     "gfx_error_string": (ctypes.c_char_p, [c_int]),
+    "gfx_kernel_launch_count": (ctypes.c_ulonglong, []),
     "gfx_device_sm_count": (c_int, []),
     "gfx_biquad_cascade_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "gfx_biquad_cascade_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -3,6 +3,7 @@
 #include "../../include/grafx_b200.h"
 
 int g_gfx_last_cuda_error = 0;
+unsigned long long g_gfx_launch_count = 0;
 
 namespace gfx {
 const DeviceInfo& device_info() {
@@ -31,6 +32,8 @@ extern "C" {
 int gfx_version(void) { return 0 * 10000 + 1 * 100 + 0; }
 
 int gfx_last_cuda_error(void) { return g_gfx_last_cuda_error; }
+
+unsigned long long gfx_kernel_launch_count(void) { return g_gfx_launch_count; }
 
 const char* gfx_error_string(int code) {
     switch (code) {

@@ -675,7 +675,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     GFX_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256 + flags_bytes + state_bytes, stream));
     const int n_sections = coef_rows * K;
     cascade_tables_kernel<T><<<(n_sections * 32 + 127) / 128, 128, 0, stream>>>(Bs, As, tables, n_sections);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    GFX_LAUNCH_CHECK();
 
     if constexpr (sizeof(T) == 4) {
         const size_t smem2 = cascade_x2_smem_bytes(K);
@@ -694,7 +694,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
             long long grid2 = (long long)device_info().sm_count * occ2;
             if (grid2 > (long long)p.n_items) grid2 = p.n_items;
             kern2<<<(unsigned)grid2, 32 * X2_WARPS, smem2, stream>>>(p);
-            GFX_CUDA_CHECK(cudaGetLastError());
+            GFX_LAUNCH_CHECK();
             return GFX_OK;
         }
     }
@@ -713,7 +713,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     long long grid = (long long)device_info().sm_count * occ;
     if (grid > (long long)p.n_items) grid = p.n_items;
     kern<<<(unsigned)grid, NT, smem, stream>>>(p);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    GFX_LAUNCH_CHECK();
     return GFX_OK;
 }
 

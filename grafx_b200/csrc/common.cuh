@@ -17,6 +17,14 @@ extern int g_gfx_last_cuda_error;
         }                                                      \
     } while (0)
 
+// after every kernel launch of the library: count it (gfx_kernel_launch_count) and pick up launch errors
+extern unsigned long long g_gfx_launch_count;
+#define GFX_LAUNCH_CHECK()                    \
+    do {                                      \
+        ++g_gfx_launch_count;                 \
+        GFX_CUDA_CHECK(cudaGetLastError());   \
+    } while (0)
+
 namespace gfx {
 
 // ---------------------------------------------------------------- device info (cached)
@@ -40,6 +48,10 @@ template <int BYTES>
 __device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gmem_src) {
     static_assert(BYTES == 4 || BYTES == 8, "cp.async.ca supports 4, 8, 16 bytes");
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES));
+}
+// 8-byte async copy with zero fill of the bytes past src_bytes (0..8)
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>

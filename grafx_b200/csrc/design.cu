@@ -114,6 +114,6 @@ extern "C" int gfx_biquad_design_f32(int family, const float* p0, const float* p
     const long long total = (long long)n_rows * K;
     biquad_design_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(family, p0, p1, p2, p3, p4,
                                                                                             Bs, As, n_rows, K, flags);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    GFX_LAUNCH_CHECK();
     return GFX_OK;
 }

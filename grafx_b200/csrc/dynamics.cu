@@ -473,7 +473,7 @@ static int launch_dynamics(DynParams& p, cudaStream_t stream) {
     long long grid = (long long)device_info().sm_count * occ;
     if (grid > (long long)p.n_items) grid = p.n_items;
     kern<<<(unsigned)grid, NT, smem, stream>>>(p);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    GFX_LAUNCH_CHECK();
     return GFX_OK;
 }
 

@@ -43,7 +43,7 @@ extern "C" int gfx_midside_f32(const float* x, float* y, int batch, long long L,
     const long long cap = (long long)gfx::device_info().sm_count * 8;
     if (blocks > cap) blocks = cap;
     gfx::midside_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, L, total, mult, vec);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    GFX_LAUNCH_CHECK();
     return GFX_OK;
 }
 
@@ -116,7 +116,7 @@ extern "C" int gfx_drywet_f32(const float* dry, const float* wet, const float* w
     const long long cap = (long long)gfx::device_info().sm_count * 8;
     if (blocks > cap) blocks = cap;
     gfx::drywet_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dry, wet, weight, y, inner, total, vec);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    GFX_LAUNCH_CHECK();
     return GFX_OK;
 }
 
@@ -133,6 +133,6 @@ extern "C" int gfx_node_sum_f32(const float* src, float* dst, const int* index, 
     gfx::node_sum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         src, dst, index, batch, n_src, n_dst, inner, src_batch_stride, src_node_stride, dst_batch_stride,
         dst_node_stride, vec);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    GFX_LAUNCH_CHECK();
     return GFX_OK;
 }

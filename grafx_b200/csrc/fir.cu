@@ -111,7 +111,7 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan
     // slot of element q of a butterfly: pidx(i0 + q ST) = pidx(i0) + q * PST  (ST is a multiple of 16, or 1)
     constexpr int PST = ST >= 16 ? ST + ST / 16 : 1;
     static_assert(ST == 1 || ST % 16 == 0, "stride must keep the padding pattern linear");
-#pragma unroll 1
+#pragma unroll (R == 2 ? 4 : 1)
     for (int b = threadIdx.x; b < N / R; b += NT) {
         const int j = b & (ST - 1);
         const int i0 = (b - j) * R + j;
@@ -210,39 +210,77 @@ __device__ __forceinline__ float2 ld_c(const pk2* z, int i) {
 }
 __device__ __forceinline__ void st_c(pk2* z, int i, float re, float im) { z[pidx(i)] = pk_make(re, im); }
 
+// plan memory: [ pair half-twiddles: n/2 float2 | pass tables: plan_total(n) float2 | partner positions: n/2 u16 ]
+//   partner[q] = position of bin n - k(q): the slot the real-FFT algebra couples with pair_pos(q)
+template <int N>
+__device__ __forceinline__ const unsigned short* plan_partner(const float2* plan) {
+    return reinterpret_cast<const unsigned short*>(plan + N / 2 + plan_total(N));
+}
+
+// The three pair loops below run in batches of PB slots: all global / table loads of a batch are issued
+// before the first use (the loops are latency-, not throughput-limited otherwise).
+constexpr int PB = 4;
+
 // smem FFT output -> pair slots in global memory (scaled)
 template <int N, int NT>
 __device__ __forceinline__ void untangle_store(const pk2* z, const float2* __restrict__ plan, float4* __restrict__ out,
                                                float scale) {
-    for (int q = threadIdx.x; q < N / 2; q += NT) {
-        float4 o;
-        if (q == 0) {
-            const float2 z0 = ld_c(z, 0), zh = ld_c(z, 8);
-            o = make_float4((z0.x + z0.y) * scale, (z0.x - z0.y) * scale, zh.x * scale, -zh.y * scale);
-        } else {
-            const int p = pair_pos(q);
-            const int pm = pos_of_bin<N>(N - bin_of_pos<N>(p));
-            const PairA a = untangle_pair(ld_c(z, p), ld_c(z, pm), __ldg(plan + q));
-            o = make_float4(a.k.x * scale, a.k.y * scale, a.m.x * scale, a.m.y * scale);
+    const unsigned short* partner = plan_partner<N>(plan);
+    static_assert((N / 2) % (NT * PB) == 0, "pair loop batches");
+#pragma unroll 1
+    for (int q0 = threadIdx.x; q0 < N / 2; q0 += NT * PB) {
+        float2 w[PB];
+        int pm[PB];
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            w[u] = __ldg(plan + q0 + u * NT);
+            pm[u] = __ldg(partner + q0 + u * NT);
         }
-        out[q] = o;
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            const int q = q0 + u * NT;
+            float4 o;
+            if (q == 0) {
+                const float2 z0 = ld_c(z, 0), zh = ld_c(z, 8);
+                o = make_float4((z0.x + z0.y) * scale, (z0.x - z0.y) * scale, zh.x * scale, -zh.y * scale);
+            } else {
+                const PairA a = untangle_pair(ld_c(z, pair_pos(q)), ld_c(z, pm[u]), w[u]);
+                o = make_float4(a.k.x * scale, a.k.y * scale, a.m.x * scale, a.m.y * scale);
+            }
+            out[q] = o;
+        }
     }
 }
 
 // pair slots in global memory -> packed spectrum in smem, ready for the inverse FFT
 template <int N, int NT>
 __device__ __forceinline__ void retangle_load(pk2* z, const float2* __restrict__ plan, const float4* __restrict__ Y) {
-    for (int q = threadIdx.x; q < N / 2; q += NT) {
-        const float4 y = ldg_stream(Y + q);
-        if (q == 0) {
-            st_c(z, 0, 0.5f * (y.x + y.y), 0.5f * (y.x - y.y));
-            st_c(z, 8, y.z, -y.w);
-        } else {
-            const int p = pair_pos(q);
-            const int pm = pos_of_bin<N>(N - bin_of_pos<N>(p));
-            const PairA a = retangle_pair(make_float2(y.x, y.y), make_float2(y.z, y.w), __ldg(plan + q));
-            st_c(z, p, a.k.x, a.k.y);
-            st_c(z, pm, a.m.x, a.m.y);
+    const unsigned short* partner = plan_partner<N>(plan);
+    constexpr int YB = 8;
+    static_assert((N / 2) % (NT * YB) == 0, "pair loop batches");
+#pragma unroll 1
+    for (int q0 = threadIdx.x; q0 < N / 2; q0 += NT * YB) {
+        float4 y[YB];
+        float2 w[YB];
+        int pm[YB];
+#pragma unroll
+        for (int u = 0; u < YB; ++u) y[u] = ldg_stream(Y + q0 + u * NT);
+#pragma unroll
+        for (int u = 0; u < YB; ++u) {
+            w[u] = __ldg(plan + q0 + u * NT);
+            pm[u] = __ldg(partner + q0 + u * NT);
+        }
+#pragma unroll
+        for (int u = 0; u < YB; ++u) {
+            const int q = q0 + u * NT;
+            if (q == 0) {
+                st_c(z, 0, 0.5f * (y[u].x + y[u].y), 0.5f * (y[u].x - y[u].y));
+                st_c(z, 8, y[u].z, -y[u].w);
+            } else {
+                const PairA a = retangle_pair(make_float2(y[u].x, y[u].y), make_float2(y[u].z, y[u].w), w[u]);
+                st_c(z, pair_pos(q), a.k.x, a.k.y);
+                st_c(z, pm[u], a.m.x, a.m.y);
+            }
         }
     }
 }
@@ -250,23 +288,36 @@ __device__ __forceinline__ void retangle_load(pk2* z, const float2* __restrict__
 // fused in place: untangle X, multiply by the (already 1/N-scaled) filter spectrum H (pair slots), retangle
 template <int N, int NT>
 __device__ __forceinline__ void pointwise_filter(pk2* z, const float2* __restrict__ plan, const float4* __restrict__ H) {
-    for (int q = threadIdx.x; q < N / 2; q += NT) {
-        const float4 h = __ldg(H + q);
-        if (q == 0) {
-            const float2 z0 = ld_c(z, 0), zh = ld_c(z, 8);
-            const float y0 = (z0.x + z0.y) * h.x, yn = (z0.x - z0.y) * h.y;
-            st_c(z, 0, 0.5f * (y0 + yn), 0.5f * (y0 - yn));
-            // X_{N/2} = conj(Z), Y = X H, Z' = conj(Y) = Z conj(H)
-            const float2 r2 = cmulc(zh, make_float2(h.z, h.w));
-            st_c(z, 8, r2.x, r2.y);
-        } else {
-            const int p = pair_pos(q);
-            const int pm = pos_of_bin<N>(N - bin_of_pos<N>(p));
-            const float2 w = __ldg(plan + q);
-            const PairA x = untangle_pair(ld_c(z, p), ld_c(z, pm), w);
-            const PairA y = retangle_pair(cmul(x.k, make_float2(h.x, h.y)), cmul(x.m, make_float2(h.z, h.w)), w);
-            st_c(z, p, y.k.x, y.k.y);
-            st_c(z, pm, y.m.x, y.m.y);
+    const unsigned short* partner = plan_partner<N>(plan);
+#pragma unroll 1
+    for (int q0 = threadIdx.x; q0 < N / 2; q0 += NT * PB) {
+        float4 h[PB];
+        float2 w[PB];
+        int pm[PB];
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            h[u] = __ldg(H + q0 + u * NT);
+            w[u] = __ldg(plan + q0 + u * NT);
+            pm[u] = __ldg(partner + q0 + u * NT);
+        }
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            const int q = q0 + u * NT;
+            if (q == 0) {
+                const float2 z0 = ld_c(z, 0), zh = ld_c(z, 8);
+                const float y0 = (z0.x + z0.y) * h[u].x, yn = (z0.x - z0.y) * h[u].y;
+                st_c(z, 0, 0.5f * (y0 + yn), 0.5f * (y0 - yn));
+                // X_{N/2} = conj(Z), Y = X H, Z' = conj(Y) = Z conj(H)
+                const float2 r2 = cmulc(zh, make_float2(h[u].z, h[u].w));
+                st_c(z, 8, r2.x, r2.y);
+            } else {
+                const int p = pair_pos(q);
+                const PairA x = untangle_pair(ld_c(z, p), ld_c(z, pm[u]), w[u]);
+                const PairA y = retangle_pair(cmul(x.k, make_float2(h[u].x, h[u].y)),
+                                              cmul(x.m, make_float2(h[u].z, h[u].w)), w[u]);
+                st_c(z, p, y.k.x, y.k.y);
+                st_c(z, pm[u], y.m.x, y.m.y);
+            }
         }
     }
 }
@@ -277,7 +328,36 @@ __device__ __forceinline__ void pointwise_filter(pk2* z, const float2* __restric
 template <int N, int NT>
 __device__ __forceinline__ void load_packed(pk2* z, const float* __restrict__ src, const float* __restrict__ src2,
                                             float sgn2, long long s0, long long len, bool vec_ok) {
-    if (vec_ok && (s0 & 3) == 0) {
+    if (vec_ok && (s0 & 3) == 0 && src2 == nullptr && s0 >= 0 && s0 + 2 * N <= len) {
+        // interior segment: asynchronous copies straight into the packed layout, the whole segment in flight
+        // at once (two 8-byte halves per 16 bytes: the padded slots are only 8-byte aligned); the slot of
+        // t = tid + i NT is linear in i (NT is a multiple of 8), so the unrolled loop has no index math
+        // one complex point (8 bytes) per copy, consecutive lanes -> consecutive points: a warp's copy is
+        // contiguous in global memory and (up to one pad slot) in shared memory: no bank conflicts
+        static_assert(NT % 16 == 0 && N % NT == 0, "load tiling");
+        const float* g = src + s0 + 2 * (int)threadIdx.x;
+        const uint32_t d = smem_u32(z) + 8u * (uint32_t)pidx((int)threadIdx.x);
+#pragma unroll
+        for (int i = 0; i < N / NT; ++i)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d + 8u * (uint32_t)(i * (NT + NT / 16))),
+                         "l"(g + i * 2 * NT));
+        cp_async_commit();
+        cp_async_wait<0>();
+    } else if (vec_ok && (s0 & 3) == 0 && src2 == nullptr) {
+        // segment crossing the start / end of the row: same copies with zero fill
+#pragma unroll 4
+        for (int t = threadIdx.x; t < N / 2; t += NT) {
+            const long long pos = s0 + 4LL * t;
+            const long long rem = (pos >= 0) ? (len - pos) : 0;  // samples available from pos on (a 4-group never straddles 0)
+            const int b0 = rem >= 2 ? 8 : (rem > 0 ? (int)rem * 4 : 0);
+            const int b1 = rem >= 4 ? 8 : (rem > 2 ? (int)(rem - 2) * 4 : 0);
+            const float* g = (rem > 0) ? src + pos : src;
+            cp_async8(&z[pidx(2 * t)], g, b0);
+            cp_async8(&z[pidx(2 * t + 1)], b1 > 0 ? g + 2 : src, b1);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+    } else if (vec_ok && (s0 & 3) == 0) {
 #pragma unroll 4
         for (int t = threadIdx.x; t < N / 2; t += NT) {
             const long long pos = s0 + 4LL * t;
@@ -316,7 +396,19 @@ __device__ __forceinline__ void load_packed(pk2* z, const float* __restrict__ sr
 template <int N, int NT>
 __device__ __forceinline__ void store_packed(const pk2* z, float* __restrict__ dst, int i_lo, int count, long long d0,
                                              long long len, bool vec_ok) {
-    if (vec_ok && (i_lo & 3) == 0 && (d0 & 3) == 0 && (count & 3) == 0) {
+    if (vec_ok && (i_lo & 3) == 0 && (d0 & 3) == 0 && (count & 3) == 0 && d0 >= 0 && d0 + count <= len) {
+        // interior block: no clipping, 32-bit index math
+        float* o = dst + d0;
+        const int h_lo = i_lo >> 1;
+#pragma unroll 4
+        for (int t = threadIdx.x; t < count / 4; t += NT) {
+            const int c = h_lo + 2 * t;  // complex index of the first of the two packed points
+            float a0, a1, b0, b1;
+            pk_split(z[pidx(c)], a0, a1);
+            pk_split(z[pidx(c + 1)], b0, b1);
+            stg_stream(reinterpret_cast<float4*>(o + 4 * t), make_float4(a0, a1, b0, b1));
+        }
+    } else if (vec_ok && (i_lo & 3) == 0 && (d0 & 3) == 0 && (count & 3) == 0) {
 #pragma unroll 4
         for (int t = threadIdx.x; t < count / 4; t += NT) {
             const int i = i_lo + 4 * t;
@@ -351,12 +443,12 @@ struct RowMap {  // output row -> (x row, h row) with channel broadcasting
     }
 };
 
-// how filter rows are read: plain, or a raw mid/side reverb IR turned into unit-energy left/right on the fly
-// (reference: ms_to_lr + normalize_impulse, reverb.py:215-228, core/utils.py:14-18)
+// filter rows, optionally with the unit-energy normalisation of a reverb IR folded into the spectra
+// (reference: normalize_impulse after the optional ms_to_lr, reverb.py:215-228, core/utils.py:14-18)
 struct FilterSrc {
     const float* h;       // [hrows, Nh]
-    const float* energy;  // [batch, 2] sum_t h^2 of the raw rows, or null (plain)
-    int to_lr;            // with energy: rows are (mid, side) -> (mid + side, mid - side)
+    const float* energy;  // [batch, 2] sum_t of the squared raw mid / side rows, or null (plain filter)
+    int to_lr;            // with energy: rows are left/right = mid +- side (mean-over-channels energy = e0 + e1)
 };
 
 constexpr int fir_min_blocks(int n) { return n <= 4096 ? 3 : (n <= 8192 ? 3 : 1); }
@@ -374,25 +466,13 @@ __global__ void __launch_bounds__(NT, fir_min_blocks(N)) fir_spectrum_kernel(Fil
     long long len = (long long)Nh - (long long)part * part_len;
     if (len > part_len) len = part_len;
     float scale = 1.f / (float)N;
-    const float* src2 = nullptr;
-    size_t off2 = 0;
     if (fs.energy) {
+        // normalize_impulse of a reverb IR: one scale per batch item from the raw mid/side energies
         const float e0 = fs.energy[hrow & ~1], e1 = fs.energy[hrow | 1];
-        if (fs.to_lr) {
-            scale *= rsqrtf(e0 + e1 + 1e-12f);  // mean_c sum_t (m +- s)^2 = sum m^2 + sum s^2
-            off2 = (size_t)(hrow ^ 1) * Nh + (size_t)part * part_len;
-            src2 = fs.h + off2;
-        } else {
-            scale *= rsqrtf(0.5f * (e0 + e1) + 1e-12f);
-        }
+        scale *= fs.to_lr ? rsqrtf(e0 + e1 + 1e-12f) : rsqrtf(0.5f * (e0 + e1) + 1e-12f);
     }
-    const bool v = vec_ok && ((off & 3) == 0) && ((off2 & 3) == 0);
-    if (src2 && (hrow & 1)) {
-        // this row is the side channel: right = mid - side
-        load_packed<N, NT>(zbuf, src2, fs.h + off, -1.f, 0, len, v);
-    } else {
-        load_packed<N, NT>(zbuf, fs.h + off, src2, 1.f, 0, len, v);
-    }
+    const bool v = vec_ok && ((off & 3) == 0);
+    load_packed<N, NT>(zbuf, fs.h + off, nullptr, 0.f, 0, len, v);
     __syncthreads();
     fft_forward<N, NT>(zbuf, plan);
     untangle_store<N, NT>(zbuf, plan, Hs + (size_t)blockIdx.x * (N / 2), scale);
@@ -467,7 +547,7 @@ __global__ void __launch_bounds__(MAC_NT, 2) fir_mac_kernel(const float4* __rest
 #pragma unroll
         for (int p = 0; p < PC; ++p) { h[p].x = 0.f; h[p].y = 0.f; }
     }
-    constexpr int G = PC < 4 ? PC : 4;  // loads issued together
+    constexpr int G = PC < 4 ? PC : (PC >= 10 ? 2 : 4);  // loads issued together
     const int last = nblk - 1 - p0;     // last valid input block index for this partition group
 #pragma unroll 1
     for (int j0 = p0; j0 < nblk; j0 += PC) {
@@ -541,6 +621,11 @@ __global__ void fft_plan_pairs_kernel(float2* ht) {
         ht[q] = make_float2((float)cospi(a), (float)(-sinpi(a)));
     }
 }
+template <int N>
+__global__ void fft_plan_partner_kernel(unsigned short* partner) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < N / 2) partner[q] = q == 0 ? 8 : (unsigned short)pos_of_bin<N>(N - bin_of_pos<N>(pair_pos(q)));
+}
 __global__ void fft_plan_pass_kernel(float2* tab, int M, int R) {
     const int ST = M / R;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -589,7 +674,7 @@ static int run_ols(const FirArgs& a) {
     }
     const int hvec = ((uintptr_t)a.fs.h % 16 == 0);
     fir_spectrum_kernel<N, NT><<<hrows, NT, smem, a.stream>>>(a.fs, Hs, 0, a.Nh, a.Nh, 1, a.plan, hvec);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    GFX_LAUNCH_CHECK();
     const int pre = (a.Nh - 1 + 3) & ~3;
     const int hop = (2 * N - pre) & ~3;
     const long long total = a.L + a.shift;
@@ -599,7 +684,7 @@ static int run_ols(const FirArgs& a) {
     RowMap rm{c_out, a.cx, a.ch};
     fir_ols_kernel<N, NT><<<(unsigned)(nblk * rows), NT, smem, a.stream>>>(a.x, a.y, Hs, rm, a.L, pre, hop, a.shift,
                                                                            (int)nblk, a.plan, vec);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    GFX_LAUNCH_CHECK();
     return GFX_OK;
 }
 
@@ -645,10 +730,10 @@ static int run_upols(const FirArgs& a) {
         if ((long long)nb * a.cx * nblk > 0x7fffffffLL || (long long)nb * c_out * nblk > 0x7fffffffLL ||
             (long long)nb * c_out > 65535) return GFX_ERR_UNSUPPORTED;
         fir_spectrum_kernel<N, NT><<<nb * a.ch * P, NT, smem, a.stream>>>(a.fs, Hs, hrow0, a.Nh, N, P, a.plan, hvec);
-        GFX_CUDA_CHECK(cudaGetLastError());
+        GFX_LAUNCH_CHECK();
         fir_xspec_kernel<N, NT><<<(unsigned)(nb * a.cx * nblk), NT, smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk,
                                                                                       a.plan, vec);
-        GFX_CUDA_CHECK(cudaGetLastError());
+        GFX_LAUNCH_CHECK();
         const dim3 grid(half / MAC_NT, nb * c_out);
         for (int p0 = 0; p0 < P; p0 += MAC_MAX_PC) {
             const int pc = P - p0 < MAC_MAX_PC ? P - p0 : MAC_MAX_PC;
@@ -659,11 +744,11 @@ static int run_upols(const FirArgs& a) {
                 GFX_MAC_CASE(7) GFX_MAC_CASE(8) GFX_MAC_CASE(9) GFX_MAC_CASE(10) GFX_MAC_CASE(11) GFX_MAC_CASE(12)
             }
 #undef GFX_MAC_CASE
-            GFX_CUDA_CHECK(cudaGetLastError());
+            GFX_LAUNCH_CHECK();
         }
         fir_inv_kernel<N, NT><<<(unsigned)(nb * c_out * nblk), NT, smem, a.stream>>>(Ys, a.y, row0, a.L, (int)nblk,
                                                                                      a.shift, a.plan, vec);
-        GFX_CUDA_CHECK(cudaGetLastError());
+        GFX_LAUNCH_CHECK();
     }
     return GFX_OK;
 }
@@ -701,7 +786,7 @@ int gfx_fir_fft_size(int filter_len) { return filter_len <= 0 ? GFX_ERR_INVALID 
 
 size_t gfx_fft_plan_bytes(int n) {
     if (!gfx::plan_ok(n)) return 0;
-    return ((size_t)n / 2 + (size_t)gfx::plan_total(n)) * sizeof(float2);
+    return ((size_t)n / 2 + (size_t)gfx::plan_total(n)) * sizeof(float2) + ((size_t)n / 2) * sizeof(unsigned short);
 }
 
 int gfx_fft_plan_init(void* plan, int n, void* stream) {
@@ -714,13 +799,19 @@ int gfx_fft_plan_init(void* plan, int n, void* stream) {
     else if (n == 4096) fft_plan_pairs_kernel<4096><<<gb, 256, 0, st>>>(base);
     else if (n == 8192) fft_plan_pairs_kernel<8192><<<gb, 256, 0, st>>>(base);
     else fft_plan_pairs_kernel<16384><<<gb, 256, 0, st>>>(base);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    GFX_LAUNCH_CHECK();
+    unsigned short* partner = (unsigned short*)(base + n / 2 + plan_total(n));
+    if (n == 1024) fft_plan_partner_kernel<1024><<<gb, 256, 0, st>>>(partner);
+    else if (n == 4096) fft_plan_partner_kernel<4096><<<gb, 256, 0, st>>>(partner);
+    else if (n == 8192) fft_plan_partner_kernel<8192><<<gb, 256, 0, st>>>(partner);
+    else fft_plan_partner_kernel<16384><<<gb, 256, 0, st>>>(partner);
+    GFX_LAUNCH_CHECK();
     for (int s = 0; s < plan_stages(n); ++s) {
         const int entries = plan_entries(n, s);
         if (entries == 0) continue;
         fft_plan_pass_kernel<<<(entries + 255) / 256, 256, 0, st>>>(base + n / 2 + plan_offset(n, s), plan_m(n, s),
                                                                    plan_radix(n, s));
-        GFX_CUDA_CHECK(cudaGetLastError());
+        GFX_LAUNCH_CHECK();
     }
     return GFX_OK;
 }

@@ -37,7 +37,7 @@ struct ReverbParams {
     const float* window;      // [384]
     float* ir;                // [B][2][ir_len]  (mid/side, un-normalised)
     float* partial;           // [B*2][tiles]  sum of ir^2 per CTA
-    int frames, ir_len, tiles;
+    int frames, ir_len, tiles, vec_ok, to_lr;
 };
 
 // inverse DFT-3 (unnormalised): y_r = sum_m a_m e^{+2 pi i m r / 3}
@@ -66,35 +66,47 @@ __device__ __forceinline__ void idft12(pk2 (&a)[12]) {
     for (int r2 = 0; r2 < 4; ++r2) idft3(a[3 * r2], a[3 * r2 + 1], a[3 * r2 + 2]);
 }
 
-__global__ void __launch_bounds__(RV_NT, 3) reverb_ir_kernel(const ReverbParams p) {
-    extern __shared__ __align__(16) unsigned char rv_smem[];
-    pk2* zb = reinterpret_cast<pk2*>(rv_smem);                        // [16][RV_ZS]
-    float* fr = reinterpret_cast<float*>(zb + RV_FT * RV_ZS);         // [16][384] windowed frames
-    float2* w192 = reinterpret_cast<float2*>(fr + RV_FT * RV_NFFT);   // [192] e^{+2 pi i j / 192}
-    float2* hw = w192 + RV_N;                                         // [96]  e^{-i pi k / 192}
-    float* win = reinterpret_cast<float*>(hw + RV_N / 2);             // [384]
-    float* a0 = win + RV_NFFT;                                        // [196] H0
-    float* a1 = a0 + RV_BINS + 3;                                     // [196] softplus(Hd)
-    float* xn = a1 + RV_BINS + 3;                                     // [16]  Nyquist bin (real) per frame
-    float* red = xn + RV_FT;                                          // [8]
+// smem carve-up (per CTA = one batch item, both mid and side rows, 16 frames each)
+constexpr int RV_ZB_BYTES = 2 * RV_FT * RV_ZS * 8;          // pk2 zb[2][16][RV_ZS]
+constexpr int RV_FR_BYTES = 2 * RV_FT * RV_NFFT * 4;        // float fr[2][16][384]
+constexpr int RV_TW_BYTES = (RV_N + RV_N / 2) * 8;          // float2 w192[192], hw[96]
+constexpr int RV_FL_FLOATS = RV_NFFT + 4 * (RV_BINS + 3) + 2 * RV_FT + 2 * 16 + 8;
+constexpr int RV_SMEM_BYTES = RV_ZB_BYTES + RV_FR_BYTES + RV_TW_BYTES + RV_FL_FLOATS * 4;
 
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.x % p.tiles, row = blockIdx.x / p.tiles;  // row = b * 2 + ch
-    const int b = row >> 1, ch = row & 1;
+__global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbParams p) {
+    extern __shared__ __align__(16) unsigned char rv_smem[];
+    pk2* zb_all = reinterpret_cast<pk2*>(rv_smem);                                    // [2][16][RV_ZS]
+    float* fr_all = reinterpret_cast<float*>(rv_smem + RV_ZB_BYTES);                  // [2][16][384] windowed frames
+    float2* w192 = reinterpret_cast<float2*>(rv_smem + RV_ZB_BYTES + RV_FR_BYTES);    // [192] e^{+2 pi i j / 192}
+    float2* hw = w192 + RV_N;                                                         // [96]  e^{-i pi k / 192}
+    float* win = reinterpret_cast<float*>(hw + RV_N / 2);                             // [384]
+    float* a0_all = win + RV_NFFT;                                                    // [2][196] H0
+    float* a1_all = a0_all + 2 * (RV_BINS + 3);                                       // [2][196] softplus(Hd)
+    float* xn_all = a1_all + 2 * (RV_BINS + 3);                                       // [2][16] Nyquist bin per frame
+    float* red = xn_all + 2 * RV_FT;                                                  // [2][16]
+
+    const int ch = threadIdx.x >> 8, tid = threadIdx.x & (RV_NT - 1);  // channel (mid | side), thread within it
+    const int tile = blockIdx.x % p.tiles, b = blockIdx.x / p.tiles;
+    const int row = 2 * b + ch;
+    pk2* zb = zb_all + ch * (RV_FT * RV_ZS);
+    float* fr = fr_all + ch * (RV_FT * RV_NFFT);
+    float* a0 = a0_all + ch * (RV_BINS + 3);
+    float* a1 = a1_all + ch * (RV_BINS + 3);
+    float* xn = xn_all + ch * RV_FT;
     const float2* noise = p.noise + (size_t)b * p.noise_bstride + (size_t)ch * RV_BINS * p.frames;
     const float* genv = p.genv ? p.genv + (size_t)row * p.frames : nullptr;
     const int m0 = tile * RV_HT;  // first frame of the CTA; hops m0+1 .. m0+15
 
-    for (int t = tid; t < RV_NFFT; t += RV_NT) {
+    for (int t = threadIdx.x; t < RV_NFFT; t += 2 * RV_NT) {
         win[t] = p.window[t];
         if (t < RV_N) {
-            float s, c;
-            sincospif((float)t * (2.f / (float)RV_N), &s, &c);
-            w192[t] = make_float2(c, s);
+            float sn, c;
+            sincospif((float)t * (2.f / (float)RV_N), &sn, &c);
+            w192[t] = make_float2(c, sn);
         } else if (t < RV_N + RV_N / 2) {
-            float s, c;
-            sincospif((float)(t - RV_N) * (1.f / (float)RV_N), &s, &c);
-            hw[t - RV_N] = make_float2(c, -s);
+            float sn, c;
+            sincospif((float)(t - RV_N) * (1.f / (float)RV_N), &sn, &c);
+            hw[t - RV_N] = make_float2(c, -sn);
         }
     }
     for (int k = tid; k < RV_BINS; k += RV_NT) {
@@ -104,20 +116,28 @@ __global__ void __launch_bounds__(RV_NT, 3) reverb_ir_kernel(const ReverbParams 
     }
     __syncthreads();
 
-    // 1. masked spectra of the CTA's frames (coalesced over the frame axis); bins 0 and 192 are real
-    for (int i = tid; i < RV_BINS * RV_FT; i += RV_NT) {
-        const int k = i >> 4, f = i & (RV_FT - 1);
+    // 1. masked spectra of the CTA's frames: lane = frame (coalesced over the frame axis), 16 bin lanes;
+    //    bins 0 and 192 are real.  mask = exp((H0 - softplus(Hd) m [+ G[m]]) / 8)  (reverb.py:189-200)
+    {
+        const int f = tid & (RV_FT - 1), kq = tid >> 4;
         const int m = m0 + f;
-        float2 v = make_float2(0.f, 0.f);
-        if (m < p.frames) {
-            const float2 nz = __ldg(noise + (size_t)k * p.frames + m);
-            float lg = a0[k] - a1[k] * (float)m;
-            if (genv) lg += genv[m];
-            const float mk = __expf(lg * 0.125f);
-            v = make_float2(nz.x * mk, nz.y * mk);
+        const bool fv = m < p.frames;
+        const float fm = (float)m;
+        const float ge = (genv && fv) ? genv[m] : 0.f;
+        const float2* np = noise + (fv ? m : 0);
+        pk2* zf = zb + f * RV_ZS;
+#pragma unroll 4
+        for (int k = kq; k < RV_BINS - 1; k += 16) {
+            const float2 nz = __ldg(np + (size_t)k * p.frames);
+            const float mk = fv ? __expf(((a0[k] - a1[k] * fm) + ge) * 0.125f) : 0.f;
+            zf[k] = pk_make(nz.x * mk, nz.y * mk);
         }
-        if (k == RV_BINS - 1) xn[f] = v.x;
-        else zb[f * RV_ZS + k] = pk_make(v.x, v.y);
+        if (kq == 0) {
+            const int k = RV_BINS - 1;
+            const float2 nz = __ldg(np + (size_t)k * p.frames);
+            const float mk = fv ? __expf(((a0[k] - a1[k] * fm) + ge) * 0.125f) : 0.f;
+            xn[f] = nz.x * mk;
+        }
     }
     __syncthreads();
 
@@ -174,8 +194,8 @@ __global__ void __launch_bounds__(RV_NT, 3) reverb_ir_kernel(const ReverbParams 
         for (int i = 0; i < 4; ++i) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int s = 4 * j + i;
-                const int n = tau + 12 * s;
+                const int sidx = 4 * j + i;
+                const int n = tau + 12 * sidx;
                 float re, im;
                 pk_split(bq[4 * i + j], re, im);
                 const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * n);
@@ -186,32 +206,68 @@ __global__ void __launch_bounds__(RV_NT, 3) reverb_ir_kernel(const ReverbParams 
     }
     __syncthreads();
 
-    // 5. overlap-add, envelope division, trim
-    float esum = 0.f;
-    float* irow = p.ir + (size_t)row * p.ir_len;
-    for (int i = tid; i < RV_HT * RV_HOP; i += RV_NT) {
-        const int hh = i / RV_HOP, n = i - hh * RV_HOP;
-        const int h = m0 + 1 + hh;                 // hop index = frame index of its first half
-        const int t = (h - 1) * RV_HOP + n;        // output sample (tp - hop)
-        if (t >= p.ir_len) continue;
-        float val = 0.f, env = 0.f;
-        if (h < p.frames) { val = fr[(hh + 1) * RV_NFFT + n]; env = win[n] * win[n]; }
-        if (h - 1 < p.frames) {
-            val += fr[hh * RV_NFFT + n + RV_HOP];
-            env += win[n + RV_HOP] * win[n + RV_HOP];
+    // 5. overlap-add, envelope division, trim -- both channels by every thread, so that the rows can be
+    //    written as mid/side or, for the pseudo_midside mode, as left/right = mid +- side (reverb.py:225-228)
+    float em = 0.f, es = 0.f;
+    float* row0 = p.ir + (size_t)(2 * b) * p.ir_len;
+    float* row1 = row0 + p.ir_len;
+    const float* frm = fr_all;
+    const float* frs = fr_all + RV_FT * RV_NFFT;
+    if (p.vec_ok) {
+        for (int i = threadIdx.x; i < RV_HT * (RV_HOP / 4); i += 2 * RV_NT) {
+            const int hh = i / (RV_HOP / 4), n = (i - hh * (RV_HOP / 4)) * 4;
+            const int h = m0 + 1 + hh;                 // hop index = frame index of its first half
+            const int t = (h - 1) * RV_HOP + n;        // output sample (tp - hop); frame h-1 exists whenever t < ir_len
+            if (t >= p.ir_len) continue;
+            const int o1 = (hh + 1) * RV_NFFT + n, o2 = hh * RV_NFFT + n + RV_HOP;
+            const float4 am = *reinterpret_cast<const float4*>(frm + o1);       // zero beyond the last frame
+            const float4 cm = *reinterpret_cast<const float4*>(frm + o2);
+            const float4 as = *reinterpret_cast<const float4*>(frs + o1);
+            const float4 cs = *reinterpret_cast<const float4*>(frs + o2);
+            const float4 w1 = *reinterpret_cast<const float4*>(win + n);
+            const float4 w2 = *reinterpret_cast<const float4*>(win + n + RV_HOP);
+            const float e1 = h < p.frames ? 1.f : 0.f;
+            const float ex = fmaf(e1 * w1.x, w1.x, w2.x * w2.x), ey = fmaf(e1 * w1.y, w1.y, w2.y * w2.y);
+            const float ez = fmaf(e1 * w1.z, w1.z, w2.z * w2.z), ew = fmaf(e1 * w1.w, w1.w, w2.w * w2.w);
+            const float4 vm = make_float4((am.x + cm.x) / ex, (am.y + cm.y) / ey, (am.z + cm.z) / ez, (am.w + cm.w) / ew);
+            const float4 vs = make_float4((as.x + cs.x) / ex, (as.y + cs.y) / ey, (as.z + cs.z) / ez, (as.w + cs.w) / ew);
+            em = fmaf(vm.x, vm.x, em); em = fmaf(vm.y, vm.y, em); em = fmaf(vm.z, vm.z, em); em = fmaf(vm.w, vm.w, em);
+            es = fmaf(vs.x, vs.x, es); es = fmaf(vs.y, vs.y, es); es = fmaf(vs.z, vs.z, es); es = fmaf(vs.w, vs.w, es);
+            if (p.to_lr) {
+                *reinterpret_cast<float4*>(row0 + t) = make_float4(vm.x + vs.x, vm.y + vs.y, vm.z + vs.z, vm.w + vs.w);
+                *reinterpret_cast<float4*>(row1 + t) = make_float4(vm.x - vs.x, vm.y - vs.y, vm.z - vs.z, vm.w - vs.w);
+            } else {
+                *reinterpret_cast<float4*>(row0 + t) = vm;
+                *reinterpret_cast<float4*>(row1 + t) = vs;
+            }
         }
-        val = val / env;
-        irow[t] = val;
-        esum = fmaf(val, val, esum);
+    } else {
+        for (int i = threadIdx.x; i < RV_HT * RV_HOP; i += 2 * RV_NT) {
+            const int hh = i / RV_HOP, n = i - hh * RV_HOP;
+            const int h = m0 + 1 + hh;
+            const int t = (h - 1) * RV_HOP + n;
+            if (t >= p.ir_len) continue;
+            const float e1 = h < p.frames ? 1.f : 0.f;
+            const float env = fmaf(e1 * win[n], win[n], win[n + RV_HOP] * win[n + RV_HOP]);
+            const float vm = (frm[(hh + 1) * RV_NFFT + n] + frm[hh * RV_NFFT + n + RV_HOP]) / env;
+            const float vs = (frs[(hh + 1) * RV_NFFT + n] + frs[hh * RV_NFFT + n + RV_HOP]) / env;
+            em = fmaf(vm, vm, em);
+            es = fmaf(vs, vs, es);
+            row0[t] = p.to_lr ? vm + vs : vm;
+            row1[t] = p.to_lr ? vm - vs : vs;
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
-    if ((tid & 31) == 0) red[tid >> 5] = esum;
+    for (int o = 16; o > 0; o >>= 1) {
+        em += __shfl_xor_sync(0xffffffffu, em, o);
+        es += __shfl_xor_sync(0xffffffffu, es, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = em; red[16 + (threadIdx.x >> 5)] = es; }
     __syncthreads();
-    if (tid == 0) {
-        float s = 0.f;
-        for (int w = 0; w < RV_NT / 32; ++w) s += red[w];
-        p.partial[(size_t)row * p.tiles + tile] = s;
+    if (threadIdx.x < 2) {
+        float sum = 0.f;
+        for (int w = 0; w < 2 * RV_NT / 32; ++w) sum += red[16 * threadIdx.x + w];
+        p.partial[(size_t)(2 * b + threadIdx.x) * p.tiles + tile] = sum;
     }
 }
 
@@ -224,27 +280,18 @@ __global__ void reverb_energy_kernel(const float* __restrict__ partial, float* _
     }
 }
 
-// ms_to_lr (optional) + unit-energy normalisation, in place: ir [B][2][T]
+// unit-energy normalisation in place (normalize_impulse, core/utils.py:14-18): ir [B][2][T], rows already in
+// their final channel layout; energy = sum_t of the squared RAW mid / side rows
 __global__ void __launch_bounds__(256) reverb_finalize_kernel(float* ir, const float* __restrict__ energy, int batch,
                                                               int T, int to_lr) {
-    const long long total = (long long)batch * T;
+    const long long total = (long long)batch * 2 * T;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const long long b = i / T, t = i - b * T;
+        const long long b = i / (2LL * T);
         const float e0 = energy[2 * b], e1 = energy[2 * b + 1];
-        float* pm = ir + (b * 2) * T + t;
-        float* ps = ir + (b * 2 + 1) * T + t;
-        const float m = *pm, s = *ps;
-        if (to_lr) {
-            // mean_c sum_t (m +- s)^2 = sum m^2 + sum s^2
-            const float sc = 1.f / sqrtf(e0 + e1 + 1e-12f);
-            *pm = (m + s) * sc;
-            *ps = (m - s) * sc;
-        } else {
-            const float sc = 1.f / sqrtf(0.5f * (e0 + e1) + 1e-12f);
-            *pm = m * sc;
-            *ps = s * sc;
-        }
+        // left/right: mean_c sum_t (m +- s)^2 = sum m^2 + sum s^2
+        const float sc = to_lr ? 1.f / sqrtf(e0 + e1 + 1e-12f) : 1.f / sqrtf(0.5f * (e0 + e1) + 1e-12f);
+        ir[i] *= sc;
     }
 }
 
@@ -262,18 +309,18 @@ size_t gfx_reverb_ir_workspace_bytes(int batch, int ir_len) {
     return ((size_t)batch * 2 * (gfx::reverb_tiles(ir_len) + 1)) * sizeof(float);
 }
 
-// mode: 0 = raw mid/side IR + energies only, 1 = normalise in place, 2 = ms_to_lr + normalise in place
+// mode: 0 raw mid/side + energies, 1 mid/side normalised, 2 left/right normalised, 3 raw left/right + energies
 int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, const float* init_log_magnitude,
                       const float* delta_log_magnitude, const float* gain_env_log_magnitude,
                       const float* window, float* ir, float* energy, void* workspace, size_t workspace_bytes,
                       int batch, int n_fft, int hop, int ir_len, int mode, void* stream) {
     using namespace gfx;
     if (!noise_stft || !init_log_magnitude || !delta_log_magnitude || !window || !ir || !energy) return GFX_ERR_INVALID;
-    if (batch <= 0 || ir_len <= 0 || mode < 0 || mode > 2) return GFX_ERR_INVALID;
+    if (batch <= 0 || ir_len <= 0 || mode < 0 || mode > 3) return GFX_ERR_INVALID;
     if (n_fft != RV_NFFT || hop != RV_HOP) return GFX_ERR_UNSUPPORTED;
     const int tiles = reverb_tiles(ir_len);
     if (!workspace || workspace_bytes < (size_t)batch * 2 * tiles * sizeof(float)) return GFX_ERR_WORKSPACE;
-    if ((long long)batch * 2 * tiles > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
+    if ((long long)batch * tiles > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
     ReverbParams p;
     p.noise = (const float2*)noise_stft;
     p.noise_bstride = noise_batch_stride;
@@ -282,26 +329,25 @@ int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, con
     p.frames = 1 + ir_len / hop;
     p.ir_len = ir_len;
     p.tiles = tiles;
-    const size_t smem = sizeof(pk2) * (RV_FT * RV_ZS) + sizeof(float) * (RV_FT * RV_NFFT) +
-                        sizeof(float2) * (RV_N + RV_N / 2) +
-                        sizeof(float) * (RV_NFFT + 2 * (RV_BINS + 3) + RV_FT + 8);
+    p.vec_ok = ((uintptr_t)ir % 16 == 0) && (ir_len % 4 == 0);
+    p.to_lr = mode >= 2;
     static bool configured = false;
     if (!configured) {
-        GFX_CUDA_CHECK(cudaFuncSetAttribute(reverb_ir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GFX_CUDA_CHECK(cudaFuncSetAttribute(reverb_ir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RV_SMEM_BYTES));
         configured = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    reverb_ir_kernel<<<(unsigned)(batch * 2 * tiles), RV_NT, smem, st>>>(p);
-    GFX_CUDA_CHECK(cudaGetLastError());
+    reverb_ir_kernel<<<(unsigned)(batch * tiles), 2 * RV_NT, RV_SMEM_BYTES, st>>>(p);
+    GFX_LAUNCH_CHECK();
     reverb_energy_kernel<<<(batch * 2 + 127) / 128, 128, 0, st>>>(p.partial, energy, batch * 2, tiles);
-    GFX_CUDA_CHECK(cudaGetLastError());
-    if (mode != 0) {
-        const long long total = (long long)batch * ir_len;
+    GFX_LAUNCH_CHECK();
+    if (mode == 1 || mode == 2) {
+        const long long total = (long long)batch * 2 * ir_len;
         long long blocks = (total + 255) / 256;
         const long long cap = (long long)device_info().sm_count * 8;
         if (blocks > cap) blocks = cap;
         reverb_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(ir, energy, batch, ir_len, mode == 2);
-        GFX_CUDA_CHECK(cudaGetLastError());
+        GFX_LAUNCH_CHECK();
     }
     return GFX_OK;
 }

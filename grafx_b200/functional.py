@@ -273,8 +273,9 @@ def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_
 
     finish = "unit": mid/side rows normalised to unit energy (normalize_impulse);
              "lr":   ms_to_lr, then normalised (pseudo_midside);
-             "raw":  returns (ir_raw, energy[B, 2]) for fir_conv_midside_ir, which applies the channel
-                     epilogue while it forms the filter spectra (the finished IR is never stored)."""
+             "raw" / "raw_lr": returns (un-normalised mid/side | left/right response, energy[B, 2] of the
+                     raw mid/side rows) for fir_conv_midside_ir, which folds the normalisation into the
+                     filter spectra (the finished IR is never stored)."""
     _cabi.require_cuda(noise_stft, init_log_magnitude, delta_log_magnitude, window)
     B = init_log_magnitude.shape[0]
     bins, frames = n_fft // 2 + 1, 1 + ir_len // hop_length
@@ -290,11 +291,11 @@ def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_
         ge = _prep(gain_env_log_magnitude, torch.float32)
         assert tuple(ge.shape) == (B, 2, frames)
     win = _prep(window, torch.float32)
-    mode = {"raw": 0, "unit": 1, "lr": 2}[finish]
+    mode = {"raw": 0, "unit": 1, "lr": 2, "raw_lr": 3}[finish]
     ir = torch.empty(B, 2, ir_len, dtype=torch.float32, device=h0.device)
     energy = torch.empty(B, 2, dtype=torch.float32, device=h0.device)
     if B == 0:
-        return (ir, energy) if mode == 0 else ir
+        return (ir, energy) if mode in (0, 3) else ir
     L_ = _cabi.lib()
     ws = _cabi.workspace(L_.gfx_reverb_ir_workspace_bytes(B, ir_len), h0.device)
     with torch.cuda.device(h0.device):
@@ -304,13 +305,13 @@ def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_
     if code == -4:
         raise NotImplementedError("reverb IR synthesis supports n_fft=384, hop_length=192 only")
     _cabi.check(code, "gfx_reverb_ir_f32")
-    return (ir, energy) if mode == 0 else ir
+    return (ir, energy) if mode in (0, 3) else ir
 
 
 def fir_conv_midside_ir(x: torch.Tensor, ir_raw: torch.Tensor, energy: torch.Tensor, to_lr: bool) -> torch.Tensor:
-    """Causal convolution of x [B, 1|2, L] with the reverb response given as the raw mid/side IR
-    [B, 2, N] + its row energies [B, 2]: ms_to_lr (optional) and normalize_impulse
-    (reverb.py:215-228) are folded into the filter spectra."""
+    """Causal convolution of x [B, 1|2, L] with a reverb response given un-normalised ([B, 2, N], rows
+    mid/side, or left/right when to_lr) + the energies [B, 2] of its raw mid/side rows:
+    normalize_impulse (reverb.py:215-228) is folded into the filter spectra."""
     _cabi.require_cuda(x, ir_raw, energy)
     assert x.ndim == 3 and ir_raw.ndim == 3 and ir_raw.shape[1] == 2 and x.shape[0] == ir_raw.shape[0]
     B, cx, L = x.shape

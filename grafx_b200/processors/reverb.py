@@ -55,12 +55,14 @@ class STFTMaskedNoiseReverb(nn.Module):
                             self.n_fft, self.hop_length, finish=_finish)
 
     def forward(self, input_signals, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude=None):
-        # raw mid/side response + energies; ms_to_lr / normalize_impulse (reverb.py:215-228) happen
-        # inside the convolution while the filter spectra are formed
-        ir_raw, energy = self.compute_ir(init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude, _finish="raw")
+        # un-normalised response (+ row energies) in its final channel layout; normalize_impulse
+        # (reverb.py:215-228) happens inside the convolution while the filter spectra are formed
+        to_lr = self.processor_channel == "pseudo_midside"
+        ir_raw, energy = self.compute_ir(init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude,
+                                         _finish="raw_lr" if to_lr else "raw")
         if self.processor_channel == "midside":
             return F_.ms_to_lr(F_.fir_conv_midside_ir(F_.lr_to_ms(input_signals), ir_raw, energy, to_lr=False))
-        return F_.fir_conv_midside_ir(input_signals, ir_raw, energy, to_lr=self.processor_channel == "pseudo_midside")
+        return F_.fir_conv_midside_ir(input_signals, ir_raw, energy, to_lr=to_lr)
 
     def parameter_size(self):
         size = {"init_log_magnitude": (2, self.num_bins), "delta_log_magnitude": (2, self.num_bins)}

@@ -41,6 +41,7 @@ extern "C" {
 GFX_API int gfx_version(void);              /* major*10000 + minor*100 + patch */
 GFX_API int gfx_last_cuda_error(void);      /* cudaError_t of the last failed runtime call, 0 if none */
 GFX_API const char* gfx_error_string(int code);
+GFX_API unsigned long long gfx_kernel_launch_count(void); /* kernels this library has launched since it was loaded */
 GFX_API int gfx_device_sm_count(void);      /* SMs of the current device (148 on B200), <0 on error */
 
 /* ---- exact biquad cascade ------------------------------------------------------------------
@@ -101,11 +102,12 @@ GFX_API int gfx_fir_conv_f32(const float* x, const float* h, float* y, int batch
                              int filter_len, int zerophase, const void* plan, void* workspace,
                              size_t workspace_bytes, void* stream);
 GFX_API int gfx_fir_set_tuning(int long_n, int mid_n);
-/* Same convolution (causal) with the filter given as the RAW mid/side impulse response of
- * gfx_reverb_ir_f32 plus its per-row energies: ms_to_lr (optional) and normalize_impulse
- * (processors/reverb.py:215-228, core/utils.py:14-18) are applied while the filter spectra are formed,
- * so the normalised left/right IR never exists in memory.  ir_raw [batch, 2, ir_len], energy [batch, 2],
- * x [batch, cx, L] (cx = 1 or 2), y [batch, 2, L].  Plan / workspace as for gfx_fir_conv_f32 with ch = 2. */
+/* Same convolution (causal) with the filter given as the UN-NORMALISED impulse response of
+ * gfx_reverb_ir_f32 (mode 0: mid/side rows, ms_to_lr = 0; mode 3: left/right rows, ms_to_lr = 1) plus the
+ * energies of its raw mid/side rows: normalize_impulse (processors/reverb.py:215-228, core/utils.py:14-18)
+ * is applied while the filter spectra are formed, so the normalised IR never exists in memory.
+ * ir_raw [batch, 2, ir_len], energy [batch, 2], x [batch, cx, L] (cx = 1 or 2), y [batch, 2, L].
+ * Plan / workspace as for gfx_fir_conv_f32 with ch = 2. */
 GFX_API int gfx_fir_conv_midside_ir_f32(const float* x, const float* ir_raw, const float* energy, float* y, int batch,
                                         int cx, long long L, int ir_len, int ms_to_lr, const void* plan,
                                         void* workspace, size_t workspace_bytes, void* stream);
@@ -119,8 +121,9 @@ GFX_API int gfx_fir_conv_midside_ir_f32(const float* x, const float* ir_raw, con
  *   window [n_fft] (the registered hann buffer); ir [batch, 2, ir_len] (output);
  *   energy [batch, 2] (output): sum_t of the squared RAW mid/side rows;
  *   workspace: gfx_reverb_ir_workspace_bytes(batch, ir_len) bytes of scratch;
- *   mode 0: ir = raw mid/side response (feed it with `energy` to gfx_fir_conv_midside_ir_f32);
- *   mode 1: ir normalised to unit energy in place; mode 2: ms_to_lr, then normalised (pseudo_midside).
+ *   mode 0: ir = raw mid/side response; mode 3: raw left/right (= mid +- side) response -- feed either,
+ *     with `energy`, to gfx_fir_conv_midside_ir_f32, which folds the normalisation into the filter spectra;
+ *   mode 1: mid/side normalised to unit energy in place; mode 2: left/right, normalised (pseudo_midside).
  * bins = n_fft/2+1, frames = 1 + ir_len/hop.  Supported geometry: n_fft = 384, hop = 192. */
 GFX_API size_t gfx_reverb_ir_workspace_bytes(int batch, int ir_len);
 GFX_API int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, const float* init_log_magnitude,
