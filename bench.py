@@ -187,7 +187,7 @@ def tree_slice(obj, lo, hi):
 
 # --------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
@@ -197,7 +197,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -217,7 +217,7 @@ class ClockSampler:
             self.proc.wait(2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, busy, mx, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [c.strip() for c in r.split(",")]
@@ -225,14 +225,17 @@ class ClockSampler:
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2]))
+                if float(f[4]) >= 10.0:
+                    busy.append(float(f[1]))
             except ValueError:
                 continue
             for n, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        use = sorted(busy if busy else sm)
+        return {"sm_mhz": use[len(use) // 2] if use else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(busy),
+                "window": "warm-up + timed steps + kernel-only loop + end-to-end loop (50 ms period)"}
 
 
 def pick_cpu_threads(fn):
@@ -332,13 +335,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             y = wl.forward(x, prm)
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         from grafx_b200 import _cabi
@@ -350,7 +353,6 @@ def main():
         barrier()
         launches_timed = int(_cabi.lib().gfx_kernel_launch_count() - launches0)
         ms_total = max_over_ranks(ev0.elapsed_time(ev1), device)
-        clocks = sampler.stop() if rank == 0 else None
         ms_step = ms_total / args.steps
         value = samples * world / (ms_step * 1e-3)
 
@@ -420,6 +422,8 @@ def main():
                    "h2d_bytes_per_step": tree_bytes(xp) + (tree_bytes(prm_p)),
                    "d2h_bytes_per_step": tree_bytes(out_p), "ms_per_step": e_ms,
                    "how": f"pinned host tensors -> {nchunk} chunks over {len(streams)} streams: H2D, nn.Module forward, D2H of the output audio"}
+
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu_baseline = None

@@ -51,6 +51,7 @@ struct DynParams {
     unsigned int* ticket;
     int* flags;
     float* state;  // [batch][2*n_stages]
+    float* tables; // [batch][DYN_ROW_FLOATS] per-row constants (dynamics_tables_kernel)
     int n_stages;
     int iir_len;
     int aligned;
@@ -62,6 +63,29 @@ __device__ __forceinline__ float softplus_torch(float v) {
     return v > 20.f ? v : log1pf(expf(v));
 }
 
+// Per-row constants, formed once per call by dynamics_tables_kernel (double precision where it matters)
+// and staged in shared memory with each tile: the sample loop never touches expf/logf/double.
+struct SmootherConst {  // 48 floats
+    float alpha, oma;   // one-pole coefficient, 1 - alpha
+    float aN;           // alpha^iir_len (0 when it underflows fp32 or when the signal is shorter than iir_len)
+    float aW;           // alpha^(32*32): one warp of chunks
+    float apow[5];      // alpha^(32 * 2^j)
+    float at, rt;       // ballistics attack / release coefficients
+    float pad[5];
+    float pl[32];       // alpha^(32 * lane)
+};
+// Knee constants.  Per-sample math uses the SFU intrinsics __logf/__expf (abs error ~1e-6 on the log-energy /
+// relative ~2e-6 on the gain, far inside the 1e-4 parity budget).
+struct KneeConst {      // 16 floats
+    float T, W, lo, hi;       // threshold, knee half-width (quadratic) or width (exponential), T-W, T+W
+    float slope;              // log-gain slope outside the knee: 1/R - 1 (compressor) | R - 1 (gate)
+    float mid_scale;          // (1/R - 1)/(4W)  |  (1 - R)/(4W)
+    float exp_scale;          // exponential knee: (1/R - 1)/W | -exp(lr)/W
+    float pad[9];
+};
+constexpr int DYN_SC_FLOATS = sizeof(SmootherConst) / 4, DYN_KC_FLOATS = sizeof(KneeConst) / 4;
+constexpr int DYN_ROW_FLOATS = DYN_MAX_STAGES * (2 * DYN_SC_FLOATS + DYN_KC_FLOATS);  // per-row table
+
 template <int NT>
 struct DynCtx {
     static constexpr int S = 32;
@@ -70,6 +94,8 @@ struct DynCtx {
     float4* work4;   // [NT*8] scratch tile (ballistics)
     float* wt;       // [2][NW]
     float* s_state;  // [2*DYN_MAX_STAGES]
+    const SmootherConst* sc;  // [2*DYN_MAX_STAGES] constants of this row (smem)
+    const KneeConst* kc;      // [DYN_MAX_STAGES]
     int tid, lane, warp;
     int t_idx, row;
     long long t0, remain;
@@ -101,17 +127,8 @@ template <int NT, typename LagFn>
 __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, float (&u)[32],
                                            const SmootherDesc& sm, int slot, LagFn lag_input) {
     constexpr int S = 32, NW = NT / 32;
-    const float zraw = sm.z[cx.row];
-    float alpha = 1.f / (1.f + expf(-zraw));
-    alpha = fminf(alpha, 1.f - 1e-5f);
-    const double ad = (double)alpha;
-    // truncation tail a^N (0 when it underflows fp32 or when the signal is shorter than N)
-    float aN = 0.f;
-    if ((long long)p.iir_len < p.L) {
-        const double v = exp((double)p.iir_len * log(ad));
-        aN = v < 1e-37 ? 0.f : (float)v;
-    }
-    const float oma = 1.f - alpha;
+    const SmootherConst& c = cx.sc[slot];
+    const float alpha = c.alpha, oma = c.oma, aN = c.aN;
     if (aN != 0.f) {
         const long long chunk0 = cx.t0 + (long long)cx.tid * S;
         if (sm.hist != nullptr) {
@@ -139,20 +156,13 @@ __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, f
         u[i] *= oma;
         w = fmaf(alpha, w, u[i]);
     }
-    // powers of alpha (double): a^32, a^(32*2^j), a^(32*lane), a^(32*32)
-    double a32 = ad;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) a32 *= a32;
-    double sq = a32, pl = 1.0;
     float z = w;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const float pv = __shfl_up_sync(0xffffffffu, z, 1 << j);
-        if (cx.lane >= (1 << j)) z = fmaf((float)sq, pv, z);
-        if ((cx.lane >> j) & 1) pl *= sq;
-        sq *= sq;
+        if (cx.lane >= (1 << j)) z = fmaf(c.apow[j], pv, z);
     }
-    const float aW = (float)sq;  // a^(32*32)
+    const float aW = c.aW;
     float* wt = cx.wt + (cx.sync_parity & 1) * NW;
     cx.sync_parity++;
     if (cx.lane == 31) wt[cx.warp] = z;
@@ -162,7 +172,7 @@ __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, f
     for (int q = 0; q < cx.warp; ++q) s = fmaf(aW, s, wt[q]);
     float ex = __shfl_up_sync(0xffffffffu, z, 1);
     if (cx.lane == 0) ex = 0.f;
-    float y = fmaf((float)pl, s, ex);  // T[-1] of this chunk
+    float y = fmaf(c.pl[cx.lane], s, ex);  // T[-1] of this chunk
     // true pass + relu
 #pragma unroll
     for (int i = 0; i < S; ++i) {
@@ -176,8 +186,7 @@ __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, f
 template <int NT>
 __device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParams& p, float (&u)[32],
                                                   const SmootherDesc& sm, int slot) {
-    const float at = 1.f / (1.f + expf(-sm.z[(size_t)cx.row * 2 + 0]));
-    const float rt = 1.f / (1.f + expf(-sm.z[(size_t)cx.row * 2 + 1]));
+    const float at = cx.sc[slot].at, rt = cx.sc[slot].rt;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
         cx.work4[swz_unit(cx.tid, c)] = make_float4(u[4 * c], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
@@ -216,69 +225,113 @@ __device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParam
     }
 }
 
-// Per-row knee constants (hoisted out of the sample loop).  The per-sample path uses the SFU
-// intrinsics __logf/__expf (abs error ~1e-6 on the log-energy / relative ~2e-6 on the gain, far
-// inside the 1e-4 parity budget) -- the accurate libdevice versions cost ~10x the instructions and
-// made this kernel issue-bound.
-struct KneeConst {
-    int kind, knee;
-    float T, W, lo, hi;       // threshold, knee half-width (quadratic) or width (exponential), T-W, T+W
-    float ratio, inv_ratio;   // R = 1 + exp(log_ratio)
-    float mid_scale;          // (1/R - 1)/(4W)  |  (1 - R)/(4W)
-    float exp_scale, inv_W;   // exponential knee: (1/R - 1)/W | -exp(lr)/W
-};
-
-__device__ __forceinline__ KneeConst make_knee(int kind, int knee, float T, float lr, float lk) {
-    KneeConst k;
-    k.kind = kind; k.knee = knee; k.T = T;
-    const float elr = expf(lr);
-    k.ratio = 1.f + elr;
-    k.inv_ratio = 1.f / k.ratio;
-    k.W = knee == 1 ? expf(lk) * 0.5f : (knee == 2 ? expf(lk) : 0.f);
-    k.lo = T - k.W; k.hi = T + k.W;
-    k.mid_scale = (kind == 0 ? (k.inv_ratio - 1.f) : (1.f - k.ratio)) / (4.f * k.W);
-    k.exp_scale = (kind == 0 ? (k.inv_ratio - 1.f) : -elr) / k.W;
-    k.inv_W = 1.f / k.W;
-    return k;
-}
-
 __device__ __forceinline__ float softplus_fast(float v) {
     // torch softplus (threshold 20); log1p(exp(v)) with the SFU exp/log
     return v > 20.f ? v : __logf(1.f + __expf(v));
 }
 
-__device__ __forceinline__ float knee_log_gain(const KneeConst& k, float G) {
-    // returns log-gain  G_out - G   (dynamics.py:443-489 compressor, :675-721 gate)
-    const float d = G - k.T;
-    if (k.kind == 0) {
-        if (k.knee == 0) return fminf(G, fmaf(d, k.inv_ratio, k.T)) - G;
-        if (k.knee == 1) {
-            float out = G;                                   // below the knee
-            if (G > k.hi) out = fmaf(d, k.inv_ratio, k.T);   // above
-            else if (!(G < k.lo)) { const float e = d + k.W; out = fmaf(k.mid_scale * e, e, G); }
-            return out - G;
-        }
-        return k.exp_scale * softplus_fast(k.W * d);
-    } else {
-        if (k.knee == 0) return fminf(G, fmaf(k.ratio, d, k.T)) - G;
-        if (k.knee == 1) {
-            float out = G;                                   // above the knee
-            if (G < k.lo) out = fmaf(k.ratio, d, k.T);       // below
-            else if (!(G > k.hi)) { const float e = d - k.W; out = fmaf(k.mid_scale * e, e, G); }
-            return out - G;
-        }
-        return k.exp_scale * softplus_fast(-k.W * d);
+// u[i] (smoothed energy) -> log-gain G_out - G of the knee (dynamics.py:443-489 compressor, :675-721 gate).
+// `mode` = kind * 3 + knee is uniform over the launch: the switch sits outside the sample loop, the loop
+// bodies are branch-free (selects).
+__device__ __forceinline__ void knee_log_gain(float (&u)[32], const KneeConst& k, int mode) {
+    const float T = k.T, W = k.W, lo = k.lo, hi = k.hi, slope = k.slope, mid = k.mid_scale, es = k.exp_scale;
+    switch (mode) {
+        case 0:  // compressor, hard:  min(G, T + d/R) - G = min(0, d (1/R - 1))
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = fminf(0.f, (__logf(u[i] + 1e-5f) - T) * slope);
+            break;
+        case 1:  // compressor, quadratic: below G | above T + d/R | knee G + (1/R - 1)(d + W)^2 / (4W)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float G = __logf(u[i] + 1e-5f), d = G - T, e = d + W;
+                const float m = mid * e * e;
+                u[i] = G > hi ? d * slope : (G < lo ? 0.f : m);
+            }
+            break;
+        case 2:  // compressor, exponential
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = es * softplus_fast(W * (__logf(u[i] + 1e-5f) - T));
+            break;
+        case 3:  // gate, hard:  min(G, R d + T) - G = min(0, (R - 1) d)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = fminf(0.f, (__logf(u[i] + 1e-5f) - T) * slope);
+            break;
+        case 4:  // gate, quadratic: below R d + T | above G | knee G + (1 - R)(d - W)^2 / (4W)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float G = __logf(u[i] + 1e-5f), d = G - T, e = d - W;
+                const float m = mid * e * e;
+                u[i] = G < lo ? d * slope : (G > hi ? 0.f : m);
+            }
+            break;
+        default:  // gate, exponential
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = es * softplus_fast(-W * (__logf(u[i] + 1e-5f) - T));
+            break;
     }
 }
 
-template <int NT, bool MULTI>
-__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 8)) dynamics_kernel(const DynParams p) {
+// one thread per (row, stage): every constant of the sample loops
+__global__ void dynamics_tables_kernel(const DynParams p, float* __restrict__ tables) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.batch * p.n_stages) return;
+    const int row = idx / p.n_stages, d = idx - row * p.n_stages;
+    const StageDesc& sd = p.st[d];
+    float* base = tables + (size_t)row * DYN_ROW_FLOATS;
+    for (int which = 0; which < 2; ++which) {
+        const SmootherDesc& sm = which ? sd.post : sd.pre;
+        SmootherConst c;
+        for (int i = 0; i < DYN_SC_FLOATS; ++i) reinterpret_cast<float*>(&c)[i] = 0.f;
+        if (sm.kind == 1) {
+            // TruncatedOnePoleIIRFilter (core/envelope.py:44-49): alpha = min(sigmoid(z), 1 - 1e-5)
+            float alpha = 1.f / (1.f + expf(-sm.z[row]));
+            alpha = fminf(alpha, 1.f - 1e-5f);
+            const double ad = (double)alpha;
+            c.alpha = alpha;
+            c.oma = 1.f - alpha;
+            if ((long long)p.iir_len < p.L) {
+                const double v = exp((double)p.iir_len * log(ad));
+                c.aN = v < 1e-37 ? 0.f : (float)v;
+            }
+            double sq = ad;
+            for (int k = 0; k < 5; ++k) sq *= sq;  // alpha^32
+            double run = 1.0;
+            for (int l = 0; l < 32; ++l) { c.pl[l] = (float)run; run *= sq; }
+            for (int j = 0; j < 5; ++j) { c.apow[j] = (float)sq; sq *= sq; }
+            c.aW = (float)sq;
+        } else if (sm.kind == 2) {
+            // Ballistics (core/envelope.py:84-101)
+            c.at = 1.f / (1.f + expf(-sm.z[(size_t)row * 2 + 0]));
+            c.rt = 1.f / (1.f + expf(-sm.z[(size_t)row * 2 + 1]));
+        }
+        float* dst = base + (2 * d + which) * DYN_SC_FLOATS;
+        for (int i = 0; i < DYN_SC_FLOATS; ++i) dst[i] = reinterpret_cast<const float*>(&c)[i];
+    }
+    KneeConst k;
+    for (int i = 0; i < DYN_KC_FLOATS; ++i) reinterpret_cast<float*>(&k)[i] = 0.f;
+    const float T = sd.log_threshold[row] - 6.f, lr = sd.log_ratio[row], lk = sd.log_knee ? sd.log_knee[row] : 0.f;
+    const float elr = expf(lr), ratio = 1.f + elr, inv_ratio = 1.f / ratio;
+    k.T = T;
+    k.W = sd.knee == 1 ? expf(lk) * 0.5f : (sd.knee == 2 ? expf(lk) : 0.f);
+    k.lo = T - k.W; k.hi = T + k.W;
+    k.slope = sd.kind == 0 ? (inv_ratio - 1.f) : (ratio - 1.f);
+    k.mid_scale = (sd.kind == 0 ? (inv_ratio - 1.f) : (1.f - ratio)) / (4.f * k.W);
+    k.exp_scale = (sd.kind == 0 ? (inv_ratio - 1.f) : -elr) / k.W;
+    float* dst = base + 2 * DYN_MAX_STAGES * DYN_SC_FLOATS + d * DYN_KC_FLOATS;
+    for (int i = 0; i < DYN_KC_FLOATS; ++i) dst[i] = reinterpret_cast<const float*>(&k)[i];
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const DynParams p) {
     constexpr int S = 32, TILE = NT * S, NW = NT / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DynCtx<NT> cx;
     cx.xs4 = reinterpret_cast<float4*>(smem_raw);
     cx.work4 = cx.xs4 + (size_t)p.C * NT * 8;
-    cx.wt = reinterpret_cast<float*>(cx.work4 + (NT == 64 ? (size_t)NT * 8 : 0));
+    float* consts = reinterpret_cast<float*>(cx.work4 + (NT == 64 ? (size_t)NT * 8 : 0));  // [DYN_ROW_FLOATS]
+    cx.sc = reinterpret_cast<const SmootherConst*>(consts);
+    cx.kc = reinterpret_cast<const KneeConst*>(consts + 2 * DYN_MAX_STAGES * DYN_SC_FLOATS);
+    cx.wt = consts + DYN_ROW_FLOATS;
     cx.s_state = cx.wt + 2 * NW;
     float* xs = reinterpret_cast<float*>(cx.xs4);
     __shared__ unsigned int sh_item;
@@ -301,7 +354,14 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 8)) dynamics_kernel(const
         const float* xrow = p.x + (size_t)cx.row * C * (size_t)p.L;
         float* yrow = p.y + (size_t)cx.row * C * (size_t)p.L;
 
-        // ---- stage all channels of the tile
+        // ---- stage the row constants and all channels of the tile
+        {
+            const float4* trow = reinterpret_cast<const float4*>(p.tables + (size_t)cx.row * DYN_ROW_FLOATS);
+            const int n4 = p.n_stages * 2 * DYN_SC_FLOATS / 4;
+            for (int i = cx.tid; i < n4; i += NT) cp_async16(consts + 4 * i, trow + i, 16);
+            constexpr int k4 = DYN_MAX_STAGES * 2 * DYN_SC_FLOATS / 4;
+            for (int i = cx.tid; i < p.n_stages * DYN_KC_FLOATS / 4; i += NT) cp_async16(consts + 4 * (k4 + i), trow + k4 + i, 16);
+        }
         if (p.aligned) {
             for (int c = 0; c < C; ++c) {
                 const float* xr = xrow + (size_t)c * p.L;
@@ -318,6 +378,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 8)) dynamics_kernel(const
             cp_async_commit();
             cp_async_wait<0>();
         } else {
+            cp_async_commit();
             for (int c = 0; c < C; ++c) {
                 const float* xr = xrow + (size_t)c * p.L;
                 for (int i = cx.tid; i < TILE; i += NT) {
@@ -325,19 +386,14 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 8)) dynamics_kernel(const
                     xs[(size_t)c * TILE + (size_t)swz_unit(i >> 5, (i & 31) >> 2) * 4 + (i & 3)] = val;
                 }
             }
+            cp_async_wait<0>();
         }
         __syncthreads();
 
-        float G[MULTI ? S : 1];   // cumulative linear gain of the stages done so far (chains only)
-        float u[S];               // working chunk
-        if constexpr (MULTI) {
-#pragma unroll
-            for (int i = 0; i < S; ++i) G[i] = 1.f;
-        }
-
+        float u[S];  // working chunk: energy -> smoothed energy -> log-gain -> gain
         for (int d = 0; d < p.n_stages; ++d) {
             const StageDesc& sd = p.st[d];
-            // energy of the signal entering this stage: mean_c (G x_c)^2
+            // energy of the signal entering this stage (earlier stages already applied their gain in place)
 #pragma unroll
             for (int i = 0; i < S; ++i) u[i] = 0.f;
             for (int c = 0; c < C; ++c) {
@@ -350,12 +406,9 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 8)) dynamics_kernel(const
                     u[4 * q + 3] = fmaf(v.w, v.w, u[4 * q + 3]);
                 }
             }
-            if constexpr (MULTI) {
+            if (C > 1) {
 #pragma unroll
-                for (int i = 0; i < S; ++i) u[i] = u[i] * inv_c * (G[i] * G[i]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < S; ++i) u[i] = u[i] * inv_c;
+                for (int i = 0; i < S; ++i) u[i] *= inv_c;
             }
 
             if (sd.pre.kind == 1) {
@@ -378,10 +431,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 8)) dynamics_kernel(const
                 smooth_ballistics<NT>(cx, p, u, sd.pre, 2 * d);
             }
 
-            const KneeConst kc = make_knee(sd.kind, sd.knee, sd.log_threshold[cx.row] - 6.f, sd.log_ratio[cx.row],
-                                           sd.log_knee ? sd.log_knee[cx.row] : 0.f);
-#pragma unroll
-            for (int i = 0; i < S; ++i) u[i] = knee_log_gain(kc, __logf(u[i] + 1e-5f));
+            knee_log_gain(u, cx.kc[d], sd.kind * 3 + sd.knee);
             if (sd.post.kind == 0) {
 #pragma unroll
                 for (int i = 0; i < S; ++i) u[i] = __expf(u[i]);
@@ -402,27 +452,20 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 8)) dynamics_kernel(const
                     for (int i = 0; i < S; ++i) u[i] = __expf(u[i]);
                 }
             }
-            if constexpr (MULTI) {
+            // apply the gain in place in shared memory (each thread owns its chunk: no barrier between stages)
+            for (int c = 0; c < C; ++c) {
 #pragma unroll
-                for (int i = 0; i < S; ++i) G[i] *= u[i];
+                for (int q = 0; q < 8; ++q) {
+                    float4* pv = &cx.xs4[(size_t)c * NT * 8 + swz_unit(cx.tid, q)];
+                    float4 v = *pv;
+                    v.x *= u[4 * q]; v.y *= u[4 * q + 1]; v.z *= u[4 * q + 2]; v.w *= u[4 * q + 3];
+                    *pv = v;
+                }
             }
         }
         if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles && cx.have_state) chain_publish(p.flags + cx.row, cx.t_idx + 1);
 
-        // ---- apply the gain in place in shared memory, then store coalesced
-        for (int c = 0; c < C; ++c) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float4* pv = &cx.xs4[(size_t)c * NT * 8 + swz_unit(cx.tid, q)];
-                float4 v = *pv;
-                if constexpr (MULTI) {
-                    v.x *= G[4 * q]; v.y *= G[4 * q + 1]; v.z *= G[4 * q + 2]; v.w *= G[4 * q + 3];
-                } else {
-                    v.x *= u[4 * q]; v.y *= u[4 * q + 1]; v.z *= u[4 * q + 2]; v.w *= u[4 * q + 3];
-                }
-                *pv = v;
-            }
-        }
+        // ---- store coalesced
         __syncthreads();
         for (int c = 0; c < C; ++c) {
             float* yr = yrow + (size_t)c * p.L;
@@ -449,19 +492,23 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 8)) dynamics_kernel(const
 
 static size_t dyn_smem_bytes(int NT, int C) {
     // the scratch tile is only used by the ballistics variant (NT == 64)
-    return (size_t)(C + (NT == 64 ? 1 : 0)) * NT * 128 + (size_t)(2 * (NT / 32) + 2 * DYN_MAX_STAGES) * sizeof(float) + 64;
+    return (size_t)(C + (NT == 64 ? 1 : 0)) * NT * 128 +
+           (size_t)(DYN_ROW_FLOATS + 2 * (NT / 32) + 2 * DYN_MAX_STAGES) * sizeof(float) + 64;
 }
 
+static size_t dyn_tables_offset(int batch, int n_stages) {
+    const size_t flags = ((size_t)batch * sizeof(int) + 255) / 256 * 256;
+    return (256 + flags + (size_t)batch * 2 * n_stages * sizeof(float) + 255) / 256 * 256;
+}
 static size_t dyn_workspace_bytes(int batch, int n_stages) {
-    size_t flags = ((size_t)batch * sizeof(int) + 255) / 256 * 256;
-    return 256 + flags + (size_t)batch * 2 * n_stages * sizeof(float);
+    return dyn_tables_offset(batch, n_stages) + (size_t)batch * DYN_ROW_FLOATS * sizeof(float);
 }
 
-template <int NT, bool MULTI>
+template <int NT>
 static int launch_dynamics(DynParams& p, cudaStream_t stream) {
     const size_t smem = dyn_smem_bytes(NT, p.C);
     if (smem > (size_t)device_info().max_smem_optin) return GFX_ERR_UNSUPPORTED;
-    auto kern = dynamics_kernel<NT, MULTI>;
+    auto kern = dynamics_kernel<NT>;
     static size_t configured = 0;
     if (smem > configured) {
         GFX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -472,6 +519,8 @@ static int launch_dynamics(DynParams& p, cudaStream_t stream) {
     if (occ < 1) return GFX_ERR_UNSUPPORTED;
     long long grid = (long long)device_info().sm_count * occ;
     if (grid > (long long)p.n_items) grid = p.n_items;
+    dynamics_tables_kernel<<<(p.batch * p.n_stages + 127) / 128, 128, 0, stream>>>(p, p.tables);
+    GFX_LAUNCH_CHECK();
     kern<<<(unsigned)grid, NT, smem, stream>>>(p);
     GFX_LAUNCH_CHECK();
     return GFX_OK;
@@ -530,9 +579,9 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
     p.iir_len = iir_len;
     p.aligned = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (L % 4 == 0);
     GFX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256 + flags_bytes, (cudaStream_t)stream));
+    p.tables = (float*)(w + dyn_tables_offset(batch, n_stages));
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_stages > 1) return any_ballistics ? launch_dynamics<64, true>(p, st) : launch_dynamics<256, true>(p, st);
-    return any_ballistics ? launch_dynamics<64, false>(p, st) : launch_dynamics<256, false>(p, st);
+    return any_ballistics ? launch_dynamics<64>(p, st) : launch_dynamics<256>(p, st);
 }
 
 }  // extern "C"
