@@ -81,7 +81,9 @@ struct KneeConst {      // 16 floats
     float slope;              // log-gain slope outside the knee: 1/R - 1 (compressor) | R - 1 (gate)
     float mid_scale;          // (1/R - 1)/(4W)  |  (1 - R)/(4W)
     float exp_scale;          // exponential knee: (1/R - 1)/W | -exp(lr)/W
-    float pad[9];
+    float slope2, mid2, exp2s; // the three scales above times log2(e): the gain is then ex2() of the result
+    float Wl2;                // W * log2(e)
+    float pad[5];
 };
 constexpr int DYN_SC_FLOATS = sizeof(SmootherConst) / 4, DYN_KC_FLOATS = sizeof(KneeConst) / 4;
 constexpr int DYN_ROW_FLOATS = DYN_MAX_STAGES * (2 * DYN_SC_FLOATS + DYN_KC_FLOATS);  // per-row table
@@ -149,13 +151,10 @@ __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, f
             u[i] = fmaf(-aN, lagv, u[i]);
         }
     }
-    // zero-state pass
+    // zero-state pass (on the un-scaled input: the factor 1 - alpha is applied once, at the end)
     float w = 0.f;
 #pragma unroll
-    for (int i = 0; i < S; ++i) {
-        u[i] *= oma;
-        w = fmaf(alpha, w, u[i]);
-    }
+    for (int i = 0; i < S; ++i) w = fmaf(alpha, w, u[i]);
     float z = w;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -172,12 +171,12 @@ __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, f
     for (int q = 0; q < cx.warp; ++q) s = fmaf(aW, s, wt[q]);
     float ex = __shfl_up_sync(0xffffffffu, z, 1);
     if (cx.lane == 0) ex = 0.f;
-    float y = fmaf(c.pl[cx.lane], s, ex);  // T[-1] of this chunk
-    // true pass + relu
+    float y = fmaf(c.pl[cx.lane], s, ex);  // (un-scaled) T[-1] of this chunk
+    // true pass, scale, relu
 #pragma unroll
     for (int i = 0; i < S; ++i) {
         y = fmaf(alpha, y, u[i]);
-        u[i] = fmaxf(y, 0.f);
+        u[i] = fmaxf(y * oma, 0.f);
     }
     if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles) p.state[(size_t)cx.row * 2 * p.n_stages + slot] = y;
 }
@@ -193,23 +192,34 @@ __device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParam
     ensure_state(cx, p);
     __syncthreads();
     if (cx.tid == 0) {
+        // the recursion is a dependent chain (2 FFMA + compare + select per sample): keep everything else off
+        // it -- a chunk's loads are issued together one chunk ahead, at*u / rt*u do not depend on y
         float y = cx.s_state[slot];
         const float omat = 1.f - at, omrt = 1.f - rt;
+        float4 cur[8], nxt[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cur[c] = cx.work4[swz_unit(0, c)];
 #pragma unroll 1
         for (int r = 0; r < NT; ++r) {
+            const int rn = r + 1 < NT ? r + 1 : r;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) nxt[c] = cx.work4[swz_unit(rn, c)];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const int idx = swz_unit(r, c);
-                float4 v = cx.work4[idx];
-                float* e = reinterpret_cast<float*>(&v);
+                float* e = reinterpret_cast<float*>(&cur[c]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float ya = fmaf(omat, y, at * e[k]);
-                    const float yr = fmaf(omrt, y, rt * e[k]);
+                    const float ua = at * e[k], ur = rt * e[k];
+                    const float ya = fmaf(omat, y, ua);
+                    const float yr = fmaf(omrt, y, ur);
                     y = e[k] < y ? ya : yr;
                     e[k] = y;
                 }
-                cx.work4[idx] = v;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                cx.work4[swz_unit(r, c)] = cur[c];
+                cur[c] = nxt[c];
             }
         }
     }
@@ -222,6 +232,59 @@ __device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParam
     if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles) {
         // the state after the last sample of a FULL tile (partial tiles are always the last)
         p.state[(size_t)cx.row * 2 * p.n_stages + slot] = u[31];
+    }
+}
+
+// bare SFU ops (no denormal / range fix-up code around them: the arguments here are >= 1e-5 resp. bounded)
+__device__ __forceinline__ float lg2_fast(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float ex2_fast(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+constexpr float DYN_LN2 = 0.69314718055994531f, DYN_LOG2E = 1.4426950408889634f;
+
+// u[i] (smoothed energy) -> LINEAR gain exp(G_out - G) of the knee, for stages without a gain smoother: the
+// log runs in base 2 (one MUFU), the knee scales carry log2(e), the exp is one ex2.
+__device__ __forceinline__ void knee_gain(float (&u)[32], const KneeConst& k, int mode) {
+    const float T = k.T, W = k.W, slope = k.slope2, mid = k.mid2, es = k.exp2s, Wl = k.Wl2;
+    switch (mode) {
+        case 0:
+        case 3:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = ex2_fast(fminf(0.f, fmaf(lg2_fast(u[i] + 1e-5f), DYN_LN2, -T) * slope));
+            break;
+        case 1:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float d = fmaf(lg2_fast(u[i] + 1e-5f), DYN_LN2, -T), e = d + W;
+                const float m = mid * e * e;
+                u[i] = ex2_fast(d > W ? d * slope : (d < -W ? 0.f : m));
+            }
+            break;
+        case 4:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float d = fmaf(lg2_fast(u[i] + 1e-5f), DYN_LN2, -T), e = d - W;
+                const float m = mid * e * e;
+                u[i] = ex2_fast(d < -W ? d * slope : (d > W ? 0.f : m));
+            }
+            break;
+        default: {  // exponential knees: scale * softplus(+-W d), softplus(v) = ln2 * lg2(1 + ex2(v log2e))
+            const float sg = mode == 2 ? Wl : -Wl;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float d = fmaf(lg2_fast(u[i] + 1e-5f), DYN_LN2, -T);
+                const float v = sg * d;  // = (+-W d) log2(e)
+                const float sp = v > 28.f ? v * DYN_LN2 : DYN_LN2 * lg2_fast(1.f + ex2_fast(v));
+                u[i] = ex2_fast(es * sp);
+            }
+            break;
+        }
     }
 }
 
@@ -317,6 +380,8 @@ __global__ void dynamics_tables_kernel(const DynParams p, float* __restrict__ ta
     k.slope = sd.kind == 0 ? (inv_ratio - 1.f) : (ratio - 1.f);
     k.mid_scale = (sd.kind == 0 ? (inv_ratio - 1.f) : (1.f - ratio)) / (4.f * k.W);
     k.exp_scale = (sd.kind == 0 ? (inv_ratio - 1.f) : -elr) / k.W;
+    k.slope2 = k.slope * DYN_LOG2E; k.mid2 = k.mid_scale * DYN_LOG2E; k.exp2s = k.exp_scale * DYN_LOG2E;
+    k.Wl2 = k.W * DYN_LOG2E;
     float* dst = base + 2 * DYN_MAX_STAGES * DYN_SC_FLOATS + d * DYN_KC_FLOATS;
     for (int i = 0; i < DYN_KC_FLOATS; ++i) dst[i] = reinterpret_cast<const float*>(&k)[i];
 }
@@ -362,7 +427,21 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
             constexpr int k4 = DYN_MAX_STAGES * 2 * DYN_SC_FLOATS / 4;
             for (int i = cx.tid; i < p.n_stages * DYN_KC_FLOATS / 4; i += NT) cp_async16(consts + 4 * (k4 + i), trow + k4 + i, 16);
         }
-        if (p.aligned) {
+        const bool full_tile = p.aligned && cx.remain >= TILE;
+        if (full_tile) {
+            // interior tile: unit g = tid + j NT sits at swz_unit(g >> 3, g & 7) = swz_unit(tid >> 3, tid & 7) + j NT
+            // (NT is a multiple of 64), so the copies are a constant stride apart
+            const uint32_t d0 = smem_u32(cx.xs4 + swz_unit(cx.tid >> 3, cx.tid & 7));
+            for (int c = 0; c < C; ++c) {
+                const float4* src = reinterpret_cast<const float4*>(xrow + (size_t)c * p.L + cx.t0) + cx.tid;
+                const uint32_t dc = d0 + (uint32_t)c * (NT * 128);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dc + (uint32_t)j * (NT * 16)), "l"(src + j * NT));
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        } else if (p.aligned) {
             for (int c = 0; c < C; ++c) {
                 const float* xr = xrow + (size_t)c * p.L;
 #pragma unroll
@@ -428,14 +507,13 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
                     smooth_iir<NT>(cx, p, u, sd.pre, 2 * d, lag);
                 }
             } else if (sd.pre.kind == 2) {
-                smooth_ballistics<NT>(cx, p, u, sd.pre, 2 * d);
+                if constexpr (NT == 64) smooth_ballistics<NT>(cx, p, u, sd.pre, 2 * d);  // (ballistics launches use NT = 64)
             }
 
-            knee_log_gain(u, cx.kc[d], sd.kind * 3 + sd.knee);
             if (sd.post.kind == 0) {
-#pragma unroll
-                for (int i = 0; i < S; ++i) u[i] = __expf(u[i]);
+                knee_gain(u, cx.kc[d], sd.kind * 3 + sd.knee);
             } else {
+                knee_log_gain(u, cx.kc[d], sd.kind * 3 + sd.knee);
                 if (!sd.log_domain) {
 #pragma unroll
                     for (int i = 0; i < S; ++i) u[i] = __expf(u[i]);
@@ -445,7 +523,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
                     auto lag = [&](long long pos) { return __ldcg(hr + pos); };
                     smooth_iir<NT>(cx, p, u, sd.post, 2 * d + 1, lag);
                 } else {
-                    smooth_ballistics<NT>(cx, p, u, sd.post, 2 * d + 1);
+                    if constexpr (NT == 64) smooth_ballistics<NT>(cx, p, u, sd.post, 2 * d + 1);
                 }
                 if (sd.log_domain) {
 #pragma unroll
@@ -469,7 +547,12 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
         __syncthreads();
         for (int c = 0; c < C; ++c) {
             float* yr = yrow + (size_t)c * p.L;
-            if (p.aligned) {
+            if (full_tile) {
+                float4* dst = reinterpret_cast<float4*>(yr + cx.t0) + cx.tid;
+                const float4* sv = cx.xs4 + (size_t)c * NT * 8 + swz_unit(cx.tid >> 3, cx.tid & 7);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) stg_stream(dst + j * NT, sv[j * NT]);
+            } else if (p.aligned) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int g = cx.tid + j * NT;
