@@ -20,6 +20,9 @@
 //       X-block and H-partition spectra (FFT kernels) -> per-bin multiply-accumulate over the
 //       partitions (streaming kernel, filter and input history in registers: each spectrum is read
 //       once) -> inverse FFT kernel.
+// The first forward pass reads its inputs straight from global memory, the last inverse pass writes straight to
+// global memory, and the stride-1 pass is fused in registers with the real-FFT pair algebra (and, for short
+// filters, with the spectral multiply): a block costs 2 passes' worth of shared-memory traffic less per direction.
 // Twiddles: per pass only w^j, w^2j, w^3j (and w^4j, w^8j, w^12j for radix 16) come from a small
 // L1-resident table built in double (gfx_fft_plan_init); the other radix-16 twiddles are products.
 #include "common.cuh"
@@ -102,8 +105,90 @@ __host__ __device__ __forceinline__ int pair_pos(int q) { return ((q >> 3) << 4)
 __device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
 __host__ __device__ constexpr int fft_smem_slots(int n) { return n + n / 16 + 16; }
 
-template <int N, int NT, int S, bool INV>
-__device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan) {
+// Thread organisation: NT = N/32 threads per transform; every radix-16 pass has N/16 = 2 NT butterflies
+// (two per thread).  The first pass takes its inputs straight from global memory, the last inverse pass
+// writes its outputs straight to global memory, and the last forward / first inverse pass (stride 1: a
+// butterfly = 16 consecutive positions) is fused, in registers, with the real-FFT pair algebra:
+//   position 16 b + r holds bin  klow(b) + (N/16) r;   bin N - k sits in butterfly b' = b(N/16 - klow) at 15 - r,
+// so a thread that owns the two butterflies {bA, bB = partner(bA)} (plan "pair table", thread 0 owns the two
+// self-paired ones) holds both members of 16 pairs.  Pair slot numbering (shared by every spectrum in HBM):
+//   slot(t, half, rk) = half N/4 + rk N/32 + t    (half 0: bin klow(bA) + (N/16) rk, rk < 8;  half 1: same for bB)
+// -> for fixed (half, rk) consecutive threads touch consecutive float4: coalesced.  Slot 0 = DC/Nyquist.
+#define OUT16(r) (4 * ((r) & 3) + ((r) >> 2))  // register of r16<>'s output index r
+
+// plan memory: [ pair half-twiddles by slot: n/2 float2 | pass tables: plan_total(n) float2 | pair table: n/32 ushort2 ]
+template <int N>
+__device__ __forceinline__ const ushort2* plan_pairtab(const float2* plan) {
+    return reinterpret_cast<const ushort2*>(plan + N / 2 + plan_total(N));
+}
+
+// ---- sources / sinks of the fused first / last passes
+__device__ __forceinline__ pk2 ldg_pk(const float* p) {
+    pk2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_pk(float* p, pk2 v) {
+    asm volatile("st.global.L1::no_allocate.b64 [%0], %1;" ::"l"(p), "l"(v));
+}
+
+// reads block-relative real samples (2c, 2c+1) of a row segment starting at s0 (zero outside [0, len))
+struct SegSrc {
+    const float* base;  // row + s0
+    int lo, hi;         // valid block-relative sample range [lo, hi)
+    bool fast;          // 8-byte aligned pairs, lo / hi even
+    __device__ __forceinline__ SegSrc(const float* row, long long s0, long long len, int span, bool aligned8) {
+        base = row + s0;
+        const long long l = s0 < 0 ? -s0 : 0, h = len - s0;
+        lo = l > span ? span : (int)l;
+        hi = h > span ? span : (h < 0 ? 0 : (int)h);
+        fast = aligned8 && ((s0 & 1) == 0) && ((lo & 1) == 0) && ((hi & 1) == 0);
+    }
+    __device__ __forceinline__ pk2 get(int c) const {
+        const int i = 2 * c;
+        if (fast) return (i >= lo && i < hi) ? ldg_pk(base + i) : 0ull;
+        const float a = (i >= lo && i < hi) ? __ldg(base + i) : 0.f;
+        const float b = (i + 1 >= lo && i + 1 < hi) ? __ldg(base + i + 1) : 0.f;
+        return pk_make(a, b);
+    }
+};
+// writes block-relative real samples (2c, 2c+1), restricted to the window [w_lo, w_hi) of the block, to
+// dst[pos0 + (i - w_lo)], clipped to [0, len)
+struct SegDst {
+    float* base;  // row + pos0 - w_lo  (indexable by the block-relative sample index)
+    int lo, hi;   // writable block-relative sample range
+    bool fast;
+    __device__ __forceinline__ SegDst(float* row, long long pos0, long long len, int w_lo, int w_hi, bool aligned8) {
+        const long long off = pos0 - w_lo;  // global position of block-relative sample 0
+        base = row + off;
+        long long l = -off, h = len - off;
+        if (l < w_lo) l = w_lo;
+        if (h > w_hi) h = w_hi;
+        if (h < l) h = l;
+        lo = (int)l; hi = (int)h;
+        fast = aligned8 && ((off & 1) == 0) && ((lo & 1) == 0) && ((hi & 1) == 0);
+    }
+    __device__ __forceinline__ void put(int c, pk2 v) const {
+        const int i = 2 * c;
+        if (fast) {
+            if (i >= lo && i < hi) stg_pk(base + i, v);
+            return;
+        }
+        float a, b;
+        pk_split(v, a, b);
+        if (i >= lo && i < hi) base[i] = a;
+        if (i + 1 >= lo && i + 1 < hi) base[i + 1] = b;
+    }
+};
+struct NoSrc { __device__ __forceinline__ pk2 get(int) const { return 0ull; } };
+struct NoDst { __device__ __forceinline__ void put(int, pk2) const {} };
+
+// One FFT pass over shared memory (see the plan tables).  FROM_GLOBAL (forward pass 0 only): inputs come from
+// `src` (complex index c = b + (N/16) q); TO_GLOBAL (inverse pass 0 only): outputs go to `dst`.
+template <int N, int NT, int S, bool INV, bool FROM_GLOBAL = false, bool TO_GLOBAL = false, typename Src = NoSrc,
+          typename Dst = NoDst>
+__device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan, const Src& src = Src(),
+                                         const Dst& dst = Dst()) {
     constexpr int R = plan_radix(N, S);
     constexpr int M = plan_m(N, S);
     constexpr int ST = M / R;
@@ -111,7 +196,8 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan
     // slot of element q of a butterfly: pidx(i0 + q ST) = pidx(i0) + q * PST  (ST is a multiple of 16, or 1)
     constexpr int PST = ST >= 16 ? ST + ST / 16 : 1;
     static_assert(ST == 1 || ST % 16 == 0, "stride must keep the padding pattern linear");
-#pragma unroll (R == 2 ? 4 : 1)
+    static_assert(!(FROM_GLOBAL || TO_GLOBAL) || (S == 0 && R == 16), "fused passes are the radix-16 pass 0");
+#pragma unroll(R == 2 ? 4 : 1)
     for (int b = threadIdx.x; b < N / R; b += NT) {
         const int j = b & (ST - 1);
         const int i0 = (b - j) * R + j;
@@ -146,7 +232,10 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan
             }
             pk2 a[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) a[q] = zb[q * PST];
+            for (int q = 0; q < 16; ++q) {
+                if constexpr (FROM_GLOBAL) a[q] = src.get(b + ST * q);
+                else a[q] = zb[q * PST];
+            }
             if constexpr (INV && ST > 1) {
 #pragma unroll
                 for (int q = 1; q < 16; ++q) {
@@ -169,266 +258,151 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan
                             v = tw_apply<false>(v, w);
                         }
                     }
-                    zb[r * PST] = v;
+                    if constexpr (TO_GLOBAL) dst.put(b + ST * r, v);
+                    else zb[r * PST] = v;
                 }
             }
         }
     }
 }
 
-template <int N, int NT>
-__device__ __forceinline__ void fft_forward(pk2* z, const float2* __restrict__ plan) {
-    fft_pass<N, NT, 0, false>(z, plan);
+// forward passes 0 .. last-1 (pass 0 reads global memory); ends with a barrier
+template <int N, int NT, typename Src>
+__device__ __forceinline__ void fft_forward_front(pk2* z, const float2* __restrict__ plan, const Src& src) {
+    fft_pass<N, NT, 0, false, true, false, Src>(z, plan, src);
     __syncthreads();
     fft_pass<N, NT, 1, false>(z, plan);
     __syncthreads();
-    fft_pass<N, NT, 2, false>(z, plan);
-    __syncthreads();
     if constexpr (plan_stages(N) > 3) {
-        fft_pass<N, NT, 3, false>(z, plan);
+        fft_pass<N, NT, 2, false>(z, plan);
         __syncthreads();
     }
 }
-template <int N, int NT>
-__device__ __forceinline__ void fft_inverse(pk2* z, const float2* __restrict__ plan) {
+// inverse passes last-1 .. 0 (pass 0 writes global memory); starts with a barrier
+template <int N, int NT, typename Dst>
+__device__ __forceinline__ void fft_inverse_back(pk2* z, const float2* __restrict__ plan, const Dst& dst) {
+    __syncthreads();
     if constexpr (plan_stages(N) > 3) {
-        fft_pass<N, NT, 3, true>(z, plan);
+        fft_pass<N, NT, 2, true>(z, plan);
         __syncthreads();
     }
-    fft_pass<N, NT, 2, true>(z, plan);
-    __syncthreads();
     fft_pass<N, NT, 1, true>(z, plan);
     __syncthreads();
-    fft_pass<N, NT, 0, true>(z, plan);
-    __syncthreads();
+    fft_pass<N, NT, 0, true, false, true, NoSrc, Dst>(z, plan, NoSrc(), dst);
 }
 
-__device__ __forceinline__ float2 ld_c(const pk2* z, int i) {
-    float re, im;
-    pk_split(z[pidx(i)], re, im);
-    return make_float2(re, im);
-}
-__device__ __forceinline__ void st_c(pk2* z, int i, float re, float im) { z[pidx(i)] = pk_make(re, im); }
-
-// plan memory: [ pair half-twiddles: n/2 float2 | pass tables: plan_total(n) float2 | partner positions: n/2 u16 ]
-//   partner[q] = position of bin n - k(q): the slot the real-FFT algebra couples with pair_pos(q)
-template <int N>
-__device__ __forceinline__ const unsigned short* plan_partner(const float2* plan) {
-    return reinterpret_cast<const unsigned short*>(plan + N / 2 + plan_total(N));
-}
-
-// The three pair loops below run in batches of PB slots: all global / table loads of a batch are issued
-// before the first use (the loops are latency-, not throughput-limited otherwise).
-constexpr int PB = 4;
-
-// smem FFT output -> pair slots in global memory (scaled)
-template <int N, int NT>
-__device__ __forceinline__ void untangle_store(const pk2* z, const float2* __restrict__ plan, float4* __restrict__ out,
-                                               float scale) {
-    const unsigned short* partner = plan_partner<N>(plan);
-    static_assert((N / 2) % (NT * PB) == 0, "pair loop batches");
-#pragma unroll 1
-    for (int q0 = threadIdx.x; q0 < N / 2; q0 += NT * PB) {
-        float2 w[PB];
-        int pm[PB];
+// ---- the fused last forward / first inverse pass
+// forward: butterfly b from smem -> r16 -> registers (output index r in a[OUT16(r)])
+__device__ __forceinline__ void last_forward(const pk2* z, int b, pk2 (&a)[16]) {
+    const pk2* zb = z + 17 * b;
 #pragma unroll
-        for (int u = 0; u < PB; ++u) {
-            w[u] = __ldg(plan + q0 + u * NT);
-            pm[u] = __ldg(partner + q0 + u * NT);
-        }
+    for (int q = 0; q < 16; ++q) a[q] = zb[q];
+    r16<false>(a);
+}
+// inverse: registers (index r in a[OUT16(r)]) -> r16 inverse -> smem butterfly b
+__device__ __forceinline__ void first_inverse(pk2* z, int b, const pk2 (&a)[16]) {
+    pk2 in[16];
 #pragma unroll
-        for (int u = 0; u < PB; ++u) {
-            const int q = q0 + u * NT;
-            float4 o;
-            if (q == 0) {
-                const float2 z0 = ld_c(z, 0), zh = ld_c(z, 8);
-                o = make_float4((z0.x + z0.y) * scale, (z0.x - z0.y) * scale, zh.x * scale, -zh.y * scale);
-            } else {
-                const PairA a = untangle_pair(ld_c(z, pair_pos(q)), ld_c(z, pm[u]), w[u]);
-                o = make_float4(a.k.x * scale, a.k.y * scale, a.m.x * scale, a.m.y * scale);
-            }
-            out[q] = o;
-        }
+    for (int q = 0; q < 16; ++q) in[q] = a[OUT16(q)];
+    r16<true>(in);
+    pk2* zb = z + 17 * b;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) zb[r] = in[OUT16(r)];
+}
+
+// pair operators: what happens to (Z_k, Z_{N-k}) once both are in registers
+struct OpSpectrum {  // untangle -> global pair slot (scaled)
+    float4* out;
+    float scale;
+    typedef int Data;
+    __device__ __forceinline__ Data fetch(int) const { return 0; }
+    __device__ __forceinline__ void pair(pk2& zk, pk2& zm, float2 w, Data, int slot) const {
+        float a, b, c, d;
+        pk_split(zk, a, b);
+        pk_split(zm, c, d);
+        const PairA x = untangle_pair(make_float2(a, b), make_float2(c, d), w);
+        out[slot] = make_float4(x.k.x * scale, x.k.y * scale, x.m.x * scale, x.m.y * scale);
     }
-}
-
-// pair slots in global memory -> packed spectrum in smem, ready for the inverse FFT
-template <int N, int NT>
-__device__ __forceinline__ void retangle_load(pk2* z, const float2* __restrict__ plan, const float4* __restrict__ Y) {
-    const unsigned short* partner = plan_partner<N>(plan);
-    constexpr int YB = 8;
-    static_assert((N / 2) % (NT * YB) == 0, "pair loop batches");
-#pragma unroll 1
-    for (int q0 = threadIdx.x; q0 < N / 2; q0 += NT * YB) {
-        float4 y[YB];
-        float2 w[YB];
-        int pm[YB];
-#pragma unroll
-        for (int u = 0; u < YB; ++u) y[u] = ldg_stream(Y + q0 + u * NT);
-#pragma unroll
-        for (int u = 0; u < YB; ++u) {
-            w[u] = __ldg(plan + q0 + u * NT);
-            pm[u] = __ldg(partner + q0 + u * NT);
-        }
-#pragma unroll
-        for (int u = 0; u < YB; ++u) {
-            const int q = q0 + u * NT;
-            if (q == 0) {
-                st_c(z, 0, 0.5f * (y[u].x + y[u].y), 0.5f * (y[u].x - y[u].y));
-                st_c(z, 8, y[u].z, -y[u].w);
-            } else {
-                const PairA a = retangle_pair(make_float2(y[u].x, y[u].y), make_float2(y[u].z, y[u].w), w[u]);
-                st_c(z, pair_pos(q), a.k.x, a.k.y);
-                st_c(z, pm[u], a.m.x, a.m.y);
-            }
-        }
+    __device__ __forceinline__ void dc(pk2& z0, pk2& zh, Data, int slot) const {
+        float a, b, c, d;
+        pk_split(z0, a, b);
+        pk_split(zh, c, d);
+        out[slot] = make_float4((a + b) * scale, (a - b) * scale, c * scale, -d * scale);
     }
-}
-
-// fused in place: untangle X, multiply by the (already 1/N-scaled) filter spectrum H (pair slots), retangle
-template <int N, int NT>
-__device__ __forceinline__ void pointwise_filter(pk2* z, const float2* __restrict__ plan, const float4* __restrict__ H) {
-    const unsigned short* partner = plan_partner<N>(plan);
-#pragma unroll 1
-    for (int q0 = threadIdx.x; q0 < N / 2; q0 += NT * PB) {
-        float4 h[PB];
-        float2 w[PB];
-        int pm[PB];
-#pragma unroll
-        for (int u = 0; u < PB; ++u) {
-            h[u] = __ldg(H + q0 + u * NT);
-            w[u] = __ldg(plan + q0 + u * NT);
-            pm[u] = __ldg(partner + q0 + u * NT);
-        }
-#pragma unroll
-        for (int u = 0; u < PB; ++u) {
-            const int q = q0 + u * NT;
-            if (q == 0) {
-                const float2 z0 = ld_c(z, 0), zh = ld_c(z, 8);
-                const float y0 = (z0.x + z0.y) * h[u].x, yn = (z0.x - z0.y) * h[u].y;
-                st_c(z, 0, 0.5f * (y0 + yn), 0.5f * (y0 - yn));
-                // X_{N/2} = conj(Z), Y = X H, Z' = conj(Y) = Z conj(H)
-                const float2 r2 = cmulc(zh, make_float2(h[u].z, h[u].w));
-                st_c(z, 8, r2.x, r2.y);
-            } else {
-                const int p = pair_pos(q);
-                const PairA x = untangle_pair(ld_c(z, p), ld_c(z, pm[u]), w[u]);
-                const PairA y = retangle_pair(cmul(x.k, make_float2(h[u].x, h[u].y)),
-                                              cmul(x.m, make_float2(h[u].z, h[u].w)), w[u]);
-                st_c(z, p, y.k.x, y.k.y);
-                st_c(z, pm[u], y.m.x, y.m.y);
-            }
-        }
+};
+struct OpFilter {  // untangle, multiply by the (1/N-scaled) filter spectrum, retangle -- in place
+    const float4* H;
+    typedef float4 Data;
+    __device__ __forceinline__ Data fetch(int slot) const { return __ldg(H + slot); }
+    __device__ __forceinline__ void pair(pk2& zk, pk2& zm, float2 w, Data h, int) const {
+        float a, b, c, d;
+        pk_split(zk, a, b);
+        pk_split(zm, c, d);
+        const PairA x = untangle_pair(make_float2(a, b), make_float2(c, d), w);
+        const PairA y = retangle_pair(cmul(x.k, make_float2(h.x, h.y)), cmul(x.m, make_float2(h.z, h.w)), w);
+        zk = pk_make(y.k.x, y.k.y);
+        zm = pk_make(y.m.x, y.m.y);
     }
-}
+    __device__ __forceinline__ void dc(pk2& z0, pk2& zh, Data h, int) const {
+        float a, b, c, d;
+        pk_split(z0, a, b);
+        pk_split(zh, c, d);
+        const float y0 = (a + b) * h.x, yn = (a - b) * h.y;
+        z0 = pk_make(0.5f * (y0 + yn), 0.5f * (y0 - yn));
+        // X_{N/2} = conj(Z), Y = X H, Z' = conj(Y) = Z conj(H)
+        const float2 r2 = cmulc(make_float2(c, d), make_float2(h.z, h.w));
+        zh = pk_make(r2.x, r2.y);
+    }
+};
+struct OpLoad {  // global pair slot -> retangle -> registers
+    const float4* Y;
+    typedef float4 Data;
+    __device__ __forceinline__ Data fetch(int slot) const { return ldg_stream(Y + slot); }
+    __device__ __forceinline__ void pair(pk2& zk, pk2& zm, float2 w, Data y, int) const {
+        const PairA a = retangle_pair(make_float2(y.x, y.y), make_float2(y.z, y.w), w);
+        zk = pk_make(a.k.x, a.k.y);
+        zm = pk_make(a.m.x, a.m.y);
+    }
+    __device__ __forceinline__ void dc(pk2& z0, pk2& zh, Data y, int) const {
+        z0 = pk_make(0.5f * (y.x + y.y), 0.5f * (y.x - y.y));
+        zh = pk_make(y.z, -y.w);
+    }
+};
 
-// ------------------------------------------------------------------ segment load / store
-// loads F = 2N real samples src[s0 .. s0+F) (zero outside [0, len)) as z[j] = x[2j] + i x[2j+1];
-// with src2 != nullptr the sample is src + sgn2 * src2 (mid/side -> left/right of a reverb IR).
-template <int N, int NT>
-__device__ __forceinline__ void load_packed(pk2* z, const float* __restrict__ src, const float* __restrict__ src2,
-                                            float sgn2, long long s0, long long len, bool vec_ok) {
-    if (vec_ok && (s0 & 3) == 0 && src2 == nullptr && s0 >= 0 && s0 + 2 * N <= len) {
-        // interior segment: asynchronous copies straight into the packed layout, the whole segment in flight
-        // at once (two 8-byte halves per 16 bytes: the padded slots are only 8-byte aligned); the slot of
-        // t = tid + i NT is linear in i (NT is a multiple of 8), so the unrolled loop has no index math
-        // one complex point (8 bytes) per copy, consecutive lanes -> consecutive points: a warp's copy is
-        // contiguous in global memory and (up to one pad slot) in shared memory: no bank conflicts
-        static_assert(NT % 16 == 0 && N % NT == 0, "load tiling");
-        const float* g = src + s0 + 2 * (int)threadIdx.x;
-        const uint32_t d = smem_u32(z) + 8u * (uint32_t)pidx((int)threadIdx.x);
+// all 16 pairs of a thread; A / B = the r16 output registers of its butterflies bA / bB
+template <int N, typename Op>
+__device__ __forceinline__ void pair_phase(pk2 (&A)[16], pk2 (&B)[16], int t, const float2* __restrict__ plan, const Op& op) {
+    constexpr int NTT = N / 32, Q = N / 4;
 #pragma unroll
-        for (int i = 0; i < N / NT; ++i)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d + 8u * (uint32_t)(i * (NT + NT / 16))),
-                         "l"(g + i * 2 * NT));
-        cp_async_commit();
-        cp_async_wait<0>();
-    } else if (vec_ok && (s0 & 3) == 0 && src2 == nullptr) {
-        // segment crossing the start / end of the row: same copies with zero fill
-#pragma unroll 4
-        for (int t = threadIdx.x; t < N / 2; t += NT) {
-            const long long pos = s0 + 4LL * t;
-            const long long rem = (pos >= 0) ? (len - pos) : 0;  // samples available from pos on (a 4-group never straddles 0)
-            const int b0 = rem >= 2 ? 8 : (rem > 0 ? (int)rem * 4 : 0);
-            const int b1 = rem >= 4 ? 8 : (rem > 2 ? (int)(rem - 2) * 4 : 0);
-            const float* g = (rem > 0) ? src + pos : src;
-            cp_async8(&z[pidx(2 * t)], g, b0);
-            cp_async8(&z[pidx(2 * t + 1)], b1 > 0 ? g + 2 : src, b1);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-    } else if (vec_ok && (s0 & 3) == 0) {
-#pragma unroll 4
-        for (int t = threadIdx.x; t < N / 2; t += NT) {
-            const long long pos = s0 + 4LL * t;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pos >= 0 && pos + 4 <= len) {
-                v = ldg_stream(reinterpret_cast<const float4*>(src + pos));
-                if (src2) {
-                    const float4 u = ldg_stream(reinterpret_cast<const float4*>(src2 + pos));
-                    v.x = fmaf(sgn2, u.x, v.x); v.y = fmaf(sgn2, u.y, v.y); v.z = fmaf(sgn2, u.z, v.z); v.w = fmaf(sgn2, u.w, v.w);
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            float2 w[4];
+            typename Op::Data d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int slot = h * Q + (4 * g + u) * NTT + t;
+                w[u] = __ldg(plan + slot);
+                d[u] = op.fetch(slot);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rk = 4 * g + u;
+                const int slot = h * Q + rk * NTT + t;
+                if (t != 0) {
+                    // bin klow(b) + (N/16) rk of one butterfly pairs with index 15 - rk of the other
+                    if (h == 0) op.pair(A[OUT16(rk)], B[OUT16(15 - rk)], w[u], d[u], slot);
+                    else op.pair(B[OUT16(rk)], A[OUT16(15 - rk)], w[u], d[u], slot);
+                } else {
+                    // thread 0: bA = butterfly of klow 0 (pairs rk <-> 16 - rk, rk = 0: DC / Nyquist with index 8),
+                    //           bB = butterfly of klow N/32 (pairs rk <-> 15 - rk)
+                    if (h == 0) {
+                        if (rk == 0) op.dc(A[OUT16(0)], A[OUT16(8)], d[u], slot);
+                        else op.pair(A[OUT16(rk)], A[OUT16((16 - rk) & 15)], w[u], d[u], slot);
+                    } else {
+                        op.pair(B[OUT16(rk)], B[OUT16(15 - rk)], w[u], d[u], slot);
+                    }
                 }
-            } else if (pos + 4 > 0 && pos < len) {
-                float e[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const bool in = (pos + c >= 0 && pos + c < len);
-                    e[c] = in ? src[pos + c] : 0.f;
-                    if (in && src2) e[c] = fmaf(sgn2, src2[pos + c], e[c]);
-                }
-                v = make_float4(e[0], e[1], e[2], e[3]);
-            }
-            z[pidx(2 * t)] = pk_make(v.x, v.y);
-            z[pidx(2 * t + 1)] = pk_make(v.z, v.w);
-        }
-    } else {
-        for (int j = threadIdx.x; j < N; j += NT) {
-            const long long pos = s0 + 2LL * j;
-            float a = 0.f, b = 0.f;
-            if (pos >= 0 && pos < len) { a = src[pos]; if (src2) a = fmaf(sgn2, src2[pos], a); }
-            if (pos + 1 >= 0 && pos + 1 < len) { b = src[pos + 1]; if (src2) b = fmaf(sgn2, src2[pos + 1], b); }
-            z[pidx(j)] = pk_make(a, b);
-        }
-    }
-}
-
-// writes segment samples [i_lo, i_lo + count) to dst[d0 .. d0+count), clipped to [0, len)
-template <int N, int NT>
-__device__ __forceinline__ void store_packed(const pk2* z, float* __restrict__ dst, int i_lo, int count, long long d0,
-                                             long long len, bool vec_ok) {
-    if (vec_ok && (i_lo & 3) == 0 && (d0 & 3) == 0 && (count & 3) == 0 && d0 >= 0 && d0 + count <= len) {
-        // interior block: no clipping, 32-bit index math
-        float* o = dst + d0;
-        const int h_lo = i_lo >> 1;
-#pragma unroll 4
-        for (int t = threadIdx.x; t < count / 4; t += NT) {
-            const int c = h_lo + 2 * t;  // complex index of the first of the two packed points
-            float a0, a1, b0, b1;
-            pk_split(z[pidx(c)], a0, a1);
-            pk_split(z[pidx(c + 1)], b0, b1);
-            stg_stream(reinterpret_cast<float4*>(o + 4 * t), make_float4(a0, a1, b0, b1));
-        }
-    } else if (vec_ok && (i_lo & 3) == 0 && (d0 & 3) == 0 && (count & 3) == 0) {
-#pragma unroll 4
-        for (int t = threadIdx.x; t < count / 4; t += NT) {
-            const int i = i_lo + 4 * t;
-            const long long pos = d0 + 4LL * t;
-            const float2 a = ld_c(z, i >> 1), b = ld_c(z, (i >> 1) + 1);
-            if (pos >= 0 && pos + 4 <= len) {
-                stg_stream(reinterpret_cast<float4*>(dst + pos), make_float4(a.x, a.y, b.x, b.y));
-            } else {
-                const float e[4] = {a.x, a.y, b.x, b.y};
-                for (int c = 0; c < 4; ++c)
-                    if (pos + c >= 0 && pos + c < len) dst[pos + c] = e[c];
-            }
-        }
-    } else {
-        for (int t = threadIdx.x; t < count; t += NT) {
-            const int i = i_lo + t;
-            const long long pos = d0 + t;
-            if (pos >= 0 && pos < len) {
-                const float2 a = ld_c(z, i >> 1);
-                dst[pos] = (i & 1) ? a.y : a.x;
             }
         }
     }
@@ -451,64 +425,88 @@ struct FilterSrc {
     int to_lr;            // with energy: rows are left/right = mid +- side (mean-over-channels energy = e0 + e1)
 };
 
-constexpr int fir_min_blocks(int n) { return n <= 4096 ? 3 : (n <= 8192 ? 3 : 1); }
+// NT = N/32 threads; registers: two butterflies (64) + pair operands live in the fused phase
+__host__ __device__ constexpr int fir_nt(int n) { return n / 32; }
+__host__ __device__ constexpr int fir_min_blocks(int n) { return n == 1024 ? 16 : (n == 4096 ? 4 : (n == 8192 ? 2 : 1)); }
 
 // ------------------------------------------------------------------ kernels
-// spectra of filter partitions: Hs[(hrow * P + part) * N/2 + q] pair slots, scaled by 1/N (and the energy norm)
-template <int N, int NT>
-__global__ void __launch_bounds__(NT, fir_min_blocks(N)) fir_spectrum_kernel(FilterSrc fs, float4* __restrict__ Hs,
-                                                                             int hrow0, int Nh, int part_len, int P,
-                                                                             const float2* __restrict__ plan, int vec_ok) {
+// forward transform of one real segment into pair slots: shared tail of the spectrum kernels
+template <int N, typename Src>
+__device__ __forceinline__ void segment_spectrum(pk2* zbuf, const float2* __restrict__ plan, const Src& src,
+                                                 float4* __restrict__ out, float scale) {
+    constexpr int NT = fir_nt(N);
+    fft_forward_front<N, NT>(zbuf, plan, src);
+    const int t = threadIdx.x;
+    const ushort2 pr = plan_pairtab<N>(plan)[t];
+    pk2 A[16], B[16];
+    last_forward(zbuf, pr.x, A);
+    last_forward(zbuf, pr.y, B);
+    pair_phase<N>(A, B, t, plan, OpSpectrum{out, scale});
+}
+
+// spectra of filter partitions: Hs[(hrow * P + part) * N/2 + slot], scaled by 1/N (and the energy norm)
+template <int N>
+__global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_spectrum_kernel(FilterSrc fs, float4* __restrict__ Hs,
+                                                                                    int hrow0, int Nh, int part_len, int P,
+                                                                                    const float2* __restrict__ plan,
+                                                                                    int aligned8) {
     extern __shared__ __align__(16) pk2 zbuf[];
     const int hloc = blockIdx.x / P, part = blockIdx.x - hloc * P;
     const int hrow = hrow0 + hloc;
-    const size_t off = (size_t)hrow * Nh + (size_t)part * part_len;
-    long long len = (long long)Nh - (long long)part * part_len;
-    if (len > part_len) len = part_len;
+    const long long s0 = (long long)part * part_len;
+    long long end = s0 + part_len;
+    if (end > Nh) end = Nh;
     float scale = 1.f / (float)N;
     if (fs.energy) {
         // normalize_impulse of a reverb IR: one scale per batch item from the raw mid/side energies
         const float e0 = fs.energy[hrow & ~1], e1 = fs.energy[hrow | 1];
         scale *= fs.to_lr ? rsqrtf(e0 + e1 + 1e-12f) : rsqrtf(0.5f * (e0 + e1) + 1e-12f);
     }
-    const bool v = vec_ok && ((off & 3) == 0);
-    load_packed<N, NT>(zbuf, fs.h + off, nullptr, 0.f, 0, len, v);
-    __syncthreads();
-    fft_forward<N, NT>(zbuf, plan);
-    untangle_store<N, NT>(zbuf, plan, Hs + (size_t)blockIdx.x * (N / 2), scale);
+    const SegSrc src(fs.h + (size_t)hrow * Nh, s0, end, 2 * N, aligned8 && ((((size_t)hrow * Nh) & 1) == 0));
+    segment_spectrum<N>(zbuf, plan, src, Hs + (size_t)blockIdx.x * (N / 2), scale);
+}
+
+// UPOLS step 1: spectra of input blocks.  Xs[(rloc * nblk + j) * N/2 + slot] = rfft of x[(j-1)B, (j+1)B), B = N
+template <int N>
+__global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_xspec_kernel(const float* __restrict__ x,
+                                                                                 float4* __restrict__ Xs, int xrow0,
+                                                                                 long long L, int nblk,
+                                                                                 const float2* __restrict__ plan,
+                                                                                 int aligned8) {
+    extern __shared__ __align__(16) pk2 zbuf[];
+    const int rloc = blockIdx.x / nblk, j = blockIdx.x - rloc * nblk;
+    const size_t xr = (size_t)(xrow0 + rloc);
+    const SegSrc src(x + xr * L, ((long long)j - 1) * N, L, 2 * N, aligned8 && (((xr * L) & 1) == 0));
+    segment_spectrum<N>(zbuf, plan, src, Xs + (size_t)blockIdx.x * (N / 2), 1.f);
 }
 
 // single-partition overlap-save: block j produces full-convolution samples [j*hop, (j+1)*hop)
-template <int N, int NT>
-__global__ void __launch_bounds__(NT, fir_min_blocks(N)) fir_ols_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                                        const float4* __restrict__ Hs, RowMap rm,
-                                                                        long long L, int pre, int hop, int shift, int nblk,
-                                                                        const float2* __restrict__ plan, int vec_ok) {
+template <int N>
+__global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_ols_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                               const float4* __restrict__ Hs, RowMap rm,
+                                                                               long long L, int pre, int hop, int shift,
+                                                                               int nblk, const float2* __restrict__ plan,
+                                                                               int aligned8) {
+    constexpr int NT = fir_nt(N);
     extern __shared__ __align__(16) pk2 zbuf[];
     const int row = blockIdx.x / nblk, j = blockIdx.x - row * nblk;
     int xr, hr;
     rm.map(row, xr, hr);
     const long long m0 = (long long)j * hop;
-    load_packed<N, NT>(zbuf, x + (size_t)xr * L, nullptr, 0.f, m0 - pre, L, vec_ok);
-    __syncthreads();
-    fft_forward<N, NT>(zbuf, plan);
-    pointwise_filter<N, NT>(zbuf, plan, Hs + (size_t)hr * (N / 2));
-    __syncthreads();
-    fft_inverse<N, NT>(zbuf, plan);
-    store_packed<N, NT>(zbuf, y + (size_t)row * L, pre, hop, m0 - shift, L, vec_ok);
-}
-
-// UPOLS step 1: spectra of input blocks.  Xs[(rloc * nblk + j) * N/2 + q] = rfft of x[(j-1)B, (j+1)B), B = N
-template <int N, int NT>
-__global__ void __launch_bounds__(NT, fir_min_blocks(N)) fir_xspec_kernel(const float* __restrict__ x, float4* __restrict__ Xs,
-                                                                          int xrow0, long long L, int nblk,
-                                                                          const float2* __restrict__ plan, int vec_ok) {
-    extern __shared__ __align__(16) pk2 zbuf[];
-    const int rloc = blockIdx.x / nblk, j = blockIdx.x - rloc * nblk;
-    load_packed<N, NT>(zbuf, x + (size_t)(xrow0 + rloc) * L, nullptr, 0.f, ((long long)j - 1) * N, L, vec_ok);
-    __syncthreads();
-    fft_forward<N, NT>(zbuf, plan);
-    untangle_store<N, NT>(zbuf, plan, Xs + (size_t)blockIdx.x * (N / 2), 1.f);
+    const SegSrc src(x + (size_t)xr * L, m0 - pre, L, 2 * N, aligned8 && ((((size_t)xr * L) & 1) == 0));
+    fft_forward_front<N, NT>(zbuf, plan, src);
+    const int t = threadIdx.x;
+    const ushort2 pr = plan_pairtab<N>(plan)[t];
+    {
+        pk2 A[16], B[16];
+        last_forward(zbuf, pr.x, A);
+        last_forward(zbuf, pr.y, B);
+        pair_phase<N>(A, B, t, plan, OpFilter{Hs + (size_t)hr * (N / 2)});
+        first_inverse(zbuf, pr.x, A);  // (each thread rewrites exactly the positions it read: no barrier in between)
+        first_inverse(zbuf, pr.y, B);
+    }
+    const SegDst dst(y + (size_t)row * L, m0 - shift, L, pre, pre + hop, aligned8 && ((((size_t)row * L) & 1) == 0));
+    fft_inverse_back<N, NT>(zbuf, plan, dst);
 }
 
 // UPOLS step 2: Y_j = sum_p X_{j-p} H_p on pair slots, partitions [p0, p0 + PC).  One thread owns one pair slot of
@@ -599,32 +597,59 @@ __global__ void __launch_bounds__(MAC_NT, 2) fir_mac_kernel(const float4* __rest
 }
 
 // UPOLS step 3: inverse FFT of Y_j, keep the second half of the block
-template <int N, int NT>
-__global__ void __launch_bounds__(NT, fir_min_blocks(N)) fir_inv_kernel(const float4* __restrict__ Ys, float* __restrict__ y,
-                                                                        int row0, long long L, int nblk, int shift,
-                                                                        const float2* __restrict__ plan, int vec_ok) {
+template <int N>
+__global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_inv_kernel(const float4* __restrict__ Ys, float* __restrict__ y,
+                                                                               int row0, long long L, int nblk, int shift,
+                                                                               const float2* __restrict__ plan, int aligned8) {
+    constexpr int NT = fir_nt(N);
     extern __shared__ __align__(16) pk2 zbuf[];
     const int rloc = blockIdx.x / nblk, j = blockIdx.x - rloc * nblk;
-    retangle_load<N, NT>(zbuf, plan, Ys + (size_t)blockIdx.x * (N / 2));
-    __syncthreads();
-    fft_inverse<N, NT>(zbuf, plan);
-    store_packed<N, NT>(zbuf, y + (size_t)(row0 + rloc) * L, N, N, (long long)j * N - shift, L, vec_ok);
+    const int t = threadIdx.x;
+    const ushort2 pr = plan_pairtab<N>(plan)[t];
+    {
+        pk2 A[16], B[16];
+        pair_phase<N>(A, B, t, plan, OpLoad{Ys + (size_t)blockIdx.x * (N / 2)});
+        first_inverse(zbuf, pr.x, A);
+        first_inverse(zbuf, pr.y, B);
+    }
+    const size_t row = (size_t)(row0 + rloc);
+    const SegDst dst(y + row * L, (long long)j * N - shift, L, N, 2 * N, aligned8 && (((row * L) & 1) == 0));
+    fft_inverse_back<N, NT>(zbuf, plan, dst);
 }
 
 // ------------------------------------------------------------------ plan construction
+// pair table: thread 0 owns the two self-paired butterflies (klow 0 and N/32); the others take the remaining
+// butterflies in increasing order together with their partners (neighbouring threads -> neighbouring
+// butterflies: few bank conflicts in the fused pass)
 template <int N>
-__global__ void fft_plan_pairs_kernel(float2* ht) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < N / 2) {
-        const int k = bin_of_pos<N>(pair_pos(q));
-        const double a = (double)k / (double)N;
-        ht[q] = make_float2((float)cospi(a), (float)(-sinpi(a)));
+__global__ void fft_plan_pairtab_kernel(ushort2* tab) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    constexpr int NB = N / 16;
+    bool used[NB];
+    for (int b = 0; b < NB; ++b) used[b] = false;
+    const int bh = pos_of_bin<N>(NB / 2) >> 4;
+    tab[0] = make_ushort2(0, (unsigned short)bh);
+    used[0] = used[bh] = true;
+    int t = 1;
+    for (int b = 1; b < NB; ++b) {
+        if (used[b]) continue;
+        const int bp = pos_of_bin<N>(NB - bin_of_pos<N>(16 * b)) >> 4;
+        tab[t++] = make_ushort2((unsigned short)b, (unsigned short)bp);
+        used[b] = used[bp] = true;
     }
 }
+// half-twiddle of every pair slot: exp(-i pi k / N), k = klow(butterfly) + (N/16) rk
 template <int N>
-__global__ void fft_plan_partner_kernel(unsigned short* partner) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < N / 2) partner[q] = q == 0 ? 8 : (unsigned short)pos_of_bin<N>(N - bin_of_pos<N>(pair_pos(q)));
+__global__ void fft_plan_pairs_kernel(float2* ht, const ushort2* __restrict__ tab) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < N / 2) {
+        constexpr int NTT = N / 32;
+        const int t = slot % NTT, rk = (slot / NTT) & 7, half = slot / (N / 4);
+        const int b = half ? tab[t].y : tab[t].x;
+        const int k = bin_of_pos<N>(16 * b) + (N / 16) * rk;
+        const double a = (double)k / (double)N;
+        ht[slot] = make_float2((float)cospi(a), (float)(-sinpi(a)));
+    }
 }
 __global__ void fft_plan_pass_kernel(float2* tab, int M, int R) {
     const int ST = M / R;
@@ -659,7 +684,7 @@ struct FirArgs {
     const float2* plan; unsigned char* ws; size_t ws_bytes; cudaStream_t stream;
 };
 
-template <int N, int NT>
+template <int N>
 static int run_ols(const FirArgs& a) {
     const int c_out = a.cx > a.ch ? a.cx : a.ch;
     const int rows = a.batch * c_out, hrows = a.batch * a.ch;
@@ -669,20 +694,20 @@ static int run_ols(const FirArgs& a) {
     const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
     static bool configured = false;
     if (!configured) {
-        if (set_smem(fir_spectrum_kernel<N, NT>, smem) || set_smem(fir_ols_kernel<N, NT>, smem)) return GFX_ERR_CUDA;
+        if (set_smem(fir_spectrum_kernel<N>, smem) || set_smem(fir_ols_kernel<N>, smem)) return GFX_ERR_CUDA;
         configured = true;
     }
-    const int hvec = ((uintptr_t)a.fs.h % 16 == 0);
-    fir_spectrum_kernel<N, NT><<<hrows, NT, smem, a.stream>>>(a.fs, Hs, 0, a.Nh, a.Nh, 1, a.plan, hvec);
+    const int hvec = ((uintptr_t)a.fs.h % 8 == 0);
+    fir_spectrum_kernel<N><<<hrows, fir_nt(N), smem, a.stream>>>(a.fs, Hs, 0, a.Nh, a.Nh, 1, a.plan, hvec);
     GFX_LAUNCH_CHECK();
     const int pre = (a.Nh - 1 + 3) & ~3;
     const int hop = (2 * N - pre) & ~3;
     const long long total = a.L + a.shift;
     const long long nblk = (total + hop - 1) / hop;
     if (nblk * rows > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
-    const int vec = (((uintptr_t)a.x | (uintptr_t)a.y) % 16 == 0) && (a.L % 4 == 0);
+    const int vec = (((uintptr_t)a.x | (uintptr_t)a.y) % 8 == 0);
     RowMap rm{c_out, a.cx, a.ch};
-    fir_ols_kernel<N, NT><<<(unsigned)(nblk * rows), NT, smem, a.stream>>>(a.x, a.y, Hs, rm, a.L, pre, hop, a.shift,
+    fir_ols_kernel<N><<<(unsigned)(nblk * rows), fir_nt(N), smem, a.stream>>>(a.x, a.y, Hs, rm, a.L, pre, hop, a.shift,
                                                                            (int)nblk, a.plan, vec);
     GFX_LAUNCH_CHECK();
     return GFX_OK;
@@ -702,7 +727,7 @@ static void launch_mac(dim3 grid, cudaStream_t st, const float4* Xs, const float
     fir_mac_kernel<PC><<<grid, MAC_NT, 0, st>>>(Xs, Hs, Ys, rm, xrow0, hrow0, row0, P, p0, nblk, half, acc);
 }
 
-template <int N, int NT>
+template <int N>
 static int run_upols(const FirArgs& a) {
     const int c_out = a.cx > a.ch ? a.cx : a.ch;
     int P; long long nblk; size_t per_item;
@@ -713,13 +738,13 @@ static int run_upols(const FirArgs& a) {
     const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
     static bool configured = false;
     if (!configured) {
-        if (set_smem(fir_spectrum_kernel<N, NT>, smem) || set_smem(fir_xspec_kernel<N, NT>, smem) ||
-            set_smem(fir_inv_kernel<N, NT>, smem)) return GFX_ERR_CUDA;
+        if (set_smem(fir_spectrum_kernel<N>, smem) || set_smem(fir_xspec_kernel<N>, smem) ||
+            set_smem(fir_inv_kernel<N>, smem)) return GFX_ERR_CUDA;
         configured = true;
     }
     constexpr int half = N / 2;
-    const int hvec = ((uintptr_t)a.fs.h % 16 == 0);
-    const int vec = (((uintptr_t)a.x | (uintptr_t)a.y) % 16 == 0) && (a.L % 4 == 0);
+    const int hvec = ((uintptr_t)a.fs.h % 8 == 0);
+    const int vec = (((uintptr_t)a.x | (uintptr_t)a.y) % 8 == 0);
     RowMap rm{c_out, a.cx, a.ch};
     for (long long b0 = 0; b0 < a.batch; b0 += chunk) {
         const int nb = (int)((a.batch - b0 < chunk) ? a.batch - b0 : chunk);
@@ -729,9 +754,9 @@ static int run_upols(const FirArgs& a) {
         const int hrow0 = (int)b0 * a.ch, xrow0 = (int)b0 * a.cx, row0 = (int)b0 * c_out;
         if ((long long)nb * a.cx * nblk > 0x7fffffffLL || (long long)nb * c_out * nblk > 0x7fffffffLL ||
             (long long)nb * c_out > 65535) return GFX_ERR_UNSUPPORTED;
-        fir_spectrum_kernel<N, NT><<<nb * a.ch * P, NT, smem, a.stream>>>(a.fs, Hs, hrow0, a.Nh, N, P, a.plan, hvec);
+        fir_spectrum_kernel<N><<<nb * a.ch * P, fir_nt(N), smem, a.stream>>>(a.fs, Hs, hrow0, a.Nh, N, P, a.plan, hvec);
         GFX_LAUNCH_CHECK();
-        fir_xspec_kernel<N, NT><<<(unsigned)(nb * a.cx * nblk), NT, smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk,
+        fir_xspec_kernel<N><<<(unsigned)(nb * a.cx * nblk), fir_nt(N), smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk,
                                                                                       a.plan, vec);
         GFX_LAUNCH_CHECK();
         const dim3 grid(half / MAC_NT, nb * c_out);
@@ -746,7 +771,7 @@ static int run_upols(const FirArgs& a) {
 #undef GFX_MAC_CASE
             GFX_LAUNCH_CHECK();
         }
-        fir_inv_kernel<N, NT><<<(unsigned)(nb * c_out * nblk), NT, smem, a.stream>>>(Ys, a.y, row0, a.L, (int)nblk,
+        fir_inv_kernel<N><<<(unsigned)(nb * c_out * nblk), fir_nt(N), smem, a.stream>>>(Ys, a.y, row0, a.L, (int)nblk,
                                                                                      a.shift, a.plan, vec);
         GFX_LAUNCH_CHECK();
     }
@@ -756,14 +781,14 @@ static int run_upols(const FirArgs& a) {
 static int fir_dispatch(const FirArgs& a) {
     const int n = pick_fft_size(a.Nh);
     if (a.Nh <= 16384) {
-        if (n == 1024) return run_ols<1024, 128>(a);
-        if (n == 4096) return run_ols<4096, 256>(a);
-        if (n == 8192) return run_ols<8192, 256>(a);
-        return run_ols<16384, 512>(a);
+        if (n == 1024) return run_ols<1024>(a);
+        if (n == 4096) return run_ols<4096>(a);
+        if (n == 8192) return run_ols<8192>(a);
+        return run_ols<16384>(a);
     }
-    if (n == 4096) return run_upols<4096, 256>(a);
-    if (n == 8192) return run_upols<8192, 256>(a);
-    return run_upols<16384, 512>(a);
+    if (n == 4096) return run_upols<4096>(a);
+    if (n == 8192) return run_upols<8192>(a);
+    return run_upols<16384>(a);
 }
 
 }  // namespace gfx
@@ -786,7 +811,7 @@ int gfx_fir_fft_size(int filter_len) { return filter_len <= 0 ? GFX_ERR_INVALID 
 
 size_t gfx_fft_plan_bytes(int n) {
     if (!gfx::plan_ok(n)) return 0;
-    return ((size_t)n / 2 + (size_t)gfx::plan_total(n)) * sizeof(float2) + ((size_t)n / 2) * sizeof(unsigned short);
+    return ((size_t)n / 2 + (size_t)gfx::plan_total(n)) * sizeof(float2) + ((size_t)n / 32) * sizeof(ushort2);
 }
 
 int gfx_fft_plan_init(void* plan, int n, void* stream) {
@@ -795,16 +820,12 @@ int gfx_fft_plan_init(void* plan, int n, void* stream) {
     float2* base = (float2*)plan;
     cudaStream_t st = (cudaStream_t)stream;
     const int gb = (n / 2 + 255) / 256;
-    if (n == 1024) fft_plan_pairs_kernel<1024><<<gb, 256, 0, st>>>(base);
-    else if (n == 4096) fft_plan_pairs_kernel<4096><<<gb, 256, 0, st>>>(base);
-    else if (n == 8192) fft_plan_pairs_kernel<8192><<<gb, 256, 0, st>>>(base);
-    else fft_plan_pairs_kernel<16384><<<gb, 256, 0, st>>>(base);
-    GFX_LAUNCH_CHECK();
-    unsigned short* partner = (unsigned short*)(base + n / 2 + plan_total(n));
-    if (n == 1024) fft_plan_partner_kernel<1024><<<gb, 256, 0, st>>>(partner);
-    else if (n == 4096) fft_plan_partner_kernel<4096><<<gb, 256, 0, st>>>(partner);
-    else if (n == 8192) fft_plan_partner_kernel<8192><<<gb, 256, 0, st>>>(partner);
-    else fft_plan_partner_kernel<16384><<<gb, 256, 0, st>>>(partner);
+    ushort2* tab = (ushort2*)(base + n / 2 + plan_total(n));
+    if (n == 1024) { fft_plan_pairtab_kernel<1024><<<1, 32, 0, st>>>(tab); fft_plan_pairs_kernel<1024><<<gb, 256, 0, st>>>(base, tab); }
+    else if (n == 4096) { fft_plan_pairtab_kernel<4096><<<1, 32, 0, st>>>(tab); fft_plan_pairs_kernel<4096><<<gb, 256, 0, st>>>(base, tab); }
+    else if (n == 8192) { fft_plan_pairtab_kernel<8192><<<1, 32, 0, st>>>(tab); fft_plan_pairs_kernel<8192><<<gb, 256, 0, st>>>(base, tab); }
+    else { fft_plan_pairtab_kernel<16384><<<1, 32, 0, st>>>(tab); fft_plan_pairs_kernel<16384><<<gb, 256, 0, st>>>(base, tab); }
+    ++g_gfx_launch_count;
     GFX_LAUNCH_CHECK();
     for (int s = 0; s < plan_stages(n); ++s) {
         const int entries = plan_entries(n, s);
