@@ -132,33 +132,39 @@ __device__ __forceinline__ void stg_pk(float* p, pk2 v) {
     asm volatile("st.global.L1::no_allocate.b64 [%0], %1;" ::"l"(p), "l"(v));
 }
 
-// reads block-relative real samples (2c, 2c+1) of a row segment starting at s0 (zero outside [0, len))
+// reads block-relative real samples (2c, 2c+1) of a row segment starting at s0 (zero outside [0, len)).
+// FAST: every (2c, 2c+1) pair is 8-byte aligned and wholly inside or outside the row (the host checks
+// pointer alignment and the parity of every offset involved) -> one predicated 64-bit load, no branches.
+template <bool FAST>
 struct SegSrc {
     const float* base;  // row + s0
     int lo, hi;         // valid block-relative sample range [lo, hi)
-    bool fast;          // 8-byte aligned pairs, lo / hi even
-    __device__ __forceinline__ SegSrc(const float* row, long long s0, long long len, int span, bool aligned8) {
+    __device__ __forceinline__ SegSrc(const float* row, long long s0, long long len, int span) {
         base = row + s0;
         const long long l = s0 < 0 ? -s0 : 0, h = len - s0;
         lo = l > span ? span : (int)l;
         hi = h > span ? span : (h < 0 ? 0 : (int)h);
-        fast = aligned8 && ((s0 & 1) == 0) && ((lo & 1) == 0) && ((hi & 1) == 0);
     }
     __device__ __forceinline__ pk2 get(int c) const {
         const int i = 2 * c;
-        if (fast) return (i >= lo && i < hi) ? ldg_pk(base + i) : 0ull;
-        const float a = (i >= lo && i < hi) ? __ldg(base + i) : 0.f;
-        const float b = (i + 1 >= lo && i + 1 < hi) ? __ldg(base + i + 1) : 0.f;
-        return pk_make(a, b);
+        if constexpr (FAST) {
+            pk2 r = 0ull;
+            if (i >= lo && i < hi) r = ldg_pk(base + i);
+            return r;
+        } else {
+            const float a = (i >= lo && i < hi) ? __ldg(base + i) : 0.f;
+            const float b = (i + 1 >= lo && i + 1 < hi) ? __ldg(base + i + 1) : 0.f;
+            return pk_make(a, b);
+        }
     }
 };
 // writes block-relative real samples (2c, 2c+1), restricted to the window [w_lo, w_hi) of the block, to
 // dst[pos0 + (i - w_lo)], clipped to [0, len)
+template <bool FAST>
 struct SegDst {
     float* base;  // row + pos0 - w_lo  (indexable by the block-relative sample index)
     int lo, hi;   // writable block-relative sample range
-    bool fast;
-    __device__ __forceinline__ SegDst(float* row, long long pos0, long long len, int w_lo, int w_hi, bool aligned8) {
+    __device__ __forceinline__ SegDst(float* row, long long pos0, long long len, int w_lo, int w_hi) {
         const long long off = pos0 - w_lo;  // global position of block-relative sample 0
         base = row + off;
         long long l = -off, h = len - off;
@@ -166,18 +172,17 @@ struct SegDst {
         if (h > w_hi) h = w_hi;
         if (h < l) h = l;
         lo = (int)l; hi = (int)h;
-        fast = aligned8 && ((off & 1) == 0) && ((lo & 1) == 0) && ((hi & 1) == 0);
     }
     __device__ __forceinline__ void put(int c, pk2 v) const {
         const int i = 2 * c;
-        if (fast) {
+        if constexpr (FAST) {
             if (i >= lo && i < hi) stg_pk(base + i, v);
-            return;
+        } else {
+            float a, b;
+            pk_split(v, a, b);
+            if (i >= lo && i < hi) base[i] = a;
+            if (i + 1 >= lo && i + 1 < hi) base[i + 1] = b;
         }
-        float a, b;
-        pk_split(v, a, b);
-        if (i >= lo && i < hi) base[i] = a;
-        if (i + 1 >= lo && i + 1 < hi) base[i + 1] = b;
     }
 };
 struct NoSrc { __device__ __forceinline__ pk2 get(int) const { return 0ull; } };
@@ -369,10 +374,47 @@ struct OpLoad {  // global pair slot -> retangle -> registers
     }
 };
 
+// Thread 0 owns the two self-paired butterflies: bA (klow 0) pairs index rk with 16 - rk (rk = 0: DC with the
+// Nyquist bin at index 8), bB (klow N/32) pairs rk with 15 - rk.  Swapping register halves between A and B puts
+// them into the general cross pattern (A'[rk] <-> B'[15 - rk], B'[rk] <-> A'[15 - rk]):
+//   A' = { A[0..7], B[8..15] },   B' = { B[0..7], A[9..15], A[8] }.
+// The swap is its own inverse up to the rotation of B'[8..15]; both directions below (selects, no branches).
+__device__ __forceinline__ void self_pair_swap(pk2 (&A)[16], pk2 (&B)[16], bool t0, bool back) {
+    if (!back) {
+        pk2 a8 = A[OUT16(8)];
+#pragma unroll
+        for (int j = 8; j < 15; ++j) {
+            const pk2 an = A[OUT16(j + 1)], bj = B[OUT16(j)];
+            B[OUT16(j)] = t0 ? an : bj;
+            A[OUT16(j)] = t0 ? bj : A[OUT16(j)];
+        }
+        const pk2 b15 = B[OUT16(15)];
+        B[OUT16(15)] = t0 ? a8 : b15;
+        A[OUT16(15)] = t0 ? b15 : A[OUT16(15)];
+    } else {
+        // A[8] = B'[15], A[j+1] = B'[j] (j = 8..14), B[j] = A'[j] (j = 8..15)
+        const pk2 na8 = B[OUT16(15)];
+        pk2 nb[8], na[8];
+#pragma unroll
+        for (int j = 8; j < 16; ++j) nb[j - 8] = A[OUT16(j)];
+#pragma unroll
+        for (int j = 9; j < 16; ++j) na[j - 8] = B[OUT16(j - 1)];
+        na[0] = na8;
+#pragma unroll
+        for (int j = 8; j < 16; ++j) {
+            A[OUT16(j)] = t0 ? na[j - 8] : A[OUT16(j)];
+            B[OUT16(j)] = t0 ? nb[j - 8] : B[OUT16(j)];
+        }
+    }
+}
+
 // all 16 pairs of a thread; A / B = the r16 output registers of its butterflies bA / bB
-template <int N, typename Op>
+// IN: A, B hold forward outputs (false for the load-only operator); OUT: A, B are consumed afterwards
+template <int N, bool IN, bool OUT, typename Op>
 __device__ __forceinline__ void pair_phase(pk2 (&A)[16], pk2 (&B)[16], int t, const float2* __restrict__ plan, const Op& op) {
     constexpr int NTT = N / 32, Q = N / 4;
+    const bool t0 = t == 0;
+    if constexpr (IN) self_pair_swap(A, B, t0, false);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -389,23 +431,19 @@ __device__ __forceinline__ void pair_phase(pk2 (&A)[16], pk2 (&B)[16], int t, co
             for (int u = 0; u < 4; ++u) {
                 const int rk = 4 * g + u;
                 const int slot = h * Q + rk * NTT + t;
-                if (t != 0) {
-                    // bin klow(b) + (N/16) rk of one butterfly pairs with index 15 - rk of the other
-                    if (h == 0) op.pair(A[OUT16(rk)], B[OUT16(15 - rk)], w[u], d[u], slot);
-                    else op.pair(B[OUT16(rk)], A[OUT16(15 - rk)], w[u], d[u], slot);
+                // bin klow(b) + (N/16) rk of one butterfly pairs with index 15 - rk of the other
+                if (h == 0 && rk == 0) {
+                    if (t0) op.dc(A[OUT16(0)], B[OUT16(15)], d[u], slot);  // slot 0: DC / Nyquist and the bin N/2
+                    else op.pair(A[OUT16(0)], B[OUT16(15)], w[u], d[u], slot);
+                } else if (h == 0) {
+                    op.pair(A[OUT16(rk)], B[OUT16(15 - rk)], w[u], d[u], slot);
                 } else {
-                    // thread 0: bA = butterfly of klow 0 (pairs rk <-> 16 - rk, rk = 0: DC / Nyquist with index 8),
-                    //           bB = butterfly of klow N/32 (pairs rk <-> 15 - rk)
-                    if (h == 0) {
-                        if (rk == 0) op.dc(A[OUT16(0)], A[OUT16(8)], d[u], slot);
-                        else op.pair(A[OUT16(rk)], A[OUT16((16 - rk) & 15)], w[u], d[u], slot);
-                    } else {
-                        op.pair(B[OUT16(rk)], B[OUT16(15 - rk)], w[u], d[u], slot);
-                    }
+                    op.pair(B[OUT16(rk)], A[OUT16(15 - rk)], w[u], d[u], slot);
                 }
             }
         }
     }
+    if constexpr (OUT) self_pair_swap(A, B, t0, true);
 }
 
 struct RowMap {  // output row -> (x row, h row) with channel broadcasting
@@ -441,15 +479,14 @@ __device__ __forceinline__ void segment_spectrum(pk2* zbuf, const float2* __rest
     pk2 A[16], B[16];
     last_forward(zbuf, pr.x, A);
     last_forward(zbuf, pr.y, B);
-    pair_phase<N>(A, B, t, plan, OpSpectrum{out, scale});
+    pair_phase<N, true, false>(A, B, t, plan, OpSpectrum{out, scale});
 }
 
 // spectra of filter partitions: Hs[(hrow * P + part) * N/2 + slot], scaled by 1/N (and the energy norm)
-template <int N>
+template <int N, bool FAST>
 __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_spectrum_kernel(FilterSrc fs, float4* __restrict__ Hs,
                                                                                     int hrow0, int Nh, int part_len, int P,
-                                                                                    const float2* __restrict__ plan,
-                                                                                    int aligned8) {
+                                                                                    const float2* __restrict__ plan) {
     extern __shared__ __align__(16) pk2 zbuf[];
     const int hloc = blockIdx.x / P, part = blockIdx.x - hloc * P;
     const int hrow = hrow0 + hloc;
@@ -462,38 +499,36 @@ __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_spectrum_ker
         const float e0 = fs.energy[hrow & ~1], e1 = fs.energy[hrow | 1];
         scale *= fs.to_lr ? rsqrtf(e0 + e1 + 1e-12f) : rsqrtf(0.5f * (e0 + e1) + 1e-12f);
     }
-    const SegSrc src(fs.h + (size_t)hrow * Nh, s0, end, 2 * N, aligned8 && ((((size_t)hrow * Nh) & 1) == 0));
+    const SegSrc<FAST> src(fs.h + (size_t)hrow * Nh, s0, end, 2 * N);
     segment_spectrum<N>(zbuf, plan, src, Hs + (size_t)blockIdx.x * (N / 2), scale);
 }
 
 // UPOLS step 1: spectra of input blocks.  Xs[(rloc * nblk + j) * N/2 + slot] = rfft of x[(j-1)B, (j+1)B), B = N
-template <int N>
+template <int N, bool FAST>
 __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_xspec_kernel(const float* __restrict__ x,
                                                                                  float4* __restrict__ Xs, int xrow0,
                                                                                  long long L, int nblk,
-                                                                                 const float2* __restrict__ plan,
-                                                                                 int aligned8) {
+                                                                                 const float2* __restrict__ plan) {
     extern __shared__ __align__(16) pk2 zbuf[];
     const int rloc = blockIdx.x / nblk, j = blockIdx.x - rloc * nblk;
     const size_t xr = (size_t)(xrow0 + rloc);
-    const SegSrc src(x + xr * L, ((long long)j - 1) * N, L, 2 * N, aligned8 && (((xr * L) & 1) == 0));
+    const SegSrc<FAST> src(x + xr * L, ((long long)j - 1) * N, L, 2 * N);
     segment_spectrum<N>(zbuf, plan, src, Xs + (size_t)blockIdx.x * (N / 2), 1.f);
 }
 
 // single-partition overlap-save: block j produces full-convolution samples [j*hop, (j+1)*hop)
-template <int N>
+template <int N, bool FAST>
 __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_ols_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                                const float4* __restrict__ Hs, RowMap rm,
                                                                                long long L, int pre, int hop, int shift,
-                                                                               int nblk, const float2* __restrict__ plan,
-                                                                               int aligned8) {
+                                                                               int nblk, const float2* __restrict__ plan) {
     constexpr int NT = fir_nt(N);
     extern __shared__ __align__(16) pk2 zbuf[];
     const int row = blockIdx.x / nblk, j = blockIdx.x - row * nblk;
     int xr, hr;
     rm.map(row, xr, hr);
     const long long m0 = (long long)j * hop;
-    const SegSrc src(x + (size_t)xr * L, m0 - pre, L, 2 * N, aligned8 && ((((size_t)xr * L) & 1) == 0));
+    const SegSrc<FAST> src(x + (size_t)xr * L, m0 - pre, L, 2 * N);
     fft_forward_front<N, NT>(zbuf, plan, src);
     const int t = threadIdx.x;
     const ushort2 pr = plan_pairtab<N>(plan)[t];
@@ -501,11 +536,11 @@ __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_ols_kernel(c
         pk2 A[16], B[16];
         last_forward(zbuf, pr.x, A);
         last_forward(zbuf, pr.y, B);
-        pair_phase<N>(A, B, t, plan, OpFilter{Hs + (size_t)hr * (N / 2)});
+        pair_phase<N, true, true>(A, B, t, plan, OpFilter{Hs + (size_t)hr * (N / 2)});
         first_inverse(zbuf, pr.x, A);  // (each thread rewrites exactly the positions it read: no barrier in between)
         first_inverse(zbuf, pr.y, B);
     }
-    const SegDst dst(y + (size_t)row * L, m0 - shift, L, pre, pre + hop, aligned8 && ((((size_t)row * L) & 1) == 0));
+    const SegDst<FAST> dst(y + (size_t)row * L, m0 - shift, L, pre, pre + hop);
     fft_inverse_back<N, NT>(zbuf, plan, dst);
 }
 
@@ -597,10 +632,10 @@ __global__ void __launch_bounds__(MAC_NT, 2) fir_mac_kernel(const float4* __rest
 }
 
 // UPOLS step 3: inverse FFT of Y_j, keep the second half of the block
-template <int N>
+template <int N, bool FAST>
 __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_inv_kernel(const float4* __restrict__ Ys, float* __restrict__ y,
                                                                                int row0, long long L, int nblk, int shift,
-                                                                               const float2* __restrict__ plan, int aligned8) {
+                                                                               const float2* __restrict__ plan) {
     constexpr int NT = fir_nt(N);
     extern __shared__ __align__(16) pk2 zbuf[];
     const int rloc = blockIdx.x / nblk, j = blockIdx.x - rloc * nblk;
@@ -608,12 +643,12 @@ __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_inv_kernel(c
     const ushort2 pr = plan_pairtab<N>(plan)[t];
     {
         pk2 A[16], B[16];
-        pair_phase<N>(A, B, t, plan, OpLoad{Ys + (size_t)blockIdx.x * (N / 2)});
+        pair_phase<N, false, true>(A, B, t, plan, OpLoad{Ys + (size_t)blockIdx.x * (N / 2)});
         first_inverse(zbuf, pr.x, A);
         first_inverse(zbuf, pr.y, B);
     }
     const size_t row = (size_t)(row0 + rloc);
-    const SegDst dst(y + row * L, (long long)j * N - shift, L, N, 2 * N, aligned8 && (((row * L) & 1) == 0));
+    const SegDst<FAST> dst(y + row * L, (long long)j * N - shift, L, N, 2 * N);
     fft_inverse_back<N, NT>(zbuf, plan, dst);
 }
 
@@ -682,6 +717,7 @@ struct FirArgs {
     const float* x; FilterSrc fs; float* y;
     int batch, cx, ch; long long L; int Nh; int shift;
     const float2* plan; unsigned char* ws; size_t ws_bytes; cudaStream_t stream;
+    bool fast_x, fast_h;  // every (even, odd) sample pair of x / y resp. h is 8-byte aligned and never straddles a row end
 };
 
 template <int N>
@@ -694,21 +730,22 @@ static int run_ols(const FirArgs& a) {
     const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
     static bool configured = false;
     if (!configured) {
-        if (set_smem(fir_spectrum_kernel<N>, smem) || set_smem(fir_ols_kernel<N>, smem)) return GFX_ERR_CUDA;
+        if (set_smem(fir_spectrum_kernel<N, true>, smem) || set_smem(fir_spectrum_kernel<N, false>, smem) ||
+            set_smem(fir_ols_kernel<N, true>, smem) || set_smem(fir_ols_kernel<N, false>, smem)) return GFX_ERR_CUDA;
         configured = true;
     }
-    const int hvec = ((uintptr_t)a.fs.h % 8 == 0);
-    fir_spectrum_kernel<N><<<hrows, fir_nt(N), smem, a.stream>>>(a.fs, Hs, 0, a.Nh, a.Nh, 1, a.plan, hvec);
+    if (a.fast_h) fir_spectrum_kernel<N, true><<<hrows, fir_nt(N), smem, a.stream>>>(a.fs, Hs, 0, a.Nh, a.Nh, 1, a.plan);
+    else fir_spectrum_kernel<N, false><<<hrows, fir_nt(N), smem, a.stream>>>(a.fs, Hs, 0, a.Nh, a.Nh, 1, a.plan);
     GFX_LAUNCH_CHECK();
     const int pre = (a.Nh - 1 + 3) & ~3;
     const int hop = (2 * N - pre) & ~3;
     const long long total = a.L + a.shift;
     const long long nblk = (total + hop - 1) / hop;
     if (nblk * rows > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
-    const int vec = (((uintptr_t)a.x | (uintptr_t)a.y) % 8 == 0);
     RowMap rm{c_out, a.cx, a.ch};
-    fir_ols_kernel<N><<<(unsigned)(nblk * rows), fir_nt(N), smem, a.stream>>>(a.x, a.y, Hs, rm, a.L, pre, hop, a.shift,
-                                                                           (int)nblk, a.plan, vec);
+    const unsigned grid = (unsigned)(nblk * rows);
+    if (a.fast_x) fir_ols_kernel<N, true><<<grid, fir_nt(N), smem, a.stream>>>(a.x, a.y, Hs, rm, a.L, pre, hop, a.shift, (int)nblk, a.plan);
+    else fir_ols_kernel<N, false><<<grid, fir_nt(N), smem, a.stream>>>(a.x, a.y, Hs, rm, a.L, pre, hop, a.shift, (int)nblk, a.plan);
     GFX_LAUNCH_CHECK();
     return GFX_OK;
 }
@@ -738,13 +775,12 @@ static int run_upols(const FirArgs& a) {
     const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
     static bool configured = false;
     if (!configured) {
-        if (set_smem(fir_spectrum_kernel<N>, smem) || set_smem(fir_xspec_kernel<N>, smem) ||
-            set_smem(fir_inv_kernel<N>, smem)) return GFX_ERR_CUDA;
+        if (set_smem(fir_spectrum_kernel<N, true>, smem) || set_smem(fir_spectrum_kernel<N, false>, smem) ||
+            set_smem(fir_xspec_kernel<N, true>, smem) || set_smem(fir_xspec_kernel<N, false>, smem) ||
+            set_smem(fir_inv_kernel<N, true>, smem) || set_smem(fir_inv_kernel<N, false>, smem)) return GFX_ERR_CUDA;
         configured = true;
     }
     constexpr int half = N / 2;
-    const int hvec = ((uintptr_t)a.fs.h % 8 == 0);
-    const int vec = (((uintptr_t)a.x | (uintptr_t)a.y) % 8 == 0);
     RowMap rm{c_out, a.cx, a.ch};
     for (long long b0 = 0; b0 < a.batch; b0 += chunk) {
         const int nb = (int)((a.batch - b0 < chunk) ? a.batch - b0 : chunk);
@@ -754,10 +790,12 @@ static int run_upols(const FirArgs& a) {
         const int hrow0 = (int)b0 * a.ch, xrow0 = (int)b0 * a.cx, row0 = (int)b0 * c_out;
         if ((long long)nb * a.cx * nblk > 0x7fffffffLL || (long long)nb * c_out * nblk > 0x7fffffffLL ||
             (long long)nb * c_out > 65535) return GFX_ERR_UNSUPPORTED;
-        fir_spectrum_kernel<N><<<nb * a.ch * P, fir_nt(N), smem, a.stream>>>(a.fs, Hs, hrow0, a.Nh, N, P, a.plan, hvec);
+        const unsigned gh = (unsigned)(nb * a.ch * P), gx = (unsigned)(nb * a.cx * nblk);
+        if (a.fast_h) fir_spectrum_kernel<N, true><<<gh, fir_nt(N), smem, a.stream>>>(a.fs, Hs, hrow0, a.Nh, N, P, a.plan);
+        else fir_spectrum_kernel<N, false><<<gh, fir_nt(N), smem, a.stream>>>(a.fs, Hs, hrow0, a.Nh, N, P, a.plan);
         GFX_LAUNCH_CHECK();
-        fir_xspec_kernel<N><<<(unsigned)(nb * a.cx * nblk), fir_nt(N), smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk,
-                                                                                      a.plan, vec);
+        if (a.fast_x) fir_xspec_kernel<N, true><<<gx, fir_nt(N), smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk, a.plan);
+        else fir_xspec_kernel<N, false><<<gx, fir_nt(N), smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk, a.plan);
         GFX_LAUNCH_CHECK();
         const dim3 grid(half / MAC_NT, nb * c_out);
         for (int p0 = 0; p0 < P; p0 += MAC_MAX_PC) {
@@ -771,8 +809,9 @@ static int run_upols(const FirArgs& a) {
 #undef GFX_MAC_CASE
             GFX_LAUNCH_CHECK();
         }
-        fir_inv_kernel<N><<<(unsigned)(nb * c_out * nblk), fir_nt(N), smem, a.stream>>>(Ys, a.y, row0, a.L, (int)nblk,
-                                                                                     a.shift, a.plan, vec);
+        const unsigned gy = (unsigned)(nb * c_out * nblk);
+        if (a.fast_x) fir_inv_kernel<N, true><<<gy, fir_nt(N), smem, a.stream>>>(Ys, a.y, row0, a.L, (int)nblk, a.shift, a.plan);
+        else fir_inv_kernel<N, false><<<gy, fir_nt(N), smem, a.stream>>>(Ys, a.y, row0, a.L, (int)nblk, a.shift, a.plan);
         GFX_LAUNCH_CHECK();
     }
     return GFX_OK;
@@ -858,7 +897,9 @@ static int fir_conv_common(const float* x, gfx::FilterSrc fs, float* y, int batc
     if (batch <= 0 || cx <= 0 || ch <= 0 || L <= 0 || filter_len <= 0) return GFX_ERR_INVALID;
     if (cx != ch && cx != 1 && ch != 1) return GFX_ERR_INVALID;
     FirArgs a{x, fs, y, batch, cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, (const float2*)plan,
-              (unsigned char*)workspace, workspace_bytes, (cudaStream_t)stream};
+              (unsigned char*)workspace, workspace_bytes, (cudaStream_t)stream, false, false};
+    a.fast_x = (((uintptr_t)x | (uintptr_t)y) % 8 == 0) && (L % 2 == 0) && (a.shift % 2 == 0);
+    a.fast_h = ((uintptr_t)fs.h % 8 == 0) && (filter_len % 2 == 0);
     return fir_dispatch(a);
 }
 
