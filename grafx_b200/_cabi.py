@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgrafx_b200.so")
+LIB_PATH = os.environ.get("GRAFX_B200_LIB") or os.path.join(_HERE, "lib", "libgrafx_b200.so")  # (override: kernel A/B experiments)
 
 _lib = None
 _lock = threading.Lock()

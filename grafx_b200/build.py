@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libgrafx_b200.so")
+LIB = os.path.join(LIBDIR, os.environ.get("GFX_LIB_OUT", "libgrafx_b200.so"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_rebuild():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", os.environ.get("GFX_LIB_OUT", "default"))
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     objs = []
@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, *PER_FILE_FLAGS.get(os.path.basename(src), ["-fmad=true"]), "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("GFX_NVCC_EXTRA", "").split(), *PER_FILE_FLAGS.get(os.path.basename(src), ["-fmad=true"]), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -47,10 +47,17 @@ __host__ __device__ constexpr int plan_m(int n, int s) {  // sub-transform lengt
     for (int i = 0; i < s; ++i) m /= plan_radix(n, i);
     return m;
 }
-__host__ __device__ constexpr int tw_per_butterfly(int r) { return r == 16 ? 6 : (r == 4 ? 3 : (r == 2 ? 1 : 0)); }
+#ifndef GFX_TW15
+#define GFX_TW15 0  // 1: all 15 radix-16 twiddles from the table; 0: 6 from the table, 9 products
+#endif
+__host__ __device__ constexpr int tw_per_butterfly(int r) { return r == 16 ? (GFX_TW15 ? 15 : 6) : (r == 4 ? 3 : (r == 2 ? 1 : 0)); }
 __host__ __device__ constexpr int tw_exponent(int r, int e) {  // exponent of table entry e
-    return r == 16 ? (e < 3 ? e + 1 : 4 * (e - 2)) : e + 1;
+    return (r == 16 && !GFX_TW15) ? (e < 3 ? e + 1 : 4 * (e - 2)) : e + 1;
 }
+#ifndef GFX_PASS_UNROLL
+#define GFX_PASS_UNROLL 1
+#endif
+constexpr int kPassUnroll = GFX_PASS_UNROLL;  // butterflies of a shared-memory radix-16 pass processed together
 __host__ __device__ constexpr int plan_entries(int n, int s) {
     const int r = plan_radix(n, s);
     const int st = r > 1 ? plan_m(n, s) / r : 1;
@@ -202,7 +209,7 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan
     constexpr int PST = ST >= 16 ? ST + ST / 16 : 1;
     static_assert(ST == 1 || ST % 16 == 0, "stride must keep the padding pattern linear");
     static_assert(!(FROM_GLOBAL || TO_GLOBAL) || (S == 0 && R == 16), "fused passes are the radix-16 pass 0");
-#pragma unroll(R == 2 ? 4 : 1)
+#pragma unroll(R == 2 ? 4 : ((FROM_GLOBAL || TO_GLOBAL) ? 1 : kPassUnroll))
     for (int b = threadIdx.x; b < N / R; b += NT) {
         const int j = b & (ST - 1);
         const int i0 = (b - j) * R + j;
@@ -230,10 +237,15 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan
             zb[0] = a0; zb[PST] = a1; zb[2 * PST] = a2; zb[3 * PST] = a3;
         } else {
             // twiddle of index r = r0 + 4 r1:  omega^(j r0) * omega^(4 j r1);  lo[r0], hi[r1] from the table
-            float2 lo[4], hi[4];
+            float2 lo[4], hi[4], tw[16];
             if constexpr (ST > 1) {
+                if constexpr (GFX_TW15) {
 #pragma unroll
-                for (int e = 0; e < 3; ++e) { lo[e + 1] = ld_tw(tp + e * ST + j); hi[e + 1] = ld_tw(tp + (e + 3) * ST + j); }
+                    for (int e = 1; e < 16; ++e) tw[e] = ld_tw(tp + (e - 1) * ST + j);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) { lo[e + 1] = ld_tw(tp + e * ST + j); hi[e + 1] = ld_tw(tp + (e + 3) * ST + j); }
+                }
             }
             pk2 a[16];
 #pragma unroll
@@ -245,7 +257,7 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan
 #pragma unroll
                 for (int q = 1; q < 16; ++q) {
                     const int r0 = q & 3, r1 = q >> 2;
-                    const float2 w = r1 == 0 ? lo[r0] : (r0 == 0 ? hi[r1] : cmul(lo[r0], hi[r1]));
+                    const float2 w = GFX_TW15 ? tw[q] : (r1 == 0 ? lo[r0] : (r0 == 0 ? hi[r1] : cmul(lo[r0], hi[r1])));
                     a[q] = tw_apply<true>(a[q], w);
                 }
             }
@@ -259,7 +271,7 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan
                     pk2 v = a[4 * i + jj];
                     if constexpr (!INV && ST > 1) {
                         if (r > 0) {
-                            const float2 w = jj == 0 ? lo[i] : (i == 0 ? hi[jj] : cmul(lo[i], hi[jj]));
+                            const float2 w = GFX_TW15 ? tw[r] : (jj == 0 ? lo[i] : (i == 0 ? hi[jj] : cmul(lo[i], hi[jj])));
                             v = tw_apply<false>(v, w);
                         }
                     }

@@ -5,9 +5,41 @@ enqueues the kernel on the current CUDA stream.  Forward only: inputs are detach
 """
 from __future__ import annotations
 
+import threading
+
 import torch
 
 from . import _cabi
+
+
+_DEST = threading.local()
+
+
+class output_into:
+    """`with output_into(view):` -- the next kernel output of exactly this shape / dtype / device is
+    written straight into `view` (a contiguous slice of a caller-owned buffer, e.g. the signal buffer of
+    render_grafx) instead of a fresh tensor.  The caller compares data_ptr()s afterwards: a processor
+    whose last op is not one of ours simply returns its own tensor, to be copied as usual."""
+
+    def __init__(self, dest: torch.Tensor | None):
+        self.dest = dest if (dest is not None and dest.is_contiguous()) else None
+
+    def __enter__(self):
+        self.prev = getattr(_DEST, "t", None)
+        _DEST.t = self.dest
+        return self
+
+    def __exit__(self, *exc):
+        _DEST.t = self.prev
+        return False
+
+
+def _new_output(shape, dtype, device) -> torch.Tensor:
+    d = getattr(_DEST, "t", None)
+    if d is not None and tuple(d.shape) == tuple(shape) and d.dtype == dtype and d.device == device:
+        _DEST.t = None
+        return d
+    return torch.empty(shape, dtype=dtype, device=device)
 
 
 def _prep(t: torch.Tensor, dtype=None) -> torch.Tensor:
@@ -31,7 +63,7 @@ def biquad_cascade(x: torch.Tensor, Bs: torch.Tensor, As: torch.Tensor) -> torch
     dtype = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
     x, Bs, As = _prep(x, dtype), _prep(Bs, dtype), _prep(As, dtype)
     c_out = max(c_sig, c_filt)
-    y = torch.empty(b, c_out, L, dtype=dtype, device=x.device)
+    y = _new_output((b, c_out, L), dtype, x.device)
     if y.numel() == 0:
         return y
     L_ = _cabi.lib()
@@ -50,7 +82,7 @@ def _midside(x: torch.Tensor, mult: float) -> torch.Tensor:
     _cabi.require_cuda(x)
     assert x.ndim == 3 and x.shape[1] == 2, "mid/side conversion needs [B, 2, L]"
     x = _prep(x, torch.float32)
-    y = torch.empty_like(x)
+    y = _new_output(tuple(x.shape), torch.float32, x.device)
     if y.numel() == 0:
         return y
     with torch.cuda.device(x.device):
@@ -101,7 +133,7 @@ def fir_conv(x: torch.Tensor, h: torch.Tensor, mode: str = "causal") -> torch.Te
     _, ch, N = h3.shape
     assert cx == ch or cx == 1 or ch == 1, "channel mismatch between signal and filter"
     x3, h3 = _prep(x3, torch.float32), _prep(h3, torch.float32)
-    y = torch.empty(B, max(cx, ch), L, dtype=torch.float32, device=x.device)
+    y = torch.empty(B, max(cx, ch), L, dtype=torch.float32, device=x.device) if squeeze else _new_output((B, max(cx, ch), L), torch.float32, x.device)
     if y.numel():
         L_ = _cabi.lib()
         n = L_.gfx_fir_fft_size(N)
@@ -158,7 +190,7 @@ def dynamics_chain(x: torch.Tensor, stages: list[dict], iir_len: int = 16384) ->
     assert x.ndim == 3
     B, C, L = x.shape
     x = _prep(x, torch.float32)
-    y = torch.empty_like(x)
+    y = _new_output((B, C, L), torch.float32, x.device)
     if y.numel() == 0:
         return y
     L_ = _cabi.lib()
@@ -318,7 +350,7 @@ def fir_conv_midside_ir(x: torch.Tensor, ir_raw: torch.Tensor, energy: torch.Ten
     N = ir_raw.shape[2]
     assert cx in (1, 2), "channel mismatch between signal and filter"
     x, ir_raw, energy = _prep(x, torch.float32), _prep(ir_raw, torch.float32), _prep(energy, torch.float32)
-    y = torch.empty(B, 2, L, dtype=torch.float32, device=x.device)
+    y = _new_output((B, 2, L), torch.float32, x.device)
     if y.numel():
         L_ = _cabi.lib()
         plan = _fft_plan(x.device, L_.gfx_fir_fft_size(N))

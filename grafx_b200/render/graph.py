@@ -49,21 +49,26 @@ def _flatten2(x):
 
 def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_parameters: Mapping, render_data,
                  common_parameters=None, parameters_grad=True, input_signal_grad=False):
+    """Layout: the signal buffer is allocated NODE-major, `[|V|, (B,) C, L]`, so that the nodes of a render
+    order are one contiguous block of rows: processors read their inputs as views of the buffer and (ours)
+    write their outputs straight into the destination slice -- no gather / scatter copies.  For 4-D sources
+    the returned output and buffer are the `[B, ...]`-first views of those tensors (same shape and values as
+    upstream, render/graph.py:63-75,177; they are not contiguous)."""
     method = render_data.method
     ndim = input_signals.ndim
     if ndim == 3:
-        node_dim, batch_size = 0, None
+        batch_size = None
         num_sources, channels, audio_len = input_signals.shape
     elif ndim == 4:
-        node_dim = 1
         batch_size, num_sources, channels, audio_len = input_signals.shape
-        expand = lambda t: t.detach().unsqueeze(0).expand(batch_size, *t.shape)  # noqa: E731
-        per_type_parameters = _map_tensors(per_type_parameters, expand)
-        if common_parameters is not None:
-            common_parameters = _map_tensors(common_parameters, expand)
+        # node-major flattening of the batch: row = node * B + b (upstream: b * n + node; the order of the
+        # rows inside a render order is an implementation detail, signals and parameters use the same one)
+        expand = lambda t: t.detach().unsqueeze(1).expand(t.shape[0], batch_size, *t.shape[1:])  # noqa: E731
     else:
         raise Exception(f"input_signal has shape of {input_signals.shape} ({ndim} ndims), which is not 3 or 4 dims.")
+    node_dim = 0
     post = _flatten2 if ndim == 4 else (lambda t: t)
+    batched = (lambda t: post(expand(t))) if ndim == 4 else (lambda t: t)
     input_signals = input_signals.detach()
 
     # create_signal_buffer (render/core.py:6-33)
@@ -72,9 +77,9 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
         assert ndim == 3, "the one-by-one list buffer has no batch axis upstream either"
         signal_buffer = [x[None] for x in input_signals] + [None] * (render_data.num_nodes - num_sources)
     else:
-        shape = (render_data.num_nodes, channels, audio_len) if ndim == 3 else (batch_size, render_data.num_nodes, channels, audio_len)
+        shape = (render_data.num_nodes, channels, audio_len) if ndim == 3 else (render_data.num_nodes, batch_size, channels, audio_len)
         signal_buffer = torch.empty(shape, device=input_signals.device, dtype=torch.float32)
-        signal_buffer.narrow(node_dim, 0, num_sources).copy_(input_signals)
+        signal_buffer.narrow(0, 0, num_sources).copy_(input_signals if ndim == 3 else input_signals.transpose(0, 1))
 
     intermediates_list = []
     output_signals = None
@@ -85,38 +90,39 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
         if not is_proc and node_type not in UTILITY_TYPES:
             raise Exception(f"Wrong node type given: {node_type}")
         dest = it.dest_write
-        direct_dest = None
-        if (not one_by_one) and (not is_proc) and len(it.source_reads) == 1 and dest.method == "slice":
-            # utility node: aggregate straight into the destination slice of the buffer
-            direct_dest = signal_buffer.narrow(node_dim, dest.idx[0], dest.idx[1] - dest.idx[0])
+        dest_view = None
+        if (not one_by_one) and dest.method == "slice":
+            dest_view = signal_buffer.narrow(0, dest.idx[0], dest.idx[1] - dest.idx[0])
+        direct_dest = dest_view if ((not is_proc) and len(it.source_reads) == 1) else None
 
         inputs = []
         wrote_direct = False
         for read, agg in zip(it.source_reads, it.aggregations):
             src = _read(signal_buffer, read, node_dim)
             if agg.method == "sum":
-                out_view = direct_dest if (direct_dest is not None and direct_dest.shape[node_dim] == 1) else None
-                src = F_.node_sum(src, node_dim, None, 1, out=out_view)
+                out_view = direct_dest if (direct_dest is not None and direct_dest.shape[0] == 1) else None
+                src = _node_sum(src, None, 1, out_view, ndim)
                 wrote_direct = out_view is not None
             elif agg.method == "scatter":
                 n_dst = int(agg.idx.max()) + 1
-                out_view = direct_dest if (direct_dest is not None and direct_dest.shape[node_dim] == n_dst) else None
-                src = F_.node_sum(src, node_dim, agg.idx, n_dst, out=out_view)
+                out_view = direct_dest if (direct_dest is not None and direct_dest.shape[0] == n_dst) else None
+                src = _node_sum(src, agg.idx, n_dst, out_view, ndim)
                 wrote_direct = out_view is not None
             elif agg.method != "none":
                 raise Exception(f"The provided aggregation method is not available: {agg.method}.")
             inputs.append(post(src))
 
         if is_proc:
-            parameters = _map_tensors(_read(per_type_parameters[node_type], it.parameter_read, node_dim), post)
+            parameters = _map_tensors(_read(per_type_parameters[node_type], it.parameter_read, 0), batched)
             common_i = {}
             if common_parameters is not None:
-                common_i = _map_tensors(_read(common_parameters, dest, node_dim), post)
+                common_i = _map_tensors(_read(common_parameters, dest, 0), batched)
                 if isinstance(common_i, torch.Tensor):
                     common_i = {"parameter": common_i}
             if isinstance(parameters, torch.Tensor):
                 parameters = {"parameter": parameters}
-            output = processors[node_type](*inputs, **parameters, **common_i)
+            with F_.output_into(post(dest_view) if dest_view is not None else None):
+                output = processors[node_type](*inputs, **parameters, **common_i)
             if isinstance(output, tuple):
                 output_signals, intermediates = output
                 intermediates_list.append(intermediates)
@@ -126,19 +132,37 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
             output_signals = inputs
 
         if isinstance(output_signals, list):
-            output_signals = output_signals[0] if len(output_signals) == 1 else torch.stack(output_signals, -3).view(-1, channels, audio_len)
+            if len(output_signals) == 1:
+                output_signals = output_signals[0]
+            elif ndim == 3:
+                output_signals = torch.stack(output_signals, -3).view(-1, channels, audio_len)
+            else:  # same node order as upstream ((node, input) pairs), batch axis kept second
+                output_signals = torch.stack([o.view(-1, batch_size, channels, audio_len) for o in output_signals], 1)
         if ndim == 4:
-            output_signals = output_signals.view(batch_size, -1, channels, audio_len)
+            output_signals = output_signals.reshape(-1, batch_size, channels, audio_len)
 
         # inplace_write_tensor (render/core.py:80-98)
         if one_by_one:
             signal_buffer[dest.idx[0]] = output_signals
-        elif wrote_direct:
-            pass  # the aggregation kernel already wrote the slice; output_signals is that view
+        elif wrote_direct or (dest_view is not None and output_signals.data_ptr() == dest_view.data_ptr()
+                              and output_signals.shape == dest_view.shape):
+            pass  # the kernel already wrote the slice of the buffer; output_signals is that view
         elif dest.method == "slice":
-            signal_buffer.narrow(node_dim, dest.idx[0], dest.idx[1] - dest.idx[0]).copy_(output_signals)
+            dest_view.copy_(output_signals)
         elif dest.method == "index":
-            signal_buffer.index_copy_(node_dim, dest.idx.to(signal_buffer.device), output_signals)
+            signal_buffer.index_copy_(0, dest.idx.to(signal_buffer.device), output_signals)
         else:
             raise Exception(f"The provided inplace write method is not available: {dest.method}.")
+    if ndim == 4:
+        return output_signals.transpose(0, 1), intermediates_list, signal_buffer.transpose(0, 1)
     return output_signals, intermediates_list, signal_buffer
+
+
+def _node_sum(src, index, n_dst, out_view, ndim):
+    """node-axis (dim 0) sum / scatter-sum of a node-major view [Q, (B,) C, L] -> [n_dst, (B,) C, L]."""
+    if ndim == 3:
+        return F_.node_sum(src, 0, index, n_dst, out=out_view)
+    # [Q, B, C, L]: the kernel wants [batch, node, C*L] strides -> hand it the transposed views
+    out_t = out_view.transpose(0, 1) if out_view is not None else None
+    res = F_.node_sum(src.transpose(0, 1), 1, index, n_dst, out=out_t)
+    return res.transpose(0, 1)
