@@ -458,12 +458,12 @@ __device__ __forceinline__ void pair_phase(pk2 (&A)[16], pk2 (&B)[16], int t, co
     if constexpr (OUT) self_pair_swap(A, B, t0, true);
 }
 
-struct RowMap {  // output row -> (x row, h row) with channel broadcasting
-    int c_out, cx, ch;
+struct RowMap {  // output row -> (x row, h row) with channel broadcasting; h_rep consecutive batch items share a filter
+    int c_out, cx, ch, h_rep;
     __device__ __forceinline__ void map(int r, int& xr, int& hr) const {
         const int b = r / c_out, c = r - b * c_out;
         xr = b * cx + (cx == 1 ? 0 : c);
-        hr = b * ch + (ch == 1 ? 0 : c);
+        hr = (b / h_rep) * ch + (ch == 1 ? 0 : c);
     }
 };
 
@@ -727,7 +727,7 @@ static int set_smem(K kern, size_t smem) {
 
 struct FirArgs {
     const float* x; FilterSrc fs; float* y;
-    int batch, cx, ch; long long L; int Nh; int shift;
+    int batch, cx, ch; long long L; int Nh; int shift; int h_rep;
     const float2* plan; unsigned char* ws; size_t ws_bytes; cudaStream_t stream;
     bool fast_x, fast_h;  // every (even, odd) sample pair of x / y resp. h is 8-byte aligned and never straddles a row end
 };
@@ -735,7 +735,7 @@ struct FirArgs {
 template <int N>
 static int run_ols(const FirArgs& a) {
     const int c_out = a.cx > a.ch ? a.cx : a.ch;
-    const int rows = a.batch * c_out, hrows = a.batch * a.ch;
+    const int rows = a.batch * c_out, hrows = (a.batch / a.h_rep) * a.ch;
     const size_t need = (size_t)hrows * (N / 2) * sizeof(float4);
     if (!a.ws || a.ws_bytes < need) return GFX_ERR_WORKSPACE;
     float4* Hs = (float4*)a.ws;
@@ -754,7 +754,7 @@ static int run_ols(const FirArgs& a) {
     const long long total = a.L + a.shift;
     const long long nblk = (total + hop - 1) / hop;
     if (nblk * rows > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
-    RowMap rm{c_out, a.cx, a.ch};
+    RowMap rm{c_out, a.cx, a.ch, a.h_rep};
     const unsigned grid = (unsigned)(nblk * rows);
     if (a.fast_x) fir_ols_kernel<N, true><<<grid, fir_nt(N), smem, a.stream>>>(a.x, a.y, Hs, rm, a.L, pre, hop, a.shift, (int)nblk, a.plan);
     else fir_ols_kernel<N, false><<<grid, fir_nt(N), smem, a.stream>>>(a.x, a.y, Hs, rm, a.L, pre, hop, a.shift, (int)nblk, a.plan);
@@ -793,16 +793,17 @@ static int run_upols(const FirArgs& a) {
         configured = true;
     }
     constexpr int half = N / 2;
-    RowMap rm{c_out, a.cx, a.ch};
+    RowMap rm{c_out, a.cx, a.ch, a.h_rep};
     for (long long b0 = 0; b0 < a.batch; b0 += chunk) {
         const int nb = (int)((a.batch - b0 < chunk) ? a.batch - b0 : chunk);
+        const int hb0 = (int)(b0 / a.h_rep), nh = (int)((b0 + nb - 1) / a.h_rep) + 1 - hb0;  // filters of this sweep
         float4* Hs = (float4*)a.ws;
-        float4* Xs = Hs + (size_t)nb * a.ch * P * half;
+        float4* Xs = Hs + (size_t)nh * a.ch * P * half;
         float4* Ys = Xs + (size_t)nb * a.cx * nblk * half;
-        const int hrow0 = (int)b0 * a.ch, xrow0 = (int)b0 * a.cx, row0 = (int)b0 * c_out;
+        const int hrow0 = hb0 * a.ch, xrow0 = (int)b0 * a.cx, row0 = (int)b0 * c_out;
         if ((long long)nb * a.cx * nblk > 0x7fffffffLL || (long long)nb * c_out * nblk > 0x7fffffffLL ||
             (long long)nb * c_out > 65535) return GFX_ERR_UNSUPPORTED;
-        const unsigned gh = (unsigned)(nb * a.ch * P), gx = (unsigned)(nb * a.cx * nblk);
+        const unsigned gh = (unsigned)(nh * a.ch * P), gx = (unsigned)(nb * a.cx * nblk);
         if (a.fast_h) fir_spectrum_kernel<N, true><<<gh, fir_nt(N), smem, a.stream>>>(a.fs, Hs, hrow0, a.Nh, N, P, a.plan);
         else fir_spectrum_kernel<N, false><<<gh, fir_nt(N), smem, a.stream>>>(a.fs, Hs, hrow0, a.Nh, N, P, a.plan);
         GFX_LAUNCH_CHECK();
@@ -902,13 +903,14 @@ size_t gfx_fir_conv_workspace_bytes(int batch, int cx, int ch, long long L, int 
 }
 
 static int fir_conv_common(const float* x, gfx::FilterSrc fs, float* y, int batch, int cx, int ch, long long L,
-                           int filter_len, int zerophase, const void* plan, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           int filter_len, int zerophase, int filter_repeat, const void* plan, void* workspace,
+                           size_t workspace_bytes, void* stream) {
     using namespace gfx;
     if (!x || !fs.h || !y || !plan) return GFX_ERR_INVALID;
     if (batch <= 0 || cx <= 0 || ch <= 0 || L <= 0 || filter_len <= 0) return GFX_ERR_INVALID;
+    if (filter_repeat <= 0 || batch % filter_repeat != 0) return GFX_ERR_INVALID;
     if (cx != ch && cx != 1 && ch != 1) return GFX_ERR_INVALID;
-    FirArgs a{x, fs, y, batch, cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, (const float2*)plan,
+    FirArgs a{x, fs, y, batch, cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, filter_repeat, (const float2*)plan,
               (unsigned char*)workspace, workspace_bytes, (cudaStream_t)stream, false, false};
     a.fast_x = (((uintptr_t)x | (uintptr_t)y) % 8 == 0) && (L % 2 == 0) && (a.shift % 2 == 0);
     a.fast_h = ((uintptr_t)fs.h % 8 == 0) && (filter_len % 2 == 0);
@@ -916,18 +918,18 @@ static int fir_conv_common(const float* x, gfx::FilterSrc fs, float* y, int batc
 }
 
 int gfx_fir_conv_f32(const float* x, const float* h, float* y, int batch, int cx, int ch, long long L,
-                     int filter_len, int zerophase, const void* plan, void* workspace, size_t workspace_bytes,
-                     void* stream) {
-    return fir_conv_common(x, gfx::FilterSrc{h, nullptr, 0}, y, batch, cx, ch, L, filter_len, zerophase, plan,
-                           workspace, workspace_bytes, stream);
+                     int filter_len, int zerophase, int filter_repeat, const void* plan, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    return fir_conv_common(x, gfx::FilterSrc{h, nullptr, 0}, y, batch, cx, ch, L, filter_len, zerophase, filter_repeat,
+                           plan, workspace, workspace_bytes, stream);
 }
 
 int gfx_fir_conv_midside_ir_f32(const float* x, const float* ir_raw, const float* energy, float* y, int batch, int cx,
-                                long long L, int ir_len, int ms_to_lr, const void* plan, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                long long L, int ir_len, int ms_to_lr, int filter_repeat, const void* plan,
+                                void* workspace, size_t workspace_bytes, void* stream) {
     if (!energy) return GFX_ERR_INVALID;
-    return fir_conv_common(x, gfx::FilterSrc{ir_raw, energy, ms_to_lr ? 1 : 0}, y, batch, cx, 2, L, ir_len, 0, plan,
-                           workspace, workspace_bytes, stream);
+    return fir_conv_common(x, gfx::FilterSrc{ir_raw, energy, ms_to_lr ? 1 : 0}, y, batch, cx, 2, L, ir_len, 0,
+                           filter_repeat, plan, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -34,6 +34,29 @@ class output_into:
         return False
 
 
+class shared_parameters:
+    """`with shared_parameters(B):` -- tells the processors that the parameter rows they receive repeat in
+    runs of B (rows n*B .. n*B+B-1 are identical): what the 4-D source path of render_grafx produces when it
+    expands the per-node parameters over the batch of renders.  Parameter-side work that is O(samples)
+    (the reverb impulse response and its spectra) is then done once per run."""
+
+    def __init__(self, repeat: int | None):
+        self.repeat = int(repeat) if repeat else 1
+
+    def __enter__(self):
+        self.prev = getattr(_DEST, "repeat", 1)
+        _DEST.repeat = self.repeat
+        return self
+
+    def __exit__(self, *exc):
+        _DEST.repeat = self.prev
+        return False
+
+
+def parameter_repeat() -> int:
+    return getattr(_DEST, "repeat", 1)
+
+
 def _new_output(shape, dtype, device) -> torch.Tensor:
     d = getattr(_DEST, "t", None)
     if d is not None and tuple(d.shape) == tuple(shape) and d.dtype == dtype and d.device == device:
@@ -117,7 +140,7 @@ def _fft_plan(device: torch.device, n: int) -> torch.Tensor:
     return plan
 
 
-def fir_conv(x: torch.Tensor, h: torch.Tensor, mode: str = "causal") -> torch.Tensor:
+def fir_conv(x: torch.Tensor, h: torch.Tensor, mode: str = "causal", h_repeat: int = 1) -> torch.Tensor:
     """Linear convolution sliced to len(x) (reference: convolve(), core/convolution.py:119-134).
 
     x [B, Cx, L] (or [B, L]), h [B, Ch, N] (or [B, N]); channels broadcast; mode "causal" or
@@ -128,7 +151,7 @@ def fir_conv(x: torch.Tensor, h: torch.Tensor, mode: str = "causal") -> torch.Te
     squeeze = x.ndim == 2 and h.ndim == 2
     x3 = x.unsqueeze(1) if x.ndim == 2 else x
     h3 = h.unsqueeze(1) if h.ndim == 2 else h
-    assert x3.ndim == 3 and h3.ndim == 3 and x3.shape[0] == h3.shape[0]
+    assert x3.ndim == 3 and h3.ndim == 3 and x3.shape[0] == h3.shape[0] * h_repeat
     B, cx, L = x3.shape
     _, ch, N = h3.shape
     assert cx == ch or cx == 1 or ch == 1, "channel mismatch between signal and filter"
@@ -141,7 +164,7 @@ def fir_conv(x: torch.Tensor, h: torch.Tensor, mode: str = "causal") -> torch.Te
         zp = int(mode == "zerophase")
         ws = _cabi.workspace(L_.gfx_fir_conv_workspace_bytes(B, cx, ch, L, N, zp), x.device)
         with torch.cuda.device(x.device):
-            code = L_.gfx_fir_conv_f32(x3.data_ptr(), h3.data_ptr(), y.data_ptr(), B, cx, ch, L, N, zp,
+            code = L_.gfx_fir_conv_f32(x3.data_ptr(), h3.data_ptr(), y.data_ptr(), B, cx, ch, L, N, zp, int(h_repeat),
                                        plan.data_ptr(), ws.data_ptr(), ws.numel(), _cabi.stream_ptr())
         _cabi.check(code, "gfx_fir_conv_f32")
     return y.squeeze(1) if squeeze else y
@@ -340,12 +363,13 @@ def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_
     return (ir, energy) if mode in (0, 3) else ir
 
 
-def fir_conv_midside_ir(x: torch.Tensor, ir_raw: torch.Tensor, energy: torch.Tensor, to_lr: bool) -> torch.Tensor:
+def fir_conv_midside_ir(x: torch.Tensor, ir_raw: torch.Tensor, energy: torch.Tensor, to_lr: bool,
+                        h_repeat: int = 1) -> torch.Tensor:
     """Causal convolution of x [B, 1|2, L] with a reverb response given un-normalised ([B, 2, N], rows
     mid/side, or left/right when to_lr) + the energies [B, 2] of its raw mid/side rows:
     normalize_impulse (reverb.py:215-228) is folded into the filter spectra."""
     _cabi.require_cuda(x, ir_raw, energy)
-    assert x.ndim == 3 and ir_raw.ndim == 3 and ir_raw.shape[1] == 2 and x.shape[0] == ir_raw.shape[0]
+    assert x.ndim == 3 and ir_raw.ndim == 3 and ir_raw.shape[1] == 2 and x.shape[0] == ir_raw.shape[0] * h_repeat
     B, cx, L = x.shape
     N = ir_raw.shape[2]
     assert cx in (1, 2), "channel mismatch between signal and filter"
@@ -357,7 +381,7 @@ def fir_conv_midside_ir(x: torch.Tensor, ir_raw: torch.Tensor, energy: torch.Ten
         ws = _cabi.workspace(L_.gfx_fir_conv_workspace_bytes(B, cx, 2, L, N, 0), x.device)
         with torch.cuda.device(x.device):
             code = L_.gfx_fir_conv_midside_ir_f32(x.data_ptr(), ir_raw.data_ptr(), energy.data_ptr(), y.data_ptr(), B,
-                                                  cx, L, N, int(bool(to_lr)), plan.data_ptr(), ws.data_ptr(),
+                                                  cx, L, N, int(bool(to_lr)), int(h_repeat), plan.data_ptr(), ws.data_ptr(),
                                                   ws.numel(), _cabi.stream_ptr())
         _cabi.check(code, "gfx_fir_conv_midside_ir_f32")
     return y

@@ -58,11 +58,20 @@ class STFTMaskedNoiseReverb(nn.Module):
         # un-normalised response (+ row energies) in its final channel layout; normalize_impulse
         # (reverb.py:215-228) happens inside the convolution while the filter spectra are formed
         to_lr = self.processor_channel == "pseudo_midside"
+        # render_grafx (4-D sources) repeats every node's parameters over the batch of renders: synthesise each
+        # response (and its spectra) once
+        rep = F_.parameter_repeat()
+        if rep > 1 and self.fixed_noise and init_log_magnitude.shape[0] % rep == 0:
+            init_log_magnitude, delta_log_magnitude = init_log_magnitude[::rep], delta_log_magnitude[::rep]
+            if gain_env_log_magnitude is not None:
+                gain_env_log_magnitude = gain_env_log_magnitude[::rep]
+        else:
+            rep = 1
         ir_raw, energy = self.compute_ir(init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude,
                                          _finish="raw_lr" if to_lr else "raw")
         if self.processor_channel == "midside":
-            return F_.ms_to_lr(F_.fir_conv_midside_ir(F_.lr_to_ms(input_signals), ir_raw, energy, to_lr=False))
-        return F_.fir_conv_midside_ir(input_signals, ir_raw, energy, to_lr=to_lr)
+            return F_.ms_to_lr(F_.fir_conv_midside_ir(F_.lr_to_ms(input_signals), ir_raw, energy, to_lr=False, h_repeat=rep))
+        return F_.fir_conv_midside_ir(input_signals, ir_raw, energy, to_lr=to_lr, h_repeat=rep)
 
     def parameter_size(self):
         size = {"init_log_magnitude": (2, self.num_bins), "delta_log_magnitude": (2, self.num_bins)}

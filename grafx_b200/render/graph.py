@@ -121,7 +121,8 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
                     common_i = {"parameter": common_i}
             if isinstance(parameters, torch.Tensor):
                 parameters = {"parameter": parameters}
-            with F_.output_into(post(dest_view) if dest_view is not None else None):
+            with F_.output_into(post(dest_view) if dest_view is not None else None), \
+                    F_.shared_parameters(batch_size if (ndim == 4 and common_parameters is None) else 1):
                 output = processors[node_type](*inputs, **parameters, **common_i)
             if isinstance(output, tuple):
                 output_signals, intermediates = output

@@ -91,6 +91,9 @@ GFX_API int gfx_midside_f32(const float* x, float* y, int batch, long long L, fl
  * bytes once per device and fill them with gfx_fft_plan_init.  The workspace holds filter (and,
  * for filter_len > 16384, input-block and output-block) spectra; any size >= the one for batch = 1
  * works, the size returned for the full batch is the fastest.
+ * filter_repeat (>= 1, divides batch): that many consecutive batch items share one filter, i.e. h is
+ * [batch / filter_repeat, ch, filter_len] -- the 4-D path of render_grafx repeats every node's parameters over
+ * the batch of renders (render/graph.py:63-75); filter spectra are then formed once per filter.
  * gfx_fir_set_tuning(long_n, mid_n): FFT size of the partitioned path (4096 | 8192 | 16384) and of the
  * single-partition path for 2048 < filter_len <= mid_n/2 (8192 | 16384); 0 keeps a value.  Changes what
  * gfx_fir_fft_size returns, so fetch the plan again afterwards. */
@@ -99,18 +102,19 @@ GFX_API size_t gfx_fft_plan_bytes(int n);
 GFX_API int gfx_fft_plan_init(void* plan, int n, void* stream);
 GFX_API size_t gfx_fir_conv_workspace_bytes(int batch, int cx, int ch, long long L, int filter_len, int zerophase);
 GFX_API int gfx_fir_conv_f32(const float* x, const float* h, float* y, int batch, int cx, int ch, long long L,
-                             int filter_len, int zerophase, const void* plan, void* workspace,
+                             int filter_len, int zerophase, int filter_repeat, const void* plan, void* workspace,
                              size_t workspace_bytes, void* stream);
 GFX_API int gfx_fir_set_tuning(int long_n, int mid_n);
 /* Same convolution (causal) with the filter given as the UN-NORMALISED impulse response of
  * gfx_reverb_ir_f32 (mode 0: mid/side rows, ms_to_lr = 0; mode 3: left/right rows, ms_to_lr = 1) plus the
  * energies of its raw mid/side rows: normalize_impulse (processors/reverb.py:215-228, core/utils.py:14-18)
  * is applied while the filter spectra are formed, so the normalised IR never exists in memory.
- * ir_raw [batch, 2, ir_len], energy [batch, 2], x [batch, cx, L] (cx = 1 or 2), y [batch, 2, L].
+ * ir_raw [batch / filter_repeat, 2, ir_len], energy [batch / filter_repeat, 2], x [batch, cx, L] (cx = 1 or 2),
+ * y [batch, 2, L].
  * Plan / workspace as for gfx_fir_conv_f32 with ch = 2. */
 GFX_API int gfx_fir_conv_midside_ir_f32(const float* x, const float* ir_raw, const float* energy, float* y, int batch,
-                                        int cx, long long L, int ir_len, int ms_to_lr, const void* plan,
-                                        void* workspace, size_t workspace_bytes, void* stream);
+                                        int cx, long long L, int ir_len, int ms_to_lr, int filter_repeat,
+                                        const void* plan, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- reverb impulse-response synthesis ---------------------------------------------------------
  * Replaces STFTMaskedNoiseReverb.compute_stft_mask / compute_ir (processors/reverb.py:161-200:

@@ -262,6 +262,22 @@ def test_fir_conv_2d_and_broadcast():
     assert_close(F_.fir_conv(x.cuda(), h.cuda()).cpu(), O.convolve(x, h, "causal"), "conv-bcast")
 
 
+@pytest.mark.parametrize("N", [300, 3000, 40000])
+def test_fir_conv_filter_repeat(N):
+    """filter_repeat: runs of consecutive batch items sharing one filter (what render_grafx's 4-D path
+    produces) == the same filters repeated explicitly."""
+    import grafx_b200.functional as F_
+
+    torch.manual_seed(N)
+    x = torch.randn(6, 2, 20000, device="cuda")
+    h = torch.randn(3, 2, N, device="cuda") / N ** 0.5
+    y_ref = F_.fir_conv(x, h.repeat_interleave(2, 0))
+    y = F_.fir_conv(x, h, h_repeat=2)
+    assert torch.equal(y, y_ref)
+    h1 = torch.randn(2, 1, N, device="cuda") / N ** 0.5
+    assert torch.equal(F_.fir_conv(x, h1, h_repeat=3), F_.fir_conv(x, h1.repeat_interleave(3, 0)))
+
+
 def test_cfg3b_firfilter_full_size_impulse_and_linearity():
     """FIRFilter(1023, stereo) at 512 x 2 x 131072: impulse response reproduces the normalised
     taps; linearity; a sampled set of rows against the oracle."""
