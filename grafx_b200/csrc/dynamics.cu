@@ -99,6 +99,7 @@ struct DynCtx {
     const SmootherConst* sc;  // [2*DYN_MAX_STAGES] constants of this row (smem)
     const KneeConst* kc;      // [DYN_MAX_STAGES]
     int tid, lane, warp;
+    int walker;      // thread that walks the ballistics recursion
     int t_idx, row;
     long long t0, remain;
     int sync_parity;
@@ -182,51 +183,70 @@ __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, f
 }
 
 // ---- attack/release ballistics on the register chunk (sequential over the tile)
+//   y' = (u < y) ? ya : yr,  ya = (1-at) y + at u,  yr = (1-rt) y + rt u.   ya - yr = (at - rt)(u - y), so the select
+//   is min(ya, yr) when at >= rt and max(ya, yr) otherwise: the chain is FFMA || FFMA -> FMNMX, no predicate.
+// Only one lane walks the tile, but every instruction it issues still occupies its scheduler's pipe for a whole warp
+// slot (2 cycles; tools/chain_bench.cu: one SM sub-partition sustains ~2 such chains at full speed, 11-14 cycles
+// per step, and halves beyond that), so (a) the products at*u and rt*u are formed by all threads beforehand: the
+// walk issues 3 instructions per sample; (b) the walking lane is lane 0 of the warp chosen from the hardware
+// warp slot so that the walkers of the CTAs resident on an SM spread over all four sub-partitions.
 template <int NT>
 __device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParams& p, float (&u)[32],
                                                   const SmootherDesc& sm, int slot) {
     const float at = cx.sc[slot].at, rt = cx.sc[slot].rt;
+    float4* wa = cx.work4;            // at * u, overwritten by y
+    float4* wr = cx.work4 + NT * 8;   // rt * u
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-        cx.work4[swz_unit(cx.tid, c)] = make_float4(u[4 * c], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
+    for (int c = 0; c < 8; ++c) {
+        const int idx = swz_unit(cx.tid, c);
+        wa[idx] = make_float4(at * u[4 * c], at * u[4 * c + 1], at * u[4 * c + 2], at * u[4 * c + 3]);
+        wr[idx] = make_float4(rt * u[4 * c], rt * u[4 * c + 1], rt * u[4 * c + 2], rt * u[4 * c + 3]);
+    }
     ensure_state(cx, p);
     __syncthreads();
-    if (cx.tid == 0) {
-        // the recursion is a dependent chain (2 FFMA + compare + select per sample): keep everything else off
-        // it -- a chunk's loads are issued together one chunk ahead, at*u / rt*u do not depend on y
+    if (cx.tid == cx.walker) {
         float y = cx.s_state[slot];
         const float omat = 1.f - at, omrt = 1.f - rt;
-        float4 cur[8], nxt[8];
+        const bool use_min = at >= rt;
+        float4 ca[4], cr[4], na[4], nr[4];  // half a row (16 samples) in flight, the next half already loading
 #pragma unroll
-        for (int c = 0; c < 8; ++c) cur[c] = cx.work4[swz_unit(0, c)];
+        for (int c = 0; c < 4; ++c) { ca[c] = wa[swz_unit(0, c)]; cr[c] = wr[swz_unit(0, c)]; }
 #pragma unroll 1
-        for (int r = 0; r < NT; ++r) {
-            const int rn = r + 1 < NT ? r + 1 : r;
+        for (int hh = 0; hh < 2 * NT; ++hh) {
+            const int r = hh >> 1, c0 = (hh & 1) * 4;
+            const int hn = hh + 1 < 2 * NT ? hh + 1 : hh;
+            const int rn = hn >> 1, cn = (hn & 1) * 4;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) nxt[c] = cx.work4[swz_unit(rn, c)];
+            for (int c = 0; c < 4; ++c) { na[c] = wa[swz_unit(rn, cn + c)]; nr[c] = wr[swz_unit(rn, cn + c)]; }
+            if (use_min) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float* e = reinterpret_cast<float*>(&cur[c]);
+                for (int c = 0; c < 4; ++c) {
+                    float* a = reinterpret_cast<float*>(&ca[c]);
+                    const float* b = reinterpret_cast<const float*>(&cr[c]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float ua = at * e[k], ur = rt * e[k];
-                    const float ya = fmaf(omat, y, ua);
-                    const float yr = fmaf(omrt, y, ur);
-                    y = e[k] < y ? ya : yr;
-                    e[k] = y;
+                    for (int k = 0; k < 4; ++k) { y = fminf(fmaf(omat, y, a[k]), fmaf(omrt, y, b[k])); a[k] = y; }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float* a = reinterpret_cast<float*>(&ca[c]);
+                    const float* b = reinterpret_cast<const float*>(&cr[c]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { y = fmaxf(fmaf(omat, y, a[k]), fmaf(omrt, y, b[k])); a[k] = y; }
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                cx.work4[swz_unit(r, c)] = cur[c];
-                cur[c] = nxt[c];
+            for (int c = 0; c < 4; ++c) {
+                wa[swz_unit(r, c0 + c)] = ca[c];
+                ca[c] = na[c];
+                cr[c] = nr[c];
             }
         }
     }
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const float4 v = cx.work4[swz_unit(cx.tid, c)];
+        const float4 v = wa[swz_unit(cx.tid, c)];
         u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
     }
     if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles) {
@@ -393,7 +413,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
     DynCtx<NT> cx;
     cx.xs4 = reinterpret_cast<float4*>(smem_raw);
     cx.work4 = cx.xs4 + (size_t)p.C * NT * 8;
-    float* consts = reinterpret_cast<float*>(cx.work4 + (NT == 64 ? (size_t)NT * 8 : 0));  // [DYN_ROW_FLOATS]
+    float* consts = reinterpret_cast<float*>(cx.work4 + (NT == 64 ? (size_t)NT * 16 : 0));  // [DYN_ROW_FLOATS]
     cx.sc = reinterpret_cast<const SmootherConst*>(consts);
     cx.kc = reinterpret_cast<const KneeConst*>(consts + 2 * DYN_MAX_STAGES * DYN_SC_FLOATS);
     cx.wt = consts + DYN_ROW_FLOATS;
@@ -401,6 +421,19 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
     float* xs = reinterpret_cast<float*>(cx.xs4);
     __shared__ unsigned int sh_item;
     cx.tid = threadIdx.x; cx.lane = cx.tid & 31; cx.warp = cx.tid >> 5;
+    {
+        // two-warp CTAs usually occupy hardware warp slots (2j, 2j+1) -> sub-partitions (0,1) or (2,3); taking warp
+        // (j >> 1) & 1 as the walker puts the j-th resident CTA's walker on sub-partition {0, 2, 1, 3}[j & 3].
+        // One thread decides for the CTA (the slots of its warps need not be adjacent).
+        __shared__ int sh_walker;
+        if (cx.tid == 0) {
+            unsigned wid;
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+            sh_walker = (NT == 64) ? (int)(((wid >> 2) & 1u) * 32u) : 0;
+        }
+        __syncthreads();
+        cx.walker = sh_walker;
+    }
     const int C = p.C;
     const float inv_c = 1.f / (float)C;
 
@@ -574,8 +607,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
 }
 
 static size_t dyn_smem_bytes(int NT, int C) {
-    // the scratch tile is only used by the ballistics variant (NT == 64)
-    return (size_t)(C + (NT == 64 ? 1 : 0)) * NT * 128 +
+    // two scratch tiles (at*u, rt*u) are only used by the ballistics variant (NT == 64)
+    return (size_t)(C + (NT == 64 ? 2 : 0)) * NT * 128 +
            (size_t)(DYN_ROW_FLOATS + 2 * (NT / 32) + 2 * DYN_MAX_STAGES) * sizeof(float) + 64;
 }
 

@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(MAC_NT, 2) fir_mac_kernel(const float4* __rest
 #pragma unroll
         for (int p = 0; p < PC; ++p) { h[p].x = 0.f; h[p].y = 0.f; }
     }
-    constexpr int G = PC < 4 ? PC : (PC >= 10 ? 2 : 4);  // loads issued together
+    constexpr int G = PC < 4 ? PC : 4;  // loads issued together
     const int last = nblk - 1 - p0;     // last valid input block index for this partition group
 #pragma unroll 1
     for (int j0 = p0; j0 < nblk; j0 += PC) {

@@ -40,6 +40,12 @@ struct ReverbParams {
     int frames, ir_len, tiles, vec_ok, to_lr;
 };
 
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 // inverse DFT-3 (unnormalised): y_r = sum_m a_m e^{+2 pi i m r / 3}
 __device__ __forceinline__ void idft3(pk2& a0, pk2& a1, pk2& a2) {
     const pk2 s = pk_add(a1, a2), d = pk_sub(a1, a2);
@@ -109,10 +115,12 @@ __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbPar
             hw[t - RV_N] = make_float2(c, -sn);
         }
     }
+    // mask exponent in base 2: exp((H0 - softplus(Hd) m + G[m]) / 8) = ex2((H0 - softplus(Hd) m + G[m]) log2(e) / 8)
+    constexpr float kScale = 1.4426950408889634f * 0.125f;
     for (int k = tid; k < RV_BINS; k += RV_NT) {
-        a0[k] = p.h0[(size_t)row * RV_BINS + k];
+        a0[k] = p.h0[(size_t)row * RV_BINS + k] * kScale;
         const float d = p.hd[(size_t)row * RV_BINS + k];
-        a1[k] = d > 20.f ? d : log1pf(expf(d));  // torch softplus
+        a1[k] = (d > 20.f ? d : log1pf(expf(d))) * kScale;  // torch softplus
     }
     __syncthreads();
 
@@ -123,19 +131,19 @@ __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbPar
         const int m = m0 + f;
         const bool fv = m < p.frames;
         const float fm = (float)m;
-        const float ge = (genv && fv) ? genv[m] : 0.f;
+        const float ge = (genv && fv) ? genv[m] * kScale : 0.f;
         const float2* np = noise + (fv ? m : 0);
         pk2* zf = zb + f * RV_ZS;
 #pragma unroll 4
         for (int k = kq; k < RV_BINS - 1; k += 16) {
             const float2 nz = __ldg(np + (size_t)k * p.frames);
-            const float mk = fv ? __expf(((a0[k] - a1[k] * fm) + ge) * 0.125f) : 0.f;
+            const float mk = fv ? ex2_approx((a0[k] - a1[k] * fm) + ge) : 0.f;
             zf[k] = pk_make(nz.x * mk, nz.y * mk);
         }
         if (kq == 0) {
             const int k = RV_BINS - 1;
             const float2 nz = __ldg(np + (size_t)k * p.frames);
-            const float mk = fv ? __expf(((a0[k] - a1[k] * fm) + ge) * 0.125f) : 0.f;
+            const float mk = fv ? ex2_approx((a0[k] - a1[k] * fm) + ge) : 0.f;
             xn[f] = nz.x * mk;
         }
     }
@@ -229,8 +237,10 @@ __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbPar
             const float e1 = h < p.frames ? 1.f : 0.f;
             const float ex = fmaf(e1 * w1.x, w1.x, w2.x * w2.x), ey = fmaf(e1 * w1.y, w1.y, w2.y * w2.y);
             const float ez = fmaf(e1 * w1.z, w1.z, w2.z * w2.z), ew = fmaf(e1 * w1.w, w1.w, w2.w * w2.w);
-            const float4 vm = make_float4((am.x + cm.x) / ex, (am.y + cm.y) / ey, (am.z + cm.z) / ez, (am.w + cm.w) / ew);
-            const float4 vs = make_float4((as.x + cs.x) / ex, (as.y + cs.y) / ey, (as.z + cs.z) / ez, (as.w + cs.w) / ew);
+            // envelope division as a multiplication by the SFU reciprocal (error ~1 ulp), shared by both channels
+            const float rx = __frcp_rn(ex), ry = __frcp_rn(ey), rz = __frcp_rn(ez), rw = __frcp_rn(ew);
+            const float4 vm = make_float4((am.x + cm.x) * rx, (am.y + cm.y) * ry, (am.z + cm.z) * rz, (am.w + cm.w) * rw);
+            const float4 vs = make_float4((as.x + cs.x) * rx, (as.y + cs.y) * ry, (as.z + cs.z) * rz, (as.w + cs.w) * rw);
             em = fmaf(vm.x, vm.x, em); em = fmaf(vm.y, vm.y, em); em = fmaf(vm.z, vm.z, em); em = fmaf(vm.w, vm.w, em);
             es = fmaf(vs.x, vs.x, es); es = fmaf(vs.y, vs.y, es); es = fmaf(vs.z, vs.z, es); es = fmaf(vs.w, vs.w, es);
             if (p.to_lr) {
