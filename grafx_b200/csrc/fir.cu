@@ -371,10 +371,11 @@ struct OpFilter {  // untangle, multiply by the (1/N-scaled) filter spectrum, re
         zh = pk_make(r2.x, r2.y);
     }
 };
-struct OpLoad {  // global pair slot -> retangle -> registers
+template <bool COHERENT = false>
+struct OpLoad {  // global pair slot -> retangle -> registers (COHERENT: the slot was written earlier in this launch)
     const float4* Y;
     typedef float4 Data;
-    __device__ __forceinline__ Data fetch(int slot) const { return ldg_stream(Y + slot); }
+    __device__ __forceinline__ Data fetch(int slot) const { return COHERENT ? __ldcg(Y + slot) : ldg_stream(Y + slot); }
     __device__ __forceinline__ void pair(pk2& zk, pk2& zm, float2 w, Data y, int) const {
         const PairA a = retangle_pair(make_float2(y.x, y.y), make_float2(y.z, y.w), w);
         zk = pk_make(a.k.x, a.k.y);
@@ -477,7 +478,10 @@ struct FilterSrc {
 
 // NT = N/32 threads; registers: two butterflies (64) + pair operands live in the fused phase
 __host__ __device__ constexpr int fir_nt(int n) { return n / 32; }
-__host__ __device__ constexpr int fir_min_blocks(int n) { return n == 1024 ? 16 : (n == 4096 ? 4 : (n == 8192 ? 2 : 1)); }
+#ifndef GFX_FIR_MB8192
+#define GFX_FIR_MB8192 2
+#endif
+__host__ __device__ constexpr int fir_min_blocks(int n) { return n == 1024 ? 16 : (n == 4096 ? 4 : (n == 8192 ? GFX_FIR_MB8192 : 1)); }
 
 // ------------------------------------------------------------------ kernels
 // forward transform of one real segment into pair slots: shared tail of the spectrum kernels
@@ -655,13 +659,203 @@ __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_inv_kernel(c
     const ushort2 pr = plan_pairtab<N>(plan)[t];
     {
         pk2 A[16], B[16];
-        pair_phase<N, false, true>(A, B, t, plan, OpLoad{Ys + (size_t)blockIdx.x * (N / 2)});
+        pair_phase<N, false, true>(A, B, t, plan, OpLoad<false>{Ys + (size_t)blockIdx.x * (N / 2)});
         first_inverse(zbuf, pr.x, A);
         first_inverse(zbuf, pr.y, B);
     }
     const size_t row = (size_t)(row0 + rloc);
     const SegDst<FAST> dst(y + row * L, (long long)j * N - shift, L, N, 2 * N);
     fft_inverse_back<N, NT>(zbuf, plan, dst);
+}
+
+// ------------------------------------------------------------------ long filters: one persistent pipelined launch
+// The four steps above as WORK ITEMS of one launch (one CTA = one item at a time, atomic ticket), so that the
+// spectra never leave L2: item kinds  H (filter-partition spectrum), X (input-block spectrum), M (per-slot
+// multiply-accumulate of one output row over one sixteenth of the slots), O (inverse transform of one output block).
+// Tickets are laid out as a software pipeline over the batch: step s issues  H/X of item s+2D,  M of item s+D,
+// O of item s;  an item that needs data waits on per-item completion counters, and since everything it can wait
+// for has a smaller ticket (already running or done) the launch cannot deadlock.  Spectra live in a ring of R item
+// slots (R >= 2D + 3, ~5.5 MB per item at the BASELINE reverb shape): the live set is ~50 MB and stays in the 126 MB L2.
+struct UpolsJob {
+    const float* x; FilterSrc fs; float* y;
+    float4* Hs; float4* Xs; float4* Ys;   // rings [R][ch*P][half], [R][cx*nblk][half], [R][c_out*nblk][half]
+    unsigned int* ticket;
+    int* cntH; int* cntX; int* cntM; int* cntMH; int* cntO;  // [batch] completion counters (H, MH by filter item)
+    int batch, cx, ch, c_out, h_rep;
+    long long L;
+    int Nh, P, nblk, shift, R, D;
+    const float2* plan;
+};
+
+__device__ __forceinline__ void item_wait(const int* cnt, int target) {
+    if (threadIdx.x == 0) {
+        const volatile int* v = cnt;
+        while (*v < target) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void item_done(int* cnt) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(cnt, 1);
+    }
+}
+
+// M item: output row (b, c), slots [slab NT, (slab+1) NT): all partitions (P <= MAC_MAX_PC, the rest of the register
+// ring holds zeros).  Same loop as fir_mac_kernel, on L2-coherent loads.
+template <int NT>
+__device__ __forceinline__ void mac_item(const float4* __restrict__ Xrow, const float4* __restrict__ Hrow,
+                                         float4* __restrict__ Yrow, int P, int nblk, int half, int slab) {
+    constexpr int PC = MAC_MAX_PC;
+    const int q = slab * NT + threadIdx.x;
+    const float4* X = Xrow + q;
+    const float4* H = Hrow + q;
+    float4* Y = Yrow + q;
+    float4 h[PC], ring[PC];
+#pragma unroll
+    for (int p = 0; p < PC; ++p) {
+        h[p] = p < P ? __ldcg(H + (size_t)p * half) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ring[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (q == 0) {
+#pragma unroll
+        for (int p = 0; p < PC; ++p) { h[p].x = 0.f; h[p].y = 0.f; }
+    }
+    constexpr int G = 4;
+    const int last = nblk - 1;
+#pragma unroll 1
+    for (int j0 = 0; j0 < nblk; j0 += PC) {
+#pragma unroll
+        for (int g0 = 0; g0 < PC; g0 += G) {
+            float4 xn[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                int jb = j0 + g0 + g;
+                jb = jb < last ? jb : last;
+                xn[g] = __ldcg(X + (size_t)jb * half);
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int jj = g0 + g;
+                const int j = j0 + jj;
+                ring[jj] = xn[g];
+                if (j < nblk) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int p = 0; p < PC; ++p) cmac4(acc, ring[(jj - p + PC) % PC], h[p]);
+                    Y[(size_t)j * half] = acc;
+                }
+            }
+        }
+    }
+    if (slab == 0 && threadIdx.x < 32) {
+        // DC / Nyquist of every block (the .xy lanes of slot 0): lanes over output blocks
+        __syncwarp();
+        for (int j = (int)threadIdx.x; j < nblk; j += 32) {
+            float a0 = 0.f, an = 0.f;
+            for (int p = 0; p < P && p <= j; ++p) {
+                const float4 xv = __ldcg(Xrow + (size_t)(j - p) * half);
+                const float4 hv = __ldcg(Hrow + (size_t)p * half);
+                a0 = fmaf(xv.x, hv.x, a0);
+                an = fmaf(xv.y, hv.y, an);
+            }
+            // slot 0 of block j was stored by lane 0 in the loop above (ordered by the __syncwarp); go through L2
+            float4 v = __ldcg(Yrow + (size_t)j * half);
+            v.x += a0;
+            v.y += an;
+            __stcg(Yrow + (size_t)j * half, v);
+        }
+    }
+}
+
+template <int N, bool FAST>
+__global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_upols_pipeline_kernel(const UpolsJob jb) {
+    constexpr int NT = fir_nt(N), half = N / 2, NSLAB = half / NT;
+    extern __shared__ __align__(16) pk2 zbuf[];
+    __shared__ unsigned int sh_ticket;
+    const int nH = jb.ch * jb.P, nX = jb.cx * jb.nblk, nM = jb.c_out * NSLAB, nO = jb.c_out * jb.nblk;
+    const int per_step = nH + nX + nM + nO;
+    const long long total = (long long)(jb.batch + 2 * jb.D) * per_step;
+    const int t = threadIdx.x;
+    for (;;) {
+        __syncthreads();
+        if (t == 0) sh_ticket = atomicAdd(jb.ticket, 1u);
+        __syncthreads();
+        const unsigned int tk = sh_ticket;
+        if ((long long)tk >= total) break;
+        const int step = (int)(tk / (unsigned)per_step) - 2 * jb.D;
+        int u = (int)(tk % (unsigned)per_step);
+        if (u < nH) {
+            // ---- H item: partition `part` of filter row (hb, c)
+            const int b = step + 2 * jb.D;
+            if (b >= jb.batch || (b % jb.h_rep) != 0) continue;
+            const int hb = b / jb.h_rep;
+            if (hb >= jb.R) item_wait(jb.cntMH + (hb - jb.R), jb.h_rep * nM);  // ring slot free (its readers are done)
+            const int c = u / jb.P, part = u - c * jb.P;
+            const int hrow = hb * jb.ch + c;
+            const long long s0 = (long long)part * N;
+            long long end = s0 + N;
+            if (end > jb.Nh) end = jb.Nh;
+            float scale = 1.f / (float)N;
+            if (jb.fs.energy) {
+                const float e0 = jb.fs.energy[hrow & ~1], e1 = jb.fs.energy[hrow | 1];
+                scale *= jb.fs.to_lr ? rsqrtf(e0 + e1 + 1e-12f) : rsqrtf(0.5f * (e0 + e1) + 1e-12f);
+            }
+            // (the filter rows are read-only inputs: the generic, alignment-agnostic source is used when FAST is off)
+            const SegSrc<FAST> src(jb.fs.h + (size_t)hrow * jb.Nh, s0, end, 2 * N);
+            segment_spectrum<N>(zbuf, jb.plan, src, jb.Hs + ((size_t)(hb % jb.R) * nH + u) * half, scale);
+            item_done(jb.cntH + hb);
+        } else if (u < nH + nX) {
+            // ---- X item: block j of input row (b, c)
+            u -= nH;
+            const int b = step + 2 * jb.D;
+            if (b >= jb.batch) continue;
+            if (b >= jb.R) item_wait(jb.cntM + (b - jb.R), nM);
+            const int c = u / jb.nblk, j = u - c * jb.nblk;
+            const SegSrc<FAST> src(jb.x + (size_t)(b * jb.cx + c) * jb.L, ((long long)j - 1) * N, jb.L, 2 * N);
+            segment_spectrum<N>(zbuf, jb.plan, src, jb.Xs + ((size_t)(b % jb.R) * nX + u) * half, 1.f);
+            item_done(jb.cntX + b);
+        } else if (u < nH + nX + nM) {
+            // ---- M item
+            u -= nH + nX;
+            const int b = step + jb.D;
+            if (b < 0 || b >= jb.batch) continue;
+            const int hb = b / jb.h_rep;
+            item_wait(jb.cntH + hb, nH);
+            item_wait(jb.cntX + b, nX);
+            if (b >= jb.R) item_wait(jb.cntO + (b - jb.R), nO);
+            const int c = u / NSLAB, slab = u - c * NSLAB;
+            const float4* Xrow = jb.Xs + ((size_t)(b % jb.R) * nX + (size_t)(jb.cx == 1 ? 0 : c) * jb.nblk) * half;
+            const float4* Hrow = jb.Hs + ((size_t)(hb % jb.R) * nH + (size_t)(jb.ch == 1 ? 0 : c) * jb.P) * half;
+            float4* Yrow = jb.Ys + ((size_t)(b % jb.R) * nO + (size_t)c * jb.nblk) * half;
+            mac_item<NT>(Xrow, Hrow, Yrow, jb.P, jb.nblk, half, slab);
+            __syncthreads();
+            if (t == 0) {
+                __threadfence();
+                atomicAdd(jb.cntM + b, 1);
+                atomicAdd(jb.cntMH + hb, 1);
+            }
+        } else {
+            // ---- O item: output block j of row (b, c)
+            u -= nH + nX + nM;
+            const int b = step;
+            if (b < 0) continue;
+            item_wait(jb.cntM + b, nM);
+            const int c = u / jb.nblk, j = u - c * jb.nblk;
+            const ushort2 pr = plan_pairtab<N>(jb.plan)[t];
+            {
+                pk2 A[16], B[16];
+                pair_phase<N, false, true>(A, B, t, jb.plan, OpLoad<true>{jb.Ys + ((size_t)(b % jb.R) * nO + u) * half});
+                first_inverse(zbuf, pr.x, A);
+                first_inverse(zbuf, pr.y, B);
+            }
+            const SegDst<FAST> dst(jb.y + (size_t)(b * jb.c_out + c) * jb.L, (long long)j * N - jb.shift, jb.L, N, 2 * N);
+            fft_inverse_back<N, NT>(zbuf, jb.plan, dst);
+            item_done(jb.cntO + b);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ plan construction
@@ -830,6 +1024,53 @@ static int run_upols(const FirArgs& a) {
     return GFX_OK;
 }
 
+static int g_upols_d = 4;  // pipeline look-ahead (batch items); ring slots = 2 D + 4
+static int upols_r() { return 2 * g_upols_d + 4; }
+static size_t upols_ctr_bytes(int batch) { return (256 + (size_t)5 * batch * sizeof(int) + 255) / 256 * 256; }
+
+template <int N>
+static int run_upols_pipeline(const FirArgs& a) {
+    const int c_out = a.cx > a.ch ? a.cx : a.ch;
+    int P; long long nblk; size_t per_item;
+    upols_geometry(a.cx, a.ch, a.L, a.Nh, a.shift, N, P, nblk, per_item);
+    const size_t ctr = upols_ctr_bytes(a.batch);
+    if (!a.ws || a.ws_bytes < ctr + (size_t)upols_r() * per_item) return GFX_ERR_WORKSPACE;
+    const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
+    static bool configured = false;
+    if (!configured) {
+        if (set_smem(fir_upols_pipeline_kernel<N, true>, smem) || set_smem(fir_upols_pipeline_kernel<N, false>, smem)) return GFX_ERR_CUDA;
+        configured = true;
+    }
+    constexpr int half = N / 2;
+    UpolsJob j;
+    j.x = a.x; j.fs = a.fs; j.y = a.y;
+    unsigned char* w = a.ws;
+    j.ticket = (unsigned int*)w;
+    int* cnt = (int*)(w + 256);
+    j.cntH = cnt; j.cntX = cnt + a.batch; j.cntM = cnt + 2 * (size_t)a.batch; j.cntMH = cnt + 3 * (size_t)a.batch;
+    j.cntO = cnt + 4 * (size_t)a.batch;
+    j.Hs = (float4*)(w + ctr);
+    j.Xs = j.Hs + (size_t)upols_r() * a.ch * P * half;
+    j.Ys = j.Xs + (size_t)upols_r() * a.cx * nblk * half;
+    j.batch = a.batch; j.cx = a.cx; j.ch = a.ch; j.c_out = c_out; j.h_rep = a.h_rep;
+    j.L = a.L; j.Nh = a.Nh; j.P = P; j.nblk = (int)nblk; j.shift = a.shift; j.R = upols_r(); j.D = g_upols_d;
+    j.plan = a.plan;
+    GFX_CUDA_CHECK(cudaMemsetAsync(w, 0, ctr, a.stream));
+    const bool fast = a.fast_x && a.fast_h;
+    int occ = 0;
+    if (fast) GFX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fir_upols_pipeline_kernel<N, true>, fir_nt(N), smem));
+    else GFX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fir_upols_pipeline_kernel<N, false>, fir_nt(N), smem));
+    if (occ < 1) return GFX_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)(device_info().sm_count * occ);
+    if (fast) fir_upols_pipeline_kernel<N, true><<<grid, fir_nt(N), smem, a.stream>>>(j);
+    else fir_upols_pipeline_kernel<N, false><<<grid, fir_nt(N), smem, a.stream>>>(j);
+    GFX_LAUNCH_CHECK();
+    return GFX_OK;
+}
+
+static int g_long_mode = 0;  // 0: four kernels per sweep (fastest on B200: 1.94 vs 2.16 ms at the BASELINE reverb shape);
+                             // 1: one persistent pipelined launch, spectra L2-resident (2.4x less DRAM traffic), P <= 12
+
 static int fir_dispatch(const FirArgs& a) {
     const int n = pick_fft_size(a.Nh);
     if (a.Nh <= 16384) {
@@ -837,6 +1078,13 @@ static int fir_dispatch(const FirArgs& a) {
         if (n == 4096) return run_ols<4096>(a);
         if (n == 8192) return run_ols<8192>(a);
         return run_ols<16384>(a);
+    }
+    const int P = (a.Nh + n - 1) / n;
+    if (g_long_mode == 1 && P <= MAC_MAX_PC && n == 8192) {
+        int Pg; long long nblk; size_t per_item;
+        upols_geometry(a.cx, a.ch, a.L, a.Nh, a.shift, n, Pg, nblk, per_item);
+        if (a.ws_bytes >= upols_ctr_bytes(a.batch) + (size_t)upols_r() * per_item && (long long)a.batch * 5 < 0x7fffffffLL)
+            return run_upols_pipeline<8192>(a);
     }
     if (n == 4096) return run_upols<4096>(a);
     if (n == 8192) return run_upols<8192>(a);
@@ -856,6 +1104,14 @@ int gfx_fir_set_tuning(int long_n, int mid_n) {
         if (mid_n != 8192 && mid_n != 16384) return GFX_ERR_INVALID;
         gfx::g_mid_n = mid_n;
     }
+    return GFX_OK;
+}
+
+int gfx_fir_set_long_mode(int mode, int lookahead) {
+    if (mode != 0 && mode != 1) return GFX_ERR_INVALID;
+    if (lookahead < 0 || lookahead > 16) return GFX_ERR_INVALID;
+    gfx::g_long_mode = mode;
+    if (lookahead) gfx::g_upols_d = lookahead;
     return GFX_OK;
 }
 
@@ -895,6 +1151,8 @@ size_t gfx_fir_conv_workspace_bytes(int batch, int cx, int ch, long long L, int 
     if (filter_len <= 16384) return (size_t)batch * ch * (n / 2) * sizeof(float4);
     int P; long long nblk; size_t per_item;
     gfx::upols_geometry(cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, n, P, nblk, per_item);
+    if (gfx::g_long_mode == 1 && P <= gfx::MAC_MAX_PC && n == 8192)
+        return gfx::upols_ctr_bytes(batch) + (size_t)gfx::upols_r() * per_item;  // pipelined launch: a ring of item slots
     // spectra of up to ~1.5 GB worth of batch items per sweep (every kernel of a sweep then has several full waves)
     size_t items = ((size_t)1536 << 20) / per_item;
     if (items < 1) items = 1;

@@ -105,6 +105,11 @@ GFX_API int gfx_fir_conv_f32(const float* x, const float* h, float* y, int batch
                              int filter_len, int zerophase, int filter_repeat, const void* plan, void* workspace,
                              size_t workspace_bytes, void* stream);
 GFX_API int gfx_fir_set_tuning(int long_n, int mid_n);
+/* long filters (> 16384 taps): 0 (default, fastest as measured) = four kernels per sweep with the spectra in HBM;
+ * 1 = one persistent pipelined launch whose spectra stay in L2 (2.4x less DRAM traffic, ~10 % slower; used when the
+ * filter has <= 12 partitions of 8192 taps).  Affects the
+ * workspace size: query it again afterwards. */
+GFX_API int gfx_fir_set_long_mode(int mode, int lookahead); /* lookahead: pipeline depth in batch items (0 keeps it) */
 /* Same convolution (causal) with the filter given as the UN-NORMALISED impulse response of
  * gfx_reverb_ir_f32 (mode 0: mid/side rows, ms_to_lr = 0; mode 3: left/right rows, ms_to_lr = 1) plus the
  * energies of its raw mid/side rows: normalize_impulse (processors/reverb.py:215-228, core/utils.py:14-18)

@@ -278,6 +278,30 @@ def test_fir_conv_filter_repeat(N):
     assert torch.equal(F_.fir_conv(x, h1, h_repeat=3), F_.fir_conv(x, h1.repeat_interleave(3, 0)))
 
 
+def test_fir_long_filter_pipelined_launch_matches():
+    """The persistent pipelined launch of the long-filter path (gfx_fir_set_long_mode(1)) against the default
+    four-kernel sweeps and the oracle: stereo, mono-in, shared filters, more items than ring slots."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.functional as F_
+    from grafx_b200 import _cabi
+
+    torch.manual_seed(5)
+    L_ = _cabi.lib()
+    x = torch.randn(20, 2, 30000, device="cuda")
+    h = torch.randn(20, 2, 40000, device="cuda") / 200.0
+    x1 = torch.randn(20, 1, 30000, device="cuda")
+    h4 = torch.randn(5, 2, 40000, device="cuda") / 200.0
+    try:
+        ref = [F_.fir_conv(x, h), F_.fir_conv(x1, h), F_.fir_conv(x, h4, h_repeat=4)]
+        assert L_.gfx_fir_set_long_mode(1, 0) == 0
+        out = [F_.fir_conv(x, h), F_.fir_conv(x1, h), F_.fir_conv(x, h4, h_repeat=4)]
+    finally:
+        L_.gfx_fir_set_long_mode(0, 0)
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b)
+    assert_close(out[0][:3].cpu(), O.convolve(x[:3].cpu().double(), h[:3].cpu().double(), "causal").float(), "pipe", tol=2e-5)
+
+
 def test_cfg3b_firfilter_full_size_impulse_and_linearity():
     """FIRFilter(1023, stereo) at 512 x 2 x 131072: impulse response reproduces the normalised
     taps; linearity; a sampled set of rows against the oracle."""

@@ -32,3 +32,9 @@ for Nh, key in ((96000, "long"), (60000, "long"), (4000, "mid"), (16384, "mid"),
         ms = timeit(lambda: F_.fir_conv(x, h))
         print(f"taps {Nh:6d} n={L_.gfx_fir_fft_size(Nh):6d}: {ms:8.3f} ms  {B*2*L/ms/1e6:8.1f} Gsamples/s  {8*B*2*L/ms/1e6:7.0f} GB/s", flush=True)
 L_.gfx_fir_set_tuning(8192, 8192)
+h = torch.randn(B, 2, 96000, device="cuda") / 96000 ** 0.5
+for mode, d in ((0, 0), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (1, 8)):
+    L_.gfx_fir_set_long_mode(mode, d)
+    ms = timeit(lambda: F_.fir_conv(x, h))
+    print(f"long mode {mode} lookahead {d}: taps 96000: {ms:8.3f} ms", flush=True)
+L_.gfx_fir_set_long_mode(0, 4)
