@@ -68,6 +68,9 @@ SIGNATURES = {
                                  c_void_p]),
     "gfx_biquad_design_f32": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_void_p]),
+    "gfx_row_mean_f32": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_void_p]),
+    "gfx_pointwise_f32": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_int, c_void_p]),
     "gfx_midside_f32": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_float, c_void_p]),
 }
 

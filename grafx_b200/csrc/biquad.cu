@@ -43,6 +43,7 @@ struct CascadeParams {
     int* flags;  // [rows]   number of finished tiles of the row
     T* state;    // [rows][2K] (y_k[-1], y_k[-2]) left by the last finished tile
     unsigned long long* xstate;  // packed-kernel variant: [rows][K][2] {value, tag} words
+    const double* xtables;       // packed-kernel variant: [coef rows][K][X2_TAB][4] doubles
     int aligned;  // 1: x/y rows are 16-byte aligned (vector path)
 };
 
@@ -92,6 +93,68 @@ __global__ void __launch_bounds__(128) cascade_tables_kernel(const T* __restrict
         out[34 * 4 + 0] = -na2; out[34 * 4 + 1] = T(0); out[34 * 4 + 2] = T(0); out[34 * 4 + 3] = T(0);
         mat2_mul(base, base, tmp);  // M^64
         out[35 * 4 + 0] = (T)tmp[0]; out[35 * 4 + 1] = (T)tmp[1]; out[35 * 4 + 2] = (T)tmp[2]; out[35 * 4 + 3] = (T)tmp[3];
+    }
+}
+
+// ---- tables of the packed fp32 kernel, in DOUBLE: the carried state of a low-frequency section (poles within
+// ~1e-2 of z = 1: every bass EQ band) is a difference of terms hundreds of times larger than itself, and the
+// chunk matrices M^l have near-parallel eigenvectors -- rounded to fp32 they describe a different (even unstable)
+// filter.  So: state propagation in double with exact (double) powers of the matrix the fp32 coefficients define;
+// the per-sample recursions stay fp32 on those same coefficients (arithmetically the reference's loop).
+// Per (coefficient row, section), X2_TAB entries of 4 doubles:
+//   [l] = M^l, l = 0..32 (M = A^32);  [33] = N: end-state response to the two inputs before a chunk;
+//   [34] = (b0, b1, b2, -a1);  [35] = M^64;  [36] = (-a2, 0, 0, 0)          (coefficients normalised in fp32)
+constexpr int X2_TAB = 37;
+
+__global__ void __launch_bounds__(128) cascade_x2_tables_kernel(const float* __restrict__ Bs, const float* __restrict__ As,
+                                                                double* __restrict__ tables, int n_sections) {
+    constexpr int S = 32;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_sections) return;
+    const float* bp = Bs + (size_t)w * 3;
+    const float* ap = As + (size_t)w * 3;
+    const float a0 = ap[0];
+    const float nb0 = bp[0] / a0, nb1 = bp[1] / a0, nb2 = bp[2] / a0;
+    const float na1 = ap[1] / a0, na2 = ap[2] / a0;
+    const double A[4] = {-(double)na1, -(double)na2, 1.0, 0.0};
+    double base[4] = {A[0], A[1], A[2], A[3]}, tmp[4];
+#pragma unroll 1
+    for (int sq = 1; sq < S; sq <<= 1) {  // M = A^S
+        mat2_mul(base, base, tmp);
+        base[0] = tmp[0]; base[1] = tmp[1]; base[2] = tmp[2]; base[3] = tmp[3];
+    }
+    double res[4] = {1.0, 0.0, 0.0, 1.0};  // lane l -> M^l
+#pragma unroll 1
+    for (int bit = 0; bit < 5; ++bit) {
+        if ((lane >> bit) & 1) {
+            mat2_mul(res, base, tmp);
+            res[0] = tmp[0]; res[1] = tmp[1]; res[2] = tmp[2]; res[3] = tmp[3];
+        }
+        mat2_mul(base, base, tmp);
+        base[0] = tmp[0]; base[1] = tmp[1]; base[2] = tmp[2]; base[3] = tmp[3];
+    }
+    double* out = tables + (size_t)w * X2_TAB * 4;
+    out[lane * 4 + 0] = res[0]; out[lane * 4 + 1] = res[1]; out[lane * 4 + 2] = res[2]; out[lane * 4 + 3] = res[3];
+    if (lane == 0) {
+        out[32 * 4 + 0] = base[0]; out[32 * 4 + 1] = base[1]; out[32 * 4 + 2] = base[2]; out[32 * 4 + 3] = base[3];
+        mat2_mul(base, base, tmp);  // M^64
+        out[35 * 4 + 0] = tmp[0]; out[35 * 4 + 1] = tmp[1]; out[35 * 4 + 2] = tmp[2]; out[35 * 4 + 3] = tmp[3];
+        // impulse response of 1/A(z): h[n] = (A^n)[0][0]; the inputs u[-1], u[-2] reach the recursion as
+        // d[0] = b1 u[-1] + b2 u[-2], d[1] = b2 u[-1]  ->  end state (y[S-1], y[S-2]) += N (u[-1], u[-2])
+        double pw[4] = {1.0, 0.0, 0.0, 1.0}, h29 = 0.0, h30 = 0.0, h31 = 0.0;
+        for (int n = 0; n < S; ++n) {
+            if (n == S - 3) h29 = pw[0];
+            if (n == S - 2) h30 = pw[0];
+            if (n == S - 1) h31 = pw[0];
+            mat2_mul(pw, A, tmp);
+            pw[0] = tmp[0]; pw[1] = tmp[1]; pw[2] = tmp[2]; pw[3] = tmp[3];
+        }
+        const double b1 = (double)nb1, b2 = (double)nb2;
+        out[33 * 4 + 0] = h31 * b1 + h30 * b2; out[33 * 4 + 1] = h31 * b2;
+        out[33 * 4 + 2] = h30 * b1 + h29 * b2; out[33 * 4 + 3] = h30 * b2;
+        out[34 * 4 + 0] = (double)nb0; out[34 * 4 + 1] = (double)nb1; out[34 * 4 + 2] = (double)nb2; out[34 * 4 + 3] = -(double)na1;
+        out[36 * 4 + 0] = -(double)na2; out[36 * 4 + 1] = 0.0; out[36 * 4 + 2] = 0.0; out[36 * 4 + 3] = 0.0;
     }
 }
 
@@ -346,10 +409,11 @@ constexpr int X2_WARPS = 4;           // warps per CTA (pure packaging: they sha
 constexpr int X2_ROWS = 64;           // 128-byte rows per warp tile
 constexpr int X2_TILE = X2_ROWS * 32; // 2048 samples
 
-static __host__ __device__ __forceinline__ size_t x2_warp_smem_bytes(int K) {
-    // tile | tables | 2 history samples + pad
-    return (size_t)X2_ROWS * 128 + (size_t)K * TAB_ENTRIES * 16 + 16;
+static __host__ __device__ __forceinline__ size_t x2_warp_smem_bytes(int) {
+    // tile | 2 history samples + pad   (the section tables are shared by the warps of the CTA: same row)
+    return (size_t)X2_ROWS * 128 + 16;
 }
+static __host__ __device__ __forceinline__ size_t x2_tab_smem_bytes(int K) { return (size_t)K * X2_TAB * 32; }
 
 // KT > 0: the section loop is fully unrolled for K == KT (no loop-carried register shuffling of the
 // 64 sample registers); KT == 0: generic K.
@@ -359,20 +423,20 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = KT > 0 ? KT : p.K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t tab_bytes = (size_t)K * TAB_ENTRIES * 16;
     unsigned char* base = smem_raw + (size_t)warp * x2_warp_smem_bytes(K);
     float4* tile4 = reinterpret_cast<float4*>(base);
     float* tile = reinterpret_cast<float*>(base);
-    const float4* tab = reinterpret_cast<const float4*>(base + (size_t)X2_ROWS * 128);
-    float* hist = reinterpret_cast<float*>(base + (size_t)X2_ROWS * 128 + tab_bytes);
+    float* hist = reinterpret_cast<float*>(base + (size_t)X2_ROWS * 128);
+    unsigned char* tab_raw = smem_raw + (size_t)X2_WARPS * x2_warp_smem_bytes(K);   // one table per CTA (one row per item)
+    const double* tab = reinterpret_cast<const double*>(tab_raw);
     // coalesced phases: unit g = lane + 32 j lives in row (lane>>3) + 4 j, column (lane&7) ^ (row&7)
     const int cu0 = (lane & 7) ^ (lane >> 3);
     // the 4 warps of a CTA take 4 CONSECUTIVE sub-tiles of one row (one ticket = 8192 samples) and
     // hand the state from warp to warp through shared memory (cheap hop); only the hop from the last
     // warp to the next item of the row goes through global memory.
-    float2* totals = reinterpret_cast<float2*>(smem_raw + (size_t)X2_WARPS * x2_warp_smem_bytes(K));  // [K][X2_WARPS]
-    float2* sin_relay = totals + (size_t)K * X2_WARPS;                                                // [K]
-    volatile int* ready = reinterpret_cast<volatile int*>(sin_relay + K);                             // [X2_WARPS]
+    double2* totals = reinterpret_cast<double2*>(tab_raw + x2_tab_smem_bytes(K));  // [K][X2_WARPS]
+    float2* sin_relay = reinterpret_cast<float2*>(totals + (size_t)K * X2_WARPS);  // [K] (slot sized as double2)
+    volatile int* ready = reinterpret_cast<volatile int*>(reinterpret_cast<double2*>(sin_relay) + K);  // [X2_WARPS]
     volatile int* sin_ready = ready + X2_WARPS;
     __shared__ unsigned int sh_item;
     if (threadIdx.x <= X2_WARPS) ready[threadIdx.x] = 0;
@@ -417,9 +481,8 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
             }
         }
         {
-            const unsigned char* tsrc = reinterpret_cast<const unsigned char*>(p.tables + crow * K * TAB_ENTRIES * 4);
-            unsigned char* tdst = base + (size_t)X2_ROWS * 128;
-            for (int u = lane; u < K * TAB_ENTRIES; u += 32) cp_async16(tdst + (size_t)u * 16, tsrc + (size_t)u * 16, 16);
+            const unsigned char* tsrc = reinterpret_cast<const unsigned char*>(p.xtables + crow * K * X2_TAB * 4);
+            for (int u = threadIdx.x; u < K * X2_TAB * 2; u += 32 * X2_WARPS) cp_async16(tab_raw + (size_t)u * 16, tsrc + (size_t)u * 16, 16);
             if (lane < 2) {
                 if (t0 > 0 && t0 - 1 - lane < p.L) cp_async_small<4>(hist + lane, xr + t0 - 1 - lane);
                 else hist[lane] = 0.f;
@@ -427,7 +490,7 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
         }
         cp_async_commit();
         cp_async_wait<0>();
-        __syncwarp();
+        __syncthreads();  // the table was staged by all four warps
 
         pk2 v[S];
 #pragma unroll
@@ -455,19 +518,22 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
 
 #pragma unroll
         for (int k = 0; k < (KT > 0 ? KT : K); ++k) {
-            const float4* pk = tab + k * TAB_ENTRIES;
-            const float4 c0 = pk[33];
-            const pk2 B0 = pk_dup(c0.x), B1 = pk_dup(c0.y), B2 = pk_dup(c0.z), NA1 = pk_dup(c0.w), NA2 = pk_dup(pk[34].x);
+            const double* pk = tab + (size_t)k * X2_TAB * 4;
+            const float b0f = (float)pk[34 * 4 + 0], b1f = (float)pk[34 * 4 + 1], b2f = (float)pk[34 * 4 + 2];
+            const pk2 B0 = pk_dup(b0f), B1 = pk_dup(b1f), B2 = pk_dup(b2f);
+            const pk2 NA1 = pk_dup((float)pk[34 * 4 + 3]), NA2 = pk_dup((float)pk[36 * 4 + 0]);
 
-            // 1. feed-forward part in place (descending, so the taps are still inputs)
+            // 1. feed-forward part in place (descending, so the taps are still inputs) with ZERO input history:
+            //    the zero-state response below is then a genuine filter output (bounded by the filter gain), not
+            //    the difference of two large transients
 #pragma unroll
             for (int n = S - 1; n >= 2; --n) {
                 pk_mul_acc(v[n], B0);
                 pk_fma_acc(v[n], B1, v[n - 1]);
                 pk_fma_acc(v[n], B2, v[n - 2]);
             }
-            pk_mul_acc(v[1], B0); pk_fma_acc(v[1], B1, v[0]); pk_fma_acc(v[1], B2, um1);
-            pk_mul_acc(v[0], B0); pk_fma_acc(v[0], B1, um1);  pk_fma_acc(v[0], B2, um2);
+            pk_mul_acc(v[1], B0); pk_fma_acc(v[1], B1, v[0]);
+            pk_mul_acc(v[0], B0);
 
             // 2. zero-state recursion -> end states (both halves at once)
             pk2 z1 = 0ull, z2 = 0ull;
@@ -478,36 +544,51 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
                 z1 = w;
             }
 
-            // 3. packed scan of s' = M s + z over the 32 lanes (each half separately)
+            // 3. carries in double: c = z + N (u[-1], u[-2]), then the scan of s' = M s + c over the 32 lanes
+            float uA1, uB1, uA2, uB2;
+            pk_split(um1, uA1, uB1);
+            pk_split(um2, uA2, uB2);
+            double cAx, cAy, cBx, cBy;
+            {
+                float zAx, zBx, zAy, zBy;
+                pk_split(z1, zAx, zBx);
+                pk_split(z2, zAy, zBy);
+                const double n00 = pk[33 * 4 + 0], n01 = pk[33 * 4 + 1], n10 = pk[33 * 4 + 2], n11 = pk[33 * 4 + 3];
+                cAx = fma(n00, (double)uA1, fma(n01, (double)uA2, (double)zAx));
+                cAy = fma(n10, (double)uA1, fma(n11, (double)uA2, (double)zAy));
+                cBx = fma(n00, (double)uB1, fma(n01, (double)uB2, (double)zBx));
+                cBy = fma(n10, (double)uB1, fma(n11, (double)uB2, (double)zBy));
+            }
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
                 const int d = 1 << j;
-                pk2 p1 = pk_shfl_up(z1, d), p2 = pk_shfl_up(z2, d);
-                if (lane < d) { p1 = 0ull; p2 = 0ull; }
-                const float4 m = pk[d];
-                z1 = pk_fma(pk_dup(m.x), p1, pk_fma(pk_dup(m.y), p2, z1));
-                z2 = pk_fma(pk_dup(m.z), p1, pk_fma(pk_dup(m.w), p2, z2));
+                const double pAx = __shfl_up_sync(0xffffffffu, cAx, d), pAy = __shfl_up_sync(0xffffffffu, cAy, d);
+                const double pBx = __shfl_up_sync(0xffffffffu, cBx, d), pBy = __shfl_up_sync(0xffffffffu, cBy, d);
+                if (lane >= d) {
+                    const double m00 = pk[d * 4 + 0], m01 = pk[d * 4 + 1], m10 = pk[d * 4 + 2], m11 = pk[d * 4 + 3];
+                    cAx = fma(m00, pAx, fma(m01, pAy, cAx));
+                    cAy = fma(m10, pAx, fma(m11, pAy, cAy));
+                    cBx = fma(m00, pBx, fma(m01, pBy, cBx));
+                    cBy = fma(m10, pBx, fma(m11, pBy, cBy));
+                }
             }
             // ---- stitch the warps: totals of this warp's 64 chunks -> shared memory, then fold the
             //      totals of the warps before it onto the state the previous item of the row left
-            float zAx, zBx, zAy, zBy;
-            pk_split(z1, zAx, zBx);
-            pk_split(z2, zAy, zBy);
-            const float totAx = __shfl_sync(0xffffffffu, zAx, 31), totAy = __shfl_sync(0xffffffffu, zAy, 31);
-            const float4 mw = pk[32];   // M^32
+            const double totAx = __shfl_sync(0xffffffffu, cAx, 31), totAy = __shfl_sync(0xffffffffu, cAy, 31);
+            const double w00 = pk[32 * 4 + 0], w01 = pk[32 * 4 + 1], w10 = pk[32 * 4 + 2], w11 = pk[32 * 4 + 3];  // M^32
             const int seq = seq_base + k + 1;
             if (lane == 31) {
-                totals[k * X2_WARPS + warp] = make_float2(fmaf(mw.x, zAx, fmaf(mw.y, zAy, zBx)),
-                                                          fmaf(mw.z, zAx, fmaf(mw.w, zAy, zBy)));
+                totals[k * X2_WARPS + warp] = make_double2(fma(w00, cAx, fma(w01, cAy, cBx)), fma(w10, cAx, fma(w11, cAy, cBy)));
                 __threadfence_block();
                 ready[warp] = seq;
             }
             // incoming state of the item for THIS section: one 64-bit {value, tag} word per component
             // (an aligned 8-byte access is single-copy atomic: no fence, no separate flag), published
-            // section by section so that consecutive items of a row run as a pipeline
+            // section by section so that consecutive items of a row run as a pipeline.  The state is the pair of
+            // fp32 OUTPUT samples before the item: exact in fp32.
             // Only warp 0 reads the global word (the last warp of this very item overwrites it with the
             // next tag as soon as IT is done with the section); it relays the state through shared memory.
-            float sAx = 0.f, sAy = 0.f;
+            float sAxf = 0.f, sAyf = 0.f;
             if (t_idx > 0) {
                 if (warp == 0) {
                     float sv = 0.f;
@@ -517,10 +598,10 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
                         do { word = *w; } while ((unsigned)(word >> 32) != (unsigned)t_idx);
                         sv = __uint_as_float((unsigned)word);
                     }
-                    sAx = __shfl_sync(0xffffffffu, sv, 0);
-                    sAy = __shfl_sync(0xffffffffu, sv, 1);
+                    sAxf = __shfl_sync(0xffffffffu, sv, 0);
+                    sAyf = __shfl_sync(0xffffffffu, sv, 1);
                     if (lane == 0) {
-                        sin_relay[k] = make_float2(sAx, sAy);
+                        sin_relay[2 * k] = make_float2(sAxf, sAyf);
                         __threadfence_block();
                         *sin_ready = seq;
                     }
@@ -528,32 +609,36 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
                     if (lane == 0) { while (*sin_ready < seq) { } }
                     __syncwarp();
                     __threadfence_block();
-                    const float2 si = sin_relay[k];
-                    sAx = si.x;
-                    sAy = si.y;
+                    const float2 si = sin_relay[2 * k];
+                    sAxf = si.x;
+                    sAyf = si.y;
                 }
             }
+            double sAx = (double)sAxf, sAy = (double)sAyf;
             if (warp > 0) {
                 if (lane < warp) { while (ready[lane] < seq) { } }
                 __syncwarp();
                 __threadfence_block();
-                const float4 m64 = pk[35];  // M^64
+                const double q00 = pk[35 * 4 + 0], q01 = pk[35 * 4 + 1], q10 = pk[35 * 4 + 2], q11 = pk[35 * 4 + 3];  // M^64
                 for (int q = 0; q < warp; ++q) {
-                    const float2 tq = totals[k * X2_WARPS + q];
-                    const float tx = fmaf(m64.x, sAx, fmaf(m64.y, sAy, tq.x));
-                    const float ty = fmaf(m64.z, sAx, fmaf(m64.w, sAy, tq.y));
+                    const double2 tq = totals[k * X2_WARPS + q];
+                    const double tx = fma(q00, sAx, fma(q01, sAy, tq.x));
+                    const double ty = fma(q10, sAx, fma(q11, sAy, tq.y));
                     sAx = tx;
                     sAy = ty;
                 }
             }
-            const float sBx = fmaf(mw.x, sAx, fmaf(mw.y, sAy, totAx));
-            const float sBy = fmaf(mw.z, sAx, fmaf(mw.w, sAy, totAy));
-            pk2 e1 = pk_shfl_up(z1, 1), e2 = pk_shfl_up(z2, 1);
-            if (lane == 0) { e1 = 0ull; e2 = 0ull; }
-            const float4 ml = pk[lane];
-            const pk2 S1 = pk_make(sAx, sBx), S2 = pk_make(sAy, sBy);
-            const pk2 y1 = pk_fma(pk_dup(ml.x), S1, pk_fma(pk_dup(ml.y), S2, e1));  // y[-1] of the chunks
-            const pk2 y2 = pk_fma(pk_dup(ml.z), S1, pk_fma(pk_dup(ml.w), S2, e2));  // y[-2]
+            const double sBx = fma(w00, sAx, fma(w01, sAy, totAx));
+            const double sBy = fma(w10, sAx, fma(w11, sAy, totAy));
+            double eAx = __shfl_up_sync(0xffffffffu, cAx, 1), eAy = __shfl_up_sync(0xffffffffu, cAy, 1);
+            double eBx = __shfl_up_sync(0xffffffffu, cBx, 1), eBy = __shfl_up_sync(0xffffffffu, cBy, 1);
+            if (lane == 0) { eAx = 0.0; eAy = 0.0; eBx = 0.0; eBy = 0.0; }
+            const double l00 = pk[lane * 4 + 0], l01 = pk[lane * 4 + 1], l10 = pk[lane * 4 + 2], l11 = pk[lane * 4 + 3];
+            const pk2 y1 = pk_make((float)fma(l00, sAx, fma(l01, sAy, eAx)), (float)fma(l00, sBx, fma(l01, sBy, eBx)));  // y[-1] of the chunks
+            const pk2 y2 = pk_make((float)fma(l10, sAx, fma(l11, sAy, eAy)), (float)fma(l10, sBx, fma(l11, sBy, eBy)));  // y[-2]
+            // the feed-forward taps on the two inputs before the chunk, left out in step 1
+            pk_fma_acc(v[0], B1, um1); pk_fma_acc(v[0], B2, um2);
+            pk_fma_acc(v[1], B2, um1);
             um1 = y1;
             um2 = y2;
 
@@ -614,7 +699,7 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
 }
 
 static size_t cascade_x2_smem_bytes(int K) {
-    return (size_t)X2_WARPS * x2_warp_smem_bytes(K) + (size_t)K * (X2_WARPS + 1) * sizeof(float2) +
+    return (size_t)X2_WARPS * x2_warp_smem_bytes(K) + x2_tab_smem_bytes(K) + (size_t)K * (X2_WARPS + 1) * sizeof(double2) +
            (X2_WARPS + 1) * sizeof(int) + 16;
 }
 
@@ -628,8 +713,9 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 static size_t cascade_workspace_bytes(int rows, int coef_rows, int K, size_t elem) {
     // [ticket | pad to 256] [flags: rows*K ints] [state: rows*2K elems] [tables: coef_rows*K*36*4 elems]
-    return 256 + align256((size_t)rows * K * sizeof(int)) + align256((size_t)rows * 2 * K * 8) +
-           (size_t)coef_rows * K * TAB_ENTRIES * 4 * elem;
+    // (the packed fp32 kernel keeps its tables in double: X2_TAB entries of 4 doubles per section)
+    const size_t tab = elem == 4 ? (size_t)coef_rows * K * X2_TAB * 4 * sizeof(double) : (size_t)coef_rows * K * TAB_ENTRIES * 4 * elem;
+    return 256 + align256((size_t)rows * K * sizeof(int)) + align256((size_t)rows * 2 * K * 8) + tab;
 }
 
 template <typename T>
@@ -646,8 +732,9 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     const int c_out = c_sig > c_filt ? c_sig : c_filt;
     const long long rows_ll = (long long)batch * c_out;
     static const bool force_scalar = (getenv("GFX_CASCADE_SCALAR") != nullptr);  // A/B testing only
-    const bool X2 = sizeof(T) == 4 && !force_scalar &&
-                    cascade_x2_smem_bytes(K) <= (size_t)device_info().max_smem_optin;  // fp32: packed warp-tile kernel
+    (void)force_scalar;
+    const bool X2 = sizeof(T) == 4;  // fp32: packed warp-tile kernel with double-precision carries (fits for every K <= 64)
+    if (X2 && cascade_x2_smem_bytes(K) > (size_t)device_info().max_smem_optin) return GFX_ERR_UNSUPPORTED;
     const long long tile_len = X2 ? (long long)X2_WARPS * X2_TILE : (long long)NT * S;
     const long long tiles_ll = (L + tile_len - 1) / tile_len;
     if (rows_ll * tiles_ll > 0x7fff0000LL) return GFX_ERR_UNSUPPORTED;
@@ -674,7 +761,13 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
 
     GFX_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256 + flags_bytes + state_bytes, stream));
     const int n_sections = coef_rows * K;
-    cascade_tables_kernel<T><<<(n_sections * 32 + 127) / 128, 128, 0, stream>>>(Bs, As, tables, n_sections);
+    if constexpr (sizeof(T) == 4) {
+        p.xtables = (const double*)tables;
+        cascade_x2_tables_kernel<<<(n_sections * 32 + 127) / 128, 128, 0, stream>>>(Bs, As, (double*)tables, n_sections);
+    } else {
+        p.xtables = nullptr;
+        cascade_tables_kernel<T><<<(n_sections * 32 + 127) / 128, 128, 0, stream>>>(Bs, As, tables, n_sections);
+    }
     GFX_LAUNCH_CHECK();
 
     if constexpr (sizeof(T) == 4) {

@@ -411,3 +411,39 @@ def biquad_design(family: str, *params: torch.Tensor, flags: int = 0):
                                                      n_rows, K, int(flags), _cabi.stream_ptr())
         _cabi.check(code, "gfx_biquad_design_f32")
     return Bs, As
+
+
+POINTWISE_OP = {"gain": 0, "side_gain": 1, "tanh": 2, "piecewise_tanh": 3, "power": 4, "chebyshev": 5, "scale_add": 6}
+
+
+def row_mean(x: torch.Tensor) -> torch.Tensor:
+    """Mean over time of every (batch, channel) row -> [B, C] (the `remove_dc` option of nonlinear.py)."""
+    _cabi.require_cuda(x)
+    assert x.ndim == 3
+    x = _prep(x, torch.float32)
+    B, C, L = x.shape
+    m = torch.empty(B, C, dtype=torch.float32, device=x.device)
+    if m.numel():
+        with torch.cuda.device(x.device):
+            _cabi.check(_cabi.lib().gfx_row_mean_f32(x.data_ptr(), m.data_ptr(), B * C, L, _cabi.stream_ptr()), "gfx_row_mean_f32")
+    return m
+
+
+def pointwise(op: str, x: torch.Tensor, p0=None, p1=None, p2=None, p3=None, dc=None, order: int = 0, flags: int = 0,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """Sample-wise processors (stereo.py, nonlinear.py, the ParallelMix accumulation) in one pass; see
+    gfx_pointwise_f32 in include/grafx_b200.h for the parameter meaning of every op."""
+    _cabi.require_cuda(x, *[t for t in (p0, p1, p2, p3, dc) if t is not None])
+    assert x.ndim == 3
+    x = _prep(x, torch.float32)
+    B, C, L = x.shape
+    keep = [None if t is None else _prep(t, torch.float32) for t in (p0, p1, p2, p3, dc)]
+    for t in keep[:4]:
+        assert t is None or t.shape[0] == B, "parameter batch size must match the signal"
+    y = out if out is not None else _new_output((B, C, L), torch.float32, x.device)
+    if y.numel():
+        with torch.cuda.device(x.device):
+            code = _cabi.lib().gfx_pointwise_f32(POINTWISE_OP[op], x.data_ptr(), y.data_ptr(), B, C, L,
+                                                 *[_cabi.ptr(t) for t in keep], int(order), int(flags), _cabi.stream_ptr())
+        _cabi.check(code, "gfx_pointwise_f32")
+    return y

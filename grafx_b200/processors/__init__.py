@@ -1,8 +1,13 @@
 """Drop-in mirror of grafx.processors (processors/__init__.py:1-36) for the hot path."""
 from . import core  # noqa: F401
-from .container import DryWet, SerialChain  # noqa: F401
+from .container import DryWet, ParallelMix, SerialChain  # noqa: F401
 from .dynamics import Compressor, NoiseGate  # noqa: F401
-from .eq import ParametricEqualizer  # noqa: F401
+from .eq import (  # noqa: F401
+    GraphicEqualizer,
+    NewZeroPhaseFIREqualizer,
+    ParametricEqualizer,
+    ZeroPhaseFIREqualizer,
+)
 from .filter import (  # noqa: F401
     AllPassFilter,
     BandPassFilter,
@@ -18,3 +23,16 @@ from .filter import (  # noqa: F401
     StateVariableFilter,
 )
 from .reverb import STFTMaskedNoiseReverb  # noqa: F401
+from .nonlinear import (  # noqa: F401
+    ChebyshevDistortion,
+    PiecewiseTanhDistortion,
+    PowerDistortion,
+    TanhDistortion,
+)
+from .stereo import (  # noqa: F401
+    MidSideToStereo,
+    MonoToStereo,
+    SideGainImager,
+    StereoGain,
+    StereoToMidSide,
+)

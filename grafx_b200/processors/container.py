@@ -7,7 +7,11 @@ goes to HBM); otherwise the processors run one after another.
 """
 from __future__ import annotations
 
+import math
+
+import torch
 import torch.nn as nn
+import torch.nn.functional as tF
 
 from .. import functional as F_
 from .dynamics import _DynamicsBase
@@ -63,3 +67,40 @@ class SerialChain(nn.Module):
 
     def parameter_size(self):
         return {k: v.parameter_size() for k, v in self.processors.items()}
+
+
+class ParallelMix(nn.Module):
+    """Weighted sum of processors fed with the same input (container.py:151-225); weights = softmax or
+    softplus / (ln 2 * n) of `parallel_weights` [N, n].  The accumulation y (+)= w_i * out_i is one streaming
+    pass per branch (csrc/pointwise.cu)."""
+
+    def __init__(self, processors, activation="softmax"):
+        super().__init__()
+        self.processors = nn.ModuleDict(processors)
+        if activation not in ("softmax", "softplus"):
+            raise ValueError(f"Unsupported activation: {activation}")
+        self.activation = activation
+        self.mult = 1 / (math.log(2) * len(self.processors))
+
+    def forward(self, input_signals, parallel_weights, **processors_kwargs):
+        if self.activation == "softmax":
+            weights = torch.softmax(parallel_weights, dim=-1)
+        else:
+            weights = tF.softplus(parallel_weights) * self.mult
+        mix, intermediates = None, {}
+        for i, (k, processor) in enumerate(self.processors.items()):
+            out = processor(input_signals, **processors_kwargs[k])
+            if isinstance(out, tuple):
+                out, intermediates[k] = out
+            w = weights[..., i].reshape(-1, 1)
+            if mix is None:
+                mix = torch.empty_like(out)
+                F_.pointwise("scale_add", out, w, out=mix)
+            else:
+                F_.pointwise("scale_add", out, w, flags=4, out=mix)
+        return mix, intermediates
+
+    def parameter_size(self):
+        size = {k: v.parameter_size() for k, v in self.processors.items()}
+        size["parallel_weights"] = len(self.processors)
+        return size

@@ -147,6 +147,25 @@ GFX_API int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_str
 GFX_API int gfx_drywet_f32(const float* dry, const float* wet, const float* weight, float* y, int batch,
                            long long inner, void* stream);
 
+/* ---- memoryless processors ---------------------------------------------------------------------
+ * One streaming pass for the sample-wise processors of processors/stereo.py and processors/nonlinear.py and
+ * the weighted accumulation of ParallelMix (processors/container.py:203-216).  x, y [batch, channels, L];
+ * every parameter pointer has leading dim batch; dc [batch*channels] (row means to subtract first, from
+ * gfx_row_mean_f32: `remove_dc`) or NULL.
+ *   op 0 gain          y = x * exp(p0[b,c])                                   (StereoGain, stereo.py:31-38)
+ *   op 1 side gain     channels = 2: side of the mid/side pair * exp(p0[b])   (SideGainImager, stereo.py:71-84)
+ *   op 2 tanh          p0 log_pre_gain|NULL, p1 log_post_gain|NULL, p2 bias|NULL  (TanhDistortion, nonlinear.py:64-89)
+ *   op 3 piecewise tanh p0 log_hardness[b,2], p1 z_threshold[b,2], p2 log_pre_gain|NULL, p3 log_post_gain|NULL
+ *                                                                              (PiecewiseTanhDistortion, :159-205)
+ *   op 4 power series  p0 basis_weights[b,order], p1 log_pre_gain|NULL        (PowerDistortion, :268-285)
+ *   op 5 chebyshev     same parameters                                         (ChebyshevDistortion, :349-384)
+ *   op 6 scale-add     y = (flags&4 ? y : 0) + p0[b] * x
+ * flags: 1 = post gain is 1 / pre gain (inverse_post_gain), 2 = tanh on every basis function (use_tanh), 4 = accumulate. */
+GFX_API int gfx_row_mean_f32(const float* x, float* mean, int rows, long long L, void* stream);
+GFX_API int gfx_pointwise_f32(int op, const float* x, float* y, int batch, int channels, long long L, const float* p0,
+                              const float* p1, const float* p2, const float* p3, const float* dc, int order, int flags,
+                              void* stream);
+
 /* ---- node-axis aggregation of the render loop --------------------------------------------------
  * Replaces aggregate_tensor "sum" / "scatter" (render/core.py:101-112, torch.sum / torch_geometric
  * scatter).  src is a strided view [batch, n_src, inner], dst a strided view [batch, n_dst, inner]

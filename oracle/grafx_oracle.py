@@ -521,3 +521,121 @@ def render_plan(processors, input_signals, per_type_parameters, plan):
             else:
                 buf[ii] = out
     return out, buf
+
+
+# ====================================================================================================
+# "next" rows of SURVEY.md section 8(f): equalizers on the conv / cascade engines, memoryless processors
+# ====================================================================================================
+def geq_coeffs(log_gains, fc, fB, sr, neighbour_exponent=0.4):
+    """core/geq.py:176-209.  fc / fB: the band centre frequencies / bandwidths [K] (Hz) the reference registers."""
+    g = torch.exp(log_gains)
+    gt2 = torch.exp(neighbour_exponent * log_gains) ** 2
+    tan_half = torch.tan(math.pi * fB.to(log_gains.dtype) / sr)
+    mult = torch.sqrt((torch.abs(1 - gt2) + 1e-7) / (torch.abs(g ** 2 - gt2) + 1e-7))
+    beta = torch.where(log_gains.abs() >= 1e-3, tan_half * mult, tan_half.expand_as(g))
+    m2c = (-2 * torch.cos(2 * math.pi * fc.to(log_gains.dtype) / sr)).expand_as(g)
+    Bs = torch.stack([1 + g * beta, m2c, 1 - g * beta], -1)
+    As = torch.stack([1 + beta, m2c, 1 - beta], -1)
+    return Bs, As
+
+
+def graphic_equalizer(x, log_gains, fc, fB, sr=44100, processor_channel="mono", backend="lfilter", fsm_fir_len=4000,
+                      use_torchaudio=True):
+    """eq.py:407-420."""
+    Bs, As = geq_coeffs(log_gains, fc, fB, sr)
+    if processor_channel == "midside":
+        return ms_to_lr(_iir(lr_to_ms(x), Bs, As, backend, fsm_fir_len, use_torchaudio))
+    return _iir(x, Bs, As, backend, fsm_fir_len, use_torchaudio)
+
+
+def zerophase_fir(log_magnitude, window=None, filterbank=None, eps=1e-7):
+    """core/fir.py:25-40 / :106-123: h = window * roll(irfft(|H|, 2K - 1), K - 1); with a filterbank matrix
+    [K_fb, K] (synthesis direction) |H| = sqrt(exp(H_fb)^2 @ M + eps)."""
+    mag = torch.exp(log_magnitude)
+    if filterbank is not None:
+        mag = torch.sqrt((mag ** 2) @ filterbank.to(mag.dtype) + eps)
+    n = 2 * mag.shape[-1] - 1
+    ir = torch.roll(torch.fft.irfft(mag, n=n), shifts=n // 2, dims=-1)
+    if window is not None:
+        ir = ir * window.to(ir.dtype)
+    return ir
+
+
+def zerophase_fir_equalizer(x, log_magnitude, window=None, filterbank=None, eps=1e-7, processor_channel="mono"):
+    """eq.py:70-72 (log_magnitude [B, K] -> one filter for every channel) and eq.py:176-214 ([B, C_eq, K])."""
+    fir = zerophase_fir(log_magnitude, window, filterbank, eps)
+    if fir.ndim == 2:
+        fir = fir[:, None, :]
+    if processor_channel == "midside":
+        return ms_to_lr(convolve(lr_to_ms(x), fir, "zerophase"))
+    return convolve(x, fir, "zerophase")
+
+
+def stereo_gain(x, log_gain):
+    """stereo.py:31-38."""
+    return x * torch.exp(log_gain)[..., None]
+
+
+def side_gain_imager(x, log_gain):
+    """stereo.py:71-84."""
+    left, right = x[:, 0, :], x[:, 1, :]
+    mid, side = left + right, torch.exp(log_gain) * (left - right)
+    return torch.stack([(mid + side) / 2, (mid - side) / 2], 1)
+
+
+def _pre_post(x, remove_dc, log_pre_gain):
+    if remove_dc:
+        x = x - x.mean(-1, keepdim=True)
+    pre = None
+    if log_pre_gain is not None:
+        pre = torch.exp(log_pre_gain).unsqueeze(-1)
+        x = x * pre
+    return x, pre
+
+
+def tanh_distortion(x, log_pre_gain=None, log_post_gain=None, bias=None, inverse_post_gain=True, remove_dc=False):
+    """nonlinear.py:64-89 (log_pre_gain None <=> pre_post_gain False; bias None <=> use_bias False)."""
+    x, pre = _pre_post(x, remove_dc, log_pre_gain)
+    y = torch.tanh(x) if bias is None else torch.tanh(x + bias.unsqueeze(-1)) - torch.tanh(bias.unsqueeze(-1))
+    if pre is not None:
+        y = y * (1 / pre if inverse_post_gain else torch.exp(log_post_gain).unsqueeze(-1))
+    return y
+
+
+def piecewise_tanh_distortion(x, log_hardness, z_threshold, log_pre_gain=None, log_post_gain=None,
+                              inverse_post_gain=True, remove_dc=False):
+    """nonlinear.py:159-205."""
+    x, pre = _pre_post(x, remove_dc, log_pre_gain)
+    hard, thr = torch.exp(log_hardness).unsqueeze(-2), torch.sigmoid(z_threshold).unsqueeze(-2)
+    kn, kp = thr[..., 0:1], thr[..., 1:2]
+    gp, gn = hard[..., 0:1], hard[..., 1:2]
+    ap, an = (1 - torch.tanh(kp)) / gp, (1 - torch.tanh(kn)) / gn
+    above, below = x > kp, x < -kn
+    y = torch.where(above, ap * torch.tanh(gp * (x - kp)) + torch.tanh(kp),
+                    torch.where(below, an * torch.tanh(gn * (x + kn)) - torch.tanh(kn), torch.tanh(x)))
+    if pre is not None:
+        y = y * (1 / pre if inverse_post_gain else torch.exp(log_post_gain).unsqueeze(-1))
+    return y
+
+
+def series_distortion(kind, x, basis_weights, log_pre_gain=None, remove_dc=False, use_tanh=False):
+    """PowerDistortion (nonlinear.py:268-285: basis x^k) / ChebyshevDistortion (:349-384: basis T_k(x)), k < order."""
+    x, _ = _pre_post(x, remove_dc, log_pre_gain)
+    w = torch.tanh(basis_weights)
+    order = w.shape[-1]
+    basis = [torch.ones_like(x), x]
+    for k in range(2, order):
+        basis.append(basis[-1] * x if kind == "power" else 2 * x * basis[-1] - basis[-2])
+    y = torch.zeros_like(x)
+    for k in range(order):
+        b = torch.tanh(basis[k]) if use_tanh else basis[k]
+        y = y + w[:, k].view(-1, 1, 1) * b
+    return y
+
+
+def parallel_mix_weights(parallel_weights, activation="softmax"):
+    """container.py:218-222."""
+    n = parallel_weights.shape[-1]
+    if activation == "softmax":
+        return torch.softmax(parallel_weights, -1)
+    return torch.nn.functional.softplus(parallel_weights) / (math.log(2) * n)

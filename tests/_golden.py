@@ -26,6 +26,17 @@ CLASS_OF_PREFIX = {
     "compressor": "Compressor",
     "noisegate": "NoiseGate",
     "reverb": "STFTMaskedNoiseReverb",
+    # SURVEY.md section 8(f) "next" rows (oracle/make_golden_next.py)
+    "next_geq": "GraphicEqualizer",
+    "next_zpfir_old": "ZeroPhaseFIREqualizer",
+    "next_zpfir": "NewZeroPhaseFIREqualizer",
+    "next_stereogain": "StereoGain",
+    "next_sidegainimager": "SideGainImager",
+    "next_tanhdistortion": "TanhDistortion",
+    "next_piecewisetanhdistortion": "PiecewiseTanhDistortion",
+    "next_powerdistortion": "PowerDistortion",
+    "next_chebyshevdistortion": "ChebyshevDistortion",
+    "next_parallelmix": "ParallelMix",
 }
 
 
@@ -54,8 +65,8 @@ def load(name):
     return x, params, meta, y, extra
 
 
-def oracle_call(name, x, params, kwargs, dtype=None):
-    """Runs the oracle restatement for the fixture `name`."""
+def oracle_call(name, x, params, kwargs, dtype=None, extra=None):
+    """Runs the oracle restatement for the fixture `name` (`extra`: the constants the reference registered)."""
     from oracle import grafx_oracle as O
 
     if dtype is not None:
@@ -63,6 +74,33 @@ def oracle_call(name, x, params, kwargs, dtype=None):
         params = {k: v.to(dtype) for k, v in params.items()}
     cls = class_of(name)
     kw = dict(kwargs)
+    ex = {k: torch.from_numpy(np.asarray(v)) for k, v in (extra or {}).items()}
+    if cls == "GraphicEqualizer":
+        return O.graphic_equalizer(x, params["log_gains"], ex["fc"], ex["fB"], sr=kw["sr"],
+                                   processor_channel=kw["processor_channel"], use_torchaudio=dtype is None)
+    if cls in ("ZeroPhaseFIREqualizer", "NewZeroPhaseFIREqualizer"):
+        return O.zerophase_fir_equalizer(x, params["log_magnitude"], ex.get("window"), ex.get("filterbank"),
+                                         processor_channel=kw.get("processor_channel", "mono"))
+    if cls == "StereoGain":
+        return O.stereo_gain(x, params["log_gain"])
+    if cls == "SideGainImager":
+        return O.side_gain_imager(x, params["log_gain"])
+    if cls == "TanhDistortion":
+        return O.tanh_distortion(x, params.get("log_pre_gain"), params.get("log_post_gain"), params.get("bias"),
+                                 inverse_post_gain=kw.get("inverse_post_gain", True), remove_dc=kw.get("remove_dc", False))
+    if cls == "PiecewiseTanhDistortion":
+        return O.piecewise_tanh_distortion(x, params["log_hardness"], params["z_threshold"], params.get("log_pre_gain"),
+                                           params.get("log_post_gain"), inverse_post_gain=kw.get("inverse_post_gain", True),
+                                           remove_dc=kw.get("remove_dc", False))
+    if cls in ("PowerDistortion", "ChebyshevDistortion"):
+        return O.series_distortion("power" if cls == "PowerDistortion" else "chebyshev", x, params["basis_weights"],
+                                   params.get("log_pre_gain"), remove_dc=kw.get("remove_dc", False),
+                                   use_tanh=kw.get("use_tanh", False))
+    if cls == "ParallelMix":
+        w = O.parallel_mix_weights(params["parallel_weights"], kw["activation"])
+        a = O.tanh_distortion(x, params["a__log_pre_gain"])
+        b = O.stereo_gain(x, params["b__log_gain"])
+        return a * w[:, 0, None, None] + b * w[:, 1, None, None]
     backend = kw.get("backend", "lfilter")
     fir_len = kw.get("fsm_fir_len", 4000)
     ta = dtype is None

@@ -11,8 +11,8 @@ TOL = 2e-5  # fp32 restatement vs fp32 reference: only op-ordering noise is allo
 
 @pytest.mark.parametrize("name", fixture_names())
 def test_oracle_matches_reference_fixture(name):
-    x, params, meta, y_ref, _ = load(name)
-    y = oracle_call(name, x, params, meta["kwargs"])
+    x, params, meta, y_ref, extra = load(name)
+    y = oracle_call(name, x, params, meta["kwargs"], extra=extra)
     assert y.shape == y_ref.shape
     assert rel_l2(y, y_ref) < TOL, (name, rel_l2(y, y_ref))
     assert max_rel(y, y_ref) < 10 * TOL

@@ -23,12 +23,21 @@ IIR_PREFIXES = ["peq_lfilter", "cfg1_biquad_lfilter", "biquadfilter", "statevari
 def build_processor(name, kwargs):
     import grafx_b200.processors as P
 
+    if class_of(name) == "ParallelMix":
+        return P.ParallelMix({"a": P.TanhDistortion(), "b": P.StereoGain()}, **kwargs).cuda()
     return getattr(P, class_of(name))(**kwargs).cuda()
 
 
 def run_product(name, x, params, kwargs):
     proc = build_processor(name, kwargs)
-    out = proc(x.cuda(), **{k: v.cuda() for k, v in params.items()})
+    if class_of(name) == "ParallelMix":  # nested parameter dicts were flattened as "<branch>__<name>" in the fixture
+        nested = {}
+        for k, v in params.items():
+            if "__" in k:
+                nested.setdefault(k.split("__")[0], {})[k.split("__")[1]] = v.cuda()
+        out = proc(x.cuda(), params["parallel_weights"].cuda(), **nested)
+    else:
+        out = proc(x.cuda(), **{k: v.cuda() for k, v in params.items()})
     if isinstance(out, tuple):
         out = out[0]
     torch.cuda.synchronize()
@@ -356,6 +365,84 @@ def test_reverb_long_ir_vs_oracle(ir_len):
     y = proc(x.cuda(), **{k: v.cuda() for k, v in prm.items()}).cpu()
     y_ref = O.stft_masked_noise_reverb(x, **prm, ir_len=ir_len)
     assert_close(y, y_ref, f"reverb{ir_len}")
+
+
+# ------------------------------------------------------------------ SURVEY.md section 8(f) "next" processors
+@pytest.mark.parametrize("name", fixture_names(["next_"]))
+def test_next_processors_vs_reference_golden(name):
+    """GraphicEqualizer (24 / 31 sections in one cascade launch), zero-phase FIR equalizers, stereo utilities,
+    memoryless distortions, ParallelMix: the CUDA path against the reference's own outputs."""
+    x, params, meta, y_ref, _ = load(name)
+    y = run_product(name, x, params, meta["kwargs"])
+    if name.startswith("next_geq"):
+        # 24 / 31 narrow low-frequency sections: the reference's own fp32 recursion is 1e-4 .. 1e-3 away from the
+        # exact response of its (fp32) coefficients, so "within 1e-4 of the reference" is ill-posed here; the
+        # criterion is the distance to that exact response, which must not exceed the reference's own
+        y64 = _geq_truth(x, params, meta["kwargs"])
+        e_ref, e_ours = rel_l2(y_ref, y64), rel_l2(y, y64)
+        assert e_ours <= max(TOL, 1.5 * e_ref), (name, e_ours, e_ref)
+        return
+    assert_close(y, y_ref, name)
+
+
+def _geq_truth(x, params, kw):
+    """float64 evaluation of the cascade defined by the fp32-normalised coefficients (what torchaudio runs)."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    proc = P.GraphicEqualizer(**kw).cuda()
+    Bs, As = (t.cpu() for t in proc.geq(params["log_gains"].cuda()))
+    nb, na = (Bs / As[..., :1]).double(), (As / As[..., :1]).double()
+    xin = O.lr_to_ms(x.double()) if kw["processor_channel"] == "midside" else x.double()
+    y = O.iir_lfilter(xin, nb, na, use_torchaudio=False)
+    return O.ms_to_lr(y) if kw["processor_channel"] == "midside" else y
+
+
+@pytest.mark.parametrize("f0,Q", [(20, 0.7), (20, 4.0), (50, 4.0), (100, 0.7), (200, 4.0), (1000, 0.7)])
+def test_cascade_low_frequency_sections_accuracy(f0, Q):
+    """Bass EQ bands (poles within 1e-2 .. 1e-3 of z = 1) over 131072 samples: the carried state is a difference of
+    terms hundreds of times larger than itself -- the kernel propagates it in double.  Its distance to the exact
+    (float64) response of the fp32 coefficients must not exceed the reference's (torchaudio fp32 lfilter)."""
+    import math
+    from oracle import grafx_oracle as O
+    import grafx_b200.functional as F_
+
+    torch.manual_seed(f0)
+    x = torch.randn(3, 1, 131072)
+    w0 = 2 * math.pi * f0 / 48000.0
+    A, alpha, c = 10 ** (6 / 40), math.sin(w0) / (2 * Q), math.cos(w0)
+    Bs = torch.tensor([1 + alpha * A, -2 * c, 1 - alpha * A]).view(1, 1, 1, 3).expand(3, 1, 1, 3).contiguous()
+    As = torch.tensor([1 + alpha / A, -2 * c, 1 - alpha / A]).view(1, 1, 1, 3).expand(3, 1, 1, 3).contiguous()
+    y_ref = O.iir_lfilter(x, Bs, As, use_torchaudio=True)
+    y64 = O.iir_lfilter(x.double(), (Bs / As[..., :1]).double(), (As / As[..., :1]).double(), use_torchaudio=False)
+    y = F_.biquad_cascade(x.cuda(), Bs.cuda(), As.cuda()).cpu()
+    e_ref, e_ours = rel_l2(y_ref, y64), rel_l2(y, y64)
+    assert e_ours <= max(1e-5, 1.5 * e_ref), (f0, Q, e_ours, e_ref)
+
+
+def test_next_processors_full_size_properties():
+    """BASELINE-sized batches: GEQ with all gains 0 is the identity; the zero-phase equalizer with a flat
+    magnitude response is a pure (windowed-sinc) near-identity; distortions against the oracle on a row sample."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    torch.manual_seed(3)
+    x = torch.randn(64, 2, 131072, device="cuda")
+    geq = P.GraphicEqualizer(processor_channel="stereo", scale="third_octave", sr=48000, backend="lfilter").cuda()
+    y = geq(x, torch.zeros(64, 2, 31, device="cuda"))
+    # all gains 0 dB: every section has numerator == denominator, the exact response is the identity; what is left is
+    # the fp32 rounding noise of 31 sections down to 20 Hz (the reference's lfilter leaves ~1e-3 on such cascades)
+    assert rel_l2(y.cpu(), x.cpu()) < 3e-3
+    cheb = P.ChebyshevDistortion(max_order=8).cuda()
+    prm = {"basis_weights": 0.5 * torch.randn(64, 8, device="cuda"), "log_pre_gain": 0.3 * torch.randn(64, 1, device="cuda")}
+    yc = cheb(0.3 * x, **prm)
+    rows = [0, 31, 63]
+    ref = O.series_distortion("chebyshev", 0.3 * x[rows].cpu(), prm["basis_weights"][rows].cpu(), prm["log_pre_gain"][rows].cpu())
+    assert_close(yc[rows].cpu(), ref, "chebyshev full size")
+    ms = P.StereoToMidSide().cuda()
+    back = P.MidSideToStereo().cuda()
+    assert rel_l2(back(*ms(x)).cpu(), x.cpu()) < 1e-6
+    assert torch.equal(P.MonoToStereo()(x[:, :1])[:, 1], x[:, 0])
 
 
 # ------------------------------------------------------------------ graph render
