@@ -103,8 +103,12 @@ __global__ void __launch_bounds__(128) cascade_tables_kernel(const T* __restrict
 // the per-sample recursions stay fp32 on those same coefficients (arithmetically the reference's loop).
 // Per (coefficient row, section), X2_TAB entries of 4 doubles:
 //   [l] = M^l, l = 0..32 (M = A^32);  [33] = N: end-state response to the two inputs before a chunk;
-//   [34] = (b0, b1, b2, -a1);  [35] = M^64;  [36] = (-a2, 0, 0, 0)          (coefficients normalised in fp32)
-constexpr int X2_TAB = 37;
+//   [34] = (b0, b1, b2, -a1);  [35] = M^64;  [36] = (-a2, ill, 0, 0)        (coefficients normalised in fp32)
+//   [37..56] = the same matrices rounded to fp32 (float4 l = M^l, [33] = N, [34] = M^64).  ill = 1 when some entry of
+//   M^l, l <= 32, exceeds X2_ILL_GROWTH in magnitude (poles below ~2 kHz at 48 kHz); well-conditioned sections, where
+//   fp32 carries were measured to match the sequential loop, skip the double arithmetic.
+constexpr int X2_TAB = 57;        // 37 double entries + 20 (= 40 float4: M^0..32, N, M^64 as fp32, for well-conditioned sections)
+constexpr double X2_ILL_GROWTH = 4.0;  // a section whose chunk-matrix powers exceed this is propagated in double
 
 __global__ void __launch_bounds__(128) cascade_x2_tables_kernel(const float* __restrict__ Bs, const float* __restrict__ As,
                                                                 double* __restrict__ tables, int n_sections) {
@@ -135,11 +139,19 @@ __global__ void __launch_bounds__(128) cascade_x2_tables_kernel(const float* __r
         base[0] = tmp[0]; base[1] = tmp[1]; base[2] = tmp[2]; base[3] = tmp[3];
     }
     double* out = tables + (size_t)w * X2_TAB * 4;
+    float4* outf = reinterpret_cast<float4*>(out + 37 * 4);
     out[lane * 4 + 0] = res[0]; out[lane * 4 + 1] = res[1]; out[lane * 4 + 2] = res[2]; out[lane * 4 + 3] = res[3];
+    outf[lane] = make_float4((float)res[0], (float)res[1], (float)res[2], (float)res[3]);
+    double growth = fmax(fmax(fabs(res[0]), fabs(res[1])), fmax(fabs(res[2]), fabs(res[3])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) growth = fmax(growth, __shfl_xor_sync(0xffffffffu, growth, o));
     if (lane == 0) {
+        growth = fmax(growth, fmax(fmax(fabs(base[0]), fabs(base[1])), fmax(fabs(base[2]), fabs(base[3]))));
         out[32 * 4 + 0] = base[0]; out[32 * 4 + 1] = base[1]; out[32 * 4 + 2] = base[2]; out[32 * 4 + 3] = base[3];
+        outf[32] = make_float4((float)base[0], (float)base[1], (float)base[2], (float)base[3]);
         mat2_mul(base, base, tmp);  // M^64
         out[35 * 4 + 0] = tmp[0]; out[35 * 4 + 1] = tmp[1]; out[35 * 4 + 2] = tmp[2]; out[35 * 4 + 3] = tmp[3];
+        outf[34] = make_float4((float)tmp[0], (float)tmp[1], (float)tmp[2], (float)tmp[3]);
         // impulse response of 1/A(z): h[n] = (A^n)[0][0]; the inputs u[-1], u[-2] reach the recursion as
         // d[0] = b1 u[-1] + b2 u[-2], d[1] = b2 u[-1]  ->  end state (y[S-1], y[S-2]) += N (u[-1], u[-2])
         double pw[4] = {1.0, 0.0, 0.0, 1.0}, h29 = 0.0, h30 = 0.0, h31 = 0.0;
@@ -154,7 +166,8 @@ __global__ void __launch_bounds__(128) cascade_x2_tables_kernel(const float* __r
         out[33 * 4 + 0] = h31 * b1 + h30 * b2; out[33 * 4 + 1] = h31 * b2;
         out[33 * 4 + 2] = h30 * b1 + h29 * b2; out[33 * 4 + 3] = h30 * b2;
         out[34 * 4 + 0] = (double)nb0; out[34 * 4 + 1] = (double)nb1; out[34 * 4 + 2] = (double)nb2; out[34 * 4 + 3] = -(double)na1;
-        out[36 * 4 + 0] = -(double)na2; out[36 * 4 + 1] = 0.0; out[36 * 4 + 2] = 0.0; out[36 * 4 + 3] = 0.0;
+        outf[33] = make_float4((float)out[33 * 4 + 0], (float)out[33 * 4 + 1], (float)out[33 * 4 + 2], (float)out[33 * 4 + 3]);
+        out[36 * 4 + 0] = -(double)na2; out[36 * 4 + 1] = growth > X2_ILL_GROWTH ? 1.0 : 0.0; out[36 * 4 + 2] = 0.0; out[36 * 4 + 3] = 0.0;
     }
 }
 
@@ -544,13 +557,18 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
                 z1 = w;
             }
 
-            // 3. carries in double: c = z + N (u[-1], u[-2]), then the scan of s' = M s + c over the 32 lanes
-            float uA1, uB1, uA2, uB2;
-            pk_split(um1, uA1, uB1);
-            pk_split(um2, uA2, uB2);
-            double cAx, cAy, cBx, cBy;
-            {
-                float zAx, zBx, zAy, zBy;
+            // 3. carries: c = z + N (u[-1], u[-2]), the scan of s' = M s + c over the 32 lanes, the warps stitched through
+            //    shared memory, the item's incoming state from the previous item of the row.  Ill-conditioned sections
+            //    (table flag) in double, the others in packed fp32; the hand-over words are the same for both.
+            const bool ill = pk[36 * 4 + 1] != 0.0;
+            const float4* pf = reinterpret_cast<const float4*>(pk + 37 * 4);
+            const int seq = seq_base + k + 1;
+            double cAx = 0.0, cAy = 0.0, cBx = 0.0, cBy = 0.0;  // double path: inclusive carries of the lane's two chunks
+            pk2 c1 = 0ull, c2 = 0ull;                            // fp32 path: the same, packed (A, B)
+            if (ill) {
+                float uA1, uB1, uA2, uB2, zAx, zBx, zAy, zBy;
+                pk_split(um1, uA1, uB1);
+                pk_split(um2, uA2, uB2);
                 pk_split(z1, zAx, zBx);
                 pk_split(z2, zAy, zBy);
                 const double n00 = pk[33 * 4 + 0], n01 = pk[33 * 4 + 1], n10 = pk[33 * 4 + 2], n11 = pk[33 * 4 + 3];
@@ -558,29 +576,48 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
                 cAy = fma(n10, (double)uA1, fma(n11, (double)uA2, (double)zAy));
                 cBx = fma(n00, (double)uB1, fma(n01, (double)uB2, (double)zBx));
                 cBy = fma(n10, (double)uB1, fma(n11, (double)uB2, (double)zBy));
-            }
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const int d = 1 << j;
-                const double pAx = __shfl_up_sync(0xffffffffu, cAx, d), pAy = __shfl_up_sync(0xffffffffu, cAy, d);
-                const double pBx = __shfl_up_sync(0xffffffffu, cBx, d), pBy = __shfl_up_sync(0xffffffffu, cBy, d);
-                if (lane >= d) {
-                    const double m00 = pk[d * 4 + 0], m01 = pk[d * 4 + 1], m10 = pk[d * 4 + 2], m11 = pk[d * 4 + 3];
-                    cAx = fma(m00, pAx, fma(m01, pAy, cAx));
-                    cAy = fma(m10, pAx, fma(m11, pAy, cAy));
-                    cBx = fma(m00, pBx, fma(m01, pBy, cBx));
-                    cBy = fma(m10, pBx, fma(m11, pBy, cBy));
+                for (int j = 0; j < 5; ++j) {
+                    const int d = 1 << j;
+                    const double pAx = __shfl_up_sync(0xffffffffu, cAx, d), pAy = __shfl_up_sync(0xffffffffu, cAy, d);
+                    const double pBx = __shfl_up_sync(0xffffffffu, cBx, d), pBy = __shfl_up_sync(0xffffffffu, cBy, d);
+                    if (lane >= d) {
+                        const double m00 = pk[d * 4 + 0], m01 = pk[d * 4 + 1], m10 = pk[d * 4 + 2], m11 = pk[d * 4 + 3];
+                        cAx = fma(m00, pAx, fma(m01, pAy, cAx));
+                        cAy = fma(m10, pAx, fma(m11, pAy, cAy));
+                        cBx = fma(m00, pBx, fma(m01, pBy, cBx));
+                        cBy = fma(m10, pBx, fma(m11, pBy, cBy));
+                    }
                 }
-            }
-            // ---- stitch the warps: totals of this warp's 64 chunks -> shared memory, then fold the
-            //      totals of the warps before it onto the state the previous item of the row left
-            const double totAx = __shfl_sync(0xffffffffu, cAx, 31), totAy = __shfl_sync(0xffffffffu, cAy, 31);
-            const double w00 = pk[32 * 4 + 0], w01 = pk[32 * 4 + 1], w10 = pk[32 * 4 + 2], w11 = pk[32 * 4 + 3];  // M^32
-            const int seq = seq_base + k + 1;
-            if (lane == 31) {
-                totals[k * X2_WARPS + warp] = make_double2(fma(w00, cAx, fma(w01, cAy, cBx)), fma(w10, cAx, fma(w11, cAy, cBy)));
-                __threadfence_block();
-                ready[warp] = seq;
+                if (lane == 31) {
+                    const double w00 = pk[32 * 4 + 0], w01 = pk[32 * 4 + 1], w10 = pk[32 * 4 + 2], w11 = pk[32 * 4 + 3];  // M^32
+                    totals[k * X2_WARPS + warp] = make_double2(fma(w00, cAx, fma(w01, cAy, cBx)), fma(w10, cAx, fma(w11, cAy, cBy)));
+                    __threadfence_block();
+                    ready[warp] = seq;
+                }
+            } else {
+                const float4 nn = pf[33];
+                c1 = pk_fma(pk_dup(nn.x), um1, pk_fma(pk_dup(nn.y), um2, z1));
+                c2 = pk_fma(pk_dup(nn.z), um1, pk_fma(pk_dup(nn.w), um2, z2));
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int d = 1 << j;
+                    pk2 p1 = pk_shfl_up(c1, d), p2 = pk_shfl_up(c2, d);
+                    if (lane < d) { p1 = 0ull; p2 = 0ull; }
+                    const float4 m = pf[d];
+                    c1 = pk_fma(pk_dup(m.x), p1, pk_fma(pk_dup(m.y), p2, c1));
+                    c2 = pk_fma(pk_dup(m.z), p1, pk_fma(pk_dup(m.w), p2, c2));
+                }
+                if (lane == 31) {
+                    float zAx, zBx, zAy, zBy;
+                    pk_split(c1, zAx, zBx);
+                    pk_split(c2, zAy, zBy);
+                    const float4 mw = pf[32];
+                    totals[k * X2_WARPS + warp] = make_double2((double)fmaf(mw.x, zAx, fmaf(mw.y, zAy, zBx)),
+                                                               (double)fmaf(mw.z, zAx, fmaf(mw.w, zAy, zBy)));
+                    __threadfence_block();
+                    ready[warp] = seq;
+                }
             }
             // incoming state of the item for THIS section: one 64-bit {value, tag} word per component
             // (an aligned 8-byte access is single-copy atomic: no fence, no separate flag), published
@@ -614,11 +651,14 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
                     sAyf = si.y;
                 }
             }
-            double sAx = (double)sAxf, sAy = (double)sAyf;
             if (warp > 0) {
                 if (lane < warp) { while (ready[lane] < seq) { } }
                 __syncwarp();
                 __threadfence_block();
+            }
+            pk2 y1, y2;
+            if (ill) {
+                double sAx = (double)sAxf, sAy = (double)sAyf;
                 const double q00 = pk[35 * 4 + 0], q01 = pk[35 * 4 + 1], q10 = pk[35 * 4 + 2], q11 = pk[35 * 4 + 3];  // M^64
                 for (int q = 0; q < warp; ++q) {
                     const double2 tq = totals[k * X2_WARPS + q];
@@ -627,15 +667,40 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
                     sAx = tx;
                     sAy = ty;
                 }
+                const double totAx = __shfl_sync(0xffffffffu, cAx, 31), totAy = __shfl_sync(0xffffffffu, cAy, 31);
+                const double w00 = pk[32 * 4 + 0], w01 = pk[32 * 4 + 1], w10 = pk[32 * 4 + 2], w11 = pk[32 * 4 + 3];  // M^32
+                const double sBx = fma(w00, sAx, fma(w01, sAy, totAx));
+                const double sBy = fma(w10, sAx, fma(w11, sAy, totAy));
+                double eAx = __shfl_up_sync(0xffffffffu, cAx, 1), eAy = __shfl_up_sync(0xffffffffu, cAy, 1);
+                double eBx = __shfl_up_sync(0xffffffffu, cBx, 1), eBy = __shfl_up_sync(0xffffffffu, cBy, 1);
+                if (lane == 0) { eAx = 0.0; eAy = 0.0; eBx = 0.0; eBy = 0.0; }
+                const double l00 = pk[lane * 4 + 0], l01 = pk[lane * 4 + 1], l10 = pk[lane * 4 + 2], l11 = pk[lane * 4 + 3];
+                y1 = pk_make((float)fma(l00, sAx, fma(l01, sAy, eAx)), (float)fma(l00, sBx, fma(l01, sBy, eBx)));  // y[-1] of the chunks
+                y2 = pk_make((float)fma(l10, sAx, fma(l11, sAy, eAy)), (float)fma(l10, sBx, fma(l11, sBy, eBy)));  // y[-2]
+            } else {
+                float sAx = sAxf, sAy = sAyf;
+                const float4 m64 = pf[34];
+                for (int q = 0; q < warp; ++q) {
+                    const double2 tq = totals[k * X2_WARPS + q];
+                    const float tx = fmaf(m64.x, sAx, fmaf(m64.y, sAy, (float)tq.x));
+                    const float ty = fmaf(m64.z, sAx, fmaf(m64.w, sAy, (float)tq.y));
+                    sAx = tx;
+                    sAy = ty;
+                }
+                float zAx, zBx, zAy, zBy;
+                pk_split(c1, zAx, zBx);
+                pk_split(c2, zAy, zBy);
+                const float totAx = __shfl_sync(0xffffffffu, zAx, 31), totAy = __shfl_sync(0xffffffffu, zAy, 31);
+                const float4 mw = pf[32];
+                const float sBx = fmaf(mw.x, sAx, fmaf(mw.y, sAy, totAx));
+                const float sBy = fmaf(mw.z, sAx, fmaf(mw.w, sAy, totAy));
+                pk2 e1 = pk_shfl_up(c1, 1), e2 = pk_shfl_up(c2, 1);
+                if (lane == 0) { e1 = 0ull; e2 = 0ull; }
+                const float4 ml = pf[lane];
+                const pk2 S1 = pk_make(sAx, sBx), S2 = pk_make(sAy, sBy);
+                y1 = pk_fma(pk_dup(ml.x), S1, pk_fma(pk_dup(ml.y), S2, e1));
+                y2 = pk_fma(pk_dup(ml.z), S1, pk_fma(pk_dup(ml.w), S2, e2));
             }
-            const double sBx = fma(w00, sAx, fma(w01, sAy, totAx));
-            const double sBy = fma(w10, sAx, fma(w11, sAy, totAy));
-            double eAx = __shfl_up_sync(0xffffffffu, cAx, 1), eAy = __shfl_up_sync(0xffffffffu, cAy, 1);
-            double eBx = __shfl_up_sync(0xffffffffu, cBx, 1), eBy = __shfl_up_sync(0xffffffffu, cBy, 1);
-            if (lane == 0) { eAx = 0.0; eAy = 0.0; eBx = 0.0; eBy = 0.0; }
-            const double l00 = pk[lane * 4 + 0], l01 = pk[lane * 4 + 1], l10 = pk[lane * 4 + 2], l11 = pk[lane * 4 + 3];
-            const pk2 y1 = pk_make((float)fma(l00, sAx, fma(l01, sAy, eAx)), (float)fma(l00, sBx, fma(l01, sBy, eBx)));  // y[-1] of the chunks
-            const pk2 y2 = pk_make((float)fma(l10, sAx, fma(l11, sAy, eAy)), (float)fma(l10, sBx, fma(l11, sBy, eBy)));  // y[-2]
             // the feed-forward taps on the two inputs before the chunk, left out in step 1
             pk_fma_acc(v[0], B1, um1); pk_fma_acc(v[0], B2, um2);
             pk_fma_acc(v[1], B2, um1);
