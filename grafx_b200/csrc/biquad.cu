@@ -856,6 +856,9 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
             return GFX_OK;
         }
     }
+    if constexpr (sizeof(T) == 4) {
+        return GFX_ERR_UNSUPPORTED;  // (not reached: fp32 always takes the packed kernel above)
+    } else {
     const size_t smem = cascade_smem_bytes<T>(NT, K);
     if (smem > (size_t)device_info().max_smem_optin) return GFX_ERR_UNSUPPORTED;
     auto kern = biquad_cascade_kernel<T, NT, MINB>;
@@ -873,6 +876,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     kern<<<(unsigned)grid, NT, smem, stream>>>(p);
     GFX_LAUNCH_CHECK();
     return GFX_OK;
+    }
 }
 
 }  // namespace gfx

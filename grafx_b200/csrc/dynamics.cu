@@ -106,6 +106,18 @@ struct DynCtx {
     bool have_state;
 };
 
+// The ballistics variant (NT == 64) gives a whole ROW to one CTA, which walks its tiles in order: the recursion of a
+// row is one long dependent chain anyway, so nothing is gained by spreading its tiles over CTAs and a hand-over through
+// global memory (flag, fence, L1 invalidate: ~18 us per tile as measured) is saved.  The smoother states then live
+// in shared memory, double-buffered by tile parity.  The scan variant (NT == 256) chains tiles across CTAs.
+template <int NT>
+__device__ __forceinline__ constexpr bool row_owner() { return NT == 64; }
+
+template <int NT>
+__device__ __forceinline__ float* state_slots(const DynCtx<NT>& cx, int t_idx) {
+    return cx.s_state + (row_owner<NT>() ? (t_idx & 1) * 2 * DYN_MAX_STAGES : 0);
+}
+
 template <int NT>
 __device__ __forceinline__ void ensure_state(DynCtx<NT>& cx, const DynParams& p) {
     if (cx.have_state) return;
@@ -113,16 +125,26 @@ __device__ __forceinline__ void ensure_state(DynCtx<NT>& cx, const DynParams& p)
     const int ns2 = 2 * p.n_stages;
     if (cx.warp == 0) {
         if (cx.t_idx > 0) {
-            if (cx.lane == 0) chain_wait(p.flags + cx.row, cx.t_idx);
-            __syncwarp();
-            if (cx.lane < ns2) cx.s_state[cx.lane] = __ldcg(p.state + (size_t)cx.row * ns2 + cx.lane);
+            if constexpr (!row_owner<NT>()) {
+                if (cx.lane == 0) chain_wait(p.flags + cx.row, cx.t_idx);
+                __syncwarp();
+                if (cx.lane < ns2) cx.s_state[cx.lane] = __ldcg(p.state + (size_t)cx.row * ns2 + cx.lane);
+            }
         } else if (cx.lane < ns2) {
             const StageDesc& sd = p.st[cx.lane >> 1];
             const int kind = (cx.lane & 1) ? sd.post.kind : sd.pre.kind;
-            cx.s_state[cx.lane] = kind == 2 ? 1.f : 0.f;  // ballistics starts from zi = 1
+            state_slots<NT>(cx, 0)[cx.lane] = kind == 2 ? 1.f : 0.f;  // ballistics starts from zi = 1
         }
     }
     __syncthreads();
+}
+
+// the state a smoother leaves for the next tile of the row
+template <int NT>
+__device__ __forceinline__ void leave_state(DynCtx<NT>& cx, const DynParams& p, int slot, float value) {
+    if (cx.t_idx + 1 >= p.tiles) return;
+    if constexpr (row_owner<NT>()) state_slots<NT>(cx, cx.t_idx + 1)[slot] = value;
+    else p.state[(size_t)cx.row * 2 * p.n_stages + slot] = value;
 }
 
 // ---- truncated one-pole smoother on the register chunk u[32]; `slot` = index into the row state
@@ -168,7 +190,7 @@ __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, f
     if (cx.lane == 31) wt[cx.warp] = z;
     ensure_state(cx, p);  // (first stateful op of the tile also syncs here)
     __syncthreads();
-    float s = cx.s_state[slot];
+    float s = state_slots<NT>(cx, cx.t_idx)[slot];
     for (int q = 0; q < cx.warp; ++q) s = fmaf(aW, s, wt[q]);
     float ex = __shfl_up_sync(0xffffffffu, z, 1);
     if (cx.lane == 0) ex = 0.f;
@@ -179,7 +201,62 @@ __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, f
         y = fmaf(alpha, y, u[i]);
         u[i] = fmaxf(y * oma, 0.f);
     }
-    if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles) p.state[(size_t)cx.row * 2 * p.n_stages + slot] = y;
+    if (cx.tid == NT - 1) leave_state<NT>(cx, p, slot, y);
+}
+
+// The walk itself: NT rows of 32 samples.  Every instruction of the walking lane costs a full warp slot of its
+// sub-partition (2 cycles per pipe), so nothing but the chain (FFMA, FFMA, FMNMX per sample) and the 128-bit
+// shared-memory accesses is issued: rows are taken eight at a time so that the XOR swizzle (unit c of row r sits at
+// physical unit c ^ (r & 7)) and all offsets are compile-time, and two register sets alternate (the next row loads
+// while this one is walked) without copies.
+template <int NT, bool USE_MIN>
+__device__ __forceinline__ float ballistics_walk(float4* wa, const float4* wr, float y, float at, float rt) {
+    const float omat = 1.f - at, omrt = 1.f - rt;
+    float4 a0[4], r0[4], a1[4], r1[4];  // two register sets of half a row (16 samples) each
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { a0[c] = wa[c]; r0[c] = wr[c]; }  // row 0: swizzle 0, logical = physical
+    static_assert(NT % 8 == 0, "rows are walked in groups of eight");
+#pragma unroll 1
+    for (int r8 = 0; r8 < NT / 8; ++r8) {
+        float4* pa = wa + r8 * 64;        // 8 rows x 8 units
+        const float4* pr = wr + r8 * 64;
+        const bool more = r8 + 1 < NT / 8;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4(&ca)[4] = h ? a1 : a0;
+                float4(&cr)[4] = h ? r1 : r0;
+                float4(&na)[4] = h ? a0 : a1;
+                float4(&nr)[4] = h ? r0 : r1;
+                // next half row: the second half of this row, the first half of the next one, or of the next group
+                if (h == 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { na[c] = pa[rr * 8 + ((4 + c) ^ rr)]; nr[c] = pr[rr * 8 + ((4 + c) ^ rr)]; }
+                } else if (rr < 7) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { na[c] = pa[(rr + 1) * 8 + (c ^ (rr + 1))]; nr[c] = pr[(rr + 1) * 8 + (c ^ (rr + 1))]; }
+                } else if (more) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { na[c] = pa[64 + c]; nr[c] = pr[64 + c]; }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float* a = reinterpret_cast<float*>(&ca[c]);
+                    const float* b = reinterpret_cast<const float*>(&cr[c]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float ya = fmaf(omat, y, a[k]), yr = fmaf(omrt, y, b[k]);
+                        y = USE_MIN ? fminf(ya, yr) : fmaxf(ya, yr);
+                        a[k] = y;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) pa[rr * 8 + ((4 * h + c) ^ rr)] = ca[c];
+            }
+        }
+    }
+    return y;
 }
 
 // ---- attack/release ballistics on the register chunk (sequential over the tile)
@@ -205,43 +282,9 @@ __device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParam
     ensure_state(cx, p);
     __syncthreads();
     if (cx.tid == cx.walker) {
-        float y = cx.s_state[slot];
-        const float omat = 1.f - at, omrt = 1.f - rt;
-        const bool use_min = at >= rt;
-        float4 ca[4], cr[4], na[4], nr[4];  // half a row (16 samples) in flight, the next half already loading
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { ca[c] = wa[swz_unit(0, c)]; cr[c] = wr[swz_unit(0, c)]; }
-#pragma unroll 1
-        for (int hh = 0; hh < 2 * NT; ++hh) {
-            const int r = hh >> 1, c0 = (hh & 1) * 4;
-            const int hn = hh + 1 < 2 * NT ? hh + 1 : hh;
-            const int rn = hn >> 1, cn = (hn & 1) * 4;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { na[c] = wa[swz_unit(rn, cn + c)]; nr[c] = wr[swz_unit(rn, cn + c)]; }
-            if (use_min) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float* a = reinterpret_cast<float*>(&ca[c]);
-                    const float* b = reinterpret_cast<const float*>(&cr[c]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { y = fminf(fmaf(omat, y, a[k]), fmaf(omrt, y, b[k])); a[k] = y; }
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float* a = reinterpret_cast<float*>(&ca[c]);
-                    const float* b = reinterpret_cast<const float*>(&cr[c]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { y = fmaxf(fmaf(omat, y, a[k]), fmaf(omrt, y, b[k])); a[k] = y; }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                wa[swz_unit(r, c0 + c)] = ca[c];
-                ca[c] = na[c];
-                cr[c] = nr[c];
-            }
-        }
+        const float y0 = state_slots<NT>(cx, cx.t_idx)[slot];
+        const float yend = (at >= rt) ? ballistics_walk<NT, true>(wa, wr, y0, at, rt) : ballistics_walk<NT, false>(wa, wr, y0, at, rt);
+        (void)yend;
     }
     __syncthreads();
 #pragma unroll
@@ -249,10 +292,7 @@ __device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParam
         const float4 v = wa[swz_unit(cx.tid, c)];
         u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
     }
-    if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles) {
-        // the state after the last sample of a FULL tile (partial tiles are always the last)
-        p.state[(size_t)cx.row * 2 * p.n_stages + slot] = u[31];
-    }
+    if (cx.tid == NT - 1) leave_state<NT>(cx, p, slot, u[31]);  // the state after the last sample of a FULL tile
 }
 
 // bare SFU ops (no denormal / range fix-up code around them: the arguments here are >= 1e-5 resp. bounded)
@@ -443,8 +483,13 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
         __syncthreads();
         const unsigned int item = sh_item;
         if (item >= p.n_items) break;
-        cx.t_idx = (int)(item / (unsigned)p.batch);
-        cx.row = (int)(item - (unsigned)cx.t_idx * (unsigned)p.batch);
+        // scan variant: item = (tile, row), one tile; ballistics variant: item = row, all its tiles in order
+        const int t_first = row_owner<NT>() ? 0 : (int)(item / (unsigned)p.batch);
+        const int t_last = row_owner<NT>() ? p.tiles - 1 : t_first;
+        cx.row = row_owner<NT>() ? (int)item : (int)(item - (unsigned)t_first * (unsigned)p.batch);
+        for (int tt = t_first; tt <= t_last; ++tt) {
+        if (tt > t_first) __syncthreads();  // the previous tile has left shared memory
+        cx.t_idx = tt;
         cx.t0 = (long long)cx.t_idx * TILE;
         cx.remain = p.L - cx.t0;
         cx.sync_parity = 0;
@@ -574,7 +619,9 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
                 }
             }
         }
-        if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles && cx.have_state) chain_publish(p.flags + cx.row, cx.t_idx + 1);
+        if constexpr (!row_owner<NT>()) {
+            if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles && cx.have_state) chain_publish(p.flags + cx.row, cx.t_idx + 1);
+        }
 
         // ---- store coalesced
         __syncthreads();
@@ -603,13 +650,14 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
                     yr[cx.t0 + i] = xs[(size_t)c * TILE + (size_t)swz_unit(i >> 5, (i & 31) >> 2) * 4 + (i & 3)];
             }
         }
+        }  // tiles of the item
     }
 }
 
 static size_t dyn_smem_bytes(int NT, int C) {
     // two scratch tiles (at*u, rt*u) are only used by the ballistics variant (NT == 64)
     return (size_t)(C + (NT == 64 ? 2 : 0)) * NT * 128 +
-           (size_t)(DYN_ROW_FLOATS + 2 * (NT / 32) + 2 * DYN_MAX_STAGES) * sizeof(float) + 64;
+           (size_t)(DYN_ROW_FLOATS + 2 * (NT / 32) + 4 * DYN_MAX_STAGES) * sizeof(float) + 64;
 }
 
 static size_t dyn_tables_offset(int batch, int n_stages) {
@@ -685,7 +733,7 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
     if (!workspace || workspace_bytes < need) return GFX_ERR_WORKSPACE;
     p.x = x; p.y = y; p.batch = batch; p.C = channels; p.L = L;
     p.tiles = (int)tiles_ll;
-    p.n_items = (unsigned)((long long)batch * tiles_ll);
+    p.n_items = any_ballistics ? (unsigned)batch : (unsigned)((long long)batch * tiles_ll);  // rows | (tile, row) pairs
     unsigned char* w = (unsigned char*)workspace;
     const size_t flags_bytes = ((size_t)batch * sizeof(int) + 255) / 256 * 256;
     p.ticket = (unsigned int*)w;
