@@ -63,6 +63,9 @@ SIGNATURES = {
     "gfx_reverb_ir_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gfx_reverb_ir_f32": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "gfx_noise_shaping_ir_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gfx_noise_shaping_ir_f32": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "gfx_drywet_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
     "gfx_node_sum_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll,
                                  c_void_p]),

@@ -447,3 +447,27 @@ def pointwise(op: str, x: torch.Tensor, p0=None, p1=None, p2=None, p3=None, dc=N
                                                  *[_cabi.ptr(t) for t in keep], int(order), int(flags), _cabi.stream_ptr())
         _cabi.check(code, "gfx_pointwise_f32")
     return y
+
+
+def noise_shaping_ir(noise: torch.Tensor, offset: int, decay: torch.Tensor, gain: torch.Tensor, fade=None, fade_gain=None,
+                     ir_len: int = 0):
+    """FilteredNoiseShapingReverb impulse response (reverb.py:364-380): band-filtered noise [C, K, T_noise] shaped by
+    per-band exponential envelopes (already activated log-slopes / gains [B, C, K]).  Returns (ir [B, C, ir_len]
+    un-normalised, energy [B, C])."""
+    _cabi.require_cuda(noise, decay, gain)
+    assert noise.ndim == 3 and decay.ndim == 3 and decay.shape == gain.shape and decay.shape[1:] == noise.shape[:2]
+    noise = _prep(noise, torch.float32)
+    B, C, K = decay.shape
+    ps = [_prep(decay, torch.float32), _prep(gain, torch.float32), None if fade is None else _prep(fade, torch.float32),
+          None if fade_gain is None else _prep(fade_gain, torch.float32)]
+    ir = torch.empty(B, C, ir_len, dtype=torch.float32, device=noise.device)
+    energy = torch.empty(B, C, dtype=torch.float32, device=noise.device)
+    if ir.numel():
+        L_ = _cabi.lib()
+        ws = _cabi.workspace(L_.gfx_noise_shaping_ir_workspace_bytes(B, C, ir_len), noise.device)
+        with torch.cuda.device(noise.device):
+            code = L_.gfx_noise_shaping_ir_f32(noise.data_ptr(), noise.shape[2], int(offset), *[_cabi.ptr(t) for t in ps],
+                                               ir.data_ptr(), energy.data_ptr(), ws.data_ptr(), ws.numel(), B, C, K, ir_len,
+                                               _cabi.stream_ptr())
+        _cabi.check(code, "gfx_noise_shaping_ir_f32")
+    return ir, energy

@@ -22,7 +22,8 @@ from .filter import (  # noqa: F401
     PoleZeroFilter,
     StateVariableFilter,
 )
-from .reverb import STFTMaskedNoiseReverb  # noqa: F401
+from .delay import MultitapDelay  # noqa: F401
+from .reverb import FilteredNoiseShapingReverb, STFTMaskedNoiseReverb  # noqa: F401
 from .nonlinear import (  # noqa: F401
     ChebyshevDistortion,
     PiecewiseTanhDistortion,

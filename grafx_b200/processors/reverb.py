@@ -6,6 +6,8 @@ uniform noise -> torch.stft), so it is bit-identical to the reference's buffer. 
 impulse response is synthesised by csrc/reverb.cu and applied by the FIR engine (csrc/fir.cu)."""
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -77,4 +79,81 @@ class STFTMaskedNoiseReverb(nn.Module):
         size = {"init_log_magnitude": (2, self.num_bins), "delta_log_magnitude": (2, self.num_bins)}
         if self.gain_envelope:
             size["gain_env_log_magnitude"] = (2, self.num_frames)
+        return size
+
+
+def _filtered_noise(noise_len, num_channels, num_bands, f_min, f_max, scale, sr, zerophase, order):
+    """Constructor-time host preprocessing, as upstream (core/noise.py:9-75): uniform noise from numpy's global
+    generator split into `num_bands` bands by a Linkwitz-Riley tree of Butterworth sections (scipy)."""
+    from scipy.signal import butter, sosfilt, sosfiltfilt
+
+    from .core.fir import _from_scale, _to_scale
+
+    x = 2 * np.random.rand(num_channels, noise_len) - 1
+    s_breaks = np.linspace(_to_scale(f_min, scale), _to_scale(f_max, scale), num_bands * 2 - 1)[1::2]
+    f_breaks = _from_scale(torch.from_numpy(s_breaks), scale).numpy()
+    bands = []
+    for f in f_breaks:
+        lp, hp = butter(order, f, "lowpass", fs=sr, output="sos"), butter(order, f, "highpass", fs=sr, output="sos")
+        if zerophase:
+            low, x = sosfiltfilt(lp, x), sosfiltfilt(hp, x)
+        else:
+            low, x = sosfilt(lp, sosfilt(lp, x)), sosfilt(hp, sosfilt(hp, x))
+        bands.append(low)
+    bands.append(x)
+    return torch.from_numpy(np.stack(bands, 1)).float()
+
+
+class FilteredNoiseShapingReverb(nn.Module):
+    """Drop-in for grafx.processors.reverb.FilteredNoiseShapingReverb (reverb.py:231-460): band-filtered noise shaped
+    by per-band exponential decays (and optional fade-ins), unit-energy normalised, applied by causal convolution.
+    The [B, C, K, T] envelope broadcast of the reference is one fused kernel (csrc/reverb.cu:
+    noise_shaping_ir_kernel); the normalisation is folded into the filter spectra of the FIR engine."""
+
+    def __init__(self, ir_len=60000, num_bands=12, processor_channel="midside", f_min=31.5, f_max=15000, scale="log",
+                 sr=30000, zerophase=True, order=2, noise_randomness="pseudo-random", use_fade_in=False,
+                 min_decay_ms=50, max_decay_ms=2000, flashfftconv=True, max_input_len=2**17):
+        super().__init__()
+        if processor_channel not in ("midside", "stereo", "mono"):
+            raise ValueError(f"Unknown channel type: {processor_channel}")
+        if noise_randomness not in ("pseudo-random", "fixed"):
+            raise ValueError(f"Invalid noise_randomness argument: {noise_randomness}")
+        self.num_bands = num_bands
+        self.processor_channel = processor_channel
+        self.num_channels = 1 if processor_channel == "mono" else 2
+        self.ir_len = ir_len
+        self.noise_randomness = noise_randomness
+        noise_len = ir_len if noise_randomness == "fixed" else ir_len * 5
+        self.register_buffer("filtered_noise", _filtered_noise(noise_len, self.num_channels, num_bands, f_min, f_max,
+                                                               scale, sr, zerophase, order).unsqueeze(0))
+        self.min_decay = (-60 / (min_decay_ms * sr / 1000)) / 20 * math.log(10)
+        self.max_decay = (-60 / (max_decay_ms * sr / 1000)) / 20 * math.log(10)
+        self.use_fade_in = use_fade_in
+
+    def compute_ir(self, log_decay, log_gain, log_fade_in=None, z_fade_in_gain=None):
+        """Un-normalised response [B, C, ir_len] and its row energies [B, C]."""
+        decay = torch.sigmoid(log_decay) * (self.max_decay - self.min_decay) + self.min_decay
+        fade = fade_gain = None
+        if self.use_fade_in:
+            fade = torch.sigmoid(log_fade_in) * (decay - self.min_decay) + self.min_decay
+            fade_gain = torch.sigmoid(z_fade_in_gain)
+        start = 0
+        if self.noise_randomness == "pseudo-random":
+            start = int(torch.randint(0, self.filtered_noise.shape[-1] - self.ir_len, (1,)))
+        return F_.noise_shaping_ir(self.filtered_noise[0], start, decay, log_gain, fade, fade_gain, self.ir_len)
+
+    def forward(self, input_signals, log_decay, log_gain, log_fade_in=None, z_fade_in_gain=None):
+        ir, energy = self.compute_ir(log_decay, log_gain, log_fade_in, z_fade_in_gain)
+        if self.num_channels == 1:
+            return F_.fir_conv(input_signals, ir * torch.rsqrt(energy + 1e-12).unsqueeze(-1), "causal")
+        if self.processor_channel == "midside":
+            return F_.ms_to_lr(F_.fir_conv_midside_ir(F_.lr_to_ms(input_signals), ir, energy, to_lr=False))
+        return F_.fir_conv_midside_ir(input_signals, ir, energy, to_lr=False)
+
+    def parameter_size(self):
+        shape = (self.num_channels, self.num_bands)
+        size = {"log_decay": shape, "log_gain": shape}
+        if self.use_fade_in:
+            size["log_fade_in"] = shape
+            size["z_fade_in_gain"] = shape
         return size

@@ -141,6 +141,19 @@ GFX_API int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_str
                               size_t workspace_bytes, int batch, int n_fft, int hop, int ir_len, int mode,
                               void* stream);
 
+/* ---- filtered-noise-shaping reverb: impulse-response synthesis -----------------------------------
+ * Replaces the envelope broadcast of FilteredNoiseShapingReverb.forward (processors/reverb.py:364-380):
+ *   ir[b,c,t] = sum_k noise[c,k,offset+t] * gain[b,c,k] * (exp(t*decay[b,c,k]) - fade_gain[b,c,k] * exp(t*fade[b,c,k]))
+ * noise [channels, bands, noise_len] (the band-filtered noise buffer); decay/gain/fade/fade_gain [batch, channels,
+ * bands] ALREADY activated (decay, fade: log-slopes per sample; fade, fade_gain NULL without `use_fade_in`);
+ * ir [batch, channels, ir_len] un-normalised; energy [batch, channels] = sum_t ir^2 (for normalize_impulse, e.g.
+ * through gfx_fir_conv_midside_ir_f32 when channels = 2).  bands <= 32. */
+GFX_API size_t gfx_noise_shaping_ir_workspace_bytes(int batch, int channels, int ir_len);
+GFX_API int gfx_noise_shaping_ir_f32(const float* noise, long long noise_len, long long noise_offset, const float* decay,
+                                     const float* gain, const float* fade, const float* fade_gain, float* ir,
+                                     float* energy, void* workspace, size_t workspace_bytes, int batch, int channels,
+                                     int bands, int ir_len, void* stream);
+
 /* ---- dry/wet mix -----------------------------------------------------------------------------
  * Replaces the mix in DryWet.forward (processors/container.py:62-67):
  *   y[b] = weight[b] * wet[b] + (1 - weight[b]) * dry[b],   dry/wet/y [batch, inner], weight [batch]. */

@@ -639,3 +639,49 @@ def parallel_mix_weights(parallel_weights, activation="softmax"):
     if activation == "softmax":
         return torch.softmax(parallel_weights, -1)
     return torch.nn.functional.softplus(parallel_weights) / (math.log(2) * n)
+
+
+def surrogate_delay_ir(delay_z, segment_len, straight_through=True):
+    """core/delay.py:40-77 forward values: z -> z tanh|z| / |z|; irfft of (z + 1e-7)^n, n <= N/2; with the
+    straight-through trick the forward value is a unit impulse at the arg-max."""
+    z = torch.view_as_complex(delay_z.contiguous()).reshape(-1)
+    mag = z.abs()
+    loss = ((1 - torch.tanh(mag)) ** 2).sum()
+    z = z * torch.tanh(mag) / (mag + 1e-7)
+    n = torch.arange(segment_len // 2 + 1, device=z.device)[None, :]
+    irs = torch.fft.irfft((z[:, None] + 1e-7) ** n)
+    if straight_through:
+        hard = torch.zeros_like(irs)
+        hard[torch.arange(irs.shape[0]), irs.argmax(-1)] = 1
+        irs = irs + (hard - irs)
+    return irs.reshape(*delay_z.shape[:-1], -1), loss
+
+
+def multitap_delay(x, delay_z, log_fir_magnitude=None, window=None, segment_len=3000, num_segments=20,
+                   num_delay_per_segment=1, num_channels=2, pre_delay=0):
+    """delay.py:104-140."""
+    irs, loss = surrogate_delay_ir(delay_z, segment_len)
+    if log_fir_magnitude is not None:
+        irs = convolve(irs, zerophase_fir(log_fir_magnitude, window), "zerophase")
+    b, _, t = irs.shape
+    irs = irs.reshape(b, num_channels, num_segments, num_delay_per_segment, t).sum(-2).reshape(b, num_channels, -1)
+    y = convolve(x, normalize_impulse(irs), "causal")
+    if pre_delay:
+        y = F.pad(y, (pre_delay, 0))[:, :, :-pre_delay]
+    return y, loss
+
+
+def noise_shaping_reverb(x, log_decay, log_gain, filtered_noise, min_decay, max_decay, log_fade_in=None,
+                         z_fade_in_gain=None, processor_channel="midside"):
+    """reverb.py:364-398 ("fixed" noise: filtered_noise [C, K, ir_len])."""
+    t = torch.arange(filtered_noise.shape[-1], device=x.device)[None, None, None, :]
+    decay = torch.sigmoid(log_decay) * (max_decay - min_decay) + min_decay
+    env = torch.exp(t * decay.unsqueeze(-1))
+    if log_fade_in is not None:
+        fade = torch.sigmoid(log_fade_in) * (decay - min_decay) + min_decay
+        env = env - torch.exp(t * fade.unsqueeze(-1)) * torch.sigmoid(z_fade_in_gain).unsqueeze(-1)
+    ir = (filtered_noise.to(env.dtype)[None] * env * log_gain.unsqueeze(-1)).sum(2)
+    ir = normalize_impulse(ir)
+    if processor_channel == "midside":
+        return ms_to_lr(convolve(lr_to_ms(x), ir, "causal"))
+    return convolve(x, ir, "causal")

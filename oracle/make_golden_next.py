@@ -76,6 +76,28 @@ def main():
                 x = 0.5 * randn(3, 2, 1500)
                 prm = _params(proc.parameter_size(), 3, 0.5, gen)
                 _save(f"next_{cls.lower()}_{i}", x, prm, kw, proc(x, **prm))
+        # ---- MultitapDelay (surrogate delay lines + zero-phase colouring per tap)
+        for i, kw in enumerate((dict(segment_len=300, num_segments=4, num_delay_per_segment=1, processor_channel="stereo", zp_filter_bins=8),
+                                dict(segment_len=256, num_segments=3, num_delay_per_segment=2, processor_channel="mono",
+                                     zp_filter_per_tap=False, pre_delay=17))):
+            proc = P.MultitapDelay(**kw, flashfftconv=False)
+            x = randn(2, 2 if kw["processor_channel"] == "stereo" else 1, 3000)
+            prm = _params(proc.parameter_size(), 2, 1.0, gen)
+            y, _ = proc(x, **prm)
+            extra = {"window": proc.zp_filter.window.numpy()} if kw.get("zp_filter_per_tap", True) else {}
+            _save(f"next_multitapdelay_{i}", x, prm, kw, y, extra=extra)
+        # ---- FilteredNoiseShapingReverb (the noise buffer comes from numpy's global generator: seed stored)
+        import numpy as np
+        for i, kw in enumerate((dict(ir_len=2000, num_bands=4, processor_channel="stereo", noise_randomness="fixed"),
+                                dict(ir_len=1500, num_bands=6, processor_channel="midside", noise_randomness="fixed", use_fade_in=True),
+                                dict(ir_len=1800, num_bands=5, processor_channel="mono", noise_randomness="fixed", zerophase=False,
+                                     scale="bark_traunmuller", f_max=12000))):
+            np.random.seed(100 + i)
+            proc = P.FilteredNoiseShapingReverb(**kw, flashfftconv=False)
+            x = randn(2, 1 if kw["processor_channel"] == "mono" else 2, 3000)
+            prm = _params(proc.parameter_size(), 2, 1.0, gen)
+            _save(f"next_noiseshapingreverb_{i}", x, prm, dict(kw, numpy_seed=100 + i), proc(x, **prm),
+                  extra={"filtered_noise": proc.filtered_noise[0].numpy(), "min_decay": proc.min_decay, "max_decay": proc.max_decay})
         # ---- ParallelMix of two distortions
         for act in ("softmax", "softplus"):
             proc = P.ParallelMix({"a": P.TanhDistortion(), "b": P.StereoGain()}, activation=act)

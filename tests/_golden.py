@@ -37,6 +37,8 @@ CLASS_OF_PREFIX = {
     "next_powerdistortion": "PowerDistortion",
     "next_chebyshevdistortion": "ChebyshevDistortion",
     "next_parallelmix": "ParallelMix",
+    "next_multitapdelay": "MultitapDelay",
+    "next_noiseshapingreverb": "FilteredNoiseShapingReverb",
 }
 
 
@@ -96,6 +98,16 @@ def oracle_call(name, x, params, kwargs, dtype=None, extra=None):
         return O.series_distortion("power" if cls == "PowerDistortion" else "chebyshev", x, params["basis_weights"],
                                    params.get("log_pre_gain"), remove_dc=kw.get("remove_dc", False),
                                    use_tanh=kw.get("use_tanh", False))
+    if cls == "MultitapDelay":
+        nch = 1 if kw["processor_channel"] == "mono" else 2
+        return O.multitap_delay(x, params["delay_z"], params.get("log_fir_magnitude"), ex.get("window"),
+                                segment_len=kw["segment_len"], num_segments=kw["num_segments"],
+                                num_delay_per_segment=kw["num_delay_per_segment"], num_channels=nch,
+                                pre_delay=kw.get("pre_delay", 0))[0]
+    if cls == "FilteredNoiseShapingReverb":
+        return O.noise_shaping_reverb(x, params["log_decay"], params["log_gain"], ex["filtered_noise"], float(ex["min_decay"]),
+                                      float(ex["max_decay"]), params.get("log_fade_in"), params.get("z_fade_in_gain"),
+                                      processor_channel=kw["processor_channel"])
     if cls == "ParallelMix":
         w = O.parallel_mix_weights(params["parallel_weights"], kw["activation"])
         a = O.tanh_distortion(x, params["a__log_pre_gain"])

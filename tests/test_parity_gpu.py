@@ -25,6 +25,9 @@ def build_processor(name, kwargs):
 
     if class_of(name) == "ParallelMix":
         return P.ParallelMix({"a": P.TanhDistortion(), "b": P.StereoGain()}, **kwargs).cuda()
+    kwargs = dict(kwargs)
+    if "numpy_seed" in kwargs:  # FilteredNoiseShapingReverb draws its noise from numpy's global generator at construction
+        np.random.seed(kwargs.pop("numpy_seed"))
     return getattr(P, class_of(name))(**kwargs).cuda()
 
 
