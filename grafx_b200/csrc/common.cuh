@@ -97,10 +97,15 @@ __device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) {
 }
 // in-place forms (destination tied to the addend / multiplicand): keep the sample array in fixed
 // registers across the section loop -- otherwise ptxas computes into fresh pairs and copies back
+#ifdef GFX_PK_VOLATILE
+#define GFX_PK_ASM asm volatile
+#else
+#define GFX_PK_ASM asm
+#endif
 __device__ __forceinline__ void pk_fma_acc(pk2& c, pk2 a, pk2 b) {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    GFX_PK_ASM("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
 }
-__device__ __forceinline__ void pk_mul_acc(pk2& c, pk2 a) { asm("mul.rn.f32x2 %0, %1, %0;" : "+l"(c) : "l"(a)); }
+__device__ __forceinline__ void pk_mul_acc(pk2& c, pk2 a) { GFX_PK_ASM("mul.rn.f32x2 %0, %1, %0;" : "+l"(c) : "l"(a)); }
 __device__ __forceinline__ pk2 pk_shfl_up(pk2 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 
 __device__ __forceinline__ pk2 pk_add(pk2 a, pk2 b) {
