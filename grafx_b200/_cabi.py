@@ -69,9 +69,11 @@ SIGNATURES = {
     "gfx_drywet_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
     "gfx_node_sum_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll,
                                  c_void_p]),
+    "gfx_node_copy_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_void_p]),
     "gfx_biquad_design_f32": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_void_p]),
     "gfx_row_mean_f32": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_void_p]),
+    "gfx_row_mean_square_f32": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_void_p]),
     "gfx_pointwise_f32": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int, c_int, c_void_p]),
     "gfx_midside_f32": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_float, c_void_p]),

@@ -34,7 +34,7 @@ struct SmootherDesc {
 };
 struct StageDesc {
     int kind;        // 0 compressor, 1 noise gate
-    int knee;        // 0 hard, 1 quadratic, 2 exponential
+    int knee;        // 0 hard, 1 quadratic, 2 exponential, 3 quadratic as shipped in ApproxNoiseGate (gate only)
     int log_domain;  // gain smoother runs on the log-gain
     const float* log_threshold;
     const float* log_ratio;
@@ -433,12 +433,15 @@ __global__ void dynamics_tables_kernel(const DynParams p, float* __restrict__ ta
     KneeConst k;
     for (int i = 0; i < DYN_KC_FLOATS; ++i) reinterpret_cast<float*>(&k)[i] = 0.f;
     const float T = sd.log_threshold[row] - 6.f, lr = sd.log_ratio[row], lk = sd.log_knee ? sd.log_knee[row] : 0.f;
-    const float elr = expf(lr), ratio = 1.f + elr, inv_ratio = 1.f / ratio;
+    // ApproxNoiseGate.compute_gain (dynamics.py:186-204): R = exp(log_ratio) (no +1) and the knee term is
+    // (1 - R)(d - W)^2 / (2 (2W + 1e-3)); the three regions are those of the quadratic gate knee
+    const bool approx_gate = sd.knee == 3;
+    const float elr = expf(lr), ratio = approx_gate ? elr : 1.f + elr, inv_ratio = 1.f / ratio;
     k.T = T;
-    k.W = sd.knee == 1 ? expf(lk) * 0.5f : (sd.knee == 2 ? expf(lk) : 0.f);
+    k.W = (sd.knee == 1 || approx_gate) ? expf(lk) * 0.5f : (sd.knee == 2 ? expf(lk) : 0.f);
     k.lo = T - k.W; k.hi = T + k.W;
     k.slope = sd.kind == 0 ? (inv_ratio - 1.f) : (ratio - 1.f);
-    k.mid_scale = (sd.kind == 0 ? (inv_ratio - 1.f) : (1.f - ratio)) / (4.f * k.W);
+    k.mid_scale = (sd.kind == 0 ? (inv_ratio - 1.f) : (1.f - ratio)) / (approx_gate ? 4.f * k.W + 2e-3f : 4.f * k.W);
     k.exp_scale = (sd.kind == 0 ? (inv_ratio - 1.f) : -elr) / k.W;
     k.slope2 = k.slope * DYN_LOG2E; k.mid2 = k.mid_scale * DYN_LOG2E; k.exp2s = k.exp_scale * DYN_LOG2E;
     k.Wl2 = k.W * DYN_LOG2E;
@@ -588,10 +591,11 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 8)) dynamics_kernel(const
                 if constexpr (NT == 64) smooth_ballistics<NT>(cx, p, u, sd.pre, 2 * d);  // (ballistics launches use NT = 64)
             }
 
+            const int knee_mode = sd.kind * 3 + (sd.knee == 3 ? 1 : sd.knee);  // 3: quadratic regions, own constants
             if (sd.post.kind == 0) {
-                knee_gain(u, cx.kc[d], sd.kind * 3 + sd.knee);
+                knee_gain(u, cx.kc[d], knee_mode);
             } else {
-                knee_log_gain(u, cx.kc[d], sd.kind * 3 + sd.knee);
+                knee_log_gain(u, cx.kc[d], knee_mode);
                 if (!sd.log_domain) {
 #pragma unroll
                     for (int i = 0; i < S; ++i) u[i] = __expf(u[i]);
@@ -707,7 +711,7 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
     bool any_ballistics = false;
     for (int d = 0; d < n_stages; ++d) {
         const gfx_dynamics_stage& s = stages[d];
-        if (s.kind < 0 || s.kind > 1 || s.knee < 0 || s.knee > 2) return GFX_ERR_INVALID;
+        if (s.kind < 0 || s.kind > 1 || s.knee < 0 || s.knee > 3 || (s.knee == 3 && s.kind != 1)) return GFX_ERR_INVALID;
         if (s.energy_smoother < 0 || s.energy_smoother > 2 || s.gain_smoother < 0 || s.gain_smoother > 2) return GFX_ERR_INVALID;
         if (!s.log_threshold || !s.log_ratio) return GFX_ERR_INVALID;
         if (s.knee != 0 && !s.log_knee) return GFX_ERR_INVALID;

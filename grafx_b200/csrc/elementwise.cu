@@ -105,6 +105,46 @@ __global__ void __launch_bounds__(256) node_sum_kernel(const float* __restrict__
         }
     }
 }
+// Strided block copy of a [batch, nodes, inner] view (render/core.py:6-33 create_signal_buffer writes the
+// sources into the buffer; here the buffer is node-major, so a batched input [B, V0, C, L] is transposed on
+// the way in).  Four independent 16-byte loads per thread keep enough bytes in flight for HBM.
+__global__ void __launch_bounds__(256) node_copy_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                        int nodes, long long inner, long long src_bs,
+                                                        long long src_ns, long long dst_bs, long long dst_ns, int vec,
+                                                        long long total) {
+    const long long per = vec ? inner / 4 : inner;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    auto locate = [&](long long e, const float*& s, float*& d, long long& q) {
+        q = e % per;
+        const long long bj = e / per;
+        const long long j = bj % nodes, b = bj / nodes;
+        s = src + b * src_bs + j * src_ns;
+        d = dst + b * dst_bs + j * dst_ns;
+    };
+    if (vec) {
+        for (; i + 3 * stride < total; i += 4 * stride) {
+            const float* s[4]; float* d[4]; long long q[4]; float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) locate(i + u * stride, s[u], d[u], q[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ldg_stream(reinterpret_cast<const float4*>(s[u]) + q[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) stg_stream(reinterpret_cast<float4*>(d[u]) + q[u], v[u]);
+        }
+        for (; i < total; i += stride) {
+            const float* s; float* d; long long q;
+            locate(i, s, d, q);
+            stg_stream(reinterpret_cast<float4*>(d) + q, ldg_stream(reinterpret_cast<const float4*>(s) + q));
+        }
+    } else {
+        for (; i < total; i += stride) {
+            const float* s; float* d; long long q;
+            locate(i, s, d, q);
+            d[q] = s[q];
+        }
+    }
+}
 }  // namespace gfx
 
 extern "C" int gfx_drywet_f32(const float* dry, const float* wet, const float* weight, float* y, int batch,
@@ -133,6 +173,23 @@ extern "C" int gfx_node_sum_f32(const float* src, float* dst, const int* index, 
     gfx::node_sum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         src, dst, index, batch, n_src, n_dst, inner, src_batch_stride, src_node_stride, dst_batch_stride,
         dst_node_stride, vec);
+    GFX_LAUNCH_CHECK();
+    return GFX_OK;
+}
+
+extern "C" int gfx_node_copy_f32(const float* src, float* dst, int batch, int nodes, long long inner,
+                                 long long src_batch_stride, long long src_node_stride, long long dst_batch_stride,
+                                 long long dst_node_stride, void* stream) {
+    if (!src || !dst || batch <= 0 || nodes <= 0 || inner <= 0) return GFX_ERR_INVALID;
+    const int vec = (((uintptr_t)src | (uintptr_t)dst) % 16 == 0) && (inner % 4 == 0) && (src_batch_stride % 4 == 0) &&
+                    (src_node_stride % 4 == 0) && (dst_batch_stride % 4 == 0) && (dst_node_stride % 4 == 0);
+    const long long total = (long long)batch * nodes * (vec ? inner / 4 : inner);
+    long long blocks = (total + 1023) / 1024;
+    const long long cap = (long long)gfx::device_info().sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    gfx::node_copy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        src, dst, nodes, inner, src_batch_stride, src_node_stride, dst_batch_stride, dst_node_stride, vec, total);
     GFX_LAUNCH_CHECK();
     return GFX_OK;
 }

@@ -8,7 +8,8 @@
 //   nonlinear.py:268-285 PowerDistortion            sum_k tanh(w_k) [tanh] (x g_pre)^k, k = 0..order-1
 //   nonlinear.py:349-384 ChebyshevDistortion        sum_k tanh(w_k) [tanh] T_k(x g_pre)
 //   container.py:203-216 ParallelMix accumulation   y (+)= w[b] * x
-// plus the per-row mean (`remove_dc`, nonlinear.py:65-66) as a deterministic one-CTA-per-row reduction.
+// plus the per-row mean (`remove_dc`, nonlinear.py:65-66) and mean square (rms_difference, core/utils.py:7-11, of
+// GainStagingRegularization) as a deterministic one-CTA-per-row reduction.
 // Each thread handles 4 consecutive samples (float4) of one row; per-row parameters are read once per thread
 // block iteration (rows are long: L >> block).  Upstream these are 5-20 full-length elementwise launches each.
 #include "common.cuh"
@@ -162,11 +163,21 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const PwParams p) {
     }
 }
 
-// mean over time of every row: one CTA per row, fixed summation order (deterministic)
+// mean (or mean square) over time of every row: one CTA per row, fixed summation order (deterministic)
+template <bool SQUARE>
 __global__ void __launch_bounds__(256) row_mean_kernel(const float* __restrict__ x, float* __restrict__ mean, long long L) {
     const float* xr = x + (size_t)blockIdx.x * L;
     double acc = 0.0;  // (double partials: the torch reference reduces pairwise in fp32; this stays within 1e-7 of it)
-    for (long long i = threadIdx.x; i < L; i += 256) acc += (double)xr[i];
+    if ((((uintptr_t)xr) % 16 == 0) && (L % 4 == 0)) {
+        const float4* x4 = reinterpret_cast<const float4*>(xr);
+        for (long long i = threadIdx.x; i < L / 4; i += 256) {
+            const float4 v = ldg_stream(x4 + i);
+            if (SQUARE) acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+            else acc += (double)(v.x + v.y) + (double)(v.z + v.w);
+        }
+    } else {
+        for (long long i = threadIdx.x; i < L; i += 256) acc += SQUARE ? (double)(xr[i] * xr[i]) : (double)xr[i];
+    }
     __shared__ double red[256];
     red[threadIdx.x] = acc;
     __syncthreads();
@@ -183,7 +194,14 @@ extern "C" {
 
 int gfx_row_mean_f32(const float* x, float* mean, int rows, long long L, void* stream) {
     if (!x || !mean || rows <= 0 || L <= 0) return GFX_ERR_INVALID;
-    gfx::row_mean_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, mean, L);
+    gfx::row_mean_kernel<false><<<rows, 256, 0, (cudaStream_t)stream>>>(x, mean, L);
+    GFX_LAUNCH_CHECK();
+    return GFX_OK;
+}
+
+int gfx_row_mean_square_f32(const float* x, float* mean, int rows, long long L, void* stream) {
+    if (!x || !mean || rows <= 0 || L <= 0) return GFX_ERR_INVALID;
+    gfx::row_mean_kernel<true><<<rows, 256, 0, (cudaStream_t)stream>>>(x, mean, L);
     GFX_LAUNCH_CHECK();
     return GFX_OK;
 }

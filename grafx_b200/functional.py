@@ -197,7 +197,7 @@ def iir_fsm(x: torch.Tensor, Bs: torch.Tensor, As: torch.Tensor, fir_len: int) -
     return fir_conv(x, iir_fsm_fir(Bs.detach(), As.detach(), fir_len), "causal")
 
 
-_KNEE = {"hard": 0, "quadratic": 1, "exponential": 2}
+_KNEE = {"hard": 0, "quadratic": 1, "exponential": 2, "approx_gate": 3}
 _SMOOTHER = {None: 0, "iir": 1, "ballistics": 2}
 _DYN_KIND = {"compressor": 0, "noisegate": 1}
 
@@ -320,6 +320,22 @@ def node_sum(src: torch.Tensor, node_dim: int, index: torch.Tensor | None = None
     return out4.squeeze(0) if node_dim == 0 else out4
 
 
+def node_copy(src: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[i, j] = src[i, j] for [N0, N1, C, L] views whose two leading axes may be strided (a transposed
+    batch/node pair): the source write of create_signal_buffer (render/core.py:6-33) in one pass."""
+    _cabi.require_cuda(src)
+    assert src.dtype == torch.float32 and out.dtype == torch.float32 and src.shape == out.shape and src.dim() == 4
+    N0, N1, C, L = src.shape
+    for t in (src, out):
+        assert t.stride(3) == 1 and t.stride(2) == L, "only the two leading axes may be strided"
+    if src.numel():
+        with torch.cuda.device(src.device):
+            code = _cabi.lib().gfx_node_copy_f32(src.data_ptr(), out.data_ptr(), N0, N1, C * L, src.stride(0),
+                                                 src.stride(1), out.stride(0), out.stride(1), _cabi.stream_ptr())
+        _cabi.check(code, "gfx_node_copy_f32")
+    return out
+
+
 def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_log_magnitude: torch.Tensor,
               gain_env_log_magnitude: torch.Tensor | None, window: torch.Tensor, ir_len: int, n_fft: int,
               hop_length: int, finish: str = "unit"):
@@ -427,6 +443,26 @@ def row_mean(x: torch.Tensor) -> torch.Tensor:
         with torch.cuda.device(x.device):
             _cabi.check(_cabi.lib().gfx_row_mean_f32(x.data_ptr(), m.data_ptr(), B * C, L, _cabi.stream_ptr()), "gfx_row_mean_f32")
     return m
+
+
+def mean_square(x: torch.Tensor) -> torch.Tensor:
+    """Mean of x^2 over the channel and time axes -> [B] (x.square().mean((-1, -2)) of core/utils.py:8-9)."""
+    _cabi.require_cuda(x)
+    assert x.ndim == 3
+    x = _prep(x, torch.float32)
+    B, C, L = x.shape
+    m = torch.empty(B, dtype=torch.float32, device=x.device)
+    if m.numel():
+        with torch.cuda.device(x.device):
+            _cabi.check(_cabi.lib().gfx_row_mean_square_f32(x.data_ptr(), m.data_ptr(), B, C * L, _cabi.stream_ptr()),
+                        "gfx_row_mean_square_f32")
+    return m
+
+
+def rms_difference(X: torch.Tensor, Y: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    """sum_b |log(mean X_b^2 + eps) - log(mean Y_b^2 + eps)|  (processors/core/utils.py:7-11): the two reductions
+    over the audio run on the device in one pass each, the B-element tail in PyTorch."""
+    return (torch.log(mean_square(X) + eps) - torch.log(mean_square(Y) + eps)).abs().sum()
 
 
 def pointwise(op: str, x: torch.Tensor, p0=None, p1=None, p2=None, p3=None, dc=None, order: int = 0, flags: int = 0,

@@ -1,7 +1,7 @@
 """Drop-in mirror of grafx.processors (processors/__init__.py:1-36) for the hot path."""
 from . import core  # noqa: F401
-from .container import DryWet, ParallelMix, SerialChain  # noqa: F401
-from .dynamics import Compressor, NoiseGate  # noqa: F401
+from .container import DryWet, GainStagingRegularization, ParallelMix, SerialChain  # noqa: F401
+from .dynamics import ApproxCompressor, ApproxNoiseGate, Compressor, NoiseGate  # noqa: F401
 from .eq import (  # noqa: F401
     GraphicEqualizer,
     NewZeroPhaseFIREqualizer,

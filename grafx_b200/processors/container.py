@@ -104,3 +104,28 @@ class ParallelMix(nn.Module):
         size = {k: v.parameter_size() for k, v in self.processors.items()}
         size["parallel_weights"] = len(self.processors)
         return size
+
+
+class GainStagingRegularization(nn.Module):
+    """grafx.processors.container.GainStagingRegularization (container.py:231-299): runs the wrapped processor and
+    adds `key` -> rms_difference(input, output) (core/utils.py:7-11) to the intermediates.  The two energy
+    reductions are one pass each over the audio (gfx_row_mean_square_f32)."""
+
+    def __init__(self, processor, key="gain_reg"):
+        super().__init__()
+        self.processor = processor
+        self.key = key
+
+    def forward(self, input_signals, **processor_kwargs):
+        out = self.processor(input_signals, **processor_kwargs)
+        if isinstance(out, tuple):
+            output_signals, intermediates = out
+        else:
+            output_signals, intermediates = out, {}
+        gain_reg = F_.rms_difference(input_signals, output_signals)
+        assert self.key not in intermediates
+        intermediates[self.key] = gain_reg
+        return output_signals, intermediates
+
+    def parameter_size(self):
+        return self.processor.parameter_size()

@@ -64,3 +64,43 @@ class Compressor(_DynamicsBase):
 
 class NoiseGate(_DynamicsBase):
     kind = "noisegate"
+
+
+class ApproxCompressor(nn.Module):
+    """grafx.processors.dynamics.ApproxCompressor (dynamics.py:8-115): one-pole energy follower, quadratic knee,
+    no gain smoother -- the same fused kernel as Compressor(energy_smoother="iir", gain_smoother=None)."""
+
+    def __init__(self, iir_len=16384, flashfftconv=True, max_input_len=2**17):
+        super().__init__()
+        self.iir_len = iir_len
+
+    def stage(self, z_alpha, log_threshold, log_ratio, log_knee):
+        return dict(kind="compressor", knee="quadratic", energy_smoother="iir", gain_smoother=None,
+                    gain_smooth_in_log=False, log_threshold=log_threshold, log_ratio=log_ratio, log_knee=log_knee,
+                    z_alpha_pre=z_alpha, z_alpha_post=None)
+
+    def forward(self, input_signals, z_alpha, log_threshold, log_ratio, log_knee=None):
+        return F_.dynamics_chain(input_signals, [self.stage(z_alpha, log_threshold, log_ratio, log_knee)], self.iir_len)
+
+    def parameter_size(self):
+        return {"z_alpha": 1, "log_threshold": 1, "log_ratio": 1, "log_knee": 1}
+
+
+class ApproxNoiseGate(nn.Module):
+    """grafx.processors.dynamics.ApproxNoiseGate (dynamics.py:118-210), knee as shipped (compute_gain, :186-204):
+    ratio = exp(log_ratio) and the knee term divides by 2 (W + 1e-3) -- `knee="approx_gate"` of the fused kernel."""
+
+    def __init__(self, freq_sample_n=16384, flashfftconv=True, max_input_len=2**17):
+        super().__init__()
+        self.iir_len = freq_sample_n
+
+    def stage(self, z_alpha, log_threshold, log_ratio, log_knee):
+        return dict(kind="noisegate", knee="approx_gate", energy_smoother="iir", gain_smoother=None,
+                    gain_smooth_in_log=False, log_threshold=log_threshold, log_ratio=log_ratio, log_knee=log_knee,
+                    z_alpha_pre=z_alpha, z_alpha_post=None)
+
+    def forward(self, input_signals, z_alpha, log_threshold, log_ratio, log_knee):
+        return F_.dynamics_chain(input_signals, [self.stage(z_alpha, log_threshold, log_ratio, log_knee)], self.iir_len)
+
+    def parameter_size(self):
+        return {"z_alpha": 1, "log_threshold": 1, "log_ratio": 1, "log_knee": 1}

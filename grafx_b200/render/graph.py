@@ -79,7 +79,14 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
     else:
         shape = (render_data.num_nodes, channels, audio_len) if ndim == 3 else (render_data.num_nodes, batch_size, channels, audio_len)
         signal_buffer = torch.empty(shape, device=input_signals.device, dtype=torch.float32)
-        signal_buffer.narrow(0, 0, num_sources).copy_(input_signals if ndim == 3 else input_signals.transpose(0, 1))
+        sources = signal_buffer.narrow(0, 0, num_sources)
+        if ndim == 3:
+            sources.copy_(input_signals)
+        else:
+            x_in = input_signals if input_signals.dtype == torch.float32 else input_signals.float()
+            if x_in.stride(3) != 1 or x_in.stride(2) != audio_len:
+                x_in = x_in.contiguous()
+            F_.node_copy(x_in.transpose(0, 1), sources)
 
     intermediates_list = []
     output_signals = None

@@ -175,6 +175,9 @@ GFX_API int gfx_drywet_f32(const float* dry, const float* wet, const float* weig
  *   op 6 scale-add     y = (flags&4 ? y : 0) + p0[b] * x
  * flags: 1 = post gain is 1 / pre gain (inverse_post_gain), 2 = tanh on every basis function (use_tanh), 4 = accumulate. */
 GFX_API int gfx_row_mean_f32(const float* x, float* mean, int rows, long long L, void* stream);
+/* mean over the row of x^2: the energy term of rms_difference (processors/core/utils.py:7-11) used by
+ * GainStagingRegularization (processors/container.py:284-292); rows = batch (row length channels * L). */
+GFX_API int gfx_row_mean_square_f32(const float* x, float* mean, int rows, long long L, void* stream);
 GFX_API int gfx_pointwise_f32(int op, const float* x, float* y, int batch, int channels, long long L, const float* p0,
                               const float* p1, const float* p2, const float* p3, const float* dc, int order, int flags,
                               void* stream);
@@ -188,6 +191,13 @@ GFX_API int gfx_node_sum_f32(const float* src, float* dst, const int* index, int
                              long long inner, long long src_batch_stride, long long src_node_stride,
                              long long dst_batch_stride, long long dst_node_stride, void* stream);
 
+/* Source write of create_signal_buffer (render/core.py:6-33): strided block copy of a [batch, nodes, inner]
+ * view into another (strides in elements), i.e. dst[b, j] = src[b, j]; transposes a batched input
+ * [B, V0, C, L] into the node-major signal buffer in one pass. */
+GFX_API int gfx_node_copy_f32(const float* src, float* dst, int batch, int nodes, long long inner,
+                              long long src_batch_stride, long long src_node_stride, long long dst_batch_stride,
+                              long long dst_node_stride, void* stream);
+
 /* ---- dynamics: Compressor / NoiseGate, and fused serial chains of them -------------------------
  * Replaces Compressor.forward / NoiseGate.forward (processors/dynamics.py:361-419,598-651), the
  * knees (:443-489, :675-721), TruncatedOnePoleIIRFilter and Ballistics
@@ -197,7 +207,8 @@ GFX_API int gfx_node_sum_f32(const float* src, float* dst, const int* index, int
  * `stages` is a HOST array of n_stages (<= 4) descriptors, consumed before the call returns. */
 typedef struct gfx_dynamics_stage {
     int kind;               /* 0 compressor, 1 noise gate */
-    int knee;               /* 0 hard, 1 quadratic, 2 exponential */
+    int knee;               /* 0 hard, 1 quadratic, 2 exponential, 3 quadratic as shipped in ApproxNoiseGate
+                             * (dynamics.py:186-204: R = exp(log_ratio), knee / (2 (W + 1e-3)); kind 1 only) */
     int energy_smoother;    /* 0 none, 1 truncated one-pole ("iir"), 2 ballistics */
     int gain_smoother;      /* same coding */
     int gain_smooth_in_log; /* gain smoother runs on the log-gain */

@@ -360,6 +360,17 @@ def _knee_gain(kind, knee, G, T, log_ratio, log_knee):
         if knee == "exponential":
             W = torch.exp(log_knee)
             return -torch.exp(log_ratio) * F.softplus(W * (T - G)) / W
+        if knee == "approx_gate":
+            # ApproxNoiseGate.compute_gain as shipped (dynamics.py:186-204): the ratio has no "+1" and the knee
+            # denominator is 2 (W + 1e-3) with the FULL knee width W
+            ratio = torch.exp(log_ratio)
+            W = torch.exp(log_knee)
+            below_m = G < (T - W / 2)
+            above_m = G > (T + W / 2)
+            mid_m = ~below_m & ~above_m
+            below = ratio * (G - T) + T
+            mid = G + (1 - ratio) * (G - T - W / 2).square() / 2 / (W + 1e-3)
+            return below * below_m + G * above_m + mid * mid_m - G
     raise ValueError(knee)
 
 
@@ -387,6 +398,22 @@ def dynamics(kind, x, log_threshold, log_ratio, log_knee=None, z_alpha_pre=None,
     else:
         gain = _smooth(gain_smoother, torch.exp(lg), z_alpha_post, iir_len)
     return gain[:, None, :] * x
+
+
+def approx_compressor(x, z_alpha, log_threshold, log_ratio, log_knee, iir_len=16384):
+    """ApproxCompressor.forward (dynamics.py:86-110): IIREnvelopeFollower (:753-786) + Compressor.gain_quad_knee."""
+    return dynamics("compressor", x, log_threshold, log_ratio, log_knee, z_alpha_pre=z_alpha, iir_len=iir_len)
+
+
+def approx_noisegate(x, z_alpha, log_threshold, log_ratio, log_knee, iir_len=16384):
+    """ApproxNoiseGate.forward (dynamics.py:161-184) with its own compute_gain (:186-204)."""
+    return dynamics("noisegate", x, log_threshold, log_ratio, log_knee, z_alpha_pre=z_alpha, knee="approx_gate",
+                    iir_len=iir_len)
+
+
+def rms_difference(X, Y, eps=1e-7):
+    """processors/core/utils.py:7-11 (the GainStagingRegularization term, container.py:289)."""
+    return (torch.log(X.square().mean((-1, -2)) + eps) - torch.log(Y.square().mean((-1, -2)) + eps)).abs().sum()
 
 
 def compressor(x, **kw):

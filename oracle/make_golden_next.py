@@ -112,6 +112,20 @@ def main():
                     flat[f"{k}__{n}"] = v
             _save(f"next_parallelmix_{act}", x, flat, dict(activation=act), y)
 
+        # ---- ApproxCompressor / ApproxNoiseGate (deprecated upstream, still exported) and the gain-staging term
+        for cls, key in (("ApproxCompressor", "iir_len"), ("ApproxNoiseGate", "freq_sample_n")):
+            kw = {key: 1024, "flashfftconv": False}
+            proc = getattr(P, cls)(**kw)
+            x = randn(3, 2, 3000) * torch.tensor([0.02, 0.3, 1.0])[:, None, None]
+            prm = _params(proc.parameter_size(), 3, 1.0, gen)
+            prm["log_threshold"] = prm["log_threshold"] - 2.0  # put the knee inside the range of the envelopes
+            _save(f"next_{cls.lower()}", x, prm, dict(iir_len=1024), proc(x, **prm))
+        proc = P.GainStagingRegularization(P.StereoGain())
+        x = randn(3, 2, 1500)
+        prm = _params(proc.parameter_size(), 3, 0.5, gen)
+        y, inter = proc(x, **prm)
+        _save("next_gainstaging", x, prm, {}, y, extra={"gain_reg": inter["gain_reg"].numpy()})
+
 
 if __name__ == "__main__":
     main()

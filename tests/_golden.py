@@ -39,6 +39,9 @@ CLASS_OF_PREFIX = {
     "next_parallelmix": "ParallelMix",
     "next_multitapdelay": "MultitapDelay",
     "next_noiseshapingreverb": "FilteredNoiseShapingReverb",
+    "next_approxcompressor": "ApproxCompressor",
+    "next_approxnoisegate": "ApproxNoiseGate",
+    "next_gainstaging": "GainStagingRegularization",
 }
 
 
@@ -108,6 +111,12 @@ def oracle_call(name, x, params, kwargs, dtype=None, extra=None):
         return O.noise_shaping_reverb(x, params["log_decay"], params["log_gain"], ex["filtered_noise"], float(ex["min_decay"]),
                                       float(ex["max_decay"]), params.get("log_fade_in"), params.get("z_fade_in_gain"),
                                       processor_channel=kw["processor_channel"])
+    if cls in ("ApproxCompressor", "ApproxNoiseGate"):
+        fn = O.approx_compressor if cls == "ApproxCompressor" else O.approx_noisegate
+        return fn(x, params["z_alpha"], params["log_threshold"], params["log_ratio"], params["log_knee"],
+                  iir_len=kw["iir_len"])
+    if cls == "GainStagingRegularization":
+        return O.stereo_gain(x, params["log_gain"])
     if cls == "ParallelMix":
         w = O.parallel_mix_weights(params["parallel_weights"], kw["activation"])
         a = O.tanh_distortion(x, params["a__log_pre_gain"])
