@@ -416,6 +416,75 @@ def test_node_copy_transposes_batched_sources():
         assert torch.isnan(buf[V:]).all()
 
 
+@pytest.mark.parametrize("L", [1, 3, 1023, 4099])
+def test_pointwise_and_reductions_ragged_unaligned(L):
+    """Odd lengths and views that start off a 16-byte boundary take the scalar paths of the streaming kernels."""
+    import grafx_b200.functional as F_
+    import grafx_b200.processors as P
+
+    torch.manual_seed(L)
+    x = torch.randn(3 * 2 * L + 1, device="cuda")[1:].view(3, 2, L)  # contiguous, 4-byte aligned only
+    assert x.is_contiguous() and x.data_ptr() % 16 == 4
+    lg = 0.3 * torch.randn(3, 2, device="cuda")
+    assert torch.allclose(P.StereoGain().cuda()(x, lg), x * lg.exp()[..., None], rtol=1e-6, atol=1e-7)
+    pre, post = 0.3 * torch.randn(3, 1, device="cuda"), 0.3 * torch.randn(3, 1, device="cuda")
+    y = P.TanhDistortion(inverse_post_gain=False).cuda()(x, log_pre_gain=pre, log_post_gain=post)
+    assert torch.allclose(y, torch.tanh(x * pre.exp()[..., None]) * post.exp()[..., None], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(F_.row_mean(x), x.mean(-1), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(F_.mean_square(x), x.square().mean((-1, -2)), rtol=1e-5, atol=1e-7)
+    s = P.SideGainImager().cuda()(x, lg[:, :1])
+    mid, side = x[:, 0] + x[:, 1], (x[:, 0] - x[:, 1]) * lg[:, :1].exp()
+    assert torch.allclose(s, torch.stack([(mid + side) / 2, (mid - side) / 2], 1), rtol=1e-5, atol=1e-6)
+
+
+def test_new_ops_empty_batch_and_abi_argument_errors():
+    """B = 0 returns empty tensors without a launch; the C ABI rejects bad arguments with its error codes
+    instead of launching (include/grafx_b200.h: GFX_ERR_INVALID = -1, GFX_ERR_UNSUPPORTED = -4)."""
+    import grafx_b200.functional as F_
+    import grafx_b200.processors as P
+    from grafx_b200 import _cabi
+
+    e = torch.empty(0, 2, 100, device="cuda")
+    assert P.StereoGain().cuda()(e, torch.empty(0, 2, device="cuda")).shape == (0, 2, 100)
+    assert F_.mean_square(e).shape == (0,)
+    assert F_.row_mean(e).shape == (0, 2)
+    z = P.ApproxCompressor().cuda()(e, *(torch.empty(0, 1, device="cuda") for _ in range(4)))
+    assert z.shape == (0, 2, 100)
+    L_ = _cabi.lib()
+    x = torch.randn(2, 2, 64, device="cuda")
+    y = torch.empty_like(x)
+    p0 = torch.zeros(2, 40, device="cuda")
+    st = _cabi.stream_ptr()
+    assert L_.gfx_pointwise_f32(7, x.data_ptr(), y.data_ptr(), 2, 2, 64, p0.data_ptr(), None, None, None, None, 0, 0, st) == -1
+    assert L_.gfx_pointwise_f32(0, x.data_ptr(), y.data_ptr(), 2, 2, 64, None, None, None, None, None, 0, 0, st) == -1
+    assert L_.gfx_pointwise_f32(4, x.data_ptr(), y.data_ptr(), 2, 2, 64, p0.data_ptr(), None, None, None, None, 40, 0, st) == -4
+    assert L_.gfx_pointwise_f32(1, x.data_ptr(), y.data_ptr(), 2, 1, 64, p0.data_ptr(), None, None, None, None, 0, 0, st) == -1
+    assert L_.gfx_node_copy_f32(None, y.data_ptr(), 2, 2, 64, 128, 64, 128, 64, st) == -1
+    assert L_.gfx_row_mean_square_f32(x.data_ptr(), None, 2, 128, st) == -1
+    # the ApproxNoiseGate knee exists for gates only
+    with pytest.raises(_cabi.GrafxB200Error):
+        F_.dynamics_chain(x, [dict(kind="compressor", knee="approx_gate", energy_smoother="iir",
+                                   log_threshold=p0[:, :1], log_ratio=p0[:, :1], log_knee=p0[:, :1], z_alpha_pre=p0[:, :1])])
+
+
+@pytest.mark.parametrize("L", [1, 8193, 40001])
+def test_approx_dynamics_ragged_vs_oracle(L):
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    gen = torch.Generator().manual_seed(L)
+    x = torch.randn(3, 2, L, generator=gen) * torch.tensor([0.02, 0.2, 1.0])[:, None, None]
+    prm = {k: torch.randn(3, 1, generator=gen) for k in ("z_alpha", "log_threshold", "log_ratio", "log_knee")}
+    prm["log_threshold"] -= 2.0
+    cu = {k: v.cuda() for k, v in prm.items()}
+    assert_close(P.ApproxNoiseGate(freq_sample_n=2048).cuda()(x.cuda(), **cu).cpu(), O.approx_noisegate(x, **prm, iir_len=2048), "approxgate")
+    yc = P.ApproxCompressor(iir_len=2048).cuda()(x.cuda(), **cu)
+    assert_close(yc.cpu(), O.approx_compressor(x, **prm, iir_len=2048), "approxcomp")
+    same = P.Compressor(energy_smoother="iir", gain_smoother=None, knee="quadratic", iir_len=2048).cuda()(
+        x.cuda(), cu["log_threshold"], cu["log_ratio"], cu["log_knee"], z_alpha_pre=cu["z_alpha"])
+    assert torch.equal(yc, same)
+
+
 def _geq_truth(x, params, kw):
     """float64 evaluation of the cascade defined by the fp32-normalised coefficients (what torchaudio runs)."""
     from oracle import grafx_oracle as O
