@@ -418,7 +418,13 @@ __global__ void __launch_bounds__(NT, MINB) biquad_cascade_kernel(const CascadeP
 // l+32), takes its own tickets, and never meets a block barrier -- the only synchronisation is
 // __syncwarp and the row chain in global memory.  With 4 such warps per SMSP the dependent
 // FFMA2 chains, the shuffle scan and the tile loads of different warps overlap freely.
-constexpr int X2_WARPS = 4;           // warps per CTA (pure packaging: they share nothing)
+#ifndef GFX_X2_WARPS
+#define GFX_X2_WARPS 4
+#endif
+// warps per CTA = consecutive sub-tiles of one ticket (16 warps per SM in all).  Measured on B200 (tools/cascade_shapes.py):
+// 2 warps gain 2 % on 256 x 2 x 131072, K = 5 but lose 10..40 % on few rows, K = 1 and K >= 10 (twice as many global
+// hand-offs along a row); 8 warps lose 10 % (longer ripple inside the CTA).
+constexpr int X2_WARPS = GFX_X2_WARPS;
 constexpr int X2_ROWS = 64;           // 128-byte rows per warp tile
 constexpr int X2_TILE = X2_ROWS * 32; // 2048 samples
 
@@ -840,7 +846,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
         if (X2) {
             // (fully unrolling the section loop per K was measured: no gain -- ptxas keeps its
             //  register-pair copies -- and a bigger instruction footprint; generic K only)
-            auto kern2 = biquad_cascade_x2_kernel<4, 0>;
+            auto kern2 = biquad_cascade_x2_kernel<16 / X2_WARPS, 0>;
             static size_t configured2 = 0;
             if (smem2 > configured2) {
                 GFX_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
