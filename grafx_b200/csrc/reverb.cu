@@ -362,6 +362,108 @@ __global__ void __launch_bounds__(NS_NT) noise_shaping_ir_kernel(const float* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// General STFT geometry (n_fft a power of two, 32..4096, any hop <= n_fft): the same pipeline in two plain kernels.
+// The tuned kernel above covers the reference default (384 / 192); this one keeps the other constructor arguments of
+// STFTMaskedNoiseReverb(n_fft=..., hop_length=...) on the device path.
+//   1. one CTA per (row, frame): masked half spectrum -> Hermitian-extended n_fft-point inverse FFT (radix 2, in
+//      shared memory, twiddles from sincospi) -> real part / n_fft * window -> frames [rows][frames][n_fft] (workspace);
+//   2. overlap-add of the <= ceil(n_fft / hop) frames that cover an output sample (ascending frame order), division by
+//      the overlap-added squared window, trim, mid/side or left/right rows, per-CTA partial energies.
+constexpr int RG_NT = 256;
+constexpr int RG_MAX_NFFT = 4096;
+
+__global__ void __launch_bounds__(RG_NT) reverb_frames_generic_kernel(const ReverbParams p, float* __restrict__ frames_out,
+                                                                      int n_fft, int log2n) {
+    extern __shared__ __align__(16) unsigned char rg_smem[];
+    float2* z = reinterpret_cast<float2*>(rg_smem);  // [n_fft]
+    const int m = blockIdx.x % p.frames;
+    const int row = blockIdx.x / p.frames;  // 2 * b + channel
+    const int b = row >> 1, ch = row & 1;
+    const int bins = n_fft / 2 + 1;
+    const float2* noise = p.noise + (size_t)b * p.noise_bstride + (size_t)ch * bins * p.frames + m;
+    const float ge = p.genv ? p.genv[(size_t)row * p.frames + m] : 0.f;
+    const float fm = (float)m;
+    // mask = exp((H0 - softplus(Hd) m [+ G[m]]) / 8)  (reverb.py:189-200); bit-reversed placement for the DIT passes
+    for (int k = threadIdx.x; k < bins; k += RG_NT) {
+        const float d = p.hd[(size_t)row * bins + k];
+        const float sp = d > 20.f ? d : log1pf(expf(d));
+        const float mk = expf((p.h0[(size_t)row * bins + k] - sp * fm + ge) * 0.125f);
+        const float2 nz = noise[(size_t)k * p.frames];
+        const float2 v = make_float2(nz.x * mk, nz.y * mk);
+        z[__brev((unsigned)k) >> (32 - log2n)] = v;
+        if (k > 0 && k < n_fft / 2) z[__brev((unsigned)(n_fft - k)) >> (32 - log2n)] = make_float2(v.x, -v.y);
+    }
+    __syncthreads();
+    for (int s = 1; s <= log2n; ++s) {
+        const int half = 1 << (s - 1);
+        for (int i = threadIdx.x; i < n_fft / 2; i += RG_NT) {
+            const int pos = i & (half - 1);
+            const int a = ((i >> (s - 1)) << s) + pos, c = a + half;
+            float sn, cs;
+            sincospif((float)pos / (float)half, &sn, &cs);  // e^{+i pi pos / half} = e^{+2 pi i pos / 2^s}
+            const float2 x = z[c];
+            const float2 t = make_float2(x.x * cs - x.y * sn, x.x * sn + x.y * cs);
+            const float2 u = z[a];
+            z[a] = make_float2(u.x + t.x, u.y + t.y);
+            z[c] = make_float2(u.x - t.x, u.y - t.y);
+        }
+        __syncthreads();
+    }
+    float* out = frames_out + ((size_t)row * p.frames + m) * n_fft;
+    const float scale = 1.f / (float)n_fft;
+    for (int n = threadIdx.x; n < n_fft; n += RG_NT) out[n] = z[n].x * scale * p.window[n];
+}
+
+__global__ void __launch_bounds__(RG_NT) reverb_ola_generic_kernel(const ReverbParams p, const float* __restrict__ frames_in,
+                                                                   int n_fft, int hop) {
+    const int tile = blockIdx.x % p.tiles, b = blockIdx.x / p.tiles;
+    const int t = tile * RG_NT + threadIdx.x;
+    float vm = 0.f, vs = 0.f;
+    if (t < p.ir_len) {
+        const int tp = t + n_fft / 2;  // position in the centred overlap-add buffer
+        int m_hi = tp / hop;
+        if (m_hi > p.frames - 1) m_hi = p.frames - 1;
+        int m_lo = tp - n_fft + 1 <= 0 ? 0 : (tp - n_fft + hop) / hop;  // ceil((tp - n_fft + 1) / hop)
+        const float* fm = frames_in + (size_t)(2 * b) * p.frames * n_fft;
+        const float* fs = fm + (size_t)p.frames * n_fft;
+        float env = 0.f;
+        for (int m = m_lo; m <= m_hi; ++m) {
+            const int n = tp - m * hop;
+            const float w = p.window[n];
+            env = fmaf(w, w, env);
+            vm += fm[(size_t)m * n_fft + n];
+            vs += fs[(size_t)m * n_fft + n];
+        }
+        vm /= env;
+        vs /= env;
+        float* row0 = p.ir + (size_t)(2 * b) * p.ir_len;
+        float* row1 = row0 + p.ir_len;
+        row0[t] = p.to_lr ? vm + vs : vm;
+        row1[t] = p.to_lr ? vm - vs : vs;
+    }
+    float em = vm * vm, es = vs * vs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        em += __shfl_xor_sync(0xffffffffu, em, o);
+        es += __shfl_xor_sync(0xffffffffu, es, o);
+    }
+    __shared__ float red[2][RG_NT / 32];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = em; red[1][threadIdx.x >> 5] = es; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float sum = 0.f;
+        for (int w = 0; w < RG_NT / 32; ++w) sum += red[threadIdx.x][w];
+        p.partial[(size_t)(2 * b + threadIdx.x) * p.tiles + tile] = sum;
+    }
+}
+
+static bool reverb_fast_geometry(int n_fft, int hop) { return n_fft == RV_NFFT && hop == RV_HOP; }
+static bool reverb_generic_geometry(int n_fft, int hop) {
+    return n_fft >= 32 && n_fft <= RG_MAX_NFFT && (n_fft & (n_fft - 1)) == 0 && hop >= 1 && hop <= n_fft;
+}
+static int reverb_generic_tiles(int ir_len) { return (ir_len + RG_NT - 1) / RG_NT; }
+
 static int reverb_tiles(int ir_len) {
     const int last_hop = (RV_HOP - 1 + ir_len) / RV_HOP;  // hops 1 .. last_hop carry output samples
     return (last_hop + RV_HT - 1) / RV_HT;
@@ -371,9 +473,13 @@ static int reverb_tiles(int ir_len) {
 
 extern "C" {
 
-size_t gfx_reverb_ir_workspace_bytes(int batch, int ir_len) {
+size_t gfx_reverb_ir_workspace_bytes(int batch, int n_fft, int hop, int ir_len) {
     if (batch <= 0 || ir_len <= 0) return 0;
-    return ((size_t)batch * 2 * (gfx::reverb_tiles(ir_len) + 1)) * sizeof(float);
+    if (gfx::reverb_fast_geometry(n_fft, hop)) return ((size_t)batch * 2 * (gfx::reverb_tiles(ir_len) + 1)) * sizeof(float);
+    if (!gfx::reverb_generic_geometry(n_fft, hop)) return 0;
+    // partial energies, then the windowed frames [batch * 2][frames][n_fft]
+    const size_t partial = ((size_t)batch * 2 * gfx::reverb_generic_tiles(ir_len) * sizeof(float) + 255) / 256 * 256;
+    return partial + (size_t)batch * 2 * (size_t)(1 + ir_len / hop) * n_fft * sizeof(float);
 }
 
 size_t gfx_noise_shaping_ir_workspace_bytes(int batch, int channels, int ir_len) {
@@ -413,9 +519,10 @@ int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, con
     using namespace gfx;
     if (!noise_stft || !init_log_magnitude || !delta_log_magnitude || !window || !ir || !energy) return GFX_ERR_INVALID;
     if (batch <= 0 || ir_len <= 0 || mode < 0 || mode > 3) return GFX_ERR_INVALID;
-    if (n_fft != RV_NFFT || hop != RV_HOP) return GFX_ERR_UNSUPPORTED;
-    const int tiles = reverb_tiles(ir_len);
-    if (!workspace || workspace_bytes < (size_t)batch * 2 * tiles * sizeof(float)) return GFX_ERR_WORKSPACE;
+    const bool fast = reverb_fast_geometry(n_fft, hop);
+    if (!fast && !reverb_generic_geometry(n_fft, hop)) return GFX_ERR_UNSUPPORTED;
+    const int tiles = fast ? reverb_tiles(ir_len) : reverb_generic_tiles(ir_len);
+    if (!workspace || workspace_bytes < gfx_reverb_ir_workspace_bytes(batch, n_fft, hop, ir_len)) return GFX_ERR_WORKSPACE;
     if ((long long)batch * tiles > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
     ReverbParams p;
     p.noise = (const float2*)noise_stft;
@@ -427,14 +534,27 @@ int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, con
     p.tiles = tiles;
     p.vec_ok = ((uintptr_t)ir % 16 == 0) && (ir_len % 4 == 0);
     p.to_lr = mode >= 2;
-    static bool configured = false;
-    if (!configured) {
-        GFX_CUDA_CHECK(cudaFuncSetAttribute(reverb_ir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RV_SMEM_BYTES));
-        configured = true;
-    }
     cudaStream_t st = (cudaStream_t)stream;
-    reverb_ir_kernel<<<(unsigned)(batch * tiles), 2 * RV_NT, RV_SMEM_BYTES, st>>>(p);
-    GFX_LAUNCH_CHECK();
+    if (fast) {
+        static bool configured = false;
+        if (!configured) {
+            GFX_CUDA_CHECK(cudaFuncSetAttribute(reverb_ir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RV_SMEM_BYTES));
+            configured = true;
+        }
+        reverb_ir_kernel<<<(unsigned)(batch * tiles), 2 * RV_NT, RV_SMEM_BYTES, st>>>(p);
+        GFX_LAUNCH_CHECK();
+    } else {
+        if ((long long)batch * 2 * p.frames > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
+        const size_t partial = ((size_t)batch * 2 * tiles * sizeof(float) + 255) / 256 * 256;
+        float* frames_ws = (float*)((unsigned char*)workspace + partial);
+        int log2n = 0;
+        while ((1 << log2n) < n_fft) ++log2n;
+        reverb_frames_generic_kernel<<<(unsigned)(batch * 2 * p.frames), RG_NT, (size_t)n_fft * sizeof(float2), st>>>(
+            p, frames_ws, n_fft, log2n);
+        GFX_LAUNCH_CHECK();
+        reverb_ola_generic_kernel<<<(unsigned)(batch * tiles), RG_NT, 0, st>>>(p, frames_ws, n_fft, hop);
+        GFX_LAUNCH_CHECK();
+    }
     reverb_energy_kernel<<<(batch * 2 + 127) / 128, 128, 0, st>>>(p.partial, energy, batch * 2, tiles);
     GFX_LAUNCH_CHECK();
     if (mode == 1 || mode == 2) {

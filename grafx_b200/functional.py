@@ -368,13 +368,14 @@ def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_
     if B == 0:
         return (ir, energy) if mode in (0, 3) else ir
     L_ = _cabi.lib()
-    ws = _cabi.workspace(L_.gfx_reverb_ir_workspace_bytes(B, ir_len), h0.device)
+    ws = _cabi.workspace(L_.gfx_reverb_ir_workspace_bytes(B, n_fft, hop_length, ir_len), h0.device)
     with torch.cuda.device(h0.device):
         code = L_.gfx_reverb_ir_f32(nz.data_ptr(), bstride, h0.data_ptr(), hd.data_ptr(), _cabi.ptr(ge),
                                     win.data_ptr(), ir.data_ptr(), energy.data_ptr(), ws.data_ptr(), ws.numel(),
                                     B, n_fft, hop_length, ir_len, mode, _cabi.stream_ptr())
     if code == -4:
-        raise NotImplementedError("reverb IR synthesis supports n_fft=384, hop_length=192 only")
+        raise NotImplementedError("reverb IR synthesis supports n_fft=384 with hop_length=192, or a power-of-two n_fft in "
+                                  "32..4096 with hop_length <= n_fft")
     _cabi.check(code, "gfx_reverb_ir_f32")
     return (ir, energy) if mode in (0, 3) else ir
 

@@ -129,12 +129,14 @@ GFX_API int gfx_fir_conv_midside_ir_f32(const float* x, const float* ir_raw, con
  *   init/delta_log_magnitude [batch, 2, bins]; gain_env_log_magnitude [batch, 2, frames] or NULL;
  *   window [n_fft] (the registered hann buffer); ir [batch, 2, ir_len] (output);
  *   energy [batch, 2] (output): sum_t of the squared RAW mid/side rows;
- *   workspace: gfx_reverb_ir_workspace_bytes(batch, ir_len) bytes of scratch;
+ *   workspace: gfx_reverb_ir_workspace_bytes(batch, n_fft, hop, ir_len) bytes of scratch;
  *   mode 0: ir = raw mid/side response; mode 3: raw left/right (= mid +- side) response -- feed either,
  *     with `energy`, to gfx_fir_conv_midside_ir_f32, which folds the normalisation into the filter spectra;
  *   mode 1: mid/side normalised to unit energy in place; mode 2: left/right, normalised (pseudo_midside).
- * bins = n_fft/2+1, frames = 1 + ir_len/hop.  Supported geometry: n_fft = 384, hop = 192. */
-GFX_API size_t gfx_reverb_ir_workspace_bytes(int batch, int ir_len);
+ * bins = n_fft/2+1, frames = 1 + ir_len/hop.  Geometry: n_fft = 384, hop = 192 (the reference default) runs the tuned
+ * kernel; any power-of-two n_fft in 32..4096 with 1 <= hop <= n_fft runs the general two-kernel path; anything else
+ * returns GFX_ERR_UNSUPPORTED (and a workspace size of 0). */
+GFX_API size_t gfx_reverb_ir_workspace_bytes(int batch, int n_fft, int hop, int ir_len);
 GFX_API int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, const float* init_log_magnitude,
                               const float* delta_log_magnitude, const float* gain_env_log_magnitude,
                               const float* window, float* ir, float* energy, void* workspace,

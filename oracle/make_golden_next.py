@@ -126,6 +126,15 @@ def main():
         y, inter = proc(x, **prm)
         _save("next_gainstaging", x, prm, {}, y, extra={"gain_reg": inter["gain_reg"].numpy()})
 
+        # ---- STFTMaskedNoiseReverb with non-default STFT geometries (n_fft / hop_length constructor arguments)
+        for n_fft, hop, ch, genv in ((256, 64, "pseudo_midside", False), (512, 256, "midside", True), (128, 96, "stereo", False),
+                                     (1024, 256, "pseudo_midside", True)):
+            kw = dict(ir_len=3000, processor_channel=ch, n_fft=n_fft, hop_length=hop, gain_envelope=genv, flashfftconv=False)
+            proc = P.STFTMaskedNoiseReverb(**kw)
+            x = randn(2, 2, 2048)
+            prm = _params(proc.parameter_size(), 2, 0.5, gen)
+            _save(f"next_stftreverb_{n_fft}_{hop}", x, prm, kw, proc(x, **prm))
+
 
 if __name__ == "__main__":
     main()

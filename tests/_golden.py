@@ -42,6 +42,7 @@ CLASS_OF_PREFIX = {
     "next_approxcompressor": "ApproxCompressor",
     "next_approxnoisegate": "ApproxNoiseGate",
     "next_gainstaging": "GainStagingRegularization",
+    "next_stftreverb": "STFTMaskedNoiseReverb",
 }
 
 
@@ -152,7 +153,8 @@ def oracle_call(name, x, params, kwargs, dtype=None, extra=None):
         kw.pop("flashfftconv", None)
         return O.dynamics(cls.lower(), x, **params, **kw)
     if cls == "STFTMaskedNoiseReverb":
-        return O.stft_masked_noise_reverb(x, **params, ir_len=kw["ir_len"], processor_channel=kw["processor_channel"])
+        return O.stft_masked_noise_reverb(x, **params, ir_len=kw["ir_len"], processor_channel=kw["processor_channel"],
+                                          n_fft=kw.get("n_fft", 384), hop=kw.get("hop_length", 192))
     raise KeyError(cls)
 
 

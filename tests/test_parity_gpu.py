@@ -374,6 +374,31 @@ def test_reverb_long_ir_vs_oracle(ir_len):
     assert_close(y, y_ref, f"reverb{ir_len}")
 
 
+@pytest.mark.parametrize("n_fft,hop", [(64, 16), (2048, 512), (4096, 2048), (512, 200)])
+def test_reverb_general_stft_geometry_vs_oracle(n_fft, hop):
+    """Constructor geometries other than the default 384 / 192 run the general two-kernel synthesis."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    gen = torch.Generator().manual_seed(n_fft + hop)
+    B, L, ir_len = 2, 30000, 20000
+    proc = P.STFTMaskedNoiseReverb(ir_len=ir_len, n_fft=n_fft, hop_length=hop, gain_envelope=True).cuda()
+    x = torch.randn(B, 2, L, generator=gen)
+    prm = {k: 0.5 * torch.randn(B, *v, generator=gen) for k, v in proc.parameter_size().items()}
+    y = proc(x.cuda(), **{k: v.cuda() for k, v in prm.items()}).cpu()
+    y_ref = O.stft_masked_noise_reverb(x, **prm, ir_len=ir_len, n_fft=n_fft, hop=hop)
+    assert_close(y, y_ref, f"reverb-geometry-{n_fft}-{hop}")
+
+
+def test_reverb_unsupported_geometry_fails_loudly():
+    import grafx_b200.processors as P
+
+    proc = P.STFTMaskedNoiseReverb(ir_len=2000, n_fft=300, hop_length=100).cuda()
+    prm = {k: torch.zeros(1, *v, device="cuda") for k, v in proc.parameter_size().items()}
+    with pytest.raises(NotImplementedError):
+        proc(torch.randn(1, 2, 4000, device="cuda"), **prm)
+
+
 # ------------------------------------------------------------------ SURVEY.md section 8(f) "next" processors
 @pytest.mark.parametrize("name", fixture_names(["next_"]))
 def test_next_processors_vs_reference_golden(name):
