@@ -70,6 +70,7 @@ SIGNATURES = {
     "gfx_node_sum_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll,
                                  c_void_p]),
     "gfx_node_copy_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_void_p]),
+    "gfx_lag_dots_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
     "gfx_biquad_design_f32": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_void_p]),
     "gfx_row_mean_f32": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_void_p]),

@@ -145,6 +145,76 @@ __global__ void __launch_bounds__(256) node_copy_kernel(const float* __restrict_
         }
     }
 }
+// Lagged inner products of row signals, the coefficient gradients of one biquad section (adjoint of
+// IIRFilter._process_lfilter, processors/core/iir.py:154-196; upstream gets them from torchaudio's lfilter autograd):
+//   out0[row][j] = sum_n u[n] * s0[n - j],  j = 0, 1, 2   (s[n] = 0 for n < 0), and the same for s1 -> out1 if given,
+// with u optionally stored time-reversed (u[n] read at L-1-n: the adjoint recursion runs on the reversed gradient).
+// One CTA per row; four samples per thread and step (16-byte loads); products of four samples are summed in fp32, the
+// running sums in double; fixed summation order (deterministic).
+constexpr int LAG_NT = 512;
+
+struct Lag3 {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    __device__ __forceinline__ void add4(const float4& u, const float4& s, float sm1, float sm2) {
+        a0 += (double)(fmaf(u.x, s.x, u.y * s.y) + fmaf(u.z, s.z, u.w * s.w));
+        a1 += (double)(fmaf(u.x, sm1, u.y * s.x) + fmaf(u.z, s.y, u.w * s.z));
+        a2 += (double)(fmaf(u.x, sm2, u.y * sm1) + fmaf(u.z, s.x, u.w * s.y));
+    }
+    __device__ __forceinline__ void add1(float u, float s, float sm1, float sm2) {
+        a0 += (double)u * (double)s; a1 += (double)u * (double)sm1; a2 += (double)u * (double)sm2;
+    }
+};
+
+__global__ void __launch_bounds__(LAG_NT) lag_dots_kernel(const float* __restrict__ u, const float* __restrict__ s0,
+                                                          const float* __restrict__ s1, float* __restrict__ out0,
+                                                          float* __restrict__ out1, long long L, int u_reversed, int vec) {
+    const float* ur = u + (size_t)blockIdx.x * L;
+    const float* r0 = s0 + (size_t)blockIdx.x * L;
+    const float* r1 = s1 ? s1 + (size_t)blockIdx.x * L : nullptr;
+    Lag3 A, B;
+    if (vec) {
+        const long long n4 = L / 4;
+        for (long long i = threadIdx.x; i < n4; i += LAG_NT) {
+            float4 uq;
+            if (u_reversed) {
+                const float4 t = ldg_stream(reinterpret_cast<const float4*>(ur) + (n4 - 1 - i));
+                uq = make_float4(t.w, t.z, t.y, t.x);
+            } else {
+                uq = ldg_stream(reinterpret_cast<const float4*>(ur) + i);
+            }
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(r0) + i);
+            const float4 ap = i > 0 ? __ldg(reinterpret_cast<const float4*>(r0) + i - 1) : z;
+            A.add4(uq, a, ap.w, ap.z);
+            if (r1) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(r1) + i);
+                const float4 bp = i > 0 ? __ldg(reinterpret_cast<const float4*>(r1) + i - 1) : z;
+                B.add4(uq, b, bp.w, bp.z);
+            }
+        }
+    } else {
+        for (long long n = threadIdx.x; n < L; n += LAG_NT) {
+            const float uv = u_reversed ? ur[L - 1 - n] : ur[n];
+            A.add1(uv, r0[n], n >= 1 ? r0[n - 1] : 0.f, n >= 2 ? r0[n - 2] : 0.f);
+            if (r1) B.add1(uv, r1[n], n >= 1 ? r1[n - 1] : 0.f, n >= 2 ? r1[n - 2] : 0.f);
+        }
+    }
+    __shared__ double red[6][LAG_NT / 32];
+    double v[6] = {A.a0, A.a1, A.a2, B.a0, B.a1, B.a2};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double sum = 0.0;
+        for (int w = 0; w < LAG_NT / 32; ++w) sum += red[threadIdx.x][w];
+        if (threadIdx.x < 3) out0[(size_t)blockIdx.x * 3 + threadIdx.x] = (float)sum;
+        else if (out1) out1[(size_t)blockIdx.x * 3 + threadIdx.x - 3] = (float)sum;
+    }
+}
 }  // namespace gfx
 
 extern "C" int gfx_drywet_f32(const float* dry, const float* wet, const float* weight, float* y, int batch,
@@ -190,6 +260,15 @@ extern "C" int gfx_node_copy_f32(const float* src, float* dst, int batch, int no
     if (blocks < 1) blocks = 1;
     gfx::node_copy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         src, dst, nodes, inner, src_batch_stride, src_node_stride, dst_batch_stride, dst_node_stride, vec, total);
+    GFX_LAUNCH_CHECK();
+    return GFX_OK;
+}
+
+extern "C" int gfx_lag_dots_f32(const float* u, const float* s0, const float* s1, float* out0, float* out1, int rows,
+                                long long L, int u_reversed, void* stream) {
+    if (!u || !s0 || !out0 || rows <= 0 || L <= 0 || ((s1 == nullptr) != (out1 == nullptr))) return GFX_ERR_INVALID;
+    const int vec = (L % 4 == 0) && (((uintptr_t)u | (uintptr_t)s0 | (uintptr_t)s1) % 16 == 0);
+    gfx::lag_dots_kernel<<<(unsigned)rows, gfx::LAG_NT, 0, (cudaStream_t)stream>>>(u, s0, s1, out0, out1, L, u_reversed, vec);
     GFX_LAUNCH_CHECK();
     return GFX_OK;
 }

@@ -65,6 +65,20 @@ def _new_output(shape, dtype, device) -> torch.Tensor:
     return torch.empty(shape, dtype=dtype, device=device)
 
 
+def _wants_grad(*tensors) -> bool:
+    """True when autograd is recording and one of the tensors is part of a graph: the differentiable variant of the
+    op runs (grafx_b200/autograd.py for the biquad cascade, the PyTorch statements for O(parameters) design formulas);
+    ops without one raise instead of silently cutting the graph."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _no_backward(name: str, *tensors):
+    if _wants_grad(*tensors):
+        raise NotImplementedError(
+            f"{name} has no backward pass yet (forward-only CUDA kernel); wrap the call in torch.no_grad() or detach "
+            "its inputs.  Differentiable so far: the biquad cascade (IIR family with backend lfilter / ssm).")
+
+
 def _prep(t: torch.Tensor, dtype=None) -> torch.Tensor:
     t = t.detach()
     if dtype is not None and t.dtype != dtype:
@@ -83,6 +97,12 @@ def biquad_cascade(x: torch.Tensor, Bs: torch.Tensor, As: torch.Tensor) -> torch
     assert bb == b, "batch size of the coefficients must match the signal"
     if not (c_sig == c_filt or c_sig == 1 or c_filt == 1):
         raise AssertionError("channel mismatch between signal and filter")
+    if _wants_grad(x, Bs, As):
+        if x.dtype == torch.float64:
+            raise NotImplementedError("the backward pass of the biquad cascade is float32 only")
+        from .autograd import biquad_cascade_autograd
+
+        return biquad_cascade_autograd(x, Bs, As)
     dtype = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
     x, Bs, As = _prep(x, dtype), _prep(Bs, dtype), _prep(As, dtype)
     c_out = max(c_sig, c_filt)
@@ -104,6 +124,8 @@ def biquad_cascade(x: torch.Tensor, Bs: torch.Tensor, As: torch.Tensor) -> torch
 def _midside(x: torch.Tensor, mult: float) -> torch.Tensor:
     _cabi.require_cuda(x)
     assert x.ndim == 3 and x.shape[1] == 2, "mid/side conversion needs [B, 2, L]"
+    if _wants_grad(x):  # linear and its own adjoint up to the factor: the PyTorch statement carries the graph
+        return torch.stack([(x[:, 0] + x[:, 1]) * mult, (x[:, 0] - x[:, 1]) * mult], 1)
     x = _prep(x, torch.float32)
     y = _new_output(tuple(x.shape), torch.float32, x.device)
     if y.numel() == 0:
@@ -155,6 +177,13 @@ def fir_conv(x: torch.Tensor, h: torch.Tensor, mode: str = "causal", h_repeat: i
     B, cx, L = x3.shape
     _, ch, N = h3.shape
     assert cx == ch or cx == 1 or ch == 1, "channel mismatch between signal and filter"
+    if _wants_grad(x, h):
+        if mode != "causal" or h_repeat != 1:
+            raise NotImplementedError("the backward pass of fir_conv covers mode='causal' with per-item filters")
+        from .autograd import fir_conv_autograd
+
+        y = fir_conv_autograd(x3, h3)
+        return y.squeeze(1) if squeeze else y
     x3, h3 = _prep(x3, torch.float32), _prep(h3, torch.float32)
     y = torch.empty(B, max(cx, ch), L, dtype=torch.float32, device=x.device) if squeeze else _new_output((B, max(cx, ch), L), torch.float32, x.device)
     if y.numel():
@@ -194,6 +223,8 @@ def iir_fsm_fir(Bs: torch.Tensor, As: torch.Tensor, fir_len: int) -> torch.Tenso
 def iir_fsm(x: torch.Tensor, Bs: torch.Tensor, As: torch.Tensor, fir_len: int) -> torch.Tensor:
     """Frequency-sampled FIR of the cascade + causal convolution (core/iir.py:147-152,263-276)."""
     _cabi.require_cuda(x, Bs, As)
+    if _wants_grad(x, Bs, As):
+        return fir_conv(x, iir_fsm_fir(Bs, As, fir_len), "causal")  # the FIR design is PyTorch: autograd's
     return fir_conv(x, iir_fsm_fir(Bs.detach(), As.detach(), fir_len), "causal")
 
 
@@ -210,6 +241,7 @@ def dynamics_chain(x: torch.Tensor, stages: list[dict], iir_len: int = 16384) ->
     gain_smoother, gain_smooth_in_log, log_threshold, log_ratio, log_knee, z_alpha_pre,
     z_alpha_post (tensors with leading dim B)."""
     _cabi.require_cuda(x)
+    _no_backward("dynamics_chain", x, *[v for st in stages for v in st.values() if isinstance(v, torch.Tensor)])
     assert x.ndim == 3
     B, C, L = x.shape
     x = _prep(x, torch.float32)
@@ -269,6 +301,7 @@ def dynamics_chain(x: torch.Tensor, stages: list[dict], iir_len: int = 16384) ->
 def drywet_mix(dry: torch.Tensor, wet: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     """y = w * wet + (1 - w) * dry, w per batch item used as given (container.py:62-67)."""
     _cabi.require_cuda(dry, wet, weight)
+    _no_backward("drywet_mix", dry, wet, weight)
     assert dry.shape == wet.shape
     dry, wet = _prep(dry, torch.float32), _prep(wet, torch.float32)
     w = _prep(weight, torch.float32).reshape(-1)
@@ -348,6 +381,7 @@ def reverb_ir(noise_stft: torch.Tensor, init_log_magnitude: torch.Tensor, delta_
                      raw mid/side rows) for fir_conv_midside_ir, which folds the normalisation into the
                      filter spectra (the finished IR is never stored)."""
     _cabi.require_cuda(noise_stft, init_log_magnitude, delta_log_magnitude, window)
+    _no_backward("reverb_ir", init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude)
     B = init_log_magnitude.shape[0]
     bins, frames = n_fft // 2 + 1, 1 + ir_len // hop_length
     assert tuple(init_log_magnitude.shape) == (B, 2, bins) and tuple(delta_log_magnitude.shape) == (B, 2, bins)
@@ -386,6 +420,7 @@ def fir_conv_midside_ir(x: torch.Tensor, ir_raw: torch.Tensor, energy: torch.Ten
     mid/side, or left/right when to_lr) + the energies [B, 2] of its raw mid/side rows:
     normalize_impulse (reverb.py:215-228) is folded into the filter spectra."""
     _cabi.require_cuda(x, ir_raw, energy)
+    _no_backward("fir_conv_midside_ir", x, ir_raw, energy)
     assert x.ndim == 3 and ir_raw.ndim == 3 and ir_raw.shape[1] == 2 and x.shape[0] == ir_raw.shape[0] * h_repeat
     B, cx, L = x.shape
     N = ir_raw.shape[2]
@@ -408,11 +443,32 @@ DESIGN_FAMILY = {"peq": 0, "peaking": 1, "lowshelf": 2, "highshelf": 3, "lowpass
                  "bandreject": 7, "allpass": 8, "stable": 9, "svf": 10}
 
 
+def _design_torch(family: str, *params, flags: int = 0):
+    """The PyTorch statement of the same formulas (processors/design.py): O(parameters) work, differentiable."""
+    from .processors import design as D
+
+    if family == "peq":
+        return D.parametric_eq(*params, bool(flags & 1))
+    if family in ("peaking", "lowshelf", "highshelf"):
+        return D.eq_band(family, *params)
+    if family in ("lowpass", "highpass", "bandpass", "bandreject", "allpass"):
+        return D.simple_filter(family, *params)
+    if family == "stable":
+        Bs, a1, a2 = params[:3]
+        a0 = params[3] if len(params) > 3 else None
+        return D.stable_biquad(Bs, a1, a2, a0, bool(flags & 2))
+    if family == "svf":
+        return D.state_variable(*params)
+    raise ValueError(family)
+
+
 def biquad_design(family: str, *params: torch.Tensor, flags: int = 0):
     """Parameter activations -> (Bs, As) in one launch (reference: the coefficient designers of
     processors/filter.py and eq.py:300-314; same formulas as processors/design.py, which stays as
     the PyTorch statement of them).  All parameter tensors share the shape [..., K] (for "stable"
     the first one is [..., K, 3]); returns Bs, As of shape [..., K, 3]."""
+    if _wants_grad(*params):
+        return _design_torch(family, *params, flags=flags)
     fam = DESIGN_FAMILY[family]
     ref = params[1]
     _cabi.require_cuda(*[t for t in params if t is not None])
@@ -471,6 +527,7 @@ def pointwise(op: str, x: torch.Tensor, p0=None, p1=None, p2=None, p3=None, dc=N
     """Sample-wise processors (stereo.py, nonlinear.py, the ParallelMix accumulation) in one pass; see
     gfx_pointwise_f32 in include/grafx_b200.h for the parameter meaning of every op."""
     _cabi.require_cuda(x, *[t for t in (p0, p1, p2, p3, dc) if t is not None])
+    _no_backward("pointwise", x, p0, p1, p2, p3, dc)
     assert x.ndim == 3
     x = _prep(x, torch.float32)
     B, C, L = x.shape
@@ -492,6 +549,7 @@ def noise_shaping_ir(noise: torch.Tensor, offset: int, decay: torch.Tensor, gain
     per-band exponential envelopes (already activated log-slopes / gains [B, C, K]).  Returns (ir [B, C, ir_len]
     un-normalised, energy [B, C])."""
     _cabi.require_cuda(noise, decay, gain)
+    _no_backward("noise_shaping_ir", decay, gain, fade, fade_gain)
     assert noise.ndim == 3 and decay.ndim == 3 and decay.shape == gain.shape and decay.shape[1:] == noise.shape[:2]
     noise = _prep(noise, torch.float32)
     B, C, K = decay.shape

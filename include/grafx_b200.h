@@ -200,6 +200,16 @@ GFX_API int gfx_node_copy_f32(const float* src, float* dst, int batch, int nodes
                               long long src_batch_stride, long long src_node_stride, long long dst_batch_stride,
                               long long dst_node_stride, void* stream);
 
+/* ---- backward pass of the biquad cascade ---------------------------
+ * Upstream differentiates IIRFilter._process_lfilter (processors/core/iir.py:154-196) through torchaudio's lfilter
+ * autograd.  Here the adjoint of a section is the same recursion on the time-reversed gradient (gfx_biquad_cascade_f32
+ * with the section's coefficients), and the coefficient gradients are lagged inner products:
+ *   out0[row][j] = sum_n u[n] s0[n-j], j = 0..2, and the same for (s1, out1) unless both are NULL (the section's
+ *   input and output signals share one read of u); u_reversed != 0 reads u back to front (u is the reversed-time
+ *   signal the adjoint recursion produced).  u, s0, s1 [rows, L]; out0, out1 [rows, 3]. */
+GFX_API int gfx_lag_dots_f32(const float* u, const float* s0, const float* s1, float* out0, float* out1, int rows,
+                             long long L, int u_reversed, void* stream);
+
 /* ---- dynamics: Compressor / NoiseGate, and fused serial chains of them -------------------------
  * Replaces Compressor.forward / NoiseGate.forward (processors/dynamics.py:361-419,598-651), the
  * knees (:443-489, :675-721), TruncatedOnePoleIIRFilter and Ballistics

@@ -49,6 +49,8 @@ CLASS_OF_PREFIX = {
 def fixture_names(prefixes=None):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
     names = [n for n in names if not n.startswith(("kat_", "render_", "convolve_"))]
+    if not prefixes or not any(p.startswith("grad_") for p in prefixes):
+        names = [n for n in names if not n.startswith("grad_")]  # gradient fixtures (oracle/make_golden_grad.py)
     if prefixes:
         names = [n for n in names if n.startswith(tuple(prefixes))]
     return names
@@ -166,3 +168,13 @@ def rel_l2(a, b):
 def max_rel(a, b):
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def oracle_gradients(name, x, params, kw, w):
+    """float64 gradients of sum(w * y) through the oracle restatement (torchaudio lfilter / torch.fft autograd) for
+    the gradient fixture `name` ("grad_<forward fixture name>").  Returns (y, gx, {param: grad})."""
+    x64 = x.double().requires_grad_(True)
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    y = oracle_call(name[len("grad_"):], x64, p64, kw)
+    (y * w.double()).sum().backward()
+    return y.detach(), x64.grad, {k: v.grad for k, v in p64.items()}

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from _golden import fixture_names, load, max_rel, oracle_call, rel_l2
+from _golden import fixture_names, load, max_rel, oracle_call, oracle_gradients, rel_l2
 
 TOL = 2e-5  # fp32 restatement vs fp32 reference: only op-ordering noise is allowed
 
@@ -68,3 +68,17 @@ def test_istft_restatement():
     a = O.reverb_ir(*p, ir_len=1920, use_torch_istft=True)
     b = O.reverb_ir(*p, ir_len=1920, use_torch_istft=False)
     assert rel_l2(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("name", fixture_names(["grad_"]))
+def test_oracle_gradients_match_reference_autograd(name):
+    """Backward fixtures (oracle/make_golden_grad.py: the reference under PyTorch autograd, float32) against the
+    float64 gradients of the restatement."""
+    x, params, meta, y_ref, extra = load(name)
+    w = torch.from_numpy(extra["w"])
+    y, gx, gp = oracle_gradients(name, x, params, meta["kwargs"], w)
+    assert rel_l2(y, y_ref) < 1e-4
+    assert rel_l2(gx, torch.from_numpy(extra["gx"])) < 1e-4
+    for k, g in gp.items():
+        ref = torch.from_numpy(extra["g_" + k])
+        assert max_rel(g, ref) < 1e-3, (name, k, max_rel(g, ref))

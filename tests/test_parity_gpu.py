@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from _golden import GOLDEN, class_of, fixture_names, load, max_rel, oracle_call, rel_l2
+from _golden import oracle_gradients, GOLDEN, class_of, fixture_names, load, max_rel, oracle_call, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -647,6 +647,96 @@ def test_captured_render_replays_bit_identically():
         assert torch.equal(out, ref_out)
         assert torch.equal(buf, ref_buf)
     assert torch.isfinite(out).all()
+
+
+# ------------------------------------------------------------------ backward passes
+@pytest.mark.parametrize("name", fixture_names(["grad_"]))
+def test_backward_vs_reference_autograd(name):
+    """dL/dx and dL/dparameters of sum(w * y) from the CUDA backward (grafx_b200/autograd.py) against the reference
+    under PyTorch autograd (fixture, float32) with the float64 oracle gradients as the truth: the distance to the truth
+    must not exceed the reference's own by more than 1.5x (or the tolerance)."""
+    x, params, meta, y_ref, extra = load(name)
+    kw = {k: v for k, v in meta["kwargs"].items() if k != "cls"}
+    w = torch.from_numpy(extra["w"])
+    proc = build_processor(name[len("grad_"):], kw)
+    xc = x.cuda().requires_grad_(True)
+    pc = {k: v.cuda().requires_grad_(True) for k, v in params.items()}
+    y = proc(xc, **pc)
+    (y * w.cuda()).sum().backward()
+    assert_close(y.detach().cpu(), y_ref, name)
+    _, gx64, gp64 = oracle_gradients(name, x, params, meta["kwargs"], w)
+    e_ref, e_ours = rel_l2(torch.from_numpy(extra["gx"]), gx64), rel_l2(xc.grad.cpu(), gx64)
+    assert e_ours <= max(TOL, 1.5 * e_ref), (name, "gx", e_ours, e_ref)
+    for k, g64 in gp64.items():
+        e_ref, e_ours = max_rel(torch.from_numpy(extra["g_" + k]), g64), max_rel(pc[k].grad.cpu(), g64)
+        assert pc[k].grad.shape == params[k].shape
+        assert e_ours <= max(2e-4, 1.5 * e_ref), (name, k, e_ours, e_ref)
+
+
+def test_backward_adjoint_identity_full_size():
+    """BASELINE-sized cascade: <w, H x> == <H^T w, x> (the dot-product test of an adjoint), and the coefficient
+    gradient against a central finite difference along one random direction."""
+    import grafx_b200.functional as F_
+
+    torch.manual_seed(5)
+    B, C, L, K = 32, 2, 131072, 5
+    x = torch.randn(B, C, L, device="cuda", requires_grad=True)
+    w = torch.randn(B, C, L, device="cuda")
+    Bs = (torch.tensor([1.0, 0.0, 0.0], device="cuda") + 0.1 * torch.randn(B, C, K, 3, device="cuda")).requires_grad_(True)
+    a1 = 1.6 * torch.rand(B, C, K, device="cuda") - 0.8
+    As = torch.stack([torch.ones_like(a1), a1, 0.3 + 0.3 * torch.rand_like(a1)], -1).requires_grad_(True)
+    y = F_.biquad_cascade(x, Bs, As)
+    loss = (y * w).sum()
+    loss.backward()
+    lhs, rhs = float(loss.detach()), float((x.grad.double() * x.detach().double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (lhs, rhs)
+    dB, dA = torch.randn_like(Bs), torch.randn_like(As)
+    dA[..., 0] = 0.0
+    eps = 1e-3
+    with torch.no_grad():
+        lp = (F_.biquad_cascade(x.detach(), Bs + eps * dB, As + eps * dA).double() * w.double()).sum()
+        lm = (F_.biquad_cascade(x.detach(), Bs - eps * dB, As - eps * dA).double() * w.double()).sum()
+    fd = float((lp - lm) / (2 * eps))
+    an = float((Bs.grad.double() * dB.double()).sum() + (As.grad.double() * dA.double()).sum())
+    assert abs(fd - an) <= 2e-2 * max(1.0, abs(an)), (fd, an)
+
+
+def test_backward_fir_sizes_vs_torch_autograd():
+    """Causal FIR convolution backward against autograd through a float64 FFT convolution, incl. the partitioned
+    (long-filter) engine and filters longer than the signal."""
+    import grafx_b200.functional as F_
+
+    for L, N in ((1000, 64), (5000, 1023), (3000, 5000), (40000, 20000)):
+        gen = torch.Generator().manual_seed(L + N)
+        x = torch.randn(2, 2, L, generator=gen)
+        h = torch.randn(2, 1, N, generator=gen) / N ** 0.5
+        w = torch.randn(2, 2, L, generator=gen)
+        xc, hc = x.cuda().requires_grad_(True), h.cuda().requires_grad_(True)
+        (F_.fir_conv(xc, hc, "causal") * w.cuda()).sum().backward()
+        x64, h64 = x.double().requires_grad_(True), h.double().requires_grad_(True)
+        n = L + N - 1
+        y64 = torch.fft.irfft(torch.fft.rfft(x64, n) * torch.fft.rfft(h64, n), n)[..., :L]
+        (y64 * w.double()).sum().backward()
+        assert rel_l2(xc.grad.cpu(), x64.grad) <= TOL, (L, N, "gx")
+        assert hc.grad.shape == h.shape
+        assert rel_l2(hc.grad.cpu(), h64.grad) <= TOL, (L, N, "gh")
+
+
+def test_ops_without_backward_fail_loudly_in_grad_mode():
+    """No silent graph cuts: forward-only kernels raise when autograd expects a gradient from them."""
+    import grafx_b200.processors as P
+
+    x = torch.randn(2, 2, 4096, device="cuda")
+    comp = P.Compressor().cuda()
+    prm = {k: torch.zeros(2, v, device="cuda", requires_grad=True) for k, v in comp.parameter_size().items()}
+    with pytest.raises(NotImplementedError):
+        comp(x, **prm)
+    with torch.no_grad():
+        assert comp(x, **prm).shape == x.shape
+    with pytest.raises(NotImplementedError):
+        P.StereoGain().cuda()(x, torch.zeros(2, 2, device="cuda", requires_grad=True))
+    with pytest.raises(NotImplementedError):  # zero-phase slice of the FIR engine: forward only
+        P.NewZeroPhaseFIREqualizer(num_frequency_bins=64).cuda()(x, torch.zeros(2, 1, 64, device="cuda", requires_grad=True))
 
 
 def test_design_kernel_matches_torch_statement():
