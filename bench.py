@@ -179,6 +179,22 @@ def tree_pin(obj):
     return {k: tree_pin(v) for k, v in obj.items()}
 
 
+def gpu_local_cpus(gpu_index):
+    """CPUs on the NUMA node of the GPU (NVML), or None: pinned staging buffers are allocated from a thread bound to
+    them, so that the copy engines do not cross the socket interconnect."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
 def tree_bytes(obj):
     if isinstance(obj, torch.Tensor):
         return obj.numel() * obj.element_size()
@@ -398,15 +414,23 @@ def main():
         # ---- end to end through the public nn.Module API with HOST buffers (pinned), copies inside
         e2e = None
         if not args.no_e2e:
-            xp, prm_p = x_h.pin_memory(), tree_pin(prm_h)
-            out_p = torch.empty((wl.B, 1 if wl.cls == "graph" else wl.C, wl.L) if wl.cls != "graph" else (wl.B, 1, wl.C, wl.L),
-                                dtype=torch.float32).pin_memory()
+            saved_affinity = os.sched_getaffinity(0)
+            local_cpus = gpu_local_cpus(local_rank)
+            if local_cpus:
+                os.sched_setaffinity(0, local_cpus)  # (this thread only: the CPU-baseline leg keeps every core)
+            try:
+                xp, prm_p = x_h.pin_memory(), tree_pin(prm_h)
+                out_p = torch.empty((wl.B, 1 if wl.cls == "graph" else wl.C, wl.L) if wl.cls != "graph" else (wl.B, 1, wl.C, wl.L),
+                                    dtype=torch.float32).pin_memory()
+                out_b = torch.empty_like(out_p).pin_memory()
+            finally:
+                os.sched_setaffinity(0, saved_affinity)
             nchunk = min(args.e2e_chunks, wl.B) if wl.B >= 8 else 1
             streams = [torch.cuda.Stream(device) for _ in range(min(args.e2e_streams, nchunk))]
             bounds = [(wl.B * i // nchunk, wl.B * (i + 1) // nchunk) for i in range(nchunk)]
             per_item_params = wl.cls != "graph"
 
-            out_bufs = [out_p, torch.empty_like(out_p).pin_memory()]
+            out_bufs = [out_p, out_b]
 
             def e2e_enqueue(k):
                 """Enqueues step k (H2D, forward, D2H of every chunk) and returns the events that mark its results

@@ -20,4 +20,10 @@ prof cfg3 fir_spectrum_kernel 2 hspec
 prof cfg3 fir_xspec_kernel 2 xspec
 prof cfg3 fir_mac_kernel 2 mac
 prof cfg3 fir_inv_kernel 2 inv
+timeout 120 python tools/backward_time.py 256 lfilter > gpurun_out/backward_time.log 2>&1
+timeout 120 python tools/backward_time.py 256 fsm >> gpurun_out/backward_time.log 2>&1
+timeout 120 python tools/captured_bench.py 8 1 32768 > gpurun_out/captured.log 2>&1
+timeout 120 python tools/captured_bench.py 32 1 131072 >> gpurun_out/captured.log 2>&1
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train_step.csv python tools/backward_time.py 256 lfilter > /dev/null 2>&1
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
 ls -la gpurun_out | tail -40
