@@ -1,0 +1,75 @@
+"""CPU: host-side logic around the kernels that needs no GPU -- the differentiable statement of the coefficient
+design used in training mode, argument validation of the newer C-ABI entry points, workspace sizing of the
+reverb geometries, the capture wrapper's refusal of CPU tensors."""
+import pytest
+import torch
+
+
+def test_design_statement_dispatch_matches_design_module_and_carries_grad():
+    from grafx_b200 import functional as F_
+    from grafx_b200.processors import design as D
+
+    torch.manual_seed(0)
+    w0, q, g = (torch.randn(3, 2, 4, requires_grad=True) for _ in range(3))
+    for shelf in (True, False):
+        for a, b in zip(F_.biquad_design("peq", w0, q, g, flags=int(shelf)), D.parametric_eq(w0, q, g, shelf)):
+            assert torch.equal(a, b) and a.requires_grad
+    for kind in ("peaking", "lowshelf", "highshelf"):
+        for a, b in zip(F_.biquad_design(kind, w0, q, g), D.eq_band(kind, w0, q, g)):
+            assert torch.equal(a, b)
+    for kind in ("lowpass", "highpass", "bandpass", "bandreject", "allpass"):
+        for a, b in zip(F_.biquad_design(kind, w0, q), D.simple_filter(kind, w0, q)):
+            assert torch.equal(a, b)
+    Bs = torch.randn(3, 4, 3, requires_grad=True)
+    a1, a2, a0 = (torch.randn(3, 4, requires_grad=True) for _ in range(3))
+    for a, b in zip(F_.biquad_design("stable", Bs, a1, a2, a0, flags=2), D.stable_biquad(Bs, a1, a2, a0, True)):
+        assert torch.equal(a, b)
+    for a, b in zip(F_.biquad_design("stable", Bs, a1, a2, None, flags=0), D.stable_biquad(Bs, a1, a2, None, False)):
+        assert torch.equal(a, b)
+    five = [torch.randn(3, 4, requires_grad=True) for _ in range(5)]
+    num, den = F_.biquad_design("svf", *five)
+    (num.sum() + den.sum()).backward()
+    assert all(t.grad is not None for t in five)
+
+
+def test_wants_grad_follows_autograd_state():
+    from grafx_b200 import functional as F_
+
+    t = torch.zeros(2, requires_grad=True)
+    assert F_._wants_grad(None, t)
+    assert not F_._wants_grad(t.detach(), None)
+    with torch.no_grad():
+        assert not F_._wants_grad(t)
+    with pytest.raises(NotImplementedError):
+        F_._no_backward("some_op", t)
+
+
+def test_new_entry_points_validate_arguments_without_gpu():
+    from grafx_b200 import _cabi
+
+    L = _cabi.lib()
+    assert L.gfx_node_copy_f32(None, None, 1, 1, 4, 4, 4, 4, 4, None) == -1
+    assert L.gfx_lag_dots_f32(None, None, None, None, None, 1, 4, 0, None) == -1
+    assert L.gfx_row_mean_square_f32(None, None, 1, 4, None) == -1
+    assert L.gfx_pointwise_f32(9, None, None, 1, 1, 4, None, None, None, None, None, 0, 0, None) == -1
+    # reverb workspace: tuned geometry, general power-of-two geometry, unsupported geometry
+    fast = L.gfx_reverb_ir_workspace_bytes(4, 384, 192, 96000)
+    general = L.gfx_reverb_ir_workspace_bytes(4, 512, 128, 96000)
+    assert 0 < fast < general
+    assert general >= 4 * 2 * (1 + 96000 // 128) * 512 * 4
+    assert L.gfx_reverb_ir_workspace_bytes(4, 300, 100, 96000) == 0
+    assert L.gfx_reverb_ir_workspace_bytes(4, 8192, 2048, 96000) == 0
+
+
+def test_captured_render_refuses_cpu_tensors():
+    from grafx_b200.render import CapturedRender, mixing_console_plan
+
+    with pytest.raises(RuntimeError):
+        CapturedRender({}, torch.zeros(1, 2, 2, 64), {}, mixing_console_plan(2, ["eq"]))
+
+
+def test_bench_gpu_affinity_helper_degrades_without_nvml():
+    import bench
+
+    cpus = bench.gpu_local_cpus(0)
+    assert cpus is None or len(cpus) > 0
