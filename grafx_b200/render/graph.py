@@ -4,7 +4,8 @@ tensor primitives of render/core.py (:6-140) folded in.
 Same signature and return value: `(output_signals, intermediates_list, signal_buffer)`; accepts
 3-D `[|V0|, C, L]` or 4-D `[B, |V0|, C, L]` sources and any RenderData-like plan (the reference's
 own objects work: only attributes are read).  Forward only: `parameters_grad` /
-`input_signal_grad` are accepted for compatibility; nothing is recorded for autograd.
+`input_signal_grad` are accepted for compatibility; nothing is recorded for autograd, and the call raises when
+autograd expects a gradient from it (tensors that require grad outside `torch.no_grad()`).
 
 What runs where: processors are the CUDA kernels of this package; node-axis aggregation
 (`sum` / `scatter`) is csrc/elementwise.cu:node_sum_kernel reading and writing slices of the
@@ -43,6 +44,16 @@ def _map_tensors(x, fn):
     return {k: _map_tensors(v, fn) for k, v in x.items()}
 
 
+def _any_requires_grad(x) -> bool:
+    if x is None:
+        return False
+    if isinstance(x, torch.Tensor):
+        return x.requires_grad
+    if isinstance(x, (list, tuple)):
+        return any(_any_requires_grad(v) for v in x)
+    return any(_any_requires_grad(v) for v in x.values())
+
+
 def _flatten2(x):
     return x.reshape(-1, *x.shape[2:])
 
@@ -69,6 +80,13 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
     node_dim = 0
     post = _flatten2 if ndim == 4 else (lambda t: t)
     batched = (lambda t: post(expand(t))) if ndim == 4 else (lambda t: t)
+    if torch.is_grad_enabled() and (input_signals.requires_grad or _any_requires_grad(per_type_parameters)
+                                    or _any_requires_grad(common_parameters)):
+        # the loop writes processor outputs into slices of one signal buffer in place: nothing is recorded for
+        # autograd, and saying so beats returning a result whose gradients are silently zero
+        raise NotImplementedError(
+            "render_grafx is forward-only here: call it under torch.no_grad() (or with detached tensors).  Gradients "
+            "exist at the processor level for the IIR family and FIRFilter (grafx_b200/autograd.py).")
     input_signals = input_signals.detach()
 
     # create_signal_buffer (render/core.py:6-33)

@@ -73,3 +73,14 @@ def test_bench_gpu_affinity_helper_degrades_without_nvml():
 
     cpus = bench.gpu_local_cpus(0)
     assert cpus is None or len(cpus) > 0
+
+
+def test_render_grafx_refuses_to_cut_the_autograd_graph():
+    from grafx_b200.render import mixing_console_plan, render_grafx
+
+    rd = mixing_console_plan(2, ["eq"])
+    prm = {"eq": {"w0": torch.zeros(2, 1, 3, requires_grad=True)}}
+    with pytest.raises(NotImplementedError):
+        render_grafx({}, torch.zeros(2, 2, 64), prm, rd)
+    with pytest.raises(NotImplementedError):
+        render_grafx({}, torch.zeros(2, 2, 64, requires_grad=True), {}, rd)
