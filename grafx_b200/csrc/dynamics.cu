@@ -109,11 +109,13 @@ struct DynCtx {
 // The ballistics variant (NT == 64) gives a whole ROW to one CTA, which walks its tiles in order: the recursion of a
 // row is one long dependent chain anyway, so nothing is gained by spreading its tiles over CTAs and a hand-over through
 // global memory (flag, fence, L1 invalidate: ~18 us per tile as measured) is saved.  The smoother states then live
-// in shared memory, double-buffered by tile parity.  The scan variant (NT == DYN_SCAN_NT) chains tiles across CTAs.
-// Threads per CTA of the scan variant and its CTAs per SM (80 registers).  Measured on B200, config 4 (two fused
-// stages, 1024 rows x 65536): 256 threads x 3 CTAs 0.211 ms, 128 x 6 0.193 ms -- the same warps per SM, but a block
-// barrier joins 4 warps instead of 8 and twice as many tiles of a row are in flight along the chain.
-constexpr int DYN_SCAN_NT = 128, DYN_SCAN_CTAS = 6;
+// in shared memory, double-buffered by tile parity.  The scan variant (NT == DYN_SCAN_NT or DYN_SCAN_NT_SMALL) chains tiles across CTAs.
+// Threads per CTA of the scan variant (80 registers: 3 CTAs of 256 threads or 6 of 128 per SM).  Measured on B200:
+// config 4 (two fused stages, 1024 rows x 65536) 256 threads 0.211 ms, 128 threads 0.193 ms -- the same warps per SM,
+// but a block barrier joins 4 warps instead of 8; config 5's compressor (512 rows x 2 x 131072) 0.204 ms vs 0.301 ms --
+// with fewer rows than resident CTAs the extra CTAs only queue up behind the tile chain of a row.  So: the small CTA
+// when every resident CTA can own a different row, the large one otherwise.
+constexpr int DYN_SCAN_NT = 256, DYN_SCAN_NT_SMALL = 128, DYN_SCAN_CTAS_SMALL = 6;
 template <int NT>
 __device__ __forceinline__ constexpr bool row_owner() { return NT == 64; }
 
@@ -454,7 +456,7 @@ __global__ void dynamics_tables_kernel(const DynParams p, float* __restrict__ ta
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? DYN_SCAN_CTAS : 8)) dynamics_kernel(const DynParams p) {
+__global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_NT_SMALL ? DYN_SCAN_CTAS_SMALL : 8))) dynamics_kernel(const DynParams p) {
     constexpr int S = 32, TILE = NT * S, NW = NT / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DynCtx<NT> cx;
@@ -733,7 +735,8 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
         o.post = SmootherDesc{s.gain_smoother, s.z_alpha_post, s.hist_post};
         any_ballistics |= (s.energy_smoother == 2 || s.gain_smoother == 2);
     }
-    const int NT = any_ballistics ? 64 : DYN_SCAN_NT;
+    const bool small_cta = batch >= device_info().sm_count * DYN_SCAN_CTAS_SMALL;
+    const int NT = any_ballistics ? 64 : (small_cta ? DYN_SCAN_NT_SMALL : DYN_SCAN_NT);
     const long long tile = (long long)NT * 32;
     const long long tiles_ll = (L + tile - 1) / tile;
     if ((long long)batch * tiles_ll > 0x7fff0000LL) return GFX_ERR_UNSUPPORTED;
@@ -753,7 +756,8 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
     GFX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256 + flags_bytes, (cudaStream_t)stream));
     p.tables = (float*)(w + dyn_tables_offset(batch, n_stages));
     cudaStream_t st = (cudaStream_t)stream;
-    return any_ballistics ? launch_dynamics<64>(p, st) : launch_dynamics<DYN_SCAN_NT>(p, st);
+    if (any_ballistics) return launch_dynamics<64>(p, st);
+    return small_cta ? launch_dynamics<DYN_SCAN_NT_SMALL>(p, st) : launch_dynamics<DYN_SCAN_NT>(p, st);
 }
 
 }  // extern "C"
