@@ -58,6 +58,10 @@ class BiquadCascadeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, nb, na):
         K = nb.shape[2]
+        if not (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+            # only dL/dx is wanted: no section signal is needed, forward and backward are one fused launch each
+            ctx.save_for_backward(nb, na)
+            return _cascade_raw(x, nb, na)
         sections = [x]
         for k in range(K):
             sections.append(_cascade_raw(sections[-1], nb[:, :, k:k + 1].contiguous(), na[:, :, k:k + 1].contiguous()))
@@ -70,6 +74,9 @@ class BiquadCascadeFn(torch.autograd.Function):
         nb, na, *sections = ctx.saved_tensors
         K = nb.shape[2]
         need_x, need_b, need_a = ctx.needs_input_grad
+        if not sections:
+            # the sections are LTI and commute: the adjoint of the whole cascade is the cascade on reversed time
+            return _cascade_raw(grad_y.detach().to(torch.float32).flip(-1).contiguous(), nb, na).flip(-1), None, None
         one = torch.zeros_like(nb[:, :, :1])
         one[..., 0] = 1.0
         r = grad_y.detach().to(torch.float32).flip(-1).contiguous()  # the gradient, time-reversed

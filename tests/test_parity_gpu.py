@@ -701,6 +701,29 @@ def test_backward_adjoint_identity_full_size():
     assert abs(fd - an) <= 2e-2 * max(1.0, abs(an)), (fd, an)
 
 
+def test_backward_signal_only_uses_the_fused_cascade():
+    """Only dL/dx wanted (parameters without grad): one fused launch each way; same gradient as the sectioned path."""
+    import grafx_b200.functional as F_
+
+    x, params, meta, _, extra = load("grad_peq_lfilter_stereo")
+    kw = {k: v for k, v in meta["kwargs"].items() if k != "cls"}
+    proc = build_processor("peq_lfilter_stereo", kw)
+    w = torch.from_numpy(extra["w"]).cuda()
+    xc = x.cuda().requires_grad_(True)
+    n0 = F_._cabi.lib().gfx_kernel_launch_count()
+    (proc(xc, **{k: v.cuda() for k, v in params.items()}) * w).sum().backward()
+    fused_launches = F_._cabi.lib().gfx_kernel_launch_count() - n0
+    _, gx64, _ = oracle_gradients("grad_peq_lfilter_stereo", x, params, meta["kwargs"], w.cpu())
+    e_ref = rel_l2(torch.from_numpy(extra["gx"]), gx64)
+    assert rel_l2(xc.grad.cpu(), gx64) <= max(TOL, 1.5 * e_ref)
+    xs = x.cuda().requires_grad_(True)
+    ps = {k: v.cuda().requires_grad_(True) for k, v in params.items()}
+    n0 = F_._cabi.lib().gfx_kernel_launch_count()
+    (proc(xs, **ps) * w).sum().backward()
+    assert F_._cabi.lib().gfx_kernel_launch_count() - n0 > fused_launches
+    assert rel_l2(xs.grad, xc.grad) <= 1e-5
+
+
 def test_backward_fir_sizes_vs_torch_autograd():
     """Causal FIR convolution backward against autograd through a float64 FFT convolution, incl. the partitioned
     (long-filter) engine and filters longer than the signal."""
