@@ -181,6 +181,50 @@ def test_cfg4_chain_fused_vs_oracle(smoother):
     assert_close(y_unfused.cpu(), y_ref, f"cfg4-unfused-{smoother}")
 
 
+@pytest.mark.parametrize("kind", ["compressor", "noisegate"])
+@pytest.mark.parametrize("knee", ["hard", "exponential"])
+@pytest.mark.parametrize("gain_smoother", ["iir", "ballistics"])
+@pytest.mark.parametrize("in_log", [False, True])
+def test_dynamics_knee_gain_smoother_grid_vs_oracle(kind, knee, gain_smoother, in_log):
+    """The reference fixtures pair the gain smoothers with the quadratic knee only; the hard and exponential
+    knees in their log-gain form (the branch taken whenever a gain smoother follows) against the oracle."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    gen = torch.Generator().manual_seed(len(kind) + 10 * len(knee) + 100 * len(gain_smoother) + 1000 * int(in_log))
+    B, L = 3, 9000
+    x = torch.randn(B, 2, L, generator=gen) * torch.tensor([0.05, 0.3, 1.0])[:, None, None]
+    kw = dict(energy_smoother="iir", gain_smoother=gain_smoother, gain_smooth_in_log=in_log, knee=knee, iir_len=512)
+    proc = (P.Compressor if kind == "compressor" else P.NoiseGate)(**kw).cuda()
+    prm = _dyn_params(proc, B, gen)
+    prm["log_threshold"] = prm["log_threshold"] - 2.0
+    y = proc(x.cuda(), **{k: v.cuda() for k, v in prm.items()}).cpu()
+    assert_close(y, O.dynamics(kind, x, **prm, **kw), f"{kind}-{knee}-{gain_smoother}-{in_log}")
+
+
+def test_dynamics_three_channels_and_long_cascade_vs_oracle():
+    """Shapes outside the BASELINE configs: a 3-channel compressor (energy = mean over 3 rows) and a 48-section
+    cascade (section tables of one row no longer fit the small-K fast paths)."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.functional as F_
+    import grafx_b200.processors as P
+
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(4, 3, 20000, generator=gen)
+    proc = P.Compressor(iir_len=2048).cuda()
+    prm = _dyn_params(proc, 4, gen)
+    y = proc(x.cuda(), **{k: v.cuda() for k, v in prm.items()}).cpu()
+    assert_close(y, O.compressor(x, **prm, iir_len=2048), "compressor-3ch")
+    K = 48
+    xb = torch.randn(2, 1, 30000, generator=gen)
+    Bs = torch.tensor([1.0, 0.0, 0.0]) + 0.05 * torch.randn(2, 1, K, 3, generator=gen)
+    a1 = 1.2 * torch.rand(2, 1, K, generator=gen) - 0.6
+    As = torch.stack([torch.ones_like(a1), a1, 0.2 + 0.3 * torch.rand(2, 1, K, generator=gen)], -1)
+    yk = F_.biquad_cascade(xb.cuda(), Bs.cuda(), As.cuda()).cpu()
+    y64 = O.iir_lfilter(xb.double(), Bs.double(), As.double(), use_torchaudio=False)
+    assert rel_l2(yk, y64) <= TOL
+
+
 def test_dynamics_slow_pole_long_signal():
     """Truncation tail a^N that does matter (alpha ~ 0.9975, N = 1024) across many tiles, stereo,
     with an iir gain smoother (history-buffer path) -- vs the oracle's FFT convolution."""
