@@ -565,7 +565,20 @@ __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_ols_kernel(c
 // registers, so every spectrum is read exactly once.  accumulate != 0 adds to Ys (filters with more than
 // MAC_MAX_PC partitions are processed in groups).
 constexpr int MAC_MAX_PC = 12;
-constexpr int MAC_NT = 256;
+// CTA shape of the MAC kernel: (threads, min CTAs per SM, loads issued together).  The kernel is HBM-bound, so what
+// matters is bytes in flight per SM and no spills.  Measured on B200, config 3 step: (256, 2, 4) 2.446 ms (128
+// registers, 104 B of spills) | (256, 1, 12) 2.603 | (128, 3, 6) 2.450 | (128, 2, 12) 2.550 | (64, 5, 12) 2.386 ms (160
+// registers, no spills, 61 KB of loads in flight per SM).
+#ifndef GFX_MAC_NT
+#define GFX_MAC_NT 64
+#endif
+#ifndef GFX_MAC_MINB
+#define GFX_MAC_MINB 5
+#endif
+#ifndef GFX_MAC_G
+#define GFX_MAC_G 12
+#endif
+constexpr int MAC_NT = GFX_MAC_NT;
 
 __device__ __forceinline__ void cmac4(float4& acc, const float4& x, const float4& h) {
     acc.x = fmaf(x.x, h.x, acc.x); acc.x = fmaf(-x.y, h.y, acc.x);
@@ -575,7 +588,7 @@ __device__ __forceinline__ void cmac4(float4& acc, const float4& x, const float4
 }
 
 template <int PC>
-__global__ void __launch_bounds__(MAC_NT, 2) fir_mac_kernel(const float4* __restrict__ Xs, const float4* __restrict__ Hs,
+__global__ void __launch_bounds__(MAC_NT, GFX_MAC_MINB) fir_mac_kernel(const float4* __restrict__ Xs, const float4* __restrict__ Hs,
                                                             float4* __restrict__ Ys, RowMap rm, int xrow0, int hrow0,
                                                             int row0, int P, int p0, int nblk, int half, int accumulate) {
     const int q = blockIdx.x * MAC_NT + threadIdx.x;
@@ -596,7 +609,7 @@ __global__ void __launch_bounds__(MAC_NT, 2) fir_mac_kernel(const float4* __rest
 #pragma unroll
         for (int p = 0; p < PC; ++p) { h[p].x = 0.f; h[p].y = 0.f; }
     }
-    constexpr int G = PC < 4 ? PC : 4;  // loads issued together
+    constexpr int G = PC < GFX_MAC_G ? PC : ((PC % GFX_MAC_G == 0) ? GFX_MAC_G : (PC < 4 ? PC : 4));  // loads issued together
     const int last = nblk - 1 - p0;     // last valid input block index for this partition group
 #pragma unroll 1
     for (int j0 = p0; j0 < nblk; j0 += PC) {
