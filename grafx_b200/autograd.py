@@ -153,3 +153,61 @@ def fir_conv_autograd(x: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
     ch, N = h.shape[1], h.shape[2]
     c = max(cx, ch)
     return FirConvCausalFn.apply(x.to(torch.float32).expand(B, c, L).contiguous(), h.to(torch.float32).expand(B, c, N).contiguous())
+
+
+# ---------------------------------------------------------------------------------------------- gains and mixes
+def _pointwise_raw(op, x, p0):
+    from . import functional as F_
+
+    with torch.no_grad():
+        return F_.pointwise(op, x, p0)
+
+
+class GainFn(torch.autograd.Function):
+    """y[b, c] = x[b, c] * exp(log_gain[b, c])  (StereoGain.forward, processors/stereo.py:31-38).
+    dL/dx is the same kernel on the gradient; dL/dlog_gain[b, c] = sum_t g y (a lag-0 inner product per row)."""
+
+    @staticmethod
+    def forward(ctx, x, log_gain):
+        y = _pointwise_raw("gain", x, log_gain)
+        ctx.save_for_backward(log_gain, y)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_y):
+        log_gain, y = ctx.saved_tensors
+        g = grad_y.detach().to(torch.float32).contiguous()
+        gx = _pointwise_raw("gain", g, log_gain) if ctx.needs_input_grad[0] else None
+        glg = _lag_dots(g, y, None, False)[0][..., 0].reshape(log_gain.shape) if ctx.needs_input_grad[1] else None
+        return gx, glg
+
+
+class DryWetFn(torch.autograd.Function):
+    """y = w wet + (1 - w) dry with one weight per batch item (DryWet.forward, processors/container.py:62-67)."""
+
+    @staticmethod
+    def forward(ctx, dry, wet, w):
+        from . import functional as F_
+
+        with torch.no_grad():
+            y = F_.drywet_mix(dry, wet, w)
+        ctx.save_for_backward(dry, wet, w)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_y):
+        dry, wet, w = ctx.saved_tensors
+        g = grad_y.detach().to(torch.float32).contiguous()
+        B = g.shape[0]
+        wv = w.detach().to(torch.float32).reshape(B).contiguous()
+        need_dry, need_wet, need_w = ctx.needs_input_grad
+        g_dry = _pointwise_raw("scale_add", g, 1.0 - wv) if need_dry else None
+        g_wet = _pointwise_raw("scale_add", g, wv) if need_wet else None
+        g_w = None
+        if need_w:
+            flat = lambda t: t.reshape(B, 1, -1)  # noqa: E731
+            d_wet, d_dry = _lag_dots(flat(g), flat(wet), flat(dry), False)
+            g_w = (d_wet[..., 0] - d_dry[..., 0]).reshape(w.shape)
+        return g_dry, g_wet, g_w

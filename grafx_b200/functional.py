@@ -76,7 +76,7 @@ def _no_backward(name: str, *tensors):
     if _wants_grad(*tensors):
         raise NotImplementedError(
             f"{name} has no backward pass yet (forward-only CUDA kernel); wrap the call in torch.no_grad() or detach "
-            "its inputs.  Differentiable so far: the biquad cascade (IIR family with backend lfilter / ssm).")
+            "its inputs.  Differentiable so far: the IIR family, the causal FIR convolution, StereoGain, the DryWet mix.")
 
 
 def _prep(t: torch.Tensor, dtype=None) -> torch.Tensor:
@@ -301,7 +301,10 @@ def dynamics_chain(x: torch.Tensor, stages: list[dict], iir_len: int = 16384) ->
 def drywet_mix(dry: torch.Tensor, wet: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     """y = w * wet + (1 - w) * dry, w per batch item used as given (container.py:62-67)."""
     _cabi.require_cuda(dry, wet, weight)
-    _no_backward("drywet_mix", dry, wet, weight)
+    if _wants_grad(dry, wet, weight):
+        from .autograd import DryWetFn
+
+        return DryWetFn.apply(dry.to(torch.float32).contiguous(), wet.to(torch.float32).contiguous(), weight)
     assert dry.shape == wet.shape
     dry, wet = _prep(dry, torch.float32), _prep(wet, torch.float32)
     w = _prep(weight, torch.float32).reshape(-1)
@@ -527,6 +530,10 @@ def pointwise(op: str, x: torch.Tensor, p0=None, p1=None, p2=None, p3=None, dc=N
     """Sample-wise processors (stereo.py, nonlinear.py, the ParallelMix accumulation) in one pass; see
     gfx_pointwise_f32 in include/grafx_b200.h for the parameter meaning of every op."""
     _cabi.require_cuda(x, *[t for t in (p0, p1, p2, p3, dc) if t is not None])
+    if op == "gain" and out is None and dc is None and _wants_grad(x, p0):
+        from .autograd import GainFn
+
+        return GainFn.apply(x.to(torch.float32).contiguous(), p0.to(torch.float32).contiguous())
     _no_backward("pointwise", x, p0, p1, p2, p3, dc)
     assert x.ndim == 3
     x = _prep(x, torch.float32)

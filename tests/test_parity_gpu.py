@@ -789,6 +789,27 @@ def test_backward_fir_sizes_vs_torch_autograd():
         assert rel_l2(hc.grad.cpu(), h64.grad) <= TOL, (L, N, "gh")
 
 
+def test_backward_gain_and_drywet_vs_torch_autograd():
+    """StereoGain and the DryWet mix: gradients from the kernels (pointwise passes + lag-0 inner products) against
+    float64 autograd of the formulas (stereo.py:31-38, container.py:62-67)."""
+    import grafx_b200.processors as P
+
+    torch.manual_seed(8)
+    for L in (4096, 3001):
+        x = torch.randn(3, 2, L)
+        lg, wt, w = 0.3 * torch.randn(3, 2), torch.rand(3, 1), torch.randn(3, 2, L)
+        xc, lgc, wc = (t.cuda().requires_grad_(True) for t in (x, lg, wt))
+        proc = P.DryWet(P.StereoGain()).cuda()
+        (proc(xc, wc, log_gain=lgc) * w.cuda()).sum().backward()
+        x64, lg64, w64 = (t.double().requires_grad_(True) for t in (x, lg, wt))
+        wet = x64 * lg64.exp()[..., None]
+        y64 = w64[..., None] * wet + (1 - w64[..., None]) * x64
+        (y64 * w.double()).sum().backward()
+        assert rel_l2(xc.grad.cpu(), x64.grad) <= 1e-5
+        assert max_rel(lgc.grad.cpu(), lg64.grad) <= 1e-4 and lgc.grad.shape == lg.shape
+        assert max_rel(wc.grad.cpu(), w64.grad) <= 1e-4 and wc.grad.shape == wt.shape
+
+
 def test_ops_without_backward_fail_loudly_in_grad_mode():
     """No silent graph cuts: forward-only kernels raise when autograd expects a gradient from them."""
     import grafx_b200.processors as P
@@ -801,7 +822,7 @@ def test_ops_without_backward_fail_loudly_in_grad_mode():
     with torch.no_grad():
         assert comp(x, **prm).shape == x.shape
     with pytest.raises(NotImplementedError):
-        P.StereoGain().cuda()(x, torch.zeros(2, 2, device="cuda", requires_grad=True))
+        P.SideGainImager().cuda()(x, torch.zeros(2, 1, device="cuda", requires_grad=True))
     with pytest.raises(NotImplementedError):  # zero-phase slice of the FIR engine: forward only
         P.NewZeroPhaseFIREqualizer(num_frequency_bins=64).cuda()(x, torch.zeros(2, 1, 64, device="cuda", requires_grad=True))
 
