@@ -1,19 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the grafx hot path on B200 (contract: see README / DESIGN.md section 6).
+"""bench.py -- throughput of the grafx hot path on B200 (contract: DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg3b|cfg4|cfg4b|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5|cfg1|cfg2|cfg2lf|cfg3|cfg3b|cfg4|cfg4b]
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
 
-A step = one pass of the hot path over one batch of synthetic 48 kHz audio.  Default workload =
-BASELINE.json configs[1]: ParametricEqualizer, 5 biquads, stereo, batch 256, 131072 samples
-(backend "lfilter": the exact cascade).  Under torchrun (N > 1) every rank processes its own
-batch of the same size (weak scaling; the path shards over the batch axis with no collective).
+Default workload = BASELINE.json configs[4], the configuration the multi-GPU metric is quoted on: the 32-track mixing
+graph (in -> ParametricEqualizer -> Compressor -> STFTMaskedNoiseReverb -> out bus), batch 128, 2 ch x 131072 samples.
+The batch of renders is SHARDED over the ranks (128 / N renders per GPU, rendered in chunks of 16 through
+CUDA-graph-captured `render_grafx` plans), the mixes are all-gathered over NCCL (asynchronously, overlapping the next
+step) -> `scaling: "strong"`.  At N = 1 the same JSON line also carries `per_config`: one sub-record per other
+BASELINE config (cfg1 .. cfg4b) with its own roofline and CPU baseline.  A step = one pass over the whole batch.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -25,48 +28,46 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-L2_BYTES = 126 * 2**20
+METRIC = "audio samples/sec (batch x chan x len)"
+FMA_PER_CONV_SAMPLE = None
 
 
 # --------------------------------------------------------------------------- workloads
 class Workload:
-    """name, per-GPU shapes, parameter factory and the module(s) under test."""
+    """One processor configuration of BASELINE.json: per-GPU shapes, parameter factory, the module under test,
+    algorithmic bytes / flops per step and the oracle call of the CPU arm."""
 
-    def __init__(self, name, batch_div=1):
+    def __init__(self, name):
         self.name = name
-        g = torch.Generator().manual_seed(0)
-        self.gen = g
-        if name == "cfg2":
-            self.B, self.C, self.L = 256 // batch_div, 2, 131072
-            self.desc = "ParametricEqualizer(num_filters=5, stereo, backend=lfilter) batch=256 x 2ch x 131072"
-            self.kw = dict(num_filters=5, processor_channel="stereo", backend="lfilter", flashfftconv=False)
-            self.cls = "ParametricEqualizer"
-            self.param_shapes = {k: (2, 5) for k in ("w0", "q_inv", "log_gain")}
+        self.gen = torch.Generator().manual_seed(0)
+        self.cls = None
+        if name == "cfg1":
+            self.B, self.C, self.L = 1, 2, 48000
+            self.desc = "BiquadFilter(num_filters=1, backend=lfilter) 1 x 2ch x 48000 (the reference's CPU-runnable case)"
+            self.cls, self.kw = "BiquadFilter", dict(num_filters=1, backend="lfilter", flashfftconv=False)
+            self.flops_per_sample = 10.0
+        elif name in ("cfg2", "cfg2lf"):
+            self.B, self.C, self.L = 256, 2, 131072
+            lf = " with every band below 2 kHz (double-precision carry path)" if name == "cfg2lf" else ""
+            self.desc = f"ParametricEqualizer(num_filters=5, stereo, backend=lfilter) batch=256 x 2ch x 131072{lf}"
+            self.cls, self.kw = "ParametricEqualizer", dict(num_filters=5, processor_channel="stereo", backend="lfilter", flashfftconv=False)
+            self.flops_per_sample = 10.0 * 5
         elif name == "cfg3":
-            self.B, self.C, self.L = 512 // batch_div, 2, 131072
+            self.B, self.C, self.L = 512, 2, 131072
             self.desc = "STFTMaskedNoiseReverb(ir_len=96000) batch=512 x 2ch x 131072"
-            self.kw = dict(ir_len=96000, flashfftconv=False)
-            self.cls = "STFTMaskedNoiseReverb"
-            self.param_shapes = {"init_log_magnitude": (2, 193), "delta_log_magnitude": (2, 193)}
+            self.cls, self.kw = "STFTMaskedNoiseReverb", dict(ir_len=96000, flashfftconv=False)
+            self.flops_per_sample = 8 * math.log2(16384) + 8 * 96000 / 8192
         elif name == "cfg3b":
-            self.B, self.C, self.L = 512 // batch_div, 2, 131072
+            self.B, self.C, self.L = 512, 2, 131072
             self.desc = "FIRFilter(fir_len=1023, stereo) batch=512 x 2ch x 131072"
-            self.kw = dict(fir_len=1023, processor_channel="stereo")
-            self.cls = "FIRFilter"
-            self.param_shapes = {"fir": (2, 1023)}
+            self.cls, self.kw = "FIRFilter", dict(fir_len=1023, processor_channel="stereo")
+            self.flops_per_sample = 8 * math.log2(8192) + 8 * 1023 / (8192 - 1024)
         elif name in ("cfg4", "cfg4b"):
-            self.B, self.C, self.L = 1024 // batch_div, 1, 65536
-            sm = "iir" if name == "cfg4" else "ballistics"
-            self.desc = f"SerialChain(Compressor({sm}) -> NoiseGate({sm})) fused, batch=1024 x 1ch x 65536"
-            self.kw = dict(energy_smoother=sm, flashfftconv=False)
-            self.cls = "chain"
-            n = 1 if sm == "iir" else 2
-            self.param_shapes = {"log_threshold": (1,), "log_ratio": (1,), "log_knee": (1,), "z_alpha_pre": (n,)}
-        elif name == "cfg5":
-            self.B, self.C, self.L = 16 // batch_div if batch_div <= 16 else 1, 2, 131072
-            self.tracks = 32
-            self.desc = "mixing graph 32 x (in->eq->compressor->reverb) -> out, batch=16 per GPU (128 over 8), 2ch x 131072"
-            self.cls = "graph"
+            self.B, self.C, self.L = 1024, 1, 65536
+            self.sm = "iir" if name == "cfg4" else "ballistics"
+            self.desc = f"SerialChain(Compressor({self.sm}) -> NoiseGate({self.sm})) fused, batch=1024 x 1ch x 65536"
+            self.cls, self.kw = "chain", dict(energy_smoother=self.sm, flashfftconv=False)
+            self.flops_per_sample = 30.0 * 2
         else:
             raise SystemExit(f"unknown workload {name}")
 
@@ -76,95 +77,190 @@ class Workload:
 
         if self.cls == "chain":
             self.mod = P.SerialChain({"comp": P.Compressor(**self.kw), "gate": P.NoiseGate(**self.kw)}).to(device)
-        elif self.cls == "graph":
-            from grafx_b200.render import mixing_console_plan
-
-            self.procs = {"eq": P.ParametricEqualizer(num_filters=5, processor_channel="stereo", backend="lfilter").to(device),
-                          "compressor": P.Compressor().to(device),
-                          "reverb": P.STFTMaskedNoiseReverb(ir_len=96000).to(device)}
-            self.plan = mixing_console_plan(self.tracks, ["eq", "compressor", "reverb"])
         else:
             self.mod = getattr(P, self.cls)(**self.kw).to(device)
 
-    def host_inputs(self, pin=False):
-        if self.cls == "graph":
-            x = torch.randn(self.B, self.tracks, self.C, self.L, generator=self.gen)
-            prm = {t: {k: 0.3 * torch.randn(self.tracks, *((v,) if isinstance(v, int) else v), generator=self.gen)
-                       for k, v in p.parameter_size().items()} for t, p in self.procs.items()}
-        else:
-            x = torch.randn(self.B, self.C, self.L, generator=self.gen)
-            if self.cls == "chain":
-                prm = {n: {k: torch.randn(self.B, *s, generator=self.gen) for k, s in self.param_shapes.items()} for n in ("comp", "gate")}
-            else:
-                prm = {k: torch.randn(self.B, *s, generator=self.gen) for k, s in self.param_shapes.items()}
-        if pin:
-            x = x.pin_memory()
+    def param_shapes(self):
+        if self.cls == "chain":
+            n = 1 if self.sm == "iir" else 2
+            one = {"log_threshold": (1,), "log_ratio": (1,), "log_knee": (1,), "z_alpha_pre": (n,)}
+            return {"comp": one, "gate": one}
+        if self.name == "cfg1":
+            return {"Bs": (1, 3), "A1_pre": (1,), "A2_pre": (1,)}
+        if self.name in ("cfg2", "cfg2lf"):
+            return {k: (2, 5) for k in ("w0", "q_inv", "log_gain")}
+        if self.name == "cfg3":
+            return {"init_log_magnitude": (2, 193), "delta_log_magnitude": (2, 193)}
+        return {"fir": (2, 1023)}
+
+    def host_inputs(self, B=None):
+        B = self.B if B is None else B
+        x = torch.randn(B, self.C, self.L, generator=self.gen)
+
+        def draw(shapes):
+            return {k: (draw(s) if isinstance(s, dict) else torch.randn(B, *s, generator=self.gen)) for k, s in shapes.items()}
+
+        prm = draw(self.param_shapes())
+        if self.name == "cfg2lf":
+            # w0 = pi * sigmoid(p): p <= -2.4 puts every band below 2 kHz at 48 kHz (down to a few tens of Hz)
+            prm["w0"] = -2.4 - 1.5 * torch.rand(B, 2, 5, generator=self.gen) ** 2 * 3.0
         return x, prm
 
     def forward(self, x, prm):
-        if self.cls == "graph":
-            from grafx_b200.render import render_grafx
-
-            return render_grafx(self.procs, x, prm, self.plan, parameters_grad=False)[0]
-        if self.cls == "chain":
-            return self.mod(x, **prm)[0]
-        return self.mod(x, **prm)
+        out = self.mod(x, **prm)
+        return out[0] if isinstance(out, tuple) else out
 
     def dominant_call(self, x, prm):
-        """(callable, kernel name(s), algorithmic bytes per call) of the O(samples) kernel(s) of the workload,
-        without the parameter-side statement around them.  Algorithmic bytes: SURVEY.md section 8(d)."""
+        """(callable, kernel name) of the O(samples) kernel(s) without the parameter-side statement around them."""
         import grafx_b200.functional as F_
         from grafx_b200.processors import design
 
-        n = self.B * self.C * self.L
-        if self.name == "cfg2":
+        if self.name in ("cfg2", "cfg2lf"):
             Bs, As = design.parametric_eq(prm["w0"], prm["q_inv"], prm["log_gain"])
-            return (lambda: F_.biquad_cascade(x, Bs, As)), "biquad_cascade_x2_kernel<4,0> (+ cascade_tables_kernel)", 8 * n
+            return (lambda: F_.biquad_cascade(x, Bs, As)), "biquad_cascade_x2_kernel (+ cascade_x2_tables_kernel)"
         if self.name == "cfg3":
-            return (lambda: self.mod(x, **prm)), \
-                "reverb pipeline: reverb_ir + fir_spectrum<8192> + fir_xspec<8192> + fir_mac<12> + fir_inv<8192>", 8 * n
+            return (lambda: self.mod(x, **prm)), "reverb pipeline: reverb_ir + filter spectra + partitioned overlap-save (fir.cu)"
         if self.name == "cfg3b":
             h = F_.normalize_impulse(torch.tanh(prm["fir"]))
-            return (lambda: F_.fir_conv(x, h)), "fir_ols_kernel<4096,256> (+ fir_spectrum_kernel)", 8 * n + 4 * h.numel()
-        if self.name in ("cfg4", "cfg4b"):
-            return (lambda: self.mod(x, **prm)), "dynamics_kernel (Compressor -> NoiseGate fused, one launch)", 8 * n
-        if self.name == "cfg5":
-            # contract-preserving render (signal buffer returned): 129 node signals written, 160 read
-            return (lambda: self.forward(x, prm)), "render_grafx: 5 orders (copy, cascade, dynamics, reverb pipeline, node_sum)", \
-                289 * self.B * self.C * self.L * 4
-        raise SystemExit(self.name)
+            return (lambda: F_.fir_conv(x, h)), "fir_ols_kernel<4096> (+ fir_spectrum_kernel)"
+        if self.name == "cfg1":
+            return (lambda: self.forward(x, prm)), "biquad_cascade_x2_kernel (+ design, tables)"
+        return (lambda: self.forward(x, prm)), "dynamics_kernel (Compressor -> NoiseGate fused, one launch)"
 
-    def samples(self):
-        if self.cls == "graph":
-            return self.B * self.C * self.L       # rendered output samples per graph render
-        return self.B * self.C * self.L
+    def alg_bytes(self):
+        n = self.B * self.C * self.L
+        return 8 * n + (4 * self.B * 2 * 1023 if self.name == "cfg3b" else 0)
 
-    # ---- reference arm: the oracle port on the host CPU (torch CPU ops + torchaudio lfilter,
-    # the same library calls the reference makes)
+    def samples(self, B=None):
+        return (self.B if B is None else B) * self.C * self.L
+
+    # ---- CPU arm: the oracle port (torch CPU ops + torchaudio lfilter, the library calls the reference makes)
     def cpu_forward(self, x, prm):
         from oracle import grafx_oracle as O
 
-        if self.name == "cfg2":
+        if self.name == "cfg1":
+            return O.biquad_filter(x, **prm, backend="lfilter")
+        if self.name in ("cfg2", "cfg2lf"):
             return O.parametric_equalizer(x, **prm, processor_channel="stereo", backend="lfilter")
         if self.name == "cfg3":
             return O.stft_masked_noise_reverb(x, **prm, ir_len=96000)
         if self.name == "cfg3b":
             return O.fir_filter(x, prm["fir"], "stereo")
-        if self.name in ("cfg4", "cfg4b"):
-            sm = "iir" if self.name == "cfg4" else "ballistics"
-            return O.noisegate(O.compressor(x, **prm["comp"], energy_smoother=sm), **prm["gate"], energy_smoother=sm)
-        if self.name == "cfg5":
-            procs = {"eq": lambda s, **p: O.parametric_equalizer(s, **p, processor_channel="stereo", backend="lfilter"),
-                     "compressor": lambda s, **p: O.compressor(s, **p),
-                     "reverb": lambda s, **p: O.stft_masked_noise_reverb(s, **p, ir_len=96000)}
-            T = self.tracks
-            plan = {"num_nodes": 4 * T + 1, "iters": [None] + [
-                {"type": t, "reads": [("slice", (i * T, (i + 1) * T))], "aggs": [("none", None)], "param": ("slice", (0, T)),
-                 "write": ("slice", ((i + 1) * T, (i + 2) * T))} for i, t in enumerate(["eq", "compressor", "reverb"])] + [
-                {"type": "out", "reads": [("slice", (3 * T, 4 * T))], "aggs": [("sum", None)], "param": ("slice", (0, 1)),
-                 "write": ("slice", (4 * T, 4 * T + 1))}]}
-            return O.render_plan(procs, x, prm, plan)[0]
-        raise SystemExit(self.name)
+        return O.noisegate(O.compressor(x, **prm["comp"], energy_smoother=self.sm), **prm["gate"], energy_smoother=self.sm)
+
+    def cpu_sample_batch(self):
+        """Batch of the bounded CPU sample (a few hundred ms to a few s of host work per call)."""
+        return {"cfg1": 1, "cfg2": 32, "cfg2lf": 32, "cfg3": 8, "cfg3b": 16, "cfg4": 64, "cfg4b": 16}[self.name]
+
+
+class GraphWorkload:
+    """BASELINE config 5: 32 x (in -> eq -> compressor -> reverb) -> out, batch 128 sharded over the ranks."""
+
+    name = "cfg5"
+    TOTAL, CHUNK, TRACKS, C, L = 128, 16, 32, 2, 131072
+
+    def __init__(self, world=1, rank=0):
+        self.world, self.rank = world, rank
+        assert self.TOTAL % (self.CHUNK * world) == 0 or self.TOTAL // world < self.CHUNK, "128 renders split evenly over 1/2/4/8 ranks"
+        self.B_local = self.TOTAL // world
+        self.chunk = min(self.CHUNK, self.B_local)
+        self.n_chunks = self.B_local // self.chunk
+        self.desc = ("mixing graph 32 x (in -> ParametricEqualizer(5, stereo, lfilter) -> Compressor -> STFTMaskedNoiseReverb(96000)) "
+                     "-> out, batch=128 renders x 2ch x 131072")
+        # per node-sample: cascade 10 K + dynamics 30 + reverb (FFT overlap-save) ; + 1 add per track at the bus
+        self.flops_per_out_sample = self.TRACKS * (50.0 + 30.0 + 8 * math.log2(16384) + 8 * 96000 / 8192 + 1.0)
+
+    def build(self, device):
+        import grafx_b200.processors as P
+        from grafx_b200.render import mixing_console_plan
+
+        self.device = device
+        self.procs = {"eq": P.ParametricEqualizer(num_filters=5, processor_channel="stereo", backend="lfilter").to(device),
+                      "compressor": P.Compressor().to(device), "reverb": P.STFTMaskedNoiseReverb(ir_len=96000).to(device)}
+        self.plan = mixing_console_plan(self.TRACKS, ["eq", "compressor", "reverb"])
+
+    def host_params(self, procs=None):
+        g = torch.Generator().manual_seed(0)
+        procs = procs or self.procs
+        return {t: {k: 0.3 * torch.randn(self.TRACKS, *((v,) if isinstance(v, int) else v), generator=g)
+                    for k, v in p.parameter_size().items()} for t, p in procs.items()}
+
+    def capture(self):
+        """One CUDA-graph-captured render plan per chunk of 16 renders; the chunk's sources are the capture's static
+        input tensor (filled on the device: inputs are HBM-resident when the timed region starts)."""
+        from grafx_b200.render import CapturedRender
+
+        self.prm = tree_to(self.host_params(), self.device)
+        g = torch.Generator(device=self.device).manual_seed(1000 + self.rank)
+        self.caps = []
+        for _ in range(self.n_chunks):
+            x = torch.randn(self.chunk, self.TRACKS, self.C, self.L, device=self.device, generator=g)
+            self.caps.append(CapturedRender(self.procs, x, self.prm, self.plan))
+            del x
+        # mixes of this rank, double-buffered (the gather of step k reads one while step k+1 fills the other)
+        self.mix = [torch.empty(self.B_local, 1, self.C, self.L, device=self.device) for _ in range(2)]
+        self.gathered = [torch.empty(self.TOTAL, 1, self.C, self.L, device=self.device) for _ in range(2)] if self.world > 1 else None
+        self.pending = None
+        self.k = 0
+
+    def step(self):
+        """Renders this rank's 128 / N items and starts the all-gather of the mixes (N > 1)."""
+        import torch.distributed as dist
+
+        mix = self.mix[self.k & 1]
+        for i, cap in enumerate(self.caps):
+            out, _, _ = cap()
+            mix[i * self.chunk:(i + 1) * self.chunk].copy_(out)
+        if self.world > 1:
+            if self.pending is not None:
+                self.pending.wait()
+            self.pending = dist.all_gather_into_tensor(self.gathered[self.k & 1], mix, async_op=True)
+        self.k += 1
+        return mix
+
+    def finish(self):
+        if self.pending is not None:
+            self.pending.wait()
+            self.pending = None
+
+    def samples(self):
+        return self.TOTAL * self.C * self.L      # rendered output samples per step (whole job)
+
+    def alg_bytes_local(self):
+        # contract-preserving render (signal buffer returned): 129 node signals written, 160 read (SURVEY.md 8(d))
+        return 289 * self.B_local * self.C * self.L * 4
+
+    def cpu_forward(self, x, prm):
+        from oracle import grafx_oracle as O
+
+        procs = {"eq": lambda s, **p: O.parametric_equalizer(s, **p, processor_channel="stereo", backend="lfilter"),
+                 "compressor": lambda s, **p: O.compressor(s, **p),
+                 "reverb": lambda s, **p: O.stft_masked_noise_reverb(s, **p, ir_len=96000)}
+        T = self.TRACKS
+        plan = {"num_nodes": 4 * T + 1, "iters": [None] + [
+            {"type": t, "reads": [("slice", (i * T, (i + 1) * T))], "aggs": [("none", None)], "param": ("slice", (0, T)),
+             "write": ("slice", ((i + 1) * T, (i + 2) * T))} for i, t in enumerate(["eq", "compressor", "reverb"])] + [
+            {"type": "out", "reads": [("slice", (3 * T, 4 * T))], "aggs": [("sum", None)], "param": ("slice", (0, 1)),
+             "write": ("slice", (4 * T, 4 * T + 1))}]}
+        return O.render_plan(procs, x, prm, plan)[0]
+
+
+def config_of(name, world=1):
+    """The `config` object of the JSON line -- the SAME dictionary in both arms (the reference arm runs a bounded
+    sample of exactly this configuration; what the sample was is said in its `cpu_baseline.sample`)."""
+    if name == "cfg5":
+        g = GraphWorkload(world)
+        return {"workload": g.desc, "batch": 128, "tracks": 32, "channels": 2, "length": 131072,
+                "renders_per_gpu": g.B_local, "chunks_per_gpu": g.n_chunks,
+                "l2": "inputs larger than L2: each chunk of 16 renders reads 537 MB of sources and fills a 2.16 GB signal buffer (126 MiB L2)",
+                "parallelism": (f"batch-of-renders shard x{world}; async NCCL all_gather of the mixes overlapping the next step"
+                                if world > 1 else "single GPU: all 128 renders, no collective")}
+    wl = Workload(name)
+    big = wl.samples() * 4 > 126 * 2**20
+    return {"workload": wl.desc, "batch": wl.B, "channels": wl.C, "length": wl.L,
+            "l2": (f"inputs larger than L2 ({wl.samples() * 4 / 2**20:.0f} MiB read + as much written per step vs 126 MiB L2)" if big
+                   else "working set fits L2 (single latency-bound item, the reference's CPU-runnable case)"),
+            "parallelism": f"replicas x{world}: every rank processes its own batch of this size, no collective on the data path"}
 
 
 def tree_to(obj, device, non_blocking=False):
@@ -177,6 +273,18 @@ def tree_pin(obj):
     if isinstance(obj, torch.Tensor):
         return obj.pin_memory()
     return {k: tree_pin(v) for k, v in obj.items()}
+
+
+def tree_bytes(obj):
+    if isinstance(obj, torch.Tensor):
+        return obj.numel() * obj.element_size()
+    return sum(tree_bytes(v) for v in obj.values())
+
+
+def tree_slice(obj, lo, hi):
+    if isinstance(obj, torch.Tensor):
+        return obj[lo:hi]
+    return {k: tree_slice(v, lo, hi) for k, v in obj.items()}
 
 
 def gpu_local_cpus(gpu_index):
@@ -195,16 +303,20 @@ def gpu_local_cpus(gpu_index):
         return None
 
 
-def tree_bytes(obj):
-    if isinstance(obj, torch.Tensor):
-        return obj.numel() * obj.element_size()
-    return sum(tree_bytes(v) for v in obj.values())
+class pinned_near:
+    """Context: allocate pinned host memory from CPUs local to the GPU."""
 
+    def __init__(self, gpu_index):
+        self.cpus = gpu_local_cpus(gpu_index)
 
-def tree_slice(obj, lo, hi):
-    if isinstance(obj, torch.Tensor):
-        return obj[lo:hi]
-    return {k: tree_slice(v, lo, hi) for k, v in obj.items()}
+    def __enter__(self):
+        self.saved = os.sched_getaffinity(0)
+        if self.cpus:
+            os.sched_setaffinity(0, self.cpus)
+
+    def __exit__(self, *exc):
+        os.sched_setaffinity(0, self.saved)
+        return False
 
 
 # --------------------------------------------------------------------------- clocks sampler
@@ -257,7 +369,7 @@ class ClockSampler:
         use = sorted(busy if busy else sm)
         return {"sm_mhz": use[len(use) // 2] if use else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(busy),
-                "window": "warm-up + timed steps + kernel-only loop + end-to-end loop + 1 s of back-to-back steps (50 ms period)"}
+                "window": "every timed region of this run: main workload, kernel-only loops, end-to-end loop, per-config records (50 ms period)"}
 
 
 def pick_cpu_threads(fn):
@@ -278,39 +390,312 @@ def pick_cpu_threads(fn):
     return best_n, cores
 
 
+def cpu_arm(name, steps=None, warmup=1, budget_s=10.0):
+    """Times the oracle port on a bounded sample of workload `name` on the host cores.  steps=None: best of as many
+    repetitions as fit in `budget_s` (>= 2); otherwise exactly `steps` timed steps after `warmup`."""
+    if name == "cfg5":
+        wl = GraphWorkload()
+        import grafx_b200.processors as P  # parameter_size() only (no CUDA)
+
+        procs = {"eq": P.ParametricEqualizer(num_filters=5, processor_channel="stereo", backend="lfilter"),
+                 "compressor": P.Compressor(), "reverb": P.STFTMaskedNoiseReverb(ir_len=96000)}
+        prm = wl.host_params(procs)
+        Bs = 1
+        x = torch.randn(Bs, wl.TRACKS, wl.C, wl.L, generator=torch.Generator().manual_seed(1))
+        samples = Bs * wl.C * wl.L
+        what = f"cfg5: {Bs} render of the 32-track graph (of 128) x 2ch x 131072"
+    else:
+        wl = Workload(name)
+        Bs = wl.cpu_sample_batch()
+        x, prm = wl.host_inputs(Bs)
+        samples = wl.samples(Bs)
+        what = f"{name}: batch {Bs} (of {wl.B}) x {wl.C}ch x {wl.L}"
+    with torch.no_grad():
+        threads, cores = pick_cpu_threads(lambda: wl.cpu_forward(x, prm))
+        if steps is None:
+            best, reps, t_start = 1e30, 0, time.perf_counter()
+            while reps < 2 or (time.perf_counter() - t_start < budget_s and reps < 10):
+                t0 = time.perf_counter()
+                wl.cpu_forward(x, prm)
+                best = min(best, time.perf_counter() - t0)
+                reps += 1
+            dt, how = best, f"best of {reps}"
+        else:
+            for _ in range(warmup):
+                wl.cpu_forward(x, prm)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                wl.cpu_forward(x, prm)
+            dt, how = (time.perf_counter() - t0) / steps, f"mean of {steps} steps after {warmup} warm-up"
+    return {"value": samples / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{what}, {how} at the best thread count ({threads} of {cores} host cores); oracle port = torch CPU ops + "
+                      "torchaudio lfilter as the reference calls them (the reference is Python: no oracle/_ref binary)",
+            "ms_per_sample_step": dt * 1e3}
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args, rank):
     if rank != 0:
         return
-    wl = Workload(args.workload)
-    if wl.cls == "graph":
-        wl.B = 1
-        import grafx_b200.processors as P  # parameter_size() only (no CUDA)
-
-        wl.procs = {"eq": P.ParametricEqualizer(num_filters=5, processor_channel="stereo", backend="lfilter"),
-                    "compressor": P.Compressor(), "reverb": P.STFTMaskedNoiseReverb(ir_len=96000)}
-    else:
-        # bounded sample of the workload: 1/8 of the batch per step
-        wl.B = max(1, wl.B // 8)
-    x, prm = wl.host_inputs()
-    with torch.no_grad():
-        threads, cores = pick_cpu_threads(lambda: wl.cpu_forward(x, prm))
-        for _ in range(args.warmup):
-            wl.cpu_forward(x, prm)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            wl.cpu_forward(x, prm)
-        dt = (time.perf_counter() - t0) / args.steps
-    val = wl.samples() / dt
-    line = {"impl": "reference", "metric": "audio samples/sec (batch x chan x len)", "value": val, "unit": "samples/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.desc, "sample": f"batch {wl.B} per step (bounded sample of the workload)"},
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{wl.name}: batch {wl.B} x {wl.C}ch x {wl.L}, oracle port (torch CPU ops + torchaudio lfilter as the reference calls them), {args.steps} steps, best of thread counts <= {cores} host cores"},
-            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    cb = cpu_arm(args.workload, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_sample_step"], "higher_is_better": True,
+            "scaling": "strong" if args.workload == "cfg5" else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_of(args.workload, args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- device-side measurement helpers
+def capture_step(fn, device):
+    """CUDA-graph capture of `fn` (host launch cost out of the timed region).  Returns (replay, mode, launches of the
+    library per call, keepalive)."""
+    from grafx_b200 import _cabi
+
+    L_ = _cabi.lib()
+    cur = torch.cuda.current_stream(device)
+    side = torch.cuda.Stream(device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fn()
+    cur.wait_stream(side)
+    torch.cuda.synchronize(device)
+    n0 = L_.gfx_kernel_launch_count()
+    fn()
+    torch.cuda.synchronize(device)
+    launches = int(L_.gfx_kernel_launch_count() - n0)
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = fn()
+        return g.replay, "cuda_graph", launches, (g, out)
+    except Exception as e:  # a forward that cannot be captured is timed eagerly (and says so)
+        torch.cuda.synchronize(device)
+        return fn, f"eager ({type(e).__name__})", launches, None
+
+
+def timed_blocks(step, steps, min_seconds, barrier, device, max_over_ranks, finish=None, max_blocks=400):
+    """Blocks of exactly `steps` steps, each bracketed by barrier + synchronize and timed with CUDA events on the
+    launching stream; repeated until `min_seconds` of device time (first block decides how many).  Returns
+    (ms per step = total over all blocks / steps run, max over ranks; list of block times)."""
+    def block():
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        if finish is not None:
+            finish()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1), device)
+
+    first = block()
+    n = int(min(max_blocks, max(1, math.ceil(min_seconds * 1e3 / max(first, 1e-3)))))
+    times = [block() for _ in range(n)]
+    return sum(times) / (len(times) * steps), times
+
+
+def fma_peak(device):
+    """Measured fp32 FMA rate of this GPU (FMA/s), gfx_fma_probe_f32 timed with events; best of 3."""
+    from grafx_b200 import _cabi
+
+    L_ = _cabi.lib()
+    out = torch.zeros(16, device=device)
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = L_.gfx_fma_probe_f32(out.data_ptr(), 4096, _cabi.stream_ptr())
+        e1.record()
+        torch.cuda.synchronize(device)
+        if n > 0:
+            best = max(best, n / (e0.elapsed_time(e1) * 1e-3))
+    return best
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "of measured"
+    except Exception:
+        return 6650.0, "of fallback"
+
+
+def traffic_of(name):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+    except Exception:
+        return None
+
+
+def roofline_of(name, alg_bytes, flops, k_ms, kernel, launches, fma_rate):
+    peak, how = hbm_peak()
+    ach = alg_bytes / (k_ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic_of(name),
+         "kernel": kernel, "kernel_ms": k_ms, "launches_per_step": launches, "algorithmic_bytes": alg_bytes, "peak_source": how,
+         "algorithmic_flops": flops}
+    if fma_rate:
+        r["fp32_fma_frac"] = flops / (k_ms * 1e-3) / (2.0 * fma_rate)
+        r["fp32_fma_peak_tflops"] = 2.0 * fma_rate / 1e12
+    return r
+
+
+def measure_processor(name, device, steps, warmup, min_seconds, world, barrier, max_over_ranks, fma_rate, local_rank,
+                      want_e2e=True, e2e_chunks=4, e2e_streams=3):
+    """Device-resident throughput, kernel-only roofline and (optionally) the end-to-end figure of one processor
+    workload.  Returns a record with the bench-line fields."""
+    wl = Workload(name)
+    wl.build(device)
+    x_h, prm_h = wl.host_inputs()
+    x, prm = x_h.to(device), tree_to(prm_h, device)
+    with torch.no_grad():
+        step, mode, launches, keep = capture_step(lambda: wl.forward(x, prm), device)
+        for _ in range(max(warmup, 3)):
+            step()
+        ms_step, blocks = timed_blocks(step, steps, min_seconds, barrier, device, max_over_ranks)
+        dom_fn, dom_name = wl.dominant_call(x, prm)
+        kstep, kmode, klaunches, kkeep = capture_step(dom_fn, device)
+        for _ in range(3):
+            kstep()
+        k_ms, _ = timed_blocks(kstep, steps, min(min_seconds, 0.3), barrier, device, lambda v, d: v)
+        rec = {"workload": wl.desc, "value": wl.samples() * world / (ms_step * 1e-3), "unit": "samples/s", "ms_per_step": ms_step,
+               "timed_blocks": len(blocks), "steps_per_block": steps, "launch": mode, "launches_per_step": launches,
+               "roofline": roofline_of(name, wl.alg_bytes(), wl.flops_per_sample * wl.samples(), k_ms, dom_name, klaunches, fma_rate)}
+        del keep, kkeep
+        if want_e2e:
+            rec["e2e"] = e2e_processor(wl, x_h, prm_h, device, steps, world, barrier, max_over_ranks, local_rank, e2e_chunks, e2e_streams)
+    del x, prm
+    torch.cuda.empty_cache()
+    return rec, wl
+
+
+def e2e_processor(wl, x_h, prm_h, device, steps, world, barrier, max_over_ranks, local_rank, n_chunks, n_streams):
+    """The same metric through the public nn.Module API from pinned HOST tensors: H2D of the inputs, forward, D2H of
+    the output audio, chunk-pipelined over streams and software-pipelined over steps."""
+    with pinned_near(local_rank):
+        xp, prm_p = x_h.pin_memory(), tree_pin(prm_h)
+        out_bufs = [torch.empty(wl.B, wl.C, wl.L, dtype=torch.float32).pin_memory() for _ in range(2)]
+    nchunk = min(n_chunks, wl.B) if wl.B >= 8 else 1
+    streams = [torch.cuda.Stream(device) for _ in range(min(n_streams, nchunk))]
+    bounds = [(wl.B * i // nchunk, wl.B * (i + 1) // nchunk) for i in range(nchunk)]
+
+    def enqueue(k):
+        out_k = out_bufs[k % 2]
+        for i, (lo, hi) in enumerate(bounds):
+            s = streams[(k * nchunk + i) % len(streams)]
+            with torch.cuda.stream(s):
+                xd = xp[lo:hi].to(device, non_blocking=True)
+                pd = tree_to(tree_slice(prm_p, lo, hi), device, True)
+                out_k[lo:hi].copy_(wl.forward(xd, pd), non_blocking=True)
+        evs = []
+        for s in streams:
+            e = torch.cuda.Event()
+            e.record(s)
+            evs.append(e)
+        return evs
+
+    def run(n):
+        pending = None
+        for k in range(n):
+            evs = enqueue(k)
+            if pending is not None:
+                for e in pending:
+                    e.synchronize()
+            pending = evs
+        for e in pending:
+            e.synchronize()
+
+    run(2)
+    barrier()
+    n_e2e = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    run(n_e2e)
+    barrier()
+    e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_e2e, device)
+    return {"value": wl.samples() * world / (e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": tree_bytes(xp) + tree_bytes(prm_p),
+            "d2h_bytes_per_step": tree_bytes(out_bufs[0]), "ms_per_step": e_ms,
+            "how": f"pinned host tensors -> {nchunk} chunks over {len(streams)} streams: H2D, nn.Module forward, D2H of the output audio; "
+                   "steps pipelined (host waits for step k-1 after enqueuing step k, two result buffers)"}
+
+
+def e2e_graph(wl, device, steps, barrier, max_over_ranks, local_rank):
+    """Config 5 end to end: every chunk's sources come from pinned host memory straight into the captured plan's
+    static input tensor (H2D stream), the plan is replayed (compute stream), the mixes go back to pinned host memory
+    (D2H stream); chunks and steps overlap through events.  Also measures the bare H2D ceiling of the same buffers."""
+    with pinned_near(local_rank):
+        x_host = [torch.empty(wl.chunk, wl.TRACKS, wl.C, wl.L, dtype=torch.float32).pin_memory() for _ in wl.caps]
+        prm_host = tree_pin(wl.host_params())
+        out_host = [torch.empty(wl.B_local, 1, wl.C, wl.L, dtype=torch.float32).pin_memory() for _ in range(2)]
+    for h, cap in zip(x_host, wl.caps):
+        h.copy_(cap.input_signals)  # (same synthetic audio as the device-resident run)
+    torch.cuda.synchronize(device)
+    s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    cur = torch.cuda.current_stream(device)
+    done = [None] * len(wl.caps)      # compute of chunk i (previous step) finished: its input may be overwritten
+    drained = [None] * len(wl.caps)   # D2H of chunk i (previous step) finished: its output may be overwritten
+
+    def step(k):
+        out_k = out_host[k & 1]
+        last = None
+        for i, cap in enumerate(wl.caps):
+            with torch.cuda.stream(s_in):
+                if done[i] is not None:
+                    s_in.wait_event(done[i])
+                cap.input_signals.copy_(x_host[i], non_blocking=True)
+                if i == 0:
+                    for t, d in prm_host.items():
+                        for n, v in d.items():
+                            wl.prm[t][n].copy_(v, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            cur.wait_event(ev_in)
+            if drained[i] is not None:
+                cur.wait_event(drained[i])
+            out, _, _ = cap(None, wl.prm if i == 0 else None)
+            done[i] = torch.cuda.Event()
+            done[i].record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done[i])
+                out_k[i * wl.chunk:(i + 1) * wl.chunk].copy_(out, non_blocking=True)
+                drained[i] = torch.cuda.Event()
+                drained[i].record(s_out)
+                last = drained[i]
+        return last
+
+    def run(n):
+        pending = None
+        for k in range(n):
+            ev = step(k)
+            if pending is not None:
+                pending.synchronize()
+            pending = ev
+        pending.synchronize()
+
+    run(1)
+    barrier()
+    n_e2e = max(2, min(steps, 5))
+    t0 = time.perf_counter()
+    run(n_e2e)
+    barrier()
+    e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_e2e, device)
+    # ceiling: the H2D copies alone, all ranks at once (what the host's PCIe / memory path sustains)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        for h, cap in zip(x_host, wl.caps):
+            cap.input_signals.copy_(h, non_blocking=True)
+    torch.cuda.synchronize(device)
+    barrier()
+    c_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / 2, device)
+    h2d = sum(tree_bytes(h) for h in x_host) + tree_bytes(prm_host)
+    return {"value": wl.samples() / (e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": tree_bytes(out_host[0]), "ms_per_step": e_ms,
+            "ceiling_ms_per_step": c_ms, "ceiling_gbs_per_rank": h2d / (c_ms * 1e-3) / 1e9,
+            "how": "per rank: pinned host sources -> H2D stream straight into each captured plan's static input, CapturedRender replay, "
+                   "mixes D2H on a third stream; chunks and steps overlap through events; `ceiling_*` = the same H2D copies "
+                   "alone on all ranks at once (the step is bound by the host-to-device path: 32 input tracks per output mix)"}
 
 
 # --------------------------------------------------------------------------- main arm
@@ -320,10 +705,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default="cfg5")
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="device time per workload (blocks of --steps steps are repeated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="batch chunks per end-to-end step (copy/compute overlap)")
+    ap.add_argument("--no-per-config", action="store_true")
+    ap.add_argument("--per-config", default="cfg1,cfg2,cfg2lf,cfg3,cfg3b,cfg4,cfg4b")
+    ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--e2e-streams", type=int, default=3)
     args = ap.parse_args()
 
@@ -344,16 +732,6 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from grafx_b200.render.parallel import max_over_ranks
 
-    batch_div = 1
-    if args.workload == "cfg5":
-        batch_div = 1  # 16 renders per GPU (= 128 over 8 GPUs)
-    wl = Workload(args.workload, batch_div)
-    wl.build(device)
-    x_h, prm_h = wl.host_inputs(pin=False)
-    x = x_h.to(device)
-    prm = tree_to(prm_h, device)
-    samples = wl.samples()
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -362,164 +740,81 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            y = wl.forward(x, prm)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        from grafx_b200 import _cabi
-        launches0 = _cabi.lib().gfx_kernel_launch_count()
-        ev0.record()
-        for _ in range(args.steps):
-            y = wl.forward(x, prm)
-        ev1.record()
-        barrier()
-        launches_timed = int(_cabi.lib().gfx_kernel_launch_count() - launches0)
-        ms_total = max_over_ranks(ev0.elapsed_time(ev1), device)
-        ms_step = ms_total / args.steps
-        value = samples * world / (ms_step * 1e-3)
+    fma_rate = fma_peak(device)
+    steps, warmup = args.steps, max(args.warmup, 3)
 
-        # ---- dominant kernel(s) alone (device time, events on the launching stream = torch's current stream)
-        dom_fn, dom_name, alg = wl.dominant_call(x, prm)
-        L_ = _cabi.lib()
-        for _ in range(3):
-            dom_fn()
-        torch.cuda.synchronize()
-        n0 = L_.gfx_kernel_launch_count()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(args.steps):
-            dom_fn()
-        k1.record()
-        torch.cuda.synchronize()
-        k_ms = k0.elapsed_time(k1) / args.steps
-        dom_launches = (L_.gfx_kernel_launch_count() - n0) / args.steps
-        peak, how = 6650.0, "of fallback"
-        try:
-            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-            how = "of measured"
-        except Exception:
-            pass
-        ach = alg / (k_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl.name)
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "kernel": dom_name, "kernel_ms": k_ms, "launches_per_step": dom_launches,
-                    "algorithmic_bytes": alg, "peak_source": how}
+    if args.workload == "cfg5":
+        wl = GraphWorkload(world, rank)
+        wl.build(device)
+        with torch.no_grad():
+            wl.capture()
+            for _ in range(warmup):
+                wl.step()
+            wl.finish()
+            ms_step, blocks = timed_blocks(wl.step, steps, args.min_seconds, barrier, device, max_over_ranks, finish=wl.finish)
+            value = wl.samples() / (ms_step * 1e-3)
+            # the renders alone (no gather): roofline of the graph path on this rank
+            def renders_only():
+                for cap in wl.caps:
+                    cap()
+            for _ in range(2):
+                renders_only()
+            k_ms, _ = timed_blocks(renders_only, max(2, steps // 4), min(args.min_seconds, 0.3), barrier, device, max_over_ranks)
+            launches = wl.caps[0].launches_per_replay
+            roofline = roofline_of("cfg5", wl.alg_bytes_local(), wl.flops_per_out_sample * wl.B_local * wl.C * wl.L, k_ms,
+                                   "render_grafx, 5 render orders per chunk of 16 renders: node_copy, biquad_cascade_x2, dynamics, "
+                                   "reverb pipeline (reverb_ir + filter spectra + partitioned overlap-save), node_sum; CUDA-graph replay",
+                                   launches, fma_rate)
+            roofline["bytes_convention"] = "contract-preserving render: 289 node-signal passes (129 written, 160 read) x 1 MiB per render"
+            roofline["gather_ms_per_step"] = max(ms_step - k_ms, 0.0)
+            e2e = None if args.no_e2e else e2e_graph(wl, device, steps, barrier, max_over_ranks, local_rank)
+        gpu_launches = None if launches is None else launches * wl.n_chunks * steps * len(blocks) * world
+        config = config_of("cfg5", world)
+        scaling = "strong"
+        main_wl_for_cpu = "cfg5"
+        extra = {"timed_blocks": len(blocks), "steps_per_block": steps, "launch": "cuda_graph (CapturedRender, one plan per chunk of 16 renders)"}
+    else:
+        with torch.no_grad():
+            rec, pw = measure_processor(args.workload, device, steps, warmup, args.min_seconds, world, barrier, max_over_ranks,
+                                        fma_rate, local_rank, want_e2e=not args.no_e2e, e2e_chunks=args.e2e_chunks,
+                                        e2e_streams=args.e2e_streams)
+        value, ms_step, roofline, e2e = rec["value"], rec["ms_per_step"], rec["roofline"], rec.get("e2e")
+        gpu_launches = rec["launches_per_step"] * steps * rec["timed_blocks"] * world
+        config = config_of(args.workload, world)
+        scaling = "weak"
+        main_wl_for_cpu = args.workload
+        extra = {"timed_blocks": rec["timed_blocks"], "steps_per_block": steps, "launch": rec["launch"]}
 
-        # ---- end to end through the public nn.Module API with HOST buffers (pinned), copies inside
-        e2e = None
-        if not args.no_e2e:
-            saved_affinity = os.sched_getaffinity(0)
-            local_cpus = gpu_local_cpus(local_rank)
-            if local_cpus:
-                os.sched_setaffinity(0, local_cpus)  # (this thread only: the CPU-baseline leg keeps every core)
-            try:
-                xp, prm_p = x_h.pin_memory(), tree_pin(prm_h)
-                out_p = torch.empty((wl.B, 1 if wl.cls == "graph" else wl.C, wl.L) if wl.cls != "graph" else (wl.B, 1, wl.C, wl.L),
-                                    dtype=torch.float32).pin_memory()
-                out_b = torch.empty_like(out_p).pin_memory()
-            finally:
-                os.sched_setaffinity(0, saved_affinity)
-            nchunk = min(args.e2e_chunks, wl.B) if wl.B >= 8 else 1
-            streams = [torch.cuda.Stream(device) for _ in range(min(args.e2e_streams, nchunk))]
-            bounds = [(wl.B * i // nchunk, wl.B * (i + 1) // nchunk) for i in range(nchunk)]
-            per_item_params = wl.cls != "graph"
-
-            out_bufs = [out_p, out_b]
-
-            def e2e_enqueue(k):
-                """Enqueues step k (H2D, forward, D2H of every chunk) and returns the events that mark its results
-                as readable on the host.  Results alternate between two pinned buffers, so the host may still be
-                reading step k-1 while step k is in flight."""
-                out_k = out_bufs[k % 2]
-                for i, (lo, hi) in enumerate(bounds):
-                    s = streams[(k * nchunk + i) % len(streams)]
-                    with torch.cuda.stream(s):
-                        xd = xp[lo:hi].to(device, non_blocking=True)
-                        pd = tree_to(tree_slice(prm_p, lo, hi) if per_item_params else prm_p, device, True)
-                        yd = wl.forward(xd, pd)
-                        out_k[lo:hi].copy_(yd, non_blocking=True)
-                evs = []
-                for s in streams:
-                    e = torch.cuda.Event()
-                    e.record(s)
-                    evs.append(e)
-                return evs
-
-            def e2e_run(n):
-                # software pipeline over steps: the host waits for step k-1 right after it has enqueued step k, so
-                # the copy engines do not idle at step boundaries; every step's result is observed on the host
-                pending = None
-                for k in range(n):
-                    evs = e2e_enqueue(k)
-                    if pending is not None:
-                        for e in pending:
-                            e.synchronize()
-                    pending = evs
-                for e in pending:
-                    e.synchronize()
-
-            e2e_run(2)
-            barrier()
-            t0 = time.perf_counter()
-            n_e2e = max(3, min(args.steps, 10))
-            e2e_run(n_e2e)
-            barrier()
-            e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_e2e, device)
-            e2e = {"value": samples * world / (e_ms * 1e-3), "unit": "samples/s",
-                   "h2d_bytes_per_step": tree_bytes(xp) + (tree_bytes(prm_p)),
-                   "d2h_bytes_per_step": tree_bytes(out_p), "ms_per_step": e_ms,
-                   "how": f"pinned host tensors -> {nchunk} chunks over {len(streams)} streams: H2D, nn.Module forward, D2H of the output audio; "
-                          "steps pipelined (host waits for step k-1 after enqueuing step k, two result buffers)"}
-
-    # the timed region lasts milliseconds -- shorter than one nvidia-smi sample -- so the same step is also run
-    # back to back for about a second with the sampler on (not timed): these are the clocks "under load"
-    with torch.no_grad():
-        t_end = time.perf_counter() + 1.0
-        while time.perf_counter() < t_end:
-            for _ in range(20):
-                wl.forward(x, prm)
-            torch.cuda.synchronize()
+    # ---- the other BASELINE configs (N = 1 only): one sub-record each
+    per_config = None
+    if world == 1 and not args.no_per_config and args.workload == "cfg5":
+        if args.workload == "cfg5":
+            del wl.caps, wl.mix
+            torch.cuda.empty_cache()
+        per_config = {}
+        for name in [n for n in args.per_config.split(",") if n]:
+            with torch.no_grad():
+                rec, _ = measure_processor(name, device, steps, 3, min(args.min_seconds, 0.5), 1, barrier, max_over_ranks, fma_rate,
+                                           local_rank, want_e2e=False)
+            per_config[name] = rec
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cwl = Workload(args.workload)
-        if cwl.cls == "graph":
-            cwl.B = 1
-            cwl.procs = wl.procs
-        else:
-            cwl.B = max(1, cwl.B // 4)
-        cx, cprm = cwl.host_inputs()
-        with torch.no_grad():
-            threads, cores = pick_cpu_threads(lambda: cwl.cpu_forward(cx, cprm))
-            best = 1e30
-            t_start = time.perf_counter()
-            reps = 0
-            while reps < 3 or (time.perf_counter() - t_start < 10 and reps < 10):
-                t0 = time.perf_counter()
-                cwl.cpu_forward(cx, cprm)
-                best = min(best, time.perf_counter() - t0)
-                reps += 1
-        cpu_baseline = {"value": cwl.samples() / best, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{cwl.name}: batch {cwl.B} x {cwl.C}ch x {cwl.L} (1/4 of the workload), best of {reps} at the best thread count ({threads} of {cores} host cores), oracle port = torch CPU ops + torchaudio lfilter as the reference calls them"}
+        cpu_baseline = cpu_arm(main_wl_for_cpu, budget_s=12.0)
+        if per_config:
+            for name, rec in per_config.items():
+                rec["cpu_baseline"] = cpu_arm(name, budget_s=3.0)
+                rec["gpu_over_cpu"] = rec["value"] / rec["cpu_baseline"]["value"]
 
     if rank == 0:
-        line = {"metric": "audio samples/sec (batch x chan x len)", "value": value, "unit": "samples/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl.desc, "per_gpu_batch": wl.B, "channels": wl.C, "length": wl.L,
-                           "l2": f"inputs larger than L2 ({tree_bytes(x) / 2**20:.0f} MiB read + as much written per step vs 126 MiB L2)",
-                           "parallelism": f"batch shard x{world}, no collective on the data path"},
-                "clocks": clocks, "e2e": e2e,
-                "gpu_launches": launches_timed * world,
-                "roofline": roofline, "cpu_baseline": cpu_baseline}
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, **extra}
+        if per_config is not None:
+            line["per_config"] = per_config
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

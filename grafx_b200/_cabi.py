@@ -42,6 +42,7 @@ SIGNATURES = {
     "gfx_error_string": (ctypes.c_char_p, [c_int]),
     "gfx_kernel_launch_count": (ctypes.c_ulonglong, []),
     "gfx_device_sm_count": (c_int, []),
+    "gfx_fma_probe_f32": (c_ll, [c_void_p, c_int, c_void_p]),
     "gfx_biquad_cascade_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "gfx_biquad_cascade_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_ll, c_void_p, c_size_t, c_void_p]),
@@ -50,6 +51,8 @@ SIGNATURES = {
     "gfx_dynamics_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gfx_dynamics_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, ctypes.POINTER(DynamicsStage), c_int,
                                  c_int, c_void_p, c_size_t, c_void_p]),
+    "gfx_envelope_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                 c_size_t, c_void_p]),
     "gfx_fir_fft_size": (c_int, [c_int]),
     "gfx_fft_plan_bytes": (c_size_t, [c_int]),
     "gfx_fft_plan_init": (c_int, [c_void_p, c_int, c_void_p]),
@@ -93,10 +96,19 @@ def lib():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        if not os.environ.get("GRAFX_B200_LIB"):
             from . import build as _build
 
-            _build.build()
+            try:
+                stale = _build.needs_rebuild()
+            except OSError:  # sources not shipped next to a prebuilt library
+                stale = not os.path.exists(LIB_PATH)
+            if stale:
+                try:
+                    _build.build()
+                except Exception:
+                    if not os.path.exists(LIB_PATH):
+                        raise
         if not os.path.exists(LIB_PATH):
             raise GrafxB200Error(
                 f"{LIB_PATH} is missing and could not be built; grafx_b200 has no CPU fallback")

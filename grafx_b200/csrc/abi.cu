@@ -27,7 +27,33 @@ const DeviceInfo& device_info() {
 }
 }  // namespace gfx
 
+namespace gfx {
+// fp32 FMA issue-rate probe: 16 independent FFMA chains per thread (tools/fma_peak.cu in library form)
+__global__ void __launch_bounds__(512) fma_probe_kernel(float* out, float a, float b, int iters) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = threadIdx.x * 0.001f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == 12345.678f) out[0] = s;  // (keeps the chains alive; practically never true)
+}
+}  // namespace gfx
+
 extern "C" {
+
+long long gfx_fma_probe_f32(float* out, int iters, void* stream) {
+    if (!out || iters <= 0) return GFX_ERR_INVALID;
+    const int blocks = gfx::device_info().sm_count * 4;
+    gfx::fma_probe_kernel<<<blocks, 512, 0, (cudaStream_t)stream>>>(out, 1.0001f, 0.5f, iters);
+    ++g_gfx_launch_count;
+    if (cudaGetLastError() != cudaSuccess) return GFX_ERR_CUDA;
+    return (long long)blocks * 512LL * 16LL * (long long)iters;  // FMAs executed by the launch
+}
 
 int gfx_version(void) { return 0 * 10000 + 1 * 100 + 0; }
 

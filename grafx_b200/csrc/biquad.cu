@@ -869,7 +869,8 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
             // (fully unrolling the section loop per K was measured: no gain -- ptxas keeps its
             //  register-pair copies -- and a bigger instruction footprint; generic K only)
             auto kern2 = biquad_cascade_x2_kernel<16 / X2_WARPS, 0>;
-            static size_t configured2 = 0;
+            static size_t configured2_dev[64] = {0};
+            size_t& configured2 = configured2_dev[device_slot()];
             if (smem2 > configured2) {
                 GFX_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
                 configured2 = smem2;
@@ -890,11 +891,12 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     const size_t smem = cascade_smem_bytes<T>(NT, K);
     if (smem > (size_t)device_info().max_smem_optin) return GFX_ERR_UNSUPPORTED;
     auto kern = biquad_cascade_kernel<T, NT, MINB>;
-    static size_t configured_smem[2] = {0, 0};
+    static size_t configured_smem[64][2] = {{0, 0}};
     const int slot = sizeof(T) == 4 ? 0 : 1;
-    if (smem > configured_smem[slot]) {
+    size_t& conf = configured_smem[device_slot()][slot];
+    if (smem > conf) {
         GFX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured_smem[slot] = smem;
+        conf = smem;
     }
     int occ = 0;
     GFX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));

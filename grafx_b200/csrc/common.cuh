@@ -33,6 +33,12 @@ struct DeviceInfo {
     int max_smem_optin;
 };
 const DeviceInfo& device_info();
+// index of the current device for per-device "already configured" state (cudaFuncSetAttribute is per device)
+inline int device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev < 0 || dev >= 64) ? 0 : dev;
+}
 
 // ---------------------------------------------------------------- cp.async (LDGSTS) helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

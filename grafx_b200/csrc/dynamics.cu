@@ -55,6 +55,11 @@ struct DynParams {
     int n_stages;
     int iir_len;
     int aligned;
+    // envelope mode (gfx_envelope_f32: the stand-alone smoothers / envelope followers, core/envelope.py:10-101,
+    // dynamics.py:745-790): one stage, no knee, y [batch, 1, L] = the smoothed detector signal (or its log)
+    int envelope;   // 0: dynamics processors; 1: envelope output
+    int detect;     // envelope mode: 0 mean_c x^2, 1 mean_c |x|, 2 x itself (C == 1)
+    int env_log;    // envelope mode: y = log(envelope + 1e-5)
     StageDesc st[DYN_MAX_STAGES];
 };
 
@@ -562,6 +567,19 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
             // energy of the signal entering this stage (earlier stages already applied their gain in place)
 #pragma unroll
             for (int i = 0; i < S; ++i) u[i] = 0.f;
+            if (p.envelope && p.detect != 0) {
+                for (int c = 0; c < C; ++c) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 v = cx.xs4[(size_t)c * NT * 8 + swz_unit(cx.tid, q)];
+                        if (p.detect == 1) {
+                            u[4 * q] += fabsf(v.x); u[4 * q + 1] += fabsf(v.y); u[4 * q + 2] += fabsf(v.z); u[4 * q + 3] += fabsf(v.w);
+                        } else {
+                            u[4 * q] = v.x; u[4 * q + 1] = v.y; u[4 * q + 2] = v.z; u[4 * q + 3] = v.w;
+                        }
+                    }
+                }
+            } else
             for (int c = 0; c < C; ++c) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -582,8 +600,12 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
                     // lagged energy re-derived from x itself (read-only input): no history buffer
                     auto lag = [&](long long pos) {
                         float e = 0.f;
-                        for (int c = 0; c < C; ++c) { const float v = xrow[(size_t)c * p.L + pos]; e = fmaf(v, v, e); }
-                        return e * inv_c;
+                        const int det = p.envelope ? p.detect : 0;
+                        for (int c = 0; c < C; ++c) {
+                            const float v = xrow[(size_t)c * p.L + pos];
+                            e = det == 0 ? fmaf(v, v, e) : (det == 1 ? e + fabsf(v) : v);
+                        }
+                        return C > 1 ? e * inv_c : e;
                     };
                     SmootherDesc sm = sd.pre;
                     sm.hist = nullptr;
@@ -597,6 +619,17 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
                 if constexpr (NT == 64) smooth_ballistics<NT>(cx, p, u, sd.pre, 2 * d);  // (ballistics launches use NT = 64)
             }
 
+            if (p.envelope) {
+                // stand-alone smoother / envelope follower: the (log of the) smoothed detector signal is the output
+                if (p.env_log) {
+#pragma unroll
+                    for (int i = 0; i < S; ++i) u[i] = logf(u[i] + 1e-5f);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    cx.xs4[swz_unit(cx.tid, q)] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+                break;
+            }
             const int knee_mode = sd.kind * 3 + (sd.knee == 3 ? 1 : sd.knee);  // 3: quadratic regions, own constants
             if (sd.post.kind == 0) {
                 knee_gain(u, cx.kc[d], knee_mode);
@@ -635,7 +668,9 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
 
         // ---- store coalesced
         __syncthreads();
-        for (int c = 0; c < C; ++c) {
+        const int C_out = p.envelope ? 1 : C;
+        if (p.envelope) yrow = p.y + (size_t)cx.row * (size_t)p.L;
+        for (int c = 0; c < C_out; ++c) {
             float* yr = yrow + (size_t)c * p.L;
             if (full_tile) {
                 float4* dst = reinterpret_cast<float4*>(yr + cx.t0) + cx.tid;
@@ -683,7 +718,8 @@ static int launch_dynamics(DynParams& p, cudaStream_t stream) {
     const size_t smem = dyn_smem_bytes(NT, p.C);
     if (smem > (size_t)device_info().max_smem_optin) return GFX_ERR_UNSUPPORTED;
     auto kern = dynamics_kernel<NT>;
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {0};
+    size_t& configured = configured_dev[device_slot()];
     if (smem > configured) {
         GFX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -714,6 +750,7 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
     if (batch <= 0 || channels <= 0 || L <= 0 || n_stages <= 0 || iir_len <= 0) return GFX_ERR_INVALID;
     if (n_stages > DYN_MAX_STAGES) return GFX_ERR_UNSUPPORTED;
     DynParams p;
+    p.envelope = 0; p.detect = 0; p.env_log = 0;
     bool any_ballistics = false;
     for (int d = 0; d < n_stages; ++d) {
         const gfx_dynamics_stage& s = stages[d];
@@ -757,6 +794,44 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
     p.tables = (float*)(w + dyn_tables_offset(batch, n_stages));
     cudaStream_t st = (cudaStream_t)stream;
     if (any_ballistics) return launch_dynamics<64>(p, st);
+    return small_cta ? launch_dynamics<DYN_SCAN_NT_SMALL>(p, st) : launch_dynamics<DYN_SCAN_NT>(p, st);
+}
+
+int gfx_envelope_f32(const float* x, float* y, int batch, int channels, long long L, int smoother, const float* z,
+                     int detect, int log_out, int iir_len, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace gfx;
+    if (!x || !y || !z) return GFX_ERR_INVALID;
+    if (batch <= 0 || channels <= 0 || L <= 0 || iir_len <= 0) return GFX_ERR_INVALID;
+    if (smoother < 1 || smoother > 2 || detect < 0 || detect > 2 || (detect == 2 && channels != 1)) return GFX_ERR_INVALID;
+    DynParams p;
+    p.envelope = 1; p.detect = detect; p.env_log = log_out ? 1 : 0;
+    StageDesc& o = p.st[0];
+    o.kind = 0; o.knee = 0; o.log_domain = 0;
+    o.log_threshold = z; o.log_ratio = z; o.log_knee = nullptr;  // (the knee constants are formed but never used)
+    o.pre = SmootherDesc{smoother, z, nullptr};
+    o.post = SmootherDesc{0, nullptr, nullptr};
+    const bool ball = smoother == 2;
+    const bool small_cta = batch >= device_info().sm_count * DYN_SCAN_CTAS_SMALL;
+    const int NT = ball ? 64 : (small_cta ? DYN_SCAN_NT_SMALL : DYN_SCAN_NT);
+    const long long tile = (long long)NT * 32;
+    const long long tiles_ll = (L + tile - 1) / tile;
+    if ((long long)batch * tiles_ll > 0x7fff0000LL) return GFX_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < dyn_workspace_bytes(batch, 1)) return GFX_ERR_WORKSPACE;
+    p.x = x; p.y = y; p.batch = batch; p.C = channels; p.L = L;
+    p.tiles = (int)tiles_ll;
+    p.n_items = ball ? (unsigned)batch : (unsigned)((long long)batch * tiles_ll);
+    unsigned char* w = (unsigned char*)workspace;
+    const size_t flags_bytes = ((size_t)batch * sizeof(int) + 255) / 256 * 256;
+    p.ticket = (unsigned int*)w;
+    p.flags = (int*)(w + 256);
+    p.state = (float*)(w + 256 + flags_bytes);
+    p.n_stages = 1;
+    p.iir_len = iir_len;
+    p.aligned = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && (L % 4 == 0);
+    GFX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256 + flags_bytes, (cudaStream_t)stream));
+    p.tables = (float*)(w + dyn_tables_offset(batch, 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ball) return launch_dynamics<64>(p, st);
     return small_cta ? launch_dynamics<DYN_SCAN_NT_SMALL>(p, st) : launch_dynamics<DYN_SCAN_NT>(p, st);
 }
 

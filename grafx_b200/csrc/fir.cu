@@ -947,7 +947,8 @@ static int run_ols(const FirArgs& a) {
     if (!a.ws || a.ws_bytes < need) return GFX_ERR_WORKSPACE;
     float4* Hs = (float4*)a.ws;
     const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
-    static bool configured = false;
+    static bool configured_dev[64] = {false};
+    bool& configured = configured_dev[device_slot()];
     if (!configured) {
         if (set_smem(fir_spectrum_kernel<N, true>, smem) || set_smem(fir_spectrum_kernel<N, false>, smem) ||
             set_smem(fir_ols_kernel<N, true>, smem) || set_smem(fir_ols_kernel<N, false>, smem)) return GFX_ERR_CUDA;
@@ -992,7 +993,8 @@ static int run_upols(const FirArgs& a) {
     long long chunk = (long long)(a.ws_bytes / per_item);
     if (chunk > a.batch) chunk = a.batch;
     const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
-    static bool configured = false;
+    static bool configured_dev[64] = {false};
+    bool& configured = configured_dev[device_slot()];
     if (!configured) {
         if (set_smem(fir_spectrum_kernel<N, true>, smem) || set_smem(fir_spectrum_kernel<N, false>, smem) ||
             set_smem(fir_xspec_kernel<N, true>, smem) || set_smem(fir_xspec_kernel<N, false>, smem) ||
@@ -1049,7 +1051,8 @@ static int run_upols_pipeline(const FirArgs& a) {
     const size_t ctr = upols_ctr_bytes(a.batch);
     if (!a.ws || a.ws_bytes < ctr + (size_t)upols_r() * per_item) return GFX_ERR_WORKSPACE;
     const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
-    static bool configured = false;
+    static bool configured_dev[64] = {false};
+    bool& configured = configured_dev[device_slot()];
     if (!configured) {
         if (set_smem(fir_upols_pipeline_kernel<N, true>, smem) || set_smem(fir_upols_pipeline_kernel<N, false>, smem)) return GFX_ERR_CUDA;
         configured = true;

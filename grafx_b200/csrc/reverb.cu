@@ -565,7 +565,8 @@ int gfx_reverb_ir_f32(const float* noise_stft, long long noise_batch_stride, con
     p.to_lr = mode >= 2;
     cudaStream_t st = (cudaStream_t)stream;
     if (fast) {
-        static bool configured = false;
+        static bool configured_dev[64] = {false};
+        bool& configured = configured_dev[device_slot()];
         if (!configured) {
             GFX_CUDA_CHECK(cudaFuncSetAttribute(reverb_ir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RV_SMEM_BYTES));
             configured = true;

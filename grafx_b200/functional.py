@@ -298,6 +298,40 @@ def dynamics_chain(x: torch.Tensor, stages: list[dict], iir_len: int = 16384) ->
     return y
 
 
+_DETECT = {"energy": 0, "amplitude": 1, None: 2}
+
+
+def envelope(x: torch.Tensor, z: torch.Tensor, smoother: str, detect: str | None = None, log_out: bool = False,
+             iir_len: int = 16384) -> torch.Tensor:
+    """Stand-alone envelope smoothers / followers (core/envelope.py:34-60, 84-101; dynamics.py:745-767).
+
+    x [B, L] with detect=None (the smoother applied to x itself) or [B, C, L] with detect "energy" |
+    "amplitude"; z [B, 1] (smoother "iir") or [B, 2] ("ballistics") -> [B, L]."""
+    _cabi.require_cuda(x, z)
+    _no_backward("envelope", x, z)
+    if detect is None:
+        assert x.ndim == 2, "the smoothers take [B, L] signals"
+        x3 = x.unsqueeze(1)
+    else:
+        assert x.ndim == 3
+        x3 = x
+    B, C, L = x3.shape
+    sm = _SMOOTHER[smoother]
+    assert sm in (1, 2)
+    x3 = _prep(x3, torch.float32)
+    z = _prep(z, torch.float32).reshape(B, -1)
+    assert z.shape[1] == sm, f"z_alpha has {z.shape[1]} columns, expected {sm}"
+    y = torch.empty(B, L, dtype=torch.float32, device=x.device)
+    if y.numel():
+        L_ = _cabi.lib()
+        ws = _cabi.workspace(L_.gfx_dynamics_workspace_bytes(B, 1), x.device)
+        with torch.cuda.device(x.device):
+            code = L_.gfx_envelope_f32(x3.data_ptr(), y.data_ptr(), B, C, L, sm, z.data_ptr(), _DETECT[detect],
+                                       int(bool(log_out)), int(iir_len), ws.data_ptr(), ws.numel(), _cabi.stream_ptr())
+        _cabi.check(code, "gfx_envelope_f32")
+    return y
+
+
 def drywet_mix(dry: torch.Tensor, wet: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     """y = w * wet + (1 - w) * dry, w per batch item used as given (container.py:62-67)."""
     _cabi.require_cuda(dry, wet, weight)
@@ -496,6 +530,8 @@ def row_mean(x: torch.Tensor) -> torch.Tensor:
     """Mean over time of every (batch, channel) row -> [B, C] (the `remove_dc` option of nonlinear.py)."""
     _cabi.require_cuda(x)
     assert x.ndim == 3
+    if _wants_grad(x):  # O(1) flops per sample and its adjoint is a broadcast: the PyTorch statement carries the graph
+        return x.to(torch.float32).mean(-1)
     x = _prep(x, torch.float32)
     B, C, L = x.shape
     m = torch.empty(B, C, dtype=torch.float32, device=x.device)
@@ -509,6 +545,8 @@ def mean_square(x: torch.Tensor) -> torch.Tensor:
     """Mean of x^2 over the channel and time axes -> [B] (x.square().mean((-1, -2)) of core/utils.py:8-9)."""
     _cabi.require_cuda(x)
     assert x.ndim == 3
+    if _wants_grad(x):  # a training regulariser upstream (GainStagingRegularization): never cut the graph silently
+        return x.to(torch.float32).square().mean((-1, -2))
     x = _prep(x, torch.float32)
     B, C, L = x.shape
     m = torch.empty(B, dtype=torch.float32, device=x.device)

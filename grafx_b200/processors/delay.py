@@ -1,7 +1,7 @@
 """MultitapDelay -- drop-in for grafx.processors.delay.MultitapDelay (delay.py:12-177) and the surrogate delay line of
 grafx.processors.core.delay (core/delay.py:16-142).
 
-Forward only.  The impulse response is designed in PyTorch on the device (O(taps x segment) work: one surrogate
+The impulse response is designed in PyTorch on the device (O(taps x segment) work: one surrogate
 "delay" per tap from a complex pole, an optional zero-phase colouring FIR per tap, taps of a segment summed,
 segments concatenated, unit-energy normalisation); the two O(samples) steps -- the zero-phase colouring convolution
 of the tap responses and the causal convolution of the audio -- run on the FIR engine (csrc/fir.cu).  With
@@ -16,13 +16,28 @@ from .. import functional as F_
 from .core.fir import ZeroPhaseFIR
 
 
+class _UnitModulusGradient(torch.autograd.Function):
+    """Identity whose backward rescales every (complex) gradient entry to modulus ~1 -- the
+    `normalize_gradients` option of the surrogate delay (core/delay.py:5-13)."""
+
+    @staticmethod
+    def forward(ctx, z):
+        return z
+
+    @staticmethod
+    def backward(ctx, g):
+        return g / (g.abs() + 1e-7)
+
+
 class SurrogateDelay(nn.Module):
-    """core/delay.py:16-142 (forward values; the gradient tricks are out of scope here)."""
+    """core/delay.py:16-142: soft delays from complex poles; with `straight_through` the forward value is the hard
+    unit impulse while the gradient is the soft response's; `normalize_gradients` as upstream."""
 
     def __init__(self, N, straight_through=True, radii_loss=True, normalize_gradients=True):
         super().__init__()
         self.straight_through = straight_through
         self.radii_loss = radii_loss
+        self.normalize_gradients = normalize_gradients
         self.register_buffer("arange_sin", torch.arange(N // 2 + 1)[None, :])
 
     def forward(self, z):
@@ -31,12 +46,16 @@ class SurrogateDelay(nn.Module):
         z = z.reshape(-1)
         mag = torch.abs(z)
         loss = (1 - torch.tanh(mag)).square().sum()
+        if self.normalize_gradients and z.requires_grad and torch.is_grad_enabled():
+            z = _UnitModulusGradient.apply(z)
+            mag = torch.abs(z)
         z = z * torch.tanh(mag) / (mag + 1e-7)
         irs = torch.fft.irfft((z[:, None] + 1e-7) ** self.arange_sin)
         if self.straight_through:
-            hard = torch.zeros_like(irs)
-            hard[torch.arange(irs.shape[0], device=irs.device), torch.argmax(irs, -1)] = 1
-            irs = irs + (hard - irs)
+            with torch.no_grad():
+                hard = torch.zeros_like(irs)
+                hard[torch.arange(irs.shape[0], device=irs.device), torch.argmax(irs, -1)] = 1
+            irs = irs + (hard - irs).detach()
         return irs.reshape(*shape, -1), loss
 
 

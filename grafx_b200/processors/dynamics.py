@@ -104,3 +104,47 @@ class ApproxNoiseGate(nn.Module):
 
     def parameter_size(self):
         return {"z_alpha": 1, "log_threshold": 1, "log_ratio": 1, "log_knee": 1}
+
+
+class BaseEnvelopeFollower(nn.Module):
+    """dynamics.py:745-767: detector (mean over channels of x^2 or |x|) -> smoother -> log(envelope + 1e-5), one
+    fused kernel launch (gfx_envelope_f32).  `detect_with="rms_channel"` cannot run upstream (it reads an undefined
+    `self.eps`) and is rejected here."""
+
+    _smoother_kind = None
+
+    def __init__(self, smoother, detect_with="energy"):
+        super().__init__()
+        if detect_with not in ("energy", "amplitude"):
+            raise ValueError(f"Unknown detect_with: {detect_with}")
+        self.detect_with = detect_with
+        self.smoother = smoother
+
+    def forward(self, signal, z_alpha):
+        return F_.envelope(signal, z_alpha, self._smoother_kind, detect=self.detect_with, log_out=True,
+                           iir_len=getattr(self.smoother, "iir_len", 16384))
+
+    def parameter_size(self):
+        return self.smoother.parameter_size()
+
+
+class IIREnvelopeFollower(BaseEnvelopeFollower):
+    """dynamics.py:770-784."""
+
+    _smoother_kind = "iir"
+
+    def __init__(self, detect_with="energy", iir_len=16384, flashfftconv=True, max_input_len=2**17):
+        from .core.envelope import TruncatedOnePoleIIRFilter
+
+        super().__init__(TruncatedOnePoleIIRFilter(iir_len=iir_len), detect_with=detect_with)
+
+
+class BallisticsEnvelopeFollower(BaseEnvelopeFollower):
+    """dynamics.py:787-790."""
+
+    _smoother_kind = "ballistics"
+
+    def __init__(self, detect_with="energy"):
+        from .core.envelope import Ballistics
+
+        super().__init__(Ballistics(), detect_with=detect_with)

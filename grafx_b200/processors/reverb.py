@@ -47,14 +47,16 @@ class STFTMaskedNoiseReverb(nn.Module):
         st = self._stft(noise)
         return st.reshape(batch, 2, st.shape[-2], st.shape[-1])
 
-    def compute_ir(self, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude=None, _finish="unit"):
-        """Mid/side impulse response.  NB upstream returns it un-normalised; here the kernel also
-        applies the channel-mode epilogue, selected by `_finish`: "unit" keeps upstream's meaning up
-        to the unit-energy scale, "lr" adds ms_to_lr, "raw" returns (raw response, row energies)."""
+    def _synthesize(self, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude, finish):
         genv = gain_env_log_magnitude if self.gain_envelope else None
         noise = self._noise(init_log_magnitude.shape[0], init_log_magnitude.device)
         return F_.reverb_ir(noise, init_log_magnitude, delta_log_magnitude, genv, self.window, self.ir_len,
-                            self.n_fft, self.hop_length, finish=_finish)
+                            self.n_fft, self.hop_length, finish=finish)
+
+    def compute_ir(self, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude=None):
+        """The un-normalised mid/side impulse response [B, 2, ir_len], as upstream (reverb.py:161-200: the
+        channel-mode epilogue and normalize_impulse belong to _process_*, not to compute_ir)."""
+        return self._synthesize(init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude, "raw")[0]
 
     def forward(self, input_signals, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude=None):
         # un-normalised response (+ row energies) in its final channel layout; normalize_impulse
@@ -69,8 +71,8 @@ class STFTMaskedNoiseReverb(nn.Module):
                 gain_env_log_magnitude = gain_env_log_magnitude[::rep]
         else:
             rep = 1
-        ir_raw, energy = self.compute_ir(init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude,
-                                         _finish="raw_lr" if to_lr else "raw")
+        ir_raw, energy = self._synthesize(init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude,
+                                          "raw_lr" if to_lr else "raw")
         if self.processor_channel == "midside":
             return F_.ms_to_lr(F_.fir_conv_midside_ir(F_.lr_to_ms(input_signals), ir_raw, energy, to_lr=False, h_repeat=rep))
         return F_.fir_conv_midside_ir(input_signals, ir_raw, energy, to_lr=to_lr, h_repeat=rep)

@@ -59,6 +59,13 @@ class CapturedRender:
                     run()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            from .. import _cabi
+
+            n0 = _cabi.lib().gfx_kernel_launch_count()
+            run()
+            torch.cuda.synchronize()
+            #: kernels of libgrafx_b200 inside one replay (the library's own launch counter over one eager pass)
+            self.launches_per_replay = int(_cabi.lib().gfx_kernel_launch_count() - n0)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.output_signals, self.intermediates_list, self.signal_buffer = run()

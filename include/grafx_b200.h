@@ -43,6 +43,9 @@ GFX_API int gfx_last_cuda_error(void);      /* cudaError_t of the last failed ru
 GFX_API const char* gfx_error_string(int code);
 GFX_API unsigned long long gfx_kernel_launch_count(void); /* kernels this library has launched since it was loaded */
 GFX_API int gfx_device_sm_count(void);      /* SMs of the current device (148 on B200), <0 on error */
+/* Measurement aid (bench.py roofline: the fp32-FMA fraction beside the HBM one): enqueues a kernel of independent
+ * FFMA chains on every SM and returns the number of FMAs it executes (negative: error code); time it with events. */
+GFX_API long long gfx_fma_probe_f32(float* out, int iters, void* stream);
 
 /* ---- exact biquad cascade ------------------------------------------------------------------
  * Replaces IIRFilter._process_lfilter (processors/core/iir.py:154-184: K sequential
@@ -237,6 +240,18 @@ GFX_API size_t gfx_dynamics_workspace_bytes(int batch, int n_stages);
 GFX_API int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long long L,
                              const gfx_dynamics_stage* stages, int n_stages, int iir_len,
                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stand-alone envelope smoothers and followers on the same kernel.
+ * Replaces: TruncatedOnePoleIIRFilter.forward (processors/core/envelope.py:34-60), Ballistics.forward
+ * (core/envelope.py:84-101), BaseEnvelopeFollower.forward (processors/dynamics.py:745-767).
+ *   x [batch, channels, L] -> y [batch, L]
+ *   detect:   0 mean over channels of x^2 ("energy"), 1 mean of |x| ("amplitude"), 2 x itself (channels == 1)
+ *   smoother: 1 truncated one-pole (z [batch,1], relu as upstream), 2 ballistics (z [batch,2], starts from 1)
+ *   log_out:  y = log(envelope + 1e-5) (the envelope followers)
+ * workspace: gfx_dynamics_workspace_bytes(batch, 1). */
+GFX_API int gfx_envelope_f32(const float* x, float* y, int batch, int channels, long long L, int smoother,
+                             const float* z, int detect, int log_out, int iir_len, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,9 +9,11 @@ Pinning: the reference's tests hold no golden vectors; the
 known-answer test is ssm == lfilter (tests/processors/test_filter.py:215-233).  This oracle
 is therefore pinned by executing the reference's own code in the build container
 (oracle/ref_loader.py, oracle/make_golden.py) and comparing: see tests/test_oracle_golden.py
-and the fixtures in tests/golden/.  One exception: `ballistics` (torchcomp.compressor_core is
-absent from the reference tree and from this image) -- PARITY UNPINNED for that recurrence;
-the assumed semantics are stated in `ballistics()`.
+and the fixtures in tests/golden/.  One third-party recurrence is not in the reference tree nor in this image:
+`ballistics` = torchcomp.compressor_core.  It is pinned to the upstream kernel text as restated in
+oracle/torchcomp_core.py (bit-exact agreement in float64) and by reference-side invariants (equal coefficients ==
+the linear one-pole; single-branch inputs): tests/test_oracle_golden.py::test_ballistics_*.  It has NOT been compared
+with an installed torchcomp (none is available offline).
 
 Everything is dtype-generic torch code (run it in float64 for a ground truth, in float32 to
 mimic the reference's arithmetic) plus scipy/numpy for the sequential loops.  The exact IIR
@@ -309,10 +311,11 @@ def truncated_one_pole_recursive(u, z_alpha, iir_len=16384):
 
 # ------------------------------------------------------------------ core/envelope.py:84-101
 def ballistics(u, z_alpha):
-    """ASSUMED recurrence of torchcomp.compressor_core(x, zi=1, at, rt) -- PARITY UNPINNED:
+    """Ballistics.forward (core/envelope.py:84-101) = torchcomp.compressor_core(u, zi=1, at, rt), whose kernel
+    (torchcomp/core.py: compressor_kernel, restated in oracle/torchcomp_core.py) is
         at, rt = sigmoid(z[:,0]), sigmoid(z[:,1]);  y[-1] = 1
         c = at if u[t] < y[t-1] else rt;  y[t] = (1 - c) y[t-1] + c u[t]
-    Sequential; evaluated in the dtype of u with numpy."""
+    Sequential; evaluated in the dtype of u with numpy.  Pins: tests/test_oracle_golden.py::test_ballistics_*."""
     ts = torch.sigmoid(z_alpha)
     at, rt = ts[..., 0].numpy(), ts[..., 1].numpy()
     un = u.numpy()
@@ -325,6 +328,14 @@ def ballistics(u, z_alpha):
         prev = (one - c) * prev + c * x_t
         y[:, t] = prev
     return torch.from_numpy(y)
+
+
+def envelope_follower(x, z_alpha, smoother="iir", detect_with="energy", iir_len=16384):
+    """BaseEnvelopeFollower.forward (dynamics.py:745-767): detector over the channel axis -> smoother ->
+    log(envelope + 1e-5).  x [B, C, L] -> [B, L]."""
+    loud = x.square().mean(-2) if detect_with == "energy" else x.abs().mean(-2)
+    env = truncated_one_pole(loud, z_alpha, iir_len) if smoother == "iir" else ballistics(loud, z_alpha)
+    return torch.log(env + 1e-5)
 
 
 # ------------------------------------------------------------------ dynamics.py:361-419,443-489 / 598-651,675-721

@@ -78,9 +78,9 @@ def _sample_wise_lpc(x, a, zi=None):
 
 
 def compressor_core_loop(x, zi, at, rt):
-    """torchcomp.compressor_core recurrence as ASSUMED by this repo (parity unpinned,
-    SURVEY.md section 8(c) item 3): c = at if x[t] < y[t-1] else rt;
-    y[t] = (1-c) y[t-1] + c x[t]; y[-1] = zi."""
+    """torchcomp.compressor_core (the stand-in installed for the reference's import): c = at if x[t] < y[t-1]
+    else rt; y[t] = (1-c) y[t-1] + c x[t]; y[-1] = zi -- the upstream kernel restated in oracle/torchcomp_core.py,
+    vectorised over the batch (bit-identical in float64: tests/test_oracle_golden.py::test_ballistics_*)."""
     x_np = x.detach().cpu().numpy()
     y = np.empty_like(x_np)
     atn, rtn = at.detach().cpu().numpy(), rt.detach().cpu().numpy()

@@ -48,7 +48,7 @@ CLASS_OF_PREFIX = {
 
 def fixture_names(prefixes=None):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    names = [n for n in names if not n.startswith(("kat_", "render_", "convolve_"))]
+    names = [n for n in names if not n.startswith(("kat_", "render_", "convolve_", "envelope_", "fullsize_"))]
     if not prefixes or not any(p.startswith("grad_") for p in prefixes):
         names = [n for n in names if not n.startswith("grad_")]  # gradient fixtures (oracle/make_golden_grad.py)
     if prefixes:

@@ -1,0 +1,229 @@
+"""GPU parity at the FULL BASELINE.json sizes ("untested configs"): the product runs the whole
+configuration, a sampled set of rows is compared with the oracle on the host; plus the stand-alone envelope modules and
+the render_grafx branches that had no test (one-by-one buffer, common_parameters).
+
+Tolerance: rel-L2 <= 1e-4 and max|err| <= 1e-4 * max|ref| per compared block (north_star: within 1e-4 relative)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _golden import GOLDEN, max_rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def assert_close(y, y_ref, name, tol=TOL):
+    assert y.shape == y_ref.shape, (name, y.shape, y_ref.shape)
+    assert torch.isfinite(y).all(), name
+    r, m = rel_l2(y, y_ref), max_rel(y, y_ref)
+    assert r <= tol and m <= tol, (name, r, m)
+
+
+def _cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+# ------------------------------------------------------------------ config 3: reverb, 512 x 2 x 131072, 96000 taps
+def test_cfg3_reverb_full_size_rows_vs_oracle():
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    gen = torch.Generator().manual_seed(3)
+    B, L = 512, 131072
+    proc = P.STFTMaskedNoiseReverb(ir_len=96000).cuda()
+    x = torch.randn(B, 2, L, generator=gen)
+    prm = {k: torch.randn(B, *v, generator=gen) for k, v in proc.parameter_size().items()}
+    y = proc(x.cuda(), **_cuda(prm))
+    torch.cuda.synchronize()
+    rows = [0, 129, 300, 511]
+    y_ref = O.stft_masked_noise_reverb(x[rows], **{k: v[rows] for k, v in prm.items()}, ir_len=96000)
+    for i, r in enumerate(rows):
+        assert_close(y[r].cpu(), y_ref[i], f"cfg3 row {r}")
+    # linearity over the whole batch (size-independent property)
+    x2 = torch.randn(B, 2, L, generator=gen).cuda()
+    lhs = proc(x.cuda() - 0.5 * x2, **_cuda(prm))
+    rhs = y - 0.5 * proc(x2, **_cuda(prm))
+    assert rel_l2(lhs.cpu(), rhs.cpu()) < 2e-5
+
+
+# ------------------------------------------------------------------ config 4 / 4b: Compressor -> NoiseGate, 1024 x 1 x 65536
+@pytest.mark.parametrize("smoother", ["iir", "ballistics"])
+def test_cfg4_chain_full_size_rows_vs_oracle(smoother):
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    gen = torch.Generator().manual_seed(44)
+    B, L = 1024, 65536
+    x = torch.randn(B, 1, L, generator=gen)
+    comp, gate = P.Compressor(energy_smoother=smoother), P.NoiseGate(energy_smoother=smoother)
+
+    def draw(proc):
+        return {k: torch.randn(B, v, generator=gen) for k, v in proc.parameter_size().items()}
+
+    pc, pg = draw(comp), draw(gate)
+    chain = P.SerialChain({"comp": comp, "gate": gate}).cuda()
+    y, _ = chain(x.cuda(), comp=_cuda(pc), gate=_cuda(pg))
+    torch.cuda.synchronize()
+    rows = [0, 1, 257, 600, 1023]
+    y1 = O.compressor(x[rows], **{k: v[rows] for k, v in pc.items()}, energy_smoother=smoother)
+    y_ref = O.noisegate(y1, **{k: v[rows] for k, v in pg.items()}, energy_smoother=smoother)
+    for i, r in enumerate(rows):
+        assert_close(y[r].cpu(), y_ref[i], f"cfg4-{smoother} row {r}")
+
+
+# ------------------------------------------------------------------ config 5: one 32-track render, output AND buffer
+def test_cfg5_graph_32_tracks_vs_oracle_render():
+    """32 x (in -> eq -> compressor -> reverb) -> out at L = 131072, B = 2 renders: the `filter_repeat` /
+    `shared_parameters` path of the product against the oracle's restatement of render_grafx (which has no such path)."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+    from grafx_b200.render import mixing_console_plan, render_grafx
+
+    gen = torch.Generator().manual_seed(5)
+    T, B, L = 32, 2, 131072
+    procs = {"eq": P.ParametricEqualizer(num_filters=5, processor_channel="stereo", backend="lfilter").cuda(),
+             "compressor": P.Compressor().cuda(), "reverb": P.STFTMaskedNoiseReverb(ir_len=96000).cuda()}
+    x = torch.randn(B, T, 2, L, generator=gen)
+    prm = {t: {k: 0.3 * torch.randn(T, *((v,) if isinstance(v, int) else v), generator=gen)
+               for k, v in p.parameter_size().items()} for t, p in procs.items()}
+    rd = mixing_console_plan(T, ["eq", "compressor", "reverb"])
+    out, inter, buf = render_grafx(procs, x.cuda(), {t: _cuda(p) for t, p in prm.items()}, rd, parameters_grad=False)
+    torch.cuda.synchronize()
+    oprocs = {"eq": lambda s, **p: O.parametric_equalizer(s, **p, processor_channel="stereo", backend="lfilter"),
+              "compressor": lambda s, **p: O.compressor(s, **p),
+              "reverb": lambda s, **p: O.stft_masked_noise_reverb(s, **p, ir_len=96000)}
+    plan = {"num_nodes": 4 * T + 1, "iters": [None] + [
+        {"type": t, "reads": [("slice", (i * T, (i + 1) * T))], "aggs": [("none", None)], "param": ("slice", (0, T)),
+         "write": ("slice", ((i + 1) * T, (i + 2) * T))} for i, t in enumerate(["eq", "compressor", "reverb"])] + [
+        {"type": "out", "reads": [("slice", (3 * T, 4 * T))], "aggs": [("sum", None)], "param": ("slice", (0, 1)),
+         "write": ("slice", (4 * T, 4 * T + 1))}]}
+    ref_out, ref_buf = O.render_plan(oprocs, x, prm, plan)
+    assert inter == []
+    assert_close(out.cpu(), ref_out, "cfg5 output")
+    assert tuple(buf.shape) == (B, 4 * T + 1, 2, L)
+    # every node signal of the buffer, stage by stage (sources, eq, compressor, reverb, mix)
+    for name, lo, hi in (("in", 0, T), ("eq", T, 2 * T), ("compressor", 2 * T, 3 * T), ("reverb", 3 * T, 4 * T), ("out", 4 * T, 4 * T + 1)):
+        assert_close(buf[:, lo:hi].cpu(), ref_buf[:, lo:hi], f"cfg5 buffer[{name}]")
+
+
+# ------------------------------------------------------------------ stand-alone envelope modules
+def test_envelope_modules_vs_reference_golden():
+    from grafx_b200.processors.core.envelope import Ballistics, TruncatedOnePoleIIRFilter
+    from grafx_b200.processors.dynamics import BallisticsEnvelopeFollower, IIREnvelopeFollower
+
+    zf = np.load(os.path.join(GOLDEN, "envelope_modules.npz"))
+    u, x = torch.from_numpy(zf["u"]).cuda(), torch.from_numpy(zf["x"]).cuda()
+    z1, z2 = torch.from_numpy(zf["z1"]).cuda(), torch.from_numpy(zf["z2"]).cuda()
+    n = int(zf["iir_len"])
+    assert_close(TruncatedOnePoleIIRFilter(iir_len=n).cuda()(u, z1).cpu(), torch.from_numpy(zf["y_onepole"]), "one-pole")
+    assert_close(Ballistics().cuda()(u, z2).cpu(), torch.from_numpy(zf["y_ballistics"]), "ballistics")
+    for det in ("energy", "amplitude"):
+        assert_close(IIREnvelopeFollower(detect_with=det, iir_len=n).cuda()(x, z1).cpu(),
+                     torch.from_numpy(zf[f"env_iir_{det}"]), f"iir follower {det}")
+        assert_close(BallisticsEnvelopeFollower(detect_with=det).cuda()(x, z2).cpu(),
+                     torch.from_numpy(zf[f"env_ballistics_{det}"]), f"ballistics follower {det}")
+    with pytest.raises(ValueError):
+        IIREnvelopeFollower(detect_with="rms_channel")
+
+
+@pytest.mark.parametrize("L", [1, 31, 8193, 70001])
+def test_envelope_modules_ragged_vs_oracle(L):
+    from oracle import grafx_oracle as O
+    from grafx_b200.processors.core.envelope import Ballistics, TruncatedOnePoleIIRFilter
+    from grafx_b200.processors.dynamics import IIREnvelopeFollower
+
+    gen = torch.Generator().manual_seed(L)
+    B = 5
+    u = torch.randn(B, L, generator=gen)  # signed input: the relu of the one-pole matters
+    z1 = torch.tensor([[9.0], [2.0], [0.0], [-3.0], [5.0]])
+    z2 = torch.randn(B, 2, generator=gen)
+    assert_close(TruncatedOnePoleIIRFilter(iir_len=4096).cuda()(u.cuda(), z1.cuda()).cpu(),
+                 O.truncated_one_pole_recursive(u, z1, iir_len=4096), f"one-pole L={L}", tol=2e-5)
+    assert_close(Ballistics().cuda()(u.abs().cuda(), z2.cuda()).cpu(), O.ballistics(u.abs(), z2), f"ballistics L={L}", tol=2e-5)
+    x = torch.randn(B, 3, L, generator=gen)
+    got = IIREnvelopeFollower(iir_len=4096).cuda()(x.cuda(), z1.cuda()).cpu()
+    ref = torch.log(O.truncated_one_pole_recursive(x.square().mean(-2), z1, iir_len=4096) + 1e-5)
+    assert float((got - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+
+
+def test_ballistics_equal_coefficients_is_one_pole_on_gpu():
+    """The reference-side invariant that pins the recursion (tests/test_oracle_golden.py) on the CUDA kernel itself:
+    at == rt must reproduce the linear one-pole started from 1, at the full config-4 row length."""
+    import scipy.signal
+    from grafx_b200.processors.core.envelope import Ballistics
+
+    gen = torch.Generator().manual_seed(9)
+    B, L = 6, 65536
+    u = torch.rand(B, L, generator=gen) * 2
+    z = torch.randn(B, 1, generator=gen).expand(B, 2).contiguous()
+    y = Ballistics().cuda()(u.cuda(), z.cuda()).cpu().double().numpy()
+    a = torch.sigmoid(z[:, 0].double()).numpy()
+    for r in range(B):
+        ref, _ = scipy.signal.lfilter([a[r]], [1.0, -(1.0 - a[r])], u[r].double().numpy(), zi=[(1.0 - a[r])])
+        assert np.abs(y[r] - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+# ------------------------------------------------------------------ render_grafx branches without a test so far
+def _three_track_plan(method):
+    from grafx_b200.render import mixing_console_plan
+
+    return mixing_console_plan(3, ["eq", "compressor"], method=method)
+
+
+def test_render_one_by_one_list_buffer_matches_tensor_buffer():
+    """`method="one-by-one"`: the signal buffer is a Python list with one entry per node (render/core.py:15-17,81-82);
+    one node per render order."""
+    import grafx_b200.processors as P
+    from grafx_b200.render import render_grafx
+    from grafx_b200.render.plan import RenderData, _AggregationData as Agg, _SingleRenderData as It, _TensorAccessData as Acc
+
+    torch.manual_seed(31)
+    L = 5000
+    x = torch.randn(2, 2, L, device="cuda")
+    eq, comp = P.ParametricEqualizer(num_filters=3).cuda(), P.Compressor().cuda()
+    prm = {"eq": {k: 0.5 * torch.randn(2, *v, device="cuda") for k, v in eq.parameter_size().items()},
+           "compressor": {k: torch.randn(2, v, device="cuda") for k, v in comp.parameter_size().items()}}
+    procs = {"eq": eq, "compressor": comp}
+    # nodes: 0,1 inputs | 2 = eq(0) | 3 = eq(1) | 4 = compressor(2) | 5 = compressor(3) | 6 = out(4 + 5)
+    def one(t, src, par, dst):
+        return It(t, [Acc("slice", (src, src + 1))], [Agg("none")], Acc("slice", (par, par + 1)), Acc("slice", (dst, dst + 1)))
+    iters = [It("in", [Acc("none", ())], [Agg("none")], Acc("slice", (0, 2)), Acc("slice", (0, 2))),
+             one("eq", 0, 0, 2), one("eq", 1, 1, 3), one("compressor", 2, 0, 4), one("compressor", 3, 1, 5)]
+    rd_list = RenderData("one-by-one", 6, 4, True, iters)
+    out_l, _, buf_l = render_grafx(procs, x, prm, rd_list)
+    assert isinstance(buf_l, list) and len(buf_l) == 6
+    batched = RenderData("beam", 6, 2, True, [iters[0],
+        It("eq", [Acc("slice", (0, 2))], [Agg("none")], Acc("slice", (0, 2)), Acc("slice", (2, 4))),
+        It("compressor", [Acc("slice", (2, 4))], [Agg("none")], Acc("slice", (0, 2)), Acc("slice", (4, 6)))])
+    out_t, _, buf_t = render_grafx(procs, x, prm, batched)
+    for n in range(6):
+        assert torch.allclose(buf_l[n][0], buf_t[n], rtol=1e-5, atol=1e-6), n
+    assert torch.allclose(out_l[0], buf_t[5], rtol=1e-5, atol=1e-6)
+
+
+def test_render_common_parameters_reach_the_processor():
+    """`common_parameters` (render/graph.py:132-141): per-NODE tensors read with the destination access of every
+    render order and passed as extra keyword arguments -- here the DryWet weight of each track."""
+    import grafx_b200.processors as P
+    from grafx_b200.render import mixing_console_plan, render_grafx
+
+    torch.manual_seed(32)
+    T, L = 3, 4000
+    x = torch.randn(T, 2, L, device="cuda")
+    wet = P.DryWet(P.TanhDistortion()).cuda()
+    inner = wet.processor.parameter_size()
+    prm = {"fx": {k: 0.5 * torch.randn(T, *((v,) if isinstance(v, int) else v), device="cuda") for k, v in inner.items()}}
+    rd = mixing_console_plan(T, ["fx"])
+    num_nodes = rd.num_nodes
+    weights = torch.rand(num_nodes, 1, device="cuda")
+    out, _, buf = render_grafx({"fx": wet}, x, prm, rd, common_parameters={"drywet_weight": weights})
+    ref = wet(x, drywet_weight=weights[T:2 * T], **prm["fx"])
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    assert torch.allclose(buf[T:2 * T], ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(out[0], ref.sum(0), rtol=1e-5, atol=1e-5)
+    # a single tensor instead of a dict is passed as `parameter=` upstream; processors without that argument raise
+    with pytest.raises(TypeError):
+        render_grafx({"fx": wet}, x, prm, rd, common_parameters=weights)
