@@ -660,6 +660,175 @@ __global__ void __launch_bounds__(MAC_NT, GFX_MAC_MINB) fir_mac_kernel(const flo
     }
 }
 
+// UPOLS step 2, streaming form.  fir_mac_kernel above is latency-bound (profiles/r01_final_fir_mac_12.txt: 2.8 warps per
+// scheduler, 40 % of the stalls wait for the 12 loads a thread issues and then consumes): with the 4096-point partitioning
+// (24 partitions of a 96000-tap response; FFT kernels at 4 CTAs per SM) the arithmetic per byte doubles and a load-then-
+// compute thread takes twice as long.  Here (a) one thread owns ONE complex bin (half a pair slot, 8 bytes), which halves
+// the registers per partition: up to MAC2_MAX_PC = 24 partitions (filter 48 + input ring 48 registers) in one pass over
+// the spectra; (b) the input blocks arrive through a cp.async ring in shared memory, MAC2_STAGES blocks ahead of the
+// arithmetic (every thread copies and later reads its own 8 bytes: no barrier), so no register holds a load in flight;
+// (c) the loop body covers U = 4 output blocks with compile-time operand indices and then moves the ring (small code);
+// the bodies in which the ring is still filling up are peeled and skip the empty entries.
+// A CTA can also walk `bpc` consecutive batch items that share the filter (render_grafx's 4-D sources) with the filter partitions loaded once.
+// Element e = 2 slot + (0: bin k | 1: bin n-k); element 0 is (A_0, A_N), two real bins.
+constexpr int MAC2_MAX_PC = 24;
+#ifndef GFX_MAC2_NT
+#define GFX_MAC2_NT 64
+#endif
+#ifndef GFX_MAC2_MINB
+#define GFX_MAC2_MINB 8
+#endif
+#ifndef GFX_MAC2_STAGES
+#define GFX_MAC2_STAGES 8
+#endif
+constexpr int MAC2_NT = GFX_MAC2_NT, MAC2_D = GFX_MAC2_STAGES;
+
+__device__ __forceinline__ void cmac2(float2& acc, const float2& x, const float2& h) {
+    acc.x = fmaf(x.x, h.x, acc.x); acc.x = fmaf(-x.y, h.y, acc.x);
+    acc.y = fmaf(x.x, h.y, acc.y); acc.y = fmaf(x.y, h.x, acc.y);
+}
+__device__ __forceinline__ void stg_stream2(float2* p, const float2& v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y));
+}
+
+// running pointers of one row walk (kept as serial updates so that the unrolled tile does not precompute 2 x PC
+// 64-bit addresses into registers)
+struct Mac2Walk {
+    const float2* xn;   // input block that enters the copy ring next
+    float2* yp;         // output block written next
+    float2* s_in;       // ring stage the next copy lands in
+    const float2* s_out;  // ring stage the next block is read from
+    float2* s_end;
+    int to_copy;        // input blocks not yet requested
+    int to_do;          // output blocks left
+};
+
+// U output blocks per loop body.  ring[k] = input block (newest - k) when the body starts; inside the body every operand
+// index is a compile-time constant; afterwards the ring moves U places (PC - U register moves per U x PC products).
+// The body is U x PC complex products = 4 U PC FFMA: 6 KB of code at U = 4, PC = 24 -- the fully unrolled PC x PC tile
+// (93 KB) ran out of the 32 KB instruction cache (profiles/r02_mac2_unrolled.txt: 45 % of the stalls no_inst).
+// VALID = ring entries that hold data (the ring fills up over the first PC blocks of a row: products with the
+// still-empty entries are left out of the peeled bodies -- 36 % of the multiplies at 24 partitions x 32 blocks).
+template <int PC, int U, int VALID>
+__device__ __forceinline__ void mac2_body(Mac2Walk& w, float2 (&h)[PC], float2 (&ring)[PC], size_t half2, int accumulate) {
+    float2 xn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        // one block enters the copy ring (D - 1 blocks ahead), one leaves it
+        if (w.to_copy > 0) cp_async_small<8>(w.s_in, w.xn);
+        cp_async_commit();
+        w.xn += half2; --w.to_copy;
+        w.s_in += MAC2_NT; if (w.s_in == w.s_end) w.s_in -= MAC2_D * MAC2_NT;
+        cp_async_wait<MAC2_D - 1>();
+        xn[u] = *w.s_out;   // (past the end of the row: stale data, its products are never stored)
+        w.s_out += MAC2_NT; if (w.s_out == w.s_end) w.s_out -= MAC2_D * MAC2_NT;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        float2 acc = make_float2(0.f, 0.f);
+        if (accumulate && u < w.to_do) acc = w.yp[(size_t)u * half2];
+#pragma unroll
+        for (int p = 0; p < PC; ++p) {
+            if (p > u && p - u - 1 >= VALID) continue;
+            cmac2(acc, p <= u ? xn[u - p] : ring[p - u - 1], h[p]);
+        }
+        if (u < w.to_do) stg_stream2(w.yp + (size_t)u * half2, acc);
+    }
+#pragma unroll
+    for (int k = PC - 1; k >= U; --k) ring[k] = ring[k - U];
+#pragma unroll
+    for (int k = 0; k < U && k < PC; ++k) ring[k] = xn[U - 1 - k];
+    w.yp += (size_t)U * half2;
+    w.to_do -= U;
+}
+// the bodies of a row: ring filling up (VALID = 0, U, 2U, ...), then the steady loop
+template <int PC, int U, int VALID>
+__device__ __forceinline__ void mac2_row(Mac2Walk& w, float2 (&h)[PC], float2 (&ring)[PC], size_t half2, int accumulate) {
+    if constexpr (VALID >= PC) {
+#pragma unroll 1
+        while (w.to_do > 0) mac2_body<PC, U, PC>(w, h, ring, half2, accumulate);
+    } else {
+        if (w.to_do > 0) {
+            mac2_body<PC, U, VALID>(w, h, ring, half2, accumulate);
+            mac2_row<PC, U, (VALID + U < PC ? VALID + U : PC)>(w, h, ring, half2, accumulate);
+        }
+    }
+}
+
+// grid: (2 * half / MAC2_NT, groups * c_out); group g covers batch items [b0 + g bpc, b0 + (g + 1) bpc) of the sweep, all
+// on the filter of its first item (the host guarantees bpc divides h_rep and b0 is a multiple of it)
+template <int PC>
+__global__ void __launch_bounds__(MAC2_NT, GFX_MAC2_MINB) fir_mac2_kernel(const float2* __restrict__ Xs, const float2* __restrict__ Hs,
+                                                                          float2* __restrict__ Ys, RowMap rm, int xrow0, int hrow0,
+                                                                          int b0, int nb, int bpc, int P, int p0, int nblk,
+                                                                          int half2, int accumulate) {
+    __shared__ float2 stage_all[MAC2_D * MAC2_NT];
+    float2* stage = stage_all + threadIdx.x;
+    const int e = blockIdx.x * MAC2_NT + threadIdx.x;
+    const int g = blockIdx.y / rm.c_out, c = blockIdx.y - g * rm.c_out;
+    const int bfirst = b0 + g * bpc;
+    int xr, hr;
+    rm.map(bfirst * rm.c_out + c, xr, hr);
+    const float2* H = Hs + ((size_t)(hr - hrow0) * P + p0) * half2 + e;
+    float2 h[PC], ring[PC];
+#pragma unroll
+    for (int p = 0; p < PC; ++p) h[p] = (p0 + p < P) ? __ldg(H + (size_t)p * half2) : make_float2(0.f, 0.f);
+    if (e == 0) {
+        // (A_0, A_N): two REAL bins, not a complex product -- lanes of warp 0 add them below
+#pragma unroll
+        for (int p = 0; p < PC; ++p) h[p] = make_float2(0.f, 0.f);
+    }
+    int blast = bfirst + bpc;
+    if (blast > b0 + nb) blast = b0 + nb;
+#pragma unroll 1
+    for (int b = bfirst; b < blast; ++b) {
+        rm.map(b * rm.c_out + c, xr, hr);
+        const float2* X = Xs + (size_t)(xr - xrow0) * nblk * half2 + e;
+        float2* Y = Ys + (size_t)((b - b0) * rm.c_out + c) * nblk * half2 + e;
+#pragma unroll
+        for (int p = 0; p < PC; ++p) ring[p] = make_float2(0.f, 0.f);
+        // prologue of the copy ring: input blocks 0 .. D-2 (one commit group each, empty past the end)
+        Mac2Walk w;
+        w.xn = X; w.yp = Y + (size_t)p0 * half2; w.s_in = stage; w.s_out = stage; w.s_end = stage + MAC2_D * MAC2_NT;
+        w.to_copy = nblk - p0; w.to_do = nblk - p0;
+#pragma unroll
+        for (int d = 0; d < MAC2_D - 1; ++d) {
+            if (w.to_copy > 0) cp_async_small<8>(w.s_in, w.xn);
+            cp_async_commit();
+            w.xn += half2; --w.to_copy; w.s_in += MAC2_NT;
+        }
+#ifdef GFX_MAC2_U
+        constexpr int U = GFX_MAC2_U;
+#else
+        constexpr int U = 4;  // (measured on B200 at 24 partitions: U = 4 1.655 ms per reverb-shape convolution, U = 8 1.737 ms)
+#endif
+        mac2_row<PC, U, 0>(w, h, ring, (size_t)half2, accumulate);
+        cp_async_wait<0>();
+        if (blockIdx.x == 0 && threadIdx.x < 32) {
+            // DC / Nyquist of every block (element 0): lanes over output blocks
+            __syncwarp();
+            const float2* X0 = X - e;
+            const float2* H0 = H - e;
+            float2* Y0 = Y - e;
+            for (int j = p0 + (int)threadIdx.x; j < nblk; j += 32) {
+                float a0 = 0.f, an = 0.f;
+                for (int p = 0; p < PC && p0 + p <= j && p0 + p < P; ++p) {
+                    const float2 xv = __ldg(X0 + (size_t)(j - p0 - p) * half2);
+                    const float2 hv = __ldg(H0 + (size_t)p * half2);
+                    a0 = fmaf(xv.x, hv.x, a0);
+                    an = fmaf(xv.y, hv.y, an);
+                }
+                // lane 0 (e == 0) wrote element 0 of block j in the main loop; the __syncwarp above orders that store
+                float2 v = Y0[(size_t)j * half2];
+                v.x += a0;
+                v.y += an;
+                Y0[(size_t)j * half2] = v;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // UPOLS step 3: inverse FFT of Y_j, keep the second half of the block
 template <int N, bool FAST>
 __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_inv_kernel(const float4* __restrict__ Ys, float* __restrict__ y,
@@ -916,7 +1085,10 @@ __global__ void fft_plan_pass_kernel(float2* tab, int M, int R) {
 }
 
 // ------------------------------------------------------------------ host side
-static int g_long_n = 8192;  // partition size of the long-filter path (tunable: gfx_fir_set_tuning)
+static int g_long_n = 4096;  // partition size of the long-filter path (tunable: gfx_fir_set_tuning).  Measured on B200 at the
+                             // BASELINE reverb shape (profiles/r02_*): 4096-point FFT kernels run 4 CTAs per SM (955 us for the three
+                             // FFT kernels vs 1350 us at 8192 points, 2 CTAs per SM); fir_mac2_kernel keeps the 24 partitions in one pass
+static int g_mac_form = 1;   // 0: fir_mac_kernel (<= 12 partitions per pass) when it applies; 1: fir_mac2_kernel
 static int g_mid_n = 8192;   // FFT size for 2048 < taps <= g_mid_n / 2 (longer single-partition filters: 16384)
 
 static int pick_fft_size(int Nh) {
@@ -992,6 +1164,7 @@ static int run_upols(const FirArgs& a) {
     if (!a.ws || a.ws_bytes < per_item) return GFX_ERR_WORKSPACE;
     long long chunk = (long long)(a.ws_bytes / per_item);
     if (chunk > a.batch) chunk = a.batch;
+    if (a.h_rep > 1 && chunk >= a.h_rep) chunk -= chunk % a.h_rep;  // sweeps of whole filter runs (fir_mac2_kernel walks a run per CTA)
     const size_t smem = (size_t)fft_smem_slots(N) * sizeof(pk2);
     static bool configured_dev[64] = {false};
     bool& configured = configured_dev[device_slot()];
@@ -1019,17 +1192,39 @@ static int run_upols(const FirArgs& a) {
         if (a.fast_x) fir_xspec_kernel<N, true><<<gx, fir_nt(N), smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk, a.plan);
         else fir_xspec_kernel<N, false><<<gx, fir_nt(N), smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk, a.plan);
         GFX_LAUNCH_CHECK();
-        const dim3 grid(half / MAC_NT, nb * c_out);
-        for (int p0 = 0; p0 < P; p0 += MAC_MAX_PC) {
-            const int pc = P - p0 < MAC_MAX_PC ? P - p0 : MAC_MAX_PC;
-            const int acc = p0 > 0;
+        if (g_mac_form == 0 && P <= MAC_MAX_PC) {
+            const dim3 grid(half / MAC_NT, nb * c_out);
+            for (int p0 = 0; p0 < P; p0 += MAC_MAX_PC) {
+                const int pc = P - p0 < MAC_MAX_PC ? P - p0 : MAC_MAX_PC;
+                const int acc = p0 > 0;
 #define GFX_MAC_CASE(PCV) case PCV: launch_mac<PCV>(grid, a.stream, Xs, Hs, Ys, rm, xrow0, hrow0, row0, P, p0, (int)nblk, half, acc); break;
-            switch (pc) {
-                GFX_MAC_CASE(1) GFX_MAC_CASE(2) GFX_MAC_CASE(3) GFX_MAC_CASE(4) GFX_MAC_CASE(5) GFX_MAC_CASE(6)
-                GFX_MAC_CASE(7) GFX_MAC_CASE(8) GFX_MAC_CASE(9) GFX_MAC_CASE(10) GFX_MAC_CASE(11) GFX_MAC_CASE(12)
-            }
+                switch (pc) {
+                    GFX_MAC_CASE(1) GFX_MAC_CASE(2) GFX_MAC_CASE(3) GFX_MAC_CASE(4) GFX_MAC_CASE(5) GFX_MAC_CASE(6)
+                    GFX_MAC_CASE(7) GFX_MAC_CASE(8) GFX_MAC_CASE(9) GFX_MAC_CASE(10) GFX_MAC_CASE(11) GFX_MAC_CASE(12)
+                }
 #undef GFX_MAC_CASE
-            GFX_LAUNCH_CHECK();
+                GFX_LAUNCH_CHECK();
+            }
+        } else {
+            // (walking the batch items that share a filter in one CTA -- bpc = h_rep -- was measured: slower; the
+            //  shared filter spectra are L2 hits anyway)
+            const int bpc = 1;
+            const int groups = (nb + bpc - 1) / bpc;
+            {
+                // one complex bin per thread: up to 24 partitions per pass, inputs through a cp.async ring
+                const dim3 grid(2 * half / MAC2_NT, groups * c_out);
+                for (int p0 = 0; p0 < P; p0 += MAC2_MAX_PC) {
+                    const int rem = P - p0 < MAC2_MAX_PC ? P - p0 : MAC2_MAX_PC;
+                    const int pc = rem <= 4 ? 4 : (rem <= 8 ? 8 : (rem <= 12 ? 12 : (rem <= 16 ? 16 : (rem <= 20 ? 20 : 24))));
+                    const int acc = p0 > 0;
+#define GFX_MAC2_CASE(PCV) case PCV: fir_mac2_kernel<PCV><<<grid, MAC2_NT, 0, a.stream>>>((const float2*)Xs, (const float2*)Hs, (float2*)Ys, rm, xrow0, hrow0, (int)b0, nb, bpc, P, p0, (int)nblk, 2 * half, acc); break;
+                    switch (pc) {
+                        GFX_MAC2_CASE(4) GFX_MAC2_CASE(8) GFX_MAC2_CASE(12) GFX_MAC2_CASE(16) GFX_MAC2_CASE(20) GFX_MAC2_CASE(24)
+                    }
+#undef GFX_MAC2_CASE
+                    GFX_LAUNCH_CHECK();
+                }
+            }
         }
         const unsigned gy = (unsigned)(nb * c_out * nblk);
         if (a.fast_x) fir_inv_kernel<N, true><<<gy, fir_nt(N), smem, a.stream>>>(Ys, a.y, row0, a.L, (int)nblk, a.shift, a.plan);
@@ -1128,6 +1323,12 @@ int gfx_fir_set_long_mode(int mode, int lookahead) {
     if (lookahead < 0 || lookahead > 16) return GFX_ERR_INVALID;
     gfx::g_long_mode = mode;
     if (lookahead) gfx::g_upols_d = lookahead;
+    return GFX_OK;
+}
+
+int gfx_fir_set_mac_form(int form) {
+    if (form != 0 && form != 1) return GFX_ERR_INVALID;
+    gfx::g_mac_form = form;
     return GFX_OK;
 }
 

@@ -113,6 +113,11 @@ GFX_API int gfx_fir_set_tuning(int long_n, int mid_n);
  * filter has <= 12 partitions of 8192 taps).  Affects the
  * workspace size: query it again afterwards. */
 GFX_API int gfx_fir_set_long_mode(int mode, int lookahead); /* lookahead: pipeline depth in batch items (0 keeps it) */
+/* per-bin multiply-accumulate of the long-filter path: 1 (default) = fir_mac2_kernel (one complex bin per thread, up to 24
+ * partitions per pass, inputs through a cp.async ring, batch items that share a filter walked by one CTA); 0 = fir_mac_kernel (<= 12
+ * partitions per pass, the round-1 kernel, used when the filter has <= 12 partitions; kept for A/B measurements).
+ * The two differ in summation order only (~1e-7 relative). */
+GFX_API int gfx_fir_set_mac_form(int form);
 /* Same convolution (causal) with the filter given as the UN-NORMALISED impulse response of
  * gfx_reverb_ir_f32 (mode 0: mid/side rows, ms_to_lr = 0; mode 3: left/right rows, ms_to_lr = 1) plus the
  * energies of its raw mid/side rows: normalize_impulse (processors/reverb.py:215-228, core/utils.py:14-18)

@@ -352,14 +352,44 @@ def test_fir_long_filter_pipelined_launch_matches():
     x1 = torch.randn(20, 1, 30000, device="cuda")
     h4 = torch.randn(5, 2, 40000, device="cuda") / 200.0
     try:
+        assert L_.gfx_fir_set_tuning(8192, 0) == 0  # (the pipelined launch exists for 8192-tap partitions)
         ref = [F_.fir_conv(x, h), F_.fir_conv(x1, h), F_.fir_conv(x, h4, h_repeat=4)]
+        assert L_.gfx_fir_set_mac_form(0) == 0
+        ref0 = [F_.fir_conv(x, h), F_.fir_conv(x1, h), F_.fir_conv(x, h4, h_repeat=4)]
         assert L_.gfx_fir_set_long_mode(1, 0) == 0
         out = [F_.fir_conv(x, h), F_.fir_conv(x1, h), F_.fir_conv(x, h4, h_repeat=4)]
     finally:
         L_.gfx_fir_set_long_mode(0, 0)
-    for a, b in zip(out, ref):
-        assert torch.equal(a, b)
+        L_.gfx_fir_set_mac_form(1)
+        L_.gfx_fir_set_tuning(4096, 0)
+    for a, b, c in zip(out, ref, ref0):
+        assert torch.equal(a, c)              # the pipelined launch and the sweeps with fir_mac_kernel agree bit for bit
+        assert rel_l2(a.cpu(), b.cpu()) < 2e-6  # fir_mac_split_kernel sums the partitions in another order
     assert_close(out[0][:3].cpu(), O.convolve(x[:3].cpu().double(), h[:3].cpu().double(), "causal").float(), "pipe", tol=2e-5)
+
+
+@pytest.mark.parametrize("Nh,L,hrep", [(96000, 131072, 1), (60000, 50001, 1), (20000, 9000, 3), (120000, 70000, 2), (16385, 4096, 1)])
+def test_fir_long_filter_partition_sizes_vs_oracle(Nh, L, hrep):
+    """Long filters (> 16384 taps) on every partition size the engine offers (4096 = default: up to 24 partitions per
+    multiply-accumulate pass, more in accumulate groups; 8192; 16384), shared filters walked by one CTA (h_repeat),
+    against the float64 oracle."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.functional as F_
+    from grafx_b200 import _cabi
+
+    g = torch.Generator().manual_seed(Nh + L)
+    B = 2 * hrep
+    x = torch.randn(B, 2, L, generator=g)
+    h = torch.randn(B // hrep, 2, Nh, generator=g) / Nh ** 0.5
+    ref = O.convolve(x.double(), h.double().repeat_interleave(hrep, 0), "causal").float()
+    L_ = _cabi.lib()
+    try:
+        for n in (4096, 8192, 16384):
+            assert L_.gfx_fir_set_tuning(n, 0) == 0
+            y = F_.fir_conv(x.cuda(), h.cuda(), h_repeat=hrep).cpu()
+            assert_close(y, ref, f"long n={n}", tol=2e-5)
+    finally:
+        L_.gfx_fir_set_tuning(4096, 0)
 
 
 def test_cfg3b_firfilter_full_size_impulse_and_linearity():

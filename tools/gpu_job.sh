@@ -1,9 +1,9 @@
 #!/bin/bash
-# scratch driver for one gpurun call (edited per call); outputs under gpurun_out/
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/r02_gpu.txt 2>&1
-timeout 900 python -m pytest tests/test_fullsize_gpu.py -q -m gpu 2>&1 | tail -40 > gpurun_out/r02_t1.log
-timeout 900 python -m pytest tests -q -m gpu -x --deselect tests/test_fullsize_gpu.py 2>&1 | tail -25 > gpurun_out/r02_tests_all.log
-timeout 600 python bench.py > gpurun_out/r02_bench1.json 2> gpurun_out/r02_bench1.err
-tail -5 gpurun_out/r02_t1.log; tail -5 gpurun_out/r02_tests_all.log; tail -c 1500 gpurun_out/r02_bench1.err; head -c 3000 gpurun_out/r02_bench1.json
+rm -f gpurun_out/r02_conv_time.log
+timeout 900 python -m pytest tests/test_parity_gpu.py -q -m gpu -x -k "fir or reverb or render or conv" 2>&1 | tail -15 > gpurun_out/r02_t2.log
+for lib in libgrafx_b200.so libgfx_u4.so; do
+GRAFX_B200_LIB=$PWD/grafx_b200/lib/$lib timeout 300 python tools/conv_time.py >> gpurun_out/r02_conv_time.log 2>&1
+done
+cat gpurun_out/r02_t2.log gpurun_out/r02_conv_time.log
