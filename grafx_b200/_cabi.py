@@ -49,6 +49,7 @@ SIGNATURES = {
     "gfx_biquad_cascade_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_ll, c_void_p, c_size_t, c_void_p]),
     "gfx_dynamics_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gfx_dynamics_set_tuning": (c_int, [c_int]),
     "gfx_dynamics_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, ctypes.POINTER(DynamicsStage), c_int,
                                  c_int, c_void_p, c_size_t, c_void_p]),
     "gfx_envelope_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
@@ -59,6 +60,8 @@ SIGNATURES = {
     "gfx_fir_conv_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_ll, c_int, c_int]),
     "gfx_fir_conv_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_int, c_int, c_int, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),
+    "gfx_fir_filter_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_int, c_void_p, c_void_p, c_size_t,
+                                   c_void_p]),
     "gfx_fir_set_tuning": (c_int, [c_int, c_int]),
     "gfx_fir_set_long_mode": (c_int, [c_int, c_int]),
     "gfx_fir_set_mac_form": (c_int, [c_int]),

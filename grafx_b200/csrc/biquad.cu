@@ -168,12 +168,10 @@ __global__ void __launch_bounds__(128) cascade_x2_tables_kernel(const float* __r
         out[34 * 4 + 0] = (double)nb0; out[34 * 4 + 1] = (double)nb1; out[34 * 4 + 2] = (double)nb2; out[34 * 4 + 3] = -(double)na1;
         outf[33] = make_float4((float)out[33 * 4 + 0], (float)out[33 * 4 + 1], (float)out[33 * 4 + 2], (float)out[33 * 4 + 3]);
         out[36 * 4 + 0] = -(double)na2; out[36 * 4 + 1] = growth > X2_ILL_GROWTH ? 1.0 : 0.0; out[36 * 4 + 2] = 0.0; out[36 * 4 + 3] = 0.0;
-#ifdef GFX_X2_LEAN
         // fp32 copies of the five coefficients + the flag, and a zero matrix (the scan identity for lanes below the stride)
         outf[35] = make_float4(nb0, nb1, nb2, -na1);
         outf[36] = make_float4(-na2, growth > X2_ILL_GROWTH ? 1.f : 0.f, 0.f, 0.f);
         outf[37] = make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
     }
 }
 
@@ -544,17 +542,11 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
 #pragma unroll
         for (int k = 0; k < (KT > 0 ? KT : K); ++k) {
             const double* pk = tab + (size_t)k * X2_TAB * 4;
-#ifdef GFX_X2_LEAN
-            // (experiment, off by default: float copies of the coefficients instead of five double loads + conversions)
+            // float copies of the coefficients in the table (no double loads + conversions in the section loop)
             const float4 cf = reinterpret_cast<const float4*>(pk + 37 * 4)[35];
             const float2 cg = *reinterpret_cast<const float2*>(reinterpret_cast<const float4*>(pk + 37 * 4) + 36);
             const pk2 B0 = pk_dup(cf.x), B1 = pk_dup(cf.y), B2 = pk_dup(cf.z);
             const pk2 NA1 = pk_dup(cf.w), NA2 = pk_dup(cg.x);
-#else
-            const float b0f = (float)pk[34 * 4 + 0], b1f = (float)pk[34 * 4 + 1], b2f = (float)pk[34 * 4 + 2];
-            const pk2 B0 = pk_dup(b0f), B1 = pk_dup(b1f), B2 = pk_dup(b2f);
-            const pk2 NA1 = pk_dup((float)pk[34 * 4 + 3]), NA2 = pk_dup((float)pk[36 * 4 + 0]);
-#endif
 
             // 1. feed-forward part in place (descending, so the taps are still inputs) with ZERO input history:
             //    the zero-state response below is then a genuine filter output (bounded by the filter gain), not
@@ -580,11 +572,7 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
             // 3. carries: c = z + N (u[-1], u[-2]), the scan of s' = M s + c over the 32 lanes, the warps stitched through
             //    shared memory, the item's incoming state from the previous item of the row.  Ill-conditioned sections
             //    (table flag) in double, the others in packed fp32; the hand-over words are the same for both.
-#ifdef GFX_X2_LEAN
             const bool ill = cg.y != 0.f;
-#else
-            const bool ill = pk[36 * 4 + 1] != 0.0;
-#endif
             const float4* pf = reinterpret_cast<const float4*>(pk + 37 * 4);
             const int seq = seq_base + k + 1;
             double cAx = 0.0, cAy = 0.0, cBx = 0.0, cBy = 0.0;  // double path: inclusive carries of the lane's two chunks
@@ -627,12 +615,7 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
                 for (int j = 0; j < 5; ++j) {
                     const int d = 1 << j;
                     pk2 p1 = pk_shfl_up(c1, d), p2 = pk_shfl_up(c2, d);
-#ifdef GFX_X2_LEAN
                     const float4 m = pf[lane < d ? 37 : d];  // zero matrix: lanes below the stride keep their carry
-#else
-                    if (lane < d) { p1 = 0ull; p2 = 0ull; }
-                    const float4 m = pf[d];
-#endif
                     c1 = pk_fma(pk_dup(m.x), p1, pk_fma(pk_dup(m.y), p2, c1));
                     c2 = pk_fma(pk_dup(m.z), p1, pk_fma(pk_dup(m.w), p2, c2));
                 }

@@ -93,7 +93,7 @@ struct KneeConst {      // 16 floats
 constexpr int DYN_SC_FLOATS = sizeof(SmootherConst) / 4, DYN_KC_FLOATS = sizeof(KneeConst) / 4;
 constexpr int DYN_ROW_FLOATS = DYN_MAX_STAGES * (2 * DYN_SC_FLOATS + DYN_KC_FLOATS);  // per-row table
 
-template <int NT>
+template <int NT, bool RO>
 struct DynCtx {
     static constexpr int S = 32;
     static constexpr int NW = NT / 32;
@@ -121,22 +121,22 @@ struct DynCtx {
 // with fewer rows than resident CTAs the extra CTAs only queue up behind the tile chain of a row.  So: the small CTA
 // when every resident CTA can own a different row, the large one otherwise.
 constexpr int DYN_SCAN_NT = 256, DYN_SCAN_NT_SMALL = 128, DYN_SCAN_CTAS_SMALL = 6;
-template <int NT>
-__device__ __forceinline__ constexpr bool row_owner() { return NT == 64; }
+static int g_dyn_scan_nt = 0;  // 0: by row count (below); 32 | 64 | 128 | 256: forced (gfx_dynamics_set_tuning)
+// RO: the CTA owns whole rows (ballistics); otherwise one (tile, row) item at a time (scan variant)
 
-template <int NT>
-__device__ __forceinline__ float* state_slots(const DynCtx<NT>& cx, int t_idx) {
-    return cx.s_state + (row_owner<NT>() ? (t_idx & 1) * 2 * DYN_MAX_STAGES : 0);
+template <int NT, bool RO>
+__device__ __forceinline__ float* state_slots(const DynCtx<NT, RO>& cx, int t_idx) {
+    return cx.s_state + (RO ? (t_idx & 1) * 2 * DYN_MAX_STAGES : 0);
 }
 
-template <int NT>
-__device__ __forceinline__ void ensure_state(DynCtx<NT>& cx, const DynParams& p) {
+template <int NT, bool RO>
+__device__ __forceinline__ void ensure_state(DynCtx<NT, RO>& cx, const DynParams& p) {
     if (cx.have_state) return;
     cx.have_state = true;
     const int ns2 = 2 * p.n_stages;
     if (cx.warp == 0) {
         if (cx.t_idx > 0) {
-            if constexpr (!row_owner<NT>()) {
+            if constexpr (!RO) {
                 if (cx.lane == 0) chain_wait(p.flags + cx.row, cx.t_idx);
                 __syncwarp();
                 if (cx.lane < ns2) cx.s_state[cx.lane] = __ldcg(p.state + (size_t)cx.row * ns2 + cx.lane);
@@ -144,23 +144,23 @@ __device__ __forceinline__ void ensure_state(DynCtx<NT>& cx, const DynParams& p)
         } else if (cx.lane < ns2) {
             const StageDesc& sd = p.st[cx.lane >> 1];
             const int kind = (cx.lane & 1) ? sd.post.kind : sd.pre.kind;
-            state_slots<NT>(cx, 0)[cx.lane] = kind == 2 ? 1.f : 0.f;  // ballistics starts from zi = 1
+            state_slots<NT, RO>(cx, 0)[cx.lane] = kind == 2 ? 1.f : 0.f;  // ballistics starts from zi = 1
         }
     }
     __syncthreads();
 }
 
 // the state a smoother leaves for the next tile of the row
-template <int NT>
-__device__ __forceinline__ void leave_state(DynCtx<NT>& cx, const DynParams& p, int slot, float value) {
+template <int NT, bool RO>
+__device__ __forceinline__ void leave_state(DynCtx<NT, RO>& cx, const DynParams& p, int slot, float value) {
     if (cx.t_idx + 1 >= p.tiles) return;
-    if constexpr (row_owner<NT>()) state_slots<NT>(cx, cx.t_idx + 1)[slot] = value;
+    if constexpr (RO) state_slots<NT, RO>(cx, cx.t_idx + 1)[slot] = value;
     else p.state[(size_t)cx.row * 2 * p.n_stages + slot] = value;
 }
 
 // ---- truncated one-pole smoother on the register chunk u[32]; `slot` = index into the row state
-template <int NT, typename LagFn>
-__device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, float (&u)[32],
+template <int NT, bool RO, typename LagFn>
+__device__ __forceinline__ void smooth_iir(DynCtx<NT, RO>& cx, const DynParams& p, float (&u)[32],
                                            const SmootherDesc& sm, int slot, LagFn lag_input) {
     constexpr int S = 32, NW = NT / 32;
     const SmootherConst& c = cx.sc[slot];
@@ -201,7 +201,7 @@ __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, f
     if (cx.lane == 31) wt[cx.warp] = z;
     ensure_state(cx, p);  // (first stateful op of the tile also syncs here)
     __syncthreads();
-    float s = state_slots<NT>(cx, cx.t_idx)[slot];
+    float s = state_slots<NT, RO>(cx, cx.t_idx)[slot];
     for (int q = 0; q < cx.warp; ++q) s = fmaf(aW, s, wt[q]);
     float ex = __shfl_up_sync(0xffffffffu, z, 1);
     if (cx.lane == 0) ex = 0.f;
@@ -212,7 +212,7 @@ __device__ __forceinline__ void smooth_iir(DynCtx<NT>& cx, const DynParams& p, f
         y = fmaf(alpha, y, u[i]);
         u[i] = fmaxf(y * oma, 0.f);
     }
-    if (cx.tid == NT - 1) leave_state<NT>(cx, p, slot, y);
+    if (cx.tid == NT - 1) leave_state<NT, RO>(cx, p, slot, y);
 }
 
 // The walk itself: NT rows of 32 samples.  Every instruction of the walking lane costs a full warp slot of its
@@ -278,8 +278,8 @@ __device__ __forceinline__ float ballistics_walk(float4* wa, const float4* wr, f
 // per step, and halves beyond that), so (a) the products at*u and rt*u are formed by all threads beforehand: the
 // walk issues 3 instructions per sample; (b) the walking lane is lane 0 of the warp chosen from the hardware
 // warp slot so that the walkers of the CTAs resident on an SM spread over all four sub-partitions.
-template <int NT>
-__device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParams& p, float (&u)[32],
+template <int NT, bool RO>
+__device__ __forceinline__ void smooth_ballistics(DynCtx<NT, RO>& cx, const DynParams& p, float (&u)[32],
                                                   const SmootherDesc& sm, int slot) {
     const float at = cx.sc[slot].at, rt = cx.sc[slot].rt;
     float4* wa = cx.work4;            // at * u, overwritten by y
@@ -293,7 +293,7 @@ __device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParam
     ensure_state(cx, p);
     __syncthreads();
     if (cx.tid == cx.walker) {
-        const float y0 = state_slots<NT>(cx, cx.t_idx)[slot];
+        const float y0 = state_slots<NT, RO>(cx, cx.t_idx)[slot];
         const float yend = (at >= rt) ? ballistics_walk<NT, true>(wa, wr, y0, at, rt) : ballistics_walk<NT, false>(wa, wr, y0, at, rt);
         (void)yend;
     }
@@ -303,7 +303,7 @@ __device__ __forceinline__ void smooth_ballistics(DynCtx<NT>& cx, const DynParam
         const float4 v = wa[swz_unit(cx.tid, c)];
         u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
     }
-    if (cx.tid == NT - 1) leave_state<NT>(cx, p, slot, u[31]);  // the state after the last sample of a FULL tile
+    if (cx.tid == NT - 1) leave_state<NT, RO>(cx, p, slot, u[31]);  // the state after the last sample of a FULL tile
 }
 
 // bare SFU ops (no denormal / range fix-up code around them: the arguments here are >= 1e-5 resp. bounded)
@@ -460,14 +460,18 @@ __global__ void dynamics_tables_kernel(const DynParams p, float* __restrict__ ta
     for (int i = 0; i < DYN_KC_FLOATS; ++i) dst[i] = reinterpret_cast<const float*>(&k)[i];
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_NT_SMALL ? DYN_SCAN_CTAS_SMALL : 8))) dynamics_kernel(const DynParams p) {
+__host__ __device__ constexpr int dyn_min_ctas(int NT, bool RO) {
+    return RO ? 8 : (NT >= 256 ? 3 : (768 / NT > 24 ? 24 : 768 / NT));  // scan variant: 24 warps per SM (80 registers)
+}
+// ENV: envelope mode (gfx_envelope_f32) -- a separate instantiation so that the processors' kernel carries none of it
+template <int NT, bool RO, bool ENV>
+__global__ void __launch_bounds__(NT, dyn_min_ctas(NT, RO)) dynamics_kernel(const DynParams p) {
     constexpr int S = 32, TILE = NT * S, NW = NT / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    DynCtx<NT> cx;
+    DynCtx<NT, RO> cx;
     cx.xs4 = reinterpret_cast<float4*>(smem_raw);
     cx.work4 = cx.xs4 + (size_t)p.C * NT * 8;
-    float* consts = reinterpret_cast<float*>(cx.work4 + (NT == 64 ? (size_t)NT * 16 : 0));  // [DYN_ROW_FLOATS]
+    float* consts = reinterpret_cast<float*>(cx.work4 + (RO ? (size_t)NT * 16 : 0));  // [DYN_ROW_FLOATS]
     cx.sc = reinterpret_cast<const SmootherConst*>(consts);
     cx.kc = reinterpret_cast<const KneeConst*>(consts + 2 * DYN_MAX_STAGES * DYN_SC_FLOATS);
     cx.wt = consts + DYN_ROW_FLOATS;
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
         if (cx.tid == 0) {
             unsigned wid;
             asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-            sh_walker = (NT == 64) ? (int)(((wid >> 2) & 1u) * 32u) : 0;
+            sh_walker = RO ? (int)(((wid >> 2) & 1u) * 32u) : 0;
         }
         __syncthreads();
         cx.walker = sh_walker;
@@ -498,9 +502,9 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
         const unsigned int item = sh_item;
         if (item >= p.n_items) break;
         // scan variant: item = (tile, row), one tile; ballistics variant: item = row, all its tiles in order
-        const int t_first = row_owner<NT>() ? 0 : (int)(item / (unsigned)p.batch);
-        const int t_last = row_owner<NT>() ? p.tiles - 1 : t_first;
-        cx.row = row_owner<NT>() ? (int)item : (int)(item - (unsigned)t_first * (unsigned)p.batch);
+        const int t_first = RO ? 0 : (int)(item / (unsigned)p.batch);
+        const int t_last = RO ? p.tiles - 1 : t_first;
+        cx.row = RO ? (int)item : (int)(item - (unsigned)t_first * (unsigned)p.batch);
         for (int tt = t_first; tt <= t_last; ++tt) {
         if (tt > t_first) __syncthreads();  // the previous tile has left shared memory
         cx.t_idx = tt;
@@ -524,12 +528,17 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
             // interior tile: unit g = tid + j NT sits at swz_unit(g >> 3, g & 7) = swz_unit(tid >> 3, tid & 7) + j NT
             // (NT is a multiple of 64), so the copies are a constant stride apart
             const uint32_t d0 = smem_u32(cx.xs4 + swz_unit(cx.tid >> 3, cx.tid & 7));
+            const uint32_t d1 = smem_u32(cx.xs4 + ((cx.tid >> 3) << 3 | (((cx.tid & 7) ^ ((cx.tid >> 3) & 7)) ^ 4)));  // odd j at NT = 32
             for (int c = 0; c < C; ++c) {
                 const float4* src = reinterpret_cast<const float4*>(xrow + (size_t)c * p.L + cx.t0) + cx.tid;
                 const uint32_t dc = d0 + (uint32_t)c * (NT * 128);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dc + (uint32_t)j * (NT * 16)), "l"(src + j * NT));
+                for (int j = 0; j < 8; ++j) {
+                    // (NT = 32: the row parity, hence the swizzle, alternates with j: unit ^ 4 on odd j)
+                    const uint32_t dj = (NT % 64 == 0 || (j & 1) == 0) ? dc + (uint32_t)j * (NT * 16)
+                                                                        : d1 + (uint32_t)c * (NT * 128) + (uint32_t)j * (NT * 16);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dj), "l"(src + j * NT));
+                }
             }
             cp_async_commit();
             cp_async_wait<0>();
@@ -567,7 +576,7 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
             // energy of the signal entering this stage (earlier stages already applied their gain in place)
 #pragma unroll
             for (int i = 0; i < S; ++i) u[i] = 0.f;
-            if (p.envelope && p.detect != 0) {
+            if (ENV && p.detect != 0) {
                 for (int c = 0; c < C; ++c) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -600,7 +609,7 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
                     // lagged energy re-derived from x itself (read-only input): no history buffer
                     auto lag = [&](long long pos) {
                         float e = 0.f;
-                        const int det = p.envelope ? p.detect : 0;
+                        const int det = ENV ? p.detect : 0;
                         for (int c = 0; c < C; ++c) {
                             const float v = xrow[(size_t)c * p.L + pos];
                             e = det == 0 ? fmaf(v, v, e) : (det == 1 ? e + fabsf(v) : v);
@@ -609,17 +618,17 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
                     };
                     SmootherDesc sm = sd.pre;
                     sm.hist = nullptr;
-                    smooth_iir<NT>(cx, p, u, sm, 2 * d, lag);
+                    smooth_iir<NT, RO>(cx, p, u, sm, 2 * d, lag);
                 } else {
                     const float* hr = sd.pre.hist + (size_t)cx.row * (size_t)p.L;
                     auto lag = [&](long long pos) { return __ldcg(hr + pos); };
-                    smooth_iir<NT>(cx, p, u, sd.pre, 2 * d, lag);
+                    smooth_iir<NT, RO>(cx, p, u, sd.pre, 2 * d, lag);
                 }
             } else if (sd.pre.kind == 2) {
-                if constexpr (NT == 64) smooth_ballistics<NT>(cx, p, u, sd.pre, 2 * d);  // (ballistics launches use NT = 64)
+                if constexpr (RO) smooth_ballistics<NT, RO>(cx, p, u, sd.pre, 2 * d);  // (ballistics launches use NT = 64)
             }
 
-            if (p.envelope) {
+            if constexpr (ENV) {
                 // stand-alone smoother / envelope follower: the (log of the) smoothed detector signal is the output
                 if (p.env_log) {
 #pragma unroll
@@ -628,8 +637,7 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
                     cx.xs4[swz_unit(cx.tid, q)] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
-                break;
-            }
+            } else {
             const int knee_mode = sd.kind * 3 + (sd.knee == 3 ? 1 : sd.knee);  // 3: quadratic regions, own constants
             if (sd.post.kind == 0) {
                 knee_gain(u, cx.kc[d], knee_mode);
@@ -642,9 +650,9 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
                 if (sd.post.kind == 1) {
                     const float* hr = sd.post.hist ? sd.post.hist + (size_t)cx.row * (size_t)p.L : nullptr;
                     auto lag = [&](long long pos) { return __ldcg(hr + pos); };
-                    smooth_iir<NT>(cx, p, u, sd.post, 2 * d + 1, lag);
+                    smooth_iir<NT, RO>(cx, p, u, sd.post, 2 * d + 1, lag);
                 } else {
-                    if constexpr (NT == 64) smooth_ballistics<NT>(cx, p, u, sd.post, 2 * d + 1);
+                    if constexpr (RO) smooth_ballistics<NT, RO>(cx, p, u, sd.post, 2 * d + 1);
                 }
                 if (sd.log_domain) {
 #pragma unroll
@@ -661,22 +669,24 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
                     *pv = v;
                 }
             }
+            }  // !ENV
         }
-        if constexpr (!row_owner<NT>()) {
+        if constexpr (!RO) {
             if (cx.tid == NT - 1 && cx.t_idx + 1 < p.tiles && cx.have_state) chain_publish(p.flags + cx.row, cx.t_idx + 1);
         }
 
         // ---- store coalesced
         __syncthreads();
-        const int C_out = p.envelope ? 1 : C;
-        if (p.envelope) yrow = p.y + (size_t)cx.row * (size_t)p.L;
+        const int C_out = ENV ? 1 : C;
+        if (ENV) yrow = p.y + (size_t)cx.row * (size_t)p.L;
         for (int c = 0; c < C_out; ++c) {
             float* yr = yrow + (size_t)c * p.L;
             if (full_tile) {
                 float4* dst = reinterpret_cast<float4*>(yr + cx.t0) + cx.tid;
                 const float4* sv = cx.xs4 + (size_t)c * NT * 8 + swz_unit(cx.tid >> 3, cx.tid & 7);
+                const float4* sv1 = cx.xs4 + (size_t)c * NT * 8 + ((cx.tid >> 3) << 3 | (((cx.tid & 7) ^ ((cx.tid >> 3) & 7)) ^ 4));
 #pragma unroll
-                for (int j = 0; j < 8; ++j) stg_stream(dst + j * NT, sv[j * NT]);
+                for (int j = 0; j < 8; ++j) stg_stream(dst + j * NT, (NT % 64 == 0 || (j & 1) == 0) ? sv[j * NT] : sv1[j * NT]);
             } else if (p.aligned) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -699,9 +709,9 @@ __global__ void __launch_bounds__(NT, (NT == DYN_SCAN_NT ? 3 : (NT == DYN_SCAN_N
     }
 }
 
-static size_t dyn_smem_bytes(int NT, int C) {
-    // two scratch tiles (at*u, rt*u) are only used by the ballistics variant (NT == 64)
-    return (size_t)(C + (NT == 64 ? 2 : 0)) * NT * 128 +
+static size_t dyn_smem_bytes(int NT, int C, bool RO) {
+    // two scratch tiles (at*u, rt*u) are only used by the ballistics (row owner) variant
+    return (size_t)(C + (RO ? 2 : 0)) * NT * 128 +
            (size_t)(DYN_ROW_FLOATS + 2 * (NT / 32) + 4 * DYN_MAX_STAGES) * sizeof(float) + 64;
 }
 
@@ -713,11 +723,11 @@ static size_t dyn_workspace_bytes(int batch, int n_stages) {
     return dyn_tables_offset(batch, n_stages) + (size_t)batch * DYN_ROW_FLOATS * sizeof(float);
 }
 
-template <int NT>
+template <int NT, bool RO, bool ENV = false>
 static int launch_dynamics(DynParams& p, cudaStream_t stream) {
-    const size_t smem = dyn_smem_bytes(NT, p.C);
+    const size_t smem = dyn_smem_bytes(NT, p.C, RO);
     if (smem > (size_t)device_info().max_smem_optin) return GFX_ERR_UNSUPPORTED;
-    auto kern = dynamics_kernel<NT>;
+    auto kern = dynamics_kernel<NT, RO, ENV>;
     static size_t configured_dev[64] = {0};
     size_t& configured = configured_dev[device_slot()];
     if (smem > configured) {
@@ -736,9 +746,29 @@ static int launch_dynamics(DynParams& p, cudaStream_t stream) {
     return GFX_OK;
 }
 
+static int scan_nt_for(int batch) {
+    if (g_dyn_scan_nt) return g_dyn_scan_nt;
+    return batch >= device_info().sm_count * DYN_SCAN_CTAS_SMALL ? DYN_SCAN_NT_SMALL : DYN_SCAN_NT;
+}
+template <bool ENV>
+static int launch_scan(int NT, DynParams& p, cudaStream_t st) {
+    switch (NT) {
+        case 32: return launch_dynamics<32, false, ENV>(p, st);
+        case 64: return launch_dynamics<64, false, ENV>(p, st);
+        case 128: return launch_dynamics<128, false, ENV>(p, st);
+        default: return launch_dynamics<256, false, ENV>(p, st);
+    }
+}
+
 }  // namespace gfx
 
 extern "C" {
+
+int gfx_dynamics_set_tuning(int scan_threads) {
+    if (scan_threads != 0 && scan_threads != 32 && scan_threads != 64 && scan_threads != 128 && scan_threads != 256) return GFX_ERR_INVALID;
+    gfx::g_dyn_scan_nt = scan_threads;
+    return GFX_OK;
+}
 
 size_t gfx_dynamics_workspace_bytes(int batch, int n_stages) { return gfx::dyn_workspace_bytes(batch, n_stages); }
 
@@ -772,8 +802,7 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
         o.post = SmootherDesc{s.gain_smoother, s.z_alpha_post, s.hist_post};
         any_ballistics |= (s.energy_smoother == 2 || s.gain_smoother == 2);
     }
-    const bool small_cta = batch >= device_info().sm_count * DYN_SCAN_CTAS_SMALL;
-    const int NT = any_ballistics ? 64 : (small_cta ? DYN_SCAN_NT_SMALL : DYN_SCAN_NT);
+    const int NT = any_ballistics ? 64 : scan_nt_for(batch);
     const long long tile = (long long)NT * 32;
     const long long tiles_ll = (L + tile - 1) / tile;
     if ((long long)batch * tiles_ll > 0x7fff0000LL) return GFX_ERR_UNSUPPORTED;
@@ -793,8 +822,8 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
     GFX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256 + flags_bytes, (cudaStream_t)stream));
     p.tables = (float*)(w + dyn_tables_offset(batch, n_stages));
     cudaStream_t st = (cudaStream_t)stream;
-    if (any_ballistics) return launch_dynamics<64>(p, st);
-    return small_cta ? launch_dynamics<DYN_SCAN_NT_SMALL>(p, st) : launch_dynamics<DYN_SCAN_NT>(p, st);
+    if (any_ballistics) return launch_dynamics<64, true>(p, st);
+    return launch_scan<false>(NT, p, st);
 }
 
 int gfx_envelope_f32(const float* x, float* y, int batch, int channels, long long L, int smoother, const float* z,
@@ -811,8 +840,7 @@ int gfx_envelope_f32(const float* x, float* y, int batch, int channels, long lon
     o.pre = SmootherDesc{smoother, z, nullptr};
     o.post = SmootherDesc{0, nullptr, nullptr};
     const bool ball = smoother == 2;
-    const bool small_cta = batch >= device_info().sm_count * DYN_SCAN_CTAS_SMALL;
-    const int NT = ball ? 64 : (small_cta ? DYN_SCAN_NT_SMALL : DYN_SCAN_NT);
+    const int NT = ball ? 64 : scan_nt_for(batch);
     const long long tile = (long long)NT * 32;
     const long long tiles_ll = (L + tile - 1) / tile;
     if ((long long)batch * tiles_ll > 0x7fff0000LL) return GFX_ERR_UNSUPPORTED;
@@ -831,8 +859,8 @@ int gfx_envelope_f32(const float* x, float* y, int batch, int channels, long lon
     GFX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256 + flags_bytes, (cudaStream_t)stream));
     p.tables = (float*)(w + dyn_tables_offset(batch, 1));
     cudaStream_t st = (cudaStream_t)stream;
-    if (ball) return launch_dynamics<64>(p, st);
-    return small_cta ? launch_dynamics<DYN_SCAN_NT_SMALL>(p, st) : launch_dynamics<DYN_SCAN_NT>(p, st);
+    if (ball) return launch_dynamics<64, true, true>(p, st);
+    return launch_scan<true>(NT, p, st);
 }
 
 }  // extern "C"

@@ -474,7 +474,50 @@ struct FilterSrc {
     const float* h;       // [hrows, Nh]
     const float* energy;  // [batch, 2] sum_t of the squared raw mid / side rows, or null (plain filter)
     int to_lr;            // with energy: rows are left/right = mid +- side (mean-over-channels energy = e0 + e1)
+    int act;              // 1: FIRFilter (filter.py:65-77): taps = tanh(h), energy [batch] = mean_c sum_t tanh(h)^2; ch_act rows per item
+    int ch_act;
 };
+// tanh on the fly (tanh(0) = 0: the zero padding of a segment is unaffected)
+template <typename Src>
+struct TanhSrc {
+    Src s;
+    __device__ __forceinline__ pk2 get(int c) const {
+        float a, b;
+        pk_split(s.get(c), a, b);
+        return pk_make(tanhf(a), tanhf(b));
+    }
+};
+// scale of a filter row: 1/N, times the unit-energy normalisation where the source asks for it
+__device__ __forceinline__ float filter_scale(const FilterSrc& fs, int hrow, int N) {
+    float scale = 1.f / (float)N;
+    if (fs.act) {
+        scale *= rsqrtf(fs.energy[hrow / fs.ch_act] + 1e-12f);
+    } else if (fs.energy) {
+        // normalize_impulse of a reverb IR: one scale per batch item from the raw mid/side energies
+        const float e0 = fs.energy[hrow & ~1], e1 = fs.energy[hrow | 1];
+        scale *= fs.to_lr ? rsqrtf(e0 + e1 + 1e-12f) : rsqrtf(0.5f * (e0 + e1) + 1e-12f);
+    }
+    return scale;
+}
+// energy [batch] = mean over the ch rows of sum_t tanh(h)^2 (normalize_impulse of the activated taps, core/utils.py:14-18)
+__global__ void __launch_bounds__(256) fir_tanh_energy_kernel(const float* __restrict__ h, float* __restrict__ energy, int ch, int Nh) {
+    __shared__ float red[8];
+    const float* row = h + (size_t)blockIdx.x * ch * Nh;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < ch * Nh; i += 256) {
+        const float t = tanhf(row[i]);
+        acc = fmaf(t, t, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        energy[blockIdx.x] = t / (float)ch;
+    }
+}
 
 // NT = N/32 threads; registers: two butterflies (64) + pair operands live in the fused phase
 __host__ __device__ constexpr int fir_nt(int n) { return n / 32; }
@@ -509,14 +552,10 @@ __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_spectrum_ker
     const long long s0 = (long long)part * part_len;
     long long end = s0 + part_len;
     if (end > Nh) end = Nh;
-    float scale = 1.f / (float)N;
-    if (fs.energy) {
-        // normalize_impulse of a reverb IR: one scale per batch item from the raw mid/side energies
-        const float e0 = fs.energy[hrow & ~1], e1 = fs.energy[hrow | 1];
-        scale *= fs.to_lr ? rsqrtf(e0 + e1 + 1e-12f) : rsqrtf(0.5f * (e0 + e1) + 1e-12f);
-    }
+    const float scale = filter_scale(fs, hrow, N);
     const SegSrc<FAST> src(fs.h + (size_t)hrow * Nh, s0, end, 2 * N);
-    segment_spectrum<N>(zbuf, plan, src, Hs + (size_t)blockIdx.x * (N / 2), scale);
+    if (fs.act) segment_spectrum<N>(zbuf, plan, TanhSrc<SegSrc<FAST>>{src}, Hs + (size_t)blockIdx.x * (N / 2), scale);
+    else segment_spectrum<N>(zbuf, plan, src, Hs + (size_t)blockIdx.x * (N / 2), scale);
 }
 
 // UPOLS step 1: spectra of input blocks.  Xs[(rloc * nblk + j) * N/2 + slot] = rfft of x[(j-1)B, (j+1)B), B = N
@@ -980,11 +1019,7 @@ __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_upols_pipeli
             const long long s0 = (long long)part * N;
             long long end = s0 + N;
             if (end > jb.Nh) end = jb.Nh;
-            float scale = 1.f / (float)N;
-            if (jb.fs.energy) {
-                const float e0 = jb.fs.energy[hrow & ~1], e1 = jb.fs.energy[hrow | 1];
-                scale *= jb.fs.to_lr ? rsqrtf(e0 + e1 + 1e-12f) : rsqrtf(0.5f * (e0 + e1) + 1e-12f);
-            }
+            const float scale = filter_scale(jb.fs, hrow, N);
             // (the filter rows are read-only inputs: the generic, alignment-agnostic source is used when FAST is off)
             const SegSrc<FAST> src(jb.fs.h + (size_t)hrow * jb.Nh, s0, end, 2 * N);
             segment_spectrum<N>(zbuf, jb.plan, src, jb.Hs + ((size_t)(hb % jb.R) * nH + u) * half, scale);
@@ -1291,7 +1326,7 @@ static int fir_dispatch(const FirArgs& a) {
         return run_ols<16384>(a);
     }
     const int P = (a.Nh + n - 1) / n;
-    if (g_long_mode == 1 && P <= MAC_MAX_PC && n == 8192) {
+    if (g_long_mode == 1 && P <= MAC_MAX_PC && n == 8192 && !a.fs.act) {
         int Pg; long long nblk; size_t per_item;
         upols_geometry(a.cx, a.ch, a.L, a.Nh, a.shift, n, Pg, nblk, per_item);
         if (a.ws_bytes >= upols_ctr_bytes(a.batch) + (size_t)upols_r() * per_item && (long long)a.batch * 5 < 0x7fffffffLL)
@@ -1395,15 +1430,27 @@ static int fir_conv_common(const float* x, gfx::FilterSrc fs, float* y, int batc
 int gfx_fir_conv_f32(const float* x, const float* h, float* y, int batch, int cx, int ch, long long L,
                      int filter_len, int zerophase, int filter_repeat, const void* plan, void* workspace,
                      size_t workspace_bytes, void* stream) {
-    return fir_conv_common(x, gfx::FilterSrc{h, nullptr, 0}, y, batch, cx, ch, L, filter_len, zerophase, filter_repeat,
+    return fir_conv_common(x, gfx::FilterSrc{h, nullptr, 0, 0, 1}, y, batch, cx, ch, L, filter_len, zerophase, filter_repeat,
                            plan, workspace, workspace_bytes, stream);
+}
+
+int gfx_fir_filter_f32(const float* x, const float* fir_raw, float* y, int batch, int cx, int ch, long long L,
+                       int filter_len, const void* plan, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!fir_raw || !workspace || batch <= 0 || ch <= 0 || filter_len <= 0) return GFX_ERR_INVALID;
+    const size_t ebytes = ((size_t)batch * sizeof(float) + 255) / 256 * 256;
+    if (workspace_bytes < ebytes) return GFX_ERR_WORKSPACE;
+    float* energy = (float*)workspace;
+    gfx::fir_tanh_energy_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(fir_raw, energy, ch, filter_len);
+    GFX_LAUNCH_CHECK();
+    return fir_conv_common(x, gfx::FilterSrc{fir_raw, energy, 0, 1, ch}, y, batch, cx, ch, L, filter_len, 0, 1, plan,
+                           (unsigned char*)workspace + ebytes, workspace_bytes - ebytes, stream);
 }
 
 int gfx_fir_conv_midside_ir_f32(const float* x, const float* ir_raw, const float* energy, float* y, int batch, int cx,
                                 long long L, int ir_len, int ms_to_lr, int filter_repeat, const void* plan,
                                 void* workspace, size_t workspace_bytes, void* stream) {
     if (!energy) return GFX_ERR_INVALID;
-    return fir_conv_common(x, gfx::FilterSrc{ir_raw, energy, ms_to_lr ? 1 : 0}, y, batch, cx, 2, L, ir_len, 0,
+    return fir_conv_common(x, gfx::FilterSrc{ir_raw, energy, ms_to_lr ? 1 : 0, 0, 1}, y, batch, cx, 2, L, ir_len, 0,
                            filter_repeat, plan, workspace, workspace_bytes, stream);
 }
 

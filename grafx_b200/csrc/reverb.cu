@@ -77,13 +77,7 @@ constexpr int RV_ZB_BYTES = 2 * RV_FT * RV_ZS * 8;          // pk2 zb[2][16][RV_
 constexpr int RV_FR_BYTES = 2 * RV_FT * RV_NFFT * 4;        // float fr[2][16][384]
 constexpr int RV_TW_BYTES = (RV_N + RV_N / 2) * 8;          // float2 w192[192], hw[96]
 constexpr int RV_FL_FLOATS = RV_NFFT + 4 * (RV_BINS + 3) + 2 * RV_FT + 2 * 16 + 8;
-#ifdef GFX_RV_LEAN
-// (experiment, off by default) window / 192 and the reciprocal overlap-add envelopes as per-CTA tables
-constexpr int RV_LEAN_FLOATS = RV_NFFT + 2 * RV_HOP;
-#else
-constexpr int RV_LEAN_FLOATS = 0;
-#endif
-constexpr int RV_SMEM_BYTES = RV_ZB_BYTES + RV_FR_BYTES + RV_TW_BYTES + (RV_FL_FLOATS + RV_LEAN_FLOATS) * 4;
+constexpr int RV_SMEM_BYTES = RV_ZB_BYTES + RV_FR_BYTES + RV_TW_BYTES + RV_FL_FLOATS * 4;
 
 __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbParams p) {
     extern __shared__ __align__(16) unsigned char rv_smem[];
@@ -96,11 +90,6 @@ __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbPar
     float* a1_all = a0_all + 2 * (RV_BINS + 3);                                       // [2][196] softplus(Hd)
     float* xn_all = a1_all + 2 * (RV_BINS + 3);                                       // [2][16] Nyquist bin per frame
     float* red = xn_all + 2 * RV_FT;                                                  // [2][16]
-#ifdef GFX_RV_LEAN
-    float* wsc = red + 2 * 16 + 8;                                                    // [384] window / 192
-    float* renv = wsc + RV_NFFT;                                                      // [192] 1 / (w[n]^2 + w[n+192]^2)
-    float* renl = renv + RV_HOP;                                                      // [192] 1 / w[n+192]^2 (past the last frame)
-#endif
 
     const int ch = threadIdx.x >> 8, tid = threadIdx.x & (RV_NT - 1);  // channel (mid | side), thread within it
     const int tile = blockIdx.x % p.tiles, b = blockIdx.x / p.tiles;
@@ -116,14 +105,6 @@ __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbPar
 
     for (int t = threadIdx.x; t < RV_NFFT; t += 2 * RV_NT) {
         win[t] = p.window[t];
-#ifdef GFX_RV_LEAN
-        wsc[t] = p.window[t] * (1.f / (float)RV_N);
-        if (t < RV_HOP) {
-            const float wa = p.window[t], wb = p.window[t + RV_HOP];
-            renv[t] = __frcp_rn(fmaf(wa, wa, wb * wb));
-            renl[t] = __frcp_rn(fmaf(0.f, wa, wb * wb));
-        }
-#endif
         if (t < RV_N) {
             float sn, c;
             sincospif((float)t * (2.f / (float)RV_N), &sn, &c);
@@ -225,14 +206,9 @@ __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbPar
                 const int n = tau + 12 * sidx;
                 float re, im;
                 pk_split(bq[4 * i + j], re, im);
-#ifdef GFX_RV_LEAN
-                const float2 w2 = *reinterpret_cast<const float2*>(wsc + 2 * n);
-                *reinterpret_cast<float2*>(frame + 2 * n) = make_float2(re * w2.x, im * w2.y);
-#else
                 const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * n);
                 *reinterpret_cast<float2*>(frame + 2 * n) =
                     make_float2(re * (1.f / (float)RV_N) * w2.x, im * (1.f / (float)RV_N) * w2.y);
-#endif
             }
         }
     }
@@ -256,10 +232,6 @@ __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbPar
             const float4 cm = *reinterpret_cast<const float4*>(frm + o2);
             const float4 as = *reinterpret_cast<const float4*>(frs + o1);
             const float4 cs = *reinterpret_cast<const float4*>(frs + o2);
-#ifdef GFX_RV_LEAN
-            const float4 rq = *reinterpret_cast<const float4*>((h < p.frames ? renv : renl) + n);
-            const float rx = rq.x, ry = rq.y, rz = rq.z, rw = rq.w;
-#else
             const float4 w1 = *reinterpret_cast<const float4*>(win + n);
             const float4 w2 = *reinterpret_cast<const float4*>(win + n + RV_HOP);
             const float e1 = h < p.frames ? 1.f : 0.f;
@@ -267,7 +239,6 @@ __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbPar
             const float ez = fmaf(e1 * w1.z, w1.z, w2.z * w2.z), ew = fmaf(e1 * w1.w, w1.w, w2.w * w2.w);
             // envelope division as a multiplication by the SFU reciprocal (error ~1 ulp), shared by both channels
             const float rx = __frcp_rn(ex), ry = __frcp_rn(ey), rz = __frcp_rn(ez), rw = __frcp_rn(ew);
-#endif
             const float4 vm = make_float4((am.x + cm.x) * rx, (am.y + cm.y) * ry, (am.z + cm.z) * rz, (am.w + cm.w) * rw);
             const float4 vs = make_float4((as.x + cs.x) * rx, (as.y + cs.y) * ry, (as.z + cs.z) * rz, (as.w + cs.w) * rw);
             em = fmaf(vm.x, vm.x, em); em = fmaf(vm.y, vm.y, em); em = fmaf(vm.z, vm.z, em); em = fmaf(vm.w, vm.w, em);

@@ -199,6 +199,30 @@ def fir_conv(x: torch.Tensor, h: torch.Tensor, mode: str = "causal", h_repeat: i
     return y.squeeze(1) if squeeze else y
 
 
+def fir_filter(x: torch.Tensor, fir: torch.Tensor) -> torch.Tensor:
+    """FIRFilter semantics in one call (filter.py:65-77): causal convolution of x [B, Cx, L] with
+    normalize_impulse(tanh(fir)), fir [B, Ch, N]; the activation and the unit-energy scale are folded into the filter
+    spectra (csrc/fir.cu: fir_tanh_energy_kernel + TanhSrc)."""
+    _cabi.require_cuda(x, fir)
+    assert x.ndim == 3 and fir.ndim == 3 and x.shape[0] == fir.shape[0]
+    B, cx, L = x.shape
+    _, ch, N = fir.shape
+    assert cx == ch or cx == 1 or ch == 1, "channel mismatch between signal and filter"
+    if _wants_grad(x, fir):
+        return fir_conv(x, normalize_impulse(torch.tanh(fir)), "causal")  # the differentiable statement
+    x, fir = _prep(x, torch.float32), _prep(fir, torch.float32)
+    y = _new_output((B, max(cx, ch), L), torch.float32, x.device)
+    if y.numel():
+        L_ = _cabi.lib()
+        plan = _fft_plan(x.device, L_.gfx_fir_fft_size(N))
+        ws = _cabi.workspace(L_.gfx_fir_conv_workspace_bytes(B, cx, ch, L, N, 0) + (4 * B + 255) // 256 * 256, x.device)
+        with torch.cuda.device(x.device):
+            code = L_.gfx_fir_filter_f32(x.data_ptr(), fir.data_ptr(), y.data_ptr(), B, cx, ch, L, N, plan.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), _cabi.stream_ptr())
+        _cabi.check(code, "gfx_fir_filter_f32")
+    return y
+
+
 def normalize_impulse(ir: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
     """core/utils.py:14-18 -- O(filter taps) parameter-side math, stays in PyTorch."""
     assert ir.ndim == 3

@@ -31,10 +31,10 @@ class FIRFilter(nn.Module):
         self.conv = FIRConvolution(mode="causal", **backend_kwargs)
 
     def forward(self, input_signals, fir):
-        fir = F_.normalize_impulse(torch.tanh(fir))
+        # tanh + normalize_impulse happen inside the convolution while the filter spectra are formed
         if self.processor_channel == "midside":
-            return F_.ms_to_lr(self.conv(F_.lr_to_ms(input_signals), fir))
-        return self.conv(input_signals, fir)
+            return F_.ms_to_lr(F_.fir_filter(F_.lr_to_ms(input_signals), fir))
+        return F_.fir_filter(input_signals, fir)
 
     def parameter_size(self):
         return {"fir": (self.num_channels, self.fir_len)}

@@ -118,6 +118,11 @@ GFX_API int gfx_fir_set_long_mode(int mode, int lookahead); /* lookahead: pipeli
  * partitions per pass, the round-1 kernel, used when the filter has <= 12 partitions; kept for A/B measurements).
  * The two differ in summation order only (~1e-7 relative). */
 GFX_API int gfx_fir_set_mac_form(int form);
+/* FIRFilter.forward (processors/filter.py:65-77): taps = normalize_impulse(tanh(fir_raw)) -- the activation and the
+ * unit-energy scale are applied while the filter spectra are formed (one small reduction kernel + the convolution).
+ * fir_raw [batch, ch, filter_len]; workspace: gfx_fir_conv_workspace_bytes(...) + 256 * ceil(4 batch / 256) bytes. */
+GFX_API int gfx_fir_filter_f32(const float* x, const float* fir_raw, float* y, int batch, int cx, int ch, long long L,
+                               int filter_len, const void* plan, void* workspace, size_t workspace_bytes, void* stream);
 /* Same convolution (causal) with the filter given as the UN-NORMALISED impulse response of
  * gfx_reverb_ir_f32 (mode 0: mid/side rows, ms_to_lr = 0; mode 3: left/right rows, ms_to_lr = 1) plus the
  * energies of its raw mid/side rows: normalize_impulse (processors/reverb.py:215-228, core/utils.py:14-18)
@@ -242,6 +247,8 @@ typedef struct gfx_dynamics_stage {
     float* hist_post;           /* [batch, L] scratch; required for an iir gain smoother when iir_len < L */
 } gfx_dynamics_stage;
 GFX_API size_t gfx_dynamics_workspace_bytes(int batch, int n_stages);
+/* threads per CTA of the scan (one-pole smoother) variant: 0 = chosen from the row count (default), or 32/64/128/256 */
+GFX_API int gfx_dynamics_set_tuning(int scan_threads);
 GFX_API int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long long L,
                              const gfx_dynamics_stage* stages, int n_stages, int iir_len,
                              void* workspace, size_t workspace_bytes, void* stream);

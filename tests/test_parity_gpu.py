@@ -392,6 +392,23 @@ def test_fir_long_filter_partition_sizes_vs_oracle(Nh, L, hrep):
         L_.gfx_fir_set_tuning(4096, 0)
 
 
+@pytest.mark.parametrize("N,mode,L", [(1, "mono", 100), (255, "stereo", 5000), (3000, "midside", 20001), (20000, "stereo", 30000)])
+def test_firfilter_fused_activation_sizes_vs_oracle(N, mode, L):
+    """FIRFilter with the tanh + unit-energy normalisation folded into the filter spectra (gfx_fir_filter_f32): every
+    FFT plan incl. the partitioned long-filter path, all channel modes, odd lengths."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+
+    g = torch.Generator().manual_seed(N)
+    B = 3
+    proc = P.FIRFilter(fir_len=N, processor_channel=mode).cuda()
+    C = 1 if mode == "mono" else 2
+    x = torch.randn(B, 2 if mode == "midside" else C, L, generator=g)
+    fir = 2.0 * torch.randn(B, C, N, generator=g)
+    y = proc(x.cuda(), fir.cuda()).cpu()
+    assert_close(y, O.fir_filter(x.double(), fir.double(), mode).float(), f"firfilter {N} {mode}", tol=2e-5)
+
+
 def test_cfg3b_firfilter_full_size_impulse_and_linearity():
     """FIRFilter(1023, stereo) at 512 x 2 x 131072: impulse response reproduces the normalised
     taps; linearity; a sampled set of rows against the oracle."""

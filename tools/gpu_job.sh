@@ -1,9 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
-rm -f gpurun_out/r02_conv_time.log
-timeout 900 python -m pytest tests/test_parity_gpu.py -q -m gpu -x -k "fir or reverb or render or conv" 2>&1 | tail -15 > gpurun_out/r02_t2.log
-for lib in libgrafx_b200.so libgfx_u4.so; do
-GRAFX_B200_LIB=$PWD/grafx_b200/lib/$lib timeout 300 python tools/conv_time.py >> gpurun_out/r02_conv_time.log 2>&1
-done
-cat gpurun_out/r02_t2.log gpurun_out/r02_conv_time.log
+timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_fullsize_gpu.py -q -m gpu -x -k "dynamics or cfg4 or envelope or approx or ballistics or slow_pole or compressor or noisegate" 2>&1 | tail -5 > gpurun_out/r02_dyn_tests.log
+timeout 300 python tools/dyn_time.py > gpurun_out/r02_dyn_time.log 2>&1
+cat gpurun_out/r02_dyn_tests.log gpurun_out/r02_dyn_time.log
