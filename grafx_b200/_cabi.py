@@ -50,6 +50,7 @@ SIGNATURES = {
                                        c_int, c_ll, c_void_p, c_size_t, c_void_p]),
     "gfx_dynamics_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gfx_dynamics_set_tuning": (c_int, [c_int]),
+    "gfx_dynamics_set_ballistics_mode": (c_int, [c_int]),
     "gfx_dynamics_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, ctypes.POINTER(DynamicsStage), c_int,
                                  c_int, c_void_p, c_size_t, c_void_p]),
     "gfx_envelope_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_void_p,

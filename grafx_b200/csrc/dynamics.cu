@@ -57,6 +57,9 @@ struct DynParams {
     int aligned;
     // envelope mode (gfx_envelope_f32: the stand-alone smoothers / envelope followers, core/envelope.py:10-101,
     // dynamics.py:745-790): one stage, no knee, y [batch, 1, L] = the smoothed detector signal (or its log)
+    int* lookback;  // [batch] ballistics launches: samples of warm-up that make a chunk independent of its past (>= 0: the row
+                    // is done by dynamics_spec_kernel), or -1 (the row-owner kernel walks the row); null: walk every row
+    int spec_ch;    // samples per thread of dynamics_spec_kernel
     int envelope;   // 0: dynamics processors; 1: envelope output
     int detect;     // envelope mode: 0 mean_c x^2, 1 mean_c |x|, 2 x itself (C == 1)
     int env_log;    // envelope mode: y = log(envelope + 1e-5)
@@ -406,10 +409,34 @@ __device__ __forceinline__ void knee_log_gain(float (&u)[32], const KneeConst& k
 }
 
 // one thread per (row, stage): every constant of the sample loops
+// Warm-up length of an attack / release follower.  Both branches of y' = (1 - c) y + c u are affine in y with slope
+// 1 - c in (0, 1), and the branch taken only makes the result their min or max: the step is a contraction with factor
+// 1 - min(at, rt) WHATEVER the input, so two runs from different states differ by at most (1 - cmin)^W times their
+// initial distance after W samples: 2^-24 of it (below fp32 resolution) once W >= ln(2^-24) / ln(1 - cmin).
+__device__ __forceinline__ int ballistics_warmup(float at, float rt) {
+    const float cmin = fminf(at, rt);
+    if (!(cmin > 1e-6f)) return 0x3fffffff;
+    const float w = ceilf(-16.635532f / log1pf(-fminf(cmin, 0.999f)));
+    return w > 1e9f ? 0x3fffffff : (int)w + 1;
+}
+
 __global__ void dynamics_tables_kernel(const DynParams p, float* __restrict__ tables) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.batch * p.n_stages) return;
     const int row = idx / p.n_stages, d = idx - row * p.n_stages;
+    if (d == 0 && p.lookback) {
+        // total warm-up of the chain: the followers of the stages settle one after the other
+        long long lb = 0;
+        for (int dd = 0; dd < p.n_stages; ++dd) {
+            for (int which = 0; which < 2; ++which) {
+                const SmootherDesc& sm = which ? p.st[dd].post : p.st[dd].pre;
+                if (sm.kind == 2)
+                    lb += ballistics_warmup(1.f / (1.f + expf(-sm.z[(size_t)row * 2 + 0])), 1.f / (1.f + expf(-sm.z[(size_t)row * 2 + 1])));
+            }
+        }
+        // worth it while the redundant warm-up stays below ~16 chunks (a single slow row is still far ahead of a walk)
+        p.lookback[row] = (p.spec_ch > 0 && lb <= 16LL * p.spec_ch) ? (int)lb : -1;
+    }
     const StageDesc& sd = p.st[d];
     float* base = tables + (size_t)row * DYN_ROW_FLOATS;
     for (int which = 0; which < 2; ++which) {
@@ -505,6 +532,7 @@ __global__ void __launch_bounds__(NT, dyn_min_ctas(NT, RO)) dynamics_kernel(cons
         const int t_first = RO ? 0 : (int)(item / (unsigned)p.batch);
         const int t_last = RO ? p.tiles - 1 : t_first;
         cx.row = RO ? (int)item : (int)(item - (unsigned)t_first * (unsigned)p.batch);
+        if (RO && p.lookback != nullptr && p.lookback[cx.row] >= 0) continue;  // done by dynamics_spec_kernel
         for (int tt = t_first; tt <= t_last; ++tt) {
         if (tt > t_first) __syncthreads();  // the previous tile has left shared memory
         cx.t_idx = tt;
@@ -709,6 +737,166 @@ __global__ void __launch_bounds__(NT, dyn_min_ctas(NT, RO)) dynamics_kernel(cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Attack / release ballistics without the serial walk.  The recursion is not associative, but it is a contraction (see
+// ballistics_warmup): a thread that starts `lookback` samples before its chunk from ANY state holds the true state of
+// every follower (to fp32 resolution) when it reaches the chunk.  So one thread = one chunk of spec_ch samples + its
+// warm-up, the whole chain of stages evaluated sample by sample in registers, no shared memory, no barrier, no hand-over
+// between tiles or CTAs: rows x L / spec_ch independent threads instead of `rows` walkers.  The warm-up is redundant
+// work (lookback / spec_ch of it, ~0.5-1x for coefficients sigmoid(N(0,1)) at 256-sample chunks); rows whose followers
+// are too slow for that (lookback > 16 chunks, i.e. time constants beyond a few hundred samples) keep the row-owner
+// walk (dynamics_kernel<64, true>), launched right after and skipping the rows done here.
+// Stages with a one-pole ("iir") smoother are not handled here (launch-level decision on the host).
+__device__ __forceinline__ float ball_step(float y, float u, float at, float rt, float omat, float omrt, bool use_min) {
+    const float ya = fmaf(omat, y, at * u), yr = fmaf(omrt, y, rt * u);
+    return use_min ? fminf(ya, yr) : fmaxf(ya, yr);
+}
+// scalar forms of knee_gain / knee_log_gain (same arithmetic)
+__device__ __forceinline__ float knee_gain1(float e, const KneeConst& k, int mode) {
+    const float d = fmaf(lg2_fast(e + 1e-5f), DYN_LN2, -k.T);
+    switch (mode) {
+        case 0:
+        case 3: return ex2_fast(fminf(0.f, d * k.slope2));
+        case 1: { const float q = d + k.W; return ex2_fast(d > k.W ? d * k.slope2 : (d < -k.W ? 0.f : k.mid2 * q * q)); }
+        case 4: { const float q = d - k.W; return ex2_fast(d < -k.W ? d * k.slope2 : (d > k.W ? 0.f : k.mid2 * q * q)); }
+        default: {
+            const float v = (mode == 2 ? k.Wl2 : -k.Wl2) * d;
+            const float sp = v > 28.f ? v * DYN_LN2 : DYN_LN2 * lg2_fast(1.f + ex2_fast(v));
+            return ex2_fast(k.exp2s * sp);
+        }
+    }
+}
+__device__ __forceinline__ float knee_log_gain1(float e, const KneeConst& k, int mode) {
+    const float G = __logf(e + 1e-5f), d = G - k.T;
+    switch (mode) {
+        case 0:
+        case 3: return fminf(0.f, d * k.slope);
+        case 1: { const float q = d + k.W; return G > k.hi ? d * k.slope : (G < k.lo ? 0.f : k.mid_scale * q * q); }
+        case 4: { const float q = d - k.W; return G < k.lo ? d * k.slope : (G > k.hi ? 0.f : k.mid_scale * q * q); }
+        case 2: return k.exp_scale * softplus_fast(k.W * d);
+        default: return k.exp_scale * softplus_fast(-k.W * d);
+    }
+}
+
+struct SpecStage {  // per-thread registers of one stage
+    float at0, rt0, at1, rt1;   // pre / post follower coefficients
+    bool min0, min1;
+    float s0, s1;               // follower states
+};
+
+#ifndef GFX_SPEC_NT
+#define GFX_SPEC_NT 128
+#endif
+__host__ __device__ constexpr int SPEC_NT(int) { return GFX_SPEC_NT; }
+template <int C, int NS>
+__global__ void __launch_bounds__(SPEC_NT(C)) dynamics_spec_kernel(const DynParams p) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunks = (int)((p.L + p.spec_ch - 1) / p.spec_ch);
+    const int row = (int)(gid / chunks);
+    if (row >= p.batch) return;
+    const int lb = p.lookback[row];
+    if (lb < 0) return;
+    const long long p0 = (long long)(gid - (long long)row * chunks) * p.spec_ch;
+    long long n0 = p0 - lb;
+    if (n0 < 0) n0 = 0;
+    long long n1 = p0 + p.spec_ch;
+    if (n1 > p.L) n1 = p.L;
+    const float* tab = p.tables + (size_t)row * DYN_ROW_FLOATS;
+    const SmootherConst* sc = reinterpret_cast<const SmootherConst*>(tab);
+    const KneeConst* kc = reinterpret_cast<const KneeConst*>(tab + 2 * DYN_MAX_STAGES * DYN_SC_FLOATS);
+    SpecStage st[NS];
+    KneeConst kk[NS];
+    int mode[NS];
+#pragma unroll
+    for (int d = 0; d < NS; ++d) {
+        st[d].at0 = sc[2 * d].at; st[d].rt0 = sc[2 * d].rt; st[d].at1 = sc[2 * d + 1].at; st[d].rt1 = sc[2 * d + 1].rt;
+        st[d].min0 = st[d].at0 >= st[d].rt0; st[d].min1 = st[d].at1 >= st[d].rt1;
+        st[d].s0 = 1.f; st[d].s1 = 1.f;  // ballistics starts from zi = 1 (exact when the thread starts at sample 0)
+        kk[d] = kc[d];
+        mode[d] = p.st[d].kind * 3 + (p.st[d].knee == 3 ? 1 : p.st[d].knee);
+    }
+    const float inv_c = 1.f / (float)C;
+    auto sample = [&](float (&v)[C]) {
+#pragma unroll
+        for (int d = 0; d < NS; ++d) {
+            float e = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) e = fmaf(v[c], v[c], e);
+            if (C > 1) e *= inv_c;
+            const StageDesc& sd = p.st[d];
+            if (sd.pre.kind == 2) {
+                st[d].s0 = ball_step(st[d].s0, e, st[d].at0, st[d].rt0, 1.f - st[d].at0, 1.f - st[d].rt0, st[d].min0);
+                e = st[d].s0;
+            }
+            float g;
+            if (sd.post.kind == 0) {
+                g = knee_gain1(e, kk[d], mode[d]);
+            } else {
+                float lg = knee_log_gain1(e, kk[d], mode[d]);
+                if (!sd.log_domain) lg = __expf(lg);
+                st[d].s1 = ball_step(st[d].s1, lg, st[d].at1, st[d].rt1, 1.f - st[d].at1, 1.f - st[d].rt1, st[d].min1);
+                g = sd.log_domain ? __expf(st[d].s1) : st[d].s1;
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] *= g;
+        }
+    };
+
+    // Every thread streams its own samples with 16-byte accesses (a thread's lines stay in L1 between its accesses).
+    // Measured on B200 (config 4b): this form 0.45 ms; warp-cooperative coalesced tiles in shared memory 0.94 ms, the same
+    // with cp.async double buffering 0.64 ms -- the per-sample shared-memory round trip costs more than the sectors save.
+    const float* x0 = p.x + (size_t)row * C * (size_t)p.L;
+    float* y0 = p.y + (size_t)row * C * (size_t)p.L;
+    long long n = n0;
+    if (p.aligned) {
+        // warm-up: scalar steps up to a 16-byte boundary, then float4 blocks (the chunk start is a multiple of 4)
+        for (; n < p0 && (n & 3); ++n) {
+            float v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = __ldg(x0 + (size_t)c * p.L + n);
+            sample(v);
+        }
+        for (; n + 4 <= p0; n += 4) {
+            float4 q[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) q[c] = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)c * p.L + n));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) v[c] = reinterpret_cast<const float*>(&q[c])[i];
+                sample(v);
+            }
+        }
+        for (; n + 4 <= n1; n += 4) {
+            float4 q[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) q[c] = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)c * p.L + n));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) v[c] = reinterpret_cast<const float*>(&q[c])[i];
+                sample(v);
+#pragma unroll
+                for (int c = 0; c < C; ++c) reinterpret_cast<float*>(&q[c])[i] = v[c];
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(y0 + (size_t)c * p.L + n) = q[c];
+        }
+    }
+    for (; n < n1; ++n) {
+        float v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = __ldg(x0 + (size_t)c * p.L + n);
+        sample(v);
+        if (n >= p0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) y0[(size_t)c * p.L + n] = v[c];
+        }
+    }
+}
+
 static size_t dyn_smem_bytes(int NT, int C, bool RO) {
     // two scratch tiles (at*u, rt*u) are only used by the ballistics (row owner) variant
     return (size_t)(C + (RO ? 2 : 0)) * NT * 128 +
@@ -719,8 +907,29 @@ static size_t dyn_tables_offset(int batch, int n_stages) {
     const size_t flags = ((size_t)batch * sizeof(int) + 255) / 256 * 256;
     return (256 + flags + (size_t)batch * 2 * n_stages * sizeof(float) + 255) / 256 * 256;
 }
+static size_t dyn_lookback_offset(int batch, int n_stages) {
+    return (dyn_tables_offset(batch, n_stages) + (size_t)batch * DYN_ROW_FLOATS * sizeof(float) + 255) / 256 * 256;
+}
 static size_t dyn_workspace_bytes(int batch, int n_stages) {
-    return dyn_tables_offset(batch, n_stages) + (size_t)batch * DYN_ROW_FLOATS * sizeof(float);
+    return dyn_lookback_offset(batch, n_stages) + ((size_t)batch * sizeof(int) + 255) / 256 * 256;
+}
+static int g_dyn_spec_threads_per_sm = 1536;  // chunk size: as large as still gives this many threads per SM
+static int g_dyn_ballistics_spec = 1;  // 1: warm-up chunks (dynamics_spec_kernel) where the followers allow it; 0: always walk
+
+template <int C>
+static int launch_spec_c(const DynParams& p, cudaStream_t stream) {
+    const long long chunks = (p.L + p.spec_ch - 1) / p.spec_ch;
+    const long long threads = (long long)p.batch * chunks;
+    constexpr int NT = SPEC_NT(C);
+    const unsigned grid = (unsigned)((threads + NT - 1) / NT);
+    switch (p.n_stages) {
+        case 1: dynamics_spec_kernel<C, 1><<<grid, NT, 0, stream>>>(p); break;
+        case 2: dynamics_spec_kernel<C, 2><<<grid, NT, 0, stream>>>(p); break;
+        case 3: dynamics_spec_kernel<C, 3><<<grid, NT, 0, stream>>>(p); break;
+        default: dynamics_spec_kernel<C, 4><<<grid, NT, 0, stream>>>(p); break;
+    }
+    GFX_LAUNCH_CHECK();
+    return GFX_OK;
 }
 
 template <int NT, bool RO, bool ENV = false>
@@ -741,6 +950,10 @@ static int launch_dynamics(DynParams& p, cudaStream_t stream) {
     if (grid > (long long)p.n_items) grid = p.n_items;
     dynamics_tables_kernel<<<(p.batch * p.n_stages + 127) / 128, 128, 0, stream>>>(p, p.tables);
     GFX_LAUNCH_CHECK();
+    if (RO && !ENV && p.lookback != nullptr) {
+        const int rc = p.C == 1 ? launch_spec_c<1>(p, stream) : launch_spec_c<2>(p, stream);
+        if (rc != GFX_OK) return rc;
+    }
     kern<<<(unsigned)grid, NT, smem, stream>>>(p);
     GFX_LAUNCH_CHECK();
     return GFX_OK;
@@ -770,6 +983,13 @@ int gfx_dynamics_set_tuning(int scan_threads) {
     return GFX_OK;
 }
 
+int gfx_dynamics_set_ballistics_mode(int mode) {
+    if (mode >= 64) { gfx::g_dyn_spec_threads_per_sm = mode; return GFX_OK; }  // (tuning: threads per SM the chunk size aims at)
+    if (mode != 0 && mode != 1) return GFX_ERR_INVALID;
+    gfx::g_dyn_ballistics_spec = mode;
+    return GFX_OK;
+}
+
 size_t gfx_dynamics_workspace_bytes(int batch, int n_stages) { return gfx::dyn_workspace_bytes(batch, n_stages); }
 
 int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long long L,
@@ -780,8 +1000,8 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
     if (batch <= 0 || channels <= 0 || L <= 0 || n_stages <= 0 || iir_len <= 0) return GFX_ERR_INVALID;
     if (n_stages > DYN_MAX_STAGES) return GFX_ERR_UNSUPPORTED;
     DynParams p;
-    p.envelope = 0; p.detect = 0; p.env_log = 0;
-    bool any_ballistics = false;
+    p.envelope = 0; p.detect = 0; p.env_log = 0; p.lookback = nullptr; p.spec_ch = 0;
+    bool any_ballistics = false, any_iir = false;
     for (int d = 0; d < n_stages; ++d) {
         const gfx_dynamics_stage& s = stages[d];
         if (s.kind < 0 || s.kind > 1 || s.knee < 0 || s.knee > 3 || (s.knee == 3 && s.kind != 1)) return GFX_ERR_INVALID;
@@ -801,6 +1021,7 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
         o.pre = SmootherDesc{s.energy_smoother, s.z_alpha_pre, s.hist_pre};
         o.post = SmootherDesc{s.gain_smoother, s.z_alpha_post, s.hist_post};
         any_ballistics |= (s.energy_smoother == 2 || s.gain_smoother == 2);
+        any_iir |= (s.energy_smoother == 1 || s.gain_smoother == 1);
     }
     const int NT = any_ballistics ? 64 : scan_nt_for(batch);
     const long long tile = (long long)NT * 32;
@@ -822,6 +1043,13 @@ int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long lon
     GFX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256 + flags_bytes, (cudaStream_t)stream));
     p.tables = (float*)(w + dyn_tables_offset(batch, n_stages));
     cudaStream_t st = (cudaStream_t)stream;
+    if (any_ballistics && !any_iir && channels <= 2 && g_dyn_ballistics_spec && L < 0x40000000LL) {
+        // chunks with warm-up: as many independent threads as fill the chip (at least 64 samples each)
+        int ch = 1024;
+        while (ch > 64 && (long long)batch * L / ch < (long long)device_info().sm_count * g_dyn_spec_threads_per_sm) ch >>= 1;
+        p.lookback = (int*)(w + dyn_lookback_offset(batch, n_stages));
+        p.spec_ch = ch;
+    }
     if (any_ballistics) return launch_dynamics<64, true>(p, st);
     return launch_scan<false>(NT, p, st);
 }
@@ -833,7 +1061,7 @@ int gfx_envelope_f32(const float* x, float* y, int batch, int channels, long lon
     if (batch <= 0 || channels <= 0 || L <= 0 || iir_len <= 0) return GFX_ERR_INVALID;
     if (smoother < 1 || smoother > 2 || detect < 0 || detect > 2 || (detect == 2 && channels != 1)) return GFX_ERR_INVALID;
     DynParams p;
-    p.envelope = 1; p.detect = detect; p.env_log = log_out ? 1 : 0;
+    p.envelope = 1; p.detect = detect; p.env_log = log_out ? 1 : 0; p.lookback = nullptr; p.spec_ch = 0;
     StageDesc& o = p.st[0];
     o.kind = 0; o.knee = 0; o.log_domain = 0;
     o.log_threshold = z; o.log_ratio = z; o.log_knee = nullptr;  // (the knee constants are formed but never used)

@@ -39,10 +39,12 @@ class GraphicEqualizerBiquad(nn.Module):
         fc = torch.tensor([b[0] for b in bands], dtype=torch.float32)
         fb = torch.tensor([b[1] for b in bands], dtype=torch.float32)
         self.num_bands = len(bands)
-        self.register_buffer("fc", fc)
+        # (upstream builds `fc` from a Python list: an all-integer table gives an int64 buffer, core/geq.py:148-167)
+        self.register_buffer("fc", fc.to(torch.int64) if bool((fc == fc.round()).all()) else fc)
         self.register_buffer("fB", fb)
         self.register_buffer("m2_cos_wc", -2 * torch.cos(2 * math.pi * fc / sr))
         self.register_buffer("tan_B_half", torch.tan(math.pi * fb / sr))
+        self.register_buffer("c", torch.tensor([0.4] * len(fc)))  # neighbour exponents as upstream registers them (core/geq.py:171)
 
     def forward(self, log_gains):
         g = torch.exp(log_gains)

@@ -31,6 +31,12 @@ class IIRFilter(nn.Module):
             raise AssertionError("fsm_regularization is not supported (asserts False upstream)")
         self.backend = backend
         self.fsm_fir_len = fsm_fir_len
+        if backend == "fsm":
+            # same buffer as upstream (core/iir.py:115-117, 269-276) so that its checkpoints load with strict=True; the
+            # frequency-sampled design itself evaluates the same phases on the fly (functional.iir_fsm_fir)
+            k = torch.arange(fsm_fir_len // 2 + 1)
+            phase = torch.arange(order + 1).unsqueeze(-1) * k / fsm_fir_len * 2 * torch.pi
+            self.register_buffer("delays", torch.exp(-1j * phase))
 
     def forward(self, input_signal, Bs, As):
         if self.backend == "fsm":

@@ -71,6 +71,7 @@ class MultitapDelay(nn.Module):
         self.num_delay_per_segment = num_delay_per_segment
         self.zp_filter_per_tap = zp_filter_per_tap
         self.zp_filter_bins = zp_filter_bins
+        self.register_buffer("window", torch.hann_window(zp_filter_bins * 2 - 1).view(1, 1, -1))  # (upstream buffer, delay.py:83-85)
         if zp_filter_per_tap:
             self.zp_filter = ZeroPhaseFIR(zp_filter_bins)
         self.delay = SurrogateDelay(N=segment_len, **surrogate_delay_kwargs)

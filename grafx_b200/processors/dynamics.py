@@ -34,6 +34,15 @@ class _DynamicsBase(nn.Module):
         self.gain_smooth_in_log = gain_smooth_in_log
         self.knee = knee
         self.iir_len = iir_len
+        # the smoother sub-modules of upstream (dynamics.py:314-340): same names and buffers, so that its checkpoints load
+        # with strict=True; the fused kernel does their work
+        from .core.envelope import Ballistics, TruncatedOnePoleIIRFilter
+
+        for name, kind in (("energy_smoother_module", energy_smoother), ("gain_smoother_module", gain_smoother)):
+            if kind == "iir":
+                setattr(self, name, TruncatedOnePoleIIRFilter(iir_len=iir_len))
+            elif kind == "ballistics":
+                setattr(self, name, Ballistics())
 
     def stage(self, log_threshold, log_ratio, log_knee=None, z_alpha_pre=None, z_alpha_post=None):
         """Descriptor of this processor for functional.dynamics_chain (also used by SerialChain)."""
@@ -73,6 +82,7 @@ class ApproxCompressor(nn.Module):
     def __init__(self, iir_len=16384, flashfftconv=True, max_input_len=2**17):
         super().__init__()
         self.iir_len = iir_len
+        self.env_follower = IIREnvelopeFollower(iir_len=iir_len)  # (upstream sub-module, dynamics.py:79: buffers for checkpoints)
 
     def stage(self, z_alpha, log_threshold, log_ratio, log_knee):
         return dict(kind="compressor", knee="quadratic", energy_smoother="iir", gain_smoother=None,
@@ -93,6 +103,7 @@ class ApproxNoiseGate(nn.Module):
     def __init__(self, freq_sample_n=16384, flashfftconv=True, max_input_len=2**17):
         super().__init__()
         self.iir_len = freq_sample_n
+        self.env_follower = IIREnvelopeFollower(iir_len=freq_sample_n)  # (upstream sub-module, dynamics.py:155)
 
     def stage(self, z_alpha, log_threshold, log_ratio, log_knee):
         return dict(kind="noisegate", knee="approx_gate", energy_smoother="iir", gain_smoother=None,

@@ -4,6 +4,7 @@ Same class names, constructor kwargs, forward signatures and parameter_size(); o
 (csrc/pointwise.cu), plus a per-row mean reduction when `remove_dc` is set."""
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
 
 from .. import functional as F_
@@ -76,6 +77,8 @@ class _SeriesDistortion(nn.Module):
         self.max_order = max_order
         self.remove_dc = remove_dc
         self.use_tanh = use_tanh
+        if self.op == "power":  # (upstream buffer, nonlinear.py:268-270; the kernel forms the powers in registers)
+            self.register_buffer("arange", torch.arange(max_order)[:, None, None, None])
 
     def forward(self, input_signals, basis_weights, log_pre_gain=None):
         dc = F_.row_mean(input_signals) if self.remove_dc else None

@@ -30,6 +30,7 @@ class STFTMaskedNoiseReverb(nn.Module):
         self.gain_envelope = gain_envelope
         self.processor_channel = processor_channel
         self.register_buffer("window", torch.hann_window(n_fft))
+        self.register_buffer("arange", torch.arange(self.num_frames).view(1, 1, 1, -1))  # (upstream buffer, reverb.py:77-78)
         if fixed_noise:
             rng = np.random.RandomState(0)
             noise = torch.tensor(rng.uniform(size=(2, ir_len)) * 2 - 1).float()
@@ -131,6 +132,7 @@ class FilteredNoiseShapingReverb(nn.Module):
         self.min_decay = (-60 / (min_decay_ms * sr / 1000)) / 20 * math.log(10)
         self.max_decay = (-60 / (max_decay_ms * sr / 1000)) / 20 * math.log(10)
         self.use_fade_in = use_fade_in
+        self.register_buffer("arange", torch.arange(ir_len)[None, None, None, :])  # (upstream buffer, reverb.py:361-362)
 
     def compute_ir(self, log_decay, log_gain, log_fade_in=None, z_fade_in_gain=None):
         """Un-normalised response [B, C, ir_len] and its row energies [B, C]."""

@@ -249,6 +249,9 @@ typedef struct gfx_dynamics_stage {
 GFX_API size_t gfx_dynamics_workspace_bytes(int batch, int n_stages);
 /* threads per CTA of the scan (one-pole smoother) variant: 0 = chosen from the row count (default), or 32/64/128/256 */
 GFX_API int gfx_dynamics_set_tuning(int scan_threads);
+/* attack / release ballistics: 1 (default) = independent chunks with a warm-up (dynamics_spec_kernel) for every row whose
+ * followers forget their state within 16 chunks, the row walk for the others; 0 = always the row walk */
+GFX_API int gfx_dynamics_set_ballistics_mode(int mode);
 GFX_API int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long long L,
                              const gfx_dynamics_stage* stages, int n_stages, int iir_len,
                              void* workspace, size_t workspace_bytes, void* stream);

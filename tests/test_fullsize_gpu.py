@@ -229,3 +229,47 @@ def test_render_common_parameters_reach_the_processor():
     # a single tensor instead of a dict is passed as `parameter=` upstream; processors without that argument raise
     with pytest.raises(TypeError):
         render_grafx({"fx": wet}, x, prm, rd, common_parameters=weights)
+
+
+# ------------------------------------------------------------------ ballistics: warm-up chunks vs the row walk
+@pytest.mark.parametrize("C,L", [(1, 65536), (2, 40001), (1, 3000)])
+def test_ballistics_speculative_chunks_match_the_row_walk(C, L):
+    """dynamics_spec_kernel (independent chunks, contraction warm-up) against the sequential row walk of the same
+    library (gfx_dynamics_set_ballistics_mode(0)) and the oracle: fast followers, a few slow rows that must fall back
+    to the walk inside the same launch, energy AND gain followers, two fused stages."""
+    from oracle import grafx_oracle as O
+    import grafx_b200.processors as P
+    from grafx_b200 import _cabi
+
+    gen = torch.Generator().manual_seed(100 + C)
+    B = 24
+    x = torch.randn(B, C, L, generator=gen)
+    comp = P.Compressor(energy_smoother="ballistics", gain_smoother="ballistics", gain_smooth_in_log=True)
+    gate = P.NoiseGate(energy_smoother="ballistics")
+
+    def draw(proc):
+        return {k: torch.randn(B, v, generator=gen) for k, v in proc.parameter_size().items()}
+
+    pc, pg = draw(comp), draw(gate)
+    pc["z_alpha_pre"][3] = torch.tensor([-7.0, 0.3])    # release-side time constant ~1100 samples: beyond 16 chunks -> walk
+    pg["z_alpha_pre"][5] = torch.tensor([1.0, -9.0])
+    pc["z_alpha_post"][7] = torch.tensor([-3.0, -3.5])  # slow but inside the warm-up budget
+    chain = P.SerialChain({"comp": comp, "gate": gate}).cuda()
+    L_ = _cabi.lib()
+    try:
+        assert L_.gfx_dynamics_set_ballistics_mode(1) == 0
+        y_spec, _ = chain(x.cuda(), comp=_cuda(pc), gate=_cuda(pg))
+        assert L_.gfx_dynamics_set_ballistics_mode(0) == 0
+        y_walk, _ = chain(x.cuda(), comp=_cuda(pc), gate=_cuda(pg))
+    finally:
+        L_.gfx_dynamics_set_ballistics_mode(1)
+    y_spec, y_walk = y_spec.cpu(), y_walk.cpu()
+    for r in range(B):
+        assert rel_l2(y_spec[r], y_walk[r]) < 2e-6, (r, rel_l2(y_spec[r], y_walk[r]))
+    assert torch.equal(y_spec[3], y_walk[3]) and torch.equal(y_spec[5], y_walk[5])   # the rows that fell back
+    rows = [0, 3, 5, 7, 11]
+    y1 = O.compressor(x[rows], **{k: v[rows] for k, v in pc.items()}, energy_smoother="ballistics", gain_smoother="ballistics",
+                      gain_smooth_in_log=True)
+    y_ref = O.noisegate(y1, **{k: v[rows] for k, v in pg.items()}, energy_smoother="ballistics")
+    for i, r in enumerate(rows):
+        assert_close(y_spec[r], y_ref[i], f"spec row {r}")

@@ -84,3 +84,23 @@ def test_render_grafx_refuses_to_cut_the_autograd_graph():
         render_grafx({}, torch.zeros(2, 2, 64), prm, rd)
     with pytest.raises(NotImplementedError):
         render_grafx({}, torch.zeros(2, 2, 64, requires_grad=True), {}, rd)
+
+
+def test_state_dict_keys_match_the_reference():
+    """Every drop-in module registers the buffers its upstream class registers (same names, shapes, dtypes): an upstream
+    checkpoint loads with strict=True.  Fixture: oracle/make_state_dict_keys.py run against the reference."""
+    import json
+    import os
+
+    import grafx_b200.processors as P
+
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "state_dict_keys.json")))
+    checked = 0
+    for name, keys in ref.items():
+        if "error" in keys:
+            continue
+        mod = getattr(P, name)()
+        ours = {k: [list(v.shape), str(v.dtype)] for k, v in mod.state_dict().items()}
+        assert ours == keys, (name, sorted(set(ours) ^ set(keys)))
+        checked += 1
+    assert checked >= 25

@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_fullsize_gpu.py -q -m gpu -x -k "dynamics or cfg4 or envelope or approx or ballistics or slow_pole or compressor or noisegate" 2>&1 | tail -5 > gpurun_out/r02_dyn_tests.log
-timeout 300 python tools/dyn_time.py > gpurun_out/r02_dyn_time.log 2>&1
-cat gpurun_out/r02_dyn_tests.log gpurun_out/r02_dyn_time.log
+timeout 900 python -m pytest tests/test_fullsize_gpu.py -q -m gpu -x -k "ballistics or cfg4" 2>&1 | tail -5 > gpurun_out/r02_ball.log
+timeout 300 python tools/ball_time.py >> gpurun_out/r02_ball.log 2>&1
+cat gpurun_out/r02_ball.log
