@@ -57,7 +57,10 @@ __host__ __device__ constexpr int tw_exponent(int r, int e) {  // exponent of ta
 #ifndef GFX_PASS_UNROLL
 #define GFX_PASS_UNROLL 1
 #endif
-constexpr int kPassUnroll = GFX_PASS_UNROLL;  // butterflies of a shared-memory radix-16 pass processed together
+constexpr int kPassUnroll = GFX_PASS_UNROLL;
+// GUNR (fft_pass): butterflies of a global-memory pass issued together.  2 in the one-transform kernels (spectra, inverse:
+// both butterflies' 32 loads / stores of a thread in flight, reverb-shape convolution 1.66 -> 1.59 ms on B200); 1 in the
+// fused forward + inverse kernel (fir_ols_kernel: 128 registers, the second set spills, 0.367 -> 0.388 ms).  // butterflies of a shared-memory radix-16 pass processed together
 __host__ __device__ constexpr int plan_entries(int n, int s) {
     const int r = plan_radix(n, s);
     const int st = r > 1 ? plan_m(n, s) / r : 1;
@@ -198,7 +201,7 @@ struct NoDst { __device__ __forceinline__ void put(int, pk2) const {} };
 // One FFT pass over shared memory (see the plan tables).  FROM_GLOBAL (forward pass 0 only): inputs come from
 // `src` (complex index c = b + (N/16) q); TO_GLOBAL (inverse pass 0 only): outputs go to `dst`.
 template <int N, int NT, int S, bool INV, bool FROM_GLOBAL = false, bool TO_GLOBAL = false, typename Src = NoSrc,
-          typename Dst = NoDst>
+          typename Dst = NoDst, int GUNR = 1>
 __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan, const Src& src = Src(),
                                          const Dst& dst = Dst()) {
     constexpr int R = plan_radix(N, S);
@@ -209,7 +212,7 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan
     constexpr int PST = ST >= 16 ? ST + ST / 16 : 1;
     static_assert(ST == 1 || ST % 16 == 0, "stride must keep the padding pattern linear");
     static_assert(!(FROM_GLOBAL || TO_GLOBAL) || (S == 0 && R == 16), "fused passes are the radix-16 pass 0");
-#pragma unroll(R == 2 ? 4 : ((FROM_GLOBAL || TO_GLOBAL) ? 1 : kPassUnroll))
+#pragma unroll(R == 2 ? 4 : ((FROM_GLOBAL || TO_GLOBAL) ? GUNR : kPassUnroll))
     for (int b = threadIdx.x; b < N / R; b += NT) {
         const int j = b & (ST - 1);
         const int i0 = (b - j) * R + j;
@@ -284,9 +287,9 @@ __device__ __forceinline__ void fft_pass(pk2* z, const float2* __restrict__ plan
 }
 
 // forward passes 0 .. last-1 (pass 0 reads global memory); ends with a barrier
-template <int N, int NT, typename Src>
+template <int N, int NT, typename Src, int GUNR = 1>
 __device__ __forceinline__ void fft_forward_front(pk2* z, const float2* __restrict__ plan, const Src& src) {
-    fft_pass<N, NT, 0, false, true, false, Src>(z, plan, src);
+    fft_pass<N, NT, 0, false, true, false, Src, NoDst, GUNR>(z, plan, src);
     __syncthreads();
     fft_pass<N, NT, 1, false>(z, plan);
     __syncthreads();
@@ -296,7 +299,7 @@ __device__ __forceinline__ void fft_forward_front(pk2* z, const float2* __restri
     }
 }
 // inverse passes last-1 .. 0 (pass 0 writes global memory); starts with a barrier
-template <int N, int NT, typename Dst>
+template <int N, int NT, typename Dst, int GUNR = 1>
 __device__ __forceinline__ void fft_inverse_back(pk2* z, const float2* __restrict__ plan, const Dst& dst) {
     __syncthreads();
     if constexpr (plan_stages(N) > 3) {
@@ -305,7 +308,7 @@ __device__ __forceinline__ void fft_inverse_back(pk2* z, const float2* __restric
     }
     fft_pass<N, NT, 1, true>(z, plan);
     __syncthreads();
-    fft_pass<N, NT, 0, true, false, true, NoSrc, Dst>(z, plan, NoSrc(), dst);
+    fft_pass<N, NT, 0, true, false, true, NoSrc, Dst, GUNR>(z, plan, NoSrc(), dst);
 }
 
 // ---- the fused last forward / first inverse pass
@@ -532,7 +535,7 @@ template <int N, typename Src>
 __device__ __forceinline__ void segment_spectrum(pk2* zbuf, const float2* __restrict__ plan, const Src& src,
                                                  float4* __restrict__ out, float scale) {
     constexpr int NT = fir_nt(N);
-    fft_forward_front<N, NT>(zbuf, plan, src);
+    fft_forward_front<N, NT, Src, 2>(zbuf, plan, src);
     const int t = threadIdx.x;
     const ushort2 pr = plan_pairtab<N>(plan)[t];
     pk2 A[16], B[16];
@@ -886,7 +889,7 @@ __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_inv_kernel(c
     }
     const size_t row = (size_t)(row0 + rloc);
     const SegDst<FAST> dst(y + row * L, (long long)j * N - shift, L, N, 2 * N);
-    fft_inverse_back<N, NT>(zbuf, plan, dst);
+    fft_inverse_back<N, NT, SegDst<FAST>, 2>(zbuf, plan, dst);
 }
 
 // ------------------------------------------------------------------ long filters: one persistent pipelined launch

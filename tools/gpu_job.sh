@@ -1,6 +1,8 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_fullsize_gpu.py -q -m gpu -x -k "ballistics or cfg4" 2>&1 | tail -5 > gpurun_out/r02_ball.log
-timeout 300 python tools/ball_time.py >> gpurun_out/r02_ball.log 2>&1
-cat gpurun_out/r02_ball.log
+rm -f gpurun_out/r02_fft_time.log
+for lib in libgrafx_b200.so libgfx_tw15.so; do
+GRAFX_B200_LIB=$PWD/grafx_b200/lib/$lib timeout 300 python tools/fft_time.py >> gpurun_out/r02_fft_time.log 2>&1
+done
+cat gpurun_out/r02_fft_time.log
