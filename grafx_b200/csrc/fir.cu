@@ -733,16 +733,16 @@ __device__ __forceinline__ void stg_stream2(float2* p, const float2& v) {
     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y));
 }
 
-// running pointers of one row walk (kept as serial updates so that the unrolled tile does not precompute 2 x PC
-// 64-bit addresses into registers)
+// state of one row walk.  The copy ring is two sets of U stages: while a body works on one set, the U blocks of the
+// next body land in the other (offsets inside a set are compile-time constants; the sets swap by two pointer moves)
 struct Mac2Walk {
-    const float2* xn;   // input block that enters the copy ring next
-    float2* yp;         // output block written next
-    float2* s_in;       // ring stage the next copy lands in
-    const float2* s_out;  // ring stage the next block is read from
-    float2* s_end;
-    int to_copy;        // input blocks not yet requested
-    int to_do;          // output blocks left
+    const float2* x;     // input block 0 of the row (this thread's bin)
+    float2* yp;          // output block written next
+    float2* s_read;      // stage set the body reads
+    float2* s_write;     // stage set the copies of the next body land in
+    int next;            // index of the first input block of the NEXT body
+    int last;            // last input block index (copies past the end re-read it; their products are never stored)
+    int to_do;           // output blocks left
 };
 
 // U output blocks per loop body.  ring[k] = input block (newest - k) when the body starts; inside the body every operand
@@ -751,30 +751,32 @@ struct Mac2Walk {
 // (93 KB) ran out of the 32 KB instruction cache (profiles/r02_mac2_unrolled.txt: 45 % of the stalls no_inst).
 // VALID = ring entries that hold data (the ring fills up over the first PC blocks of a row: products with the
 // still-empty entries are left out of the peeled bodies -- 36 % of the multiplies at 24 partitions x 32 blocks).
-template <int PC, int U, int VALID>
+// GUARD: the body may run past the end of the row (peeled bodies and the tail); the steady loop has no per-block tests.
+template <int PC, int U, int VALID, bool GUARD>
 __device__ __forceinline__ void mac2_body(Mac2Walk& w, float2 (&h)[PC], float2 (&ring)[PC], size_t half2, int accumulate) {
-    float2 xn[U];
+    // the U blocks of the next body enter the other stage set ...
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        // one block enters the copy ring (D - 1 blocks ahead), one leaves it
-        if (w.to_copy > 0) cp_async_small<8>(w.s_in, w.xn);
-        cp_async_commit();
-        w.xn += half2; --w.to_copy;
-        w.s_in += MAC2_NT; if (w.s_in == w.s_end) w.s_in -= MAC2_D * MAC2_NT;
-        cp_async_wait<MAC2_D - 1>();
-        xn[u] = *w.s_out;   // (past the end of the row: stale data, its products are never stored)
-        w.s_out += MAC2_NT; if (w.s_out == w.s_end) w.s_out -= MAC2_D * MAC2_NT;
+        const int jb = min(w.next + u, w.last);
+        cp_async_small<8>(w.s_write + u * MAC2_NT, w.x + (size_t)jb * half2);
     }
+    cp_async_commit();
+    w.next += U;
+    // ... while this body's blocks (requested one body ago) are complete
+    cp_async_wait<1>();
+    float2 xn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) xn[u] = w.s_read[u * MAC2_NT];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         float2 acc = make_float2(0.f, 0.f);
-        if (accumulate && u < w.to_do) acc = w.yp[(size_t)u * half2];
+        if (accumulate && (!GUARD || u < w.to_do)) acc = w.yp[(size_t)u * half2];
 #pragma unroll
         for (int p = 0; p < PC; ++p) {
             if (p > u && p - u - 1 >= VALID) continue;
             cmac2(acc, p <= u ? xn[u - p] : ring[p - u - 1], h[p]);
         }
-        if (u < w.to_do) stg_stream2(w.yp + (size_t)u * half2, acc);
+        if (!GUARD || u < w.to_do) stg_stream2(w.yp + (size_t)u * half2, acc);
     }
 #pragma unroll
     for (int k = PC - 1; k >= U; --k) ring[k] = ring[k - U];
@@ -782,16 +784,18 @@ __device__ __forceinline__ void mac2_body(Mac2Walk& w, float2 (&h)[PC], float2 (
     for (int k = 0; k < U && k < PC; ++k) ring[k] = xn[U - 1 - k];
     w.yp += (size_t)U * half2;
     w.to_do -= U;
+    float2* t = w.s_read; w.s_read = w.s_write; w.s_write = t;
 }
-// the bodies of a row: ring filling up (VALID = 0, U, 2U, ...), then the steady loop
+// the bodies of a row: ring filling up (VALID = 0, U, 2U, ...), then the steady loop, then a guarded tail
 template <int PC, int U, int VALID>
 __device__ __forceinline__ void mac2_row(Mac2Walk& w, float2 (&h)[PC], float2 (&ring)[PC], size_t half2, int accumulate) {
     if constexpr (VALID >= PC) {
 #pragma unroll 1
-        while (w.to_do > 0) mac2_body<PC, U, PC>(w, h, ring, half2, accumulate);
+        while (w.to_do >= U) mac2_body<PC, U, PC, false>(w, h, ring, half2, accumulate);
+        if (w.to_do > 0) mac2_body<PC, U, PC, true>(w, h, ring, half2, accumulate);
     } else {
         if (w.to_do > 0) {
-            mac2_body<PC, U, VALID>(w, h, ring, half2, accumulate);
+            mac2_body<PC, U, VALID, true>(w, h, ring, half2, accumulate);
             mac2_row<PC, U, (VALID + U < PC ? VALID + U : PC)>(w, h, ring, half2, accumulate);
         }
     }
@@ -829,21 +833,19 @@ __global__ void __launch_bounds__(MAC2_NT, GFX_MAC2_MINB) fir_mac2_kernel(const 
         float2* Y = Ys + (size_t)((b - b0) * rm.c_out + c) * nblk * half2 + e;
 #pragma unroll
         for (int p = 0; p < PC; ++p) ring[p] = make_float2(0.f, 0.f);
-        // prologue of the copy ring: input blocks 0 .. D-2 (one commit group each, empty past the end)
-        Mac2Walk w;
-        w.xn = X; w.yp = Y + (size_t)p0 * half2; w.s_in = stage; w.s_out = stage; w.s_end = stage + MAC2_D * MAC2_NT;
-        w.to_copy = nblk - p0; w.to_do = nblk - p0;
-#pragma unroll
-        for (int d = 0; d < MAC2_D - 1; ++d) {
-            if (w.to_copy > 0) cp_async_small<8>(w.s_in, w.xn);
-            cp_async_commit();
-            w.xn += half2; --w.to_copy; w.s_in += MAC2_NT;
-        }
+        // prologue of the copy ring: the U blocks of the first body
 #ifdef GFX_MAC2_U
         constexpr int U = GFX_MAC2_U;
 #else
         constexpr int U = 4;  // (measured on B200 at 24 partitions: U = 4 1.655 ms per reverb-shape convolution, U = 8 1.737 ms)
 #endif
+        static_assert(2 * U <= MAC2_D, "two stage sets of U blocks");
+        Mac2Walk w;
+        w.x = X; w.yp = Y + (size_t)p0 * half2; w.s_read = stage; w.s_write = stage + U * MAC2_NT;
+        w.last = nblk - 1 - p0; w.to_do = nblk - p0; w.next = U;
+#pragma unroll
+        for (int u = 0; u < U; ++u) cp_async_small<8>(w.s_read + u * MAC2_NT, X + (size_t)min(u, w.last) * half2);
+        cp_async_commit();
         mac2_row<PC, U, 0>(w, h, ring, (size_t)half2, accumulate);
         cp_async_wait<0>();
         if (blockIdx.x == 0 && threadIdx.x < 32) {
