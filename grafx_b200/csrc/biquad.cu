@@ -851,6 +851,9 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
         if (X2) {
             // (fully unrolling the section loop per K was measured: no gain -- ptxas keeps its
             //  register-pair copies -- and a bigger instruction footprint; generic K only)
+            // (occupancy was measured on B200, profiles/r02_cascade_occupancy.txt: 5 CTAs / 96 registers 215 us, 6 CTAs / 80
+            //  registers 314 us vs 201 us here -- the spills cost more than the extra warps hide; the end states of the
+            //  zero-state pass as dot products with the tabulated impulse response: 207 us and less accurate)
             auto kern2 = biquad_cascade_x2_kernel<16 / X2_WARPS, 0>;
             static size_t configured2_dev[64] = {0};
             size_t& configured2 = configured2_dev[device_slot()];
