@@ -849,29 +849,17 @@ __global__ void __launch_bounds__(SPEC_NT(C)) dynamics_spec_kernel(const DynPara
     float* y0 = p.y + (size_t)row * C * (size_t)p.L;
     long long n = n0;
     if (p.aligned) {
-        // warm-up: scalar steps up to a 16-byte boundary, then float4 blocks (the chunk start is a multiple of 4)
-        for (; n < p0 && (n & 3); ++n) {
-            float v[C];
+        // one loop over 16-byte groups for warm-up and chunk (the warm-up may start up to 3 samples early: harmless),
+        // the next group loaded while this one is walked; only groups inside the chunk are stored
+        n = n0 & ~3LL;
+        float4 q[C], qn[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) v[c] = __ldg(x0 + (size_t)c * p.L + n);
-            sample(v);
-        }
-        for (; n + 4 <= p0; n += 4) {
-            float4 q[C];
+        for (int c = 0; c < C; ++c) q[c] = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)c * p.L + n));
+#pragma unroll 1
+        for (; n < n1; n += 4) {
+            const long long nn = n + 4 < n1 ? n + 4 : n;
 #pragma unroll
-            for (int c = 0; c < C; ++c) q[c] = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)c * p.L + n));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float v[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) v[c] = reinterpret_cast<const float*>(&q[c])[i];
-                sample(v);
-            }
-        }
-        for (; n + 4 <= n1; n += 4) {
-            float4 q[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) q[c] = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)c * p.L + n));
+            for (int c = 0; c < C; ++c) qn[c] = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)c * p.L + nn));
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float v[C];
@@ -881,9 +869,14 @@ __global__ void __launch_bounds__(SPEC_NT(C)) dynamics_spec_kernel(const DynPara
 #pragma unroll
                 for (int c = 0; c < C; ++c) reinterpret_cast<float*>(&q[c])[i] = v[c];
             }
+            if (n >= p0) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(y0 + (size_t)c * p.L + n) = q[c];
+                for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(y0 + (size_t)c * p.L + n) = q[c];
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) q[c] = qn[c];
         }
+        return;
     }
     for (; n < n1; ++n) {
         float v[C];
