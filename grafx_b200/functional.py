@@ -177,6 +177,9 @@ def fir_conv(x: torch.Tensor, h: torch.Tensor, mode: str = "causal", h_repeat: i
     B, cx, L = x3.shape
     _, ch, N = h3.shape
     assert cx == ch or cx == 1 or ch == 1, "channel mismatch between signal and filter"
+    if x.dtype == torch.float64 or h.dtype == torch.float64:
+        raise TypeError("the FFT convolution engine is float32 only (upstream would compute float64 inputs in float64): "
+                        "cast the operands explicitly; the biquad cascade has a float64 kernel")
     if _wants_grad(x, h):
         if mode != "causal" or h_repeat != 1:
             raise NotImplementedError("the backward pass of fir_conv covers mode='causal' with per-item filters")
@@ -359,6 +362,12 @@ def envelope(x: torch.Tensor, z: torch.Tensor, smoother: str, detect: str | None
 def drywet_mix(dry: torch.Tensor, wet: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     """y = w * wet + (1 - w) * dry, w per batch item used as given (container.py:62-67)."""
     _cabi.require_cuda(dry, wet, weight)
+    if dry.shape != wet.shape and dry.ndim == 3 and wet.ndim == 3 and dry.shape[0] == wet.shape[0] and dry.shape[2] == wet.shape[2]:
+        # upstream mixes by tensor broadcasting (container.py:62-65): a mono side follows the stereo one
+        if dry.shape[1] == 1:
+            dry = dry.expand_as(wet)
+        elif wet.shape[1] == 1:
+            wet = wet.expand_as(dry)
     if _wants_grad(dry, wet, weight):
         from .autograd import DryWetFn
 

@@ -16,7 +16,11 @@ class StereoGain(nn.Module):
     """Per-channel gain exp(log_gain) (stereo.py:9-41)."""
 
     def forward(self, input_signals, log_gain):
-        assert input_signals.ndim == 3 and log_gain.shape[-1] == input_signals.shape[1]
+        assert input_signals.ndim == 3
+        if input_signals.shape[1] == 1 and log_gain.shape[-1] == 2:
+            # mono in, stereo out: upstream's `input * exp(log_gain)[:, :, None]` broadcasts the channel axis (stereo.py:38-41)
+            input_signals = input_signals.expand(-1, 2, -1)
+        assert log_gain.shape[-1] == input_signals.shape[1]
         return F_.pointwise("gain", input_signals, log_gain)
 
     def parameter_size(self):

@@ -273,3 +273,22 @@ def test_ballistics_speculative_chunks_match_the_row_walk(C, L):
     y_ref = O.noisegate(y1, **{k: v[rows] for k, v in pg.items()}, energy_smoother="ballistics")
     for i, r in enumerate(rows):
         assert_close(y_spec[r], y_ref[i], f"spec row {r}")
+
+
+def test_channel_broadcast_and_float64_guard():
+    """Mono -> stereo broadcasting of StereoGain and the DryWet mix as upstream's tensor expressions do
+    (stereo.py:38-41, container.py:62-65); float64 FIR operands fail loudly instead of being computed in float32."""
+    import grafx_b200.functional as F_
+    import grafx_b200.processors as P
+
+    torch.manual_seed(77)
+    x1 = torch.randn(3, 1, 4001, device="cuda")
+    lg = torch.randn(3, 2, device="cuda")
+    y = P.StereoGain().cuda()(x1, lg)
+    assert torch.allclose(y, x1 * torch.exp(lg)[:, :, None], rtol=1e-6, atol=1e-7)
+    wet = torch.randn(3, 2, 4001, device="cuda")
+    w = torch.rand(3, 1, device="cuda")
+    mixed = F_.drywet_mix(x1, wet, w)
+    assert torch.allclose(mixed, w.view(-1, 1, 1) * wet + (1 - w.view(-1, 1, 1)) * x1, rtol=1e-6, atol=1e-6)
+    with pytest.raises(TypeError):
+        F_.fir_conv(wet.double(), torch.randn(3, 2, 33, device="cuda", dtype=torch.float64))

@@ -104,3 +104,28 @@ def test_state_dict_keys_match_the_reference():
         assert ours == keys, (name, sorted(set(ours) ^ set(keys)))
         checked += 1
     assert checked >= 25
+
+
+def test_bench_config_is_identical_in_both_arms_and_the_shard_covers_the_batch():
+    """bench.py: the `config` object is built by one function for both arms (the driver compares them), and the
+    config-5 shard hands every one of the 128 renders to exactly one rank, in whole chunks, for 1 / 2 / 4 / 8 ranks."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for world in (1, 2, 4, 8):
+        assert bench.config_of("cfg5", world) == bench.config_of("cfg5", world)
+        total = 0
+        for rank in range(world):
+            g = bench.GraphWorkload(world, rank)
+            assert g.n_chunks * g.chunk == g.B_local and g.chunk <= 16
+            total += g.B_local
+        assert total == 128
+        assert bench.config_of("cfg5", world)["renders_per_gpu"] == 128 // world
+    for name in ("cfg1", "cfg2", "cfg2lf", "cfg3", "cfg3b", "cfg4", "cfg4b"):
+        wl = bench.Workload(name)
+        x, prm = wl.host_inputs(B=2)
+        assert x.shape == (2, wl.C, wl.L) and wl.alg_bytes() >= 8 * wl.samples()
+        assert set(bench.config_of(name, 1)) == {"workload", "batch", "channels", "length", "l2", "parallelism"}
