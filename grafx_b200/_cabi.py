@@ -66,6 +66,7 @@ SIGNATURES = {
     "gfx_fir_set_tuning": (c_int, [c_int, c_int]),
     "gfx_fir_set_long_mode": (c_int, [c_int, c_int]),
     "gfx_fir_set_mac_form": (c_int, [c_int]),
+    "gfx_fir_set_sweep_mb": (c_int, [c_int]),
     "gfx_fir_conv_midside_ir_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_int,
                                             c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gfx_reverb_ir_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

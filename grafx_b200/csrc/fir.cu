@@ -1128,6 +1128,7 @@ __global__ void fft_plan_pass_kernel(float2* tab, int M, int R) {
 static int g_long_n = 4096;  // partition size of the long-filter path (tunable: gfx_fir_set_tuning).  Measured on B200 at the
                              // BASELINE reverb shape (profiles/r02_*): 4096-point FFT kernels run 4 CTAs per SM (955 us for the three
                              // FFT kernels vs 1350 us at 8192 points, 2 CTAs per SM); fir_mac2_kernel keeps the 24 partitions in one pass
+static int g_sweep_mb = 1536; // spectra workspace per sweep of the long-filter path (gfx_fir_set_sweep_mb)
 static int g_mac_form = 1;   // 0: fir_mac_kernel (<= 12 partitions per pass) when it applies; 1: fir_mac2_kernel
 static int g_mid_n = 8192;   // FFT size for 2048 < taps <= g_mid_n / 2 (longer single-partition filters: 16384)
 
@@ -1366,6 +1367,12 @@ int gfx_fir_set_long_mode(int mode, int lookahead) {
     return GFX_OK;
 }
 
+int gfx_fir_set_sweep_mb(int mb) {
+    if (mb < 8 || mb > 16384) return GFX_ERR_INVALID;
+    gfx::g_sweep_mb = mb;
+    return GFX_OK;
+}
+
 int gfx_fir_set_mac_form(int form) {
     if (form != 0 && form != 1) return GFX_ERR_INVALID;
     gfx::g_mac_form = form;
@@ -1411,7 +1418,7 @@ size_t gfx_fir_conv_workspace_bytes(int batch, int cx, int ch, long long L, int 
     if (gfx::g_long_mode == 1 && P <= gfx::MAC_MAX_PC && n == 8192)
         return gfx::upols_ctr_bytes(batch) + (size_t)gfx::upols_r() * per_item;  // pipelined launch: a ring of item slots
     // spectra of up to ~1.5 GB worth of batch items per sweep (every kernel of a sweep then has several full waves)
-    size_t items = ((size_t)1536 << 20) / per_item;
+    size_t items = ((size_t)gfx::g_sweep_mb << 20) / per_item;
     if (items < 1) items = 1;
     if (items > (size_t)batch) items = batch;
     return items * per_item;

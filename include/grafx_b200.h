@@ -118,6 +118,9 @@ GFX_API int gfx_fir_set_long_mode(int mode, int lookahead); /* lookahead: pipeli
  * partitions per pass, the round-1 kernel, used when the filter has <= 12 partitions; kept for A/B measurements).
  * The two differ in summation order only (~1e-7 relative). */
 GFX_API int gfx_fir_set_mac_form(int form);
+/* spectra workspace per sweep of the long-filter path in MiB (default 1536; affects gfx_fir_conv_workspace_bytes).  Small
+ * sweeps keep the spectra in L2 between the kernels of a sweep at the price of more, smaller launches. */
+GFX_API int gfx_fir_set_sweep_mb(int mb);
 /* FIRFilter.forward (processors/filter.py:65-77): taps = normalize_impulse(tanh(fir_raw)) -- the activation and the
  * unit-energy scale are applied while the filter spectra are formed (one small reduction kernel + the convolution).
  * fir_raw [batch, ch, filter_len]; workspace: gfx_fir_conv_workspace_bytes(...) + 256 * ceil(4 batch / 256) bytes. */
