@@ -3,9 +3,10 @@ tensor primitives of render/core.py (:6-140) folded in.
 
 Same signature and return value: `(output_signals, intermediates_list, signal_buffer)`; accepts
 3-D `[|V0|, C, L]` or 4-D `[B, |V0|, C, L]` sources and any RenderData-like plan (the reference's
-own objects work: only attributes are read).  Forward only: `parameters_grad` /
-`input_signal_grad` are accepted for compatibility; nothing is recorded for autograd, and the call raises when
-autograd expects a gradient from it (tensors that require grad outside `torch.no_grad()`).
+own objects work: only attributes are read).  `parameters_grad` / `input_signal_grad` are accepted for compatibility.
+Under `torch.no_grad()` (or with detached tensors) the loop writes into one signal buffer in place; when autograd
+expects a gradient (a tensor that requires grad, grad mode on) the same plan runs functionally
+(`_render_grafx_functional`): differentiable for the processors that have a backward pass, a loud error for the rest.
 
 What runs where: processors are the CUDA kernels of this package; node-axis aggregation
 (`sum` / `scatter`) is csrc/elementwise.cu:node_sum_kernel reading and writing slices of the
@@ -82,11 +83,10 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
     batched = (lambda t: post(expand(t))) if ndim == 4 else (lambda t: t)
     if torch.is_grad_enabled() and (input_signals.requires_grad or _any_requires_grad(per_type_parameters)
                                     or _any_requires_grad(common_parameters)):
-        # the loop writes processor outputs into slices of one signal buffer in place: nothing is recorded for
-        # autograd, and saying so beats returning a result whose gradients are silently zero
-        raise NotImplementedError(
-            "render_grafx is forward-only here: call it under torch.no_grad() (or with detached tensors).  Gradients "
-            "exist at the processor level for the IIR family and FIRFilter (grafx_b200/autograd.py).")
+        # the loop below writes processor outputs into slices of one signal buffer in place, which records nothing for
+        # autograd: training mode takes the functional path instead (no in-place write; processors without a backward
+        # pass raise there -- a loud error beats a result whose gradients are silently zero)
+        return _render_grafx_functional(processors, input_signals, per_type_parameters, render_data, common_parameters)
     input_signals = input_signals.detach()
 
     # create_signal_buffer (render/core.py:6-33)
@@ -179,6 +179,131 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
             signal_buffer.index_copy_(0, dest.idx.to(signal_buffer.device), output_signals)
         else:
             raise Exception(f"The provided inplace write method is not available: {dest.method}.")
+    if ndim == 4:
+        return output_signals.transpose(0, 1), intermediates_list, signal_buffer.transpose(0, 1)
+    return output_signals, intermediates_list, signal_buffer
+
+
+def _render_grafx_functional(processors, input_signals, per_type_parameters, render_data, common_parameters):
+    """render_grafx for training mode: the same plan evaluated without in-place writes, so that autograd sees every step
+    (upstream clones its reads for the same reason, render/graph.py:108).  Node signals are kept as the list of blocks
+    the render orders produced (node-major, `[nodes, (B,) C, L]`); a read is a block, a narrow of one, or -- irregular
+    plans -- an index into their concatenation; aggregation is torch's `sum` / `index_add`; processors get fresh
+    outputs (those with a backward pass, grafx_b200/autograd.py, carry the graph; the others raise).  Returns the same
+    triple as the forward path; the signal buffer is the concatenation of the blocks."""
+    method = render_data.method
+    ndim = input_signals.ndim
+    if ndim == 4:
+        batch_size, num_sources, channels, audio_len = input_signals.shape
+        expand = lambda t: t.unsqueeze(1).expand(t.shape[0], batch_size, *t.shape[1:])  # noqa: E731
+        flat = lambda t: t.reshape(-1, *t.shape[2:])  # noqa: E731
+        batched = lambda t: flat(expand(t))  # noqa: E731
+        src0 = input_signals.to(torch.float32).transpose(0, 1)      # node-major view [V0, B, C, L]
+    elif ndim == 3:
+        batch_size = None
+        num_sources, channels, audio_len = input_signals.shape
+        flat = batched = lambda t: t  # noqa: E731
+        src0 = input_signals.to(torch.float32)
+    else:
+        raise Exception(f"input_signal has shape of {input_signals.shape} ({ndim} ndims), which is not 3 or 4 dims.")
+    num_nodes = int(render_data.num_nodes)
+    blocks = {0: src0}                      # first node index -> block of consecutive nodes
+    owner = [0] * num_sources + [None] * (num_nodes - num_sources)
+
+    def whole_buffer():
+        missing = [i for i, o in enumerate(owner) if o is None]
+        parts, i = [], 0
+        while i < num_nodes:
+            if owner[i] is None:  # nodes not rendered yet read as zeros (upstream's buffer starts as zeros)
+                j = i
+                while j < num_nodes and owner[j] is None:
+                    j += 1
+                parts.append(src0.new_zeros((j - i,) + tuple(src0.shape[1:])))
+                i = j
+            else:
+                b = blocks[owner[i]]
+                parts.append(b.narrow(0, i - owner[i], min(b.shape[0] - (i - owner[i]), num_nodes - i)))
+                i += parts[-1].shape[0]
+        del missing
+        return torch.cat(parts, 0)
+
+    def read(access):
+        if access.method == "slice":
+            a, b = int(access.idx[0]), int(access.idx[1])
+            o = owner[a]
+            if o is not None and all(owner[i] == o for i in range(a, b)):
+                return blocks[o].narrow(0, a - o, b - a)
+            return whole_buffer().narrow(0, a, b - a)
+        if access.method == "index":
+            return whole_buffer().index_select(0, access.idx.to(src0.device))
+        raise Exception(f"The provided read method is not available: {access.method}.")
+
+    def write(access, value):
+        if access.method == "slice":
+            a, b = int(access.idx[0]), int(access.idx[1])
+            assert value.shape[0] == b - a
+            blocks[a] = value
+            for i in range(a, b):
+                owner[i] = a
+        elif access.method == "index":
+            idx = access.idx.tolist()
+            for k, node in enumerate(idx):
+                blocks[node] = value.narrow(0, k, 1)
+                owner[node] = node
+        else:
+            raise Exception(f"The provided inplace write method is not available: {access.method}.")
+
+    intermediates_list, output_signals = [], None
+    for i in range(1, int(render_data.max_order) + 1):
+        it = render_data.iter_list[i]
+        node_type = it.node_type
+        is_proc = node_type in processors
+        if not is_proc and node_type not in UTILITY_TYPES:
+            raise Exception(f"Wrong node type given: {node_type}")
+        inputs = []
+        for rd, agg in zip(it.source_reads, it.aggregations):
+            src = read(rd)
+            if agg.method == "sum":
+                src = src.sum(0, keepdim=True)
+            elif agg.method == "scatter":
+                idx = agg.idx.to(src.device)
+                n_dst = int(agg.idx.max()) + 1
+                src = src.new_zeros((n_dst,) + tuple(src.shape[1:])).index_add(0, idx, src)
+            elif agg.method != "none":
+                raise Exception(f"The provided aggregation method is not available: {agg.method}.")
+            inputs.append(flat(src).contiguous())
+        if is_proc:
+            parameters = _map_tensors(_read(per_type_parameters[node_type], it.parameter_read, 0), batched)
+            common_i = {}
+            if common_parameters is not None:
+                common_i = _map_tensors(_read(common_parameters, it.dest_write, 0), batched)
+                if isinstance(common_i, torch.Tensor):
+                    common_i = {"parameter": common_i}
+            if isinstance(parameters, torch.Tensor):
+                parameters = {"parameter": parameters}
+            output = processors[node_type](*inputs, **parameters, **common_i)
+            if isinstance(output, tuple):
+                output_signals, intermediates = output
+                intermediates_list.append(intermediates)
+            else:
+                output_signals = output
+        else:
+            output_signals = inputs
+        if isinstance(output_signals, list):
+            if len(output_signals) == 1:
+                output_signals = output_signals[0]
+            elif ndim == 3:
+                output_signals = torch.stack(output_signals, -3).view(-1, channels, audio_len)
+            else:
+                output_signals = torch.stack([o.view(-1, batch_size, channels, audio_len) for o in output_signals], 1)
+        if ndim == 4:
+            output_signals = output_signals.reshape(-1, batch_size, channels, audio_len)
+        write(it.dest_write, output_signals)
+    if method == "one-by-one":
+        assert ndim == 3
+        buf = whole_buffer()
+        return output_signals, intermediates_list, [buf[n:n + 1] for n in range(num_nodes)]
+    signal_buffer = whole_buffer()
     if ndim == 4:
         return output_signals.transpose(0, 1), intermediates_list, signal_buffer.transpose(0, 1)
     return output_signals, intermediates_list, signal_buffer

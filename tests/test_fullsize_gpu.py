@@ -292,3 +292,39 @@ def test_channel_broadcast_and_float64_guard():
     assert torch.allclose(mixed, w.view(-1, 1, 1) * wet + (1 - w.view(-1, 1, 1)) * x1, rtol=1e-6, atol=1e-6)
     with pytest.raises(TypeError):
         F_.fir_conv(wet.double(), torch.randn(3, 2, 33, device="cuda", dtype=torch.float64))
+
+
+def test_render_grafx_training_mode_reaches_the_processor_backward_passes():
+    """Grad mode through the graph API: in -> ParametricEqualizer -> StereoGain -> out bus with the CUDA processors that
+    have a backward pass (grafx_b200/autograd.py).  Forward values equal the in-place (no_grad) render; gradients equal
+    the same processors composed by hand; a plan with a forward-only processor raises instead of cutting the graph."""
+    import grafx_b200.processors as P
+    from grafx_b200.render import mixing_console_plan, render_grafx
+
+    torch.manual_seed(41)
+    T, B, L = 3, 2, 6000
+    procs = {"eq": P.ParametricEqualizer(num_filters=3, processor_channel="stereo", backend="lfilter").cuda(), "gain": P.StereoGain().cuda()}
+    rd = mixing_console_plan(T, ["eq", "gain"])
+    x = torch.randn(B, T, 2, L, device="cuda", requires_grad=True)
+    prm = {"eq": {k: (0.3 * torch.randn(T, 2, 3, device="cuda")).requires_grad_(True) for k in ("w0", "q_inv", "log_gain")},
+           "gain": {"log_gain": (0.3 * torch.randn(T, 2, device="cuda")).requires_grad_(True)}}
+    out, inter, buf = render_grafx(procs, x, prm, rd)
+    assert out.requires_grad and buf.requires_grad and tuple(buf.shape) == (B, 3 * T + 1, 2, L)
+    with torch.no_grad():
+        out0, _, buf0 = render_grafx(procs, x, prm, rd)
+    assert rel_l2(out.detach().cpu(), out0.cpu()) < 1e-6 and rel_l2(buf.detach().cpu(), buf0.cpu()) < 1e-6
+    w = torch.randn_like(out)
+    leaves = [x] + list(prm["eq"].values()) + [prm["gain"]["log_gain"]]
+    grads = torch.autograd.grad((out * w).sum(), leaves)
+    # the same computation by hand (batch-major rows here, node-major inside render_grafx)
+    rows = x.reshape(B * T, 2, L)
+    rep = lambda t: t.unsqueeze(0).expand(B, *t.shape).reshape(B * T, *t.shape[1:])  # noqa: E731
+    y = procs["gain"](procs["eq"](rows, **{k: rep(v) for k, v in prm["eq"].items()}), rep(prm["gain"]["log_gain"]))
+    ref = y.reshape(B, T, 2, L).sum(1, keepdim=True)
+    ref_grads = torch.autograd.grad((ref * w).sum(), leaves)
+    for g, r in zip(grads, ref_grads):
+        assert rel_l2(g.cpu(), r.cpu()) < 1e-4, rel_l2(g.cpu(), r.cpu())
+    procs2 = {"eq": procs["eq"], "gain": P.Compressor().cuda()}
+    prm2 = {"eq": prm["eq"], "gain": {k: torch.zeros(T, v, device="cuda", requires_grad=True) for k, v in procs2["gain"].parameter_size().items()}}
+    with pytest.raises(NotImplementedError):
+        render_grafx(procs2, x, prm2, rd)

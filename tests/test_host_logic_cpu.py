@@ -75,15 +75,43 @@ def test_bench_gpu_affinity_helper_degrades_without_nvml():
     assert cpus is None or len(cpus) > 0
 
 
-def test_render_grafx_refuses_to_cut_the_autograd_graph():
+def test_render_grafx_training_mode_is_functional_and_differentiable():
+    """Grad mode: the plan is evaluated without in-place writes (host logic checked here with plain torch modules on
+    the CPU: slice / sum / scatter / index paths, 3-D and 4-D sources, gradients to sources and parameters)."""
+    import torch.nn as nn
     from grafx_b200.render import mixing_console_plan, render_grafx
+    from grafx_b200.render.plan import RenderData, _AggregationData as Agg, _SingleRenderData as It, _TensorAccessData as Acc
 
-    rd = mixing_console_plan(2, ["eq"])
-    prm = {"eq": {"w0": torch.zeros(2, 1, 3, requires_grad=True)}}
-    with pytest.raises(NotImplementedError):
-        render_grafx({}, torch.zeros(2, 2, 64), prm, rd)
-    with pytest.raises(NotImplementedError):
-        render_grafx({}, torch.zeros(2, 2, 64, requires_grad=True), {}, rd)
+    class Gain(nn.Module):
+        def forward(self, x, g):
+            return x * g.view(-1, 1, 1)
+
+    rd = mixing_console_plan(3, ["gain", "gain"])
+    for shape in ((3, 2, 16), (4, 3, 2, 16)):
+        x = torch.randn(*shape, requires_grad=True)
+        g = torch.randn(3, 1, requires_grad=True)
+        out, inter, buf = render_grafx({"gain": Gain()}, x, {"gain": {"g": g}}, rd)
+        node_axis = 0 if len(shape) == 3 else 1
+        ref = (x * (g * g).view(-1, 1, 1)).sum(node_axis, keepdim=True)
+        assert torch.allclose(out, ref, atol=1e-6) and inter == []
+        assert buf.shape[node_axis] == rd.num_nodes and torch.allclose(buf.narrow(node_axis, 0, 3), x)
+        assert torch.allclose(buf.narrow(node_axis, 3, 3), x * g.view(-1, 1, 1), atol=1e-6)
+        gx, gg = torch.autograd.grad(out.square().sum(), (x, g))
+        rx, rg = torch.autograd.grad(ref.square().sum(), (x, g))
+        assert torch.allclose(gx, rx, atol=1e-5) and torch.allclose(gg, rg, atol=1e-4)
+    # irregular plan: index read, scatter into two buses, index write
+    idx = torch.tensor([2, 0, 3, 1])
+    rd2 = RenderData("beam", 10, 2, True, [
+        It("in", [Acc("none", ())], [Agg("none")], Acc("slice", (0, 4)), Acc("slice", (0, 4))),
+        It("gain", [Acc("index", idx)], [Agg("none")], Acc("index", idx), Acc("index", torch.tensor([4, 5, 6, 7]))),
+        It("mix", [Acc("slice", (4, 8))], [Agg("scatter", torch.tensor([0, 1, 1, 0]))], Acc("slice", (0, 2)), Acc("slice", (8, 10)))])
+    x = torch.randn(4, 2, 8, requires_grad=True)
+    g = torch.randn(4, 1, requires_grad=True)
+    out, _, buf = render_grafx({"gain": Gain()}, x, {"gain": {"g": g}}, rd2)
+    y = x[idx] * g[idx].view(-1, 1, 1)
+    ref = torch.stack([y[0] + y[3], y[1] + y[2]])
+    assert torch.allclose(out, ref, atol=1e-6) and torch.allclose(buf[8:10], ref, atol=1e-6)
+    assert torch.allclose(torch.autograd.grad(out.sum(), g)[0], torch.autograd.grad(ref.sum(), g)[0], atol=1e-5)
 
 
 def test_state_dict_keys_match_the_reference():
