@@ -181,11 +181,15 @@ def fir_conv(x: torch.Tensor, h: torch.Tensor, mode: str = "causal", h_repeat: i
         raise TypeError("the FFT convolution engine is float32 only (upstream would compute float64 inputs in float64): "
                         "cast the operands explicitly; the biquad cascade has a float64 kernel")
     if _wants_grad(x, h):
-        if mode != "causal" or h_repeat != 1:
-            raise NotImplementedError("the backward pass of fir_conv covers mode='causal' with per-item filters")
         from .autograd import fir_conv_autograd
 
-        y = fir_conv_autograd(x3, h3)
+        if h_repeat != 1:  # (the expand is differentiable: autograd sums the gradient over the run)
+            h3 = h3.repeat_interleave(h_repeat, 0)
+        if mode == "zerophase":
+            # y[n] = sum_k h[k] x[n + N//2 - k]: the causal convolution of the right-padded signal, read N//2 later
+            y = fir_conv_autograd(torch.nn.functional.pad(x3, (0, N // 2)), h3)[..., N // 2: N // 2 + L]
+        else:
+            y = fir_conv_autograd(x3, h3)
         return y.squeeze(1) if squeeze else y
     x3, h3 = _prep(x3, torch.float32), _prep(h3, torch.float32)
     y = torch.empty(B, max(cx, ch), L, dtype=torch.float32, device=x.device) if squeeze else _new_output((B, max(cx, ch), L), torch.float32, x.device)
@@ -268,7 +272,10 @@ def dynamics_chain(x: torch.Tensor, stages: list[dict], iir_len: int = 16384) ->
     gain_smoother, gain_smooth_in_log, log_threshold, log_ratio, log_knee, z_alpha_pre,
     z_alpha_post (tensors with leading dim B)."""
     _cabi.require_cuda(x)
-    _no_backward("dynamics_chain", x, *[v for st in stages for v in st.values() if isinstance(v, torch.Tensor)])
+    if _wants_grad(x, *[v for st in stages for v in st.values() if isinstance(v, torch.Tensor)]):
+        from . import training
+
+        return training.dynamics_chain(x, stages, iir_len)  # (ballistics smoothers raise there)
     assert x.ndim == 3
     B, C, L = x.shape
     x = _prep(x, torch.float32)
@@ -605,7 +612,13 @@ def pointwise(op: str, x: torch.Tensor, p0=None, p1=None, p2=None, p3=None, dc=N
         from .autograd import GainFn
 
         return GainFn.apply(x.to(torch.float32).contiguous(), p0.to(torch.float32).contiguous())
-    _no_backward("pointwise", x, p0, p1, p2, p3, dc)
+    if _wants_grad(x, p0, p1, p2, p3, dc):
+        from . import training
+
+        if op == "scale_add":  # ParallelMix accumulation (container.py:203-216)
+            term = p0.reshape(-1, 1, 1) * x
+            return term if (out is None or not (flags & 4)) else out + term
+        return training.pointwise(op, x, p0, p1, p2, p3, dc, order, flags)
     assert x.ndim == 3
     x = _prep(x, torch.float32)
     B, C, L = x.shape

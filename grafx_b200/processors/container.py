@@ -93,7 +93,9 @@ class ParallelMix(nn.Module):
             if isinstance(out, tuple):
                 out, intermediates[k] = out
             w = weights[..., i].reshape(-1, 1)
-            if mix is None:
+            if F_._wants_grad(out, w):  # training mode: no in-place accumulation
+                mix = F_.pointwise("scale_add", out, w, flags=0 if mix is None else 4, out=mix)
+            elif mix is None:
                 mix = torch.empty_like(out)
                 F_.pointwise("scale_add", out, w, out=mix)
             else:

@@ -63,6 +63,8 @@ class STFTMaskedNoiseReverb(nn.Module):
         # un-normalised response (+ row energies) in its final channel layout; normalize_impulse
         # (reverb.py:215-228) happens inside the convolution while the filter spectra are formed
         to_lr = self.processor_channel == "pseudo_midside"
+        if F_._wants_grad(input_signals, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude):
+            return self._forward_training(input_signals, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude)
         # render_grafx (4-D sources) repeats every node's parameters over the batch of renders: synthesise each
         # response (and its spectra) once
         rep = F_.parameter_repeat()
@@ -77,6 +79,26 @@ class STFTMaskedNoiseReverb(nn.Module):
         if self.processor_channel == "midside":
             return F_.ms_to_lr(F_.fir_conv_midside_ir(F_.lr_to_ms(input_signals), ir_raw, energy, to_lr=False, h_repeat=rep))
         return F_.fir_conv_midside_ir(input_signals, ir_raw, energy, to_lr=to_lr, h_repeat=rep)
+
+    def _forward_training(self, input_signals, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude):
+        """Grad mode (grafx_b200/training.py): the response as upstream states it (PyTorch istft, O(parameters x frames)),
+        the channel-mode epilogue of reverb.py:215-228, the convolution on the differentiable FIR engine."""
+        from .. import training
+
+        if F_._wants_grad(init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude):
+            genv = gain_env_log_magnitude if self.gain_envelope else None
+            noise = self._noise(init_log_magnitude.shape[0], init_log_magnitude.device)
+            ir = training.stft_reverb_ir(noise, init_log_magnitude, delta_log_magnitude, genv, self.window, self.ir_len,
+                                         self.n_fft, self.hop_length)
+        else:  # only the audio needs a gradient: the synthesis kernel, no graph
+            with torch.no_grad():
+                ir = self.compute_ir(init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude)
+        if self.processor_channel == "pseudo_midside":
+            ir = torch.stack([ir[:, 0] + ir[:, 1], ir[:, 0] - ir[:, 1]], 1)
+        ir = F_.normalize_impulse(ir)
+        if self.processor_channel == "midside":
+            return F_.ms_to_lr(F_.fir_conv(F_.lr_to_ms(input_signals), ir, "causal"))
+        return F_.fir_conv(input_signals, ir, "causal")
 
     def parameter_size(self):
         size = {"init_log_magnitude": (2, self.num_bins), "delta_log_magnitude": (2, self.num_bins)}

@@ -861,16 +861,19 @@ def test_ops_without_backward_fail_loudly_in_grad_mode():
     import grafx_b200.processors as P
 
     x = torch.randn(2, 2, 4096, device="cuda")
-    comp = P.Compressor().cuda()
+    comp = P.Compressor(energy_smoother="ballistics").cuda()  # (one-pole smoothers train: grafx_b200/training.py)
     prm = {k: torch.zeros(2, v, device="cuda", requires_grad=True) for k, v in comp.parameter_size().items()}
     with pytest.raises(NotImplementedError):
         comp(x, **prm)
     with torch.no_grad():
         assert comp(x, **prm).shape == x.shape
+    import grafx_b200.functional as F_
+
+    with pytest.raises(NotImplementedError):  # the stand-alone smoothers / followers are forward-only
+        F_.envelope(x[:, 0], torch.zeros(2, 1, device="cuda", requires_grad=True), "iir")
+    fns = P.FilteredNoiseShapingReverb(ir_len=2000, noise_randomness="fixed").cuda()
     with pytest.raises(NotImplementedError):
-        P.SideGainImager().cuda()(x, torch.zeros(2, 1, device="cuda", requires_grad=True))
-    with pytest.raises(NotImplementedError):  # zero-phase slice of the FIR engine: forward only
-        P.NewZeroPhaseFIREqualizer(num_frequency_bins=64).cuda()(x, torch.zeros(2, 1, 64, device="cuda", requires_grad=True))
+        fns(x, **{k: torch.zeros(2, *v, device="cuda", requires_grad=True) for k, v in fns.parameter_size().items()})
 
 
 def test_design_kernel_matches_torch_statement():
@@ -895,3 +898,38 @@ def test_design_kernel_matches_torch_statement():
     p = [torch.randn(7, 6, device="cuda") for _ in range(5)]
     for a, b in zip(F_.biquad_design("svf", *p), D.state_variable(*p)):
         assert torch.allclose(a, b, rtol=5e-6, atol=1e-5)
+
+
+TRAINABLE_NEXT = ["next_tanhdistortion", "next_piecewisetanhdistortion", "next_powerdistortion", "next_chebyshevdistortion",
+                  "next_sidegainimager", "next_parallelmix", "next_zpfir", "next_multitapdelay_1", "next_approxcompressor",
+                  "next_approxnoisegate"]
+
+
+@pytest.mark.parametrize("name", fixture_names(TRAINABLE_NEXT))
+def test_training_mode_statements_vs_fixture_and_float64_autograd(name):
+    """Grad mode of the memoryless processors, ParallelMix, the zero-phase FIR equalizers, MultitapDelay and the Approx
+    dynamics (grafx_b200/training.py + the differentiable FIR engine): the forward value still matches the reference
+    fixture, the gradient of sum(w y) with respect to the audio matches float64 autograd through the oracle."""
+    x, params, meta, y_ref, extra = load(name)
+    kw = meta["kwargs"]
+    proc = build_processor(name, kw)
+    xc = x.cuda().requires_grad_(True)
+    pc = {k: v.cuda().requires_grad_(True) if v.is_floating_point() else v.cuda() for k, v in params.items()}
+    if class_of(name) == "ParallelMix":
+        nested = {}
+        for k, v in pc.items():
+            if "__" in k:
+                nested.setdefault(k.split("__")[0], {})[k.split("__")[1]] = v
+        out = proc(xc, pc["parallel_weights"], **nested)
+    else:
+        out = proc(xc, **pc)
+    y = out[0] if isinstance(out, tuple) else out
+    assert y.requires_grad
+    assert_close(y.detach().cpu(), y_ref, name + ":training forward")
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(y_ref.shape, generator=g)
+    gx = torch.autograd.grad((y * w.cuda()).sum(), xc)[0].cpu()
+    x64 = x.double().requires_grad_(True)
+    y64 = oracle_call(name, x64, {k: v.double() if v.is_floating_point() else v for k, v in params.items()}, kw, extra=extra)
+    gx64 = torch.autograd.grad((y64 * w.double()).sum(), x64)[0].float()
+    assert rel_l2(gx, gx64) < 5e-4, (name, rel_l2(gx, gx64))
