@@ -89,7 +89,18 @@ __global__ void __launch_bounds__(256) node_sum_kernel(const float* __restrict__
         float* out = dst + b * dst_bs + (long long)j * dst_ns;
         if (vec) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < n_src; ++s) {
+            int s = 0;
+            if (!index) {
+                // plain bus sum: eight independent 16-byte loads in flight per thread (same summation order)
+                for (; s + 8 <= n_src; s += 8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = ldg_stream(reinterpret_cast<const float4*>(sb + (long long)(s + u) * src_ns) + q);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+                }
+            }
+            for (; s < n_src; ++s) {
                 if (index && index[s] != j) continue;
                 const float4 v = ldg_stream(reinterpret_cast<const float4*>(sb + (long long)s * src_ns) + q);
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -123,14 +134,15 @@ __global__ void __launch_bounds__(256) node_copy_kernel(const float* __restrict_
         d = dst + b * dst_bs + j * dst_ns;
     };
     if (vec) {
-        for (; i + 3 * stride < total; i += 4 * stride) {
-            const float* s[4]; float* d[4]; long long q[4]; float4 v[4];
+        constexpr int NU = 4;  // independent 16-byte loads in flight per thread (8 measured: no change, 5.5 TB/s either way)
+        for (; i + (NU - 1) * stride < total; i += NU * stride) {
+            const float* s[NU]; float* d[NU]; long long q[NU]; float4 v[NU];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) locate(i + u * stride, s[u], d[u], q[u]);
+            for (int u = 0; u < NU; ++u) locate(i + u * stride, s[u], d[u], q[u]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ldg_stream(reinterpret_cast<const float4*>(s[u]) + q[u]);
+            for (int u = 0; u < NU; ++u) v[u] = ldg_stream(reinterpret_cast<const float4*>(s[u]) + q[u]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) stg_stream(reinterpret_cast<float4*>(d[u]) + q[u], v[u]);
+            for (int u = 0; u < NU; ++u) stg_stream(reinterpret_cast<float4*>(d[u]) + q[u], v[u]);
         }
         for (; i < total; i += stride) {
             const float* s; float* d; long long q;

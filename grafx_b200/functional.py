@@ -1,7 +1,9 @@
 """Tensor-level wrappers around the C ABI (include/grafx_b200.h).  Each function validates
 shapes the way the reference does (bare asserts / ValueError), makes the operands contiguous,
 allocates the output and the scratch workspace with torch (device memory plumbing only) and
-enqueues the kernel on the current CUDA stream.  Forward only: inputs are detached.
+enqueues the kernel on the current CUDA stream.  Without autograd (the hot path) inputs are detached and the fused
+kernels run; when autograd expects a gradient the differentiable variants take over (autograd.py, training.py) or, where
+none exists, the call raises.
 """
 from __future__ import annotations
 

@@ -1,3 +1,4 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
-timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_fullsize_gpu.py -q -m gpu -k "training or trains or without_backward or backward or next_" 2>&1 | grep -E "Error|error|assert|^E |passed|failed|FAILED" | head -40
+timeout 300 python tools/node_time.py
+timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_fullsize_gpu.py -q -m gpu -k "render or node or cfg5" 2>&1 | tail -3
