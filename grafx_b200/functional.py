@@ -355,10 +355,10 @@ def envelope(x: torch.Tensor, z: torch.Tensor, smoother: str, detect: str | None
     sm = _SMOOTHER[smoother]
     assert sm in (1, 2)
     x3 = _prep(x3, torch.float32)
-    z = _prep(z, torch.float32).reshape(B, -1)
-    assert z.shape[1] == sm, f"z_alpha has {z.shape[1]} columns, expected {sm}"
     y = torch.empty(B, L, dtype=torch.float32, device=x.device)
     if y.numel():
+        z = _prep(z, torch.float32).reshape(B, -1)
+        assert z.shape[1] == sm, f"z_alpha has {z.shape[1]} columns, expected {sm}"
         L_ = _cabi.lib()
         ws = _cabi.workspace(L_.gfx_dynamics_workspace_bytes(B, 1), x.device)
         with torch.cuda.device(x.device):

@@ -232,7 +232,7 @@ def test_render_common_parameters_reach_the_processor():
 
 
 # ------------------------------------------------------------------ ballistics: warm-up chunks vs the row walk
-@pytest.mark.parametrize("C,L", [(1, 65536), (2, 40001), (1, 3000)])
+@pytest.mark.parametrize("C,L", [(1, 65536), (2, 40001), (1, 3000), (1, 7), (2, 63), (2, 1)])
 def test_ballistics_speculative_chunks_match_the_row_walk(C, L):
     """dynamics_spec_kernel (independent chunks, contraction warm-up) against the sequential row walk of the same
     library (gfx_dynamics_set_ballistics_mode(0)) and the oracle: fast followers, a few slow rows that must fall back
@@ -267,6 +267,7 @@ def test_ballistics_speculative_chunks_match_the_row_walk(C, L):
     for r in range(B):
         assert rel_l2(y_spec[r], y_walk[r]) < 2e-6, (r, rel_l2(y_spec[r], y_walk[r]))
     assert torch.equal(y_spec[3], y_walk[3]) and torch.equal(y_spec[5], y_walk[5])   # the rows that fell back
+    assert torch.isfinite(y_spec).all()
     rows = [0, 3, 5, 7, 11]
     y1 = O.compressor(x[rows], **{k: v[rows] for k, v in pc.items()}, energy_smoother="ballistics", gain_smoother="ballistics",
                       gain_smooth_in_log=True)
@@ -422,3 +423,26 @@ def test_render_eq_compressor_reverb_trains_end_to_end():
         nonzero += int(float(g.abs().max()) > 0)
     # (the knee width only matters for samples inside the knee: its gradient may legitimately vanish)
     assert float(grads[0].abs().max()) > 0 and nonzero >= len(grads) - 1
+
+
+def test_new_entry_points_empty_batch_and_argument_errors():
+    """Empty batches return empty tensors without a launch; the raw ABI rejects bad arguments with error codes."""
+    import ctypes
+    import grafx_b200.functional as F_
+    import grafx_b200.processors as P
+    from grafx_b200 import _cabi
+
+    e = torch.empty(0, 2, 100, device="cuda")
+    assert F_.fir_filter(e, torch.empty(0, 2, 31, device="cuda")).shape == (0, 2, 100)
+    assert F_.envelope(torch.empty(0, 100, device="cuda"), torch.empty(0, 1, device="cuda"), "iir").shape == (0, 100)
+    comp = P.Compressor(energy_smoother="ballistics").cuda()
+    assert comp(e, **{k: torch.empty(0, v, device="cuda") for k, v in comp.parameter_size().items()}).shape == (0, 2, 100)
+    L_ = _cabi.lib()
+    x = torch.zeros(1, 1, 64, device="cuda")
+    assert L_.gfx_envelope_f32(x.data_ptr(), x.data_ptr(), 1, 1, 64, 3, x.data_ptr(), 0, 0, 16, None, 0, None) == -1   # bad smoother
+    assert L_.gfx_envelope_f32(x.data_ptr(), x.data_ptr(), 1, 2, 64, 1, x.data_ptr(), 2, 0, 16, None, 0, None) == -1   # detect=2 needs mono
+    assert L_.gfx_envelope_f32(x.data_ptr(), x.data_ptr(), 1, 1, 64, 1, x.data_ptr(), 0, 0, 16, None, 0, None) == -2   # no workspace
+    assert L_.gfx_fir_filter_f32(x.data_ptr(), None, x.data_ptr(), 1, 1, 1, 64, 8, None, None, 0, None) == -1
+    assert L_.gfx_fir_set_sweep_mb(1) == -1 and L_.gfx_fir_set_mac_form(7) == -1
+    assert L_.gfx_dynamics_set_tuning(48) == -1 and L_.gfx_dynamics_set_ballistics_mode(5) == -1
+    assert L_.gfx_fma_probe_f32(None, 16, None) == -1
