@@ -124,8 +124,11 @@ __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbPar
     }
     __syncthreads();
 
-    // 1. masked spectra of the CTA's frames: lane = frame (coalesced over the frame axis), 16 bin lanes;
-    //    bins 0 and 192 are real.  mask = exp((H0 - softplus(Hd) m [+ G[m]]) / 8)  (reverb.py:189-200)
+    // 1 + 2. masked spectra of the CTA's frames, re-tangled into the 192-point complex spectrum on the way: lane = frame
+    //    (global reads coalesced over the frame axis), 16 bin lanes; a thread takes the bins k and 192 - k of a pair,
+    //    masks both (mask = exp((H0 - softplus(Hd) m [+ G[m]]) / 8), reverb.py:189-200), re-tangles them in registers and
+    //    writes each slot once (the spectrum used to be written, re-read pair by pair and written again).  Bins 0 and
+    //    192 are real and share slot 0; bin 96 pairs with itself.
     {
         const int f = tid & (RV_FT - 1), kq = tid >> 4;
         const int m = m0 + f;
@@ -134,44 +137,29 @@ __global__ void __launch_bounds__(2 * RV_NT, 2) reverb_ir_kernel(const ReverbPar
         const float ge = (genv && fv) ? genv[m] * kScale : 0.f;
         const float2* np = noise + (fv ? m : 0);
         pk2* zf = zb + f * RV_ZS;
-#pragma unroll 4
-        for (int k = kq; k < RV_BINS - 1; k += 16) {
+        auto masked = [&](int k) {
             const float2 nz = __ldg(np + (size_t)k * p.frames);
             const float mk = fv ? ex2_approx((a0[k] - a1[k] * fm) + ge) : 0.f;
-            zf[k] = pk_make(nz.x * mk, nz.y * mk);
-        }
-        if (kq == 0) {
-            const int k = RV_BINS - 1;
-            const float2 nz = __ldg(np + (size_t)k * p.frames);
-            const float mk = fv ? ex2_approx((a0[k] - a1[k] * fm) + ge) : 0.f;
-            xn[f] = nz.x * mk;
+            return make_float2(nz.x * mk, nz.y * mk);
+        };
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int k = kq + 16 * i;
+            if (k == 0) {
+                const float2 x0 = masked(0), xN = masked(RV_BINS - 1), xh = masked(RV_N / 2);
+                zf[0] = pk_make(0.5f * (x0.x + xN.x), 0.5f * (x0.x - xN.x));
+                zf[RV_N / 2] = pk_make(xh.x, -xh.y);
+            } else {
+                const PairA a = retangle_pair(masked(k), masked(RV_N - k), hw[k]);
+                zf[k] = pk_make(a.k.x, a.k.y);
+                zf[RV_N - k] = pk_make(a.m.x, a.m.y);
+            }
         }
     }
     __syncthreads();
 
     const int g = tid >> 4, tau = tid & 15;  // frame slot, thread within the frame group
     pk2* z = zb + g * RV_ZS;
-    // 2. re-tangle the half spectrum into the 192-point complex spectrum (in place, pair-local)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const int k = tau + 16 * i;
-        if (k == 0) {
-            float x0, x0i, xh, xhi;
-            pk_split(z[0], x0, x0i);
-            pk_split(z[RV_N / 2], xh, xhi);
-            const float xN = xn[g];
-            z[0] = pk_make(0.5f * (x0 + xN), 0.5f * (x0 - xN));
-            z[RV_N / 2] = pk_make(xh, -xhi);
-        } else {
-            float yr, yi, mr, mi;
-            pk_split(z[k], yr, yi);
-            pk_split(z[RV_N - k], mr, mi);
-            const PairA a = retangle_pair(make_float2(yr, yi), make_float2(mr, mi), hw[k]);
-            z[k] = pk_make(a.k.x, a.k.y);
-            z[RV_N - k] = pk_make(a.m.x, a.m.y);
-        }
-    }
-    __syncwarp();
     // 3. thread tau: inverse DFT-12 over Z[tau + 16 m], twiddle, to B[r][tau] at slot r * 17 + tau
     {
         pk2 a[12];
