@@ -124,7 +124,7 @@ struct DynCtx {
 // with fewer rows than resident CTAs the extra CTAs only queue up behind the tile chain of a row.  So: the small CTA
 // when every resident CTA can own a different row, the large one otherwise.
 constexpr int DYN_SCAN_NT = 256, DYN_SCAN_NT_SMALL = 128, DYN_SCAN_CTAS_SMALL = 6;
-static int g_dyn_scan_nt = 0;  // 0: by row count (below); 32 | 64 | 128 | 256: forced (gfx_dynamics_set_tuning)
+static int g_dyn_scan_nt = 0;  // 0: by row count (below); 128 | 256: forced (gfx_dynamics_set_tuning)
 // RO: the CTA owns whole rows (ballistics); otherwise one (tile, row) item at a time (scan variant)
 
 template <int NT, bool RO>
@@ -958,12 +958,8 @@ static int scan_nt_for(int batch) {
 }
 template <bool ENV>
 static int launch_scan(int NT, DynParams& p, cudaStream_t st) {
-    switch (NT) {
-        case 32: return launch_dynamics<32, false, ENV>(p, st);
-        case 64: return launch_dynamics<64, false, ENV>(p, st);
-        case 128: return launch_dynamics<128, false, ENV>(p, st);
-        default: return launch_dynamics<256, false, ENV>(p, st);
-    }
+    // (32- and 64-thread CTAs were measured and are 1.5-3x slower: profiles/r02_dynamics_cta_size.txt; not instantiated)
+    return NT == 128 ? launch_dynamics<128, false, ENV>(p, st) : launch_dynamics<256, false, ENV>(p, st);
 }
 
 }  // namespace gfx
@@ -971,7 +967,7 @@ static int launch_scan(int NT, DynParams& p, cudaStream_t st) {
 extern "C" {
 
 int gfx_dynamics_set_tuning(int scan_threads) {
-    if (scan_threads != 0 && scan_threads != 32 && scan_threads != 64 && scan_threads != 128 && scan_threads != 256) return GFX_ERR_INVALID;
+    if (scan_threads != 0 && scan_threads != 128 && scan_threads != 256) return GFX_ERR_INVALID;
     gfx::g_dyn_scan_nt = scan_threads;
     return GFX_OK;
 }

@@ -250,7 +250,7 @@ typedef struct gfx_dynamics_stage {
     float* hist_post;           /* [batch, L] scratch; required for an iir gain smoother when iir_len < L */
 } gfx_dynamics_stage;
 GFX_API size_t gfx_dynamics_workspace_bytes(int batch, int n_stages);
-/* threads per CTA of the scan (one-pole smoother) variant: 0 = chosen from the row count (default), or 32/64/128/256 */
+/* threads per CTA of the scan (one-pole smoother) variant: 0 = chosen from the row count (default), or 128 / 256 */
 GFX_API int gfx_dynamics_set_tuning(int scan_threads);
 /* attack / release ballistics: 1 (default) = independent chunks with a warm-up (dynamics_spec_kernel) for every row whose
  * followers forget their state within 16 chunks, the row walk for the others; 0 = always the row walk */

@@ -29,7 +29,7 @@ for name, B, C, L, is_chain in shapes:
     pc = {k: torch.randn(B, v, device="cuda") for k, v in comp.parameter_size().items()}
     pg = {k: torch.randn(B, v, device="cuda") for k, v in gate.parameter_size().items()}
     res = []
-    for nt in (0, 32, 64, 128, 256):
+    for nt in (0, 128, 256):
         assert L_.gfx_dynamics_set_tuning(nt) == 0
         fn = (lambda: chain(x, comp=pc, gate=pg)) if is_chain else (lambda: comp(x, **pc))
         res.append(f"nt={nt}: {timeit(fn):.4f} ms")
