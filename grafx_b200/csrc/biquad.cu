@@ -539,6 +539,13 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
             um2 = pk_make(a2v, tile[rb + 2]);
         }
 
+        // Incoming section states of the item, all requested at once: the previous item of the row was issued a whole
+        // round of tickets earlier and has usually finished every section, so one L2 round trip here replaces one per
+        // section on warp 0's critical path (a word whose tag is not there yet is polled for in its section, as before).
+        unsigned long long pre_state = 0ull;
+        if (warp == 0 && t_idx > 0 && lane < 2 * K)
+            pre_state = *reinterpret_cast<const volatile unsigned long long*>(p.xstate + (size_t)row * K * 2 + lane);
+
 #pragma unroll
         for (int k = 0; k < (KT > 0 ? KT : K); ++k) {
             const double* pk = tab + (size_t)k * X2_TAB * 4;
@@ -640,10 +647,13 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
             if (t_idx > 0) {
                 if (warp == 0) {
                     float sv = 0.f;
+                    // (sections 0..15 come from the words requested before the loop)
+                    unsigned long long word = __shfl_sync(0xffffffffu, pre_state, (2 * k + (lane & 1)) & 31);
                     if (lane < 2) {
-                        const volatile unsigned long long* w = p.xstate + ((size_t)row * K + k) * 2 + lane;
-                        unsigned long long word;
-                        do { word = *w; } while ((unsigned)(word >> 32) != (unsigned)t_idx);
+                        if (2 * k + 1 >= 32 || (unsigned)(word >> 32) != (unsigned)t_idx) {
+                            const volatile unsigned long long* w = p.xstate + ((size_t)row * K + k) * 2 + lane;
+                            do { word = *w; } while ((unsigned)(word >> 32) != (unsigned)t_idx);
+                        }
                         sv = __uint_as_float((unsigned)word);
                     }
                     sAxf = __shfl_sync(0xffffffffu, sv, 0);
