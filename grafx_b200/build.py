@@ -38,13 +38,37 @@ def sources() -> list[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def _deps() -> list[str]:
+    deps = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    deps.append(os.path.join(HERE, "..", "include", "grafx_b200.h"))
+    return deps
+
+
+def source_hash() -> str:
+    """Digest of everything the library is built from (sources, headers, flags)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS + os.environ.get("GFX_NVCC_EXTRA", "").split()).encode())
+    for d in _deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_rebuild() -> bool:
+    """True when the library is absent or was built from other sources.  The comparison is by content (a digest
+    recorded next to the .so at build time), not by mtime: a copy of the tree -- e.g. the snapshot sent to a GPU box --
+    need not preserve timestamps, and a spurious rebuild there costs a minute per process."""
     if not os.path.exists(LIB):
         return True
+    stamp = LIB + ".srchash"
+    if os.path.exists(stamp):
+        with open(stamp) as f:
+            return f.read().strip() != source_hash()
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
-    deps.append(os.path.join(HERE, "..", "include", "grafx_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -71,6 +95,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
     cmd = [nvcc, "-shared", "-cudart", "static", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs]
     subprocess.check_call(cmd)
+    with open(LIB + ".srchash", "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

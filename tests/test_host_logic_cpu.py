@@ -157,3 +157,21 @@ def test_bench_config_is_identical_in_both_arms_and_the_shard_covers_the_batch()
         x, prm = wl.host_inputs(B=2)
         assert x.shape == (2, wl.C, wl.L) and wl.alg_bytes() >= 8 * wl.samples()
         assert set(bench.config_of(name, 1)) == {"workload", "batch", "channels", "length", "l2", "parallelism"}
+
+
+def test_library_staleness_is_decided_by_content_not_mtime():
+    """grafx_b200.build.needs_rebuild compares a digest of the sources with the one recorded at build time: a copy of the
+    tree that does not preserve timestamps (the snapshot sent to a GPU box) must not trigger a rebuild."""
+    import os
+
+    from grafx_b200 import _cabi, build
+
+    _cabi.lib()  # (builds if needed)
+    assert os.path.exists(build.LIB + ".srchash") and not build.needs_rebuild()
+    src = os.path.join(build.CSRC, "abi.cu")
+    st = os.stat(src)
+    try:
+        os.utime(src, (st.st_atime, st.st_mtime + 10_000))
+        assert not build.needs_rebuild()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
