@@ -29,7 +29,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "audio samples/sec (batch x chan x len)"
-FMA_PER_CONV_SAMPLE = None
 
 
 # --------------------------------------------------------------------------- workloads

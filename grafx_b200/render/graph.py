@@ -211,7 +211,6 @@ def _render_grafx_functional(processors, input_signals, per_type_parameters, ren
     owner = [0] * num_sources + [None] * (num_nodes - num_sources)
 
     def whole_buffer():
-        missing = [i for i, o in enumerate(owner) if o is None]
         parts, i = [], 0
         while i < num_nodes:
             if owner[i] is None:  # nodes not rendered yet read as zeros (upstream's buffer starts as zeros)
@@ -224,7 +223,6 @@ def _render_grafx_functional(processors, input_signals, per_type_parameters, ren
                 b = blocks[owner[i]]
                 parts.append(b.narrow(0, i - owner[i], min(b.shape[0] - (i - owner[i]), num_nodes - i)))
                 i += parts[-1].shape[0]
-        del missing
         return torch.cat(parts, 0)
 
     def read(access):
