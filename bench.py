@@ -761,7 +761,7 @@ def main():
             k_ms, _ = timed_blocks(renders_only, max(2, steps // 4), min(args.min_seconds, 0.3), barrier, device, max_over_ranks)
             launches = wl.caps[0].launches_per_replay
             roofline = roofline_of("cfg5", wl.alg_bytes_local(), wl.flops_per_out_sample * wl.B_local * wl.C * wl.L, k_ms,
-                                   "render_grafx, 5 render orders per chunk of 16 renders: node_copy, biquad_cascade_x2, dynamics, "
+                                   "render_grafx, 5 render orders per chunk of 16 renders: biquad_cascade_x2 (reads the sources, fills the buffer's source slice), dynamics, "
                                    "reverb pipeline (reverb_ir + filter spectra + partitioned overlap-save), node_sum; CUDA-graph replay",
                                    launches, fma_rate)
             roofline["bytes_convention"] = "contract-preserving render: 289 node-signal passes (129 written, 160 read) x 1 MiB per render"

@@ -45,6 +45,12 @@ struct CascadeParams {
     unsigned long long* xstate;  // packed-kernel variant: [rows][K][2] {value, tag} words
     const double* xtables;       // packed-kernel variant: [coef rows][K][X2_TAB][4] doubles
     int aligned;  // 1: x/y rows are 16-byte aligned (vector path)
+    // packed-kernel variant, render_grafx's first render order (gfx_biquad_cascade_src_f32): the signal is read from
+    // the caller's [src_outer, src_inner, c_sig, L] sources (item b of this launch = source item
+    // (b % src_outer) * src_inner + b / src_outer: the node-major order of the signal buffer) and every staged tile is
+    // also stored to xcopy [rows, L] -- the source slice of the signal buffer -- so no separate copy pass reads it again
+    T* xcopy;
+    int src_outer, src_inner;
 };
 
 __device__ __forceinline__ void mat2_mul(const double a[4], const double b[4], double c[4]) {
@@ -474,7 +480,12 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
         const int t_idx = (int)(item / (unsigned)p.rows);
         const int row = (int)(item - (unsigned)t_idx * (unsigned)p.rows);
         const int b = row / p.c_out, c = row - b * p.c_out;
-        const float* xr = p.x + ((size_t)b * p.c_sig + (p.c_sig == 1 ? 0 : c)) * (size_t)p.L;
+        int bs = b;
+        if (p.src_outer > 0) {
+            const int node = b / p.src_outer;
+            bs = (b - node * p.src_outer) * p.src_inner + node;
+        }
+        const float* xr = p.x + ((size_t)bs * p.c_sig + (p.c_sig == 1 ? 0 : c)) * (size_t)p.L;
         float* yr = p.y + (size_t)row * (size_t)p.L;
         const size_t crow = (size_t)b * p.c_filt + (p.c_filt == 1 ? 0 : c);
         const long long t0 = (long long)t_idx * ITEM + (long long)warp * TILE;  // this warp's sub-tile
@@ -514,6 +525,20 @@ __global__ void __launch_bounds__(32 * X2_WARPS, MINB) biquad_cascade_x2_kernel(
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();  // the table was staged by all four warps
+
+        if (p.xcopy != nullptr) {
+            // the untouched input tile also goes to the signal buffer's source slice (c_sig == c_out: row = input row)
+            float* xc = p.xcopy + (size_t)row * (size_t)p.L;
+            if (full) {
+                float4* dst = reinterpret_cast<float4*>(xc + t0) + lane;
+                const float4* src = tile4 + (lane >> 3) * 8;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) stg_stream(dst + j * 32, src[j * 32 + (cu0 ^ ((j & 1) << 2))]);
+            } else {
+                for (int i = lane; i < TILE && i < remain; i += 32)
+                    xc[t0 + i] = tile[(size_t)swz_unit(i >> 5, (i & 31) >> 2) * 4 + (i & 3)];
+            }
+        }
 
         pk2 v[S];
 #pragma unroll
@@ -807,7 +832,7 @@ static size_t cascade_workspace_bytes(int rows, int coef_rows, int K, size_t ele
 template <typename T>
 static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch, int c_sig,
                           int c_filt, int K, long long L, void* ws, size_t ws_bytes,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, T* xcopy = nullptr, int src_outer = 0, int src_inner = 0) {
     constexpr int NT = 256;
     constexpr int S = 128 / (int)sizeof(T);
     constexpr int MINB = sizeof(T) == 4 ? 3 : 1;
@@ -816,6 +841,11 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     if (c_sig != c_filt && c_sig != 1 && c_filt != 1) return GFX_ERR_INVALID;
     if (K > 64) return GFX_ERR_UNSUPPORTED;
     const int c_out = c_sig > c_filt ? c_sig : c_filt;
+    if (xcopy != nullptr || src_outer != 0 || src_inner != 0) {
+        // source-reading form: fp32 packed kernel only, one output row per input row, batch = src_outer * src_inner
+        if (sizeof(T) != 4 || xcopy == nullptr || c_sig != c_out) return GFX_ERR_INVALID;
+        if (src_outer <= 0 || src_inner <= 0 || (long long)src_outer * src_inner != (long long)batch) return GFX_ERR_INVALID;
+    }
     const long long rows_ll = (long long)batch * c_out;
     static const bool force_scalar = (getenv("GFX_CASCADE_SCALAR") != nullptr);  // A/B testing only
     (void)force_scalar;
@@ -831,6 +861,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
 
     CascadeParams<T> p;
     p.x = x; p.y = y;
+    p.xcopy = xcopy; p.src_outer = src_outer; p.src_inner = src_inner;
     p.batch = batch; p.c_sig = c_sig; p.c_filt = c_filt; p.c_out = c_out; p.K = K;
     p.L = L; p.rows = rows; p.tiles = tiles;
     p.n_items = (unsigned)(rows * (long long)tiles);
@@ -843,7 +874,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     const size_t state_bytes = align256((size_t)rows * 2 * K * 8);
     T* tables = (T*)(w + 256 + flags_bytes + state_bytes);
     p.tables = tables;
-    p.aligned = (((uintptr_t)x | (uintptr_t)y) % 16 == 0) && ((L * (long long)sizeof(T)) % 16 == 0);
+    p.aligned = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)xcopy) % 16 == 0) && ((L * (long long)sizeof(T)) % 16 == 0);
 
     GFX_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256 + flags_bytes + state_bytes, stream));
     const int n_sections = coef_rows * K;
@@ -919,6 +950,14 @@ int gfx_biquad_cascade_f32(const float* x, float* y, const float* Bs, const floa
                            size_t workspace_bytes, void* stream) {
     return gfx::launch_cascade<float>(x, y, Bs, As, batch, c_sig, c_filt, K, L, workspace,
                                       workspace_bytes, (cudaStream_t)stream);
+}
+
+int gfx_biquad_cascade_src_f32(const float* src, float* xcopy, float* y, const float* Bs, const float* As,
+                               int src_outer, int src_inner, int c_sig, int c_filt, int K, long long L,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    if ((long long)src_outer * src_inner > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
+    return gfx::launch_cascade<float>(src, y, Bs, As, src_outer * src_inner, c_sig, c_filt, K, L, workspace,
+                                      workspace_bytes, (cudaStream_t)stream, xcopy, src_outer, src_inner);
 }
 
 int gfx_biquad_cascade_f64(const double* x, double* y, const double* Bs, const double* As, int batch,

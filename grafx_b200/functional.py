@@ -59,6 +59,35 @@ def parameter_repeat() -> int:
     return getattr(_DEST, "repeat", 1)
 
 
+class source_fold:
+    """`with source_fold(sources, view) as f:` -- render_grafx's first render order (4-D sources).  `view` is the
+    source slice of the signal buffer, flattened node-major `[V0 * B, C, L]` and NOT filled yet; `sources` is the
+    caller's `[B, V0, C, L]` tensor.  An op that supports it (the biquad cascade, gfx_biquad_cascade_src_f32) and is
+    handed `view` as its signal reads `sources` instead and fills `view` from the tile it staged anyway, so the separate
+    copy pass never reads the sources a second time.  `f.used` tells the caller whether that happened: if not, the
+    caller fills `view` itself and runs the processor again (render/graph.py)."""
+
+    def __init__(self, sources: torch.Tensor, view: torch.Tensor):
+        self.sources, self.view, self.used = sources, view, False
+
+    def __enter__(self):
+        self.prev = getattr(_DEST, "fold", None)
+        _DEST.fold = self
+        return self
+
+    def __exit__(self, *exc):
+        _DEST.fold = self.prev
+        return False
+
+
+def _take_source_fold(x: torch.Tensor):
+    f = getattr(_DEST, "fold", None)
+    if (f is None or f.used or x.dtype != torch.float32 or x.data_ptr() != f.view.data_ptr()
+            or tuple(x.shape) != tuple(f.view.shape) or not x.is_contiguous()):
+        return None
+    return f
+
+
 def _new_output(shape, dtype, device) -> torch.Tensor:
     d = getattr(_DEST, "t", None)
     if d is not None and tuple(d.shape) == tuple(shape) and d.dtype == dtype and d.device == device:
@@ -106,6 +135,7 @@ def biquad_cascade(x: torch.Tensor, Bs: torch.Tensor, As: torch.Tensor) -> torch
 
         return biquad_cascade_autograd(x, Bs, As)
     dtype = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
+    fold = _take_source_fold(x) if c_sig >= c_filt else None
     x, Bs, As = _prep(x, dtype), _prep(Bs, dtype), _prep(As, dtype)
     c_out = max(c_sig, c_filt)
     y = _new_output((b, c_out, L), dtype, x.device)
@@ -115,6 +145,16 @@ def biquad_cascade(x: torch.Tensor, Bs: torch.Tensor, As: torch.Tensor) -> torch
     elem = 4 if dtype == torch.float32 else 8
     ws_bytes = L_.gfx_biquad_cascade_workspace_bytes(b, c_sig, c_filt, K, elem)
     ws = _cabi.workspace(ws_bytes, x.device)
+    if fold is not None:
+        # first render order of render_grafx: read the caller's [B, V0, C, L] sources, fill the buffer's source slice (x)
+        n_renders, n_sources = fold.sources.shape[0], fold.sources.shape[1]
+        with torch.cuda.device(x.device):
+            code = L_.gfx_biquad_cascade_src_f32(fold.sources.data_ptr(), x.data_ptr(), y.data_ptr(), Bs.data_ptr(),
+                                                 As.data_ptr(), n_renders, n_sources, c_sig, c_filt, K, L,
+                                                 ws.data_ptr(), ws.numel(), _cabi.stream_ptr())
+        _cabi.check(code, "gfx_biquad_cascade_src")
+        fold.used = True
+        return y
     fn = L_.gfx_biquad_cascade_f32 if dtype == torch.float32 else L_.gfx_biquad_cascade_f64
     with torch.cuda.device(x.device):
         code = fn(x.data_ptr(), y.data_ptr(), Bs.data_ptr(), As.data_ptr(), b, c_sig, c_filt, K, L,

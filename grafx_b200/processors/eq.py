@@ -29,6 +29,10 @@ class ParametricEqualizer(nn.Module):
             return F_.ms_to_lr(self.biquad(F_.lr_to_ms(input_signals), Bs, As))
         return self.biquad(input_signals, Bs, As)
 
+    def folds_source_read(self):
+        """render_grafx: the first kernel to read `input_signals` is the biquad cascade (F_.source_fold)."""
+        return self.processor_channel != "midside" and self.biquad.backend != "fsm"
+
     def parameter_size(self):
         n_channels = 1 if self.processor_channel == "mono" else 2
         return {k: (n_channels, self.num_filters) for k in ("w0", "q_inv", "log_gain")}
@@ -51,6 +55,9 @@ class GraphicEqualizer(nn.Module):
         if self.processor_channel == "midside":
             return F_.ms_to_lr(self.biquad(F_.lr_to_ms(input_signals), Bs, As))
         return self.biquad(input_signals, Bs, As)
+
+    def folds_source_read(self):
+        return self.processor_channel != "midside" and self.biquad.backend != "fsm"
 
     def parameter_size(self):
         n_channels = 1 if self.processor_channel == "mono" else 2

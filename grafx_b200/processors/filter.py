@@ -50,6 +50,10 @@ class _BiquadStack(nn.Module):
     def _run(self, input_signals, num, den):
         return self.biquad(input_signals, num.unsqueeze(1), den.unsqueeze(1))
 
+    def folds_source_read(self):
+        """render_grafx: the first kernel to read `input_signals` is the biquad cascade (F_.source_fold)."""
+        return self.biquad.backend != "fsm"
+
 
 class BiquadFilter(_BiquadStack):
     """filter.py:87-168."""

@@ -91,6 +91,7 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
 
     # create_signal_buffer (render/core.py:6-33)
     one_by_one = method == "one-by-one"
+    pending_sources = None
     if one_by_one:
         assert ndim == 3, "the one-by-one list buffer has no batch axis upstream either"
         signal_buffer = [x[None] for x in input_signals] + [None] * (render_data.num_nodes - num_sources)
@@ -98,13 +99,21 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
         shape = (render_data.num_nodes, channels, audio_len) if ndim == 3 else (render_data.num_nodes, batch_size, channels, audio_len)
         signal_buffer = torch.empty(shape, device=input_signals.device, dtype=torch.float32)
         sources = signal_buffer.narrow(0, 0, num_sources)
-        if ndim == 3:
-            sources.copy_(input_signals)
+        x_in = input_signals if input_signals.dtype == torch.float32 else input_signals.float()
+        if ndim == 4 and (x_in.stride(3) != 1 or x_in.stride(2) != audio_len):
+            x_in = x_in.contiguous()
+
+        def fill_sources():
+            if ndim == 3:
+                sources.copy_(x_in)
+            else:
+                F_.node_copy(x_in.transpose(0, 1), sources)
+
+        if x_in.is_contiguous() and x_in.numel() > 0 and _first_order_folds(processors, render_data, num_sources):
+            # the first processor reads the caller's sources and fills this slice itself (F_.source_fold)
+            pending_sources = x_in if ndim == 4 else x_in.unsqueeze(0)
         else:
-            x_in = input_signals if input_signals.dtype == torch.float32 else input_signals.float()
-            if x_in.stride(3) != 1 or x_in.stride(2) != audio_len:
-                x_in = x_in.contiguous()
-            F_.node_copy(x_in.transpose(0, 1), sources)
+            fill_sources()
 
     intermediates_list = []
     output_signals = None
@@ -146,9 +155,23 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
                     common_i = {"parameter": common_i}
             if isinstance(parameters, torch.Tensor):
                 parameters = {"parameter": parameters}
-            with F_.output_into(post(dest_view) if dest_view is not None else None), \
-                    F_.shared_parameters(batch_size if (ndim == 4 and common_parameters is None) else 1):
-                output = processors[node_type](*inputs, **parameters, **common_i)
+            def run():
+                with F_.output_into(post(dest_view) if dest_view is not None else None), \
+                        F_.shared_parameters(batch_size if (ndim == 4 and common_parameters is None) else 1):
+                    return processors[node_type](*inputs, **parameters, **common_i)
+
+            if pending_sources is not None:
+                with F_.source_fold(pending_sources, post(sources)) as fold:
+                    output = run()
+                pending_sources = None
+                if not fold.used:
+                    # the processor did not take the offer (its first op is not the cascade kernel for these shapes):
+                    # fill the slice the usual way, run it again, and do not offer again to this module
+                    fill_sources()
+                    processors[node_type]._gfx_no_source_fold = True
+                    output = run()
+            else:
+                output = run()
             if isinstance(output, tuple):
                 output_signals, intermediates = output
                 intermediates_list.append(intermediates)
@@ -182,6 +205,25 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
     if ndim == 4:
         return output_signals.transpose(0, 1), intermediates_list, signal_buffer.transpose(0, 1)
     return output_signals, intermediates_list, signal_buffer
+
+
+def _first_order_folds(processors, render_data, num_sources) -> bool:
+    """True when the first render order is ONE processor call on exactly the source slice and that processor starts
+    with the biquad cascade on its input (`folds_source_read`): the cascade kernel then reads the caller's sources and
+    writes the buffer's source slice on the way (gfx_biquad_cascade_src_f32) instead of a separate copy pass."""
+    if int(render_data.max_order) < 1:
+        return False
+    it = render_data.iter_list[1]
+    proc = processors[it.node_type] if it.node_type in processors else None
+    if proc is None or getattr(proc, "_gfx_no_source_fold", False):
+        return False
+    wants = getattr(proc, "folds_source_read", None)
+    if wants is None or not wants():
+        return False
+    if len(it.source_reads) != 1 or it.aggregations[0].method != "none":
+        return False
+    read = it.source_reads[0]
+    return read.method == "slice" and int(read.idx[0]) == 0 and int(read.idx[1]) == num_sources
 
 
 def _render_grafx_functional(processors, input_signals, per_type_parameters, render_data, common_parameters):

@@ -58,6 +58,18 @@ GFX_API size_t gfx_biquad_cascade_workspace_bytes(int batch, int c_sig, int c_fi
 GFX_API int gfx_biquad_cascade_f32(const float* x, float* y, const float* Bs, const float* As, int batch,
                            int c_sig, int c_filt, int K, long long L, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* The same cascade as the FIRST render order of render_grafx (render/graph.py:63-75, render/core.py:6-33: upstream
+ * copies the sources into the signal buffer, then the first processor reads that copy back).  The signal is read from
+ * the caller's sources  src [src_outer, src_inner, c_sig, L]  (4-D input_signals: renders x source nodes); item b of
+ * the launch (b < src_outer * src_inner, node-major like the signal buffer: b = node * src_outer + render) takes
+ * source item (b % src_outer) * src_inner + b / src_outer.  Every input row is ALSO written to  xcopy [items, c_sig, L]
+ * -- the source slice of the signal buffer -- from the tile the kernel staged anyway, so the separate copy pass
+ * (gfx_node_copy_f32: one more read of every source) is not needed.  Requires c_sig == max(c_sig, c_filt).
+ * Bs, As [items, c_filt, K, 3] and y [items, c_sig, L] as above; workspace as gfx_biquad_cascade_workspace_bytes
+ * (batch = items, elem_size 4). */
+GFX_API int gfx_biquad_cascade_src_f32(const float* src, float* xcopy, float* y, const float* Bs, const float* As,
+                               int src_outer, int src_inner, int c_sig, int c_filt, int K, long long L,
+                               void* workspace, size_t workspace_bytes, void* stream);
 /* float64 variant: the reference's only known-answer test runs in double
  * (tests/processors/test_filter.py:215-233). */
 GFX_API int gfx_biquad_cascade_f64(const double* x, double* y, const double* Bs, const double* As, int batch,

@@ -446,3 +446,100 @@ def test_new_entry_points_empty_batch_and_argument_errors():
     assert L_.gfx_fir_set_sweep_mb(1) == -1 and L_.gfx_fir_set_mac_form(7) == -1
     assert L_.gfx_dynamics_set_tuning(48) == -1 and L_.gfx_dynamics_set_ballistics_mode(5) == -1
     assert L_.gfx_fma_probe_f32(None, 16, None) == -1
+
+
+# ------------------------------------------------------------------ first render order reading the caller's sources
+@pytest.mark.parametrize("L", [8192 * 3, 5000, 4099, 2050])
+@pytest.mark.parametrize("batch", [None, 1, 3])
+def test_first_order_source_fold_matches_the_copy_path(batch, L):
+    """render_grafx, first render order = a biquad-cascade processor on exactly the source slice: the cascade kernel reads
+    the caller's sources and fills the buffer's source slice on the way (gfx_biquad_cascade_src_f32) instead of a separate
+    copy pass.  Output, intermediates and the WHOLE signal buffer must be bit-identical to the copy path (the same kernel
+    on the same values), for full tiles, ragged tails and rows that are not 16-byte aligned, 3-D and 4-D sources."""
+    import grafx_b200.processors as P
+    from grafx_b200 import functional as F_
+    from grafx_b200.render import mixing_console_plan, render_grafx
+
+    torch.manual_seed(77)
+    T = 5
+    shape = (T, 2, L) if batch is None else (batch, T, 2, L)
+    x = torch.randn(*shape, device="cuda")
+    eq, comp = P.ParametricEqualizer(num_filters=4, processor_channel="stereo", backend="lfilter").cuda(), P.Compressor().cuda()
+    prm = {"eq": {k: 0.5 * torch.randn(T, *v, device="cuda") for k, v in eq.parameter_size().items()},
+           "compressor": {k: torch.randn(T, v, device="cuda") for k, v in comp.parameter_size().items()}}
+    rd = mixing_console_plan(T, ["eq", "compressor"])
+    procs = {"eq": eq, "compressor": comp}
+    taken = []
+    orig = F_.source_fold.__exit__
+
+    def spy(self, *exc):
+        taken.append(self.used)
+        return orig(self, *exc)
+
+    F_.source_fold.__exit__ = spy
+    try:
+        out_f, _, buf_f = render_grafx(procs, x, prm, rd)
+    finally:
+        F_.source_fold.__exit__ = orig
+    assert taken == [True]
+    eq._gfx_no_source_fold = True   # the copy path: node_copy / copy_ first, plain cascade
+    out_c, _, buf_c = render_grafx(procs, x, prm, rd)
+    del eq._gfx_no_source_fold
+    assert torch.equal(out_f, out_c)
+    assert torch.equal(buf_f, buf_c)
+    src = buf_f[:, :T] if batch is not None else buf_f[:T]
+    assert torch.equal(src, x)
+
+
+def test_first_order_source_fold_declined_falls_back_to_the_copy():
+    """A processor that offers `folds_source_read` but whose first op on the sources is not the cascade kernel (here: a
+    mid/side conversion in front of it) leaves the offer unused: render_grafx fills the source slice itself, runs the
+    processor again and stops offering to that module."""
+    import grafx_b200.processors as P
+    from grafx_b200.render import mixing_console_plan, render_grafx
+    import torch.nn as nn
+
+    class MidFirst(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.eq = P.ParametricEqualizer(num_filters=3, processor_channel="stereo", backend="lfilter")
+
+        def folds_source_read(self):
+            return True
+
+        def forward(self, input_signals, **kw):
+            from grafx_b200 import functional as F_
+            return F_.ms_to_lr(self.eq(F_.lr_to_ms(input_signals), **kw))
+
+        def parameter_size(self):
+            return self.eq.parameter_size()
+
+    torch.manual_seed(78)
+    T, L = 3, 6000
+    x = torch.randn(2, T, 2, L, device="cuda")
+    proc = MidFirst().cuda()
+    prm = {"eq": {k: 0.5 * torch.randn(T, *v, device="cuda") for k, v in proc.parameter_size().items()}}
+    rd = mixing_console_plan(T, ["eq"])
+    out, _, buf = render_grafx({"eq": proc}, x, prm, rd)
+    assert getattr(proc, "_gfx_no_source_fold", False)
+    assert torch.equal(buf[:, :T], x)
+    ref = P.ParametricEqualizer(num_filters=3, processor_channel="midside", backend="lfilter").cuda()
+    out_r, _, buf_r = render_grafx({"eq": ref}, x, prm, rd)
+    assert torch.equal(buf, buf_r) and torch.equal(out, out_r)
+
+
+def test_cascade_src_abi_rejects_bad_arguments():
+    from grafx_b200 import _cabi
+
+    L_ = _cabi.lib()
+    x = torch.randn(2, 3, 1, 64, device="cuda")
+    y = torch.empty(6, 2, 64, device="cuda")
+    c = torch.randn(6, 2, 1, 3, device="cuda")
+    ws = torch.empty(1 << 16, dtype=torch.uint8, device="cuda")
+    # c_sig (1) < c_filt (2): one output row per input row is required
+    code = L_.gfx_biquad_cascade_src_f32(x.data_ptr(), y.data_ptr(), y.data_ptr(), c.data_ptr(), c.data_ptr(), 2, 3, 1, 2, 1, 64,
+                                         ws.data_ptr(), ws.numel(), 0)
+    assert code != 0
+    code = L_.gfx_biquad_cascade_src_f32(x.data_ptr(), None, y.data_ptr(), c.data_ptr(), c.data_ptr(), 2, 3, 1, 1, 1, 64,
+                                         ws.data_ptr(), ws.numel(), 0)
+    assert code != 0

@@ -67,3 +67,34 @@ def test_gloo_world2_shard_gather_and_max():
         p.join(60)
     assert all(ok for _, ok, _ in res)
     assert all(t == 11.0 for _, _, t in res)
+
+
+def test_first_order_fold_decision():
+    """Host logic of the source fold (render/graph.py:_first_order_folds): offered only when the first render order is one
+    processor call on exactly the source slice, without aggregation, and the processor says its first kernel is the
+    biquad cascade."""
+    import grafx_b200.processors as P
+    from grafx_b200.render import mixing_console_plan
+    from grafx_b200.render.graph import _first_order_folds
+    from grafx_b200.render.plan import RenderData, _AggregationData as Agg, _SingleRenderData as It, _TensorAccessData as Acc
+
+    eq = P.ParametricEqualizer(num_filters=3, processor_channel="stereo", backend="lfilter")
+    rd = mixing_console_plan(4, ["eq", "compressor"])
+    assert _first_order_folds({"eq": eq, "compressor": P.Compressor()}, rd, 4)
+    assert not _first_order_folds({"eq": P.ParametricEqualizer(processor_channel="midside", backend="lfilter")}, rd, 4)
+    assert not _first_order_folds({"eq": P.ParametricEqualizer(backend="fsm")}, rd, 4)
+    assert not _first_order_folds({"eq": P.Compressor()}, rd, 4)                      # no cascade in front
+    assert _first_order_folds({"eq": P.LowPassFilter(backend="lfilter")}, rd, 4)
+    assert _first_order_folds({"eq": P.GraphicEqualizer(backend="lfilter")}, rd, 4)
+    assert not _first_order_folds({"eq": eq}, rd, 5)                                  # reads only part of the sources
+    eq._gfx_no_source_fold = True
+    assert not _first_order_folds({"eq": eq}, rd, 4)
+    del eq._gfx_no_source_fold
+    first = rd.iter_list[1]
+    summed = RenderData("beam", rd.num_nodes, rd.max_order, True, [rd.iter_list[0],
+        It("eq", first.source_reads, [Agg("sum")], first.parameter_read, first.dest_write)] + list(rd.iter_list[2:]))
+    assert not _first_order_folds({"eq": eq}, summed, 4)
+    indexed = RenderData("beam", rd.num_nodes, rd.max_order, True, [rd.iter_list[0],
+        It("eq", [Acc("index", torch.arange(4))], [Agg("none")], first.parameter_read, first.dest_write)] + list(rd.iter_list[2:]))
+    assert not _first_order_folds({"eq": eq}, indexed, 4)
+    assert not _first_order_folds({"mix": eq}, rd, 4)                                 # first order is not a processor
