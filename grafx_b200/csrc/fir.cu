@@ -873,6 +873,124 @@ __global__ void __launch_bounds__(MAC2_NT, GFX_MAC2_MINB) fir_mac2_kernel(const 
     }
 }
 
+// UPOLS step 2, packed form (the default where it applies: all partitions in one pass, P <= 24, and rows of at most
+// MAC3_MAXBLK = 32 blocks -- 131072 samples at 4096-tap partitions, every BASELINE shape).  fir_mac2_kernel above issues
+// 115 instructions per (bin, block) of which 64.5 are scalar FFMA (profiles/r02_final_mac2_24.txt: issue 66 %, FMA pipe
+// 42 %): it is bound by instruction issue, not by the pipe.  Here
+//   (a) the complex product is two PACKED accumulations with the input as loaded, x = (re, im):
+//         s1 += x * (h.re, h.re) = (x.re h.re, x.im h.re),   s2 += x * (h.im, h.im) = (x.re h.im, x.im h.im),
+//         y = (s1.lo - s2.hi, s1.hi + s2.lo)   -- 2 FFMA2 per complex product instead of 4 FFMA, no swaps or negations;
+//       the filter sits in registers as duplicated pairs (4 registers per partition);
+//   (b) the whole input history of the row (<= 32 blocks x 8 bytes per thread, 16 KB per CTA) is copied to shared memory by
+//       cp.async up front, in commit groups of U = 4 blocks, and read back with compile-time offsets: no register ring,
+//       no ring moves, no stage juggling; body k waits for group k only (cp.async.wait_group 7 - k);
+//   (c) the (at most 8) bodies of U output blocks are unrolled with compile-time block indices, the products with blocks
+//       before the start of the row simply do not exist (the peeled ramp-up of fir_mac2_kernel, for free);
+//   (d) element 0 -- (A_0, A_N), two REAL bins whose products are component-wise -- takes h = ((h.x, h.y), 0): the same
+//       arithmetic then yields (x.x h.x, x.y h.y), so there is no separate DC / Nyquist pass.
+constexpr int MAC3_NT = 64, MAC3_MAXBLK = 32, MAC3_U = 4;
+#ifndef GFX_MAC3_MINB
+#define GFX_MAC3_MINB 6
+#endif
+
+// FULL: the row has exactly MAC3_MAXBLK blocks (no per-block tests: 131072 samples at 4096-tap partitions)
+template <int PC, int K, bool FULL>
+__device__ __forceinline__ void mac3_body(const pk2* __restrict__ xs, const pk2 (&hrr)[PC], const pk2 (&hii)[PC],
+                                          float2*& yp, unsigned long long bstride, int nblk) {
+    constexpr int U = MAC3_U, J0 = K * U;
+    if (!FULL && J0 >= nblk) return;             // (uniform over the CTA)
+    cp_async_wait<MAC3_MAXBLK / U - 1 - K>();     // groups 0 .. K have landed (each thread reads its own copies only)
+    pk2 s1[U], s2[U];
+    bool started[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) started[u] = false;
+#pragma unroll
+    for (int d = U - 1; d >= -(PC - 1); --d) {   // input block J0 + d feeds output block J0 + u through partition u - d
+        if (J0 + d < 0) continue;
+        const pk2 x = xs[(J0 + d) * MAC3_NT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = u - d;
+            if (p < 0 || p >= PC) continue;
+            if (!started[u]) {                    // (resolved at compile time: the first product initialises the sums)
+                s1[u] = pk_mul(x, hrr[p]);
+                s2[u] = pk_mul(x, hii[p]);
+                started[u] = true;
+            } else {
+                pk_fma_acc(s1[u], x, hrr[p]);
+                pk_fma_acc(s2[u], x, hii[p]);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (FULL || J0 + u < nblk) {
+            float a, b, c, d;
+            pk_split(s1[u], a, b);
+            pk_split(s2[u], c, d);
+            stg_stream2(yp, make_float2(a - d, b + c));
+        }
+        yp = reinterpret_cast<float2*>(reinterpret_cast<unsigned long long>(yp) + bstride);
+    }
+}
+
+// a pointer ptxas must treat as an opaque 64-bit value: bumping it is one 64-bit add (2 instructions) instead of the
+// index + scale + base form (4 instructions) it otherwise rebuilds for every block
+template <typename T>
+__device__ __forceinline__ T* opaque_ptr(T* p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
+template <typename T>
+__device__ __forceinline__ T* bump_bytes(T* p, unsigned long long bytes) {
+    return reinterpret_cast<T*>(reinterpret_cast<unsigned long long>(p) + bytes);
+}
+
+// grid: (2 * half / MAC3_NT, c_out, nb): one CTA = 64 consecutive elements of one output row, all its blocks
+template <int PC, bool FULL>
+__global__ void __launch_bounds__(MAC3_NT, GFX_MAC3_MINB) fir_mac3_kernel(const float2* __restrict__ Xs, const float2* __restrict__ Hs,
+                                                                          float2* __restrict__ Ys, RowMap rm, int xrow0, int hrow0,
+                                                                          int b0, int P, int nblk, int half2) {
+    __shared__ pk2 xsm[MAC3_MAXBLK * MAC3_NT];
+    pk2* xs = xsm + threadIdx.x;
+    const int e = blockIdx.x * MAC3_NT + threadIdx.x;
+    const int c = blockIdx.y, bl = blockIdx.z, b = b0 + bl;
+    const int xr = b * rm.cx + (rm.cx == 1 ? 0 : c);
+    const int hr = (rm.h_rep == 1 ? b : b / rm.h_rep) * rm.ch + (rm.ch == 1 ? 0 : c);
+    const unsigned long long bstride = (unsigned long long)half2 * sizeof(float2);
+    const float2* xp = opaque_ptr(Xs + (size_t)(xr - xrow0) * nblk * half2 + e);
+    const float2* hp = opaque_ptr(Hs + (size_t)(hr - hrow0) * P * half2 + e);
+    float2* yp = opaque_ptr(Ys + (size_t)(bl * rm.c_out + c) * nblk * half2 + e);
+#pragma unroll
+    for (int g = 0; g < MAC3_MAXBLK / MAC3_U; ++g) {
+#pragma unroll
+        for (int u = 0; u < MAC3_U; ++u) {
+            const int j = g * MAC3_U + u;
+            if (FULL || j < nblk) cp_async_small<8>(xs + j * MAC3_NT, xp);
+            xp = bump_bytes(xp, bstride);
+        }
+        cp_async_commit();
+    }
+    pk2 hrr[PC], hii[PC];
+    const bool e0 = e == 0;
+#pragma unroll
+    for (int p = 0; p < PC; ++p) {
+        const float2 h = p < P ? __ldg(hp) : make_float2(0.f, 0.f);
+        hp = bump_bytes(hp, bstride);
+        hrr[p] = pk_make(h.x, e0 ? h.y : h.x);
+        hii[p] = pk_dup(e0 ? 0.f : h.y);
+    }
+    mac3_body<PC, 0, FULL>(xs, hrr, hii, yp, bstride, nblk);
+    mac3_body<PC, 1, FULL>(xs, hrr, hii, yp, bstride, nblk);
+    mac3_body<PC, 2, FULL>(xs, hrr, hii, yp, bstride, nblk);
+    mac3_body<PC, 3, FULL>(xs, hrr, hii, yp, bstride, nblk);
+    mac3_body<PC, 4, FULL>(xs, hrr, hii, yp, bstride, nblk);
+    mac3_body<PC, 5, FULL>(xs, hrr, hii, yp, bstride, nblk);
+    mac3_body<PC, 6, FULL>(xs, hrr, hii, yp, bstride, nblk);
+    mac3_body<PC, 7, FULL>(xs, hrr, hii, yp, bstride, nblk);
+    cp_async_wait<0>();
+}
+
 // UPOLS step 3: inverse FFT of Y_j, keep the second half of the block
 template <int N, bool FAST>
 __global__ void __launch_bounds__(fir_nt(N), fir_min_blocks(N)) fir_inv_kernel(const float4* __restrict__ Ys, float* __restrict__ y,
@@ -1129,7 +1247,8 @@ static int g_long_n = 4096;  // partition size of the long-filter path (tunable:
                              // BASELINE reverb shape (profiles/r02_*): 4096-point FFT kernels run 4 CTAs per SM (955 us for the three
                              // FFT kernels vs 1350 us at 8192 points, 2 CTAs per SM); fir_mac2_kernel keeps the 24 partitions in one pass
 static int g_sweep_mb = 1536; // spectra workspace per sweep of the long-filter path (gfx_fir_set_sweep_mb)
-static int g_mac_form = 1;   // 0: fir_mac_kernel (<= 12 partitions per pass) when it applies; 1: fir_mac2_kernel
+static int g_mac_form = 2;   // 0: fir_mac_kernel (<= 12 partitions per pass) when it applies; 1: fir_mac2_kernel;
+                             // 2: fir_mac3_kernel (packed) when it applies (P <= 24, <= 32 blocks per row), else fir_mac2_kernel
 static int g_mid_n = 8192;   // FFT size for 2048 < taps <= g_mid_n / 2 (longer single-partition filters: 16384)
 
 static int pick_fft_size(int Nh) {
@@ -1233,7 +1352,20 @@ static int run_upols(const FirArgs& a) {
         if (a.fast_x) fir_xspec_kernel<N, true><<<gx, fir_nt(N), smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk, a.plan);
         else fir_xspec_kernel<N, false><<<gx, fir_nt(N), smem, a.stream>>>(a.x, Xs, xrow0, a.L, (int)nblk, a.plan);
         GFX_LAUNCH_CHECK();
-        if (g_mac_form == 0 && P <= MAC_MAX_PC) {
+        if (g_mac_form == 2 && P <= MAC2_MAX_PC && nblk <= MAC3_MAXBLK) {
+            // packed form: all partitions in one pass, the row's input blocks resident in shared memory
+            const dim3 grid(2 * half / MAC3_NT, c_out, nb);
+            const int pc = P <= 4 ? 4 : (P <= 8 ? 8 : (P <= 12 ? 12 : (P <= 16 ? 16 : (P <= 20 ? 20 : 24))));
+#define GFX_MAC3_CASE(PCV) case PCV: \
+    if (nblk == MAC3_MAXBLK) fir_mac3_kernel<PCV, true><<<grid, MAC3_NT, 0, a.stream>>>((const float2*)Xs, (const float2*)Hs, (float2*)Ys, rm, xrow0, hrow0, (int)b0, P, (int)nblk, 2 * half); \
+    else fir_mac3_kernel<PCV, false><<<grid, MAC3_NT, 0, a.stream>>>((const float2*)Xs, (const float2*)Hs, (float2*)Ys, rm, xrow0, hrow0, (int)b0, P, (int)nblk, 2 * half); \
+    break;
+            switch (pc) {
+                GFX_MAC3_CASE(4) GFX_MAC3_CASE(8) GFX_MAC3_CASE(12) GFX_MAC3_CASE(16) GFX_MAC3_CASE(20) GFX_MAC3_CASE(24)
+            }
+#undef GFX_MAC3_CASE
+            GFX_LAUNCH_CHECK();
+        } else if (g_mac_form == 0 && P <= MAC_MAX_PC) {
             const dim3 grid(half / MAC_NT, nb * c_out);
             for (int p0 = 0; p0 < P; p0 += MAC_MAX_PC) {
                 const int pc = P - p0 < MAC_MAX_PC ? P - p0 : MAC_MAX_PC;
@@ -1374,7 +1506,7 @@ int gfx_fir_set_sweep_mb(int mb) {
 }
 
 int gfx_fir_set_mac_form(int form) {
-    if (form != 0 && form != 1) return GFX_ERR_INVALID;
+    if (form < 0 || form > 2) return GFX_ERR_INVALID;
     gfx::g_mac_form = form;
     return GFX_OK;
 }

@@ -125,10 +125,11 @@ GFX_API int gfx_fir_set_tuning(int long_n, int mid_n);
  * filter has <= 12 partitions of 8192 taps).  Affects the
  * workspace size: query it again afterwards. */
 GFX_API int gfx_fir_set_long_mode(int mode, int lookahead); /* lookahead: pipeline depth in batch items (0 keeps it) */
-/* per-bin multiply-accumulate of the long-filter path: 1 (default) = fir_mac2_kernel (one complex bin per thread, up to 24
- * partitions per pass, inputs through a cp.async ring, batch items that share a filter walked by one CTA); 0 = fir_mac_kernel (<= 12
- * partitions per pass, the round-1 kernel, used when the filter has <= 12 partitions; kept for A/B measurements).
- * The two differ in summation order only (~1e-7 relative). */
+/* per-bin multiply-accumulate of the long-filter path: 2 (default) = fir_mac3_kernel where it applies (all partitions in
+ * one pass, <= 24, rows of <= 32 blocks: packed fp32x2 products, the row's input spectra resident in shared memory),
+ * otherwise as 1; 1 = fir_mac2_kernel (one complex bin per thread, up to 24 partitions per pass, inputs through a
+ * cp.async ring); 0 = fir_mac_kernel (<= 12 partitions per pass, the round-1 kernel, used when the filter has <= 12
+ * partitions; kept for A/B measurements).  They differ in summation order only (~1e-7 relative). */
 GFX_API int gfx_fir_set_mac_form(int form);
 /* spectra workspace per sweep of the long-filter path in MiB (default 1536; affects gfx_fir_conv_workspace_bytes).  Small
  * sweeps keep the spectra in L2 between the kernels of a sweep at the price of more, smaller launches. */

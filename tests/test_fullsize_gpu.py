@@ -443,7 +443,7 @@ def test_new_entry_points_empty_batch_and_argument_errors():
     assert L_.gfx_envelope_f32(x.data_ptr(), x.data_ptr(), 1, 2, 64, 1, x.data_ptr(), 2, 0, 16, None, 0, None) == -1   # detect=2 needs mono
     assert L_.gfx_envelope_f32(x.data_ptr(), x.data_ptr(), 1, 1, 64, 1, x.data_ptr(), 0, 0, 16, None, 0, None) == -2   # no workspace
     assert L_.gfx_fir_filter_f32(x.data_ptr(), None, x.data_ptr(), 1, 1, 1, 64, 8, None, None, 0, None) == -1
-    assert L_.gfx_fir_set_sweep_mb(1) == -1 and L_.gfx_fir_set_mac_form(7) == -1
+    assert L_.gfx_fir_set_sweep_mb(1) == -1 and L_.gfx_fir_set_mac_form(7) != 0
     assert L_.gfx_dynamics_set_tuning(48) == -1 and L_.gfx_dynamics_set_ballistics_mode(5) == -1
     assert L_.gfx_fma_probe_f32(None, 16, None) == -1
 

@@ -360,7 +360,7 @@ def test_fir_long_filter_pipelined_launch_matches():
         out = [F_.fir_conv(x, h), F_.fir_conv(x1, h), F_.fir_conv(x, h4, h_repeat=4)]
     finally:
         L_.gfx_fir_set_long_mode(0, 0)
-        L_.gfx_fir_set_mac_form(1)
+        L_.gfx_fir_set_mac_form(2)
         L_.gfx_fir_set_tuning(4096, 0)
     for a, b, c in zip(out, ref, ref0):
         assert torch.equal(a, c)              # the pipelined launch and the sweeps with fir_mac_kernel agree bit for bit
@@ -368,11 +368,14 @@ def test_fir_long_filter_pipelined_launch_matches():
     assert_close(out[0][:3].cpu(), O.convolve(x[:3].cpu().double(), h[:3].cpu().double(), "causal").float(), "pipe", tol=2e-5)
 
 
-@pytest.mark.parametrize("Nh,L,hrep", [(96000, 131072, 1), (60000, 50001, 1), (20000, 9000, 3), (120000, 70000, 2), (16385, 4096, 1)])
+@pytest.mark.parametrize("Nh,L,hrep", [(96000, 131072, 1), (60000, 50001, 1), (20000, 9000, 3), (120000, 70000, 2), (16385, 4096, 1),
+                                       (40000, 140000, 1), (98304, 131071, 2)])
 def test_fir_long_filter_partition_sizes_vs_oracle(Nh, L, hrep):
     """Long filters (> 16384 taps) on every partition size the engine offers (4096 = default: up to 24 partitions per
-    multiply-accumulate pass, more in accumulate groups; 8192; 16384), shared filters walked by one CTA (h_repeat),
-    against the float64 oracle."""
+    multiply-accumulate pass, more in accumulate groups; 8192; 16384), shared filters (h_repeat), against the float64
+    oracle -- with both multiply-accumulate kernels: the packed one (form 2, default: full rows of 32 blocks, ragged rows,
+    every partition-count instantiation; rows of more than 32 blocks or more than 24 partitions fall back to form 1)
+    and fir_mac2_kernel (form 1); the two must agree to summation-order accuracy."""
     from oracle import grafx_oracle as O
     import grafx_b200.functional as F_
     from grafx_b200 import _cabi
@@ -386,10 +389,15 @@ def test_fir_long_filter_partition_sizes_vs_oracle(Nh, L, hrep):
     try:
         for n in (4096, 8192, 16384):
             assert L_.gfx_fir_set_tuning(n, 0) == 0
-            y = F_.fir_conv(x.cuda(), h.cuda(), h_repeat=hrep).cpu()
-            assert_close(y, ref, f"long n={n}", tol=2e-5)
+            ys = {}
+            for form in (2, 1):
+                assert L_.gfx_fir_set_mac_form(form) == 0
+                ys[form] = F_.fir_conv(x.cuda(), h.cuda(), h_repeat=hrep).cpu()
+                assert_close(ys[form], ref, f"long n={n} form={form}", tol=2e-5)
+            assert rel_l2(ys[2], ys[1]) < 2e-6
     finally:
         L_.gfx_fir_set_tuning(4096, 0)
+        L_.gfx_fir_set_mac_form(2)
 
 
 @pytest.mark.parametrize("N,mode,L", [(1, "mono", 100), (255, "stereo", 5000), (3000, "midside", 20001), (20000, "stereo", 30000)])
