@@ -158,11 +158,13 @@ class GraphWorkload:
     name = "cfg5"
     TOTAL, CHUNK, TRACKS, C, L = 128, 16, 32, 2, 131072
 
-    def __init__(self, world=1, rank=0):
+    def __init__(self, world=1, rank=0, chunk=None):
         self.world, self.rank = world, rank
-        assert self.TOTAL % (self.CHUNK * world) == 0 or self.TOTAL // world < self.CHUNK, "128 renders split evenly over 1/2/4/8 ranks"
+        self.CHUNK = int(chunk) if chunk else self.CHUNK
+        assert self.TOTAL % world == 0, "128 renders split evenly over 1/2/4/8 ranks"
         self.B_local = self.TOTAL // world
         self.chunk = min(self.CHUNK, self.B_local)
+        assert self.B_local % self.chunk == 0, "the renders of a rank split evenly into chunks"
         self.n_chunks = self.B_local // self.chunk
         self.desc = ("mixing graph 32 x (in -> ParametricEqualizer(5, stereo, lfilter) -> Compressor -> STFTMaskedNoiseReverb(96000)) "
                      "-> out, batch=128 renders x 2ch x 131072")
@@ -244,14 +246,15 @@ class GraphWorkload:
         return O.render_plan(procs, x, prm, plan)[0]
 
 
-def config_of(name, world=1):
+def config_of(name, world=1, chunk=None):
     """The `config` object of the JSON line -- the SAME dictionary in both arms (the reference arm runs a bounded
     sample of exactly this configuration; what the sample was is said in its `cpu_baseline.sample`)."""
     if name == "cfg5":
-        g = GraphWorkload(world)
+        g = GraphWorkload(world, chunk=chunk)
         return {"workload": g.desc, "batch": 128, "tracks": 32, "channels": 2, "length": 131072,
                 "renders_per_gpu": g.B_local, "chunks_per_gpu": g.n_chunks,
-                "l2": "inputs larger than L2: each chunk of 16 renders reads 537 MB of sources and fills a 2.16 GB signal buffer (126 MiB L2)",
+                "l2": (f"inputs larger than L2: each chunk of {g.chunk} renders reads {g.chunk * 33.554432:.0f} MB of sources and fills a "
+                       f"{g.chunk * 0.135266304:.2f} GB signal buffer (126 MiB L2)"),
                 "parallelism": (f"batch-of-renders shard x{world}; async NCCL all_gather of the mixes overlapping the next step"
                                 if world > 1 else "single GPU: all 128 renders, no collective")}
     wl = Workload(name)
@@ -440,7 +443,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_sample_step"], "higher_is_better": True,
             "scaling": "strong" if args.workload == "cfg5" else "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config_of(args.workload, args.gpus), "cpu_baseline": cb,
+            "data": "synthetic", "config": config_of(args.workload, args.gpus, args.chunk), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -710,6 +713,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-per-config", action="store_true")
     ap.add_argument("--per-config", default="cfg1,cfg2,cfg2lf,cfg3,cfg3b,cfg4,cfg4b")
+    ap.add_argument("--chunk", type=int, default=None, help="config 5: renders per captured plan (default: GraphWorkload.CHUNK)")
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--e2e-streams", type=int, default=3)
     args = ap.parse_args()
@@ -743,7 +747,7 @@ def main():
     steps, warmup = args.steps, max(args.warmup, 3)
 
     if args.workload == "cfg5":
-        wl = GraphWorkload(world, rank)
+        wl = GraphWorkload(world, rank, chunk=args.chunk)
         wl.build(device)
         with torch.no_grad():
             wl.capture()
@@ -761,17 +765,17 @@ def main():
             k_ms, _ = timed_blocks(renders_only, max(2, steps // 4), min(args.min_seconds, 0.3), barrier, device, max_over_ranks)
             launches = wl.caps[0].launches_per_replay
             roofline = roofline_of("cfg5", wl.alg_bytes_local(), wl.flops_per_out_sample * wl.B_local * wl.C * wl.L, k_ms,
-                                   "render_grafx, 5 render orders per chunk of 16 renders: biquad_cascade_x2 (reads the sources, fills the buffer's source slice), dynamics, "
+                                   f"render_grafx, 5 render orders per chunk of {wl.chunk} renders: biquad_cascade_x2 (reads the sources, fills the buffer's source slice), dynamics, "
                                    "reverb pipeline (reverb_ir + filter spectra + partitioned overlap-save), node_sum; CUDA-graph replay",
                                    launches, fma_rate)
             roofline["bytes_convention"] = "contract-preserving render: 289 node-signal passes (129 written, 160 read) x 1 MiB per render"
             roofline["gather_ms_per_step"] = max(ms_step - k_ms, 0.0)
             e2e = None if args.no_e2e else e2e_graph(wl, device, steps, barrier, max_over_ranks, local_rank)
         gpu_launches = None if launches is None else launches * wl.n_chunks * steps * len(blocks) * world
-        config = config_of("cfg5", world)
+        config = config_of("cfg5", world, args.chunk)
         scaling = "strong"
         main_wl_for_cpu = "cfg5"
-        extra = {"timed_blocks": len(blocks), "steps_per_block": steps, "launch": "cuda_graph (CapturedRender, one plan per chunk of 16 renders)"}
+        extra = {"timed_blocks": len(blocks), "steps_per_block": steps, "launch": f"cuda_graph (CapturedRender, one plan per chunk of {wl.chunk} renders)"}
     else:
         with torch.no_grad():
             rec, pw = measure_processor(args.workload, device, steps, warmup, args.min_seconds, world, barrier, max_over_ranks,

@@ -25,7 +25,8 @@ x = torch.randn(512, 2, 131072, device="cuda")
 h = torch.randn(512, 2, 96000, device="cuda") / 300
 h32 = torch.randn(32, 2, 96000, device="cuda") / 300
 h60 = torch.randn(512, 2, 60000, device="cuda") / 300
-for n, form in ((4096, 2), (4096, 1), (8192, 2), (8192, 1)):
+combos = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]] or [(4096, 2), (4096, 1), (8192, 2), (8192, 1)]
+for n, form in combos:
     L_.gfx_fir_set_tuning(n, 0)
     L_.gfx_fir_set_mac_form(form)
     a = timeit(lambda: F_.fir_conv(x, h))
