@@ -6,7 +6,7 @@
 
 Default workload = BASELINE.json configs[4], the configuration the multi-GPU metric is quoted on: the 32-track mixing
 graph (in -> ParametricEqualizer -> Compressor -> STFTMaskedNoiseReverb -> out bus), batch 128, 2 ch x 131072 samples.
-The batch of renders is SHARDED over the ranks (128 / N renders per GPU, rendered in chunks of 16 through
+The batch of renders is SHARDED over the ranks (128 / N renders per GPU, rendered in chunks of (up to) 32 through
 CUDA-graph-captured `render_grafx` plans), the mixes are all-gathered over NCCL (asynchronously, overlapping the next
 step) -> `scaling: "strong"`.  At N = 1 the same JSON line also carries `per_config`: one sub-record per other
 BASELINE config (cfg1 .. cfg4b) with its own roofline and CPU baseline.  A step = one pass over the whole batch.
@@ -156,7 +156,9 @@ class GraphWorkload:
     """BASELINE config 5: 32 x (in -> eq -> compressor -> reverb) -> out, batch 128 sharded over the ranks."""
 
     name = "cfg5"
-    TOTAL, CHUNK, TRACKS, C, L = 128, 16, 32, 2, 131072
+    # CHUNK: renders per captured plan (every tensor of a chunk stays below 2^31 elements: the signal buffer of 32 renders
+    # has 1.08e9); measured on one B200: 16 renders per plan 16.47 ms per step, 32 renders 15.96 ms (profiles/r02_chunk_size.txt)
+    TOTAL, CHUNK, TRACKS, C, L = 128, 32, 32, 2, 131072
 
     def __init__(self, world=1, rank=0, chunk=None):
         self.world, self.rank = world, rank

@@ -1255,7 +1255,8 @@ __global__ void fft_plan_pass_kernel(float2* tab, int M, int R) {
 static int g_long_n = 4096;  // partition size of the long-filter path (tunable: gfx_fir_set_tuning).  Measured on B200 at the
                              // BASELINE reverb shape (profiles/r02_*): 4096-point FFT kernels run 4 CTAs per SM (955 us for the three
                              // FFT kernels vs 1350 us at 8192 points, 2 CTAs per SM); fir_mac2_kernel keeps the 24 partitions in one pass
-static int g_sweep_mb = 1536; // spectra workspace per sweep of the long-filter path (gfx_fir_set_sweep_mb)
+static int g_sweep_mb = 6144; // spectra workspace per sweep of the long-filter path (gfx_fir_set_sweep_mb); fewer, larger launches
+                              // win: 768 / 1536 / 3072 MiB = 1.473 / 1.390 / 1.342 ms at the BASELINE reverb shape (profiles/r02_sweep_size_mac3.txt)
 static int g_mac_form = 2;   // 0: fir_mac_kernel (<= 12 partitions per pass) when it applies; 1: fir_mac2_kernel;
                              // 2: fir_mac3_kernel (packed) when it applies (P <= 24, <= 32 blocks per row), else fir_mac2_kernel
 static int g_mid_n = 8192;   // FFT size for 2048 < taps <= g_mid_n / 2 (longer single-partition filters: 16384)
@@ -1558,7 +1559,7 @@ size_t gfx_fir_conv_workspace_bytes(int batch, int cx, int ch, long long L, int 
     gfx::upols_geometry(cx, ch, L, filter_len, zerophase ? filter_len / 2 : 0, n, P, nblk, per_item);
     if (gfx::g_long_mode == 1 && P <= gfx::MAC_MAX_PC && n == 8192)
         return gfx::upols_ctr_bytes(batch) + (size_t)gfx::upols_r() * per_item;  // pipelined launch: a ring of item slots
-    // spectra of up to ~1.5 GB worth of batch items per sweep (every kernel of a sweep then has several full waves)
+    // spectra of up to g_sweep_mb worth of batch items per sweep (every kernel of a sweep then has many full waves)
     size_t items = ((size_t)gfx::g_sweep_mb << 20) / per_item;
     if (items < 1) items = 1;
     if (items > (size_t)batch) items = batch;

@@ -131,7 +131,7 @@ GFX_API int gfx_fir_set_long_mode(int mode, int lookahead); /* lookahead: pipeli
  * cp.async ring); 0 = fir_mac_kernel (<= 12 partitions per pass, the round-1 kernel, used when the filter has <= 12
  * partitions; kept for A/B measurements).  They differ in summation order only (~1e-7 relative). */
 GFX_API int gfx_fir_set_mac_form(int form);
-/* spectra workspace per sweep of the long-filter path in MiB (default 1536; affects gfx_fir_conv_workspace_bytes).  Small
+/* spectra workspace per sweep of the long-filter path in MiB (default 6144; affects gfx_fir_conv_workspace_bytes).  Small
  * sweeps keep the spectra in L2 between the kernels of a sweep at the price of more, smaller launches. */
 GFX_API int gfx_fir_set_sweep_mb(int mb);
 /* FIRFilter.forward (processors/filter.py:65-77): taps = normalize_impulse(tanh(fir_raw)) -- the activation and the

@@ -148,7 +148,7 @@ def test_bench_config_is_identical_in_both_arms_and_the_shard_covers_the_batch()
         total = 0
         for rank in range(world):
             g = bench.GraphWorkload(world, rank)
-            assert g.n_chunks * g.chunk == g.B_local and g.chunk <= 16
+            assert g.n_chunks * g.chunk == g.B_local and g.chunk <= 32
             total += g.B_local
         assert total == 128
         assert bench.config_of("cfg5", world)["renders_per_gpu"] == 128 // world
