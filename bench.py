@@ -160,8 +160,9 @@ class GraphWorkload:
     # has 1.08e9); measured on one B200: 16 renders per plan 16.47 ms per step, 32 renders 15.96 ms (profiles/r02_chunk_size.txt)
     TOTAL, CHUNK, TRACKS, C, L = 128, 32, 32, 2, 131072
 
-    def __init__(self, world=1, rank=0, chunk=None):
+    def __init__(self, world=1, rank=0, chunk=None, chunk_streams=1):
         self.world, self.rank = world, rank
+        self.chunk_streams = max(1, int(chunk_streams))
         self.CHUNK = int(chunk) if chunk else self.CHUNK
         assert self.TOTAL % world == 0, "128 renders split evenly over 1/2/4/8 ranks"
         self.B_local = self.TOTAL // world
@@ -211,9 +212,23 @@ class GraphWorkload:
         import torch.distributed as dist
 
         mix = self.mix[self.k & 1]
-        for i, cap in enumerate(self.caps):
-            out, _, _ = cap()
-            mix[i * self.chunk:(i + 1) * self.chunk].copy_(out)
+        if self.chunk_streams > 1 and len(self.caps) > 1:
+            # independent chunks on a few streams (experiment: --chunk-streams): fork from / join into the current stream
+            main = torch.cuda.current_stream()
+            if not hasattr(self, "_side"):
+                self._side = [torch.cuda.Stream(self.device) for _ in range(min(self.chunk_streams, len(self.caps)))]
+            for st in self._side:
+                st.wait_stream(main)
+            for i, cap in enumerate(self.caps):
+                with torch.cuda.stream(self._side[i % len(self._side)]):
+                    out, _, _ = cap()
+                    mix[i * self.chunk:(i + 1) * self.chunk].copy_(out)
+            for st in self._side:
+                main.wait_stream(st)
+        else:
+            for i, cap in enumerate(self.caps):
+                out, _, _ = cap()
+                mix[i * self.chunk:(i + 1) * self.chunk].copy_(out)
         if self.world > 1:
             if self.pending is not None:
                 self.pending.wait()
@@ -716,6 +731,7 @@ def main():
     ap.add_argument("--no-per-config", action="store_true")
     ap.add_argument("--per-config", default="cfg1,cfg2,cfg2lf,cfg3,cfg3b,cfg4,cfg4b")
     ap.add_argument("--chunk", type=int, default=None, help="config 5: renders per captured plan (default: GraphWorkload.CHUNK)")
+    ap.add_argument("--chunk-streams", type=int, default=1, help="config 5: independent chunks replayed on this many streams")
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--e2e-streams", type=int, default=3)
     args = ap.parse_args()
@@ -749,7 +765,7 @@ def main():
     steps, warmup = args.steps, max(args.warmup, 3)
 
     if args.workload == "cfg5":
-        wl = GraphWorkload(world, rank, chunk=args.chunk)
+        wl = GraphWorkload(world, rank, chunk=args.chunk, chunk_streams=args.chunk_streams)
         wl.build(device)
         with torch.no_grad():
             wl.capture()
