@@ -190,7 +190,7 @@ class GraphWorkload:
                     for k, v in p.parameter_size().items()} for t, p in procs.items()}
 
     def capture(self):
-        """One CUDA-graph-captured render plan per chunk of 16 renders; the chunk's sources are the capture's static
+        """One CUDA-graph-captured render plan per chunk of (up to) 32 renders; the chunk's sources are the capture's static
         input tensor (filled on the device: inputs are HBM-resident when the timed region starts)."""
         from grafx_b200.render import CapturedRender
 
