@@ -46,8 +46,8 @@ SIGNATURES = {
     "gfx_biquad_cascade_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "gfx_biquad_cascade_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_ll, c_void_p, c_size_t, c_void_p]),
-    "gfx_biquad_cascade_src_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                           c_int, c_ll, c_void_p, c_size_t, c_void_p]),
+    "gfx_biquad_cascade_ex_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ll,
+                                          c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "gfx_biquad_cascade_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_ll, c_void_p, c_size_t, c_void_p]),
     "gfx_dynamics_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -55,6 +55,8 @@ SIGNATURES = {
     "gfx_dynamics_set_ballistics_mode": (c_int, [c_int]),
     "gfx_dynamics_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, ctypes.POINTER(DynamicsStage), c_int,
                                  c_int, c_void_p, c_size_t, c_void_p]),
+    "gfx_dynamics_rep_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, ctypes.POINTER(DynamicsStage), c_int,
+                                     c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "gfx_envelope_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                  c_size_t, c_void_p]),
     "gfx_fir_fft_size": (c_int, [c_int]),

@@ -116,14 +116,23 @@ __global__ void __launch_bounds__(128) cascade_tables_kernel(const T* __restrict
 constexpr int X2_TAB = 57;        // 37 double entries + 20 (= 40 float4: M^0..32, N, M^64 as fp32, for well-conditioned sections)
 constexpr double X2_ILL_GROWTH = 4.0;  // a section whose chunk-matrix powers exceed this is propagated in double
 
+// coef_rep > 1: runs of coef_rep consecutive batch items share one coefficient row of Bs / As (render_grafx's 4-D sources);
+// the table of every (item, channel, section) is written all the same, so the sample kernel is unaware of it
 __global__ void __launch_bounds__(128) cascade_x2_tables_kernel(const float* __restrict__ Bs, const float* __restrict__ As,
-                                                                double* __restrict__ tables, int n_sections) {
+                                                                double* __restrict__ tables, int n_sections, int K, int c_filt,
+                                                                int coef_rep) {
     constexpr int S = 32;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= n_sections) return;
-    const float* bp = Bs + (size_t)w * 3;
-    const float* ap = As + (size_t)w * 3;
+    size_t src = (size_t)w;
+    if (coef_rep > 1) {
+        const int crow = w / K, k = w - crow * K;
+        const int b = crow / c_filt, cf = crow - b * c_filt;
+        src = ((size_t)(b / coef_rep) * c_filt + cf) * K + k;
+    }
+    const float* bp = Bs + src * 3;
+    const float* ap = As + src * 3;
     const float a0 = ap[0];
     const float nb0 = bp[0] / a0, nb1 = bp[1] / a0, nb2 = bp[2] / a0;
     const float na1 = ap[1] / a0, na2 = ap[2] / a0;
@@ -832,7 +841,7 @@ static size_t cascade_workspace_bytes(int rows, int coef_rows, int K, size_t ele
 template <typename T>
 static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch, int c_sig,
                           int c_filt, int K, long long L, void* ws, size_t ws_bytes,
-                          cudaStream_t stream, T* xcopy = nullptr, int src_outer = 0, int src_inner = 0) {
+                          cudaStream_t stream, T* xcopy = nullptr, int src_outer = 0, int src_inner = 0, int coef_repeat = 1) {
     constexpr int NT = 256;
     constexpr int S = 128 / (int)sizeof(T);
     constexpr int MINB = sizeof(T) == 4 ? 3 : 1;
@@ -841,6 +850,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     if (c_sig != c_filt && c_sig != 1 && c_filt != 1) return GFX_ERR_INVALID;
     if (K > 64) return GFX_ERR_UNSUPPORTED;
     const int c_out = c_sig > c_filt ? c_sig : c_filt;
+    if (coef_repeat < 1 || batch % coef_repeat != 0 || (coef_repeat > 1 && sizeof(T) != 4)) return GFX_ERR_INVALID;
     if (xcopy != nullptr || src_outer != 0 || src_inner != 0) {
         // source-reading form: fp32 packed kernel only, one output row per input row, batch = src_outer * src_inner
         if (sizeof(T) != 4 || xcopy == nullptr || c_sig != c_out) return GFX_ERR_INVALID;
@@ -880,7 +890,7 @@ static int launch_cascade(const T* x, T* y, const T* Bs, const T* As, int batch,
     const int n_sections = coef_rows * K;
     if constexpr (sizeof(T) == 4) {
         p.xtables = (const double*)tables;
-        cascade_x2_tables_kernel<<<(n_sections * 32 + 127) / 128, 128, 0, stream>>>(Bs, As, (double*)tables, n_sections);
+        cascade_x2_tables_kernel<<<(n_sections * 32 + 127) / 128, 128, 0, stream>>>(Bs, As, (double*)tables, n_sections, K, c_filt, coef_repeat);
     } else {
         p.xtables = nullptr;
         cascade_tables_kernel<T><<<(n_sections * 32 + 127) / 128, 128, 0, stream>>>(Bs, As, tables, n_sections);
@@ -952,12 +962,11 @@ int gfx_biquad_cascade_f32(const float* x, float* y, const float* Bs, const floa
                                       workspace_bytes, (cudaStream_t)stream);
 }
 
-int gfx_biquad_cascade_src_f32(const float* src, float* xcopy, float* y, const float* Bs, const float* As,
-                               int src_outer, int src_inner, int c_sig, int c_filt, int K, long long L,
-                               void* workspace, size_t workspace_bytes, void* stream) {
-    if ((long long)src_outer * src_inner > 0x7fffffffLL) return GFX_ERR_UNSUPPORTED;
-    return gfx::launch_cascade<float>(src, y, Bs, As, src_outer * src_inner, c_sig, c_filt, K, L, workspace,
-                                      workspace_bytes, (cudaStream_t)stream, xcopy, src_outer, src_inner);
+int gfx_biquad_cascade_ex_f32(const float* x, float* xcopy, float* y, const float* Bs, const float* As, int batch,
+                              int c_sig, int c_filt, int K, long long L, int src_outer, int src_inner, int coef_repeat,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    return gfx::launch_cascade<float>(x, y, Bs, As, batch, c_sig, c_filt, K, L, workspace, workspace_bytes,
+                                      (cudaStream_t)stream, xcopy, src_outer, src_inner, coef_repeat);
 }
 
 int gfx_biquad_cascade_f64(const double* x, double* y, const double* Bs, const double* As, int batch,

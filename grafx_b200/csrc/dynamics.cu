@@ -60,6 +60,8 @@ struct DynParams {
     int* lookback;  // [batch] ballistics launches: samples of warm-up that make a chunk independent of its past (>= 0: the row
                     // is done by dynamics_spec_kernel), or -1 (the row-owner kernel walks the row); null: walk every row
     int spec_ch;    // samples per thread of dynamics_spec_kernel
+    int param_rep;  // runs of this many consecutive rows share one parameter row (render_grafx's 4-D sources; 1 otherwise):
+                    // only dynamics_tables_kernel reads the parameter tensors, it writes every row's table
     int envelope;   // 0: dynamics processors; 1: envelope output
     int detect;     // envelope mode: 0 mean_c x^2, 1 mean_c |x|, 2 x itself (C == 1)
     int env_log;    // envelope mode: y = log(envelope + 1e-5)
@@ -424,6 +426,7 @@ __global__ void dynamics_tables_kernel(const DynParams p, float* __restrict__ ta
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.batch * p.n_stages) return;
     const int row = idx / p.n_stages, d = idx - row * p.n_stages;
+    const int prow = row / p.param_rep;  // row of the parameter tensors
     if (d == 0 && p.lookback) {
         // total warm-up of the chain: the followers of the stages settle one after the other
         long long lb = 0;
@@ -431,7 +434,7 @@ __global__ void dynamics_tables_kernel(const DynParams p, float* __restrict__ ta
             for (int which = 0; which < 2; ++which) {
                 const SmootherDesc& sm = which ? p.st[dd].post : p.st[dd].pre;
                 if (sm.kind == 2)
-                    lb += ballistics_warmup(1.f / (1.f + expf(-sm.z[(size_t)row * 2 + 0])), 1.f / (1.f + expf(-sm.z[(size_t)row * 2 + 1])));
+                    lb += ballistics_warmup(1.f / (1.f + expf(-sm.z[(size_t)prow * 2 + 0])), 1.f / (1.f + expf(-sm.z[(size_t)prow * 2 + 1])));
             }
         }
         // worth it while the redundant warm-up stays below ~16 chunks (a single slow row is still far ahead of a walk)
@@ -445,7 +448,7 @@ __global__ void dynamics_tables_kernel(const DynParams p, float* __restrict__ ta
         for (int i = 0; i < DYN_SC_FLOATS; ++i) reinterpret_cast<float*>(&c)[i] = 0.f;
         if (sm.kind == 1) {
             // TruncatedOnePoleIIRFilter (core/envelope.py:44-49): alpha = min(sigmoid(z), 1 - 1e-5)
-            float alpha = 1.f / (1.f + expf(-sm.z[row]));
+            float alpha = 1.f / (1.f + expf(-sm.z[prow]));
             alpha = fminf(alpha, 1.f - 1e-5f);
             const double ad = (double)alpha;
             c.alpha = alpha;
@@ -462,15 +465,15 @@ __global__ void dynamics_tables_kernel(const DynParams p, float* __restrict__ ta
             c.aW = (float)sq;
         } else if (sm.kind == 2) {
             // Ballistics (core/envelope.py:84-101)
-            c.at = 1.f / (1.f + expf(-sm.z[(size_t)row * 2 + 0]));
-            c.rt = 1.f / (1.f + expf(-sm.z[(size_t)row * 2 + 1]));
+            c.at = 1.f / (1.f + expf(-sm.z[(size_t)prow * 2 + 0]));
+            c.rt = 1.f / (1.f + expf(-sm.z[(size_t)prow * 2 + 1]));
         }
         float* dst = base + (2 * d + which) * DYN_SC_FLOATS;
         for (int i = 0; i < DYN_SC_FLOATS; ++i) dst[i] = reinterpret_cast<const float*>(&c)[i];
     }
     KneeConst k;
     for (int i = 0; i < DYN_KC_FLOATS; ++i) reinterpret_cast<float*>(&k)[i] = 0.f;
-    const float T = sd.log_threshold[row] - 6.f, lr = sd.log_ratio[row], lk = sd.log_knee ? sd.log_knee[row] : 0.f;
+    const float T = sd.log_threshold[prow] - 6.f, lr = sd.log_ratio[prow], lk = sd.log_knee ? sd.log_knee[prow] : 0.f;
     // ApproxNoiseGate.compute_gain (dynamics.py:186-204): R = exp(log_ratio) (no +1) and the knee term is
     // (1 - R)(d - W)^2 / (2 (2W + 1e-3)); the three regions are those of the quadratic gate knee
     const bool approx_gate = sd.knee == 3;
@@ -984,11 +987,19 @@ size_t gfx_dynamics_workspace_bytes(int batch, int n_stages) { return gfx::dyn_w
 int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long long L,
                      const gfx_dynamics_stage* stages, int n_stages, int iir_len, void* workspace,
                      size_t workspace_bytes, void* stream) {
+    return gfx_dynamics_rep_f32(x, y, batch, channels, L, stages, n_stages, iir_len, 1, workspace, workspace_bytes, stream);
+}
+
+int gfx_dynamics_rep_f32(const float* x, float* y, int batch, int channels, long long L,
+                         const gfx_dynamics_stage* stages, int n_stages, int iir_len, int param_repeat, void* workspace,
+                         size_t workspace_bytes, void* stream) {
     using namespace gfx;
     if (!x || !y || !stages) return GFX_ERR_INVALID;
     if (batch <= 0 || channels <= 0 || L <= 0 || n_stages <= 0 || iir_len <= 0) return GFX_ERR_INVALID;
+    if (param_repeat <= 0 || batch % param_repeat != 0) return GFX_ERR_INVALID;
     if (n_stages > DYN_MAX_STAGES) return GFX_ERR_UNSUPPORTED;
     DynParams p;
+    p.param_rep = param_repeat;
     p.envelope = 0; p.detect = 0; p.env_log = 0; p.lookback = nullptr; p.spec_ch = 0;
     bool any_ballistics = false, any_iir = false;
     for (int d = 0; d < n_stages; ++d) {
@@ -1050,6 +1061,7 @@ int gfx_envelope_f32(const float* x, float* y, int batch, int channels, long lon
     if (batch <= 0 || channels <= 0 || L <= 0 || iir_len <= 0) return GFX_ERR_INVALID;
     if (smoother < 1 || smoother > 2 || detect < 0 || detect > 2 || (detect == 2 && channels != 1)) return GFX_ERR_INVALID;
     DynParams p;
+    p.param_rep = 1;
     p.envelope = 1; p.detect = detect; p.env_log = log_out ? 1 : 0; p.lookback = nullptr; p.spec_ch = 0;
     StageDesc& o = p.st[0];
     o.kind = 0; o.knee = 0; o.log_domain = 0;

@@ -62,7 +62,7 @@ def parameter_repeat() -> int:
 class source_fold:
     """`with source_fold(sources, view) as f:` -- render_grafx's first render order (4-D sources).  `view` is the
     source slice of the signal buffer, flattened node-major `[V0 * B, C, L]` and NOT filled yet; `sources` is the
-    caller's `[B, V0, C, L]` tensor.  An op that supports it (the biquad cascade, gfx_biquad_cascade_src_f32) and is
+    caller's `[B, V0, C, L]` tensor.  An op that supports it (the biquad cascade, gfx_biquad_cascade_ex_f32) and is
     handed `view` as its signal reads `sources` instead and fills `view` from the tile it staged anyway, so the separate
     copy pass never reads the sources a second time.  `f.used` tells the caller whether that happened: if not, the
     caller fills `view` itself and runs the processor again (render/graph.py)."""
@@ -120,14 +120,21 @@ def _prep(t: torch.Tensor, dtype=None) -> torch.Tensor:
 def biquad_cascade(x: torch.Tensor, Bs: torch.Tensor, As: torch.Tensor) -> torch.Tensor:
     """Exact cascade of K biquads (reference: IIRFilter._process_lfilter, core/iir.py:154-184).
 
-    x [B, C, L]; Bs, As [B, Cf, K, 3] -> y [B, max(C, Cf), L].  float32 or float64."""
+    x [B, C, L]; Bs, As [B, Cf, K, 3] -> y [B, max(C, Cf), L].  float32 or float64.
+    Inside `shared_parameters(R)` (render_grafx's 4-D sources) the coefficients may also come un-expanded,
+    [B / R, Cf, K, 3]: runs of R consecutive batch items then share a coefficient row."""
     _cabi.require_cuda(x, Bs, As)
     assert x.ndim == 3 and Bs.ndim == 4 and As.shape == Bs.shape and Bs.shape[-1] == 3
     b, c_sig, L = x.shape
     bb, c_filt, K, _ = Bs.shape
-    assert bb == b, "batch size of the coefficients must match the signal"
+    rep = 1
+    if bb != b:
+        rep = parameter_repeat()
+        assert rep > 1 and bb * rep == b, "batch size of the coefficients must match the signal"
     if not (c_sig == c_filt or c_sig == 1 or c_filt == 1):
         raise AssertionError("channel mismatch between signal and filter")
+    if rep > 1 and (_wants_grad(x, Bs, As) or x.dtype == torch.float64):
+        Bs, As, rep = Bs.repeat_interleave(rep, 0), As.repeat_interleave(rep, 0), 1  # (differentiable; float64: no repeat form)
     if _wants_grad(x, Bs, As):
         if x.dtype == torch.float64:
             raise NotImplementedError("the backward pass of the biquad cascade is float32 only")
@@ -145,15 +152,19 @@ def biquad_cascade(x: torch.Tensor, Bs: torch.Tensor, As: torch.Tensor) -> torch
     elem = 4 if dtype == torch.float32 else 8
     ws_bytes = L_.gfx_biquad_cascade_workspace_bytes(b, c_sig, c_filt, K, elem)
     ws = _cabi.workspace(ws_bytes, x.device)
-    if fold is not None:
-        # first render order of render_grafx: read the caller's [B, V0, C, L] sources, fill the buffer's source slice (x)
-        n_renders, n_sources = fold.sources.shape[0], fold.sources.shape[1]
+    if fold is not None or rep > 1:
+        # render_grafx's batched sources: un-expanded coefficient rows and / or the first render order, which reads the
+        # caller's [B, V0, C, L] sources and fills the buffer's source slice (x) on the way
+        src, xcopy, n_renders, n_sources = x.data_ptr(), None, 0, 0
+        if fold is not None:
+            src, xcopy = fold.sources.data_ptr(), x.data_ptr()
+            n_renders, n_sources = fold.sources.shape[0], fold.sources.shape[1]
         with torch.cuda.device(x.device):
-            code = L_.gfx_biquad_cascade_src_f32(fold.sources.data_ptr(), x.data_ptr(), y.data_ptr(), Bs.data_ptr(),
-                                                 As.data_ptr(), n_renders, n_sources, c_sig, c_filt, K, L,
-                                                 ws.data_ptr(), ws.numel(), _cabi.stream_ptr())
-        _cabi.check(code, "gfx_biquad_cascade_src")
-        fold.used = True
+            code = L_.gfx_biquad_cascade_ex_f32(src, xcopy, y.data_ptr(), Bs.data_ptr(), As.data_ptr(), b, c_sig, c_filt, K, L,
+                                                n_renders, n_sources, rep, ws.data_ptr(), ws.numel(), _cabi.stream_ptr())
+        _cabi.check(code, "gfx_biquad_cascade_ex")
+        if fold is not None:
+            fold.used = True
         return y
     fn = L_.gfx_biquad_cascade_f32 if dtype == torch.float32 else L_.gfx_biquad_cascade_f64
     with torch.cuda.device(x.device):
@@ -327,11 +338,20 @@ def dynamics_chain(x: torch.Tensor, stages: list[dict], iir_len: int = 16384) ->
     L_ = _cabi.lib()
     keep = []  # keep parameter tensors alive until the launch is enqueued
 
+    # parameter rows: B, or -- inside `shared_parameters(R)`, render_grafx's 4-D sources -- B / R un-expanded rows
+    # (runs of R consecutive batch items share a row; every parameter tensor of the call the same way)
+    rows = next(v.shape[0] for st in stages for v in st.values() if isinstance(v, torch.Tensor))
+    rep = 1
+    if rows != B:
+        rep = parameter_repeat()
+        assert rep > 1 and rows * rep == B, "batch size of the parameters must match the signal"
+
     def dev(t, cols):
         if t is None:
             return None
         _cabi.require_cuda(t)
-        t = _prep(t, torch.float32).reshape(B, -1)
+        assert t.shape[0] == rows, "every parameter tensor of a dynamics call has the same number of rows"
+        t = _prep(t, torch.float32).reshape(rows, -1)
         assert t.shape[1] == cols, f"parameter has {t.shape[1]} columns, expected {cols}"
         keep.append(t)
         return t.data_ptr()
@@ -367,8 +387,8 @@ def dynamics_chain(x: torch.Tensor, stages: list[dict], iir_len: int = 16384) ->
                 s.hist_post = h.data_ptr()
     ws = _cabi.workspace(L_.gfx_dynamics_workspace_bytes(B, len(stages)), x.device)
     with torch.cuda.device(x.device):
-        code = L_.gfx_dynamics_f32(x.data_ptr(), y.data_ptr(), B, C, L, arr, len(stages), int(iir_len),
-                                   ws.data_ptr(), ws.numel(), _cabi.stream_ptr())
+        code = L_.gfx_dynamics_rep_f32(x.data_ptr(), y.data_ptr(), B, C, L, arr, len(stages), int(iir_len), rep,
+                                       ws.data_ptr(), ws.numel(), _cabi.stream_ptr())
     _cabi.check(code, "gfx_dynamics_f32")
     # the caching allocator keeps stream order: freeing `keep`/`ws` here is safe on this stream
     return y

@@ -55,6 +55,11 @@ class _DynamicsBase(nn.Module):
         st = self.stage(log_threshold, log_ratio, log_knee, z_alpha_pre, z_alpha_post)
         return F_.dynamics_chain(input_signals, [st], self.iir_len)
 
+    def accepts_parameter_repeat(self):
+        """render_grafx (4-D sources): un-expanded per-node parameter rows are fine (F_.shared_parameters,
+        gfx_dynamics_rep_f32)."""
+        return True
+
     def parameter_size(self):
         size = {"log_threshold": 1, "log_ratio": 1}
         if self.knee != "hard":

@@ -33,6 +33,11 @@ class ParametricEqualizer(nn.Module):
         """render_grafx: the first kernel to read `input_signals` is the biquad cascade (F_.source_fold)."""
         return self.processor_channel != "midside" and self.biquad.backend != "fsm"
 
+    def accepts_parameter_repeat(self):
+        """render_grafx (4-D sources): the per-node parameter rows may arrive un-expanded (F_.shared_parameters): the
+        design runs on them as they are and the cascade shares a coefficient row over each run of batch items."""
+        return self.biquad.backend != "fsm"
+
     def parameter_size(self):
         n_channels = 1 if self.processor_channel == "mono" else 2
         return {k: (n_channels, self.num_filters) for k in ("w0", "q_inv", "log_gain")}
@@ -58,6 +63,9 @@ class GraphicEqualizer(nn.Module):
 
     def folds_source_read(self):
         return self.processor_channel != "midside" and self.biquad.backend != "fsm"
+
+    def accepts_parameter_repeat(self):
+        return self.biquad.backend != "fsm"
 
     def parameter_size(self):
         n_channels = 1 if self.processor_channel == "mono" else 2

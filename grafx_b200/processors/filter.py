@@ -54,6 +54,10 @@ class _BiquadStack(nn.Module):
         """render_grafx: the first kernel to read `input_signals` is the biquad cascade (F_.source_fold)."""
         return self.biquad.backend != "fsm"
 
+    def accepts_parameter_repeat(self):
+        """render_grafx (4-D sources): un-expanded per-node parameter rows are fine (F_.shared_parameters)."""
+        return self.biquad.backend != "fsm"
+
 
 class BiquadFilter(_BiquadStack):
     """filter.py:87-168."""

@@ -54,6 +54,10 @@ class STFTMaskedNoiseReverb(nn.Module):
         return F_.reverb_ir(noise, init_log_magnitude, delta_log_magnitude, genv, self.window, self.ir_len,
                             self.n_fft, self.hop_length, finish=finish)
 
+    def accepts_parameter_repeat(self):
+        """render_grafx (4-D sources): this module takes the per-node parameter rows un-expanded (functional.shared_parameters)."""
+        return bool(self.fixed_noise)
+
     def compute_ir(self, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude=None):
         """The un-normalised mid/side impulse response [B, 2, ir_len], as upstream (reverb.py:161-200: the
         channel-mode epilogue and normalize_impulse belong to _process_*, not to compute_ir)."""
@@ -66,9 +70,12 @@ class STFTMaskedNoiseReverb(nn.Module):
         if F_._wants_grad(input_signals, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude):
             return self._forward_training(input_signals, init_log_magnitude, delta_log_magnitude, gain_env_log_magnitude)
         # render_grafx (4-D sources) repeats every node's parameters over the batch of renders: synthesise each
-        # response (and its spectra) once
+        # response (and its spectra) once -- the parameters arrive expanded ([N, ...]: every rep-th row is taken) or, when
+        # render_grafx knows this module accepts them (`accepts_parameter_repeat`), as the un-expanded [N / rep, ...] rows
         rep = F_.parameter_repeat()
-        if rep > 1 and self.fixed_noise and init_log_magnitude.shape[0] % rep == 0:
+        if rep > 1 and self.fixed_noise and init_log_magnitude.shape[0] * rep == input_signals.shape[0]:
+            pass
+        elif rep > 1 and self.fixed_noise and init_log_magnitude.shape[0] % rep == 0:
             init_log_magnitude, delta_log_magnitude = init_log_magnitude[::rep], delta_log_magnitude[::rep]
             if gain_env_log_magnitude is not None:
                 gain_env_log_magnitude = gain_env_log_magnitude[::rep]

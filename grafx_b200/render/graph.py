@@ -147,7 +147,13 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
             inputs.append(post(src))
 
         if is_proc:
-            parameters = _map_tensors(_read(per_type_parameters[node_type], it.parameter_read, 0), batched)
+            # 4-D sources: every node's parameter rows repeat over the batch of renders; a processor that says so
+            # (`accepts_parameter_repeat`) gets them un-expanded inside `shared_parameters(B)` and shares each row over a run
+            # of B batch items in its kernels, the others get the expansion upstream makes (render/graph.py:132-147)
+            share = ndim == 4 and common_parameters is None
+            plain = share and getattr(processors[node_type], "accepts_parameter_repeat", lambda: False)()
+            parameters = _map_tensors(_read(per_type_parameters[node_type], it.parameter_read, 0),
+                                      (lambda t: t.detach()) if plain else batched)
             common_i = {}
             if common_parameters is not None:
                 common_i = _map_tensors(_read(common_parameters, dest, 0), batched)
@@ -157,7 +163,7 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
                 parameters = {"parameter": parameters}
             def run():
                 with F_.output_into(post(dest_view) if dest_view is not None else None), \
-                        F_.shared_parameters(batch_size if (ndim == 4 and common_parameters is None) else 1):
+                        F_.shared_parameters(batch_size if share else 1):
                     return processors[node_type](*inputs, **parameters, **common_i)
 
             if pending_sources is not None:

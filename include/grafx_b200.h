@@ -58,18 +58,22 @@ GFX_API size_t gfx_biquad_cascade_workspace_bytes(int batch, int c_sig, int c_fi
 GFX_API int gfx_biquad_cascade_f32(const float* x, float* y, const float* Bs, const float* As, int batch,
                            int c_sig, int c_filt, int K, long long L, void* workspace,
                            size_t workspace_bytes, void* stream);
-/* The same cascade as the FIRST render order of render_grafx (render/graph.py:63-75, render/core.py:6-33: upstream
- * copies the sources into the signal buffer, then the first processor reads that copy back).  The signal is read from
- * the caller's sources  src [src_outer, src_inner, c_sig, L]  (4-D input_signals: renders x source nodes); item b of
- * the launch (b < src_outer * src_inner, node-major like the signal buffer: b = node * src_outer + render) takes
- * source item (b % src_outer) * src_inner + b / src_outer.  Every input row is ALSO written to  xcopy [items, c_sig, L]
- * -- the source slice of the signal buffer -- from the tile the kernel staged anyway, so the separate copy pass
- * (gfx_node_copy_f32: one more read of every source) is not needed.  Requires c_sig == max(c_sig, c_filt).
- * Bs, As [items, c_filt, K, 3] and y [items, c_sig, L] as above; workspace as gfx_biquad_cascade_workspace_bytes
- * (batch = items, elem_size 4). */
-GFX_API int gfx_biquad_cascade_src_f32(const float* src, float* xcopy, float* y, const float* Bs, const float* As,
-                               int src_outer, int src_inner, int c_sig, int c_filt, int K, long long L,
-                               void* workspace, size_t workspace_bytes, void* stream);
+/* The cascade with the two options render_grafx's batched (4-D) sources call for (render/graph.py:63-75, 132-147;
+ * render/core.py:6-33); with xcopy == NULL, src_outer == src_inner == 0 and coef_repeat == 1 it is gfx_biquad_cascade_f32.
+ *  - coef_repeat > 1: runs of coef_repeat consecutive batch items share ONE coefficient row -- Bs, As are
+ *    [batch / coef_repeat, c_filt, K, 3] (upstream expands every node's parameters over the batch of renders and
+ *    designs / filters each copy; here the expansion never exists in memory).
+ *  - xcopy != NULL (the FIRST render order: upstream copies the sources into the signal buffer, then the first processor
+ *    reads that copy back): the signal is read from the caller's sources  x [src_outer, src_inner, c_sig, L]  (renders x
+ *    source nodes, src_outer * src_inner == batch); item b of the launch (node-major like the signal buffer:
+ *    b = node * src_outer + render) takes source item (b % src_outer) * src_inner + b / src_outer, and every input row is
+ *    ALSO written to  xcopy [batch, c_sig, L]  -- the source slice of the signal buffer -- from the tile the kernel staged
+ *    anyway, so the separate copy pass (gfx_node_copy_f32: one more read of every source) is not needed.  Requires
+ *    c_sig == max(c_sig, c_filt).
+ * y [batch, max(c_sig, c_filt), L]; workspace as gfx_biquad_cascade_workspace_bytes (elem_size 4). */
+GFX_API int gfx_biquad_cascade_ex_f32(const float* x, float* xcopy, float* y, const float* Bs, const float* As, int batch,
+                              int c_sig, int c_filt, int K, long long L, int src_outer, int src_inner, int coef_repeat,
+                              void* workspace, size_t workspace_bytes, void* stream);
 /* float64 variant: the reference's only known-answer test runs in double
  * (tests/processors/test_filter.py:215-233). */
 GFX_API int gfx_biquad_cascade_f64(const double* x, double* y, const double* Bs, const double* As, int batch,
@@ -271,6 +275,12 @@ GFX_API int gfx_dynamics_set_ballistics_mode(int mode);
 GFX_API int gfx_dynamics_f32(const float* x, float* y, int batch, int channels, long long L,
                              const gfx_dynamics_stage* stages, int n_stages, int iir_len,
                              void* workspace, size_t workspace_bytes, void* stream);
+/* The same with parameter rows shared by runs of param_repeat consecutive batch items (render_grafx's 4-D sources,
+ * render/graph.py:132-147: upstream expands every node's parameters over the batch of renders): the parameter tensors of
+ * every stage are [batch / param_repeat, ...]; hist_pre / hist_post stay [batch, L].  param_repeat == 1 is gfx_dynamics_f32. */
+GFX_API int gfx_dynamics_rep_f32(const float* x, float* y, int batch, int channels, long long L,
+                                 const gfx_dynamics_stage* stages, int n_stages, int iir_len, int param_repeat,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stand-alone envelope smoothers and followers on the same kernel.
  * Replaces: TruncatedOnePoleIIRFilter.forward (processors/core/envelope.py:34-60), Ballistics.forward

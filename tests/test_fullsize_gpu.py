@@ -528,7 +528,7 @@ def test_first_order_source_fold_declined_falls_back_to_the_copy():
     assert torch.equal(buf, buf_r) and torch.equal(out, out_r)
 
 
-def test_cascade_src_abi_rejects_bad_arguments():
+def test_cascade_ex_abi_rejects_bad_arguments():
     from grafx_b200 import _cabi
 
     L_ = _cabi.lib()
@@ -536,10 +536,45 @@ def test_cascade_src_abi_rejects_bad_arguments():
     y = torch.empty(6, 2, 64, device="cuda")
     c = torch.randn(6, 2, 1, 3, device="cuda")
     ws = torch.empty(1 << 16, dtype=torch.uint8, device="cuda")
-    # c_sig (1) < c_filt (2): one output row per input row is required
-    code = L_.gfx_biquad_cascade_src_f32(x.data_ptr(), y.data_ptr(), y.data_ptr(), c.data_ptr(), c.data_ptr(), 2, 3, 1, 2, 1, 64,
-                                         ws.data_ptr(), ws.numel(), 0)
-    assert code != 0
-    code = L_.gfx_biquad_cascade_src_f32(x.data_ptr(), None, y.data_ptr(), c.data_ptr(), c.data_ptr(), 2, 3, 1, 1, 1, 64,
-                                         ws.data_ptr(), ws.numel(), 0)
-    assert code != 0
+    args = lambda xcopy, c_filt, so, si, rep: (x.data_ptr(), xcopy, y.data_ptr(), c.data_ptr(), c.data_ptr(), 6, 1, c_filt, 1, 64,  # noqa: E731
+                                               so, si, rep, ws.data_ptr(), ws.numel(), 0)
+    assert L_.gfx_biquad_cascade_ex_f32(*args(y.data_ptr(), 2, 2, 3, 1)) != 0   # source form with c_sig (1) < c_filt (2)
+    assert L_.gfx_biquad_cascade_ex_f32(*args(None, 1, 2, 3, 1)) != 0           # source mapping without a copy target
+    assert L_.gfx_biquad_cascade_ex_f32(*args(y.data_ptr(), 1, 2, 2, 1)) != 0   # src_outer * src_inner != batch
+    assert L_.gfx_biquad_cascade_ex_f32(*args(None, 1, 0, 0, 4)) != 0           # batch not a multiple of coef_repeat
+    assert L_.gfx_biquad_cascade_ex_f32(*args(None, 1, 0, 0, 0)) != 0
+    st = (_cabi.DynamicsStage * 1)()
+    assert L_.gfx_dynamics_rep_f32(x.data_ptr(), y.data_ptr(), 6, 1, 64, st, 1, 16, 4, ws.data_ptr(), ws.numel(), 0) != 0  # 6 % 4
+
+
+@pytest.mark.parametrize("batch,L", [(3, 20000), (2, 4099), (1, 5000)])
+def test_render_parameter_rows_by_repeat_match_the_expansion(batch, L):
+    """4-D sources: processors that accept it get the per-node parameter rows UN-expanded (`accepts_parameter_repeat`): the
+    cascade and dynamics kernels share a coefficient / parameter row over each run of B batch items (gfx_biquad_cascade_ex_f32,
+    gfx_dynamics_rep_f32; only their tables kernels know), the reverb synthesises each response once.  Output and the whole
+    signal buffer must be bit-identical to the expansion upstream makes (render/graph.py:132-147), here forced by
+    switching the offer off on every module."""
+    import grafx_b200.processors as P
+    from grafx_b200.render import mixing_console_plan, render_grafx
+
+    torch.manual_seed(79 + batch)
+    T = 4
+    x = torch.randn(batch, T, 2, L, device="cuda")
+    procs = {"eq": P.ParametricEqualizer(num_filters=3, processor_channel="midside", backend="lfilter").cuda(),
+             "lp": P.LowPassFilter(backend="lfilter").cuda(),
+             "compressor": P.Compressor(energy_smoother="ballistics", gain_smoother="iir").cuda(),
+             "gate": P.NoiseGate().cuda(),
+             "reverb": P.STFTMaskedNoiseReverb(ir_len=20000).cuda()}
+    prm = {t: {k: 0.5 * torch.randn(T, *((v,) if isinstance(v, int) else v), device="cuda") for k, v in p.parameter_size().items()}
+           for t, p in procs.items()}
+    rd = mixing_console_plan(T, ["eq", "lp", "compressor", "gate", "reverb"])
+    out_r, _, buf_r = render_grafx(procs, x, prm, rd)
+    try:
+        for p in procs.values():
+            p.accepts_parameter_repeat = lambda: False
+        out_e, _, buf_e = render_grafx(procs, x, prm, rd)
+    finally:
+        for p in procs.values():
+            del p.accepts_parameter_repeat
+    assert torch.equal(out_r, out_e)
+    assert torch.equal(buf_r, buf_e)
