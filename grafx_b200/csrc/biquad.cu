@@ -45,7 +45,7 @@ struct CascadeParams {
     unsigned long long* xstate;  // packed-kernel variant: [rows][K][2] {value, tag} words
     const double* xtables;       // packed-kernel variant: [coef rows][K][X2_TAB][4] doubles
     int aligned;  // 1: x/y rows are 16-byte aligned (vector path)
-    // packed-kernel variant, render_grafx's first render order (gfx_biquad_cascade_src_f32): the signal is read from
+    // packed-kernel variant, render_grafx's first render order (gfx_biquad_cascade_ex_f32 with xcopy): the signal is read from
     // the caller's [src_outer, src_inner, c_sig, L] sources (item b of this launch = source item
     // (b % src_outer) * src_inner + b / src_outer: the node-major order of the signal buffer) and every staged tile is
     // also stored to xcopy [rows, L] -- the source slice of the signal buffer -- so no separate copy pass reads it again

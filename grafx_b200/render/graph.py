@@ -216,7 +216,7 @@ def render_grafx(processors: Mapping, input_signals: torch.Tensor, per_type_para
 def _first_order_folds(processors, render_data, num_sources) -> bool:
     """True when the first render order is ONE processor call on exactly the source slice and that processor starts
     with the biquad cascade on its input (`folds_source_read`): the cascade kernel then reads the caller's sources and
-    writes the buffer's source slice on the way (gfx_biquad_cascade_src_f32) instead of a separate copy pass."""
+    writes the buffer's source slice on the way (gfx_biquad_cascade_ex_f32) instead of a separate copy pass."""
     if int(render_data.max_order) < 1:
         return False
     it = render_data.iter_list[1]

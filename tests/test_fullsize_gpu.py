@@ -453,7 +453,7 @@ def test_new_entry_points_empty_batch_and_argument_errors():
 @pytest.mark.parametrize("batch", [None, 1, 3])
 def test_first_order_source_fold_matches_the_copy_path(batch, L):
     """render_grafx, first render order = a biquad-cascade processor on exactly the source slice: the cascade kernel reads
-    the caller's sources and fills the buffer's source slice on the way (gfx_biquad_cascade_src_f32) instead of a separate
+    the caller's sources and fills the buffer's source slice on the way (gfx_biquad_cascade_ex_f32) instead of a separate
     copy pass.  Output, intermediates and the WHOLE signal buffer must be bit-identical to the copy path (the same kernel
     on the same values), for full tiles, ragged tails and rows that are not 16-byte aligned, 3-D and 4-D sources."""
     import grafx_b200.processors as P

@@ -22,6 +22,6 @@ python tools/launch_agg.py gpurun_out/${R}_launches_bench_default.csv 1 2>/dev/n
 # memcheck over the tests of the kernels added last (packed multiply-accumulate, source-reading cascade); bounded
 if [ "$2" = "memcheck" ]; then
   timeout 110 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_fullsize_gpu.py tests/test_parity_gpu.py -m gpu -x -q \
-    -k "source_fold or cascade_src or (long_filter_partition and (20000 or 16385 or 60000))" > gpurun_out/${R}_memcheck2.log 2>&1
+    -k "source_fold or cascade_ex or parameter_rows or (long_filter_partition and (20000 or 16385 or 60000))" > gpurun_out/${R}_memcheck2.log 2>&1
   echo "memcheck rc=$?"; tail -4 gpurun_out/${R}_memcheck2.log
 fi
